@@ -1,0 +1,197 @@
+// ShuffleMixer feature-mixing layers (shufflemixer.py:23-132) as fused per-pixel kernels.
+// The reference runs each SMLayer as ~30 small ops (two `rearrange` copies + 5 elementwise/reduce
+// kernels per hand-rolled LayerNorm, chunk/cat, two 1x1 convs, a channel-shuffle copy, a depthwise
+// conv); with C in {8,16} a whole pixel fits in registers, so each half of an SMLayer is ONE kernel
+// that reads C planes and writes C planes (bandwidth bound: 8*C bytes per pixel).
+#include "common.cuh"
+
+namespace esm {
+
+template <int C>
+struct MlpSmem {
+  float ln_w[C];
+  float fc0_w[C * (C / 2)];  // [hidden=C][C/2]
+  float fc0_b[C];
+  float fc2_w[(C / 2) * C];  // [C/2][hidden=C]
+  float fc2_b[C / 2];
+};
+
+template <int C>
+__device__ __forceinline__ void load_mlp(MlpSmem<C>& s, const esm_mixer_mlp_t& m, int tid, int nt) {
+  for (int i = tid; i < C; i += nt) {
+    s.ln_w[i] = m.ln_w[i];
+    s.fc0_b[i] = m.fc0_b[i];
+  }
+  for (int i = tid; i < C * (C / 2); i += nt) {
+    s.fc0_w[i] = m.fc0_w[i];
+    s.fc2_w[i] = m.fc2_w[i];
+  }
+  for (int i = tid; i < C / 2; i += nt) s.fc2_b[i] = m.fc2_b[i];
+}
+
+// u = shuffle8(cat(MLP(LN(t)[:C/2]), LN(t)[C/2:])) + t   (t in registers, result written back into t)
+template <int C>
+__device__ __forceinline__ void ln_mlp_shuffle_residual(float (&t)[C], const MlpSmem<C>& s) {
+  constexpr int HALF = C / 2;
+  float mu = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) mu += t[c];
+  mu = mu / (float)C;
+  float var = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float dlt = t[c] - mu;
+    var = fmaf(dlt, dlt, var);
+  }
+  var = var / (float)C;
+  const float den = sqrtf(var + 1e-5f);  // shufflemixer.py:60-62: (x - mu) / sqrt(sigma + 1e-5) * weight
+  float y[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) y[c] = (t[c] - mu) / den * s.ln_w[c];
+  float hdn[C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    float a = s.fc0_b[j];
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) a = fmaf(s.fc0_w[j * HALF + i], y[i], a);
+    hdn[j] = silu(a);
+  }
+  float u[C];
+#pragma unroll
+  for (int i = 0; i < HALF; ++i) {
+    float a = s.fc2_b[i];
+#pragma unroll
+    for (int j = 0; j < C; ++j) a = fmaf(s.fc2_w[i * C + j], hdn[j], a);
+    u[i] = a;
+  }
+#pragma unroll
+  for (int i = HALF; i < C; ++i) u[i] = y[i];
+  // 'b (g d) h w -> b (d g) h w', g = 8: input channel g*(C/8)+d goes to output channel d*8+g
+  constexpr int DD = C / 8;
+  float o[C];
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+#pragma unroll
+    for (int d = 0; d < DD; ++d) o[d * 8 + g] = u[g * DD + d];
+#pragma unroll
+  for (int c = 0; c < C; ++c) t[c] = o[c] + t[c];
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) sm_pointwise_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                           long long plane, long long total, esm_mixer_mlp_t m,
+                                                           const float* __restrict__ extra) {
+  __shared__ MlpSmem<C> s;
+  load_mlp<C>(s, m, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long b = i / plane;
+  const long long p = i - b * plane;
+  const long long base = b * C * plane + p;
+  float t[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) t[c] = __ldg(x + base + c * plane);
+  ln_mlp_shuffle_residual<C>(t, s);
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float v = t[c];
+    if (extra) v += __ldg(extra + base + c * plane);
+    y[base + c * plane] = v;
+  }
+}
+
+constexpr int SP_TX = 32, SP_TY = 8;
+
+template <int C>
+__global__ void __launch_bounds__(SP_TX * SP_TY) sm_spatial_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                   int H, int W, const float* __restrict__ dw_w,
+                                                                   const float* __restrict__ dw_b, int k,
+                                                                   esm_mixer_mlp_t m, const float* __restrict__ extra) {
+  extern __shared__ __align__(16) float dyn[];
+  __shared__ MlpSmem<C> s;
+  const int tid = threadIdx.y * SP_TX + threadIdx.x;
+  const int nt = SP_TX * SP_TY;
+  load_mlp<C>(s, m, tid, nt);
+  const int r = k / 2;
+  const int TWp = SP_TX + k - 1, THp = SP_TY + k - 1;
+  float* tile = dyn;                  // [C][THp][TWp]
+  float* wsm = dyn + C * THp * TWp;   // [C][k*k]
+  float* bsm = wsm + C * k * k;       // [C]
+  for (int i = tid; i < C * k * k; i += nt) wsm[i] = dw_w[i];
+  for (int i = tid; i < C; i += nt) bsm[i] = dw_b[i];
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * SP_TX - r, y0 = blockIdx.y * SP_TY - r;
+  const long long plane = (long long)H * W;
+  const float* xb = x + (long long)b * C * plane;
+  for (int i = tid; i < C * THp * TWp; i += nt) {
+    const int c = i / (THp * TWp);
+    const int rem = i - c * THp * TWp;
+    const int ty = rem / TWp, tx = rem - ty * TWp;
+    const int gy = y0 + ty, gx = x0 + tx;
+    tile[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(xb + c * plane + (long long)gy * W + gx) : 0.f;
+  }
+  __syncthreads();
+  const int px = blockIdx.x * SP_TX + threadIdx.x, py = blockIdx.y * SP_TY + threadIdx.y;
+  if (px >= W || py >= H) return;
+  float t[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float a = bsm[c];
+    const float* tp = tile + (c * THp + threadIdx.y) * TWp + threadIdx.x;
+    const float* wp = wsm + c * k * k;
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx) a = fmaf(wp[ky * k + kx], tp[ky * TWp + kx], a);
+    t[c] = a;
+  }
+  ln_mlp_shuffle_residual<C>(t, s);
+  const long long base = (long long)b * C * plane + (long long)py * W + px;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float v = t[c];
+    if (extra) v += __ldg(extra + base + c * plane);
+    y[base + c * plane] = v;
+  }
+}
+
+static int check_mlp(const esm_mixer_mlp_t* m, int C) {
+  ESM_REQUIRE(m && m->ln_w && m->fc0_w && m->fc0_b && m->fc2_w && m->fc2_b, "mixer: null MLP parameter");
+  ESM_REQUIRE(m->hidden == C, "mixer: hidden (%d) must equal C (%d) (mlp_ratio 2 on C/2)", m->hidden, C);
+  return ESM_OK;
+}
+
+}  // namespace esm
+
+using namespace esm;
+
+extern "C" int esm_sm_pointwise_f32(const float* x, float* y, int B, int C, int H, int W, const esm_mixer_mlp_t* mlp,
+                                    const float* extra_residual, void* stream) {
+  ESM_REQUIRE(x && y && B > 0 && H > 0 && W > 0, "sm_pointwise: null pointer or empty shape");
+  ESM_REQUIRE(C == 8 || C == 16, "sm_pointwise: C must be 8 or 16 (got %d)", C);
+  if (int e = check_mlp(mlp, C)) return e;
+  const long long plane = (long long)H * W, total = plane * B;
+  const unsigned grid = (unsigned)ceil_div_ll(total, 256);
+  if (C == 16)
+    sm_pointwise_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, plane, total, *mlp, extra_residual);
+  else
+    sm_pointwise_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, plane, total, *mlp, extra_residual);
+  return check_launch("sm_pointwise");
+}
+
+extern "C" int esm_sm_spatial_f32(const float* x, float* y, int B, int C, int H, int W, const float* dw_w,
+                                  const float* dw_b, int k, const esm_mixer_mlp_t* mlp, const float* extra_residual,
+                                  void* stream) {
+  ESM_REQUIRE(x && y && dw_w && dw_b && B > 0 && H > 0 && W > 0, "sm_spatial: null pointer or empty shape");
+  ESM_REQUIRE(C == 8 || C == 16, "sm_spatial: C must be 8 or 16 (got %d)", C);
+  ESM_REQUIRE(k >= 1 && k <= 9 && (k & 1), "sm_spatial: depthwise kernel must be odd and <= 9 (got %d)", k);
+  ESM_REQUIRE(x != y, "sm_spatial: in-place not supported (halo reads)");
+  if (int e = check_mlp(mlp, C)) return e;
+  ESM_REQUIRE(B <= 65535 && ceil_div(H, SP_TY) <= 65535, "sm_spatial: grid too large");
+  dim3 grid((unsigned)ceil_div(W, SP_TX), (unsigned)ceil_div(H, SP_TY), (unsigned)B), block(SP_TX, SP_TY);
+  const size_t smem = ((size_t)C * (SP_TY + k - 1) * (SP_TX + k - 1) + (size_t)C * k * k + C) * sizeof(float);
+  if (C == 16)
+    sm_spatial_kernel<16><<<grid, block, smem, (cudaStream_t)stream>>>(x, y, H, W, dw_w, dw_b, k, *mlp, extra_residual);
+  else
+    sm_spatial_kernel<8><<<grid, block, smem, (cudaStream_t)stream>>>(x, y, H, W, dw_w, dw_b, k, *mlp, extra_residual);
+  return check_launch("sm_spatial");
+}

@@ -1,0 +1,120 @@
+// Disparity regression and final assembly (bandwidth-bound, one pass over the cost volume).
+//   esm_regression_top2_f32       <- regression_topk(k=2) (submodule.py:218-225; ESMStereo.py:719-721)
+//   esm_disparity_regression_f32  <- disparity_regression (submodule.py:211-216)  [no softmax]
+//   esm_bilinear_add_f32          <- F.interpolate(bilinear, align_corners=False) + residual, * scale
+//                                    (ESMStereo.py:307,316,497,507,745)
+// The reference sorts all D costs per pixel, gathers twice and materialises a `disp_samples`
+// tensor; here each thread streams its pixel's D costs once, keeping a running top-2 in registers.
+#include "common.cuh"
+
+namespace esm {
+
+__global__ void __launch_bounds__(128) regression_top2_kernel(const float* __restrict__ cost, float* __restrict__ pred,
+                                                              int* __restrict__ idx, int D, long long plane,
+                                                              long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long b = i / plane;
+  const long long p = i - b * plane;
+  const float* c = cost + b * D * plane + p;
+  // descending stable order: strict '>' keeps the lower index first on ties
+  float v1 = -INFINITY, v2 = -INFINITY;
+  int i1 = 0, i2 = 0;
+  bool has1 = false, has2 = false;
+  for (int d = 0; d < D; ++d) {
+    const float v = __ldg(c + (long long)d * plane);
+    if (!has1 || v > v1) {
+      v2 = v1; i2 = i1; has2 = has1;
+      v1 = v; i1 = d; has1 = true;
+    } else if (!has2 || v > v2) {
+      v2 = v; i2 = d; has2 = true;
+    }
+  }
+  float out;
+  if (D >= 2) {
+    // softmax over (v1, v2) as torch does it: exp(x - max) / sum
+    const float e2 = expf(v2 - v1);
+    const float s = 1.0f + e2;
+    const float p1 = 1.0f / s, p2 = e2 / s;
+    out = __fadd_rn(__fmul_rn((float)i1, p1), __fmul_rn((float)i2, p2));
+  } else {
+    out = (float)i1;
+  }
+  pred[i] = out;
+  if (idx) {
+    idx[(b * 2 + 0) * plane + p] = i1;
+    idx[(b * 2 + 1) * plane + p] = (D >= 2) ? i2 : i1;
+  }
+}
+
+__global__ void __launch_bounds__(128) disparity_regression_kernel(const float* __restrict__ cost,
+                                                                   float* __restrict__ pred, int D, long long plane,
+                                                                   long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long b = i / plane;
+  const long long p = i - b * plane;
+  const float* c = cost + b * D * plane + p;
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) s = __fadd_rn(s, __fmul_rn(__ldg(c + (long long)d * plane), (float)d));
+  pred[i] = s;
+}
+
+// torch upsample_bilinear2d, align_corners=False, scale_factor = factor (src = (dst+0.5)/f - 0.5, clamped at 0)
+__global__ void __launch_bounds__(256) bilinear_add_kernel(const float* __restrict__ prev, const float* __restrict__ res,
+                                                           float* __restrict__ out, int h, int w, int f, float rscale,
+                                                           float out_scale, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int W = w * f, H = h * f;
+  const int x = (int)(i % W);
+  const long long t = i / W;
+  const int y = (int)(t % H);
+  const long long b = t / H;
+  float sy = ((float)y + 0.5f) * rscale - 0.5f;
+  float sx = ((float)x + 0.5f) * rscale - 0.5f;
+  sy = sy < 0.f ? 0.f : sy;
+  sx = sx < 0.f ? 0.f : sx;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + ((y0 < h - 1) ? 1 : 0), x1 = x0 + ((x0 < w - 1) ? 1 : 0);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float* pb = prev + b * (long long)h * w;
+  const float v00 = __ldg(pb + (long long)y0 * w + x0), v01 = __ldg(pb + (long long)y0 * w + x1);
+  const float v10 = __ldg(pb + (long long)y1 * w + x0), v11 = __ldg(pb + (long long)y1 * w + x1);
+  const float up = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+  out[i] = (up + __ldg(res + i)) * out_scale;
+}
+
+}  // namespace esm
+
+using namespace esm;
+
+extern "C" int esm_regression_top2_f32(const float* cost, float* pred, int* idx, int B, int D, int H, int W,
+                                       void* stream) {
+  ESM_REQUIRE(cost && pred, "regression_top2: null pointer");
+  ESM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "regression_top2: empty shape");
+  const long long plane = (long long)H * W, total = plane * B;
+  regression_top2_kernel<<<(unsigned)ceil_div_ll(total, 128), 128, 0, (cudaStream_t)stream>>>(cost, pred, idx, D, plane,
+                                                                                              total);
+  return check_launch("regression_top2");
+}
+
+extern "C" int esm_disparity_regression_f32(const float* cost, float* pred, int B, int D, int H, int W, void* stream) {
+  ESM_REQUIRE(cost && pred, "disparity_regression: null pointer");
+  ESM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "disparity_regression: empty shape");
+  const long long plane = (long long)H * W, total = plane * B;
+  disparity_regression_kernel<<<(unsigned)ceil_div_ll(total, 128), 128, 0, (cudaStream_t)stream>>>(cost, pred, D, plane,
+                                                                                                   total);
+  return check_launch("disparity_regression");
+}
+
+extern "C" int esm_bilinear_add_f32(const float* prev, const float* residual, float* out, int B, int h, int w,
+                                    int factor, float out_scale, void* stream) {
+  ESM_REQUIRE(prev && residual && out, "bilinear_add: null pointer");
+  ESM_REQUIRE(B > 0 && h > 0 && w > 0 && factor >= 1, "bilinear_add: empty shape");
+  const long long total = (long long)B * h * factor * w * factor;
+  bilinear_add_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      prev, residual, out, h, w, factor, 1.0f / (float)factor, out_scale, total);
+  return check_launch("bilinear_add");
+}

@@ -1,0 +1,198 @@
+// Cost-volume builders (HBM-write-bound streaming kernels).
+//   esm_gwc_volume_f32        <- build_gwc_volume + groupwise_correlation (submodule.py:143-161)
+//   esm_norm_corr_volume_f32  <- build_norm_correlation_volume + norm_correlation (submodule.py:187-200)
+// The reference builds the volume with a Python loop over disparities (memset + D x {mul, mean,
+// strided copy}); here one launch writes every output element exactly once, zeros included.
+//
+// Algorithmic bytes: 4*(2*C*h*w + G*D*h*w) per pair; the kernel is bound by the
+// G*D*h*w fp32 stores.  Thread layout: a thread owns 4 consecutive x of one row and GPT groups,
+// keeps its left-feature values in registers and slides a register window over the right row as d
+// grows (one new right value per channel per disparity), so every store is a coalesced STG.128 and
+// L/R are read from L1/L2 once per thread.
+#include "common.cuh"
+
+namespace esm {
+
+// GPT = groups per thread, CPG = channels per group (template for register residency)
+template <int GPT, int CPG>
+__global__ void __launch_bounds__(256) gwc_volume_kernel(const float* __restrict__ L, const float* __restrict__ R,
+                                                         float* __restrict__ V, int C, int H, int W, int D, int G,
+                                                         int xg_per_row, long long positions) {
+  const int lane_pos = blockIdx.x * 32 + (threadIdx.x & 31);  // (y, x-group) position
+  const int gset = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.z;
+  const int g0 = gset * GPT;
+  if (lane_pos >= positions || g0 >= G) return;
+  const int y = lane_pos / xg_per_row;
+  const int x0 = (lane_pos - y * xg_per_row) * 4;
+  const long long plane = (long long)H * W;
+  const float* Lb = L + ((long long)b * C + (long long)g0 * CPG) * plane + (long long)y * W;
+  const float* Rb = R + ((long long)b * C + (long long)g0 * CPG) * plane + (long long)y * W;
+
+  float l[GPT * CPG][4];
+  float r[GPT * CPG][4];  // r[.][i] = R[x0 + i - d]
+#pragma unroll
+  for (int c = 0; c < GPT * CPG; ++c) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int x = x0 + i;
+      const bool in = x < W;
+      l[c][i] = in ? __ldg(Lb + c * plane + x) : 0.f;
+      r[c][i] = in ? __ldg(Rb + c * plane + x) : 0.f;
+    }
+  }
+  const bool vec = ((W & 3) == 0) && (x0 + 4 <= W);
+  float* Vb = V + (((long long)b * G + g0) * D) * plane + (long long)y * W + x0;
+  const long long gstride = (long long)D * plane;
+  for (int d = 0; d < D; ++d) {
+#pragma unroll
+    for (int g = 0; g < GPT; ++g) {
+      if (g0 + g >= G) break;
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPG; ++k) s = __fadd_rn(s, __fmul_rn(l[g * CPG + k][i], r[g * CPG + k][i]));
+        o[i] = (x0 + i >= d) ? s / (float)CPG : 0.f;  // zero triangle x < d, submodule.py:153,156
+      }
+      float* dst = Vb + g * gstride + (long long)d * plane;
+      if (vec) {
+        __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (x0 + i < W) dst[i] = o[i];
+      }
+    }
+    // slide the right-image window by one column: r[.][i] <- R[x0 + i - (d+1)]
+    const int xn = x0 - (d + 1);
+#pragma unroll
+    for (int c = 0; c < GPT * CPG; ++c) {
+      r[c][3] = r[c][2];
+      r[c][2] = r[c][1];
+      r[c][1] = r[c][0];
+      r[c][0] = (xn >= 0 && xn < W) ? __ldg(Rb + c * plane + xn) : 0.f;
+    }
+  }
+}
+
+// generic (any channels-per-group) fallback: one thread per output element group of 4 x
+__global__ void __launch_bounds__(256) gwc_volume_generic_kernel(const float* __restrict__ L, const float* __restrict__ R,
+                                                                 float* __restrict__ V, int C, int H, int W, int D, int G,
+                                                                 long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long t = i;
+  const int x = t % W;
+  t /= W;
+  const int y = t % H;
+  t /= H;
+  const int d = t % D;
+  t /= D;
+  const int g = t % G;
+  const int b = (int)(t / G);
+  const int cpg = C / G;
+  float s = 0.f;
+  if (x >= d) {
+    const long long plane = (long long)H * W;
+    const float* Lp = L + ((long long)b * C + (long long)g * cpg) * plane + (long long)y * W + x;
+    const float* Rp = R + ((long long)b * C + (long long)g * cpg) * plane + (long long)y * W + x - d;
+    for (int k = 0; k < cpg; ++k) s = __fadd_rn(s, __fmul_rn(__ldg(Lp + k * plane), __ldg(Rp + k * plane)));
+    s = s / (float)cpg;
+  }
+  V[i] = s;
+}
+
+// x / (||x||_2 + 1e-5) over channels, per pixel (norm_correlation, submodule.py:187-189)
+__global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restrict__ X, float* __restrict__ Y, int C,
+                                                           long long plane, long long total_pixels) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_pixels) return;
+  const long long b = i / plane;
+  const long long p = i - b * plane;
+  const float* x = X + b * C * plane + p;
+  float* y = Y + b * C * plane + p;
+  float ss = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float v = __ldg(x + c * plane);
+    ss = fmaf(v, v, ss);
+  }
+  const float den = sqrtf(ss) + 1e-5f;
+  for (int c = 0; c < C; ++c) y[c * plane] = __ldg(x + c * plane) / den;
+}
+
+// V[b,0,d,y,x] = mean_c Ln[c,y,x]*Rn[c,y,x-d]   (x >= d, else 0)
+template <int DT>  // disparities per thread
+__global__ void __launch_bounds__(128) norm_corr_kernel(const float* __restrict__ Ln, const float* __restrict__ Rn,
+                                                        float* __restrict__ V, int C, int H, int W, int D) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int d0 = (blockIdx.z % ceil_div_dev(D, DT)) * DT;
+  const int b = blockIdx.z / ceil_div_dev(D, DT);
+  if (x >= W) return;
+  const long long plane = (long long)H * W;
+  const float* lp = Ln + (long long)b * C * plane + (long long)y * W + x;
+  const float* rp = Rn + (long long)b * C * plane + (long long)y * W;
+  float acc[DT];
+#pragma unroll
+  for (int j = 0; j < DT; ++j) acc[j] = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float l = __ldg(lp + c * plane);
+#pragma unroll
+    for (int j = 0; j < DT; ++j) {
+      const int xr = x - (d0 + j);
+      if (xr >= 0) acc[j] = __fadd_rn(acc[j], __fmul_rn(l, __ldg(rp + c * plane + xr)));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < DT; ++j) {
+    const int d = d0 + j;
+    if (d < D) V[((long long)b * D + d) * plane + (long long)y * W + x] = (x >= d) ? acc[j] / (float)C : 0.f;
+  }
+}
+
+}  // namespace esm
+
+using namespace esm;
+
+extern "C" int esm_gwc_volume_f32(const float* L, const float* R, float* V, int B, int C, int H, int W, int D, int G,
+                                  void* stream) {
+  ESM_REQUIRE(L && R && V, "gwc_volume: null pointer");
+  ESM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0 && G > 0, "gwc_volume: empty shape");
+  ESM_REQUIRE(C % G == 0, "gwc_volume: C (%d) not divisible by groups (%d)", C, G);  // submodule.py:145
+  ESM_REQUIRE(B <= 65535, "gwc_volume: batch too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cpg = C / G;
+  if (cpg == 2) {
+    constexpr int GPT = 2;
+    const int xg = ceil_div(W, 4);
+    const long long positions = (long long)H * xg;
+    const int gsets = ceil_div(G, GPT);
+    const int warps = 8;
+    dim3 grid((unsigned)ceil_div_ll(positions, 32), (unsigned)ceil_div(gsets, warps), (unsigned)B);
+    gwc_volume_kernel<GPT, 2><<<grid, warps * 32, 0, st>>>(L, R, V, C, H, W, D, G, xg, positions);
+  } else {
+    const long long total = (long long)B * G * D * H * W;
+    gwc_volume_generic_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(L, R, V, C, H, W, D, G, total);
+  }
+  return check_launch("gwc_volume");
+}
+
+extern "C" int esm_norm_corr_volume_f32(const float* L, const float* R, float* V, float* ws, int B, int C, int H, int W,
+                                        int D, void* stream) {
+  ESM_REQUIRE(L && R && V && ws, "norm_corr_volume: null pointer");
+  ESM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "norm_corr_volume: empty shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long plane = (long long)H * W;
+  const long long px = plane * B;
+  float* Ln = ws;
+  float* Rn = ws + px * C;
+  l2_normalize_kernel<<<(unsigned)ceil_div_ll(px, 256), 256, 0, st>>>(L, Ln, C, plane, px);
+  l2_normalize_kernel<<<(unsigned)ceil_div_ll(px, 256), 256, 0, st>>>(R, Rn, C, plane, px);
+  constexpr int DT = 4;
+  ESM_REQUIRE((long long)B * ceil_div(D, DT) <= 65535 && H <= 65535, "norm_corr_volume: grid too large");
+  dim3 grid((unsigned)ceil_div(W, 128), (unsigned)H, (unsigned)(B * ceil_div(D, DT)));
+  norm_corr_kernel<DT><<<grid, 128, 0, st>>>(Ln, Rn, V, C, H, W, D);
+  return check_launch("norm_corr_volume");
+}

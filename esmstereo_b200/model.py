@@ -1,0 +1,230 @@
+"""ESMStereo model family behind the reference's own Python API (drop-in boundary):
+
+    __models__[name](maxdisp, gwc, norm_correlation, backbone, cv_scale[, device])
+    ESMStereo(left, right, train_status) -> [disp [B,H,W]]          (models/ESMStereo.py:512,638)
+    ESMStereo_trt(left, right)           -> disp [B,H,W]            (models/ESMStereo_trt.py:638,735)
+    ESMStereo_confidence(left, right)    -> (disp, conf) [B,H,W]    (models/ESMStereo_confidence.py:876,974)
+
+Parameter / buffer names are the reference's, so checkpoints load by key (test_kitti.py:57-61) and the
+modules survive nn.DataParallel(...).cuda().eval().  The 2D feature side is PyTorch/cuDNN
+(`feature2d`); from the matching descriptors on -- cost volume, 3D hourglass, regression, ShuffleMixer
+upsampling, confidence head -- every op is a libesm_b200 kernel (`layers`, `ops`).
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import layers as L
+from . import ops
+from .feature2d import FeatUp, Feature, TorchBasicConv, image_stem
+
+_STEM_CH = {4: [(3, 32), (32, 48)], 8: [(3, 32), (32, 48), (48, 64)], 16: [(3, 16), (16, 24), (24, 32), (32, 40)]}
+_DESC_IN = {4: 96, 8: 160, 16: 136}
+_ADD_CH = {4: 16, 8: 8, 16: 4}
+
+
+@contextlib.contextmanager
+def _exact_fp32(enabled: bool):
+    """fp32 mode: keep cuDNN / cuBLAS out of TF32 on the 2D side so the descriptors feeding the
+    cost volume match the CPU reference (hard part 2)."""
+    if not enabled:
+        yield
+        return
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+class _ESMStereoBase(nn.Module):
+    def __init__(self, maxdisp: int, gwc: bool = False, norm_correlation: bool = True, backbone: str = "efficientnet_b2",
+                 cv_scale: int = 4, confidence: bool = False) -> None:
+        super().__init__()
+        self.maxdisp, self.vol_size = maxdisp, cv_scale
+        self.gwc, self.norm_correlation, self.backbone = gwc, norm_correlation, backbone
+        self.exact_fp32 = True      # False: let cuDNN use TF32 on the 2D feature side (fast, not parity-grade)
+        self.fuse_volume = True     # gwc volume generated inside group_stem (never written to HBM)
+        self.capture: Optional[Dict[str, torch.Tensor]] = None  # set to {} to record hot-path stages (tests)
+        if cv_scale not in (4, 8, 16):
+            # the reference hits a misspelt `pirnt(...)` here -> NameError (ESMStereo.py:599)
+            raise NameError("Choose the cost volume resolution: 4, 8, 16")
+        self.feature = Feature(backbone)
+        if cv_scale in (4, 8):
+            self.feature_up = FeatUp(self.feature.chans, cv_scale)
+        for (cin, cout), n in zip(_STEM_CH[cv_scale], (2, 4, 8, 16)):
+            setattr(self, "stem_%d" % n, image_stem(cin, cout))
+        self.conv = TorchBasicConv(_DESC_IN[cv_scale], 64, kernel_size=3, padding=1, stride=1)
+        self.desc = nn.Conv2d(64, 64, kernel_size=1, padding=0, stride=1)
+        if cv_scale == 16:
+            self.conv_f2 = TorchBasicConv(96, 32, kernel_size=3, padding=1, stride=1)
+            self.conv_f0 = TorchBasicConv(16, 24, kernel_size=3, padding=1, stride=1)
+        k3 = dict(deconv=False, is_3d=True, bn=True, gelu=True, kernel_size=3, padding=1, stride=1)
+        if norm_correlation:
+            print("Cost volumes: norm correlation")
+            if cv_scale == 16:
+                self.semantic = nn.Sequential(TorchBasicConv(96, 32, kernel_size=3, stride=1, padding=1),
+                                              nn.Conv2d(32, 8, 3, 1, 1, bias=False))
+            self.corr_stem = L.BasicConv(1, 8, **k3)
+        if gwc:
+            print("Cost volumes: gwc ")
+            if cv_scale == 16:
+                self.semantic = nn.Sequential(TorchBasicConv(96, 64, kernel_size=3, stride=1, padding=1),
+                                              nn.Conv2d(64, 32, 3, 1, 1, bias=False))
+            self.num_groups = 32
+            self.group_stem = L.BasicConv(self.num_groups, 8, **k3)
+        self.agg = L.BasicConv(8, 8, **k3)
+        self.upsample_module = {4: L.upsample4, 8: L.upsample8, 16: L.upsample16}[cv_scale]()
+        if confidence and cv_scale == 16:
+            self.confidence_net = L.LAFNet_ESM(16)
+        self.aggregation_out = L.aggregation(8, _ADD_CH[cv_scale])
+
+    # ------------------------------------------------------------------ 2D side (PyTorch)
+    def _features_2d(self, left: torch.Tensor, right: torch.Tensor):
+        """Returns (features_left list, stems of the left image, match_left, match_right, att).
+        Both images go through the shared layers as one batch (ESMStereo.py:640-697)."""
+        B = left.shape[0]
+        both = torch.cat((left, right), 0)
+        with _exact_fp32(self.exact_fp32):
+            feats = self.feature(both)
+            if self.vol_size in (4, 8):
+                feats = self.feature_up(feats)
+            stems = [self.stem_2(both)]
+            for n in (4, 8, 16):
+                if hasattr(self, "stem_%d" % n):
+                    stems.append(getattr(self, "stem_%d" % n)(stems[-1]))
+            coarse = {4: feats[0], 8: feats[1], 16: feats[3]}[self.vol_size]
+            match = self.desc(self.conv(torch.cat((coarse, stems[-1]), 1)))
+            fl = [f[:B] for f in feats]
+            att = self.semantic(fl[3]) if self.vol_size == 16 else None
+            extra = None
+            if self.vol_size == 16:
+                extra = (self.conv_f2(fl[3]), self.conv_f0(fl[0]))
+        return fl, [s[:B] for s in stems], match[:B].contiguous(), match[B:].contiguous(), att, extra
+
+    # ------------------------------------------------------------------ hot path (libesm_b200)
+    def _hot_path(self, fl, stems, mL, mR, att, extra, want_scales: bool):
+        s, D = self.vol_size, self.maxdisp // self.vol_size
+        if self.norm_correlation:
+            vol = ops.build_norm_correlation_volume(mL, mR, D)
+            vol = self.corr_stem(vol, out_mul=att)  # `corr_stem(volume) * att` for cv16 (:703)
+        if self.gwc:
+            if self.fuse_volume:
+                vol = self.group_stem([mL, mR], gwc_disp=D, in_mul=att)  # group_stem(volume * att) (:711)
+            else:
+                vol = ops.build_gwc_volume(mL, mR, D, self.num_groups)
+                vol = self.group_stem(vol, in_mul=att)
+        stem = vol
+        vol = self.agg(vol)
+        cost = self.aggregation_out(vol)  # [B,1,D,h,w]
+        cost2d = cost[:, 0]
+        if self.capture is not None:
+            self.capture.update(match_left=mL, match_right=mR, stem=stem, agg=vol, cost=cost2d)
+        final = 1.0 if want_scales else 4.0  # every output is *4 regardless of scale (:737-745)
+        if s == 4:
+            init = ops.regression_top2(cost2d)
+            scales = self.upsample_module(fl[1], fl[0], stems[0], init, out_scale=final)
+        elif s == 8:
+            init = ops.disparity_regression(cost2d, D).unsqueeze(1)
+            scales = self.upsample_module(fl[2], fl[1], fl[0], stems[0], init, out_scale=final)
+        else:
+            init = ops.disparity_regression(cost2d, D).unsqueeze(1)
+            f2, f0 = extra
+            scales = self.upsample_module(fl[2], f2, fl[1], f0, init, out_scale=final)
+        if self.capture is not None:
+            self.capture.update(init_pred=init)
+            if s == 4:
+                self.capture["top2_idx"] = ops.regression_top2(cost2d, return_indices=True)[1]
+        return cost2d, init, scales
+
+    def _run(self, left: torch.Tensor, right: torch.Tensor, want_scales: bool, want_conf: bool):
+        if not (left.is_cuda and right.is_cuda):
+            raise RuntimeError("esmstereo_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self.training:
+            raise RuntimeError("esmstereo_b200 implements the inference path only: call model.eval() first")
+        with torch.no_grad():
+            left, right = left.float().contiguous(), right.float().contiguous()
+            fl, stems, mL, mR, att, extra = self._features_2d(left, right)
+            cost, init, scales = self._hot_path(fl, stems, mL, mR, att, extra, want_scales)
+            conf = None
+            if want_conf:
+                conf = self.confidence_net(cost, init, mL, fl[3], fl[1]).squeeze(1)
+            if want_scales:
+                return [t.squeeze(1) * 4 for t in scales], conf
+            return [scales[0].squeeze(1)], conf
+
+
+class ESMStereo(_ESMStereoBase):
+    def __init__(self, maxdisp: int, gwc: bool = False, norm_correlation: bool = True, backbone: str = "efficientnet_b2",
+                 cv_scale: int = 4) -> None:
+        super().__init__(maxdisp, gwc, norm_correlation, backbone, cv_scale)
+
+    def forward(self, left: torch.Tensor, right: torch.Tensor, train_status: bool) -> List[torch.Tensor]:
+        return self._run(left, right, bool(train_status), False)[0]
+
+
+class ESMStereo_trt(_ESMStereoBase):
+    def __init__(self, maxdisp: int, gwc: bool = False, norm_correlation: bool = True, backbone: str = "efficientnet_b2",
+                 cv_scale: int = 4) -> None:
+        super().__init__(maxdisp, gwc, norm_correlation, backbone, cv_scale)
+
+    def forward(self, left: torch.Tensor, right: torch.Tensor) -> torch.Tensor:
+        return self._run(left, right, False, False)[0][0]
+
+
+class ESMStereo_confidence(_ESMStereoBase):
+    def __init__(self, maxdisp: int, gwc: bool = False, norm_correlation: bool = True, backbone: str = "efficientnet_b2",
+                 cv_scale: int = 4, device=torch.device("cuda")) -> None:
+        super().__init__(maxdisp, gwc, norm_correlation, backbone, cv_scale, confidence=True)
+        self.device = device
+
+    def forward(self, left: torch.Tensor, right: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.vol_size != 16:
+            # the reference only assigns conf_out under `if self.vol_size == 16` (:966-974)
+            raise UnboundLocalError("conf_out is only produced for cv_scale == 16 (ESMStereo_confidence.py:966-974)")
+        disp, conf = self._run(left, right, False, True)
+        return disp[0], conf
+
+
+__models__ = {
+    "ESMStereo": ESMStereo,
+    "ESMStereo_trt": ESMStereo_trt,
+    "ESMStereo_confidence": ESMStereo_confidence,
+}
+
+
+class GraphedStereo:
+    """CUDA-graph replay of one model at one input shape (the batch-1 latency path is launch-bound:
+    ~150 kernels of 5-100 us each).  Inputs are copied into static buffers, outputs are views of
+    static buffers that the next `__call__` overwrites.
+
+        g = GraphedStereo(model, (1, 3, 384, 1248));  disp = g(left, right)
+    """
+
+    def __init__(self, model: nn.Module, shape, warmup: int = 3, **fwd_kwargs) -> None:
+        self.model, self.kw = model, fwd_kwargs
+        dev = next(model.parameters()).device
+        self.left = torch.zeros(shape, device=dev)
+        self.right = torch.zeros(shape, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):  # packs weights, sets func attributes, warms cuDNN heuristics
+                self.model(self.left, self.right, **self.kw)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self.model(self.left, self.right, **self.kw)
+
+    def __call__(self, left: torch.Tensor, right: torch.Tensor):
+        self.left.copy_(left, non_blocking=True)
+        self.right.copy_(right, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -1,0 +1,346 @@
+"""Tensor-level operators over the C ABI (include/esm_b200.h).
+
+The function names mirror the reference's operator seams (`models/submodule.py`) so that the
+parity tests read like the reference: `build_gwc_volume`, `build_norm_correlation_volume`,
+`regression_topk`, `disparity_regression`.  Everything here takes CUDA fp32 tensors and launches
+on torch's current stream; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT, EsmConv, EsmMixerMlp, check, lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32):
+        raise TypeError("esmstereo_b200: %s must be a CUDA float32 tensor (no CPU fallback exists)" % name)
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------
+# cost volumes  (submodule.py:143-161, 187-200)
+# ---------------------------------------------------------------------------------------------
+def build_gwc_volume(refimg_fea: torch.Tensor, targetimg_fea: torch.Tensor, maxdisp: int, num_groups: int) -> torch.Tensor:
+    L, R = _dev(refimg_fea, "refimg_fea").contiguous(), _dev(targetimg_fea, "targetimg_fea").contiguous()
+    B, Cc, H, W = L.shape
+    assert Cc % num_groups == 0  # submodule.py:145
+    V = torch.empty(B, num_groups, maxdisp, H, W, device=L.device, dtype=torch.float32)
+    if V.numel():
+        check(lib().esm_gwc_volume_f32(L.data_ptr(), R.data_ptr(), V.data_ptr(), B, Cc, H, W, maxdisp, num_groups,
+                                       _stream()), "gwc_volume")
+    return V
+
+
+def build_norm_correlation_volume(refimg_fea: torch.Tensor, targetimg_fea: torch.Tensor, maxdisp: int) -> torch.Tensor:
+    L, R = _dev(refimg_fea, "refimg_fea").contiguous(), _dev(targetimg_fea, "targetimg_fea").contiguous()
+    B, Cc, H, W = L.shape
+    V = torch.empty(B, 1, maxdisp, H, W, device=L.device, dtype=torch.float32)
+    ws = torch.empty(2 * L.numel(), device=L.device, dtype=torch.float32)
+    if V.numel():
+        check(lib().esm_norm_corr_volume_f32(L.data_ptr(), R.data_ptr(), V.data_ptr(), ws.data_ptr(), B, Cc, H, W,
+                                             maxdisp, _stream()), "norm_corr_volume")
+    return V
+
+
+# ---------------------------------------------------------------------------------------------
+# regression  (submodule.py:211-225)
+# ---------------------------------------------------------------------------------------------
+def regression_top2(cost: torch.Tensor, return_indices: bool = False):
+    """`regression_topk(cost, arange(D), 2)`: cost [B,D,H,W] -> pred [B,1,H,W] (+ int32 idx [B,2,H,W])."""
+    cost = _dev(cost, "cost").contiguous()
+    assert cost.dim() == 4
+    B, D, H, W = cost.shape
+    pred = torch.empty(B, 1, H, W, device=cost.device, dtype=torch.float32)
+    idx = torch.empty(B, 2, H, W, device=cost.device, dtype=torch.int32) if return_indices else None
+    check(lib().esm_regression_top2_f32(cost.data_ptr(), pred.data_ptr(), _ptr(idx), B, D, H, W, _stream()),
+          "regression_top2")
+    return (pred, idx) if return_indices else pred
+
+
+def regression_topk(cost: torch.Tensor, disparity_samples: Optional[torch.Tensor], k: int) -> torch.Tensor:
+    """Reference signature (submodule.py:218).  The path only ever calls it with k=2 and
+    `disparity_samples = arange(D)` broadcast (ESMStereo.py:719-721); anything else is rejected."""
+    if k != 2:
+        raise NotImplementedError("regression_topk: only k=2 is on the ESMStereo path")
+    return regression_top2(cost)
+
+
+def disparity_regression(x: torch.Tensor, maxdisp: int) -> torch.Tensor:
+    """submodule.py:211-216 -- sum_d x[d]*d, NO softmax; returns [B,H,W] like the reference."""
+    x = _dev(x, "x").contiguous()
+    assert len(x.shape) == 4 and x.shape[1] == maxdisp
+    B, D, H, W = x.shape
+    pred = torch.empty(B, H, W, device=x.device, dtype=torch.float32)
+    check(lib().esm_disparity_regression_f32(x.data_ptr(), pred.data_ptr(), B, D, H, W, _stream()), "disparity_regression")
+    return pred
+
+
+def bilinear_add(prev: torch.Tensor, residual: torch.Tensor, factor: int, out_scale: float = 1.0) -> torch.Tensor:
+    """(F.interpolate(prev, scale_factor=factor, 'bilinear', align_corners=False) + residual) * out_scale."""
+    prev, residual = _dev(prev, "prev").contiguous(), _dev(residual, "residual").contiguous()
+    B, c, h, w = prev.shape
+    assert c == 1 and tuple(residual.shape) == (B, 1, h * factor, w * factor)
+    out = torch.empty_like(residual)
+    check(lib().esm_bilinear_add_f32(prev.data_ptr(), residual.data_ptr(), out.data_ptr(), B, h, w, factor,
+                                     float(out_scale), _stream()), "bilinear_add")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# fused convolution
+# ---------------------------------------------------------------------------------------------
+class PackedConv:
+    """Device-resident packed form of one conv layer: kernel-layout weights + folded affine.
+    Built once per layer by `pack_conv` (BN fold + layout, the `esm_pack_weights` step of SURVEY 8b)."""
+
+    __slots__ = ("weight", "scale", "shift", "Cout", "Cin", "k", "stride", "pad", "transposed", "ndim")
+
+    def __init__(self, weight, scale, shift, Cout, Cin, k, stride, pad, transposed, ndim):
+        self.weight, self.scale, self.shift = weight, scale, shift
+        self.Cout, self.Cin, self.k, self.stride, self.pad = Cout, Cin, k, stride, pad
+        self.transposed, self.ndim = transposed, ndim
+
+
+def _triple(v, ndim):
+    if isinstance(v, (tuple, list)):
+        v = tuple(int(a) for a in v)
+        return ((1,) * (3 - len(v)) + v) if ndim == 2 else v
+    return (1, int(v), int(v)) if ndim == 2 else (int(v),) * 3
+
+
+def pack_conv(weight: torch.Tensor, stride=1, padding=0, transposed: bool = False, bias: Optional[torch.Tensor] = None,
+              bn: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, float]] = None) -> PackedConv:
+    """weight: torch layout ([Cout,Cin,k..] or transposed [Cin,Cout,k..]); bn = (gamma, beta, mean, var, eps)."""
+    w = _dev(weight.detach(), "weight").contiguous()
+    ndim = w.dim() - 2
+    if transposed:
+        Cin, Cout = w.shape[0], w.shape[1]
+    else:
+        Cout, Cin = w.shape[0], w.shape[1]
+    ks = tuple(w.shape[2:])
+    kd, kh, kw = ((1,) + ks) if ndim == 2 else ks
+    s = _triple(stride, ndim)
+    p = _triple(padding, ndim)
+    if ndim == 2:
+        p = (0, p[1], p[2])
+    stride_i = s[2]
+    L = lib()
+    n = L.esm_packed_weight_elems(Cout, Cin, kd, kh, kw, int(transposed))
+    packed = torch.empty(n, device=w.device, dtype=torch.float32)
+    check(L.esm_pack_conv_weight_f32(w.data_ptr(), packed.data_ptr(), Cout, Cin, kd, kh, kw, int(transposed), _stream()),
+          "pack_conv_weight")
+    scale = torch.empty(Cout, device=w.device, dtype=torch.float32)
+    shift = torch.empty(Cout, device=w.device, dtype=torch.float32)
+    if bn is not None:
+        g, b_, m, v, eps = bn
+        g, b_, m, v = [_dev(t.detach(), "bn").contiguous() for t in (g, b_, m, v)]
+        args = (g.data_ptr(), b_.data_ptr(), m.data_ptr(), v.data_ptr())
+    else:
+        eps, args = 0.0, (None, None, None, None)
+    bias_t = _dev(bias.detach(), "bias").contiguous() if bias is not None else None
+    check(L.esm_fold_bn_f32(*args, _ptr(bias_t), float(eps), Cout, scale.data_ptr(), shift.data_ptr(), _stream()), "fold_bn")
+    return PackedConv(packed, scale, shift, Cout, Cin, (kd, kh, kw), stride_i, p, bool(transposed), ndim)
+
+
+def _src_struct(t: torch.Tensor, nd: int):
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    st = t.stride()
+    s = _lib.EsmSrc()
+    s.ptr, s.C, s.sB, s.sC = t.data_ptr(), t.shape[1], st[0], st[1]
+    if nd == 3:
+        s.sD, s.sH = st[2], st[3]
+    else:
+        s.sD, s.sH = 0, st[2]
+    return s, t
+
+
+def conv(srcs: Sequence[torch.Tensor], pc: PackedConv, act: Optional[str] = None, *, out_size: Optional[Sequence[int]] = None,
+         in_mul: Optional[torch.Tensor] = None, out_mul: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, act2: Optional[str] = None, out_scale: float = 1.0,
+         pixel_shuffle: int = 0, gwc_disp: Optional[int] = None, affine: bool = True) -> torch.Tensor:
+    """Fused conv over channel-concatenated `srcs` (views with unit W stride are used in place).
+
+    gwc_disp: if given, `srcs` = (left, right) feature maps [B,C,H,W] and the conv input is their
+    group-wise correlation volume with `pc.Cin` groups and `gwc_disp` disparities, built on the fly.
+    out_size: spatial output size for transposed convs (crop-to-skip); default 2x input.
+    """
+    if isinstance(srcs, torch.Tensor):
+        srcs = [srcs]
+    srcs = [_dev(t, "conv input") for t in srcs]
+    nd = pc.ndim
+    d = EsmConv()
+    keep: List[torch.Tensor] = []
+    x0 = srcs[0]
+    B = x0.shape[0]
+    if gwc_disp is not None:
+        assert nd == 3 and len(srcs) == 2 and srcs[0].shape == srcs[1].shape and srcs[0].dim() == 4
+        Din, Hin, Win = int(gwc_disp), x0.shape[2], x0.shape[3]
+        for i, t in enumerate(srcs):
+            s, t2 = _src_struct(t, 2)
+            d.src[i] = s
+            keep.append(t2)
+        d.nsrc, d.src_mode, d.gwc_groups = 2, _lib.SRC_GWC, pc.Cin
+    else:
+        assert all(t.dim() == nd + 2 for t in srcs), "conv: input rank does not match the layer"
+        Din = x0.shape[2] if nd == 3 else 1
+        Hin, Win = x0.shape[-2], x0.shape[-1]
+        assert len(srcs) <= 3 and sum(t.shape[1] for t in srcs) == pc.Cin, \
+            "conv: %d input channels for a layer with Cin=%d" % (sum(t.shape[1] for t in srcs), pc.Cin)
+        for i, t in enumerate(srcs):
+            assert t.shape[0] == B and tuple(t.shape[2:]) == tuple(x0.shape[2:]), "conv: concatenated sources differ in extent"
+            s, t2 = _src_struct(t, nd)
+            d.src[i] = s
+            keep.append(t2)
+        d.nsrc, d.src_mode = len(srcs), _lib.SRC_TENSORS
+    kd, kh, kw = pc.k
+    pd, ph, pw = pc.pad
+    S = pc.stride
+    if pc.transposed:
+        full = ((2 * Din) if kd == 4 else Din, 2 * Hin, 2 * Win)
+        if out_size is None:
+            Do, Ho, Wo = full
+        else:
+            o = tuple(int(v) for v in out_size)
+            Do, Ho, Wo = ((1,) + o) if len(o) == 2 else o
+    else:
+        Do = (Din + 2 * pd - kd) // S + 1
+        Ho = (Hin + 2 * ph - kh) // S + 1
+        Wo = (Win + 2 * pw - kw) // S + 1
+    r = int(pixel_shuffle)
+    if r:
+        out = torch.empty(B, pc.Cout // (r * r), Ho * r, Wo * r, device=x0.device, dtype=torch.float32)
+        ost = out.stride()
+        oB, oC, oD, oH = ost[0], ost[1], 0, ost[2]
+    elif nd == 3:
+        out = torch.empty(B, pc.Cout, Do, Ho, Wo, device=x0.device, dtype=torch.float32)
+        oB, oC, oD, oH = out.stride()[:4]
+    else:
+        out = torch.empty(B, pc.Cout, Ho, Wo, device=x0.device, dtype=torch.float32)
+        ost = out.stride()
+        oB, oC, oD, oH = ost[0], ost[1], 0, ost[2]
+    if in_mul is not None:
+        in_mul = _dev(in_mul, "in_mul").contiguous()
+        assert in_mul.numel() == B * pc.Cin * Hin * Win
+    if out_mul is not None:
+        out_mul = _dev(out_mul, "out_mul").contiguous()
+        assert out_mul.numel() == B * pc.Cout * Ho * Wo
+    if residual is not None:
+        residual = _dev(residual, "residual").contiguous()
+        assert residual.shape == out.shape
+    d.in_mul = _ptr(in_mul)
+    d.B, d.Cin, d.Din, d.Hin, d.Win = B, pc.Cin, Din, Hin, Win
+    d.Cout, d.Dout, d.Hout, d.Wout = pc.Cout, Do, Ho, Wo
+    d.kd, d.kh, d.kw, d.stride = kd, kh, kw, S
+    d.pd, d.ph, d.pw, d.transposed = pd, ph, pw, int(pc.transposed)
+    d.weight = pc.weight.data_ptr()
+    d.scale = pc.scale.data_ptr() if affine else None
+    d.shift = pc.shift.data_ptr() if affine else None
+    d.act = ACT[act]
+    d.out_mul, d.residual, d.act2 = _ptr(out_mul), _ptr(residual), ACT[act2]
+    d.out_scale, d.pixel_shuffle = float(out_scale), r
+    d.out, d.oB, d.oC, d.oD, d.oH = out.data_ptr(), oB, oC, oD, oH
+    check(lib().esm_conv_f32(C.byref(d), _stream()), "conv")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# ShuffleMixer halves (shufflemixer.py:97-112)
+# ---------------------------------------------------------------------------------------------
+class MixerMlp:
+    """Device pointers of one (LayerNorm, SplitPointMlp) pair; keeps the tensors alive."""
+
+    def __init__(self, ln_w, fc0_w, fc0_b, fc2_w, fc2_b):
+        self.t = [_dev(t.detach(), "mixer param").contiguous() for t in (ln_w, fc0_w, fc0_b, fc2_w, fc2_b)]
+        self.s = EsmMixerMlp()
+        self.s.ln_w, self.s.fc0_w, self.s.fc0_b, self.s.fc2_w, self.s.fc2_b = [t.data_ptr() for t in self.t]
+        self.s.hidden = self.t[1].shape[0]
+
+
+def sm_pointwise(x: torch.Tensor, mlp: MixerMlp, extra_residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    x = _dev(x, "x").contiguous()
+    B, Cc, H, W = x.shape
+    y = torch.empty_like(x)
+    check(lib().esm_sm_pointwise_f32(x.data_ptr(), y.data_ptr(), B, Cc, H, W, C.byref(mlp.s), _ptr(extra_residual), _stream()),
+          "sm_pointwise")
+    return y
+
+
+def sm_spatial(x: torch.Tensor, dw_w: torch.Tensor, dw_b: torch.Tensor, mlp: MixerMlp,
+               extra_residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    x = _dev(x, "x").contiguous()
+    B, Cc, H, W = x.shape
+    y = torch.empty_like(x)
+    k = dw_w.shape[-1]
+    check(lib().esm_sm_spatial_f32(x.data_ptr(), y.data_ptr(), B, Cc, H, W, dw_w.data_ptr(), dw_b.data_ptr(), k,
+                                   C.byref(mlp.s), _ptr(extra_residual), _stream()), "sm_spatial")
+    return y
+
+
+# ---------------------------------------------------------------------------------------------
+# confidence head pieces (ESMStereo_confidence.py:511-744)
+# ---------------------------------------------------------------------------------------------
+def laf_cost_top7(cost: torch.Tensor) -> torch.Tensor:
+    cost = _dev(cost, "cost").contiguous()
+    B, D, H, W = cost.shape
+    out = torch.empty(B, 7, H, W, device=cost.device, dtype=torch.float32)
+    check(lib().esm_laf_cost_top7_f32(cost.data_ptr(), out.data_ptr(), B, D, H, W, _stream()), "laf_cost_top7")
+    return out
+
+
+def laf_attention(cost_x, disp_x, imag_x, att_c, att_d, att_i) -> torch.Tensor:
+    ts = [_dev(t, "laf_attention input").contiguous() for t in (cost_x, disp_x, imag_x, att_c, att_d, att_i)]
+    B, Cc, H, W = ts[0].shape
+    out = torch.empty(B, 3 * Cc, H, W, device=ts[0].device, dtype=torch.float32)
+    check(lib().esm_laf_attention_f32(*[t.data_ptr() for t in ts], out.data_ptr(), B, Cc, H, W, _stream()), "laf_attention")
+    return out
+
+
+_LIN_CACHE = {}
+
+
+def _linspace_pm1(n: int, device) -> torch.Tensor:
+    """np.linspace(-1, 1, n) rounded to fp32, as the reference builds its grid (":695-697")."""
+    key = (n, str(device))
+    if key not in _LIN_CACHE:
+        _LIN_CACHE[key] = torch.tensor(np.linspace(-1, 1, n), dtype=torch.float32).to(device)
+    return _LIN_CACHE[key]
+
+
+def laf_sample_embed(feat, scale, weight, bn_scale, bn_shift) -> torch.Tensor:
+    feat, scale = _dev(feat, "feat").contiguous(), _dev(scale, "scale").contiguous()
+    B, Cc, H, W = feat.shape
+    lin_x, lin_y = _linspace_pm1(W, feat.device), _linspace_pm1(H, feat.device)
+    out = torch.empty_like(feat)
+    check(lib().esm_laf_sample_embed_f32(feat.data_ptr(), scale.data_ptr(), lin_x.data_ptr(), lin_y.data_ptr(),
+                                         weight.data_ptr(), bn_scale.data_ptr(), bn_shift.data_ptr(), out.data_ptr(),
+                                         B, Cc, H, W, _stream()), "laf_sample_embed")
+    return out
+
+
+def conf_convex_up4(feat, conf, weight, bias) -> torch.Tensor:
+    feat, conf = _dev(feat, "feat").contiguous(), _dev(conf, "conf").contiguous()
+    B, Cc, h, w = feat.shape
+    out = torch.empty(B, 1, 4 * h, 4 * w, device=feat.device, dtype=torch.float32)
+    check(lib().esm_conf_convex_up4_f32(feat.data_ptr(), conf.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                        out.data_ptr(), B, Cc, h, w, _stream()), "conf_convex_up4")
+    return out
+
+
+def fill_(t: torch.Tensor, value: float) -> torch.Tensor:
+    check(lib().esm_fill_f32(_dev(t, "t").data_ptr(), t.numel(), float(value), _stream()), "fill")
+    return t

@@ -1,0 +1,173 @@
+/*
+ * esm_b200.h -- C ABI of libesm_b200.so: the B200 (sm_100a) implementation of ESMStereo's
+ * feature-to-disparity hot path.
+ *
+ * The reference (rahul-rwat/ESMStereo) has no native operator API: its operator seams are Python
+ * callables in models/submodule.py, models/shufflemixer.py, models/ESMStereo.py and
+ * models/ESMStereo_confidence.py.  Each entry point below replaces one of those seams and cites it
+ * (paths relative to the reference root).  Conventions:
+ *   - all pointers are DEVICE pointers to fp32 (unless stated), caller-owned, no allocation inside;
+ *   - tensors are NCHW / NCDHW; where strides are not passed they are contiguous;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant per stream,
+ *     and legal inside CUDA-graph capture;
+ *   - return value: 0 = ok, negative = error (see esm_last_error()).
+ * There is no CPU fallback: without a CUDA device every compute entry point returns ESM_ERR_CUDA.
+ */
+#ifndef ESM_B200_H
+#define ESM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESM_OK 0
+#define ESM_ERR_ARG (-1)   /* invalid argument / unsupported shape */
+#define ESM_ERR_CUDA (-2)  /* CUDA runtime error (launch failure, no device) */
+
+/* activation codes for esm_conv_t.act / act2 */
+#define ESM_ACT_NONE 0
+#define ESM_ACT_GELU 1     /* exact erf GELU, submodule.py:37 */
+#define ESM_ACT_RELU 2
+#define ESM_ACT_SILU 3
+#define ESM_ACT_SIGMOID 4
+#define ESM_ACT_2SIGMOID 5 /* 2*sigmoid(x): LAFNet scale head, ESMStereo_confidence.py:691 */
+#define ESM_ACT_RELU6 6
+
+/* esm_conv_t.src_mode */
+#define ESM_SRC_TENSORS 0  /* up to 3 channel-concatenated strided tensors (replaces torch.cat + crop) */
+#define ESM_SRC_GWC 1      /* input voxels are the group-wise correlation of src[0]=left, src[1]=right
+                              feature maps, computed on the fly (never written to HBM);
+                              fuses submodule.py:151-161 into the consumer conv (ESMStereo.py:708-713) */
+
+const char* esm_last_error(void);
+int esm_version(void);
+/* Device properties the host side sizes grids with; returns ESM_ERR_CUDA when no device. */
+int esm_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* One source of a (possibly concatenated) conv input.  W stride is 1. */
+typedef struct {
+  const float* ptr; /* element [b=0,c=0,d=0,h=0,w=0] of the (possibly cropped) view */
+  int C;            /* channels contributed by this source */
+  long long sB, sC, sD, sH; /* strides in elements */
+} esm_src_t;
+
+/*
+ * Generic fused convolution: conv / transposed conv (2D = 3D with D=1) + per-channel affine
+ * (folded eval BatchNorm and/or bias) + activation + optional broadcast multiply + optional
+ * residual add + optional second activation, with optional PixelShuffle store.
+ * Replaces BasicConv.forward (submodule.py:32-38) and every bare nn.Conv2d / ConvTranspose on the
+ * path (ESMStereo.py:129-182 aggregation, :185-239 up_refinement, :242-509 upsample4/8/16,
+ * shufflemixer.py:123-127, ESMStereo_confidence.py:511-744).
+ */
+typedef struct {
+  esm_src_t src[3];
+  int nsrc;
+  int src_mode;              /* ESM_SRC_* */
+  int gwc_groups;            /* ESM_SRC_GWC: number of groups G (input channels of the conv);
+                                src[0].C == src[1].C == feature channels */
+  const float* in_mul;       /* optional [B,Cin,1,Hin,Win] multiplier broadcast over D (att, ESMStereo.py:711) */
+  int B, Cin, Din, Hin, Win; /* logical input extent */
+  int Cout, Dout, Hout, Wout;
+  int kd, kh, kw;            /* kernel extent; transposed: must be 4 (D: 4 or 1) */
+  int stride;                /* 1 or 2 (same in every spatial dim; D stride is 1 when kd==1) */
+  int pd, ph, pw;            /* padding */
+  int transposed;            /* 1: ConvTranspose k4 s2 p1 (sub-pixel phase decomposition) */
+  const float* weight;       /* packed by esm_pack_conv_weight_f32 */
+  const float* scale;        /* [Cout] y = acc*scale + shift  (NULL -> 1) */
+  const float* shift;        /* [Cout]                        (NULL -> 0) */
+  int act;                   /* ESM_ACT_* applied after the affine */
+  const float* out_mul;      /* optional [B,Cout,1,Hout,Wout] multiplier after act (ESMStereo.py:703) */
+  const float* residual;     /* optional tensor with the output's strides, added after act/out_mul */
+  int act2;                  /* ESM_ACT_* applied after the residual add */
+  float out_scale;           /* final multiply (1.0f = none) */
+  int pixel_shuffle;         /* 0, or r: out[b, co/(r*r), h*r+(co/r)%r, w*r+co%r] (2D only) */
+  float* out;
+  long long oB, oC, oD, oH;  /* output strides in elements (W stride 1) */
+} esm_conv_t;
+
+/* Elements needed for the packed form of a conv weight (fp32 count). */
+long long esm_packed_weight_elems(int Cout, int Cin, int kd, int kh, int kw, int transposed);
+/*
+ * Repack a torch-layout weight ([Cout,Cin,kd,kh,kw]; transposed: [Cin,Cout,kd,kh,kw]) into the
+ * kernel layout ([phase][tap][Cin_pad][Cout_pad], zero padded).  Device to device.
+ */
+int esm_pack_conv_weight_f32(const float* w, float* packed, int Cout, int Cin, int kd, int kh, int kw,
+                             int transposed, void* stream);
+/*
+ * Fold eval-mode BatchNorm (+ optional conv bias) into scale/shift:
+ *   scale = gamma / sqrt(var + eps); shift = beta - mean*scale + bias*scale.
+ * Any of gamma/beta/mean/var may be NULL together (no BN): scale = 1, shift = bias (or 0).
+ */
+int esm_fold_bn_f32(const float* gamma, const float* beta, const float* mean, const float* var,
+                    const float* bias, float eps, int C, float* scale, float* shift, void* stream);
+int esm_conv_f32(const esm_conv_t* desc, void* stream);
+
+/* build_gwc_volume (submodule.py:151-161): L,R [B,C,H,W] -> V [B,G,D,H,W]; writes the zero
+ * triangle itself (no memset). */
+int esm_gwc_volume_f32(const float* L, const float* R, float* V, int B, int C, int H, int W, int D, int G,
+                       void* stream);
+/* build_norm_correlation_volume (submodule.py:187-200): -> V [B,1,D,H,W].
+ * `ws` is scratch of 2*B*C*H*W floats (normalised copies of L and R). */
+int esm_norm_corr_volume_f32(const float* L, const float* R, float* V, float* ws, int B, int C, int H, int W,
+                             int D, void* stream);
+
+/* regression_topk(cost, arange(D), k=2) (submodule.py:218-225, ESMStereo.py:719-721):
+ * cost [B,D,H,W] -> pred [B,1,H,W]; idx (optional, int32 [B,2,H,W]) receives the top-2 indices
+ * (ties: lower index first). */
+int esm_regression_top2_f32(const float* cost, float* pred, int* idx, int B, int D, int H, int W, void* stream);
+/* disparity_regression (submodule.py:211-216): sum_d cost[d]*d, no softmax -> [B,1,H,W]. */
+int esm_disparity_regression_f32(const float* cost, float* pred, int B, int D, int H, int W, void* stream);
+
+/* out = (bilinear_up(prev, factor, align_corners=False) + residual) * out_scale
+ * (ESMStereo.py:307,316,745).  prev [B,1,h,w], residual/out [B,1,h*f,w*f]. */
+int esm_bilinear_add_f32(const float* prev, const float* residual, float* out, int B, int h, int w, int factor,
+                         float out_scale, void* stream);
+
+/*
+ * ShuffleMixer SMLayer halves (shufflemixer.py:97-112), C in {8,16}:
+ *   pointwise:  y = shuffle8(cat(MLP(LN(x)[:C/2]), LN(x)[C/2:])) + x
+ *   spatial:    t = depthwise_kxk(x) + bias; y = shuffle8(cat(MLP(LN(t)[:C/2]), LN(t)[C/2:])) + t
+ * MLP = 1x1 (C/2 -> hidden) + SiLU + 1x1 (hidden -> C/2), with bias; LN is bias-free over channels.
+ * fc0_w [hidden, C/2], fc0_b [hidden], fc2_w [C/2, hidden], fc2_b [C/2]  (torch layouts).
+ * `extra_residual` (optional) is added to the output (FMBlock's `net(x) + x`, shufflemixer.py:130).
+ */
+typedef struct {
+  const float* ln_w;                    /* [C] */
+  const float* fc0_w; const float* fc0_b;
+  const float* fc2_w; const float* fc2_b;
+  int hidden;
+} esm_mixer_mlp_t;
+int esm_sm_pointwise_f32(const float* x, float* y, int B, int C, int H, int W, const esm_mixer_mlp_t* mlp,
+                         const float* extra_residual, void* stream);
+int esm_sm_spatial_f32(const float* x, float* y, int B, int C, int H, int W, const float* dw_w /*[C,1,k,k]*/,
+                       const float* dw_b /*[C]*/, int k, const esm_mixer_mlp_t* mlp, const float* extra_residual,
+                       void* stream);
+
+/* LAFNet cost tower front end (ESMStereo_confidence.py:645-653): per pixel
+ * softmax(-cost/||cost||_2 * 100) over D, then the 7 largest probabilities, descending.
+ * cost [B,D,H,W] (D <= 64) -> out [B,7,H,W]. */
+int esm_laf_cost_top7_f32(const float* cost, float* out, int B, int D, int H, int W, void* stream);
+/* LAFNet 3-way attention (ESMStereo_confidence.py:676-686): softmax over the three 1-channel
+ * attention maps, towers scaled and concatenated: out [B,3C,H,W]. */
+int esm_laf_attention_f32(const float* cost_x, const float* disp_x, const float* imag_x, const float* att_c,
+                          const float* att_d, const float* att_i, float* out, int B, int C, int H, int W,
+                          void* stream);
+/* LAFNet scale-adaptive sampling + embed_conv2 (k3, stride 3) + affine + ReLU
+ * (ESMStereo_confidence.py:693-719), fused: the 3h x 3w `grid_sample` image is never materialised.
+ * feat [B,C,H,W], scale [B,1,H,W], lin_x [W], lin_y [H] (np.linspace(-1,1,n) as fp32),
+ * weight [C,C,3,3] (torch layout), bn scale/shift [C] -> out [B,C,H,W]. */
+int esm_laf_sample_embed_f32(const float* feat, const float* scale, const float* lin_x, const float* lin_y,
+                             const float* weight, const float* bn_scale, const float* bn_shift, float* out, int B,
+                             int C, int H, int W, void* stream);
+/* conf_upsample convex x4 upsampling (ESMStereo_confidence.py:536-543): logits = ConvTranspose2d(C->9,
+ * k4, s4)(feat) + bias; out[Y,X] = sum_k softmax(logits)[k] * conf[Y/4 + k/3 - 1, X/4 + k%3 - 1].
+ * feat [B,C,h,w], conf [B,1,h,w], weight [C,9,4,4] (torch layout), bias [9] -> out [B,1,4h,4w]. */
+int esm_conf_convex_up4_f32(const float* feat, const float* conf, const float* weight, const float* bias,
+                            float* out, int B, int C, int h, int w, void* stream);
+/* Fill `n` floats with `value`. */
+int esm_fill_f32(float* p, long long n, float value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESM_B200_H */

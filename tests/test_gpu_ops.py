@@ -1,0 +1,287 @@
+"""GPU parity of every C-ABI operator against a torch-CPU fp32 statement of the same op
+(the oracle's primitives where they exist, `torch.nn.functional` for the convolutions).
+
+Tolerances (fp32 kernels, different summation order than MKL-DNN): conv outputs 2e-5 relative to the
+tensor's max magnitude; cost volume 1e-6 (un-contracted arithmetic, expected bit-equal for cpg=2);
+top-2 indices bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.esm_oracle import EsmOracle
+
+pytestmark = pytest.mark.gpu
+
+ACTS = {None: lambda x: x, "gelu": F.gelu, "relu": F.relu, "silu": F.silu, "sigmoid": torch.sigmoid,
+        "2sigmoid": lambda x: 2 * torch.sigmoid(x), "relu6": F.relu6}
+
+
+def _ops():
+    from esmstereo_b200 import ops
+    return ops
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max() / (b.abs().max() + 1e-20))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape) * 7919)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def make_layer(cin, cout, k, nd, transposed=False, bn=True, bias=False, seed=0):
+    ks = (k,) * nd if isinstance(k, int) else tuple(k)
+    wshape = ((cin, cout) if transposed else (cout, cin)) + ks
+    fan = cin * int(np.prod(ks))
+    w = rnd(*wshape, seed=seed) * (2.0 / fan) ** 0.5
+    p = {"w": w, "bias": rnd(cout, seed=seed + 1) * 0.1 if bias else None, "bn": None}
+    if bn:
+        p["bn"] = (0.5 + torch.rand(cout), rnd(cout, seed=seed + 2) * 0.1, rnd(cout, seed=seed + 3) * 0.1,
+                   0.5 + torch.rand(cout), 1e-5)
+    return p
+
+
+def ref_conv(x, p, stride, pad, transposed, act, nd):
+    fn = {(2, False): F.conv2d, (2, True): F.conv_transpose2d, (3, False): F.conv3d, (3, True): F.conv_transpose3d}[(nd, transposed)]
+    y = fn(x, p["w"], p["bias"], stride=stride, padding=pad)
+    if p["bn"] is not None:
+        g, b, m, v, eps = p["bn"]
+        y = F.batch_norm(y, m, v, g, b, False, 0.0, eps)
+    return ACTS[act](y)
+
+
+def gpu_pack(p, stride, pad, transposed):
+    ops = _ops()
+    bn = None if p["bn"] is None else tuple(t.cuda() for t in p["bn"][:4]) + (p["bn"][4],)
+    return ops.pack_conv(p["w"].cuda(), stride, pad, transposed, None if p["bias"] is None else p["bias"].cuda(), bn)
+
+
+CONV_CASES = [
+    # name, nd, cin, cout, k, stride, pad, transposed, act, bn, bias, in_shape (spatial), batch
+    ("stem3d_32_8", 3, 32, 8, 3, 1, 1, False, "gelu", True, False, (6, 10, 36), 1),
+    ("agg3d_8_8_b2", 3, 8, 8, 3, 1, 1, False, "gelu", True, False, (5, 9, 20), 2),
+    ("down3d_8_24_s2", 3, 8, 24, 3, 2, 1, False, "gelu", True, False, (12, 18, 40), 1),
+    ("down3d_odd_40_72_s2", 3, 40, 72, 3, 2, 1, False, "gelu", True, False, (3, 5, 7), 1),
+    ("conv3d_24_24", 3, 24, 24, 3, 1, 1, False, "gelu", True, False, (6, 9, 39), 1),
+    ("conv3d_72_72", 3, 72, 72, 3, 1, 1, False, "gelu", True, False, (2, 3, 10), 1),
+    ("conv3d_12_12_pad", 3, 12, 12, 3, 1, 1, False, "gelu", True, False, (6, 7, 11), 1),
+    ("corr_stem_1_8", 3, 1, 8, 3, 1, 1, False, "gelu", True, False, (12, 6, 10), 1),
+    ("k1_3d_48_24", 3, 48, 24, 1, 1, 0, False, "gelu", True, False, (4, 6, 18), 1),
+    ("deconv3d_72_40", 3, 72, 40, 4, 2, 1, True, "gelu", True, False, (2, 3, 5), 1),
+    ("deconv3d_24_1", 3, 24, 1, 4, 2, 1, True, None, False, False, (4, 6, 13), 2),
+    ("dm0_k5p1_1_32", 2, 1, 32, 5, 1, 1, False, "gelu", True, False, (12, 40), 1),
+    ("dm3_k1p1_32_32", 2, 32, 32, 1, 1, 1, False, "gelu", True, False, (10, 38), 1),
+    ("ref_s2_1_32", 2, 1, 32, 3, 2, 1, False, "gelu", True, False, (24, 80), 1),
+    ("ref_s2_32_32", 2, 32, 32, 3, 2, 1, False, "gelu", True, False, (12, 40), 2),
+    ("conv2d_16_16", 2, 16, 16, 3, 1, 1, False, "gelu", True, False, (9, 21), 1),
+    ("deconv2d_32_32", 2, 32, 32, 4, 2, 1, True, "gelu", True, False, (6, 20), 1),
+    ("deconv2d_16_1", 2, 16, 1, 4, 2, 1, True, "gelu", True, False, (6, 10), 1),
+    ("deconv2d_32_1_plain", 2, 32, 1, 4, 2, 1, True, None, False, False, (12, 40), 1),
+    ("tail_16_1_bias", 2, 16, 1, 3, 1, 1, False, None, False, True, (24, 80), 1),
+    ("fm_16_32_silu_bias", 2, 16, 32, 3, 1, 1, False, "silu", False, True, (12, 40), 1),
+    ("laf_7_16_relu", 2, 7, 16, 3, 1, 1, False, "relu", True, True, (6, 10), 1),
+    ("laf_64_16_relu", 2, 64, 16, 3, 1, 1, False, "relu", True, True, (6, 10), 1),
+    ("laf_16_1_2sig", 2, 16, 1, 1, 1, 0, False, "2sigmoid", True, True, (6, 10), 1),
+    ("wide_row", 2, 32, 32, 3, 1, 1, False, "gelu", True, False, (4, 312), 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_matches_torch(case):
+    name, nd, cin, cout, k, stride, pad, transposed, act, bn, bias, sp, B = case
+    ops = _ops()
+    p = make_layer(cin, cout, k, nd, transposed, bn, bias, seed=len(name))
+    x = rnd(B, cin, *sp, seed=3)
+    want = ref_conv(x, p, stride, pad, transposed, act, nd)
+    got = ops.conv(x.cuda(), gpu_pack(p, stride, pad, transposed), act)
+    assert rel(got, want) < 2e-5, name
+
+
+def test_conv_concat_sources_and_crop():
+    """torch.cat((a[cropped], b, c), 1) -> k1 conv (aggregation.agg_0, up_refinement.agg_0)."""
+    ops = _ops()
+    a_full = rnd(1, 40, 4, 6, 10, seed=1)  # deconv output before crop-to-skip
+    a = a_full[:, :, :3, :5, :9]
+    b = rnd(1, 40, 3, 5, 9, seed=2)
+    p = make_layer(80, 40, 1, 3, seed=5)
+    want = ref_conv(torch.cat((a, b), 1), p, 1, 0, False, "gelu", 3)
+    got = ops.conv([a_full.cuda()[:, :, :3, :5, :9], b.cuda()], gpu_pack(p, 1, 0, False), "gelu")
+    assert rel(got, want) < 2e-5
+    srcs = [rnd(2, 32, 6, 20, seed=7), rnd(2, 32, 6, 20, seed=8), rnd(2, 96, 6, 20, seed=9)]
+    p = make_layer(160, 32, 1, 2, seed=6)
+    want = ref_conv(torch.cat(srcs, 1), p, 1, 0, False, "gelu", 2)
+    got = ops.conv([s.cuda() for s in srcs], gpu_pack(p, 1, 0, False), "gelu")
+    assert rel(got, want) < 2e-5
+    srcs = [rnd(1, 16, 6, 10, seed=7), rnd(1, 1, 6, 10, seed=8)]  # LAFNet fusion_conv1: cat(feat, out)
+    p = make_layer(17, 16, 3, 2, bias=True, seed=6)
+    want = ref_conv(torch.cat(srcs, 1), p, 1, 1, False, "relu", 2)
+    got = ops.conv([s.cuda() for s in srcs], gpu_pack(p, 1, 1, False), "relu")
+    assert rel(got, want) < 2e-5
+
+
+def test_deconv_crop_to_skip():
+    ops = _ops()
+    x = rnd(1, 24, 2, 8, 12, seed=1)
+    p = make_layer(24, 16, 4, 3, transposed=True, seed=2)
+    full = ref_conv(x, p, 2, 1, True, "gelu", 3)
+    want = full[:, :, :3, :16, :23]
+    got = ops.conv(x.cuda(), gpu_pack(p, 2, 1, True), "gelu", out_size=(3, 16, 23))
+    assert rel(got, want) < 2e-5
+
+
+def test_conv_epilogue_fusions():
+    ops = _ops()
+    x = rnd(2, 16, 6, 10, seed=1)
+    p = make_layer(16, 16, 1, 2, bn=False, bias=True, seed=2)
+    res = rnd(2, 16, 6, 10, seed=3)
+    want = ref_conv(x, p, 1, 0, False, None, 2) + res
+    got = ops.conv(x.cuda(), gpu_pack(p, 1, 0, False), None, residual=res.cuda())
+    assert rel(got, want) < 2e-5
+    # residual + second activation + scale (conf_upsample tail: sigmoid(conv1_up(x) + conf1))
+    p = make_layer(16, 1, 4, 2, transposed=True, seed=4)
+    res = rnd(2, 1, 12, 20, seed=5)
+    want = torch.sigmoid(ref_conv(x, p, 2, 1, True, "gelu", 2) + res) * 3.0
+    got = ops.conv(x.cuda(), gpu_pack(p, 2, 1, True), "gelu", residual=res.cuda(), act2="sigmoid", out_scale=3.0)
+    assert rel(got, want) < 2e-5
+    # broadcast multipliers over D (att, ESMStereo.py:703,711)
+    v = rnd(1, 32, 4, 6, 10, seed=6)
+    att_in = rnd(1, 32, 6, 10, seed=7)
+    att_out = rnd(1, 8, 6, 10, seed=8)
+    p = make_layer(32, 8, 3, 3, seed=9)
+    want = ref_conv(v * att_in.unsqueeze(2), p, 1, 1, False, "gelu", 3) * att_out.unsqueeze(2)
+    got = ops.conv(v.cuda(), gpu_pack(p, 1, 1, False), "gelu", in_mul=att_in.cuda(), out_mul=att_out.cuda())
+    assert rel(got, want) < 2e-5
+
+
+@pytest.mark.parametrize("r,n", [(2, 16), (4, 8)])
+def test_conv_pixel_shuffle_silu(r, n):
+    ops = _ops()
+    x = rnd(1, n, 6, 10, seed=1)
+    p = make_layer(n, n * r * r, 1, 2, bn=False, bias=True, seed=2)
+    want = F.silu(F.pixel_shuffle(ref_conv(x, p, 1, 0, False, None, 2), r))
+    got = ops.conv(x.cuda(), gpu_pack(p, 1, 0, False), "silu", pixel_shuffle=r)
+    assert rel(got, want) < 2e-5
+
+
+@pytest.mark.parametrize("B,C,H,W,D,G", [(1, 64, 6, 40, 12, 32), (2, 64, 5, 10, 12, 32), (1, 64, 4, 39, 48, 32),
+                                         (1, 24, 3, 16, 5, 8)])
+def test_gwc_volume(B, C, H, W, D, G):
+    ops = _ops()
+    L, R = rnd(B, C, H, W, seed=1), rnd(B, C, H, W, seed=2)
+    want = EsmOracle({}, 192).gwc_volume(L, R, D, G)
+    got = ops.build_gwc_volume(L.cuda(), R.cuda(), D, G)
+    assert rel(got, want) < 1e-6
+    if C // G == 2:
+        assert torch.equal(got.cpu(), want), "cpg=2 volume must be bit-identical to the reference arithmetic"
+
+
+def test_gwc_fused_into_stem_conv():
+    ops = _ops()
+    L, R = rnd(1, 64, 6, 40, seed=1), rnd(1, 64, 6, 40, seed=2)
+    D = 12
+    p = make_layer(32, 8, 3, 3, seed=3)
+    vol = EsmOracle({}, 192).gwc_volume(L, R, D, 32)
+    want = ref_conv(vol, p, 1, 1, False, "gelu", 3)
+    pc = gpu_pack(p, 1, 1, False)
+    got = ops.conv([L.cuda(), R.cuda()], pc, "gelu", gwc_disp=D)
+    assert rel(got, want) < 2e-5
+    att = rnd(1, 32, 6, 40, seed=4)
+    want = ref_conv(vol * att.unsqueeze(2), p, 1, 1, False, "gelu", 3)
+    got = ops.conv([L.cuda(), R.cuda()], pc, "gelu", gwc_disp=D, in_mul=att.cuda())
+    assert rel(got, want) < 2e-5
+
+
+@pytest.mark.parametrize("B,C,H,W,D", [(1, 64, 6, 40, 12), (2, 64, 3, 10, 12)])
+def test_norm_corr_volume(B, C, H, W, D):
+    ops = _ops()
+    L, R = rnd(B, C, H, W, seed=1), rnd(B, C, H, W, seed=2)
+    want = EsmOracle({}, 192).norm_corr_volume(L, R, D)
+    got = ops.build_norm_correlation_volume(L.cuda(), R.cuda(), D)
+    assert rel(got, want) < 1e-4  # the BASELINE.json volume gate
+
+
+def test_regression_top2_indices_bit_exact():
+    ops = _ops()
+    cost = rnd(2, 48, 24, 78, seed=1)
+    cost[0, :, 0, 0] = 0.0           # all ties
+    cost[0, 5, 0, 1] = cost[0, 9, 0, 1] = 7.0   # tie for the maximum
+    cost[0, 3, 0, 2] = 9.0
+    cost[0, 11, 0, 2] = cost[0, 20, 0, 2] = 8.0  # tie for second
+    want, widx = EsmOracle.regression_top2(cost)
+    got, gidx = ops.regression_top2(cost.cuda(), return_indices=True)
+    assert torch.equal(gidx.cpu().long(), widx), "top-2 indices must be bit-exact"
+    assert float((got.cpu() - want).abs().max()) < 1e-5
+    assert torch.equal(ops.regression_topk(cost.cuda(), None, 2), got)
+
+
+def test_disparity_regression_no_softmax():
+    ops = _ops()
+    cost = rnd(2, 12, 6, 10, seed=1)
+    want = EsmOracle.disparity_regression(cost).squeeze(1)
+    got = ops.disparity_regression(cost.cuda(), 12)
+    assert got.shape == want.shape and rel(got, want) < 1e-6
+
+
+@pytest.mark.parametrize("f", [2, 4])
+def test_bilinear_add(f):
+    ops = _ops()
+    prev, res = rnd(2, 1, 6, 10, seed=1), rnd(2, 1, 6 * f, 10 * f, seed=2)
+    want = (F.interpolate(prev, scale_factor=f, mode="bilinear", align_corners=False) + res) * 4
+    got = ops.bilinear_add(prev.cuda(), res.cuda(), f, 4.0)
+    assert rel(got, want) < 1e-6
+
+
+@pytest.mark.parametrize("C", [8, 16])
+def test_shufflemixer_block(C):
+    """FMBlock (2 SMLayers + conv tail) against the oracle's restatement of shufflemixer.py."""
+    from esmstereo_b200 import layers
+    torch.manual_seed(C)
+    blk = layers.FMBlock(C, 7, 2)
+    sd = {k: (torch.randn_like(v) * 0.3 + (1.0 if k.endswith("body.weight") else 0.0)) for k, v in blk.state_dict().items()}
+    blk.load_state_dict(sd)
+    x = rnd(2, C, 12, 40, seed=1)
+    want = EsmOracle({"b." + k: v for k, v in sd.items()}, 192).fm_block(x, "b")
+    got = blk.cuda().eval()(x.cuda())
+    assert rel(got, want) < 2e-5
+
+
+def test_laf_pieces():
+    ops = _ops()
+    cost = rnd(2, 12, 6, 10, seed=1)
+    nrm = torch.sqrt((cost ** 2).sum(1, keepdim=True) + 1e-6)
+    want = torch.topk(F.softmax(-(cost / nrm) * 100, 1), k=7, dim=1).values
+    assert rel(ops.laf_cost_top7(cost.cuda()), want) < 1e-5
+    towers = [rnd(2, 16, 6, 10, seed=s) for s in (2, 3, 4)]
+    atts = [rnd(2, 1, 6, 10, seed=s) for s in (5, 6, 7)]
+    a = F.softmax(torch.cat(atts, 1), 1)
+    want = torch.cat([t * a[:, i:i + 1] for i, t in enumerate(towers)], 1)
+    got = ops.laf_attention(*[t.cuda() for t in towers], *[t.cuda() for t in atts])
+    assert rel(got, want) < 1e-6
+
+
+def test_conf_convex_up4():
+    ops = _ops()
+    feat, conf = rnd(2, 16, 6, 10, seed=1), rnd(2, 1, 6, 10, seed=2)
+    w, b = rnd(16, 9, 4, 4, seed=3) * 0.3, rnd(9, seed=4) * 0.1
+    sfm = F.softmax(F.conv_transpose2d(feat, w, b, stride=4), 1)
+    nb = F.interpolate(F.unfold(conf, 3, 1, 1).reshape(2, 9, 6, 10), (24, 40), mode="nearest")
+    want = (nb * sfm).sum(1, keepdim=True)
+    got = ops.conf_convex_up4(feat.cuda(), conf.cuda(), w.cuda(), b.cuda())
+    assert rel(got, want) < 1e-5
+
+
+def test_errors_are_loud():
+    ops = _ops()
+    with pytest.raises(TypeError):
+        ops.build_gwc_volume(torch.zeros(1, 64, 4, 8), torch.zeros(1, 64, 4, 8), 4, 32)  # CPU tensors: no fallback
+    with pytest.raises(AssertionError):
+        ops.build_gwc_volume(torch.zeros(1, 30, 4, 8).cuda(), torch.zeros(1, 30, 4, 8).cuda(), 4, 32)
+    p = make_layer(8, 8, 3, 2)
+    pc = gpu_pack(p, 1, 1, False)
+    with pytest.raises(AssertionError):
+        ops.conv(torch.zeros(1, 9, 4, 8).cuda(), pc)

@@ -1,0 +1,64 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/esm_b200.h declares,
+argument validation works without a GPU, the module tree is key-compatible with the reference."""
+import contextlib
+import io
+import os
+import re
+
+import pytest
+import torch
+
+from tests.helpers import GOLDEN_NAMES, golden_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from esmstereo_b200 import _lib
+    handle = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "esm_b200.h")).read()
+    declared = set(re.findall(r"\b(esm_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(handle, name), "libesm_b200.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert handle.esm_version() >= 100
+
+
+def test_argument_errors_need_no_gpu():
+    from esmstereo_b200 import _lib
+    L = _lib.lib()
+    assert L.esm_gwc_volume_f32(None, None, None, 1, 64, 4, 8, 4, 32, None) == -1
+    assert b"null" in L.esm_last_error()
+    assert L.esm_conv_f32(None, None) == -1
+    n = L.esm_packed_weight_elems(8, 32, 3, 3, 3, 0)
+    assert n == 27 * 32 * 8
+    assert L.esm_packed_weight_elems(40, 72, 4, 4, 4, 1) == 8 * 8 * 72 * 40
+    assert L.esm_packed_weight_elems(1, 24, 4, 4, 4, 1) == 8 * 8 * 24 * 2   # Cout=1 padded to one FFMA2 pair
+    assert L.esm_packed_weight_elems(32, 1, 1, 5, 5, 0) == 25 * 1 * 32      # Cin=1 keeps CK=1
+
+
+def test_no_cpu_fallback():
+    from esmstereo_b200 import ops
+    with pytest.raises(TypeError):
+        ops.regression_top2(torch.zeros(1, 4, 2, 2))
+    if not torch.cuda.is_available():
+        from esmstereo_b200 import _lib
+        assert _lib.lib().esm_device_info(None, None, None) == -2  # ESM_ERR_CUDA, loudly
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_state_dict_keys_match_reference(name):
+    from esmstereo_b200 import __models__
+    cfg = golden_config(name)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = __models__[cfg["model"]](192, cfg["gwc"], cfg["norm_correlation"], cfg["backbone"], cfg["cv_scale"])
+    mine = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert mine == cfg["keys"]
+
+
+def test_constructor_contract():
+    from esmstereo_b200 import __models__
+    assert set(__models__) == {"ESMStereo", "ESMStereo_trt", "ESMStereo_confidence"}
+    with pytest.raises(NameError):  # the reference's `pirnt` typo path, ESMStereo.py:599
+        __models__["ESMStereo"](192, True, False, "efficientnet_b2", 5)
