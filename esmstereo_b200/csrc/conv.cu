@@ -20,6 +20,8 @@
 
 #include <string.h>
 
+#include <type_traits>
+
 namespace esm {
 
 struct ConvK {
@@ -49,6 +51,7 @@ struct ConvK {
   int TWG, TH, TD, slots, nthreads;
   int ID, IH, IWP;
   int tilesW, tilesH, tilesD;
+  int cosplit, COP;  // output channels are split over `cosplit` CTAs of COP (padded) channels each
 };
 
 template <int KW, int S, int COG, int CK>
@@ -57,7 +60,7 @@ __global__ void __launch_bounds__(320, 2) conv_kernel(const __grid_constant__ Co
   constexpr int NV = 4;
   constexpr int XN = (NV - 1) * S + KW;
   constexpr int XL = (XN + 3) / 4 * 4;
-  constexpr int NP = 4;  // max fill positions per thread per plane (host guarantees plane <= NP*nthreads)
+  constexpr int NP = 4;  // fill positions per thread per pass over a (channel, depth) plane
 
   const int tid = threadIdx.x;
   const int NT = p.nthreads;
@@ -68,8 +71,9 @@ __global__ void __launch_bounds__(320, 2) conv_kernel(const __grid_constant__ Co
   int pd = p.pd, ph = p.ph, pw = p.pw;
   int osd = 1, osh = 1, osw = 1;
   const float* wbase = p.weight;
+  const int co_base = (blockIdx.z % p.cosplit) * p.COP;
   if (p.transposed) {
-    const int z = blockIdx.z;
+    const int z = blockIdx.z / p.cosplit;
     pz_w = z & 1;
     pz_h = (z >> 1) & 1;
     pz_d = (p.phases_d == 2) ? ((z >> 2) & 1) : 0;
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(320, 2) conv_kernel(const __grid_constant__ Co
   const int ID = p.ID, IH = p.IH, IWP = p.IWP;
   const int plane = IH * IWP;
   const int chan_stride = ID * plane;
-  const int COP = p.CoutPad;
+  const int COP = p.COP;
   const int taps = p.KD * p.KH * KW;
   float* s_in = smem;
   float* s_w = smem + CK * chan_stride;
@@ -120,12 +124,12 @@ __global__ void __launch_bounds__(320, 2) conv_kernel(const __grid_constant__ Co
   for (int c0 = 0; c0 < p.Cin; c0 += CK) {
     __syncthreads();
     // ---------------- stage CK input channels (brick + halo) ----------------
-    {
+    for (int pb = 0; pb < plane; pb += NP * NT) {
       int hh[NP], ww[NP];
       bool ok[NP];
 #pragma unroll
       for (int k = 0; k < NP; ++k) {
-        const int pos = tid + k * NT;
+        const int pos = pb + tid + k * NT;
         const int hy = pos / IWP;
         const int col = pos - hy * IWP;
         hh[k] = ih0 + hy;
@@ -164,11 +168,11 @@ __global__ void __launch_bounds__(320, 2) conv_kernel(const __grid_constant__ Co
         for (int dz = 0; dz < ID; ++dz) {
           const int d = id0 + dz;
           const bool dvalid = cvalid && d >= 0 && d < p.Din;
-          float* dst = s_in + (c * ID + dz) * plane;
+          float* dst = s_in + (c * ID + dz) * plane + pb;
 #pragma unroll
           for (int k = 0; k < NP; ++k) {
             const int pos = tid + k * NT;
-            if (pos < plane) {
+            if (pb + pos < plane) {
               float v = 0.f;
               if (dvalid && ok[k]) {
                 if (p.src_mode == ESM_SRC_GWC) {
@@ -190,14 +194,22 @@ __global__ void __launch_bounds__(320, 2) conv_kernel(const __grid_constant__ Co
           }
         }
       }
+    }
+    {
       // ---------------- stage the matching weights ----------------
-      const int row_f4 = CK * COP / 4;  // float4 per tap
-      const float4* wsrc = reinterpret_cast<const float4*>(wbase);
-      float4* wdst = reinterpret_cast<float4*>(s_w);
-      for (int i = tid; i < taps * row_f4; i += NT) {
-        const int tap = i / row_f4;
-        const int r = i - tap * row_f4;
-        wdst[i] = __ldg(wsrc + ((long long)(tap * p.CinPad + c0) * COP) / 4 + r);
+      // rows of COP floats per (tap, channel); 16-byte copies, 8-byte ones for the COG=2 (Cout<=2) layout
+      using wvec_t = typename std::conditional<COG >= 4, float4, float2>::type;
+      constexpr int WV = sizeof(wvec_t) / sizeof(float);
+      const int copv = COP / WV;
+      const int row_v = CK * copv;
+      const wvec_t* wsrc = reinterpret_cast<const wvec_t*>(wbase);
+      wvec_t* wdst = reinterpret_cast<wvec_t*>(s_w);
+      for (int i = tid; i < taps * row_v; i += NT) {
+        const int tap = i / row_v;
+        const int rr = i - tap * row_v;
+        const int c = rr / copv;
+        const int r = rr - c * copv;
+        wdst[i] = __ldg(wsrc + ((long long)(tap * p.CinPad + c0 + c) * p.CoutPad + co_base) / WV + r);
       }
     }
     __syncthreads();
@@ -256,7 +268,7 @@ __global__ void __launch_bounds__(320, 2) conv_kernel(const __grid_constant__ Co
   if (od >= p.OD || oh >= p.OH) return;
 #pragma unroll
   for (int j = 0; j < COG; ++j) {
-    const int co = cog * COG + j;
+    const int co = co_base + cog * COG + j;
     if (co >= p.Cout) break;
     const float sc = p.scale ? __ldg(p.scale + co) : 1.f;
     const float sh = p.shift ? __ldg(p.shift + co) : 0.f;
@@ -396,7 +408,7 @@ struct Tiling {
 };
 
 static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int KD, int S, int CK, int COP,
-                          Tiling* out) {
+                          size_t smem_limit, Tiling* out) {
   int target = 256 / ncog;
   target = (target / 32) * 32;
   if (target < 32) target = 32;
@@ -421,11 +433,9 @@ static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int 
           const int want = (4 * TWG) % 32;  // rows of an 8-lane LDS.128 phase land on distinct banks
           while (IWP % 32 != want) IWP += 4;
         }
-        const int nthreads = slots * ncog;
-        if (IH * IWP > 4 * nthreads) continue;
         const double halo = (double)ID * IH * IWP / ((double)TD * TH * TW * S * S * (Jd == 1 ? 1 : S));
         const size_t smem = ((size_t)CK * ID * IH * IWP + (size_t)KD * KH * KW * CK * COP) * sizeof(float);
-        if (smem > 110 * 1024) continue;
+        if (smem > smem_limit) continue;
         // compute waste dominates; prefer bigger CTAs (fewer fills per FLOP) and small halos
         const double cost = waste * (1.0 + 0.05 * halo) * (1.0 + 8.0 / slots);
         if (cost < best) {
@@ -584,14 +594,22 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
 
   const int COG = g.CoutPad == 2 ? 2 : 8;
   const int CK = g.CinPad == 1 ? 1 : 8;
-  const int ncog = g.CoutPad / COG;
+  // a CTA owns at most 80 output channels (10 channel groups x >=32 voxel slots <= 320 threads)
+  int cosplit = 1;
+  while (g.CoutPad / cosplit > 80 || g.CoutPad % cosplit || (g.CoutPad / cosplit) % COG) ++cosplit;
+  const int COP = g.CoutPad / cosplit;
+  const int ncog = COP / COG;
   // logical per-phase output extent
   const int Jw = d->transposed ? ceil_div(d->Wout, 2) : d->Wout;
   const int Jh = d->transposed ? ceil_div(d->Hout, 2) : d->Hout;
   const int Jd = (d->transposed && g.phases_d == 2) ? ceil_div(d->Dout, 2) : d->Dout;
   Tiling tl;
-  ESM_REQUIRE(choose_tiling(Jw, Jh, Jd, ncog, g.KW, g.KH, g.KD, S, CK, g.CoutPad, &tl),
-              "conv: no tiling for Cout=%d k=(%d,%d,%d)", d->Cout, d->kd, d->kh, d->kw);
+  // prefer tiles that leave room for 2 CTAs per SM (fill of one overlaps the math of the other)
+  bool tiled = choose_tiling(Jw, Jh, Jd, ncog, g.KW, g.KH, g.KD, S, CK, COP, 110 * 1024, &tl) ||
+               choose_tiling(Jw, Jh, Jd, ncog, g.KW, g.KH, g.KD, S, CK, COP, 220 * 1024, &tl);
+  ESM_REQUIRE(tiled, "conv: no tiling for Cout=%d k=(%d,%d,%d)", d->Cout, d->kd, d->kh, d->kw);
+  k.cosplit = cosplit;
+  k.COP = COP;
   k.TWG = tl.TWG;
   k.TH = tl.TH;
   k.TD = tl.TD;
@@ -612,7 +630,7 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   }
   const long long ntiles = (long long)k.tilesW * k.tilesH * k.tilesD;
   ESM_REQUIRE(ntiles < (1ll << 31) && d->B <= 65535, "conv: grid too large");
-  dim3 grid((unsigned)ntiles, (unsigned)d->B, (unsigned)g.phases);
+  dim3 grid((unsigned)ntiles, (unsigned)d->B, (unsigned)(g.phases * cosplit));
   fn<<<grid, k.nthreads, tl.smem, (cudaStream_t)stream>>>(k);
   return check_launch("conv");
 }

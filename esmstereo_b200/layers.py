@@ -358,6 +358,7 @@ class LAFNet_ESM(nn.Module):
         nn.init.constant_(self.scale_bn3.weight, 0)  # ":641-642"
         nn.init.constant_(self.scale_bn3.bias, 0)
         self._caches = {}
+        self.capture = None  # set to {} to record stages (tests)
 
     def _cb(self, conv: str, bn: str, x, act: Optional[str] = "relu", **fused):
         cache = self._caches.setdefault((conv, bn), _Packed())
@@ -395,6 +396,8 @@ class LAFNet_ESM(nn.Module):
             return w, sc, sh
 
         w, sc, sh = cache.get(ts, build)
+        if self.capture is not None:
+            self.capture.update(conf_top7=ops.laf_cost_top7(cost), conf_feat=feat, conf_scale=scale)
         feat = ops.laf_sample_embed(feat, scale, w, sc, sh)
         out = ops.fill_(torch.empty_like(disp), 0.5)
         for it in (1, 2, 3):  # shared convs, per-iteration BN (":725-739")
@@ -402,4 +405,6 @@ class LAFNet_ESM(nn.Module):
             t = self._cb("fusion_conv2", "fusion_bn2_iter%d" % it, t)
             out = self._cb("fusion_conv3", "fusion_bn3_iter%d" % it, t)
         out4 = self.conf_up4(left_f1x, out)
+        if self.capture is not None:
+            self.capture.update(conf_embed=feat, conf_init=out, conf_4=out4)
         return self.conf_up1(left_f2x, out4, final_act="sigmoid")

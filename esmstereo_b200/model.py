@@ -34,13 +34,15 @@ def _exact_fp32(enabled: bool):
     if not enabled:
         yield
         return
-    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True  # cuDNN's transposed convs otherwise pick atomics-based kernels
     try:
         yield
     finally:
-        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32,
+         torch.backends.cudnn.deterministic) = old
 
 
 class _ESMStereoBase(nn.Module):
@@ -109,8 +111,9 @@ class _ESMStereoBase(nn.Module):
         return fl, [s[:B] for s in stems], match[:B].contiguous(), match[B:].contiguous(), att, extra
 
     # ------------------------------------------------------------------ hot path (libesm_b200)
-    def _hot_path(self, fl, stems, mL, mR, att, extra, want_scales: bool):
-        s, D = self.vol_size, self.maxdisp // self.vol_size
+    def _aggregate_cost(self, mL, mR, att) -> torch.Tensor:
+        """Descriptors -> aggregated cost [B,D,h,w]: volume, stem, agg, 3D hourglass (ESMStereo.py:700-716)."""
+        D = self.maxdisp // self.vol_size
         if self.norm_correlation:
             vol = ops.build_norm_correlation_volume(mL, mR, D)
             vol = self.corr_stem(vol, out_mul=att)  # `corr_stem(volume) * att` for cv16 (:703)
@@ -122,26 +125,31 @@ class _ESMStereoBase(nn.Module):
                 vol = self.group_stem(vol, in_mul=att)
         stem = vol
         vol = self.agg(vol)
-        cost = self.aggregation_out(vol)  # [B,1,D,h,w]
-        cost2d = cost[:, 0]
+        cost = self.aggregation_out(vol)[:, 0]
         if self.capture is not None:
-            self.capture.update(match_left=mL, match_right=mR, stem=stem, agg=vol, cost=cost2d)
+            self.capture.update(match_left=mL, match_right=mR, stem=stem, agg=vol, cost=cost)
+        return cost
+
+    def _disparity_from_cost(self, cost, fl, stems, extra, want_scales: bool):
+        """Aggregated cost -> (initial disparity, upsampled scales): regression + ShuffleMixer
+        upsampling (ESMStereo.py:718-745)."""
+        s, D = self.vol_size, self.maxdisp // self.vol_size
         final = 1.0 if want_scales else 4.0  # every output is *4 regardless of scale (:737-745)
         if s == 4:
-            init = ops.regression_top2(cost2d)
+            init = ops.regression_top2(cost)
             scales = self.upsample_module(fl[1], fl[0], stems[0], init, out_scale=final)
         elif s == 8:
-            init = ops.disparity_regression(cost2d, D).unsqueeze(1)
+            init = ops.disparity_regression(cost, D).unsqueeze(1)
             scales = self.upsample_module(fl[2], fl[1], fl[0], stems[0], init, out_scale=final)
         else:
-            init = ops.disparity_regression(cost2d, D).unsqueeze(1)
+            init = ops.disparity_regression(cost, D).unsqueeze(1)
             f2, f0 = extra
             scales = self.upsample_module(fl[2], f2, fl[1], f0, init, out_scale=final)
         if self.capture is not None:
             self.capture.update(init_pred=init)
             if s == 4:
-                self.capture["top2_idx"] = ops.regression_top2(cost2d, return_indices=True)[1]
-        return cost2d, init, scales
+                self.capture["top2_idx"] = ops.regression_top2(cost, return_indices=True)[1]
+        return init, scales
 
     def _run(self, left: torch.Tensor, right: torch.Tensor, want_scales: bool, want_conf: bool):
         if not (left.is_cuda and right.is_cuda):
@@ -151,7 +159,8 @@ class _ESMStereoBase(nn.Module):
         with torch.no_grad():
             left, right = left.float().contiguous(), right.float().contiguous()
             fl, stems, mL, mR, att, extra = self._features_2d(left, right)
-            cost, init, scales = self._hot_path(fl, stems, mL, mR, att, extra, want_scales)
+            cost = self._aggregate_cost(mL, mR, att)
+            init, scales = self._disparity_from_cost(cost, fl, stems, extra, want_scales)
             conf = None
             if want_conf:
                 conf = self.confidence_net(cost, init, mL, fl[3], fl[1]).squeeze(1)
