@@ -18,8 +18,11 @@
 // CK input channels of the brick + halo in shared memory together with the matching weights.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <type_traits>
 
 namespace esm {
@@ -52,78 +55,131 @@ struct ConvK {
   int ID, IH, IWP;
   int tilesW, tilesH, tilesD;
   int cosplit, COP;  // output channels are split over `cosplit` CTAs of COP (padded) channels each
+  int phases, total_work, IWR;
 };
 
-template <int KW, int S, int COG, int CK>
-__global__ void __launch_bounds__(320, 2) conv_kernel(const __grid_constant__ ConvK p) {
+// ---- cp.async helpers (LDGSTS): global -> shared without register staging; src_size 0 zero-fills ----
+__device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gsrc, bool pred) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = pred ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(n));
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_vec(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+struct TileCtx {
+  int b, co_base, tileW, tileH, tileD;
+  int pz_d, pz_h, pz_w;     // transposed-conv phase
+  int pd, ph, pw;           // effective padding of this phase
+  const float* wbase;
+};
+
+__device__ __forceinline__ TileCtx decode_work(const ConvK& p, int w) {
+  TileCtx c;
+  const int tiles = p.tilesW * p.tilesH * p.tilesD;
+  int t = w % tiles;
+  int r = w / tiles;
+  c.tileW = t % p.tilesW;
+  t /= p.tilesW;
+  c.tileH = t % p.tilesH;
+  c.tileD = t / p.tilesH;
+  c.co_base = (r % p.cosplit) * p.COP;
+  r /= p.cosplit;
+  const int z = r % p.phases;
+  c.b = r / p.phases;
+  c.pz_d = c.pz_h = c.pz_w = 0;
+  c.pd = p.pd;
+  c.ph = p.ph;
+  c.pw = p.pw;
+  c.wbase = p.weight;
+  if (p.transposed) {
+    c.pz_w = z & 1;
+    c.pz_h = (z >> 1) & 1;
+    c.pz_d = (p.phases_d == 2) ? ((z >> 2) & 1) : 0;
+    c.pw = 1 - c.pz_w;
+    c.ph = 1 - c.pz_h;
+    c.pd = (p.phases_d == 2) ? 1 - c.pz_d : 0;
+    c.wbase += (long long)z * p.phase_stride;
+  }
+  return c;
+}
+
+// Persistent, double-buffered direct convolution.  Work items (tile, channel chunk) stream through a
+// 2-stage shared-memory ring filled by cp.async: the loads of item i+1 are in flight while item i
+// runs on the FP32 pipe.  GWC=true: the "input" voxels are group-wise correlations; the left/right
+// feature rows of the next chunk are cp.async-staged and turned into the correlation tile
+// smem -> smem (the D x H x W volume never exists in HBM).
+template <int KW, int S, int COG, int CK, bool GWC>
+__global__ void __launch_bounds__(320, 1) conv_kernel(const __grid_constant__ ConvK p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int NV = 4;
   constexpr int XN = (NV - 1) * S + KW;
   constexpr int XL = (XN + 3) / 4 * 4;
-  constexpr int NP = 4;  // fill positions per thread per pass over a (channel, depth) plane
+  constexpr int NP = 4;  // fill positions per thread per pass over a plane
 
   const int tid = threadIdx.x;
   const int NT = p.nthreads;
-  const int b = blockIdx.y;
-
-  // ---- phase (transposed conv) ----
-  int pz_d = 0, pz_h = 0, pz_w = 0;
-  int pd = p.pd, ph = p.ph, pw = p.pw;
-  int osd = 1, osh = 1, osw = 1;
-  const float* wbase = p.weight;
-  const int co_base = (blockIdx.z % p.cosplit) * p.COP;
-  if (p.transposed) {
-    const int z = blockIdx.z / p.cosplit;
-    pz_w = z & 1;
-    pz_h = (z >> 1) & 1;
-    pz_d = (p.phases_d == 2) ? ((z >> 2) & 1) : 0;
-    pw = 1 - pz_w;
-    ph = 1 - pz_h;
-    pd = (p.phases_d == 2) ? 1 - pz_d : 0;
-    osw = 2;
-    osh = 2;
-    osd = (p.phases_d == 2) ? 2 : 1;
-    wbase += (long long)z * p.phase_stride;
-  }
-
-  // ---- tile ----
-  int t = blockIdx.x;
-  const int tileW = t % p.tilesW;
-  t /= p.tilesW;
-  const int tileH = t % p.tilesH;
-  const int tileD = t / p.tilesH;
-  const int TW = p.TWG * NV;
-  const int iw0 = tileW * TW * S - pw;
-  const int ih0 = tileH * p.TH * S - ph;
-  const int id0 = tileD * p.TD * S - pd;
+  const int ID = p.ID, IH = p.IH, IWP = p.IWP;
+  const int plane = IH * IWP;
+  const int chan_stride = ID * plane;
+  const int COP = p.COP;
+  const int taps = p.KD * p.KH * KW;
+  const int in_elems = CK * chan_stride;
+  const int w_elems = taps * CK * COP;
+  // smem carve-up: [in0][in1][w0][w1][w2 (GWC)][L staging][R staging]
+  float* s_in0 = smem;
+  float* s_w0 = smem + 2 * in_elems;
+  const int IWR = p.IWR;                  // GWC: right staging row pitch
+  float* s_L = s_w0 + 3 * w_elems;        // GWC only
+  float* s_R = s_L + CK * p.cpg * plane;  // GWC only: [CK*cpg][IH][IWR]
 
   const int slot = tid % p.slots;
   const int cog = tid / p.slots;
   const int twg = slot % p.TWG;
   const int th = (slot / p.TWG) % p.TH;
   const int td = slot / (p.TWG * p.TH);
+  const int TW = p.TWG * NV;
+  const int xoff = ((td * S) * IH + th * S) * IWP + twg * NV * S;
 
-  const int ID = p.ID, IH = p.IH, IWP = p.IWP;
-  const int plane = IH * IWP;
-  const int chan_stride = ID * plane;
-  const int COP = p.COP;
-  const int taps = p.KD * p.KH * KW;
-  float* s_in = smem;
-  float* s_w = smem + CK * chan_stride;
+  const int nch = (p.Cin + CK - 1) / CK;
+  const int my_tiles = (p.total_work > (int)blockIdx.x) ? (p.total_work - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_items = my_tiles * nch;
 
-  float2 acc[NV][COG / 2];
-#pragma unroll
-  for (int v = 0; v < NV; ++v)
-#pragma unroll
-    for (int j = 0; j < COG / 2; ++j) acc[v][j] = make_float2(0.f, 0.f);
+  // ---------------- loaders ----------------
+  auto load_weights = [&](int item, float* dst) {
+    const int w = blockIdx.x + (item / nch) * gridDim.x;
+    const int c0 = (item % nch) * CK;
+    const TileCtx t = decode_work(p, w);
+    constexpr int WB = (COG >= 4) ? 16 : 8;
+    constexpr int WV = WB / 4;
+    const int copv = COP / WV;
+    const int row_v = CK * copv;
+    for (int i = tid; i < taps * row_v; i += NT) {
+      const int tap = i / row_v;
+      const int rr = i - tap * row_v;
+      const int c = rr / copv;
+      const int r = rr - c * copv;
+      cp_async_vec<WB>(dst + (long long)i * WV,
+                       t.wbase + ((long long)(tap * p.CinPad + c0 + c) * p.CoutPad + t.co_base) + r * WV);
+    }
+  };
 
-  const float* xin = s_in + ((td * S) * IH + th * S) * IWP + twg * NV * S;
-  const float* wthr = s_w + cog * COG;
-  const bool compute_thread = tid < p.slots * (COP / COG);
-
-  for (int c0 = 0; c0 < p.Cin; c0 += CK) {
-    __syncthreads();
-    // ---------------- stage CK input channels (brick + halo) ----------------
+  auto load_inputs = [&](int item, float* dst) {  // ESM_SRC_TENSORS: brick + halo of CK channels
+    const int w = blockIdx.x + (item / nch) * gridDim.x;
+    const int c0 = (item % nch) * CK;
+    const TileCtx t = decode_work(p, w);
+    const int iw0 = t.tileW * TW * S - t.pw;
+    const int ih0 = t.tileH * p.TH * S - t.ph;
+    const int id0 = t.tileD * p.TD * S - t.pd;
     for (int pb = 0; pb < plane; pb += NP * NT) {
       int hh[NP], ww[NP];
       bool ok[NP];
@@ -136,85 +192,196 @@ __global__ void __launch_bounds__(320, 2) conv_kernel(const __grid_constant__ Co
         ww[k] = iw0 + col;
         ok[k] = (pos < plane) && (hh[k] >= 0) && (hh[k] < p.Hin) && (ww[k] >= 0) && (ww[k] < p.Win);
       }
+#pragma unroll 1
       for (int c = 0; c < CK; ++c) {
         const int cc = c0 + c;
         const bool cvalid = cc < p.Cin;
-        // locate the source tensor of channel cc (ESM_SRC_TENSORS)
-        const float* sbase = nullptr;
+        const float* sbase = p.src[0].ptr;
         long long sD = 0, sH = 0;
-        const float* rbase = nullptr;  // gwc: right features
-        long long sC = 0;
         if (cvalid) {
-          if (p.src_mode == ESM_SRC_GWC) {
-            sbase = p.src[0].ptr + (long long)b * p.src[0].sB + (long long)cc * p.cpg * p.src[0].sC;
-            rbase = p.src[1].ptr + (long long)b * p.src[1].sB + (long long)cc * p.cpg * p.src[1].sC;
-            sH = p.src[0].sH;
-            sC = p.src[0].sC;
-          } else {
-            int rel = cc, k = 0;
-            while (k < p.nsrc - 1 && rel >= p.src[k].C) {
-              rel -= p.src[k].C;
-              ++k;
+          int rel = cc;
+          const esm_src_t* sp = &p.src[0];
+          if (p.nsrc > 1 && rel >= p.src[0].C) {
+            rel -= p.src[0].C;
+            sp = &p.src[1];
+            if (p.nsrc > 2 && rel >= p.src[1].C) {
+              rel -= p.src[1].C;
+              sp = &p.src[2];
             }
-            sbase = p.src[k].ptr + (long long)b * p.src[k].sB + (long long)rel * p.src[k].sC;
-            sD = p.src[k].sD;
-            sH = p.src[k].sH;
           }
+          sbase = sp->ptr + (long long)t.b * sp->sB + (long long)rel * sp->sC;
+          sD = sp->sD;
+          sH = sp->sH;
         }
-        const float* mbase = (p.in_mul && cvalid) ? p.in_mul + (long long)b * p.imB + (long long)cc * p.imC : nullptr;
         long long off[NP];
 #pragma unroll
-        for (int k = 0; k < NP; ++k) off[k] = (long long)hh[k] * sH + ww[k];
+        for (int k = 0; k < NP; ++k) off[k] = ok[k] ? (long long)hh[k] * sH + ww[k] : 0;
+#pragma unroll 1
         for (int dz = 0; dz < ID; ++dz) {
           const int d = id0 + dz;
           const bool dvalid = cvalid && d >= 0 && d < p.Din;
-          float* dst = s_in + (c * ID + dz) * plane + pb;
+          const float* sd = sbase + (dvalid ? (long long)d * sD : 0);
+          float* drow = dst + (c * ID + dz) * plane + pb + tid;
 #pragma unroll
-          for (int k = 0; k < NP; ++k) {
-            const int pos = tid + k * NT;
-            if (pb + pos < plane) {
-              float v = 0.f;
-              if (dvalid && ok[k]) {
-                if (p.src_mode == ESM_SRC_GWC) {
-                  const int wr = ww[k] - d;  // right-image column, submodule.py:156
-                  if (wr >= 0) {
-                    const long long o = off[k];
-                    float s = 0.f;
-                    for (int q = 0; q < p.cpg; ++q)  // un-contracted: matches (fea1*fea2).mean(2), submodule.py:147
-                      s = __fadd_rn(s, __fmul_rn(__ldg(sbase + q * sC + o), __ldg(rbase + q * sC + o - d)));
-                    v = s / (float)p.cpg;
-                  }
-                } else {
-                  v = __ldg(sbase + (long long)d * sD + off[k]);
-                }
-                if (mbase) v *= __ldg(mbase + (long long)hh[k] * p.imH + ww[k]);
-              }
-              dst[pos] = v;
-            }
-          }
+          for (int k = 0; k < NP; ++k)
+            if (pb + tid + k * NT < plane) cp_async_4(drow + k * NT, sd + off[k], dvalid && ok[k]);
         }
       }
     }
-    {
-      // ---------------- stage the matching weights ----------------
-      // rows of COP floats per (tap, channel); 16-byte copies, 8-byte ones for the COG=2 (Cout<=2) layout
-      using wvec_t = typename std::conditional<COG >= 4, float4, float2>::type;
-      constexpr int WV = sizeof(wvec_t) / sizeof(float);
-      const int copv = COP / WV;
-      const int row_v = CK * copv;
-      const wvec_t* wsrc = reinterpret_cast<const wvec_t*>(wbase);
-      wvec_t* wdst = reinterpret_cast<wvec_t*>(s_w);
-      for (int i = tid; i < taps * row_v; i += NT) {
-        const int tap = i / row_v;
-        const int rr = i - tap * row_v;
-        const int c = rr / copv;
-        const int r = rr - c * copv;
-        wdst[i] = __ldg(wsrc + ((long long)(tap * p.CinPad + c0 + c) * p.CoutPad + co_base) / WV + r);
+  };
+
+  auto load_lr = [&](int item) {  // ESM_SRC_GWC: left rows [CK*cpg][IH][IWP], right rows [CK*cpg][IH][IWR]
+    const int w = blockIdx.x + (item / nch) * gridDim.x;
+    const int c0 = (item % nch) * CK;
+    const TileCtx t = decode_work(p, w);
+    const int iw0 = t.tileW * TW * S - t.pw;
+    const int ih0 = t.tileH * p.TH * S - t.ph;
+    const int id0 = t.tileD * p.TD * S - t.pd;
+    const int nchan = CK * p.cpg;
+    const int fc0 = c0 * p.cpg;  // first feature channel of this chunk of groups
+    const int Cfeat = p.Cin * p.cpg;
+    const float* Lb = p.src[0].ptr + (long long)t.b * p.src[0].sB;
+    const float* Rb = p.src[1].ptr + (long long)t.b * p.src[1].sB;
+    const long long sC = p.src[0].sC, sH = p.src[0].sH;
+    for (int i = tid; i < nchan * plane; i += NT) {
+      const int c = i / plane;
+      const int rem = i - c * plane;
+      const int hy = rem / IWP;
+      const int col = rem - hy * IWP;
+      const int h = ih0 + hy, x = iw0 + col;
+      const bool ok = (fc0 + c < Cfeat) && h >= 0 && h < p.Hin && x >= 0 && x < p.Win;
+      cp_async_4(s_L + i, Lb + (ok ? (long long)(fc0 + c) * sC + (long long)h * sH + x : 0), ok);
+    }
+    const int rw0 = iw0 - id0 - (ID - 1);  // right-image column of staging column 0
+    const int rplane = IH * IWR;
+    for (int i = tid; i < nchan * rplane; i += NT) {
+      const int c = i / rplane;
+      const int rem = i - c * rplane;
+      const int hy = rem / IWR;
+      const int col = rem - hy * IWR;
+      const int h = ih0 + hy, x = rw0 + col;
+      const bool ok = (fc0 + c < Cfeat) && h >= 0 && h < p.Hin && x >= 0 && x < p.Win;
+      cp_async_4(s_R + i, Rb + (ok ? (long long)(fc0 + c) * sC + (long long)h * sH + x : 0), ok);
+    }
+  };
+
+  auto build_volume = [&](int item, float* dst) {  // correlation tile from the staged rows (smem -> smem)
+    const int w = blockIdx.x + (item / nch) * gridDim.x;
+    const int c0 = (item % nch) * CK;
+    const TileCtx t = decode_work(p, w);
+    const int iw0 = t.tileW * TW * S - t.pw;
+    const int ih0 = t.tileH * p.TH * S - t.ph;
+    const int id0 = t.tileD * p.TD * S - t.pd;
+    const float* mb = p.in_mul ? p.in_mul + (long long)t.b * p.imB : nullptr;
+    const float inv = 1.0f / (float)p.cpg;
+    const bool pow2 = (p.cpg & (p.cpg - 1)) == 0;
+    for (int i = tid; i < CK * plane; i += NT) {
+      const int g = i / plane;
+      const int rem = i - g * plane;
+      const int hy = rem / IWP;
+      const int col = rem - hy * IWP;
+      const int h = ih0 + hy, x = iw0 + col;
+      const bool ok = (c0 + g < p.Cin) && h >= 0 && h < p.Hin && x >= 0 && x < p.Win;
+      float m = 1.f;
+      if (mb && ok) m = __ldg(mb + (long long)(c0 + g) * p.imC + (long long)h * p.imH + x);
+      const float* lp = s_L + (g * p.cpg) * plane + rem;
+      const float* rp = s_R + (g * p.cpg) * (IH * IWR) + hy * IWR + col + (ID - 1);
+      for (int dz = 0; dz < ID; ++dz) {
+        const int d = id0 + dz;
+        float v = 0.f;
+        if (ok && d >= 0 && d < p.Din && x - d >= 0) {
+          float s = 0.f;
+          for (int q = 0; q < p.cpg; ++q)  // un-contracted: (fea1*fea2).mean(2), submodule.py:147
+            s = __fadd_rn(s, __fmul_rn(lp[q * plane], rp[q * IH * IWR - dz]));
+          v = pow2 ? s * inv : s / (float)p.cpg;
+          v *= m;
+        }
+        dst[(g * ID + dz) * plane + rem] = v;
       }
     }
-    __syncthreads();
+  };
+
+  auto scale_inputs = [&](int item, float* buf) {  // buf[c][dz][hy][col] *= in_mul[b, c0+c, 0, h, x]
+    const int w = blockIdx.x + (item / nch) * gridDim.x;
+    const int c0 = (item % nch) * CK;
+    const TileCtx t = decode_work(p, w);
+    const int iw0 = t.tileW * TW * S - t.pw;
+    const int ih0 = t.tileH * p.TH * S - t.ph;
+    const float* mb = p.in_mul + (long long)t.b * p.imB;
+    for (int i = tid; i < CK * plane; i += NT) {
+      const int c = i / plane;
+      const int rem = i - c * plane;
+      const int hy = rem / IWP;
+      const int col = rem - hy * IWP;
+      const int h = ih0 + hy, x = iw0 + col;
+      if ((c0 + c < p.Cin) && h >= 0 && h < p.Hin && x >= 0 && x < p.Win) {
+        const float m = __ldg(mb + (long long)(c0 + c) * p.imC + (long long)h * p.imH + x);
+        for (int dz = 0; dz < ID; ++dz) buf[(c * ID + dz) * plane + rem] *= m;
+      }
+    }
+  };
+
+  float2 acc[NV][COG / 2];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < COG / 2; ++j) acc[v][j] = make_float2(0.f, 0.f);
+
+  // ---------------- prologue ----------------
+  if (n_items > 0) {
+    if (GWC) {
+      load_weights(0, s_w0);
+      load_lr(0);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncthreads();
+      build_volume(0, s_in0);
+      __syncthreads();
+      if (n_items > 1) {
+        load_weights(1, s_w0 + w_elems);
+        load_lr(1);
+      }
+      cp_async_commit();
+    } else {
+      load_weights(0, s_w0);
+      load_inputs(0, s_in0);
+      cp_async_commit();
+    }
+  }
+
+  for (int item = 0; item < n_items; ++item) {
+    const float* s_in = s_in0 + (item & 1) * in_elems;
+    const float* s_w;
+    if (GWC) {
+      s_w = s_w0 + (item % 3) * w_elems;
+      cp_async_wait<0>();  // rows + weights of item+1 have landed
+      __syncthreads();     // ...and every warp is done reading V[(item+1)&1] (FFMA2 of item-1)
+      if (item + 1 < n_items) build_volume(item + 1, s_in0 + ((item + 1) & 1) * in_elems);
+      __syncthreads();     // staging rows are free again
+      if (item + 2 < n_items) {
+        load_weights(item + 2, s_w0 + ((item + 2) % 3) * w_elems);
+        load_lr(item + 2);
+      }
+      cp_async_commit();
+    } else {
+      s_w = s_w0 + (item & 1) * w_elems;
+      if (item + 1 < n_items) {
+        load_weights(item + 1, s_w0 + ((item + 1) & 1) * w_elems);
+        load_inputs(item + 1, s_in0 + ((item + 1) & 1) * in_elems);
+      }
+      cp_async_commit();
+      cp_async_wait<1>();  // everything but the group just committed -> item's data has landed
+      __syncthreads();
+      if (p.in_mul) {  // rare (unfused cv16 volume * att): scale the staged brick in place
+        scale_inputs(item, s_in0 + (item & 1) * in_elems);
+        __syncthreads();
+      }
+    }
+
     // ---------------- FFMA2 inner product ----------------
-    if (compute_thread) {
+    {
+      const float* xin = s_in + xoff;
+      const float* wthr = s_w + cog * COG;
       for (int kd = 0; kd < p.KD; ++kd) {
         for (int kh = 0; kh < p.KH; ++kh) {
           const float* xr = xin + (kd * IH + kh) * IWP;
@@ -256,67 +423,79 @@ __global__ void __launch_bounds__(320, 2) conv_kernel(const __grid_constant__ Co
         }
       }
     }
-  }
 
-  // ---------------- epilogue ----------------
-  if (!compute_thread) return;
-  const int jd = tileD * p.TD + td;
-  const int jh = tileH * p.TH + th;
-  const int jw0 = tileW * TW + twg * NV;
-  const int od = jd * osd + pz_d;
-  const int oh = jh * osh + pz_h;
-  if (od >= p.OD || oh >= p.OH) return;
+    // ---------------- epilogue (last channel chunk of a tile) ----------------
+    if ((item % nch) == nch - 1) {
+      const TileCtx t = decode_work(p, blockIdx.x + (item / nch) * gridDim.x);
+      const int osd = (p.transposed && p.phases_d == 2) ? 2 : 1;
+      const int osw = p.transposed ? 2 : 1;
+      const int jd = t.tileD * p.TD + td;
+      const int jh = t.tileH * p.TH + th;
+      const int jw0 = t.tileW * TW + twg * NV;
+      const int od = jd * osd + t.pz_d;
+      const int oh = jh * osw + t.pz_h;
+      const int b = t.b;
+      if (od < p.OD && oh < p.OH) {
 #pragma unroll
-  for (int j = 0; j < COG; ++j) {
-    const int co = co_base + cog * COG + j;
-    if (co >= p.Cout) break;
-    const float sc = p.scale ? __ldg(p.scale + co) : 1.f;
-    const float sh = p.shift ? __ldg(p.shift + co) : 0.f;
-    float r[NV];
+        for (int j = 0; j < COG; ++j) {
+          const int co = t.co_base + cog * COG + j;
+          if (co >= p.Cout) break;
+          const float sc = p.scale ? __ldg(p.scale + co) : 1.f;
+          const float sh = p.shift ? __ldg(p.shift + co) : 0.f;
+          float r[NV];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const float a = (j & 1) ? acc[v][j / 2].y : acc[v][j / 2].x;
-      r[v] = apply_act(fmaf(a, sc, sh), p.act);
-    }
-    if (p.ps == 0) {
-      const long long obase = (long long)b * p.oB + (long long)co * p.oC + (long long)od * p.oD + (long long)oh * p.oH;
-      const float* om = p.out_mul ? p.out_mul + (long long)b * p.omB + (long long)co * p.omC + (long long)oh * p.omH : nullptr;
+          for (int v = 0; v < NV; ++v) {
+            const float a = (j & 1) ? acc[v][j / 2].y : acc[v][j / 2].x;
+            r[v] = apply_act(fmaf(a, sc, sh), p.act);
+          }
+          if (p.ps == 0) {
+            const long long obase = (long long)b * p.oB + (long long)co * p.oC + (long long)od * p.oD + (long long)oh * p.oH;
+            const float* om = p.out_mul ? p.out_mul + (long long)b * p.omB + (long long)co * p.omC + (long long)oh * p.omH : nullptr;
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int ow = (jw0 + v) * osw + pz_w;
-        if (ow < p.OW) {
-          float y = r[v];
-          if (om) y *= __ldg(om + ow);
-          if (p.residual) y += __ldg(p.residual + obase + ow);
-          y = apply_act(y, p.act2) * p.out_scale;
-          r[v] = y;
+            for (int v = 0; v < NV; ++v) {
+              const int ow = (jw0 + v) * osw + t.pz_w;
+              if (ow < p.OW) {
+                float y = r[v];
+                if (om) y *= __ldg(om + ow);
+                if (p.residual) y += __ldg(p.residual + obase + ow);
+                y = apply_act(y, p.act2) * p.out_scale;
+                r[v] = y;
+              }
+            }
+            float* o = p.out + obase;
+            const int ow0 = jw0 * osw + t.pz_w;
+            if (osw == 1 && ow0 + NV <= p.OW && ((reinterpret_cast<uintptr_t>(o + ow0) & 15) == 0)) {
+              *reinterpret_cast<float4*>(o + ow0) = make_float4(r[0], r[1], r[2], r[3]);
+            } else {
+#pragma unroll
+              for (int v = 0; v < NV; ++v) {
+                const int ow = (jw0 + v) * osw + t.pz_w;
+                if (ow < p.OW) o[ow] = r[v];
+              }
+            }
+          } else {
+            // PixelShuffle(r): channel co -> (c, a, bb); out[c, oh*r + a, ow*r + bb]   (2D only)
+            const int rr = p.ps;
+            const int c = co / (rr * rr);
+            const int a = (co / rr) % rr;
+            const int bb = co % rr;
+            float* o = p.out + (long long)b * p.oB + (long long)c * p.oC + (long long)(oh * rr + a) * p.oH;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              const int ow = jw0 + v;
+              if (ow < p.OW) o[ow * rr + bb] = apply_act(r[v], p.act2) * p.out_scale;
+            }
+          }
         }
       }
-      float* o = p.out + obase;
-      const int ow0 = jw0 * osw + pz_w;
-      if (osw == 1 && ow0 + NV <= p.OW && ((reinterpret_cast<uintptr_t>(o + ow0) & 15) == 0)) {
-        *reinterpret_cast<float4*>(o + ow0) = make_float4(r[0], r[1], r[2], r[3]);
-      } else {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int ow = (jw0 + v) * osw + pz_w;
-          if (ow < p.OW) o[ow] = r[v];
-        }
-      }
-    } else {
-      // PixelShuffle(r): channel co -> (c, a, bb); out[c, oh*r + a, ow*r + bb]   (2D only)
-      const int rr = p.ps;
-      const int c = co / (rr * rr);
-      const int a = (co / rr) % rr;
-      const int bb = co % rr;
-      float* o = p.out + (long long)b * p.oB + (long long)c * p.oC + (long long)(oh * rr + a) * p.oH;
+      for (int v = 0; v < NV; ++v)
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int ow = jw0 + v;
-        if (ow < p.OW) o[ow * rr + bb] = apply_act(r[v], p.act2) * p.out_scale;
-      }
+        for (int j = 0; j < COG / 2; ++j) acc[v][j] = make_float2(0.f, 0.f);
     }
+    if (!GWC) __syncthreads();  // stage (item&1) may be refilled by the loads issued next iteration
   }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -403,20 +582,36 @@ static PackGeom pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transpo
 // host-side tiling + dispatch
 // ------------------------------------------------------------------------------------------
 struct Tiling {
-  int TWG, TH, TD, slots, IWP, ID, IH;
+  int TWG, TH, TD, slots, IWP, ID, IH, IWR;
   size_t smem;
 };
 
-static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int KD, int S, int CK, int COP,
-                          size_t smem_limit, Tiling* out) {
-  int target = 256 / ncog;
-  target = (target / 32) * 32;
-  if (target < 32) target = 32;
-  while (target * ncog > 320 && target > 32) target -= 32;
-  if (target * ncog > 320) return false;
-  double best = 1e30;
+static size_t conv_smem_bytes(int CK, int ID, int IH, int IWP, int taps, int COP, bool gwc, int cpg, int* IWR_out) {
+  const size_t in_elems = (size_t)CK * ID * IH * IWP;
+  const size_t w_elems = (size_t)taps * CK * COP;
+  size_t total = 2 * in_elems + (gwc ? 3 : 2) * w_elems;
+  int IWR = 0;
+  if (gwc) {
+    IWR = round_up(IWP + ID - 1, 4);
+    total += (size_t)CK * cpg * IH * IWP + (size_t)CK * cpg * IH * IWR;
+  }
+  if (IWR_out) *IWR_out = IWR;
+  return total * sizeof(float);
+}
+
+// Per-SM residency estimate: the kernels compile to <=128 registers, so at most 512 threads per SM;
+// shared memory: 227 KB usable per SM, 1 KB reserved per CTA.
+static int resident_ctas(int nthreads, size_t smem) {
+  const int by_regs = 512 / nthreads;
+  const int by_smem = (int)((227 * 1024) / (smem + 1024));
+  int r = by_regs < by_smem ? by_regs : by_smem;
+  return r > 8 ? 8 : r;
+}
+
+static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int KD, int S, int CK, int COP, bool gwc,
+                          int cpg, Tiling* out, double* best_cost) {
   bool found = false;
-  for (int slots = target; slots >= 32; slots -= 32) {
+  for (int slots = 32; slots * ncog <= 320 && slots <= 256; slots += 32) {
     for (int TWG = 1; TWG <= 16; TWG *= 2) {
       if (slots % TWG) continue;
       const int R = slots / TWG;
@@ -433,13 +628,21 @@ static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int 
           const int want = (4 * TWG) % 32;  // rows of an 8-lane LDS.128 phase land on distinct banks
           while (IWP % 32 != want) IWP += 4;
         }
+        int IWR = 0;
+        const size_t smem = conv_smem_bytes(CK, ID, IH, IWP, KD * KH * KW, COP, gwc, cpg, &IWR);
+        if (smem > 224 * 1024) continue;
+        const int nthreads = slots * ncog;
+        const int ctas = resident_ctas(nthreads, smem);
+        if (ctas < 1) continue;
         const double halo = (double)ID * IH * IWP / ((double)TD * TH * TW * S * S * (Jd == 1 ? 1 : S));
-        const size_t smem = ((size_t)CK * ID * IH * IWP + (size_t)KD * KH * KW * CK * COP) * sizeof(float);
-        if (smem > smem_limit) continue;
-        // compute waste dominates; prefer bigger CTAs (fewer fills per FLOP) and small halos
-        const double cost = waste * (1.0 + 0.05 * halo) * (1.0 + 8.0 / slots);
-        if (cost < best) {
-          best = cost;
+        // FMA-pipe utilisation needs ~12+ resident warps per SM to cover LDS/FFMA2 latencies; below
+        // that the cost grows quickly.  Then: wasted lanes, fill traffic (halo), barriers per FLOP
+        // (small CTAs / small channel chunks sync more often).
+        const double warps = (double)ctas * nthreads / 32.0;
+        const double occ = warps >= 14.0 ? 1.0 : 14.0 / warps;
+        const double cost = waste * occ * (1.0 + 0.05 * halo) * (1.0 + 8.0 / slots) * (CK >= 8 ? 1.0 : 1.04);
+        if (cost < *best_cost) {
+          *best_cost = cost;
           found = true;
           out->TWG = TWG;
           out->TH = TH;
@@ -448,6 +651,7 @@ static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int 
           out->IWP = IWP;
           out->ID = ID;
           out->IH = IH;
+          out->IWR = IWR;
           out->smem = smem;
         }
       }
@@ -459,24 +663,41 @@ static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int 
 typedef void (*conv_fn_t)(const ConvK);
 
 template <int KW, int S>
-static conv_fn_t pick_cog_ck(int COG, int CK) {
-  if (COG == 8 && CK == 8) return conv_kernel<KW, S, 8, 8>;
-  if (COG == 8 && CK == 1) return conv_kernel<KW, S, 8, 1>;
-  if (COG == 2 && CK == 8) return conv_kernel<KW, S, 2, 8>;
+static conv_fn_t pick_cog_ck(int COG, int CK, bool gwc) {
+  if (gwc) {
+    if (!(COG == 8 && KW == 3 && S == 1)) return nullptr;
+    return CK == 8 ? (conv_fn_t)conv_kernel<3, 1, 8, 8, true> : CK == 4 ? (conv_fn_t)conv_kernel<3, 1, 8, 4, true> : nullptr;
+  }
+  if (COG == 8 && CK == 8) return conv_kernel<KW, S, 8, 8, false>;
+  if (COG == 8 && CK == 4) return conv_kernel<KW, S, 8, 4, false>;
+  if (COG == 8 && CK == 1) return conv_kernel<KW, S, 8, 1, false>;
+  if (COG == 2 && CK == 8) return conv_kernel<KW, S, 2, 8, false>;
   return nullptr;
 }
 
-static conv_fn_t pick_kernel(int KW, int S, int COG, int CK) {
+static conv_fn_t pick_kernel(int KW, int S, int COG, int CK, bool gwc) {
   if (S == 1) {
-    if (KW == 1) return pick_cog_ck<1, 1>(COG, CK);
-    if (KW == 2) return pick_cog_ck<2, 1>(COG, CK);
-    if (KW == 3) return pick_cog_ck<3, 1>(COG, CK);
-    if (KW == 5) return pick_cog_ck<5, 1>(COG, CK);
+    if (KW == 1) return pick_cog_ck<1, 1>(COG, CK, gwc);
+    if (KW == 2) return pick_cog_ck<2, 1>(COG, CK, gwc);
+    if (KW == 3) return pick_cog_ck<3, 1>(COG, CK, gwc);
+    if (KW == 5) return pick_cog_ck<5, 1>(COG, CK, gwc);
   } else if (S == 2 && KW == 3) {
-    return pick_cog_ck<3, 2>(COG, CK);
+    return pick_cog_ck<3, 2>(COG, CK, gwc);
   }
   return nullptr;
 }
+
+// Launch plans are memoised per shape: the tiling search and the occupancy query cost ~50 us on the
+// host, which matters in eager mode (under CUDA-graph replay the host never runs them).
+struct PlanKey {
+  int v[16];
+  bool operator<(const PlanKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
+};
+struct Plan {
+  Tiling tl;
+  conv_fn_t fn;
+  int cosplit, COP, COG, CK, blocks_per_sm;
+};
 
 }  // namespace esm
 
@@ -592,24 +813,80 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   k.oD = d->oD;
   k.oH = d->oH;
 
-  const int COG = g.CoutPad == 2 ? 2 : 8;
-  const int CK = g.CinPad == 1 ? 1 : 8;
-  // a CTA owns at most 80 output channels (10 channel groups x >=32 voxel slots <= 320 threads)
-  int cosplit = 1;
-  while (g.CoutPad / cosplit > 80 || g.CoutPad % cosplit || (g.CoutPad / cosplit) % COG) ++cosplit;
-  const int COP = g.CoutPad / cosplit;
-  const int ncog = COP / COG;
-  // logical per-phase output extent
+  const bool gwc = d->src_mode == ESM_SRC_GWC;
   const int Jw = d->transposed ? ceil_div(d->Wout, 2) : d->Wout;
   const int Jh = d->transposed ? ceil_div(d->Hout, 2) : d->Hout;
   const int Jd = (d->transposed && g.phases_d == 2) ? ceil_div(d->Dout, 2) : d->Dout;
-  Tiling tl;
-  // prefer tiles that leave room for 2 CTAs per SM (fill of one overlaps the math of the other)
-  bool tiled = choose_tiling(Jw, Jh, Jd, ncog, g.KW, g.KH, g.KD, S, CK, COP, 110 * 1024, &tl) ||
-               choose_tiling(Jw, Jh, Jd, ncog, g.KW, g.KH, g.KD, S, CK, COP, 220 * 1024, &tl);
-  ESM_REQUIRE(tiled, "conv: no tiling for Cout=%d k=(%d,%d,%d)", d->Cout, d->kd, d->kh, d->kw);
-  k.cosplit = cosplit;
-  k.COP = COP;
+
+  static std::map<PlanKey, Plan> plans;
+  static std::mutex plans_mu;
+  static int num_sms = 0;
+  PlanKey key = {{d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed, Jw, Jh, Jd, gwc ? k.cpg : 0, 0, 0, 0, 0, 0}};
+  Plan plan;
+  {
+    std::lock_guard<std::mutex> lock(plans_mu);
+    if (num_sms == 0) {
+      int dev = 0;
+      cudaDeviceProp prop;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+        // no device: still run the validation / tiling below so shapes can be checked on a CPU box
+        cudaGetLastError();
+        num_sms = -1;
+      } else {
+        num_sms = prop.multiProcessorCount;
+      }
+    }
+    auto it = plans.find(key);
+    if (it == plans.end()) {
+      Plan np;
+      np.COG = g.CoutPad == 2 ? 2 : 8;
+      np.CK = g.CinPad == 1 ? 1 : 8;
+      // a CTA owns at most 80 output channels (10 channel groups x >=32 voxel slots <= 320 threads)
+      int cosplit = 1;
+      while (g.CoutPad / cosplit > 80 || g.CoutPad % cosplit || (g.CoutPad / cosplit) % np.COG) ++cosplit;
+      np.cosplit = cosplit;
+      np.COP = g.CoutPad / cosplit;
+      const int ncog = np.COP / np.COG;
+      // search tile shapes and channel-chunk depth (8 or 4: a shallower chunk halves the staged
+      // brick, which buys resident warps on the wide 8-channel layers)
+      double best = 1e30;
+      bool tiled = choose_tiling(Jw, Jh, Jd, ncog, g.KW, g.KH, g.KD, S, np.CK, np.COP, gwc, k.cpg, &np.tl, &best);
+      if (np.CK == 8 && np.COG == 8) {
+        Tiling t4;
+        if (choose_tiling(Jw, Jh, Jd, ncog, g.KW, g.KH, g.KD, S, 4, np.COP, gwc, k.cpg, &t4, &best)) {
+          np.tl = t4;
+          np.CK = 4;
+          tiled = true;
+        }
+      }
+      ESM_REQUIRE(tiled, "conv: no tiling for Cin=%d Cout=%d k=(%d,%d,%d)%s", d->Cin, d->Cout, d->kd, d->kh, d->kw,
+                  gwc ? " +gwc" : "");
+      np.fn = pick_kernel(g.KW, S, np.COG, np.CK, gwc);
+      ESM_REQUIRE(np.fn, "conv: unsupported kernel width %d / stride %d%s", g.KW, S, gwc ? " with ESM_SRC_GWC" : "");
+      np.blocks_per_sm = 1;
+      if (num_sms > 0) {
+        if (np.tl.smem > 48 * 1024 &&
+            cudaFuncSetAttribute((const void*)np.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess)
+          return check_launch("conv(cudaFuncSetAttribute)");
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)np.fn, np.tl.slots * ncog, np.tl.smem) != cudaSuccess)
+          return check_launch("conv(occupancy)");
+        np.blocks_per_sm = occ > 0 ? occ : 1;
+      }
+      if (getenv("ESM_DEBUG_PLAN"))
+        fprintf(stderr, "[esm plan] Cin=%d Cout=%d k=(%d,%d,%d) s=%d%s%s J=(%d,%d,%d): CK=%d COP=%d cosplit=%d tile=(%d,%d,%d) "
+                "threads=%d smem=%zu KB ctas/SM(est)=%d occ(query)=%d\n",
+                d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed ? " T" : "", gwc ? " gwc" : "", Jd, Jh, Jw, np.CK,
+                np.COP, np.cosplit, np.tl.TD, np.tl.TH, np.tl.TWG * 4, np.tl.slots * ncog, np.tl.smem / 1024,
+                resident_ctas(np.tl.slots * ncog, np.tl.smem), np.blocks_per_sm);
+      it = plans.emplace(key, np).first;
+    }
+    plan = it->second;
+  }
+  const Tiling& tl = plan.tl;
+  const int ncog = plan.COP / plan.COG;
+  k.cosplit = plan.cosplit;
+  k.COP = plan.COP;
   k.TWG = tl.TWG;
   k.TH = tl.TH;
   k.TD = tl.TD;
@@ -618,19 +895,20 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   k.ID = tl.ID;
   k.IH = tl.IH;
   k.IWP = tl.IWP;
+  k.IWR = tl.IWR;
   k.tilesW = ceil_div(Jw, tl.TWG * 4);
   k.tilesH = ceil_div(Jh, tl.TH);
   k.tilesD = ceil_div(Jd, tl.TD);
-
-  conv_fn_t fn = pick_kernel(g.KW, S, COG, CK);
-  ESM_REQUIRE(fn, "conv: unsupported kernel width %d / stride %d", g.KW, S);
-  if (tl.smem > 48 * 1024) {
-    if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem) != cudaSuccess)
-      return check_launch("conv(cudaFuncSetAttribute)");
+  k.phases = g.phases;
+  const long long total = (long long)k.tilesW * k.tilesH * k.tilesD * d->B * g.phases * plan.cosplit;
+  ESM_REQUIRE(total < (1ll << 30), "conv: too many tiles");
+  k.total_work = (int)total;
+  if (num_sms <= 0) {
+    set_error("conv: no CUDA device");
+    return ESM_ERR_CUDA;
   }
-  const long long ntiles = (long long)k.tilesW * k.tilesH * k.tilesD;
-  ESM_REQUIRE(ntiles < (1ll << 31) && d->B <= 65535, "conv: grid too large");
-  dim3 grid((unsigned)ntiles, (unsigned)d->B, (unsigned)(g.phases * cosplit));
-  fn<<<grid, k.nthreads, tl.smem, (cudaStream_t)stream>>>(k);
+  const long long resident = (long long)num_sms * plan.blocks_per_sm;
+  const unsigned grid = (unsigned)(total < resident ? total : resident);  // persistent CTAs stride over the tiles
+  plan.fn<<<grid, k.nthreads, tl.smem, (cudaStream_t)stream>>>(k);
   return check_launch("conv");
 }

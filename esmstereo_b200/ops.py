@@ -17,8 +17,34 @@ from . import _lib
 from ._lib import ACT, EsmConv, EsmMixerMlp, check, lib
 
 
+LAUNCHES = 0          # number of libesm_b200 kernels launched through this module (bench.py's gpu_launches)
+PROFILE = None        # set to a list to record (label, start_event, end_event) per operator call
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+class _Prof:
+    """Counts launches and, when PROFILE is a list, brackets the call with CUDA events."""
+
+    def __init__(self, label: str, kernels: int = 1):
+        self.label, self.kernels = label, kernels
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += self.kernels
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.label, self.e0, self.e1))
+        return False
 
 
 def _dev(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -40,8 +66,9 @@ def build_gwc_volume(refimg_fea: torch.Tensor, targetimg_fea: torch.Tensor, maxd
     assert Cc % num_groups == 0  # submodule.py:145
     V = torch.empty(B, num_groups, maxdisp, H, W, device=L.device, dtype=torch.float32)
     if V.numel():
-        check(lib().esm_gwc_volume_f32(L.data_ptr(), R.data_ptr(), V.data_ptr(), B, Cc, H, W, maxdisp, num_groups,
-                                       _stream()), "gwc_volume")
+        with _Prof("gwc_volume C%d G%d D%d %dx%d" % (Cc, num_groups, maxdisp, H, W)):
+            check(lib().esm_gwc_volume_f32(L.data_ptr(), R.data_ptr(), V.data_ptr(), B, Cc, H, W, maxdisp, num_groups,
+                                           _stream()), "gwc_volume")
     return V
 
 
@@ -51,8 +78,9 @@ def build_norm_correlation_volume(refimg_fea: torch.Tensor, targetimg_fea: torch
     V = torch.empty(B, 1, maxdisp, H, W, device=L.device, dtype=torch.float32)
     ws = torch.empty(2 * L.numel(), device=L.device, dtype=torch.float32)
     if V.numel():
-        check(lib().esm_norm_corr_volume_f32(L.data_ptr(), R.data_ptr(), V.data_ptr(), ws.data_ptr(), B, Cc, H, W,
-                                             maxdisp, _stream()), "norm_corr_volume")
+        with _Prof("norm_corr_volume C%d D%d %dx%d" % (Cc, maxdisp, H, W), 3):
+            check(lib().esm_norm_corr_volume_f32(L.data_ptr(), R.data_ptr(), V.data_ptr(), ws.data_ptr(), B, Cc, H, W,
+                                                 maxdisp, _stream()), "norm_corr_volume")
     return V
 
 
@@ -66,8 +94,9 @@ def regression_top2(cost: torch.Tensor, return_indices: bool = False):
     B, D, H, W = cost.shape
     pred = torch.empty(B, 1, H, W, device=cost.device, dtype=torch.float32)
     idx = torch.empty(B, 2, H, W, device=cost.device, dtype=torch.int32) if return_indices else None
-    check(lib().esm_regression_top2_f32(cost.data_ptr(), pred.data_ptr(), _ptr(idx), B, D, H, W, _stream()),
-          "regression_top2")
+    with _Prof("regression_top2 D%d %dx%d" % (D, H, W)):
+        check(lib().esm_regression_top2_f32(cost.data_ptr(), pred.data_ptr(), _ptr(idx), B, D, H, W, _stream()),
+              "regression_top2")
     return (pred, idx) if return_indices else pred
 
 
@@ -85,7 +114,8 @@ def disparity_regression(x: torch.Tensor, maxdisp: int) -> torch.Tensor:
     assert len(x.shape) == 4 and x.shape[1] == maxdisp
     B, D, H, W = x.shape
     pred = torch.empty(B, H, W, device=x.device, dtype=torch.float32)
-    check(lib().esm_disparity_regression_f32(x.data_ptr(), pred.data_ptr(), B, D, H, W, _stream()), "disparity_regression")
+    with _Prof("disparity_regression D%d %dx%d" % (D, H, W)):
+        check(lib().esm_disparity_regression_f32(x.data_ptr(), pred.data_ptr(), B, D, H, W, _stream()), "disparity_regression")
     return pred
 
 
@@ -95,8 +125,9 @@ def bilinear_add(prev: torch.Tensor, residual: torch.Tensor, factor: int, out_sc
     B, c, h, w = prev.shape
     assert c == 1 and tuple(residual.shape) == (B, 1, h * factor, w * factor)
     out = torch.empty_like(residual)
-    check(lib().esm_bilinear_add_f32(prev.data_ptr(), residual.data_ptr(), out.data_ptr(), B, h, w, factor,
-                                     float(out_scale), _stream()), "bilinear_add")
+    with _Prof("bilinear_add x%d %dx%d" % (factor, h, w)):
+        check(lib().esm_bilinear_add_f32(prev.data_ptr(), residual.data_ptr(), out.data_ptr(), B, h, w, factor,
+                                         float(out_scale), _stream()), "bilinear_add")
     return out
 
 
@@ -254,7 +285,11 @@ def conv(srcs: Sequence[torch.Tensor], pc: PackedConv, act: Optional[str] = None
     d.out_mul, d.residual, d.act2 = _ptr(out_mul), _ptr(residual), ACT[act2]
     d.out_scale, d.pixel_shuffle = float(out_scale), r
     d.out, d.oB, d.oC, d.oD, d.oH = out.data_ptr(), oB, oC, oD, oH
-    check(lib().esm_conv_f32(C.byref(d), _stream()), "conv")
+    label = "%s%dd %d->%d k%d%s s%d in %s%s" % ("deconv" if pc.transposed else "conv", nd, pc.Cin, pc.Cout, kw,
+                                                  "+gwc" if gwc_disp is not None else "", S,
+                                                  "x".join(str(v) for v in (Din, Hin, Win)), " ps%d" % r if r else "")
+    with _Prof(label):
+        check(lib().esm_conv_f32(C.byref(d), _stream()), "conv")
     return out
 
 
@@ -275,8 +310,9 @@ def sm_pointwise(x: torch.Tensor, mlp: MixerMlp, extra_residual: Optional[torch.
     x = _dev(x, "x").contiguous()
     B, Cc, H, W = x.shape
     y = torch.empty_like(x)
-    check(lib().esm_sm_pointwise_f32(x.data_ptr(), y.data_ptr(), B, Cc, H, W, C.byref(mlp.s), _ptr(extra_residual), _stream()),
-          "sm_pointwise")
+    with _Prof("sm_pointwise C%d %dx%d" % (Cc, H, W)):
+        check(lib().esm_sm_pointwise_f32(x.data_ptr(), y.data_ptr(), B, Cc, H, W, C.byref(mlp.s), _ptr(extra_residual),
+                                         _stream()), "sm_pointwise")
     return y
 
 
@@ -286,8 +322,9 @@ def sm_spatial(x: torch.Tensor, dw_w: torch.Tensor, dw_b: torch.Tensor, mlp: Mix
     B, Cc, H, W = x.shape
     y = torch.empty_like(x)
     k = dw_w.shape[-1]
-    check(lib().esm_sm_spatial_f32(x.data_ptr(), y.data_ptr(), B, Cc, H, W, dw_w.data_ptr(), dw_b.data_ptr(), k,
-                                   C.byref(mlp.s), _ptr(extra_residual), _stream()), "sm_spatial")
+    with _Prof("sm_spatial C%d k%d %dx%d" % (Cc, k, H, W)):
+        check(lib().esm_sm_spatial_f32(x.data_ptr(), y.data_ptr(), B, Cc, H, W, dw_w.data_ptr(), dw_b.data_ptr(), k,
+                                       C.byref(mlp.s), _ptr(extra_residual), _stream()), "sm_spatial")
     return y
 
 
@@ -298,7 +335,8 @@ def laf_cost_top7(cost: torch.Tensor) -> torch.Tensor:
     cost = _dev(cost, "cost").contiguous()
     B, D, H, W = cost.shape
     out = torch.empty(B, 7, H, W, device=cost.device, dtype=torch.float32)
-    check(lib().esm_laf_cost_top7_f32(cost.data_ptr(), out.data_ptr(), B, D, H, W, _stream()), "laf_cost_top7")
+    with _Prof("laf_cost_top7 D%d %dx%d" % (D, H, W)):
+        check(lib().esm_laf_cost_top7_f32(cost.data_ptr(), out.data_ptr(), B, D, H, W, _stream()), "laf_cost_top7")
     return out
 
 
@@ -306,7 +344,8 @@ def laf_attention(cost_x, disp_x, imag_x, att_c, att_d, att_i) -> torch.Tensor:
     ts = [_dev(t, "laf_attention input").contiguous() for t in (cost_x, disp_x, imag_x, att_c, att_d, att_i)]
     B, Cc, H, W = ts[0].shape
     out = torch.empty(B, 3 * Cc, H, W, device=ts[0].device, dtype=torch.float32)
-    check(lib().esm_laf_attention_f32(*[t.data_ptr() for t in ts], out.data_ptr(), B, Cc, H, W, _stream()), "laf_attention")
+    with _Prof("laf_attention C%d %dx%d" % (Cc, H, W)):
+        check(lib().esm_laf_attention_f32(*[t.data_ptr() for t in ts], out.data_ptr(), B, Cc, H, W, _stream()), "laf_attention")
     return out
 
 
@@ -326,9 +365,10 @@ def laf_sample_embed(feat, scale, weight, bn_scale, bn_shift) -> torch.Tensor:
     B, Cc, H, W = feat.shape
     lin_x, lin_y = _linspace_pm1(W, feat.device), _linspace_pm1(H, feat.device)
     out = torch.empty_like(feat)
-    check(lib().esm_laf_sample_embed_f32(feat.data_ptr(), scale.data_ptr(), lin_x.data_ptr(), lin_y.data_ptr(),
-                                         weight.data_ptr(), bn_scale.data_ptr(), bn_shift.data_ptr(), out.data_ptr(),
-                                         B, Cc, H, W, _stream()), "laf_sample_embed")
+    with _Prof("laf_sample_embed C%d %dx%d" % (Cc, H, W)):
+        check(lib().esm_laf_sample_embed_f32(feat.data_ptr(), scale.data_ptr(), lin_x.data_ptr(), lin_y.data_ptr(),
+                                             weight.data_ptr(), bn_scale.data_ptr(), bn_shift.data_ptr(), out.data_ptr(),
+                                             B, Cc, H, W, _stream()), "laf_sample_embed")
     return out
 
 
@@ -336,11 +376,13 @@ def conf_convex_up4(feat, conf, weight, bias) -> torch.Tensor:
     feat, conf = _dev(feat, "feat").contiguous(), _dev(conf, "conf").contiguous()
     B, Cc, h, w = feat.shape
     out = torch.empty(B, 1, 4 * h, 4 * w, device=feat.device, dtype=torch.float32)
-    check(lib().esm_conf_convex_up4_f32(feat.data_ptr(), conf.data_ptr(), weight.data_ptr(), bias.data_ptr(),
-                                        out.data_ptr(), B, Cc, h, w, _stream()), "conf_convex_up4")
+    with _Prof("conf_convex_up4 C%d %dx%d" % (Cc, h, w)):
+        check(lib().esm_conf_convex_up4_f32(feat.data_ptr(), conf.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                            out.data_ptr(), B, Cc, h, w, _stream()), "conf_convex_up4")
     return out
 
 
 def fill_(t: torch.Tensor, value: float) -> torch.Tensor:
-    check(lib().esm_fill_f32(_dev(t, "t").data_ptr(), t.numel(), float(value), _stream()), "fill")
+    with _Prof("fill"):
+        check(lib().esm_fill_f32(_dev(t, "t").data_ptr(), t.numel(), float(value), _stream()), "fill")
     return t
