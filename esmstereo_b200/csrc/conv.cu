@@ -16,7 +16,7 @@
 // Each thread owns 4 consecutive output voxels along W x COG output channels (packed as float2
 // pairs for FFMA2); a CTA owns a TD x TH x 4*TWG brick of voxels and ALL output channels, stages
 // CK input channels of the brick + halo in shared memory together with the matching weights.
-#include "common.cuh"
+#include "conv_kernel.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -27,484 +27,13 @@
 
 namespace esm {
 
-struct ConvK {
-  esm_src_t src[3];
-  int nsrc, src_mode, cpg;
-  const float* in_mul;
-  long long imB, imC, imH;
-  int B, Cin, Din, Hin, Win;
-  int OD, OH, OW;       // real output extent
-  int Cout, CinPad, CoutPad;
-  int KD, KH;           // taps per CTA pass in d / h (KW is a template parameter)
-  int pd, ph, pw;       // in = j*S - p + tap
-  int transposed, phases_d;
-  const float* weight;
-  long long phase_stride;  // packed weight elements per phase
-  const float* scale;
-  const float* shift;
-  int act, act2;
-  const float* out_mul;
-  long long omB, omC, omH;
-  const float* residual;
-  float out_scale;
-  int ps;
-  float* out;
-  long long oB, oC, oD, oH;
-  // tiling
-  int TWG, TH, TD, slots, nthreads;
-  int ID, IH, IWP;
-  int tilesW, tilesH, tilesD;
-  int cosplit, COP;  // output channels are split over `cosplit` CTAs of COP (padded) channels each
-  int phases, total_work, IWR;
-};
-
-// ---- cp.async helpers (LDGSTS): global -> shared without register staging; src_size 0 zero-fills ----
-__device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gsrc, bool pred) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int n = pred ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(n));
-}
-template <int BYTES>
-__device__ __forceinline__ void cp_async_vec(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  if (BYTES == 16)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
-  else
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-struct TileCtx {
-  int b, co_base, tileW, tileH, tileD;
-  int pz_d, pz_h, pz_w;     // transposed-conv phase
-  int pd, ph, pw;           // effective padding of this phase
-  const float* wbase;
-};
-
-__device__ __forceinline__ TileCtx decode_work(const ConvK& p, int w) {
-  TileCtx c;
-  const int tiles = p.tilesW * p.tilesH * p.tilesD;
-  int t = w % tiles;
-  int r = w / tiles;
-  c.tileW = t % p.tilesW;
-  t /= p.tilesW;
-  c.tileH = t % p.tilesH;
-  c.tileD = t / p.tilesH;
-  c.co_base = (r % p.cosplit) * p.COP;
-  r /= p.cosplit;
-  const int z = r % p.phases;
-  c.b = r / p.phases;
-  c.pz_d = c.pz_h = c.pz_w = 0;
-  c.pd = p.pd;
-  c.ph = p.ph;
-  c.pw = p.pw;
-  c.wbase = p.weight;
-  if (p.transposed) {
-    c.pz_w = z & 1;
-    c.pz_h = (z >> 1) & 1;
-    c.pz_d = (p.phases_d == 2) ? ((z >> 2) & 1) : 0;
-    c.pw = 1 - c.pz_w;
-    c.ph = 1 - c.pz_h;
-    c.pd = (p.phases_d == 2) ? 1 - c.pz_d : 0;
-    c.wbase += (long long)z * p.phase_stride;
-  }
-  return c;
-}
-
-// Persistent, double-buffered direct convolution.  Work items (tile, channel chunk) stream through a
-// 2-stage shared-memory ring filled by cp.async: the loads of item i+1 are in flight while item i
-// runs on the FP32 pipe.  GWC=true: the "input" voxels are group-wise correlations; the left/right
-// feature rows of the next chunk are cp.async-staged and turned into the correlation tile
-// smem -> smem (the D x H x W volume never exists in HBM).
-template <int KW, int S, int COG, int CK, bool GWC>
-__global__ void __launch_bounds__(320, 1) conv_kernel(const __grid_constant__ ConvK p) {
-  extern __shared__ __align__(16) float smem[];
-  constexpr int NV = 4;
-  constexpr int XN = (NV - 1) * S + KW;
-  constexpr int XL = (XN + 3) / 4 * 4;
-  constexpr int NP = 4;  // fill positions per thread per pass over a plane
-
-  const int tid = threadIdx.x;
-  const int NT = p.nthreads;
-  const int ID = p.ID, IH = p.IH, IWP = p.IWP;
-  const int plane = IH * IWP;
-  const int chan_stride = ID * plane;
-  const int COP = p.COP;
-  const int taps = p.KD * p.KH * KW;
-  const int in_elems = CK * chan_stride;
-  const int w_elems = taps * CK * COP;
-  // smem carve-up: [in0][in1][w0][w1][w2 (GWC)][L staging][R staging]
-  float* s_in0 = smem;
-  float* s_w0 = smem + 2 * in_elems;
-  const int IWR = p.IWR;                  // GWC: right staging row pitch
-  float* s_L = s_w0 + 3 * w_elems;        // GWC only
-  float* s_R = s_L + CK * p.cpg * plane;  // GWC only: [CK*cpg][IH][IWR]
-
-  const int slot = tid % p.slots;
-  const int cog = tid / p.slots;
-  const int twg = slot % p.TWG;
-  const int th = (slot / p.TWG) % p.TH;
-  const int td = slot / (p.TWG * p.TH);
-  const int TW = p.TWG * NV;
-  const int xoff = ((td * S) * IH + th * S) * IWP + twg * NV * S;
-
-  const int nch = (p.Cin + CK - 1) / CK;
-  const int my_tiles = (p.total_work > (int)blockIdx.x) ? (p.total_work - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int n_items = my_tiles * nch;
-
-  // ---------------- loaders ----------------
-  auto load_weights = [&](int item, float* dst) {
-    const int w = blockIdx.x + (item / nch) * gridDim.x;
-    const int c0 = (item % nch) * CK;
-    const TileCtx t = decode_work(p, w);
-    constexpr int WB = (COG >= 4) ? 16 : 8;
-    constexpr int WV = WB / 4;
-    const int copv = COP / WV;
-    const int row_v = CK * copv;
-    for (int i = tid; i < taps * row_v; i += NT) {
-      const int tap = i / row_v;
-      const int rr = i - tap * row_v;
-      const int c = rr / copv;
-      const int r = rr - c * copv;
-      cp_async_vec<WB>(dst + (long long)i * WV,
-                       t.wbase + ((long long)(tap * p.CinPad + c0 + c) * p.CoutPad + t.co_base) + r * WV);
-    }
-  };
-
-  auto load_inputs = [&](int item, float* dst) {  // ESM_SRC_TENSORS: brick + halo of CK channels
-    const int w = blockIdx.x + (item / nch) * gridDim.x;
-    const int c0 = (item % nch) * CK;
-    const TileCtx t = decode_work(p, w);
-    const int iw0 = t.tileW * TW * S - t.pw;
-    const int ih0 = t.tileH * p.TH * S - t.ph;
-    const int id0 = t.tileD * p.TD * S - t.pd;
-    for (int pb = 0; pb < plane; pb += NP * NT) {
-      int hh[NP], ww[NP];
-      bool ok[NP];
-#pragma unroll
-      for (int k = 0; k < NP; ++k) {
-        const int pos = pb + tid + k * NT;
-        const int hy = pos / IWP;
-        const int col = pos - hy * IWP;
-        hh[k] = ih0 + hy;
-        ww[k] = iw0 + col;
-        ok[k] = (pos < plane) && (hh[k] >= 0) && (hh[k] < p.Hin) && (ww[k] >= 0) && (ww[k] < p.Win);
-      }
-#pragma unroll 1
-      for (int c = 0; c < CK; ++c) {
-        const int cc = c0 + c;
-        const bool cvalid = cc < p.Cin;
-        const float* sbase = p.src[0].ptr;
-        long long sD = 0, sH = 0;
-        if (cvalid) {
-          int rel = cc;
-          const esm_src_t* sp = &p.src[0];
-          if (p.nsrc > 1 && rel >= p.src[0].C) {
-            rel -= p.src[0].C;
-            sp = &p.src[1];
-            if (p.nsrc > 2 && rel >= p.src[1].C) {
-              rel -= p.src[1].C;
-              sp = &p.src[2];
-            }
-          }
-          sbase = sp->ptr + (long long)t.b * sp->sB + (long long)rel * sp->sC;
-          sD = sp->sD;
-          sH = sp->sH;
-        }
-        long long off[NP];
-#pragma unroll
-        for (int k = 0; k < NP; ++k) off[k] = ok[k] ? (long long)hh[k] * sH + ww[k] : 0;
-#pragma unroll 1
-        for (int dz = 0; dz < ID; ++dz) {
-          const int d = id0 + dz;
-          const bool dvalid = cvalid && d >= 0 && d < p.Din;
-          const float* sd = sbase + (dvalid ? (long long)d * sD : 0);
-          float* drow = dst + (c * ID + dz) * plane + pb + tid;
-#pragma unroll
-          for (int k = 0; k < NP; ++k)
-            if (pb + tid + k * NT < plane) cp_async_4(drow + k * NT, sd + off[k], dvalid && ok[k]);
-        }
-      }
-    }
-  };
-
-  auto load_lr = [&](int item) {  // ESM_SRC_GWC: left rows [CK*cpg][IH][IWP], right rows [CK*cpg][IH][IWR]
-    const int w = blockIdx.x + (item / nch) * gridDim.x;
-    const int c0 = (item % nch) * CK;
-    const TileCtx t = decode_work(p, w);
-    const int iw0 = t.tileW * TW * S - t.pw;
-    const int ih0 = t.tileH * p.TH * S - t.ph;
-    const int id0 = t.tileD * p.TD * S - t.pd;
-    const int nchan = CK * p.cpg;
-    const int fc0 = c0 * p.cpg;  // first feature channel of this chunk of groups
-    const int Cfeat = p.Cin * p.cpg;
-    const float* Lb = p.src[0].ptr + (long long)t.b * p.src[0].sB;
-    const float* Rb = p.src[1].ptr + (long long)t.b * p.src[1].sB;
-    const long long sC = p.src[0].sC, sH = p.src[0].sH;
-    for (int i = tid; i < nchan * plane; i += NT) {
-      const int c = i / plane;
-      const int rem = i - c * plane;
-      const int hy = rem / IWP;
-      const int col = rem - hy * IWP;
-      const int h = ih0 + hy, x = iw0 + col;
-      const bool ok = (fc0 + c < Cfeat) && h >= 0 && h < p.Hin && x >= 0 && x < p.Win;
-      cp_async_4(s_L + i, Lb + (ok ? (long long)(fc0 + c) * sC + (long long)h * sH + x : 0), ok);
-    }
-    const int rw0 = iw0 - id0 - (ID - 1);  // right-image column of staging column 0
-    const int rplane = IH * IWR;
-    for (int i = tid; i < nchan * rplane; i += NT) {
-      const int c = i / rplane;
-      const int rem = i - c * rplane;
-      const int hy = rem / IWR;
-      const int col = rem - hy * IWR;
-      const int h = ih0 + hy, x = rw0 + col;
-      const bool ok = (fc0 + c < Cfeat) && h >= 0 && h < p.Hin && x >= 0 && x < p.Win;
-      cp_async_4(s_R + i, Rb + (ok ? (long long)(fc0 + c) * sC + (long long)h * sH + x : 0), ok);
-    }
-  };
-
-  auto build_volume = [&](int item, float* dst) {  // correlation tile from the staged rows (smem -> smem)
-    const int w = blockIdx.x + (item / nch) * gridDim.x;
-    const int c0 = (item % nch) * CK;
-    const TileCtx t = decode_work(p, w);
-    const int iw0 = t.tileW * TW * S - t.pw;
-    const int ih0 = t.tileH * p.TH * S - t.ph;
-    const int id0 = t.tileD * p.TD * S - t.pd;
-    const float* mb = p.in_mul ? p.in_mul + (long long)t.b * p.imB : nullptr;
-    const float inv = 1.0f / (float)p.cpg;
-    const bool pow2 = (p.cpg & (p.cpg - 1)) == 0;
-    for (int i = tid; i < CK * plane; i += NT) {
-      const int g = i / plane;
-      const int rem = i - g * plane;
-      const int hy = rem / IWP;
-      const int col = rem - hy * IWP;
-      const int h = ih0 + hy, x = iw0 + col;
-      const bool ok = (c0 + g < p.Cin) && h >= 0 && h < p.Hin && x >= 0 && x < p.Win;
-      float m = 1.f;
-      if (mb && ok) m = __ldg(mb + (long long)(c0 + g) * p.imC + (long long)h * p.imH + x);
-      const float* lp = s_L + (g * p.cpg) * plane + rem;
-      const float* rp = s_R + (g * p.cpg) * (IH * IWR) + hy * IWR + col + (ID - 1);
-      for (int dz = 0; dz < ID; ++dz) {
-        const int d = id0 + dz;
-        float v = 0.f;
-        if (ok && d >= 0 && d < p.Din && x - d >= 0) {
-          float s = 0.f;
-          for (int q = 0; q < p.cpg; ++q)  // un-contracted: (fea1*fea2).mean(2), submodule.py:147
-            s = __fadd_rn(s, __fmul_rn(lp[q * plane], rp[q * IH * IWR - dz]));
-          v = pow2 ? s * inv : s / (float)p.cpg;
-          v *= m;
-        }
-        dst[(g * ID + dz) * plane + rem] = v;
-      }
-    }
-  };
-
-  auto scale_inputs = [&](int item, float* buf) {  // buf[c][dz][hy][col] *= in_mul[b, c0+c, 0, h, x]
-    const int w = blockIdx.x + (item / nch) * gridDim.x;
-    const int c0 = (item % nch) * CK;
-    const TileCtx t = decode_work(p, w);
-    const int iw0 = t.tileW * TW * S - t.pw;
-    const int ih0 = t.tileH * p.TH * S - t.ph;
-    const float* mb = p.in_mul + (long long)t.b * p.imB;
-    for (int i = tid; i < CK * plane; i += NT) {
-      const int c = i / plane;
-      const int rem = i - c * plane;
-      const int hy = rem / IWP;
-      const int col = rem - hy * IWP;
-      const int h = ih0 + hy, x = iw0 + col;
-      if ((c0 + c < p.Cin) && h >= 0 && h < p.Hin && x >= 0 && x < p.Win) {
-        const float m = __ldg(mb + (long long)(c0 + c) * p.imC + (long long)h * p.imH + x);
-        for (int dz = 0; dz < ID; ++dz) buf[(c * ID + dz) * plane + rem] *= m;
-      }
-    }
-  };
-
-  float2 acc[NV][COG / 2];
-#pragma unroll
-  for (int v = 0; v < NV; ++v)
-#pragma unroll
-    for (int j = 0; j < COG / 2; ++j) acc[v][j] = make_float2(0.f, 0.f);
-
-  // ---------------- prologue ----------------
-  if (n_items > 0) {
-    if (GWC) {
-      load_weights(0, s_w0);
-      load_lr(0);
-      cp_async_commit();
-      cp_async_wait<0>();
-      __syncthreads();
-      build_volume(0, s_in0);
-      __syncthreads();
-      if (n_items > 1) {
-        load_weights(1, s_w0 + w_elems);
-        load_lr(1);
-      }
-      cp_async_commit();
-    } else {
-      load_weights(0, s_w0);
-      load_inputs(0, s_in0);
-      cp_async_commit();
-    }
-  }
-
-  for (int item = 0; item < n_items; ++item) {
-    const float* s_in = s_in0 + (item & 1) * in_elems;
-    const float* s_w;
-    if (GWC) {
-      s_w = s_w0 + (item % 3) * w_elems;
-      cp_async_wait<0>();  // rows + weights of item+1 have landed
-      __syncthreads();     // ...and every warp is done reading V[(item+1)&1] (FFMA2 of item-1)
-      if (item + 1 < n_items) build_volume(item + 1, s_in0 + ((item + 1) & 1) * in_elems);
-      __syncthreads();     // staging rows are free again
-      if (item + 2 < n_items) {
-        load_weights(item + 2, s_w0 + ((item + 2) % 3) * w_elems);
-        load_lr(item + 2);
-      }
-      cp_async_commit();
-    } else {
-      s_w = s_w0 + (item & 1) * w_elems;
-      if (item + 1 < n_items) {
-        load_weights(item + 1, s_w0 + ((item + 1) & 1) * w_elems);
-        load_inputs(item + 1, s_in0 + ((item + 1) & 1) * in_elems);
-      }
-      cp_async_commit();
-      cp_async_wait<1>();  // everything but the group just committed -> item's data has landed
-      __syncthreads();
-      if (p.in_mul) {  // rare (unfused cv16 volume * att): scale the staged brick in place
-        scale_inputs(item, s_in0 + (item & 1) * in_elems);
-        __syncthreads();
-      }
-    }
-
-    // ---------------- FFMA2 inner product ----------------
-    {
-      const float* xin = s_in + xoff;
-      const float* wthr = s_w + cog * COG;
-      for (int kd = 0; kd < p.KD; ++kd) {
-        for (int kh = 0; kh < p.KH; ++kh) {
-          const float* xr = xin + (kd * IH + kh) * IWP;
-          const float* wr = wthr + ((kd * p.KH + kh) * KW) * CK * COP;
-#pragma unroll
-          for (int c = 0; c < CK; ++c) {
-            float x[XL];
-#pragma unroll
-            for (int q = 0; q < XL / 4; ++q) {
-              const float4 t4 = *reinterpret_cast<const float4*>(xr + c * chan_stride + q * 4);
-              x[q * 4 + 0] = t4.x;
-              x[q * 4 + 1] = t4.y;
-              x[q * 4 + 2] = t4.z;
-              x[q * 4 + 3] = t4.w;
-            }
-#pragma unroll
-            for (int kw = 0; kw < KW; ++kw) {
-              float2 w2[COG / 2];
-              const float* wp = wr + (kw * CK + c) * COP;
-              if (COG >= 4) {
-#pragma unroll
-                for (int q = 0; q < COG / 4; ++q) {
-                  const float4 t4 = *reinterpret_cast<const float4*>(wp + q * 4);
-                  w2[q * 2 + 0] = make_float2(t4.x, t4.y);
-                  w2[q * 2 + 1] = make_float2(t4.z, t4.w);
-                }
-              } else {
-                w2[0] = *reinterpret_cast<const float2*>(wp);
-              }
-#pragma unroll
-              for (int v = 0; v < NV; ++v) {
-                const float xv = x[v * S + kw];
-                const float2 xx = make_float2(xv, xv);
-#pragma unroll
-                for (int j = 0; j < COG / 2; ++j) ffma2(acc[v][j], xx, w2[j]);
-              }
-            }
-          }
-        }
-      }
-    }
-
-    // ---------------- epilogue (last channel chunk of a tile) ----------------
-    if ((item % nch) == nch - 1) {
-      const TileCtx t = decode_work(p, blockIdx.x + (item / nch) * gridDim.x);
-      const int osd = (p.transposed && p.phases_d == 2) ? 2 : 1;
-      const int osw = p.transposed ? 2 : 1;
-      const int jd = t.tileD * p.TD + td;
-      const int jh = t.tileH * p.TH + th;
-      const int jw0 = t.tileW * TW + twg * NV;
-      const int od = jd * osd + t.pz_d;
-      const int oh = jh * osw + t.pz_h;
-      const int b = t.b;
-      if (od < p.OD && oh < p.OH) {
-#pragma unroll
-        for (int j = 0; j < COG; ++j) {
-          const int co = t.co_base + cog * COG + j;
-          if (co >= p.Cout) break;
-          const float sc = p.scale ? __ldg(p.scale + co) : 1.f;
-          const float sh = p.shift ? __ldg(p.shift + co) : 0.f;
-          float r[NV];
-#pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            const float a = (j & 1) ? acc[v][j / 2].y : acc[v][j / 2].x;
-            r[v] = apply_act(fmaf(a, sc, sh), p.act);
-          }
-          if (p.ps == 0) {
-            const long long obase = (long long)b * p.oB + (long long)co * p.oC + (long long)od * p.oD + (long long)oh * p.oH;
-            const float* om = p.out_mul ? p.out_mul + (long long)b * p.omB + (long long)co * p.omC + (long long)oh * p.omH : nullptr;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              const int ow = (jw0 + v) * osw + t.pz_w;
-              if (ow < p.OW) {
-                float y = r[v];
-                if (om) y *= __ldg(om + ow);
-                if (p.residual) y += __ldg(p.residual + obase + ow);
-                y = apply_act(y, p.act2) * p.out_scale;
-                r[v] = y;
-              }
-            }
-            float* o = p.out + obase;
-            const int ow0 = jw0 * osw + t.pz_w;
-            if (osw == 1 && ow0 + NV <= p.OW && ((reinterpret_cast<uintptr_t>(o + ow0) & 15) == 0)) {
-              *reinterpret_cast<float4*>(o + ow0) = make_float4(r[0], r[1], r[2], r[3]);
-            } else {
-#pragma unroll
-              for (int v = 0; v < NV; ++v) {
-                const int ow = (jw0 + v) * osw + t.pz_w;
-                if (ow < p.OW) o[ow] = r[v];
-              }
-            }
-          } else {
-            // PixelShuffle(r): channel co -> (c, a, bb); out[c, oh*r + a, ow*r + bb]   (2D only)
-            const int rr = p.ps;
-            const int c = co / (rr * rr);
-            const int a = (co / rr) % rr;
-            const int bb = co % rr;
-            float* o = p.out + (long long)b * p.oB + (long long)c * p.oC + (long long)(oh * rr + a) * p.oH;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              const int ow = jw0 + v;
-              if (ow < p.OW) o[ow * rr + bb] = apply_act(r[v], p.act2) * p.out_scale;
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int v = 0; v < NV; ++v)
-#pragma unroll
-        for (int j = 0; j < COG / 2; ++j) acc[v][j] = make_float2(0.f, 0.f);
-    }
-    if (!GWC) __syncthreads();  // stage (item&1) may be refilled by the loads issued next iteration
-  }
-  cp_async_wait<0>();
-}
-
 // ------------------------------------------------------------------------------------------
 // weight packing / BN folding
 // ------------------------------------------------------------------------------------------
-static int pad_cout(int Cout) { return Cout <= 2 ? 2 : round_up(Cout, 8); }
+static int pad_cout(int Cout) { return Cout <= 4 ? 4 : round_up(Cout, 8); }
 // single-channel inputs (disparity / confidence maps) get their own CK=1 instantiation instead of
-// 8x zero padding; the (Cin=1, Cout<=2) corner keeps the padded form so weight rows stay 16 B wide
-static int pad_cin(int Cin, int Cout) { return (Cin == 1 && Cout > 2) ? 1 : round_up(Cin, 8); }
+// 8x zero padding (only instantiated for the 8-wide channel groups)
+static int pad_cin(int Cin, int Cout) { return (Cin == 1 && Cout > 4) ? 1 : round_up(Cin, 8); }
 
 __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kd,
                                    int kh, int kw, int transposed, int CinPad, int CoutPad, int KD, int KH, int KW,
@@ -582,21 +111,25 @@ static PackGeom pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transpo
 // host-side tiling + dispatch
 // ------------------------------------------------------------------------------------------
 struct Tiling {
-  int TWG, TH, TD, slots, IWP, ID, IH, IWR;
+  int TWG, TH, TD, slots, IWP, ID, IH, IWR, IWL;
   size_t smem;
 };
 
-static size_t conv_smem_bytes(int CK, int ID, int IH, int IWP, int taps, int COP, bool gwc, int cpg, int* IWR_out) {
-  const size_t in_elems = (size_t)CK * ID * IH * IWP;
-  const size_t w_elems = (size_t)taps * CK * COP;
+static size_t conv_smem_bytes(int CK, int ID, int IH, int IWP, int taps, int COP, bool gwc, int cpg, int* IWR_out,
+                              int* IWL_out) {
+  auto pad32 = [](size_t n) { return (n + 31) & ~(size_t)31; };  // buffers are multiples of 128 bytes (TMA destinations)
+  const size_t in_elems = pad32((size_t)CK * ID * IH * IWP);
+  const size_t w_elems = pad32((size_t)taps * CK * COP);
   size_t total = 2 * in_elems + (gwc ? 3 : 2) * w_elems;
-  int IWR = 0;
-  if (gwc) {
-    IWR = round_up(IWP + ID - 1, 4);
-    total += (size_t)CK * cpg * IH * IWP + (size_t)CK * cpg * IH * IWR;
+  int IWR = 0, IWL = 0;
+  if (gwc) {  // staging boxes start on a multiple of 4 columns (TMA): up to 3 extra columns on the left
+    IWL = round_up(IWP + 3, 4);
+    IWR = round_up(IWP + ID - 1 + 3, 4);
+    total += pad32((size_t)CK * cpg * IH * IWL) + pad32((size_t)CK * cpg * IH * IWR);
   }
   if (IWR_out) *IWR_out = IWR;
-  return total * sizeof(float);
+  if (IWL_out) *IWL_out = IWL;
+  return total * sizeof(float) + 128 /* base alignment slack */ + 32 /* mbarriers */;
 }
 
 // Per-SM residency estimate: the kernels compile to <=128 registers, so at most 512 threads per SM;
@@ -609,7 +142,7 @@ static int resident_ctas(int nthreads, size_t smem) {
 }
 
 static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int KD, int S, int CK, int COP, bool gwc,
-                          int cpg, Tiling* out, double* best_cost) {
+                          int cpg, int xo, Tiling* out, double* best_cost) {
   bool found = false;
   for (int slots = 32; slots * ncog <= 320 && slots <= 256; slots += 32) {
     for (int TWG = 1; TWG <= 16; TWG *= 2) {
@@ -623,13 +156,14 @@ static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int 
         const double waste = (double)ceil_div(Jw, TW) * TW / Jw * ceil_div(Jh, TH) * TH / Jh * ceil_div(Jd, TD) * TD / Jd;
         const int ID = (TD - 1) * S + KD, IH = (TH - 1) * S + KH;
         const int XN = 3 * S + KW, XL = (XN + 3) / 4 * 4;
-        int IWP = (TWG - 1) * 4 * S + XL;
+        // row window of the last thread: aligned float4s (xo=0) or scalar@3 + float4s from column 4 (xo=3)
+        int IWP = (TWG - 1) * 4 * S + (xo == 3 ? 4 + 4 * ((XN + 2) / 4) : XL);
         if (S == 1 && TWG < 8) {
           const int want = (4 * TWG) % 32;  // rows of an 8-lane LDS.128 phase land on distinct banks
           while (IWP % 32 != want) IWP += 4;
         }
-        int IWR = 0;
-        const size_t smem = conv_smem_bytes(CK, ID, IH, IWP, KD * KH * KW, COP, gwc, cpg, &IWR);
+        int IWR = 0, IWL = 0;
+        const size_t smem = conv_smem_bytes(CK, ID, IH, IWP, KD * KH * KW, COP, gwc, cpg, &IWR, &IWL);
         if (smem > 224 * 1024) continue;
         const int nthreads = slots * ncog;
         const int ctas = resident_ctas(nthreads, smem);
@@ -652,6 +186,7 @@ static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int 
           out->ID = ID;
           out->IH = IH;
           out->IWR = IWR;
+          out->IWL = IWL;
           out->smem = smem;
         }
       }
@@ -660,31 +195,55 @@ static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int 
   return found;
 }
 
-typedef void (*conv_fn_t)(const ConvK);
-
-template <int KW, int S>
-static conv_fn_t pick_cog_ck(int COG, int CK, bool gwc) {
-  if (gwc) {
-    if (!(COG == 8 && KW == 3 && S == 1)) return nullptr;
-    return CK == 8 ? (conv_fn_t)conv_kernel<3, 1, 8, 8, true> : CK == 4 ? (conv_fn_t)conv_kernel<3, 1, 8, 4, true> : nullptr;
+static conv_fn_t pick_kernel(int KW, int S, int COG, int CK, bool gwc, bool tma, int xo) {
+  if (S == 1) {
+    if (KW == 1) return conv_kernels_k1(COG, CK, gwc, tma, xo);
+    if (KW == 2) return conv_kernels_k2(COG, CK, gwc, tma, xo);
+    if (KW == 3) return conv_kernels_k3(COG, CK, gwc, tma, xo);
+    if (KW == 5) return conv_kernels_k5(COG, CK, gwc, tma, xo);
+  } else if (S == 2 && KW == 3) {
+    return conv_kernels_k3s2(COG, CK, gwc, tma, xo);
   }
-  if (COG == 8 && CK == 8) return conv_kernel<KW, S, 8, 8, false>;
-  if (COG == 8 && CK == 4) return conv_kernel<KW, S, 8, 4, false>;
-  if (COG == 8 && CK == 1) return conv_kernel<KW, S, 8, 1, false>;
-  if (COG == 2 && CK == 8) return conv_kernel<KW, S, 2, 8, false>;
   return nullptr;
 }
 
-static conv_fn_t pick_kernel(int KW, int S, int COG, int CK, bool gwc) {
-  if (S == 1) {
-    if (KW == 1) return pick_cog_ck<1, 1>(COG, CK, gwc);
-    if (KW == 2) return pick_cog_ck<2, 1>(COG, CK, gwc);
-    if (KW == 3) return pick_cog_ck<3, 1>(COG, CK, gwc);
-    if (KW == 5) return pick_cog_ck<5, 1>(COG, CK, gwc);
-  } else if (S == 2 && KW == 3) {
-    return pick_cog_ck<3, 2>(COG, CK, gwc);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encoder() {
+  static encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (encode_tiled_fn)ptr;
+    else
+      cudaGetLastError();
   }
-  return nullptr;
+  return fn;
+}
+
+// fp32 tensor map of rank `rank` (innermost first); strides in elements for dims 1..rank-1
+static bool encode_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const long long* strides_elems,
+                       const int* box) {
+  encode_tiled_fn enc = get_encoder();
+  if (!enc) return false;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+    es[i] = 1;
+    if (box[i] < 1 || box[i] > 256) return false;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = (cuuint64_t)strides_elems[i] * sizeof(float);
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Launch plans are memoised per shape: the tiling search and the occupancy query cost ~50 us on the
@@ -695,7 +254,8 @@ struct PlanKey {
 };
 struct Plan {
   Tiling tl;
-  conv_fn_t fn;
+  conv_fn_t fn;         // cp.async pipeline (any strides)
+  conv_fn_t fn_tma[2];  // TMA pipeline for window offset XO = 0 / 3 (nullptr if not instantiated)
   int cosplit, COP, COG, CK, blocks_per_sm;
 };
 
@@ -839,7 +399,7 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
     auto it = plans.find(key);
     if (it == plans.end()) {
       Plan np;
-      np.COG = g.CoutPad == 2 ? 2 : 8;
+      np.COG = g.CoutPad == 4 ? 4 : 8;
       np.CK = g.CinPad == 1 ? 1 : 8;
       // a CTA owns at most 80 output channels (10 channel groups x >=32 voxel slots <= 320 threads)
       int cosplit = 1;
@@ -849,11 +409,13 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
       const int ncog = np.COP / np.COG;
       // search tile shapes and channel-chunk depth (8 or 4: a shallower chunk halves the staged
       // brick, which buys resident warps on the wide 8-channel layers)
+      // row geometry leaves room for the XO=3 window whenever some launch of this layer may use it
+      const int xo_plan = (!gwc && (d->transposed || (d->pw & 3) == 1)) ? 3 : 0;
       double best = 1e30;
-      bool tiled = choose_tiling(Jw, Jh, Jd, ncog, g.KW, g.KH, g.KD, S, np.CK, np.COP, gwc, k.cpg, &np.tl, &best);
+      bool tiled = choose_tiling(Jw, Jh, Jd, ncog, g.KW, g.KH, g.KD, S, np.CK, np.COP, gwc, k.cpg, xo_plan, &np.tl, &best);
       if (np.CK == 8 && np.COG == 8) {
         Tiling t4;
-        if (choose_tiling(Jw, Jh, Jd, ncog, g.KW, g.KH, g.KD, S, 4, np.COP, gwc, k.cpg, &t4, &best)) {
+        if (choose_tiling(Jw, Jh, Jd, ncog, g.KW, g.KH, g.KD, S, 4, np.COP, gwc, k.cpg, xo_plan, &t4, &best)) {
           np.tl = t4;
           np.CK = 4;
           tiled = true;
@@ -861,17 +423,22 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
       }
       ESM_REQUIRE(tiled, "conv: no tiling for Cin=%d Cout=%d k=(%d,%d,%d)%s", d->Cin, d->Cout, d->kd, d->kh, d->kw,
                   gwc ? " +gwc" : "");
-      np.fn = pick_kernel(g.KW, S, np.COG, np.CK, gwc);
+      np.fn = pick_kernel(g.KW, S, np.COG, np.CK, gwc, false, 0);
+      np.fn_tma[0] = pick_kernel(g.KW, S, np.COG, np.CK, gwc, true, 0);
+      np.fn_tma[1] = pick_kernel(g.KW, S, np.COG, np.CK, gwc, true, 3);
       ESM_REQUIRE(np.fn, "conv: unsupported kernel width %d / stride %d%s", g.KW, S, gwc ? " with ESM_SRC_GWC" : "");
       np.blocks_per_sm = 1;
       if (num_sms > 0) {
-        if (np.tl.smem > 48 * 1024 &&
-            cudaFuncSetAttribute((const void*)np.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess)
-          return check_launch("conv(cudaFuncSetAttribute)");
-        int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)np.fn, np.tl.slots * ncog, np.tl.smem) != cudaSuccess)
-          return check_launch("conv(occupancy)");
-        np.blocks_per_sm = occ > 0 ? occ : 1;
+        conv_fn_t fns[3] = {np.fn, np.fn_tma[0], np.fn_tma[1]};
+        for (int i = 0; i < 3; ++i) {
+          if (!fns[i]) continue;
+          if (cudaFuncSetAttribute((const void*)fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
+            return check_launch("conv(cudaFuncSetAttribute)");
+          int occ = 0;
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fns[i], np.tl.slots * ncog, np.tl.smem) != cudaSuccess)
+            return check_launch("conv(occupancy)");
+          if (i == 0 || occ < np.blocks_per_sm) np.blocks_per_sm = occ > 0 ? occ : 1;
+        }
       }
       if (getenv("ESM_DEBUG_PLAN"))
         fprintf(stderr, "[esm plan] Cin=%d Cout=%d k=(%d,%d,%d) s=%d%s%s J=(%d,%d,%d): CK=%d COP=%d cosplit=%d tile=(%d,%d,%d) "
@@ -896,6 +463,8 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   k.IH = tl.IH;
   k.IWP = tl.IWP;
   k.IWR = tl.IWR;
+  k.IWL = tl.IWL;
+  k.pzw_sel = -1;
   k.tilesW = ceil_div(Jw, tl.TWG * 4);
   k.tilesH = ceil_div(Jh, tl.TH);
   k.tilesD = ceil_div(Jd, tl.TD);
@@ -907,8 +476,72 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
     set_error("conv: no CUDA device");
     return ESM_ERR_CUDA;
   }
+  // ---- TMA eligibility: 16-byte aligned bases and pitches, channel chunks that never straddle two sources ----
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  bool use_tma = get_encoder() != nullptr && !getenv("ESM_NO_TMA");
+  auto aligned = [](const esm_src_t& sv, bool has_d) {
+    return (reinterpret_cast<uintptr_t>(sv.ptr) & 15) == 0 && sv.sH % 4 == 0 && sv.sC % 4 == 0 && sv.sB % 4 == 0 &&
+           (!has_d || sv.sD % 4 == 0);
+  };
+  if (use_tma && (reinterpret_cast<uintptr_t>(d->weight) & 15)) use_tma = false;
+  if (use_tma && !gwc && d->in_mul) use_tma = false;
+  for (int i = 0; use_tma && i < d->nsrc; ++i) {
+    if (!aligned(d->src[i], d->Din > 1 && !gwc)) use_tma = false;
+    if (!gwc && i + 1 < d->nsrc && d->src[i].C % plan.CK) use_tma = false;
+  }
+  if (use_tma) {
+    const int taps = g.KD * g.KH * g.KW;
+    if (gwc) {
+      const int nch = plan.CK * k.cpg;
+      for (int i = 0; i < 2 && use_tma; ++i) {
+        const esm_src_t& sv = d->src[i];
+        const long long dims[5] = {d->Win, d->Hin, 1, sv.C, d->B};
+        const long long str[4] = {sv.sH, sv.sH * d->Hin, sv.sC, sv.sB};
+        const int box[5] = {i == 0 ? tl.IWL : tl.IWR, tl.IH, 1, nch, 1};
+        use_tma = sv.sC >= sv.sH * d->Hin && encode_map(&maps.src[i], sv.ptr, 5, dims, str, box);
+      }
+    } else {
+      for (int i = 0; i < d->nsrc && use_tma; ++i) {
+        const esm_src_t& sv = d->src[i];
+        const long long sD = d->Din > 1 ? sv.sD : sv.sH * d->Hin;
+        const long long dims[5] = {d->Win, d->Hin, d->Din, sv.C, d->B};
+        const long long str[4] = {sv.sH, sD, sv.sC, sv.sB};
+        const int box[5] = {tl.IWP, tl.IH, tl.ID, plan.CK, 1};
+        use_tma = encode_map(&maps.src[i], sv.ptr, 5, dims, str, box);
+      }
+    }
+    if (use_tma) {
+      const long long dims[3] = {g.CoutPad, g.CinPad, (long long)taps * g.phases};
+      const long long str[2] = {g.CoutPad, (long long)g.CoutPad * g.CinPad};
+      const int box[3] = {plan.COP, plan.CK, taps};
+      use_tma = encode_map(&maps.w, d->weight, 3, dims, str, box);
+    }
+  }
+  // window offset of the TMA brick: boxes must start on a multiple of 4 columns
+  const int xo_a = gwc ? 0 : ((4 - ((d->transposed ? 1 : d->pw) & 3)) & 3);  // transposed: W phase 0 has pad 1
+  if (use_tma && !gwc && xo_a != 0 && xo_a != 3) use_tma = false;
+  if (use_tma && !plan.fn_tma[xo_a == 3]) use_tma = false;
+  if (use_tma && d->transposed && !plan.fn_tma[0]) use_tma = false;
+  if (getenv("ESM_DEBUG_PLAN")) fprintf(stderr, "[esm launch] Cin=%d Cout=%d tma=%d xo=%d\n", d->Cin, d->Cout, (int)use_tma, xo_a);
   const long long resident = (long long)num_sms * plan.blocks_per_sm;
-  const unsigned grid = (unsigned)(total < resident ? total : resident);  // persistent CTAs stride over the tiles
-  plan.fn<<<grid, k.nthreads, tl.smem, (cudaStream_t)stream>>>(k);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!use_tma) {
+    const unsigned grid = (unsigned)(total < resident ? total : resident);  // persistent CTAs stride over the tiles
+    plan.fn<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
+  } else if (!d->transposed) {
+    const unsigned grid = (unsigned)(total < resident ? total : resident);
+    plan.fn_tma[xo_a == 3]<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
+  } else {
+    // sub-pixel phases along W have pad 1 (phase 0, window offset 3) and pad 0 (phase 1, offset 0):
+    // one launch per W phase, each enumerating the (d,h) phases
+    k.phases = g.phases / 2;
+    k.total_work = (int)(total / 2);
+    const unsigned grid = (unsigned)(k.total_work < resident ? k.total_work : resident);
+    k.pzw_sel = 0;
+    plan.fn_tma[1]<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
+    k.pzw_sel = 1;
+    plan.fn_tma[0]<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
+  }
   return check_launch("conv");
 }
