@@ -35,7 +35,8 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
   d = *reinterpret_cast<float2*>(&dd);
 }
 
-__device__ __forceinline__ float apply_act(float x, int act) {
+// kept out of line on purpose: one copy of the erff / expf code per kernel instead of one per call site
+static __device__ __noinline__ float apply_act(float x, int act) {
   switch (act) {
     case ESM_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
     case ESM_ACT_RELU: return fmaxf(x, 0.0f);

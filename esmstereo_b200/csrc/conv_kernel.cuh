@@ -554,6 +554,10 @@ __global__ void __launch_bounds__(320, 1) conv_kernel(const __grid_constant__ Co
     }
 
     // ---------------- epilogue (last channel chunk of a tile) ----------------
+    // Deliberately NOT unrolled over the 32 outputs: an unrolled epilogue (7-way activation switch
+    // with erff/expf, twice, plus multiply / residual / pixel-shuffle variants) is ~15k SASS
+    // instructions, which thrashes the instruction cache once per tile (ncu: 40% stall_no_inst).
+    // The accumulators take a round trip through a small local array instead.
     if ((item % nch) == nch - 1) {
       const TileCtx t = decode_work(p, blockIdx.x + (item / nch) * gridDim.x);
       const int osd = (p.transposed && p.phases_d == 2) ? 2 : 1;
@@ -564,42 +568,49 @@ __global__ void __launch_bounds__(320, 1) conv_kernel(const __grid_constant__ Co
       const int od = jd * osd + t.pz_d;
       const int oh = jh * osw + t.pz_h;
       const int b = t.b;
-      if (od < p.OD && oh < p.OH) {
+      float r[COG * NV];
 #pragma unroll
+      for (int j = 0; j < COG; ++j)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) r[j * NV + v] = (j & 1) ? acc[v][j / 2].y : acc[v][j / 2].x;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < COG / 2; ++j) acc[v][j] = make_float2(0.f, 0.f);
+      if (od < p.OD && oh < p.OH) {
+        const int act = p.act, act2 = p.act2;
+#pragma unroll 1
         for (int j = 0; j < COG; ++j) {
           const int co = t.co_base + cog * COG + j;
           if (co >= p.Cout) break;
           const float sc = p.scale ? __ldg(p.scale + co) : 1.f;
           const float sh = p.shift ? __ldg(p.shift + co) : 0.f;
-          float r[NV];
-#pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            const float a = (j & 1) ? acc[v][j / 2].y : acc[v][j / 2].x;
-            r[v] = apply_act(fmaf(a, sc, sh), p.act);
-          }
+#pragma unroll 1
+          for (int v = 0; v < NV; ++v) r[j * NV + v] = apply_act(fmaf(r[j * NV + v], sc, sh), act);
           if (p.ps == 0) {
             const long long obase = (long long)b * p.oB + (long long)co * p.oC + (long long)od * p.oD + (long long)oh * p.oH;
             const float* om = p.out_mul ? p.out_mul + (long long)b * p.omB + (long long)co * p.omC + (long long)oh * p.omH : nullptr;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              const int ow = (jw0 + v) * osw + t.pz_w;
-              if (ow < p.OW) {
-                float y = r[v];
-                if (om) y *= __ldg(om + ow);
-                if (p.residual) y += __ldg(p.residual + obase + ow);
-                y = apply_act(y, p.act2) * p.out_scale;
-                r[v] = y;
+            if (om || p.residual || act2 != ESM_ACT_NONE || p.out_scale != 1.0f) {
+#pragma unroll 1
+              for (int v = 0; v < NV; ++v) {
+                const int ow = (jw0 + v) * osw + t.pz_w;
+                if (ow < p.OW) {
+                  float y = r[j * NV + v];
+                  if (om) y *= __ldg(om + ow);
+                  if (p.residual) y += __ldg(p.residual + obase + ow);
+                  r[j * NV + v] = apply_act(y, act2) * p.out_scale;
+                }
               }
             }
             float* o = p.out + obase;
             const int ow0 = jw0 * osw + t.pz_w;
             if (osw == 1 && ow0 + NV <= p.OW && ((reinterpret_cast<uintptr_t>(o + ow0) & 15) == 0)) {
-              *reinterpret_cast<float4*>(o + ow0) = make_float4(r[0], r[1], r[2], r[3]);
+              *reinterpret_cast<float4*>(o + ow0) = make_float4(r[j * NV + 0], r[j * NV + 1], r[j * NV + 2], r[j * NV + 3]);
             } else {
-#pragma unroll
+#pragma unroll 1
               for (int v = 0; v < NV; ++v) {
                 const int ow = (jw0 + v) * osw + t.pz_w;
-                if (ow < p.OW) o[ow] = r[v];
+                if (ow < p.OW) o[ow] = r[j * NV + v];
               }
             }
           } else {
@@ -609,18 +620,14 @@ __global__ void __launch_bounds__(320, 1) conv_kernel(const __grid_constant__ Co
             const int a = (co / rr) % rr;
             const int bb = co % rr;
             float* o = p.out + (long long)b * p.oB + (long long)c * p.oC + (long long)(oh * rr + a) * p.oH;
-#pragma unroll
+#pragma unroll 1
             for (int v = 0; v < NV; ++v) {
               const int ow = jw0 + v;
-              if (ow < p.OW) o[ow * rr + bb] = apply_act(r[v], p.act2) * p.out_scale;
+              if (ow < p.OW) o[ow * rr + bb] = apply_act(r[j * NV + v], act2) * p.out_scale;
             }
           }
         }
       }
-#pragma unroll
-      for (int v = 0; v < NV; ++v)
-#pragma unroll
-        for (int j = 0; j < COG / 2; ++j) acc[v][j] = make_float2(0.f, 0.f);
     }
     __syncthreads();  // stage (item&1) / V[item&1] may be overwritten from here on
     if (TMA && !GWC && tid == 0 && item + 2 < n_items) tma_issue(item + 2, item & 1);
