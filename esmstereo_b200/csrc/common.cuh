@@ -35,8 +35,7 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
   d = *reinterpret_cast<float2*>(&dd);
 }
 
-// kept out of line on purpose: one copy of the erff / expf code per kernel instead of one per call site
-static __device__ __noinline__ float apply_act(float x, int act) {
+__device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
     case ESM_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
     case ESM_ACT_RELU: return fmaxf(x, 0.0f);
@@ -45,6 +44,25 @@ static __device__ __noinline__ float apply_act(float x, int act) {
     case ESM_ACT_2SIGMOID: return 2.0f * (1.0f / (1.0f + expf(-x)));
     case ESM_ACT_RELU6: return fminf(fmaxf(x, 0.0f), 6.0f);
     default: return x;
+  }
+}
+
+// Activation of 4 values at once, kept out of line on purpose: one copy of the erff / expf code per
+// kernel instead of one per call site, with 4 independent evaluations in flight per call.
+static __device__ __noinline__ float4 apply_act4(float4 v, int act) {
+  switch (act) {
+#define ESM_ACT4_CASE(CODE)                                                                                   \
+  case CODE:                                                                                                  \
+    return make_float4(apply_act(v.x, CODE), apply_act(v.y, CODE), apply_act(v.z, CODE), apply_act(v.w, CODE));
+    ESM_ACT4_CASE(ESM_ACT_GELU)
+    ESM_ACT4_CASE(ESM_ACT_RELU)
+    ESM_ACT4_CASE(ESM_ACT_SILU)
+    ESM_ACT4_CASE(ESM_ACT_SIGMOID)
+    ESM_ACT4_CASE(ESM_ACT_2SIGMOID)
+    ESM_ACT4_CASE(ESM_ACT_RELU6)
+#undef ESM_ACT4_CASE
+    default:
+      return v;
   }
 }
 

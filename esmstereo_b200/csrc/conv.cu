@@ -132,7 +132,7 @@ static size_t conv_smem_bytes(int CK, int ID, int IH, int IWP, int taps, int COP
   return total * sizeof(float) + 128 /* base alignment slack */ + 32 /* mbarriers */;
 }
 
-// Per-SM residency estimate: the kernels compile to <=128 registers, so at most 512 threads per SM;
+// Per-SM residency estimate: the kernels compile to <=128 registers (__launch_bounds__(256, 2)), so at most 512 threads per SM;
 // shared memory: 227 KB usable per SM, 1 KB reserved per CTA.
 static int resident_ctas(int nthreads, size_t smem) {
   const int by_regs = 512 / nthreads;
@@ -144,7 +144,7 @@ static int resident_ctas(int nthreads, size_t smem) {
 static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int KD, int S, int CK, int COP, bool gwc,
                           int cpg, int xo, Tiling* out, double* best_cost) {
   bool found = false;
-  for (int slots = 32; slots * ncog <= 320 && slots <= 256; slots += 32) {
+  for (int slots = 32; slots * ncog <= 256; slots += 32) {
     for (int TWG = 1; TWG <= 16; TWG *= 2) {
       if (slots % TWG) continue;
       const int R = slots / TWG;
@@ -401,9 +401,9 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
       Plan np;
       np.COG = g.CoutPad == 4 ? 4 : 8;
       np.CK = g.CinPad == 1 ? 1 : 8;
-      // a CTA owns at most 80 output channels (10 channel groups x >=32 voxel slots <= 320 threads)
+      // a CTA owns at most 64 output channels (8 channel groups x >=32 voxel slots = 256 threads)
       int cosplit = 1;
-      while (g.CoutPad / cosplit > 80 || g.CoutPad % cosplit || (g.CoutPad / cosplit) % np.COG) ++cosplit;
+      while (g.CoutPad / cosplit > 64 || g.CoutPad % cosplit || (g.CoutPad / cosplit) % np.COG) ++cosplit;
       np.cosplit = cosplit;
       np.COP = g.CoutPad / cosplit;
       const int ncog = np.COP / np.COG;

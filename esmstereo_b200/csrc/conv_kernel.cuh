@@ -147,7 +147,7 @@ __device__ __forceinline__ TileCtx decode_work(const ConvK& p, int w) {
 // 16-byte boundary in W, so for pad-1 kernels the brick origin is 3 columns left of the first tap
 // (XO=3: one scalar LDS + aligned LDS.128s); XO=0 otherwise.
 template <int KW, int S, int COG, int CK, bool GWC, bool TMA, int XO>
-__global__ void __launch_bounds__(320, 1) conv_kernel(const __grid_constant__ ConvK p, const __grid_constant__ ConvMaps maps) {
+__global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ ConvK p, const __grid_constant__ ConvMaps maps) {
   extern __shared__ __align__(16) float smem_raw[];
   // TMA destinations must be 128-byte aligned; the host over-allocates by 128 bytes
   float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -321,8 +321,11 @@ __global__ void __launch_bounds__(320, 1) conv_kernel(const __grid_constant__ Co
     const float* mb = p.in_mul ? p.in_mul + (long long)t.b * p.imB : nullptr;
     int ro;
     right_origin(iw0, id0, &ro);
-    const float inv = 1.0f / (float)p.cpg;
-    const bool pow2 = (p.cpg & (p.cpg - 1)) == 0;
+    const int cpg = p.cpg;
+    const float inv = 1.0f / (float)cpg;
+    const bool pow2 = (cpg & (cpg - 1)) == 0;
+    const int lplane = IH * IWL, rplane = IH * IWR;
+    // a thread owns (group, row, column) positions and walks the ID disparity planes of each
     for (int i = tid; i < CK * plane; i += NT) {
       const int g = i / plane;
       const int rem = i - g * plane;
@@ -332,19 +335,29 @@ __global__ void __launch_bounds__(320, 1) conv_kernel(const __grid_constant__ Co
       const bool ok = (c0 + g < p.Cin) && h >= 0 && h < p.Hin && x >= 0 && x < p.Win;
       float m = 1.f;
       if (mb && ok) m = __ldg(mb + (long long)(c0 + g) * p.imC + (long long)h * p.imH + x);
-      const float* lp = s_L + (g * p.cpg) * (IH * IWL) + hy * IWL + col + LO;
-      const float* rp = s_R + (g * p.cpg) * (IH * IWR) + hy * IWR + col + (ID - 1) + ro;
-      for (int dz = 0; dz < ID; ++dz) {
-        const int d = id0 + dz;
-        float v = 0.f;
-        if (ok && d >= 0 && d < p.Din && x - d >= 0) {
-          float s = 0.f;
-          for (int q = 0; q < p.cpg; ++q)  // un-contracted: (fea1*fea2).mean(2), submodule.py:147
-            s = __fadd_rn(s, __fmul_rn(lp[q * IH * IWL], rp[q * IH * IWR - dz]));
-          v = pow2 ? s * inv : s / (float)p.cpg;
-          v *= m;
+      const float* lp = s_L + (g * cpg) * lplane + hy * IWL + col + LO;
+      const float* rp = s_R + (g * cpg) * rplane + hy * IWR + col + (ID - 1) + ro;
+      float* vp = dst + (g * ID) * plane + rem;
+      if (cpg == 2) {
+        const float l0 = lp[0], l1 = lp[lplane];
+        for (int dz = 0; dz < ID; ++dz) {
+          const int d = id0 + dz;
+          // un-contracted arithmetic: (fea1*fea2).mean(2), submodule.py:147
+          const float sum = __fadd_rn(__fmul_rn(l0, rp[-dz]), __fmul_rn(l1, rp[rplane - dz]));
+          const bool valid = ok && d >= 0 && d < p.Din && x >= d;
+          vp[dz * plane] = valid ? __fmul_rn(__fmul_rn(sum, 0.5f), m) : 0.f;
         }
-        dst[(g * ID + dz) * plane + rem] = v;
+      } else {
+        for (int dz = 0; dz < ID; ++dz) {
+          const int d = id0 + dz;
+          float v = 0.f;
+          if (ok && d >= 0 && d < p.Din && x >= d) {
+            float sum = 0.f;
+            for (int q = 0; q < cpg; ++q) sum = __fadd_rn(sum, __fmul_rn(lp[q * lplane], rp[q * rplane - dz]));
+            v = (pow2 ? sum * inv : sum / (float)cpg) * m;
+          }
+          vp[dz * plane] = v;
+        }
       }
     }
   };
@@ -554,10 +567,10 @@ __global__ void __launch_bounds__(320, 1) conv_kernel(const __grid_constant__ Co
     }
 
     // ---------------- epilogue (last channel chunk of a tile) ----------------
-    // Deliberately NOT unrolled over the 32 outputs: an unrolled epilogue (7-way activation switch
-    // with erff/expf, twice, plus multiply / residual / pixel-shuffle variants) is ~15k SASS
-    // instructions, which thrashes the instruction cache once per tile (ncu: 40% stall_no_inst).
-    // The accumulators take a round trip through a small local array instead.
+    // Code size matters here: a fully inlined epilogue (7-way activation switch with erff/expf,
+    // twice, per output) is ~15k SASS instructions and thrashes the instruction cache once per tile
+    // (ncu: 40% stall_no_inst).  The activation is an out-of-line call on 4 values at a time (ILP 4
+    // through the erf polynomial), everything else stays in registers.
     if ((item % nch) == nch - 1) {
       const TileCtx t = decode_work(p, blockIdx.x + (item / nch) * gridDim.x);
       const int osd = (p.transposed && p.phases_d == 2) ? 2 : 1;
@@ -568,66 +581,74 @@ __global__ void __launch_bounds__(320, 1) conv_kernel(const __grid_constant__ Co
       const int od = jd * osd + t.pz_d;
       const int oh = jh * osw + t.pz_h;
       const int b = t.b;
-      float r[COG * NV];
-#pragma unroll
-      for (int j = 0; j < COG; ++j)
-#pragma unroll
-        for (int v = 0; v < NV; ++v) r[j * NV + v] = (j & 1) ? acc[v][j / 2].y : acc[v][j / 2].x;
-#pragma unroll
-      for (int v = 0; v < NV; ++v)
-#pragma unroll
-        for (int j = 0; j < COG / 2; ++j) acc[v][j] = make_float2(0.f, 0.f);
       if (od < p.OD && oh < p.OH) {
         const int act = p.act, act2 = p.act2;
-#pragma unroll 1
+        const bool post = p.out_mul || p.residual || act2 != ESM_ACT_NONE || p.out_scale != 1.0f;
+#pragma unroll
         for (int j = 0; j < COG; ++j) {
           const int co = t.co_base + cog * COG + j;
-          if (co >= p.Cout) break;
-          const float sc = p.scale ? __ldg(p.scale + co) : 1.f;
-          const float sh = p.shift ? __ldg(p.shift + co) : 0.f;
-#pragma unroll 1
-          for (int v = 0; v < NV; ++v) r[j * NV + v] = apply_act(fmaf(r[j * NV + v], sc, sh), act);
-          if (p.ps == 0) {
-            const long long obase = (long long)b * p.oB + (long long)co * p.oC + (long long)od * p.oD + (long long)oh * p.oH;
-            const float* om = p.out_mul ? p.out_mul + (long long)b * p.omB + (long long)co * p.omC + (long long)oh * p.omH : nullptr;
-            if (om || p.residual || act2 != ESM_ACT_NONE || p.out_scale != 1.0f) {
-#pragma unroll 1
-              for (int v = 0; v < NV; ++v) {
-                const int ow = (jw0 + v) * osw + t.pz_w;
-                if (ow < p.OW) {
-                  float y = r[j * NV + v];
-                  if (om) y *= __ldg(om + ow);
-                  if (p.residual) y += __ldg(p.residual + obase + ow);
-                  r[j * NV + v] = apply_act(y, act2) * p.out_scale;
+          if (co < p.Cout) {
+            const float sc = p.scale ? __ldg(p.scale + co) : 1.f;
+            const float sh = p.shift ? __ldg(p.shift + co) : 0.f;
+            float4 r;
+            r.x = fmaf((j & 1) ? acc[0][j / 2].y : acc[0][j / 2].x, sc, sh);
+            r.y = fmaf((j & 1) ? acc[1][j / 2].y : acc[1][j / 2].x, sc, sh);
+            r.z = fmaf((j & 1) ? acc[2][j / 2].y : acc[2][j / 2].x, sc, sh);
+            r.w = fmaf((j & 1) ? acc[3][j / 2].y : acc[3][j / 2].x, sc, sh);
+            if (act != ESM_ACT_NONE) r = apply_act4(r, act);
+            if (p.ps == 0) {
+              const long long obase = (long long)b * p.oB + (long long)co * p.oC + (long long)od * p.oD + (long long)oh * p.oH;
+              const int ow0 = jw0 * osw + t.pz_w;
+              if (post) {
+                const float* om = p.out_mul ? p.out_mul + (long long)b * p.omB + (long long)co * p.omC + (long long)oh * p.omH : nullptr;
+                float* rv = &r.x;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                  const int ow = ow0 + v * osw;
+                  if (ow < p.OW) {
+                    if (om) rv[v] *= __ldg(om + ow);
+                    if (p.residual) rv[v] += __ldg(p.residual + obase + ow);
+                  }
+                }
+                if (act2 != ESM_ACT_NONE) r = apply_act4(r, act2);
+                r.x *= p.out_scale;
+                r.y *= p.out_scale;
+                r.z *= p.out_scale;
+                r.w *= p.out_scale;
+              }
+              float* o = p.out + obase;
+              if (osw == 1 && ow0 + NV <= p.OW && ((reinterpret_cast<uintptr_t>(o + ow0) & 15) == 0)) {
+                *reinterpret_cast<float4*>(o + ow0) = r;
+              } else {
+                const float* rv = &r.x;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                  const int ow = ow0 + v * osw;
+                  if (ow < p.OW) o[ow] = rv[v];
                 }
               }
-            }
-            float* o = p.out + obase;
-            const int ow0 = jw0 * osw + t.pz_w;
-            if (osw == 1 && ow0 + NV <= p.OW && ((reinterpret_cast<uintptr_t>(o + ow0) & 15) == 0)) {
-              *reinterpret_cast<float4*>(o + ow0) = make_float4(r[j * NV + 0], r[j * NV + 1], r[j * NV + 2], r[j * NV + 3]);
             } else {
-#pragma unroll 1
+              // PixelShuffle(r): channel co -> (c, a, bb); out[c, oh*r + a, ow*r + bb]   (2D only)
+              const int rr = p.ps;
+              const int c = co / (rr * rr);
+              const int a = (co / rr) % rr;
+              const int bb = co % rr;
+              float* o = p.out + (long long)b * p.oB + (long long)c * p.oC + (long long)(oh * rr + a) * p.oH;
+              if (act2 != ESM_ACT_NONE) r = apply_act4(r, act2);
+              const float* rv = &r.x;
+#pragma unroll
               for (int v = 0; v < NV; ++v) {
-                const int ow = (jw0 + v) * osw + t.pz_w;
-                if (ow < p.OW) o[ow] = r[j * NV + v];
+                const int ow = jw0 + v;
+                if (ow < p.OW) o[ow * rr + bb] = rv[v] * p.out_scale;
               }
-            }
-          } else {
-            // PixelShuffle(r): channel co -> (c, a, bb); out[c, oh*r + a, ow*r + bb]   (2D only)
-            const int rr = p.ps;
-            const int c = co / (rr * rr);
-            const int a = (co / rr) % rr;
-            const int bb = co % rr;
-            float* o = p.out + (long long)b * p.oB + (long long)c * p.oC + (long long)(oh * rr + a) * p.oH;
-#pragma unroll 1
-            for (int v = 0; v < NV; ++v) {
-              const int ow = jw0 + v;
-              if (ow < p.OW) o[ow * rr + bb] = apply_act(r[j * NV + v], act2) * p.out_scale;
             }
           }
         }
       }
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < COG / 2; ++j) acc[v][j] = make_float2(0.f, 0.f);
     }
     __syncthreads();  // stage (item&1) / V[item&1] may be overwritten from here on
     if (TMA && !GWC && tid == 0 && item + 2 < n_items) tma_issue(item + 2, item & 1);
