@@ -30,7 +30,14 @@ namespace esm {
 // ------------------------------------------------------------------------------------------
 // weight packing / BN folding
 // ------------------------------------------------------------------------------------------
-static int pad_cout(int Cout) { return Cout <= 4 ? 4 : round_up(Cout, 8); }
+// output channels are padded to 4 (single-channel heads: one 16-byte weight row) or to a multiple
+// of 8; above 64 they are split over n CTAs of COP = round_up(ceil(Cout/n), 8) channels each
+static int pad_cout(int Cout) {
+  if (Cout <= 4) return 4;
+  if (Cout <= 64) return round_up(Cout, 8);
+  const int n = ceil_div(Cout, 64);
+  return n * round_up(ceil_div(Cout, n), 8);
+}
 // single-channel inputs (disparity / confidence maps) get their own CK=1 instantiation instead of
 // 8x zero padding (only instantiated for the 8-wide channel groups)
 static int pad_cin(int Cin, int Cout) { return (Cin == 1 && Cout > 4) ? 1 : round_up(Cin, 8); }
@@ -142,7 +149,8 @@ static int resident_ctas(int nthreads, size_t smem) {
 }
 
 static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int KD, int S, int CK, int COP, bool gwc,
-                          int cpg, int xo, Tiling* out, double* best_cost) {
+                          int cpg, int xo, long long work_mult, int num_sms, double extra_cost, Tiling* out,
+                          double* best_cost) {
   bool found = false;
   for (int slots = 32; slots * ncog <= 256; slots += 32) {
     for (int TWG = 1; TWG <= 16; TWG *= 2) {
@@ -174,7 +182,12 @@ static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int 
         // (small CTAs / small channel chunks sync more often).
         const double warps = (double)ctas * nthreads / 32.0;
         const double occ = warps >= 14.0 ? 1.0 : 14.0 / warps;
-        const double cost = waste * occ * (1.0 + 0.05 * halo) * (1.0 + 8.0 / slots) * (CK >= 8 ? 1.0 : 1.04);
+        // grid fill: small layers (the coarse hourglass levels) must still cover all SMs, and the
+        // last wave of a persistent grid should not be mostly empty
+        const long long tiles = (long long)ceil_div(Jw, TW) * ceil_div(Jh, TH) * ceil_div(Jd, TD) * work_mult;
+        const long long wave = (long long)(num_sms > 0 ? num_sms : 148) * ctas;
+        const double fill = (double)tiles / (double)(ceil_div_ll(tiles, wave) * wave);
+        const double cost = waste * occ / fill * (1.0 + 0.05 * halo) * (1.0 + 8.0 / slots) * (CK >= 8 ? 1.0 : 1.04) * extra_cost;
         if (cost < *best_cost) {
           *best_cost = cost;
           found = true;
@@ -381,7 +394,8 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   static std::map<PlanKey, Plan> plans;
   static std::mutex plans_mu;
   static int num_sms = 0;
-  PlanKey key = {{d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed, Jw, Jh, Jd, gwc ? k.cpg : 0, 0, 0, 0, 0, 0}};
+  PlanKey key = {{d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed, Jw, Jh, Jd, gwc ? k.cpg : 0, d->B, d->pd, d->ph,
+                  d->pw, 0}};
   Plan plan;
   {
     std::lock_guard<std::mutex> lock(plans_mu);
@@ -401,28 +415,36 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
       Plan np;
       np.COG = g.CoutPad == 4 ? 4 : 8;
       np.CK = g.CinPad == 1 ? 1 : 8;
-      // a CTA owns at most 64 output channels (8 channel groups x >=32 voxel slots = 256 threads)
-      int cosplit = 1;
-      while (g.CoutPad / cosplit > 64 || g.CoutPad % cosplit || (g.CoutPad / cosplit) % np.COG) ++cosplit;
-      np.cosplit = cosplit;
-      np.COP = g.CoutPad / cosplit;
-      const int ncog = np.COP / np.COG;
-      // search tile shapes and channel-chunk depth (8 or 4: a shallower chunk halves the staged
-      // brick, which buys resident warps on the wide 8-channel layers)
-      // row geometry leaves room for the XO=3 window whenever some launch of this layer may use it
-      const int xo_plan = (!gwc && (d->transposed || (d->pw & 3) == 1)) ? 3 : 0;
+      // Search: output-channel split (a CTA owns COP <= 64 channels = 8 channel groups x >= 32 voxel
+      // slots = 256 threads; more splits re-stage the same bricks but give small layers more CTAs),
+      // channel-chunk depth (8 or 4: a shallower chunk halves the staged brick, which buys resident
+      // warps on the wide 8-channel layers) and the tile shape.
+      const int xo_plan = (!gwc && (d->transposed || (d->pw & 3) == 1)) ? 3 : 0;  // room for the XO=3 window
       double best = 1e30;
-      bool tiled = choose_tiling(Jw, Jh, Jd, ncog, g.KW, g.KH, g.KD, S, np.CK, np.COP, gwc, k.cpg, xo_plan, &np.tl, &best);
-      if (np.CK == 8 && np.COG == 8) {
-        Tiling t4;
-        if (choose_tiling(Jw, Jh, Jd, ncog, g.KW, g.KH, g.KD, S, 4, np.COP, gwc, k.cpg, xo_plan, &t4, &best)) {
-          np.tl = t4;
-          np.CK = 4;
-          tiled = true;
+      bool tiled = false;
+      const int ck0 = np.CK;
+      for (int cosplit = 1; cosplit <= g.CoutPad / np.COG; ++cosplit) {
+        if (g.CoutPad % cosplit || (g.CoutPad / cosplit) % np.COG || g.CoutPad / cosplit > 64) continue;
+        const int COP = g.CoutPad / cosplit;
+        const int ncog_c = COP / np.COG;
+        const long long mult = (long long)d->B * g.phases * cosplit;
+        const double extra = 1.0 + 0.03 * (cosplit - 1);  // each split stages the input bricks again
+        for (int ck = ck0; ck >= (ck0 == 8 && np.COG == 8 ? 4 : ck0); ck /= 2) {
+          Tiling tt;
+          if (choose_tiling(Jw, Jh, Jd, ncog_c, g.KW, g.KH, g.KD, S, ck, COP, gwc, k.cpg, xo_plan, mult, num_sms, extra, &tt,
+                            &best)) {
+            np.tl = tt;
+            np.CK = ck;
+            np.cosplit = cosplit;
+            np.COP = COP;
+            tiled = true;
+          }
+          if (ck == 1) break;
         }
       }
       ESM_REQUIRE(tiled, "conv: no tiling for Cin=%d Cout=%d k=(%d,%d,%d)%s", d->Cin, d->Cout, d->kd, d->kh, d->kw,
                   gwc ? " +gwc" : "");
+      const int ncog = np.COP / np.COG;
       np.fn = pick_kernel(g.KW, S, np.COG, np.CK, gwc, false, 0);
       np.fn_tma[0] = pick_kernel(g.KW, S, np.COG, np.CK, gwc, true, 0);
       np.fn_tma[1] = pick_kernel(g.KW, S, np.COG, np.CK, gwc, true, 3);

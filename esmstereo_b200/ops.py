@@ -8,6 +8,7 @@ on torch's current stream; there is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -200,6 +201,14 @@ def _src_struct(t: torch.Tensor, nd: int):
     return s, t
 
 
+def _alloc_rows(device, lead, width: int) -> torch.Tensor:
+    """Activation buffer whose row pitch is a multiple of 4 floats (16 bytes), so that the next
+    convolution can stage it with TMA box copies; returned as a [..., :width] view."""
+    pitch = width if os.environ.get("ESM_NO_PAD") else (width + 3) // 4 * 4
+    buf = torch.empty(*lead, pitch, device=device, dtype=torch.float32)
+    return buf if pitch == width else buf[..., :width]
+
+
 def conv(srcs: Sequence[torch.Tensor], pc: PackedConv, act: Optional[str] = None, *, out_size: Optional[Sequence[int]] = None,
          in_mul: Optional[torch.Tensor] = None, out_mul: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, act2: Optional[str] = None, out_scale: float = 1.0,
@@ -258,10 +267,10 @@ def conv(srcs: Sequence[torch.Tensor], pc: PackedConv, act: Optional[str] = None
         ost = out.stride()
         oB, oC, oD, oH = ost[0], ost[1], 0, ost[2]
     elif nd == 3:
-        out = torch.empty(B, pc.Cout, Do, Ho, Wo, device=x0.device, dtype=torch.float32)
+        out = _alloc_rows(x0.device, (B, pc.Cout, Do, Ho), Wo)
         oB, oC, oD, oH = out.stride()[:4]
     else:
-        out = torch.empty(B, pc.Cout, Ho, Wo, device=x0.device, dtype=torch.float32)
+        out = _alloc_rows(x0.device, (B, pc.Cout, Ho), Wo)
         ost = out.stride()
         oB, oC, oD, oH = ost[0], ost[1], 0, ost[2]
     if in_mul is not None:
@@ -271,8 +280,12 @@ def conv(srcs: Sequence[torch.Tensor], pc: PackedConv, act: Optional[str] = None
         out_mul = _dev(out_mul, "out_mul").contiguous()
         assert out_mul.numel() == B * pc.Cout * Ho * Wo
     if residual is not None:
-        residual = _dev(residual, "residual").contiguous()
+        residual = _dev(residual, "residual")
         assert residual.shape == out.shape
+        if residual.stride() != out.stride():  # the kernel reads it with the output's strides
+            tmp = torch.empty_strided(out.size(), out.stride(), device=out.device, dtype=out.dtype)
+            tmp.copy_(residual)
+            residual = tmp
     d.in_mul = _ptr(in_mul)
     d.B, d.Cin, d.Din, d.Hin, d.Win = B, pc.Cin, Din, Hin, Win
     d.Cout, d.Dout, d.Hout, d.Wout = pc.Cout, Do, Ho, Wo
@@ -308,6 +321,8 @@ class MixerMlp:
 
 def sm_pointwise(x: torch.Tensor, mlp: MixerMlp, extra_residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     x = _dev(x, "x").contiguous()
+    if extra_residual is not None:
+        extra_residual = _dev(extra_residual, "extra_residual").contiguous()
     B, Cc, H, W = x.shape
     y = torch.empty_like(x)
     with _Prof("sm_pointwise C%d %dx%d" % (Cc, H, W)):
@@ -319,6 +334,8 @@ def sm_pointwise(x: torch.Tensor, mlp: MixerMlp, extra_residual: Optional[torch.
 def sm_spatial(x: torch.Tensor, dw_w: torch.Tensor, dw_b: torch.Tensor, mlp: MixerMlp,
                extra_residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     x = _dev(x, "x").contiguous()
+    if extra_residual is not None:
+        extra_residual = _dev(extra_residual, "extra_residual").contiguous()
     B, Cc, H, W = x.shape
     y = torch.empty_like(x)
     k = dw_w.shape[-1]

@@ -34,6 +34,7 @@ def test_argument_errors_need_no_gpu():
     n = L.esm_packed_weight_elems(8, 32, 3, 3, 3, 0)
     assert n == 27 * 32 * 8
     assert L.esm_packed_weight_elems(40, 72, 4, 4, 4, 1) == 8 * 8 * 72 * 40
+    assert L.esm_packed_weight_elems(72, 8, 1, 1, 1, 0) == 8 * 80   # Cout 72 -> 2 CTAs x 40 channels
     assert L.esm_packed_weight_elems(1, 24, 4, 4, 4, 1) == 8 * 8 * 24 * 4   # Cout=1 padded to 4 (16-byte weight rows)
     assert L.esm_packed_weight_elems(32, 1, 1, 5, 5, 0) == 25 * 1 * 32      # Cin=1 keeps CK=1
 
