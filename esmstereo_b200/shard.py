@@ -1,0 +1,37 @@
+"""Multi-GPU sharding of stereo pairs: every pair is independent, so pair i goes to
+rank i mod N with replicated weights and NO data-path collective; the only communication is the
+gather of the per-rank disparities (and metric sums) -- NCCL over NVLink on GPUs, gloo in CPU tests.
+The reference has nothing to port here: it only wraps the model in a single-process
+`nn.DataParallel` pinned to one visible GPU (test_kitti.py:18,53).
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_pairs: int, rank: int, world: int) -> List[int]:
+    """Indices of the pairs rank `rank` processes (round robin)."""
+    return list(range(rank, n_pairs, world))
+
+
+def gather_disparities(local: torch.Tensor, n_pairs: int, rank: int, world: int) -> torch.Tensor:
+    """All-gather per-rank outputs [n_local, H, W] into dataset order [n_pairs, H, W].
+    Ranks may hold different counts (n_pairs % world != 0): shorter ranks are padded for the
+    collective and the padding is dropped afterwards."""
+    if world == 1:
+        return local
+    per_rank = (n_pairs + world - 1) // world
+    shape = (per_rank,) + tuple(local.shape[1:])
+    padded = torch.zeros(shape, dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    out = torch.empty((world,) + shape, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out.view(world * per_rank, *shape[1:]), padded)
+    full = torch.empty((n_pairs,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        idx = shard_indices(n_pairs, r, world)
+        if idx:
+            full[torch.tensor(idx, device=local.device)] = out[r, : len(idx)]
+    return full

@@ -1,0 +1,52 @@
+"""Multi-process host logic (pairs sharded by rank, gather of outputs) on CPU with the gloo backend."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n_pairs, out_dir):
+    sys.path.insert(0, ROOT)
+    from esmstereo_b200.shard import gather_disparities, shard_indices
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = shard_indices(n_pairs, rank, world)
+    # stand-in for the per-rank forward: "disparity" of pair i is a constant image of value i
+    local = torch.stack([torch.full((4, 6), float(i)) for i in mine]) if mine else torch.zeros(0, 4, 6)
+    full = gather_disparities(local, n_pairs, rank, world)
+    if rank == 0:
+        torch.save(full, os.path.join(out_dir, "full.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pairs_shard_and_gather_world2(tmp_path):
+    n_pairs, world = 5, 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_pairs, str(tmp_path)), nprocs=world, join=True)
+    full = torch.load(os.path.join(str(tmp_path), "full.pt"))
+    assert full.shape == (n_pairs, 4, 6)
+    for i in range(n_pairs):  # every pair exactly once, in dataset order
+        assert torch.all(full[i] == float(i))
+
+
+def test_shard_indices_cover_everything_once():
+    sys.path.insert(0, ROOT)
+    from esmstereo_b200.shard import shard_indices
+    for n in (0, 1, 7, 8, 9):
+        for world in (1, 2, 3, 8):
+            seen = sorted(i for r in range(world) for i in shard_indices(n, r, world))
+            assert seen == list(range(n))
