@@ -1,17 +1,39 @@
-"""2D feature side of ESMStereo -- NOT the hot path ("kept in PyTorch, must exist for
-drop-in").  Backbone taps, FPN-style FeatUp, the image stems and the matching descriptor run as
-ordinary PyTorch/cuDNN modules with the reference's parameter names (`models/ESMStereo.py:40-125,
-528-597`); left and right images are pushed through as one batch of 2B.
+"""2D feature side of ESMStereo (the first "next" row): backbone taps, FPN-style FeatUp,
+the image stems and the matching descriptor, with the reference's parameter names
+(`models/ESMStereo.py:40-125,528-597`).  Left and right images go through as one batch of 2B.
+
+Two engines, selected per model (`model.feature_engine`):
+  * "esm"   -- every conv / transposed conv + BN + activation is one launch of the same fused
+               direct-conv kernel the hot path uses (fp32-exact, concat-free); default whenever the
+               backbone is the stand-in (`esmstereo_b200.backbone`);
+  * "torch" -- plain PyTorch / cuDNN modules; used for a real `timm` backbone's own blocks, whose
+               graph this package does not know, and kept for A/B comparisons.
 """
 from __future__ import annotations
 
-from typing import List
+from typing import List, Optional
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .backbone import FEATURE_CHANS, make_backbone
+from . import ops
+from .backbone import FEATURE_CHANS, StandInBackbone, make_backbone
+from .layers import _Packed, packed_conv
+
+_TORCH_ACT = {"gelu": F.gelu, "relu": F.relu, "relu6": F.relu6, None: lambda x: x}
+
+
+def fused(cache: _Packed, conv: nn.Module, bn: Optional[nn.Module], x, act: Optional[str], engine: str, **kw):
+    """conv (+BN) (+act) on `x` (tensor or list of channel-concatenated tensors)."""
+    if engine == "esm":
+        return ops.conv(x, packed_conv(cache, conv, bn), act, **kw)
+    if isinstance(x, (list, tuple)):
+        x = torch.cat(list(x), 1)
+    y = conv(x)
+    if bn is not None:
+        y = bn(y)
+    return _TORCH_ACT[act](y)
 
 
 class TorchBasicConv(nn.Module):
@@ -22,9 +44,10 @@ class TorchBasicConv(nn.Module):
         cls = nn.ConvTranspose2d if deconv else nn.Conv2d
         self.conv = cls(cin, cout, bias=False, **kwargs)
         self.bn = nn.BatchNorm2d(cout)
+        self._pc = _Packed()
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return F.gelu(self.bn(self.conv(x)))
+    def forward(self, x, engine: str = "torch", **kw) -> torch.Tensor:
+        return fused(self._pc, self.conv, self.bn, x, "gelu", engine, **kw)
 
 
 class Conv2x(nn.Module):
@@ -35,11 +58,11 @@ class Conv2x(nn.Module):
         self.conv1 = TorchBasicConv(cin, cout, deconv=True, kernel_size=4, stride=2, padding=1)
         self.conv2 = TorchBasicConv(cout * 2, cout * 2, kernel_size=3, stride=1, padding=1)
 
-    def forward(self, x: torch.Tensor, rem: torch.Tensor) -> torch.Tensor:
-        x = self.conv1(x)
-        if x.shape != rem.shape:
-            x = F.interpolate(x, size=(rem.shape[-2], rem.shape[-1]), mode="nearest")
-        return self.conv2(torch.cat((x, rem), 1))
+    def forward(self, x: torch.Tensor, rem: torch.Tensor, engine: str = "torch") -> torch.Tensor:
+        x = self.conv1(x, engine)
+        if x.shape != rem.shape:  # never taken for inputs that are multiples of 32 (callers guarantee)
+            x = F.interpolate(x.contiguous(), size=(rem.shape[-2], rem.shape[-1]), mode="nearest")
+        return self.conv2([x, rem], engine)
 
 
 class Feature(nn.Module):
@@ -49,13 +72,23 @@ class Feature(nn.Module):
         super().__init__()
         self.backbone = backbone
         model = make_backbone(backbone)
+        self.stand_in = isinstance(model, StandInBackbone)
         self.chans = FEATURE_CHANS[backbone]
         self.conv_stem, self.bn1, self.act1 = model.conv_stem, model.bn1, nn.ReLU6()
         cuts = [0, 1, 2, 3, 5, 6]
         for i in range(5):
             setattr(self, "block%d" % i, nn.Sequential(*model.blocks[cuts[i]:cuts[i + 1]]))
+        self._caches = {}
 
-    def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
+    def forward(self, x: torch.Tensor, engine: str = "torch") -> List[torch.Tensor]:
+        if engine == "esm" and self.stand_in:
+            x = fused(self._caches.setdefault("stem", _Packed()), self.conv_stem, self.bn1, x, "relu6", "esm")
+            outs = []
+            for i in range(5):
+                for j, stage in enumerate(getattr(self, "block%d" % i)):  # stage = Sequential(conv, bn, ReLU6)
+                    x = fused(self._caches.setdefault((i, j), _Packed()), stage[0], stage[1], x, "relu6", "esm")
+                outs.append(x)
+            return outs
         x = self.act1(self.bn1(self.conv_stem(x)))
         outs = []
         for i in range(5):
@@ -81,21 +114,42 @@ class FeatUp(nn.Module):
             self.deconv8_4 = Conv2x(chans[2] * 2, chans[1])
             self.conv4 = TorchBasicConv(chans[1] * 2, chans[1] * 2, kernel_size=3, stride=1, padding=1)
 
-    def forward(self, feats: List[torch.Tensor]) -> List[torch.Tensor]:
+    def forward(self, feats: List[torch.Tensor], engine: str = "torch") -> List[torch.Tensor]:
         x2, x4, x8, x16, x32 = feats
-        x16 = self.deconv32_16(x32, x16)
+        x16 = self.deconv32_16(x32, x16, engine)
         if self.v == 16:
-            x16 = self.conv16(x16)
+            x16 = self.conv16(x16, engine)
         if self.v in (8, 4):
-            x8 = self.deconv16_8(x16, x8)
+            x8 = self.deconv16_8(x16, x8, engine)
         if self.v == 8:
-            x8 = self.conv8(x8)
+            x8 = self.conv8(x8, engine)
         if self.v == 4:
-            x4 = self.conv4(self.deconv8_4(x8, x4))
+            x4 = self.conv4(self.deconv8_4(x8, x4, engine), engine)
         return [x4, x8, x16, x32]
 
 
-def image_stem(cin: int, cout: int) -> nn.Sequential:
+class ImageStem(nn.Sequential):
     """stem_2/4/8/16 (ESMStereo.py:529-583): BasicConv(s2) + Conv2d + BN + ReLU, children 0..3."""
-    return nn.Sequential(TorchBasicConv(cin, cout, kernel_size=3, stride=2, padding=1),
+
+    def __init__(self, cin: int, cout: int) -> None:
+        super().__init__(TorchBasicConv(cin, cout, kernel_size=3, stride=2, padding=1),
                          nn.Conv2d(cout, cout, 3, 1, 1, bias=False), nn.BatchNorm2d(cout), nn.ReLU())
+        self._pc = _Packed()
+
+    def forward(self, x: torch.Tensor, engine: str = "torch") -> torch.Tensor:
+        return fused(self._pc, self[1], self[2], self[0](x, engine), "relu", engine)
+
+
+def image_stem(cin: int, cout: int) -> ImageStem:
+    return ImageStem(cin, cout)
+
+
+class ConvThenPlain(nn.Sequential):
+    """`semantic` (ESMStereo.py:606-618): Sequential(BasicConv, Conv2d(bias=False)), children 0,1."""
+
+    def __init__(self, cin: int, cmid: int, cout: int) -> None:
+        super().__init__(TorchBasicConv(cin, cmid, kernel_size=3, stride=1, padding=1), nn.Conv2d(cmid, cout, 3, 1, 1, bias=False))
+        self._pc = _Packed()
+
+    def forward(self, x: torch.Tensor, engine: str = "torch") -> torch.Tensor:
+        return fused(self._pc, self[1], None, self[0](x, engine), None, engine)

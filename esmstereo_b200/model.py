@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import layers as L
 from . import ops
-from .feature2d import FeatUp, Feature, TorchBasicConv, image_stem
+from .feature2d import ConvThenPlain, FeatUp, Feature, TorchBasicConv, fused, image_stem
 
 _STEM_CH = {4: [(3, 32), (32, 48)], 8: [(3, 32), (32, 48), (48, 64)], 16: [(3, 16), (16, 24), (24, 32), (32, 40)]}
 _DESC_IN = {4: 96, 8: 160, 16: 136}
@@ -51,19 +51,22 @@ class _ESMStereoBase(nn.Module):
         super().__init__()
         self.maxdisp, self.vol_size = maxdisp, cv_scale
         self.gwc, self.norm_correlation, self.backbone = gwc, norm_correlation, backbone
-        self.exact_fp32 = True      # False: let cuDNN use TF32 on the 2D feature side (fast, not parity-grade)
+        self.exact_fp32 = True      # engine "torch" only: keep cuDNN out of TF32 on the 2D feature side (parity-grade)
         self.fuse_volume = True     # gwc volume generated inside group_stem (never written to HBM)
         self.capture: Optional[Dict[str, torch.Tensor]] = None  # set to {} to record hot-path stages (tests)
         if cv_scale not in (4, 8, 16):
             # the reference hits a misspelt `pirnt(...)` here -> NameError (ESMStereo.py:599)
             raise NameError("Choose the cost volume resolution: 4, 8, 16")
         self.feature = Feature(backbone)
+        # 2D feature side: "esm" = the fused direct-conv kernels (stand-in backbone), "torch" = cuDNN modules
+        self.feature_engine = "esm" if self.feature.stand_in else "torch"
         if cv_scale in (4, 8):
             self.feature_up = FeatUp(self.feature.chans, cv_scale)
         for (cin, cout), n in zip(_STEM_CH[cv_scale], (2, 4, 8, 16)):
             setattr(self, "stem_%d" % n, image_stem(cin, cout))
         self.conv = TorchBasicConv(_DESC_IN[cv_scale], 64, kernel_size=3, padding=1, stride=1)
         self.desc = nn.Conv2d(64, 64, kernel_size=1, padding=0, stride=1)
+        self._desc_pc = L._Packed()
         if cv_scale == 16:
             self.conv_f2 = TorchBasicConv(96, 32, kernel_size=3, padding=1, stride=1)
             self.conv_f0 = TorchBasicConv(16, 24, kernel_size=3, padding=1, stride=1)
@@ -71,14 +74,12 @@ class _ESMStereoBase(nn.Module):
         if norm_correlation:
             print("Cost volumes: norm correlation")
             if cv_scale == 16:
-                self.semantic = nn.Sequential(TorchBasicConv(96, 32, kernel_size=3, stride=1, padding=1),
-                                              nn.Conv2d(32, 8, 3, 1, 1, bias=False))
+                self.semantic = ConvThenPlain(96, 32, 8)
             self.corr_stem = L.BasicConv(1, 8, **k3)
         if gwc:
             print("Cost volumes: gwc ")
             if cv_scale == 16:
-                self.semantic = nn.Sequential(TorchBasicConv(96, 64, kernel_size=3, stride=1, padding=1),
-                                              nn.Conv2d(64, 32, 3, 1, 1, bias=False))
+                self.semantic = ConvThenPlain(96, 64, 32)
             self.num_groups = 32
             self.group_stem = L.BasicConv(self.num_groups, 8, **k3)
         self.agg = L.BasicConv(8, 8, **k3)
@@ -93,21 +94,22 @@ class _ESMStereoBase(nn.Module):
         Both images go through the shared layers as one batch (ESMStereo.py:640-697)."""
         B = left.shape[0]
         both = torch.cat((left, right), 0)
-        with _exact_fp32(self.exact_fp32):
-            feats = self.feature(both)
+        eng = self.feature_engine
+        with _exact_fp32(self.exact_fp32 and eng == "torch"):
+            feats = self.feature(both, eng if self.feature.stand_in else "torch")
             if self.vol_size in (4, 8):
-                feats = self.feature_up(feats)
-            stems = [self.stem_2(both)]
+                feats = self.feature_up(feats, eng)
+            stems = [self.stem_2(both, eng)]
             for n in (4, 8, 16):
                 if hasattr(self, "stem_%d" % n):
-                    stems.append(getattr(self, "stem_%d" % n)(stems[-1]))
+                    stems.append(getattr(self, "stem_%d" % n)(stems[-1], eng))
             coarse = {4: feats[0], 8: feats[1], 16: feats[3]}[self.vol_size]
-            match = self.desc(self.conv(torch.cat((coarse, stems[-1]), 1)))
+            match = fused(self._desc_pc, self.desc, None, self.conv([coarse, stems[-1]], eng), None, eng)
             fl = [f[:B] for f in feats]
-            att = self.semantic(fl[3]) if self.vol_size == 16 else None
+            att = self.semantic(fl[3], eng) if self.vol_size == 16 else None
             extra = None
             if self.vol_size == 16:
-                extra = (self.conv_f2(fl[3]), self.conv_f0(fl[0]))
+                extra = (self.conv_f2(fl[3], eng), self.conv_f0(fl[0], eng))
         return fl, [s[:B] for s in stems], match[:B].contiguous(), match[B:].contiguous(), att, extra
 
     # ------------------------------------------------------------------ hot path (libesm_b200)
