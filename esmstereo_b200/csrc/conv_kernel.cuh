@@ -148,9 +148,9 @@ __device__ __forceinline__ TileCtx decode_work(const ConvK& p, int w) {
 // (XO=3: one scalar LDS + aligned LDS.128s); XO=0 otherwise.
 template <int KW, int S, int COG, int CK, bool GWC, bool TMA, int XO>
 __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ ConvK p, const __grid_constant__ ConvMaps maps) {
-  extern __shared__ __align__(16) float smem_raw[];
-  // TMA destinations must be 128-byte aligned; the host over-allocates by 128 bytes
-  float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  // TMA destinations must be 128-byte aligned.  Declared aligned (not realigned by pointer
+  // arithmetic) so that every derived pointer stays in the .shared state space: LDS, not generic LD.
+  extern __shared__ __align__(1024) float smem[];
   constexpr int NV = 4;
   constexpr int XN = (NV - 1) * S + KW;
   constexpr int XL = (XN + 3) / 4 * 4;
