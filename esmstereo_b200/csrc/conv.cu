@@ -21,8 +21,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
+#include <vector>
 #include <type_traits>
 
 namespace esm {
@@ -148,10 +150,16 @@ static int resident_ctas(int nthreads, size_t smem) {
   return r > 8 ? 8 : r;
 }
 
-static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int KD, int S, int CK, int COP, bool gwc,
-                          int cpg, int xo, long long work_mult, int num_sms, double extra_cost, Tiling* out,
-                          double* best_cost) {
-  bool found = false;
+struct Candidate {
+  Tiling tl;
+  int CK, COP, cosplit;
+  double cost;
+};
+
+// Enumerate tile shapes for one (channel split, chunk depth) and append them with their modelled cost.
+static void enumerate_tilings(int Jw, int Jh, int Jd, int cin, int ncog, int KW, int KH, int KD, int S, int CK, int COP,
+                              int cosplit, bool gwc, int cpg, int xo, long long work_mult, int num_sms, double extra_cost,
+                              std::vector<Candidate>* out) {
   for (int slots = 32; slots * ncog <= 256; slots += 32) {
     for (int TWG = 1; TWG <= 16; TWG *= 2) {
       if (slots % TWG) continue;
@@ -161,7 +169,6 @@ static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int 
         const int TH = R / TD;
         if (Jd == 1 && TD != 1) continue;
         const int TW = TWG * 4;
-        const double waste = (double)ceil_div(Jw, TW) * TW / Jw * ceil_div(Jh, TH) * TH / Jh * ceil_div(Jd, TD) * TD / Jd;
         const int ID = (TD - 1) * S + KD, IH = (TH - 1) * S + KH;
         const int XN = 3 * S + KW, XL = (XN + 3) / 4 * 4;
         // row window of the last thread: aligned float4s (xo=0) or scalar@3 + float4s from column 4 (xo=3)
@@ -170,42 +177,48 @@ static bool choose_tiling(int Jw, int Jh, int Jd, int ncog, int KW, int KH, int 
           const int want = (4 * TWG) % 32;  // rows of an 8-lane LDS.128 phase land on distinct banks
           while (IWP % 32 != want) IWP += 4;
         }
+        if (IWP > 256 || IH > 256 || ID > 256) continue;  // TMA box limits
         int IWR = 0, IWL = 0;
         const size_t smem = conv_smem_bytes(CK, ID, IH, IWP, KD * KH * KW, COP, gwc, cpg, &IWR, &IWL);
-        if (smem > 224 * 1024) continue;
+        if (smem > 224 * 1024 || IWR > 256) continue;
         const int nthreads = slots * ncog;
         const int ctas = resident_ctas(nthreads, smem);
         if (ctas < 1) continue;
-        const double halo = (double)ID * IH * IWP / ((double)TD * TH * TW * S * S * (Jd == 1 ? 1 : S));
-        // FMA-pipe utilisation needs ~12+ resident warps per SM to cover LDS/FFMA2 latencies; below
-        // that the cost grows quickly.  Then: wasted lanes, fill traffic (halo), barriers per FLOP
-        // (small CTAs / small channel chunks sync more often).
-        const double warps = (double)ctas * nthreads / 32.0;
-        const double occ = warps >= 14.0 ? 1.0 : 14.0 / warps;
-        // grid fill: small layers (the coarse hourglass levels) must still cover all SMs, and the
-        // last wave of a persistent grid should not be mostly empty
+        // Analytic time model (SM clocks).  FMA pipe: a warp-level FFMA2 holds its SMSP's pipe for
+        // 2 clk; LDS / loop overhead ~30% on top; fewer than ~12 resident warps cannot hide the
+        // LDS->FFMA2 latency.  Per work item a CTA also pays one TMA round trip unless the math
+        // covers it.  The model only RANKS candidates; the best few are then timed on the device.
+        const int warps = nthreads / 32;
+        const double smsp_load = (double)((ctas * warps + 3) / 4);
+        const double hide = ctas * warps >= 12 ? 1.0 : 12.0 / (ctas * warps);
+        const double ffma2 = (double)KD * KH * KW * CK * 16;
+        const double t_math = ffma2 * 2.0 * smsp_load * 1.3 * hide;
+        const double t_item = t_math > 1500.0 ? t_math : 1500.0;
+        const int nchunks = ceil_div(cin, CK);
         const long long tiles = (long long)ceil_div(Jw, TW) * ceil_div(Jh, TH) * ceil_div(Jd, TD) * work_mult;
         const long long wave = (long long)(num_sms > 0 ? num_sms : 148) * ctas;
-        const double fill = (double)tiles / (double)(ceil_div_ll(tiles, wave) * wave);
-        const double cost = waste * occ / fill * (1.0 + 0.05 * halo) * (1.0 + 8.0 / slots) * (CK >= 8 ? 1.0 : 1.04) * extra_cost;
-        if (cost < *best_cost) {
-          *best_cost = cost;
-          found = true;
-          out->TWG = TWG;
-          out->TH = TH;
-          out->TD = TD;
-          out->slots = slots;
-          out->IWP = IWP;
-          out->ID = ID;
-          out->IH = IH;
-          out->IWR = IWR;
-          out->IWL = IWL;
-          out->smem = smem;
-        }
+        const double waves = (double)ceil_div_ll(tiles, wave);
+        const double t_epi = 1200.0 * smsp_load;
+        const double halo = (double)ID * IH * IWP / ((double)TD * TH * TW * S * S * (Jd == 1 ? 1 : S));
+        Candidate c;
+        c.cost = (waves * (nchunks * t_item + t_epi) + 6000.0) * (1.0 + 0.02 * halo) * extra_cost;
+        c.tl.TWG = TWG;
+        c.tl.TH = TH;
+        c.tl.TD = TD;
+        c.tl.slots = slots;
+        c.tl.IWP = IWP;
+        c.tl.ID = ID;
+        c.tl.IH = IH;
+        c.tl.IWR = IWR;
+        c.tl.IWL = IWL;
+        c.tl.smem = smem;
+        c.CK = CK;
+        c.COP = COP;
+        c.cosplit = cosplit;
+        out->push_back(c);
       }
     }
   }
-  return found;
 }
 
 static conv_fn_t pick_kernel(int KW, int S, int COG, int CK, bool gwc, bool tma, int xo) {
@@ -271,6 +284,109 @@ struct Plan {
   conv_fn_t fn_tma[2];  // TMA pipeline for window offset XO = 0 / 3 (nullptr if not instantiated)
   int cosplit, COP, COG, CK, blocks_per_sm;
 };
+
+struct LayerGeom {
+  int S, Jw, Jh, Jd;
+  bool gwc;
+};
+
+// Fill the tile-dependent kernel arguments, encode the tensor maps when the operands are TMA-eligible
+// (16-byte aligned bases and pitches, channel chunks that never straddle two sources) and launch.
+static int launch_plan(const esm_conv_t* d, const PackGeom& g, ConvK k, const Plan& plan, const LayerGeom& lg, int num_sms,
+                       cudaStream_t st) {
+  const Tiling& tl = plan.tl;
+  const bool gwc = lg.gwc;
+  const int ncog = plan.COP / plan.COG;
+  k.cosplit = plan.cosplit;
+  k.COP = plan.COP;
+  k.TWG = tl.TWG;
+  k.TH = tl.TH;
+  k.TD = tl.TD;
+  k.slots = tl.slots;
+  k.nthreads = tl.slots * ncog;
+  k.ID = tl.ID;
+  k.IH = tl.IH;
+  k.IWP = tl.IWP;
+  k.IWR = tl.IWR;
+  k.IWL = tl.IWL;
+  k.pzw_sel = -1;
+  k.tilesW = ceil_div(lg.Jw, tl.TWG * 4);
+  k.tilesH = ceil_div(lg.Jh, tl.TH);
+  k.tilesD = ceil_div(lg.Jd, tl.TD);
+  k.phases = g.phases;
+  const long long total = (long long)k.tilesW * k.tilesH * k.tilesD * d->B * g.phases * plan.cosplit;
+  ESM_REQUIRE(total < (1ll << 30), "conv: too many tiles");
+  k.total_work = (int)total;
+  if (num_sms <= 0) {
+    set_error("conv: no CUDA device");
+    return ESM_ERR_CUDA;
+  }
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  bool use_tma = get_encoder() != nullptr && !getenv("ESM_NO_TMA");
+  auto aligned = [](const esm_src_t& sv, bool has_d) {
+    return (reinterpret_cast<uintptr_t>(sv.ptr) & 15) == 0 && sv.sH % 4 == 0 && sv.sC % 4 == 0 && sv.sB % 4 == 0 &&
+           (!has_d || sv.sD % 4 == 0);
+  };
+  if (use_tma && (reinterpret_cast<uintptr_t>(d->weight) & 15)) use_tma = false;
+  if (use_tma && !gwc && d->in_mul) use_tma = false;
+  for (int i = 0; use_tma && i < d->nsrc; ++i) {
+    if (!aligned(d->src[i], d->Din > 1 && !gwc)) use_tma = false;
+    if (!gwc && i + 1 < d->nsrc && d->src[i].C % plan.CK) use_tma = false;
+  }
+  // window offset of the TMA brick: boxes must start on a multiple of 4 columns
+  const int xo_a = gwc ? 0 : ((4 - ((d->transposed ? 1 : d->pw) & 3)) & 3);  // transposed: W phase 0 has pad 1
+  if (use_tma && !gwc && xo_a != 0 && xo_a != 3) use_tma = false;
+  if (use_tma && !plan.fn_tma[xo_a == 3]) use_tma = false;
+  if (use_tma && d->transposed && !plan.fn_tma[0]) use_tma = false;
+  if (use_tma) {
+    const int taps = g.KD * g.KH * g.KW;
+    if (gwc) {
+      const int nch = plan.CK * k.cpg;
+      for (int i = 0; i < 2 && use_tma; ++i) {
+        const esm_src_t& sv = d->src[i];
+        const long long dims[5] = {d->Win, d->Hin, 1, sv.C, d->B};
+        const long long str[4] = {sv.sH, sv.sH * d->Hin, sv.sC, sv.sB};
+        const int box[5] = {i == 0 ? tl.IWL : tl.IWR, tl.IH, 1, nch, 1};
+        use_tma = sv.sC >= sv.sH * d->Hin && encode_map(&maps.src[i], sv.ptr, 5, dims, str, box);
+      }
+    } else {
+      for (int i = 0; i < d->nsrc && use_tma; ++i) {
+        const esm_src_t& sv = d->src[i];
+        const long long sD = d->Din > 1 ? sv.sD : sv.sH * d->Hin;
+        const long long dims[5] = {d->Win, d->Hin, d->Din, sv.C, d->B};
+        const long long str[4] = {sv.sH, sD, sv.sC, sv.sB};
+        const int box[5] = {tl.IWP, tl.IH, tl.ID, plan.CK, 1};
+        use_tma = encode_map(&maps.src[i], sv.ptr, 5, dims, str, box);
+      }
+    }
+    if (use_tma) {
+      const long long dims[3] = {g.CoutPad, g.CinPad, (long long)taps * g.phases};
+      const long long str[2] = {g.CoutPad, (long long)g.CoutPad * g.CinPad};
+      const int box[3] = {plan.COP, plan.CK, taps};
+      use_tma = encode_map(&maps.w, d->weight, 3, dims, str, box);
+    }
+  }
+  const long long resident = (long long)num_sms * plan.blocks_per_sm;
+  if (!use_tma) {
+    const unsigned grid = (unsigned)(total < resident ? total : resident);  // persistent CTAs stride over the tiles
+    plan.fn<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
+  } else if (!d->transposed) {
+    const unsigned grid = (unsigned)(total < resident ? total : resident);
+    plan.fn_tma[xo_a == 3]<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
+  } else {
+    // sub-pixel phases along W have pad 1 (phase 0, window offset 3) and pad 0 (phase 1, offset 0):
+    // one launch per W phase, each enumerating the (d,h) phases
+    k.phases = g.phases / 2;
+    k.total_work = (int)(total / 2);
+    const unsigned grid = (unsigned)(k.total_work < resident ? k.total_work : resident);
+    k.pzw_sel = 0;
+    plan.fn_tma[1]<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
+    k.pzw_sel = 1;
+    plan.fn_tma[0]<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
+  }
+  return check_launch("conv");
+}
 
 }  // namespace esm
 
@@ -387,183 +503,146 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   k.oH = d->oH;
 
   const bool gwc = d->src_mode == ESM_SRC_GWC;
-  const int Jw = d->transposed ? ceil_div(d->Wout, 2) : d->Wout;
-  const int Jh = d->transposed ? ceil_div(d->Hout, 2) : d->Hout;
-  const int Jd = (d->transposed && g.phases_d == 2) ? ceil_div(d->Dout, 2) : d->Dout;
+  cudaStream_t st = (cudaStream_t)stream;
+  LayerGeom lg;
+  lg.S = S;
+  lg.gwc = gwc;
+  lg.Jw = d->transposed ? ceil_div(d->Wout, 2) : d->Wout;
+  lg.Jh = d->transposed ? ceil_div(d->Hout, 2) : d->Hout;
+  lg.Jd = (d->transposed && g.phases_d == 2) ? ceil_div(d->Dout, 2) : d->Dout;
 
   static std::map<PlanKey, Plan> plans;
   static std::mutex plans_mu;
   static int num_sms = 0;
-  PlanKey key = {{d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed, Jw, Jh, Jd, gwc ? k.cpg : 0, d->B, d->pd, d->ph,
-                  d->pw, 0}};
-  Plan plan;
-  {
-    std::lock_guard<std::mutex> lock(plans_mu);
-    if (num_sms == 0) {
-      int dev = 0;
-      cudaDeviceProp prop;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
-        // no device: still run the validation / tiling below so shapes can be checked on a CPU box
-        cudaGetLastError();
-        num_sms = -1;
-      } else {
-        num_sms = prop.multiProcessorCount;
-      }
+  PlanKey key = {{d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed, lg.Jw, lg.Jh, lg.Jd, gwc ? k.cpg : 0, d->B, d->pd,
+                  d->ph, d->pw, 0}};
+  std::lock_guard<std::mutex> lock(plans_mu);
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+      // no device: still run the validation / tiling below so shapes can be checked on a CPU box
+      cudaGetLastError();
+      num_sms = -1;
+    } else {
+      num_sms = prop.multiProcessorCount;
     }
-    auto it = plans.find(key);
-    if (it == plans.end()) {
-      Plan np;
-      np.COG = g.CoutPad == 4 ? 4 : 8;
-      np.CK = g.CinPad == 1 ? 1 : 8;
-      // Search: output-channel split (a CTA owns COP <= 64 channels = 8 channel groups x >= 32 voxel
-      // slots = 256 threads; more splits re-stage the same bricks but give small layers more CTAs),
-      // channel-chunk depth (8 or 4: a shallower chunk halves the staged brick, which buys resident
-      // warps on the wide 8-channel layers) and the tile shape.
-      const int xo_plan = (!gwc && (d->transposed || (d->pw & 3) == 1)) ? 3 : 0;  // room for the XO=3 window
-      double best = 1e30;
-      bool tiled = false;
-      const int ck0 = np.CK;
-      for (int cosplit = 1; cosplit <= g.CoutPad / np.COG; ++cosplit) {
-        if (g.CoutPad % cosplit || (g.CoutPad / cosplit) % np.COG || g.CoutPad / cosplit > 64) continue;
-        const int COP = g.CoutPad / cosplit;
-        const int ncog_c = COP / np.COG;
-        const long long mult = (long long)d->B * g.phases * cosplit;
-        const double extra = 1.0 + 0.03 * (cosplit - 1);  // each split stages the input bricks again
-        for (int ck = ck0; ck >= (ck0 == 8 && np.COG == 8 ? 4 : ck0); ck /= 2) {
-          Tiling tt;
-          if (choose_tiling(Jw, Jh, Jd, ncog_c, g.KW, g.KH, g.KD, S, ck, COP, gwc, k.cpg, xo_plan, mult, num_sms, extra, &tt,
-                            &best)) {
-            np.tl = tt;
-            np.CK = ck;
-            np.cosplit = cosplit;
-            np.COP = COP;
-            tiled = true;
-          }
-          if (ck == 1) break;
-        }
-      }
-      ESM_REQUIRE(tiled, "conv: no tiling for Cin=%d Cout=%d k=(%d,%d,%d)%s", d->Cin, d->Cout, d->kd, d->kh, d->kw,
-                  gwc ? " +gwc" : "");
-      const int ncog = np.COP / np.COG;
-      np.fn = pick_kernel(g.KW, S, np.COG, np.CK, gwc, false, 0);
-      np.fn_tma[0] = pick_kernel(g.KW, S, np.COG, np.CK, gwc, true, 0);
-      np.fn_tma[1] = pick_kernel(g.KW, S, np.COG, np.CK, gwc, true, 3);
-      ESM_REQUIRE(np.fn, "conv: unsupported kernel width %d / stride %d%s", g.KW, S, gwc ? " with ESM_SRC_GWC" : "");
-      np.blocks_per_sm = 1;
-      if (num_sms > 0) {
-        conv_fn_t fns[3] = {np.fn, np.fn_tma[0], np.fn_tma[1]};
-        for (int i = 0; i < 3; ++i) {
-          if (!fns[i]) continue;
-          if (cudaFuncSetAttribute((const void*)fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
-            return check_launch("conv(cudaFuncSetAttribute)");
-          int occ = 0;
-          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fns[i], np.tl.slots * ncog, np.tl.smem) != cudaSuccess)
-            return check_launch("conv(occupancy)");
-          if (i == 0 || occ < np.blocks_per_sm) np.blocks_per_sm = occ > 0 ? occ : 1;
-        }
-      }
-      if (getenv("ESM_DEBUG_PLAN"))
-        fprintf(stderr, "[esm plan] Cin=%d Cout=%d k=(%d,%d,%d) s=%d%s%s J=(%d,%d,%d): CK=%d COP=%d cosplit=%d tile=(%d,%d,%d) "
-                "threads=%d smem=%zu KB ctas/SM(est)=%d occ(query)=%d\n",
-                d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed ? " T" : "", gwc ? " gwc" : "", Jd, Jh, Jw, np.CK,
-                np.COP, np.cosplit, np.tl.TD, np.tl.TH, np.tl.TWG * 4, np.tl.slots * ncog, np.tl.smem / 1024,
-                resident_ctas(np.tl.slots * ncog, np.tl.smem), np.blocks_per_sm);
-      it = plans.emplace(key, np).first;
-    }
-    plan = it->second;
   }
-  const Tiling& tl = plan.tl;
-  const int ncog = plan.COP / plan.COG;
-  k.cosplit = plan.cosplit;
-  k.COP = plan.COP;
-  k.TWG = tl.TWG;
-  k.TH = tl.TH;
-  k.TD = tl.TD;
-  k.slots = tl.slots;
-  k.nthreads = tl.slots * ncog;
-  k.ID = tl.ID;
-  k.IH = tl.IH;
-  k.IWP = tl.IWP;
-  k.IWR = tl.IWR;
-  k.IWL = tl.IWL;
-  k.pzw_sel = -1;
-  k.tilesW = ceil_div(Jw, tl.TWG * 4);
-  k.tilesH = ceil_div(Jh, tl.TH);
-  k.tilesD = ceil_div(Jd, tl.TD);
-  k.phases = g.phases;
-  const long long total = (long long)k.tilesW * k.tilesH * k.tilesD * d->B * g.phases * plan.cosplit;
-  ESM_REQUIRE(total < (1ll << 30), "conv: too many tiles");
-  k.total_work = (int)total;
+  auto it = plans.find(key);
+  if (it != plans.end()) return launch_plan(d, g, k, it->second, lg, num_sms, st);
+
+  // ---- plan: enumerate (channel split x chunk depth x tile shape), rank by the analytic model ----
+  const int COG = g.CoutPad == 4 ? 4 : 8;
+  const int ck0 = g.CinPad == 1 ? 1 : 8;
+  const int xo_plan = (!gwc && (d->transposed || (d->pw & 3) == 1)) ? 3 : 0;  // room for the XO=3 window
+  std::vector<Candidate> cands;
+  for (int cosplit = 1; cosplit <= g.CoutPad / COG; ++cosplit) {
+    // a CTA owns COP <= 64 channels (8 channel groups x >= 32 voxel slots = 256 threads); more
+    // splits re-stage the same bricks but give small layers more CTAs
+    if (g.CoutPad % cosplit || (g.CoutPad / cosplit) % COG || g.CoutPad / cosplit > 64) continue;
+    const int COP = g.CoutPad / cosplit;
+    const long long mult = (long long)d->B * g.phases * cosplit;
+    const double extra = 1.0 + 0.03 * (cosplit - 1);
+    for (int ck = ck0; ck >= (ck0 == 8 && COG == 8 ? 4 : ck0); ck /= 2) {
+      // chunk depth 8 or 4: a shallower chunk halves the staged brick (more resident warps on the 8-channel layers)
+      enumerate_tilings(lg.Jw, lg.Jh, lg.Jd, d->Cin, COP / COG, g.KW, g.KH, g.KD, S, ck, COP, cosplit, gwc, k.cpg, xo_plan, mult,
+                        num_sms, extra, &cands);
+      if (ck == 1) break;
+    }
+  }
+  ESM_REQUIRE(!cands.empty(), "conv: no tiling for Cin=%d Cout=%d k=(%d,%d,%d)%s", d->Cin, d->Cout, d->kd, d->kh, d->kw,
+              gwc ? " +gwc" : "");
+  std::sort(cands.begin(), cands.end(), [](const Candidate& a, const Candidate& b) { return a.cost < b.cost; });
+
+  auto make_plan = [&](const Candidate& c, Plan* np) -> int {
+    np->tl = c.tl;
+    np->CK = c.CK;
+    np->COP = c.COP;
+    np->cosplit = c.cosplit;
+    np->COG = COG;
+    np->fn = pick_kernel(g.KW, S, COG, c.CK, gwc, false, 0);
+    np->fn_tma[0] = pick_kernel(g.KW, S, COG, c.CK, gwc, true, 0);
+    np->fn_tma[1] = pick_kernel(g.KW, S, COG, c.CK, gwc, true, 3);
+    ESM_REQUIRE(np->fn, "conv: unsupported kernel width %d / stride %d%s", g.KW, S, gwc ? " with ESM_SRC_GWC" : "");
+    np->blocks_per_sm = 1;
+    if (num_sms > 0) {
+      conv_fn_t fns[3] = {np->fn, np->fn_tma[0], np->fn_tma[1]};
+      for (int i = 0; i < 3; ++i) {
+        if (!fns[i]) continue;
+        if (cudaFuncSetAttribute((const void*)fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
+          return check_launch("conv(cudaFuncSetAttribute)");
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fns[i], c.tl.slots * (c.COP / COG), c.tl.smem) !=
+            cudaSuccess)
+          return check_launch("conv(occupancy)");
+        if (i == 0 || occ < np->blocks_per_sm) np->blocks_per_sm = occ > 0 ? occ : 1;
+      }
+    }
+    return ESM_OK;
+  };
+
+  Plan best_plan;
+  if (int e = make_plan(cands[0], &best_plan)) return e;
   if (num_sms <= 0) {
     set_error("conv: no CUDA device");
     return ESM_ERR_CUDA;
   }
-  // ---- TMA eligibility: 16-byte aligned bases and pitches, channel chunks that never straddle two sources ----
-  ConvMaps maps;
-  memset(&maps, 0, sizeof(maps));
-  bool use_tma = get_encoder() != nullptr && !getenv("ESM_NO_TMA");
-  auto aligned = [](const esm_src_t& sv, bool has_d) {
-    return (reinterpret_cast<uintptr_t>(sv.ptr) & 15) == 0 && sv.sH % 4 == 0 && sv.sC % 4 == 0 && sv.sB % 4 == 0 &&
-           (!has_d || sv.sD % 4 == 0);
-  };
-  if (use_tma && (reinterpret_cast<uintptr_t>(d->weight) & 15)) use_tma = false;
-  if (use_tma && !gwc && d->in_mul) use_tma = false;
-  for (int i = 0; use_tma && i < d->nsrc; ++i) {
-    if (!aligned(d->src[i], d->Din > 1 && !gwc)) use_tma = false;
-    if (!gwc && i + 1 < d->nsrc && d->src[i].C % plan.CK) use_tma = false;
-  }
-  if (use_tma) {
-    const int taps = g.KD * g.KH * g.KW;
-    if (gwc) {
-      const int nch = plan.CK * k.cpg;
-      for (int i = 0; i < 2 && use_tma; ++i) {
-        const esm_src_t& sv = d->src[i];
-        const long long dims[5] = {d->Win, d->Hin, 1, sv.C, d->B};
-        const long long str[4] = {sv.sH, sv.sH * d->Hin, sv.sC, sv.sB};
-        const int box[5] = {i == 0 ? tl.IWL : tl.IWR, tl.IH, 1, nch, 1};
-        use_tma = sv.sC >= sv.sH * d->Hin && encode_map(&maps.src[i], sv.ptr, 5, dims, str, box);
+
+  // ---- autotune: time the best-ranked candidates on the device (first call per shape, never during
+  // graph capture); "measure, don't guess" -- the model above mis-ranks latency-bound layers ----
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  const char* env = getenv("ESM_AUTOTUNE");
+  const bool tune = cap == cudaStreamCaptureStatusNone && !(env && env[0] == '0');
+  if (tune && cands.size() > 1) {
+    // shortlist: the 6 best by model + the best of every distinct CTA size (diversity)
+    std::vector<Candidate> shortlist(cands.begin(), cands.begin() + std::min<size_t>(6, cands.size()));
+    for (int nt = 32; nt <= 256; nt += 32)
+      for (const Candidate& c : cands)
+        if (c.tl.slots * (c.COP / COG) == nt) {
+          bool dup = false;
+          for (const Candidate& s2 : shortlist)
+            if (s2.tl.slots == c.tl.slots && s2.tl.TWG == c.tl.TWG && s2.tl.TD == c.tl.TD && s2.CK == c.CK && s2.COP == c.COP) dup = true;
+          if (!dup) shortlist.push_back(c);
+          break;
+        }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best_ms = 1e30f;
+    for (const Candidate& c : shortlist) {
+      Plan cp;
+      if (make_plan(c, &cp) != ESM_OK) continue;
+      if (launch_plan(d, g, k, cp, lg, num_sms, st) != ESM_OK) continue;  // warm (also sets attributes)
+      cudaEventRecord(e0, st);
+      launch_plan(d, g, k, cp, lg, num_sms, st);
+      launch_plan(d, g, k, cp, lg, num_sms, st);
+      cudaEventRecord(e1, st);
+      if (cudaEventSynchronize(e1) != cudaSuccess) {
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return check_launch("conv(autotune)");
       }
-    } else {
-      for (int i = 0; i < d->nsrc && use_tma; ++i) {
-        const esm_src_t& sv = d->src[i];
-        const long long sD = d->Din > 1 ? sv.sD : sv.sH * d->Hin;
-        const long long dims[5] = {d->Win, d->Hin, d->Din, sv.C, d->B};
-        const long long str[4] = {sv.sH, sD, sv.sC, sv.sB};
-        const int box[5] = {tl.IWP, tl.IH, tl.ID, plan.CK, 1};
-        use_tma = encode_map(&maps.src[i], sv.ptr, 5, dims, str, box);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (getenv("ESM_DEBUG_PLAN"))
+        fprintf(stderr, "[esm tune] Cin=%d Cout=%d k=%d J=(%d,%d,%d): CK=%d COP=%d tile=(%d,%d,%d) thr=%d smem=%zuKB -> %.1f us\n",
+                d->Cin, d->Cout, d->kw, lg.Jd, lg.Jh, lg.Jw, c.CK, c.COP, c.tl.TD, c.tl.TH, c.tl.TWG * 4, c.tl.slots * (c.COP / COG),
+                c.tl.smem / 1024, ms * 500.f);
+      if (ms < best_ms) {
+        best_ms = ms;
+        best_plan = cp;
       }
     }
-    if (use_tma) {
-      const long long dims[3] = {g.CoutPad, g.CinPad, (long long)taps * g.phases};
-      const long long str[2] = {g.CoutPad, (long long)g.CoutPad * g.CinPad};
-      const int box[3] = {plan.COP, plan.CK, taps};
-      use_tma = encode_map(&maps.w, d->weight, 3, dims, str, box);
-    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
   }
-  // window offset of the TMA brick: boxes must start on a multiple of 4 columns
-  const int xo_a = gwc ? 0 : ((4 - ((d->transposed ? 1 : d->pw) & 3)) & 3);  // transposed: W phase 0 has pad 1
-  if (use_tma && !gwc && xo_a != 0 && xo_a != 3) use_tma = false;
-  if (use_tma && !plan.fn_tma[xo_a == 3]) use_tma = false;
-  if (use_tma && d->transposed && !plan.fn_tma[0]) use_tma = false;
-  if (getenv("ESM_DEBUG_PLAN")) fprintf(stderr, "[esm launch] Cin=%d Cout=%d tma=%d xo=%d\n", d->Cin, d->Cout, (int)use_tma, xo_a);
-  const long long resident = (long long)num_sms * plan.blocks_per_sm;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (!use_tma) {
-    const unsigned grid = (unsigned)(total < resident ? total : resident);  // persistent CTAs stride over the tiles
-    plan.fn<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
-  } else if (!d->transposed) {
-    const unsigned grid = (unsigned)(total < resident ? total : resident);
-    plan.fn_tma[xo_a == 3]<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
-  } else {
-    // sub-pixel phases along W have pad 1 (phase 0, window offset 3) and pad 0 (phase 1, offset 0):
-    // one launch per W phase, each enumerating the (d,h) phases
-    k.phases = g.phases / 2;
-    k.total_work = (int)(total / 2);
-    const unsigned grid = (unsigned)(k.total_work < resident ? k.total_work : resident);
-    k.pzw_sel = 0;
-    plan.fn_tma[1]<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
-    k.pzw_sel = 1;
-    plan.fn_tma[0]<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
-  }
-  return check_launch("conv");
+  if (getenv("ESM_DEBUG_PLAN"))
+    fprintf(stderr, "[esm plan] Cin=%d Cout=%d k=(%d,%d,%d) s=%d%s%s J=(%d,%d,%d): CK=%d COP=%d cosplit=%d tile=(%d,%d,%d) threads=%d "
+            "smem=%zu KB occ=%d tuned=%d\n",
+            d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed ? " T" : "", gwc ? " gwc" : "", lg.Jd, lg.Jh, lg.Jw,
+            best_plan.CK, best_plan.COP, best_plan.cosplit, best_plan.tl.TD, best_plan.tl.TH, best_plan.tl.TWG * 4,
+            best_plan.tl.slots * (best_plan.COP / COG), best_plan.tl.smem / 1024, best_plan.blocks_per_sm, (int)tune);
+  plans.emplace(key, best_plan);
+  return launch_plan(d, g, k, best_plan, lg, num_sms, st);
 }

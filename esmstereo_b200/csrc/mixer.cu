@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(256) sm_pointwise_kernel(const float* __restri
 
 constexpr int SP_TX = 32, SP_TY = 8;
 
-template <int C>
+// K = depthwise kernel size when known at compile time (7 on the ESMStereo path), 0 = runtime loops
+template <int C, int K>
 __global__ void __launch_bounds__(SP_TX * SP_TY) sm_spatial_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                    int H, int W, const float* __restrict__ dw_w,
                                                                    const float* __restrict__ dw_b, int k,
@@ -135,14 +136,36 @@ __global__ void __launch_bounds__(SP_TX * SP_TY) sm_spatial_kernel(const float* 
   const int px = blockIdx.x * SP_TX + threadIdx.x, py = blockIdx.y * SP_TY + threadIdx.y;
   if (px >= W || py >= H) return;
   float t[C];
+  if (K > 0) {
+    // fully unrolled taps, two channels in flight: the serial fmaf chain of the runtime loop was
+    // latency-bound (34 us per launch at 96x312x16)
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    float a = bsm[c];
-    const float* tp = tile + (c * THp + threadIdx.y) * TWp + threadIdx.x;
-    const float* wp = wsm + c * k * k;
-    for (int ky = 0; ky < k; ++ky)
-      for (int kx = 0; kx < k; ++kx) a = fmaf(wp[ky * k + kx], tp[ky * TWp + kx], a);
-    t[c] = a;
+    for (int c = 0; c < C; c += 2) {
+      float a0 = bsm[c], a1 = bsm[c + 1];
+      const float* tp0 = tile + (c * THp + threadIdx.y) * TWp + threadIdx.x;
+      const float* tp1 = tp0 + THp * TWp;
+      const float* wp0 = wsm + c * K * K;
+      const float* wp1 = wp0 + K * K;
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          a0 = fmaf(wp0[ky * K + kx], tp0[ky * TWp + kx], a0);
+          a1 = fmaf(wp1[ky * K + kx], tp1[ky * TWp + kx], a1);
+        }
+      t[c] = a0;
+      t[c + 1] = a1;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float a = bsm[c];
+      const float* tp = tile + (c * THp + threadIdx.y) * TWp + threadIdx.x;
+      const float* wp = wsm + c * k * k;
+      for (int ky = 0; ky < k; ++ky)
+        for (int kx = 0; kx < k; ++kx) a = fmaf(wp[ky * k + kx], tp[ky * TWp + kx], a);
+      t[c] = a;
+    }
   }
   ln_mlp_shuffle_residual<C>(t, s);
   const long long base = (long long)b * C * plane + (long long)py * W + px;
@@ -189,9 +212,14 @@ extern "C" int esm_sm_spatial_f32(const float* x, float* y, int B, int C, int H,
   ESM_REQUIRE(B <= 65535 && ceil_div(H, SP_TY) <= 65535, "sm_spatial: grid too large");
   dim3 grid((unsigned)ceil_div(W, SP_TX), (unsigned)ceil_div(H, SP_TY), (unsigned)B), block(SP_TX, SP_TY);
   const size_t smem = ((size_t)C * (SP_TY + k - 1) * (SP_TX + k - 1) + (size_t)C * k * k + C) * sizeof(float);
-  if (C == 16)
-    sm_spatial_kernel<16><<<grid, block, smem, (cudaStream_t)stream>>>(x, y, H, W, dw_w, dw_b, k, *mlp, extra_residual);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 16 && k == 7)
+    sm_spatial_kernel<16, 7><<<grid, block, smem, st>>>(x, y, H, W, dw_w, dw_b, k, *mlp, extra_residual);
+  else if (C == 8 && k == 7)
+    sm_spatial_kernel<8, 7><<<grid, block, smem, st>>>(x, y, H, W, dw_w, dw_b, k, *mlp, extra_residual);
+  else if (C == 16)
+    sm_spatial_kernel<16, 0><<<grid, block, smem, st>>>(x, y, H, W, dw_w, dw_b, k, *mlp, extra_residual);
   else
-    sm_spatial_kernel<8><<<grid, block, smem, (cudaStream_t)stream>>>(x, y, H, W, dw_w, dw_b, k, *mlp, extra_residual);
+    sm_spatial_kernel<8, 0><<<grid, block, smem, st>>>(x, y, H, W, dw_w, dw_b, k, *mlp, extra_residual);
   return check_launch("sm_spatial");
 }
