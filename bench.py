@@ -366,6 +366,7 @@ def op_breakdown(model, pair):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ops.PROFILE = []
     torch.cuda.synchronize()
+    torch.cuda._sleep(60_000_000)  # keep the GPU busy (~30 ms) so the host runs ahead: event gaps are then pure device time
     e0.record()
     model(*pair, train_status=False)
     e1.record()
@@ -373,9 +374,24 @@ def op_breakdown(model, pair):
     rows = [(lbl, a.elapsed_time(b)) for lbl, a, b in ops.PROFILE]
     ops.PROFILE = None
     total_ops = sum(t for _, t in rows)
-    sys.stderr.write("---- per-operator device time (eager, one forward; includes launch gaps) ----\n")
+    sys.stderr.write("---- per-operator device time (eager forward queued behind a busy GPU: pure device time) ----\n")
+    import re
     for lbl, t in rows:
-        sys.stderr.write("%8.1f us  %s\n" % (t * 1e3, lbl))
+        m = re.match(r"(de)?conv(\d)d (\d+)->(\d+) k(\d)(\+gwc)? s(\d) in (\d+)x(\d+)x(\d+)", lbl)
+        extra = ""
+        if m:
+            dec, nd, cin, cout, k, _g, st, D, Hh, Ww = m.groups()
+            nd, cin, cout, k, st, D, Hh, Ww = int(nd), int(cin), int(cout), int(k), int(st), int(D), int(Hh), int(Ww)
+            taps = k ** nd
+            vox = D * Hh * Ww  # input voxels
+            if dec:
+                fl = 2.0 * cin * cout * taps * vox
+            else:
+                out_vox = vox / (st ** nd) if st > 1 else vox
+                fl = 2.0 * cin * cout * taps * out_vox
+            fl *= pair[0].shape[0] * (2 if lbl.startswith("conv2d 3->") or False else 1)
+            extra = "  %6.2f GFLOP %5.1f TFLOP/s" % (fl / 1e9, fl / (t * 1e-3) / 1e12)
+        sys.stderr.write("%8.1f us  %s%s\n" % (t * 1e3, lbl, extra))
     sys.stderr.write("hot-path ops total %.3f ms; forward wall (eager) %.3f ms\n" % (total_ops, e0.elapsed_time(e1)))
     agg = {}
     for lbl, t in rows:

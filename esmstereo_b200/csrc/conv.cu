@@ -120,16 +120,16 @@ static PackGeom pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transpo
 // host-side tiling + dispatch
 // ------------------------------------------------------------------------------------------
 struct Tiling {
-  int TWG, TH, TD, slots, IWP, ID, IH, IWR, IWL;
+  int TWG, TH, TD, slots, IWP, ID, IH, IWR, IWL, nstages;
   size_t smem;
 };
 
-static size_t conv_smem_bytes(int CK, int ID, int IH, int IWP, int taps, int COP, bool gwc, int cpg, int* IWR_out,
-                              int* IWL_out) {
+static size_t conv_smem_bytes(int CK, int ID, int IH, int IWP, int taps, int COP, bool gwc, int cpg, int nstages,
+                              int* IWR_out, int* IWL_out) {
   auto pad32 = [](size_t n) { return (n + 31) & ~(size_t)31; };  // buffers are multiples of 128 bytes (TMA destinations)
   const size_t in_elems = pad32((size_t)CK * ID * IH * IWP);
   const size_t w_elems = pad32((size_t)taps * CK * COP);
-  size_t total = 2 * in_elems + (gwc ? 3 : 2) * w_elems;
+  size_t total = (gwc ? 2 : nstages) * in_elems + (gwc ? 3 : nstages) * w_elems;
   int IWR = 0, IWL = 0;
   if (gwc) {  // staging boxes start on a multiple of 4 columns (TMA): up to 3 extra columns on the left
     IWL = round_up(IWP + 3, 4);
@@ -138,7 +138,7 @@ static size_t conv_smem_bytes(int CK, int ID, int IH, int IWP, int taps, int COP
   }
   if (IWR_out) *IWR_out = IWR;
   if (IWL_out) *IWL_out = IWL;
-  return total * sizeof(float) + 128 /* base alignment slack */ + 32 /* mbarriers */;
+  return total * sizeof(float) + 128 /* slack */ + 64 /* mbarriers */;
 }
 
 // Per-SM residency estimate: the kernels compile to <=128 registers (__launch_bounds__(256, 2)), so at most 512 threads per SM;
@@ -178,8 +178,11 @@ static void enumerate_tilings(int Jw, int Jh, int Jd, int cin, int ncog, int KW,
           while (IWP % 32 != want) IWP += 4;
         }
         if (IWP > 256 || IH > 256 || ID > 256) continue;  // TMA box limits
+        const int nchunks = ceil_div(cin, CK);
+        for (int nstages = 2; nstages <= (gwc ? 2 : 4); nstages += 2) {
+        if (nstages > 2 && nchunks < 3) break;  // a deeper ring only pays when a tile has more chunks than stages
         int IWR = 0, IWL = 0;
-        const size_t smem = conv_smem_bytes(CK, ID, IH, IWP, KD * KH * KW, COP, gwc, cpg, &IWR, &IWL);
+        const size_t smem = conv_smem_bytes(CK, ID, IH, IWP, KD * KH * KW, COP, gwc, cpg, nstages, &IWR, &IWL);
         if (smem > 224 * 1024 || IWR > 256) continue;
         const int nthreads = slots * ncog;
         const int ctas = resident_ctas(nthreads, smem);
@@ -193,8 +196,8 @@ static void enumerate_tilings(int Jw, int Jh, int Jd, int cin, int ncog, int KW,
         const double hide = ctas * warps >= 12 ? 1.0 : 12.0 / (ctas * warps);
         const double ffma2 = (double)KD * KH * KW * CK * 16;
         const double t_math = ffma2 * 2.0 * smsp_load * 1.3 * hide;
-        const double t_item = t_math > 1500.0 ? t_math : 1500.0;
-        const int nchunks = ceil_div(cin, CK);
+        const double t_tma = nstages > 2 ? 700.0 : 1500.0;  // exposed TMA round trip per item
+        const double t_item = t_math > t_tma ? t_math : t_tma;
         const long long tiles = (long long)ceil_div(Jw, TW) * ceil_div(Jh, TH) * ceil_div(Jd, TD) * work_mult;
         const long long wave = (long long)(num_sms > 0 ? num_sms : 148) * ctas;
         const double waves = (double)ceil_div_ll(tiles, wave);
@@ -211,11 +214,13 @@ static void enumerate_tilings(int Jw, int Jh, int Jd, int cin, int ncog, int KW,
         c.tl.IH = IH;
         c.tl.IWR = IWR;
         c.tl.IWL = IWL;
+        c.tl.nstages = nstages;
         c.tl.smem = smem;
         c.CK = CK;
         c.COP = COP;
         c.cosplit = cosplit;
         out->push_back(c);
+        }
       }
     }
   }
@@ -310,6 +315,7 @@ static int launch_plan(const esm_conv_t* d, const PackGeom& g, ConvK k, const Pl
   k.IWR = tl.IWR;
   k.IWL = tl.IWL;
   k.pzw_sel = -1;
+  k.nstages = tl.nstages;
   k.tilesW = ceil_div(lg.Jw, tl.TWG * 4);
   k.tilesH = ceil_div(lg.Jh, tl.TH);
   k.tilesD = ceil_div(lg.Jd, tl.TD);
@@ -596,13 +602,15 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   const bool tune = cap == cudaStreamCaptureStatusNone && !(env && env[0] == '0');
   if (tune && cands.size() > 1) {
     // shortlist: the 6 best by model + the best of every distinct CTA size (diversity)
-    std::vector<Candidate> shortlist(cands.begin(), cands.begin() + std::min<size_t>(6, cands.size()));
+    std::vector<Candidate> shortlist(cands.begin(), cands.begin() + std::min<size_t>(8, cands.size()));
     for (int nt = 32; nt <= 256; nt += 32)
       for (const Candidate& c : cands)
         if (c.tl.slots * (c.COP / COG) == nt) {
           bool dup = false;
           for (const Candidate& s2 : shortlist)
-            if (s2.tl.slots == c.tl.slots && s2.tl.TWG == c.tl.TWG && s2.tl.TD == c.tl.TD && s2.CK == c.CK && s2.COP == c.COP) dup = true;
+            if (s2.tl.slots == c.tl.slots && s2.tl.TWG == c.tl.TWG && s2.tl.TD == c.tl.TD && s2.CK == c.CK && s2.COP == c.COP &&
+                s2.tl.nstages == c.tl.nstages)
+              dup = true;
           if (!dup) shortlist.push_back(c);
           break;
         }
@@ -626,9 +634,9 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, e0, e1);
       if (getenv("ESM_DEBUG_PLAN"))
-        fprintf(stderr, "[esm tune] Cin=%d Cout=%d k=%d J=(%d,%d,%d): CK=%d COP=%d tile=(%d,%d,%d) thr=%d smem=%zuKB -> %.1f us\n",
+        fprintf(stderr, "[esm tune] Cin=%d Cout=%d k=%d J=(%d,%d,%d): CK=%d COP=%d tile=(%d,%d,%d) thr=%d ns=%d smem=%zuKB -> %.1f us\n",
                 d->Cin, d->Cout, d->kw, lg.Jd, lg.Jh, lg.Jw, c.CK, c.COP, c.tl.TD, c.tl.TH, c.tl.TWG * 4, c.tl.slots * (c.COP / COG),
-                c.tl.smem / 1024, ms * 500.f);
+                c.tl.nstages, c.tl.smem / 1024, ms * 500.f);
       if (ms < best_ms) {
         best_ms = ms;
         best_plan = cp;

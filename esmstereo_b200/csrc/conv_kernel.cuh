@@ -36,6 +36,7 @@ struct ConvK {
   int cosplit, COP;  // output channels are split over `cosplit` CTAs of COP (padded) channels each
   int phases, total_work, IWR, IWL;  // GWC staging row pitches (right / left)
   int pzw_sel;  // transposed conv: -1 = all W phases in this launch, 0/1 = only that W phase (TMA launches)
+  int nstages;  // ring depth of the TMA pipeline (2..4); cp.async and GWC paths use 2
 };
 
 // ---- cp.async helpers (LDGSTS): global -> shared without register staging; src_size 0 zero-fills ----
@@ -166,15 +167,16 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
   const int in_elems = (CK * chan_stride + 31) & ~31;   // every buffer is a multiple of 128 bytes
   const int w_elems = (taps * CK * COP + 31) & ~31;
   // smem carve-up: [in0][in1][w0][w1][w2 (GWC)][L staging][R staging][mbarriers]
+  const int NS = (TMA && !GWC) ? p.nstages : 2;  // ring depth
   float* s_in0 = smem;
-  float* s_w0 = smem + 2 * in_elems;
+  float* s_w0 = smem + NS * in_elems;
   const int IWR = p.IWR;                  // GWC: right staging row pitch
-  float* s_L = s_w0 + (GWC ? 3 : 2) * w_elems;              // GWC only
+  float* s_L = s_w0 + (GWC ? 3 : NS) * w_elems;             // GWC only
   const int IWL = p.IWL;                  // GWC: left staging row pitch
   const int l_elems = (CK * p.cpg * IH * IWL + 31) & ~31;
   const int r_elems = (CK * p.cpg * IH * IWR + 31) & ~31;
   float* s_R = s_L + l_elems;                               // GWC only: [CK*cpg][IH][IWR]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(GWC ? (s_R + r_elems) : s_L);  // [0],[1]: stages; [2]: GWC rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(GWC ? (s_R + r_elems) : s_L);  // [0..3]: stages; [4]: GWC rows
 
   const int slot = tid % p.slots;
   const int cog = tid / p.slots;
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
     const int iw0 = t.tileW * TW * S - t.pw;
     const int ih0 = t.tileH * p.TH * S - t.ph;
     const int id0 = t.tileD * p.TD * S - t.pd;
-    uint64_t* bar = &bars[2];
+    uint64_t* bar = &bars[4];
     mbar_expect_tx(bar, (unsigned)((CK * p.cpg * IH * (IWL + IWR) + taps * CK * COP) * sizeof(float)));
     int ro;
     const int rx0 = right_origin(iw0, id0, &ro);
@@ -415,9 +417,8 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
   };
   if (TMA) {
     if (tid == 0) {
-      mbar_init(&bars[0], 1);
-      mbar_init(&bars[1], 1);
-      mbar_init(&bars[2], 1);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
       asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
     if (GWC) {
       if (TMA) {
         if (tid == 0) tma_issue_lr(0);
-        mbar_wait(&bars[2], 0);
+        mbar_wait(&bars[4], 0);
       } else {
         load_weights(0, s_w0);
         load_lr(0);
@@ -455,10 +456,8 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
       }
       if (!TMA) cp_async_commit();
     } else if (TMA) {
-      if (tid == 0) {
-        tma_issue(0, 0);
-        if (n_items > 1) tma_issue(1, 1);
-      }
+      if (tid == 0)
+        for (int i = 0; i < NS && i < n_items; ++i) tma_issue(i, i);
     } else {
       load_weights(0, s_w0);
       load_inputs(0, s_in0);
@@ -467,14 +466,15 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
   }
 
   for (int item = 0; item < n_items; ++item) {
-    const float* s_in = s_in0 + (item & 1) * in_elems;
+    const int stage = (TMA && !GWC) ? item % NS : (item & 1);
+    const float* s_in = s_in0 + stage * in_elems;
     const float* s_w;
     if (GWC) {
       s_w = s_w0 + (item % 3) * w_elems;
       // rows + weights of item+1 have landed; every warp is done reading V[(item+1)&1] (FFMA2 of item-1,
       // fenced by the barrier that closes each iteration)
       if (TMA) {
-        if (item + 1 < n_items) mbar_wait(&bars[2], (item + 1) & 1);
+        if (item + 1 < n_items) mbar_wait(&bars[4], (item + 1) & 1);
       } else {
         cp_async_wait<0>();
         __syncthreads();
@@ -491,8 +491,8 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
       }
       if (!TMA) cp_async_commit();
     } else if (TMA) {
-      s_w = s_w0 + (item & 1) * w_elems;
-      mbar_wait(&bars[item & 1], (item >> 1) & 1);
+      s_w = s_w0 + stage * w_elems;
+      mbar_wait(&bars[stage], (item / NS) & 1);
     } else {
       s_w = s_w0 + (item & 1) * w_elems;
       if (item + 1 < n_items) {
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
         for (int j = 0; j < COG / 2; ++j) acc[v][j] = make_float2(0.f, 0.f);
     }
     __syncthreads();  // stage (item&1) / V[item&1] may be overwritten from here on
-    if (TMA && !GWC && tid == 0 && item + 2 < n_items) tma_issue(item + 2, item & 1);
+    if (TMA && !GWC && tid == 0 && item + NS < n_items) tma_issue(item + NS, stage);
   }
   if (!TMA) cp_async_wait<0>();
 }
