@@ -374,12 +374,30 @@ static int launch_plan(const esm_conv_t* d, const PackGeom& g, ConvK k, const Pl
     }
   }
   const long long resident = (long long)num_sms * plan.blocks_per_sm;
+  // Optional programmatic stream serialization (PDL, ESM_PDL=1): the kernel's prologue (mbarrier init,
+  // descriptor fetch) may overlap the tail of the previous kernel; it waits on griddepcontrol.wait
+  // before its first global access.  Measured on B200 it LOSES 5% end to end on this graph (206 vs 218
+  // pairs/s): early-launched dependents take SM slots from the persistent CTAs still running, so it is off
+  // by default.
+  static const bool pdl = getenv("ESM_PDL") != nullptr;
+  auto launch = [&](conv_fn_t fn, unsigned grid, const ConvK& kk) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3((unsigned)kk.nthreads);
+    cfg.dynamicSmemBytes = tl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, fn, kk, maps);
+  };
   if (!use_tma) {
-    const unsigned grid = (unsigned)(total < resident ? total : resident);  // persistent CTAs stride over the tiles
-    plan.fn<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
+    launch(plan.fn, (unsigned)(total < resident ? total : resident), k);  // persistent CTAs stride over the tiles
   } else if (!d->transposed) {
-    const unsigned grid = (unsigned)(total < resident ? total : resident);
-    plan.fn_tma[xo_a == 3]<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
+    launch(plan.fn_tma[xo_a == 3], (unsigned)(total < resident ? total : resident), k);
   } else {
     // sub-pixel phases along W have pad 1 (phase 0, window offset 3) and pad 0 (phase 1, offset 0):
     // one launch per W phase, each enumerating the (d,h) phases
@@ -387,9 +405,9 @@ static int launch_plan(const esm_conv_t* d, const PackGeom& g, ConvK k, const Pl
     k.total_work = (int)(total / 2);
     const unsigned grid = (unsigned)(k.total_work < resident ? k.total_work : resident);
     k.pzw_sel = 0;
-    plan.fn_tma[1]<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
+    launch(plan.fn_tma[1], grid, k);
     k.pzw_sel = 1;
-    plan.fn_tma[0]<<<grid, k.nthreads, tl.smem, st>>>(k, maps);
+    launch(plan.fn_tma[0], grid, k);
   }
   return check_launch("conv");
 }
