@@ -152,14 +152,15 @@ static int resident_ctas(int nthreads, size_t smem) {
 
 struct Candidate {
   Tiling tl;
-  int CK, COP, cosplit;
+  int CK, COP, COG, cosplit;
   double cost;
 };
 
 // Enumerate tile shapes for one (channel split, chunk depth) and append them with their modelled cost.
-static void enumerate_tilings(int Jw, int Jh, int Jd, int cin, int ncog, int KW, int KH, int KD, int S, int CK, int COP,
+static void enumerate_tilings(int Jw, int Jh, int Jd, int cin, int COG, int KW, int KH, int KD, int S, int CK, int COP,
                               int cosplit, bool gwc, int cpg, int xo, long long work_mult, int num_sms, double extra_cost,
                               std::vector<Candidate>* out) {
+  const int ncog = COP / COG;
   for (int slots = 32; slots * ncog <= 256; slots += 32) {
     for (int TWG = 1; TWG <= 16; TWG *= 2) {
       if (slots % TWG) continue;
@@ -194,7 +195,7 @@ static void enumerate_tilings(int Jw, int Jh, int Jd, int cin, int ncog, int KW,
         const int warps = nthreads / 32;
         const double smsp_load = (double)((ctas * warps + 3) / 4);
         const double hide = ctas * warps >= 12 ? 1.0 : 12.0 / (ctas * warps);
-        const double ffma2 = (double)KD * KH * KW * CK * 16;
+        const double ffma2 = (double)KD * KH * KW * CK * 2 * COG;  // per warp per item: 4 voxels x COG/2 channel pairs per (tap, channel)
         const double t_math = ffma2 * 2.0 * smsp_load * 1.3 * hide;
         const double t_tma = nstages > 2 ? 700.0 : 1500.0;  // exposed TMA round trip per item
         const double t_item = t_math > t_tma ? t_math : t_tma;
@@ -218,6 +219,7 @@ static void enumerate_tilings(int Jw, int Jh, int Jd, int cin, int ncog, int KW,
         c.tl.smem = smem;
         c.CK = CK;
         c.COP = COP;
+        c.COG = COG;
         c.cosplit = cosplit;
         out->push_back(c);
         }
@@ -556,22 +558,26 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   if (it != plans.end()) return launch_plan(d, g, k, it->second, lg, num_sms, st);
 
   // ---- plan: enumerate (channel split x chunk depth x tile shape), rank by the analytic model ----
-  const int COG = g.CoutPad == 4 ? 4 : 8;
   const int ck0 = g.CinPad == 1 ? 1 : 8;
   const int xo_plan = (!gwc && (d->transposed || (d->pw & 3) == 1)) ? 3 : 0;  // room for the XO=3 window
   std::vector<Candidate> cands;
-  for (int cosplit = 1; cosplit <= g.CoutPad / COG; ++cosplit) {
-    // a CTA owns COP <= 64 channels (8 channel groups x >= 32 voxel slots = 256 threads); more
-    // splits re-stage the same bricks but give small layers more CTAs
-    if (g.CoutPad % cosplit || (g.CoutPad / cosplit) % COG || g.CoutPad / cosplit > 64) continue;
-    const int COP = g.CoutPad / cosplit;
-    const long long mult = (long long)d->B * g.phases * cosplit;
-    const double extra = 1.0 + 0.03 * (cosplit - 1);
-    for (int ck = ck0; ck >= (ck0 == 8 && COG == 8 ? 4 : ck0); ck /= 2) {
-      // chunk depth 8 or 4: a shallower chunk halves the staged brick (more resident warps on the 8-channel layers)
-      enumerate_tilings(lg.Jw, lg.Jh, lg.Jd, d->Cin, COP / COG, g.KW, g.KH, g.KD, S, ck, COP, cosplit, gwc, k.cpg, xo_plan, mult,
-                        num_sms, extra, &cands);
-      if (ck == 1) break;
+  // channel-group width per thread: 8 (4 voxels x 8 channels = 32 accumulators) or 4 (half the serial
+  // FFMA2 chain per thread, twice the warps: wins on the latency-bound small layers)
+  for (int COG = (g.CoutPad == 4 ? 4 : 8); COG >= 4; COG -= 4) {
+    if (COG == 4 && (gwc || ck0 != 8)) break;  // instantiated for 8-channel chunks only
+    for (int cosplit = 1; cosplit <= g.CoutPad / COG; ++cosplit) {
+      // a CTA owns COP <= 64 channels (<= 256 threads); more splits re-stage the same bricks but give
+      // small layers more CTAs
+      if (g.CoutPad % cosplit || (g.CoutPad / cosplit) % COG || g.CoutPad / cosplit > 64) continue;
+      const int COP = g.CoutPad / cosplit;
+      const long long mult = (long long)d->B * g.phases * cosplit;
+      const double extra = 1.0 + 0.03 * (cosplit - 1);
+      for (int ck = ck0; ck >= (ck0 == 8 && COG == 8 ? 4 : ck0); ck /= 2) {
+        // chunk depth 8 or 4: a shallower chunk halves the staged brick (more resident warps on the 8-channel layers)
+        enumerate_tilings(lg.Jw, lg.Jh, lg.Jd, d->Cin, COG, g.KW, g.KH, g.KD, S, ck, COP, cosplit, gwc, k.cpg, xo_plan, mult,
+                          num_sms, extra, &cands);
+        if (ck == 1) break;
+      }
     }
   }
   ESM_REQUIRE(!cands.empty(), "conv: no tiling for Cin=%d Cout=%d k=(%d,%d,%d)%s", d->Cin, d->Cout, d->kd, d->kh, d->kw,
@@ -583,6 +589,7 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
     np->CK = c.CK;
     np->COP = c.COP;
     np->cosplit = c.cosplit;
+    const int COG = c.COG;
     np->COG = COG;
     np->fn = pick_kernel(g.KW, S, COG, c.CK, gwc, false, 0);
     np->fn_tma[0] = pick_kernel(g.KW, S, COG, c.CK, gwc, true, 0);
@@ -623,11 +630,11 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
     std::vector<Candidate> shortlist(cands.begin(), cands.begin() + std::min<size_t>(8, cands.size()));
     for (int nt = 32; nt <= 256; nt += 32)
       for (const Candidate& c : cands)
-        if (c.tl.slots * (c.COP / COG) == nt) {
+        if (c.tl.slots * (c.COP / c.COG) == nt) {
           bool dup = false;
           for (const Candidate& s2 : shortlist)
             if (s2.tl.slots == c.tl.slots && s2.tl.TWG == c.tl.TWG && s2.tl.TD == c.tl.TD && s2.CK == c.CK && s2.COP == c.COP &&
-                s2.tl.nstages == c.tl.nstages)
+                s2.tl.nstages == c.tl.nstages && s2.COG == c.COG)
               dup = true;
           if (!dup) shortlist.push_back(c);
           break;
@@ -653,7 +660,7 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
       cudaEventElapsedTime(&ms, e0, e1);
       if (getenv("ESM_DEBUG_PLAN"))
         fprintf(stderr, "[esm tune] Cin=%d Cout=%d k=%d J=(%d,%d,%d): CK=%d COP=%d tile=(%d,%d,%d) thr=%d ns=%d smem=%zuKB -> %.1f us\n",
-                d->Cin, d->Cout, d->kw, lg.Jd, lg.Jh, lg.Jw, c.CK, c.COP, c.tl.TD, c.tl.TH, c.tl.TWG * 4, c.tl.slots * (c.COP / COG),
+                d->Cin, d->Cout, d->kw, lg.Jd, lg.Jh, lg.Jw, c.CK, c.COP, c.tl.TD, c.tl.TH, c.tl.TWG * 4, c.tl.slots * (c.COP / c.COG),
                 c.tl.nstages, c.tl.smem / 1024, ms * 500.f);
       if (ms < best_ms) {
         best_ms = ms;
@@ -668,7 +675,7 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
             "smem=%zu KB occ=%d tuned=%d\n",
             d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed ? " T" : "", gwc ? " gwc" : "", lg.Jd, lg.Jh, lg.Jw,
             best_plan.CK, best_plan.COP, best_plan.cosplit, best_plan.tl.TD, best_plan.tl.TH, best_plan.tl.TWG * 4,
-            best_plan.tl.slots * (best_plan.COP / COG), best_plan.tl.smem / 1024, best_plan.blocks_per_sm, (int)tune);
+            best_plan.tl.slots * (best_plan.COP / best_plan.COG), best_plan.tl.smem / 1024, best_plan.blocks_per_sm, (int)tune);
   plans.emplace(key, best_plan);
   return launch_plan(d, g, k, best_plan, lg, num_sms, st);
 }
