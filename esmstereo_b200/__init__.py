@@ -9,9 +9,10 @@ Drop-in for the reference's `models` package on that path:
 The hot path has no CPU / PyTorch fallback: it needs esmstereo_b200/csrc/libesm_b200.so
 (`python -m esmstereo_b200.build`) and a CUDA device.
 """
-from .model import ESMStereo, ESMStereo_confidence, ESMStereo_trt, GraphedStereo, __models__  # noqa: F401
+from .model import (ESMStereo, ESMStereo_confidence, ESMStereo_trt, GraphedStereo, StereoPipeline,  # noqa: F401
+                    __models__)
 from .ops import (build_gwc_volume, build_norm_correlation_volume, disparity_regression,  # noqa: F401
                   regression_topk)
 
-__all__ = ["ESMStereo", "ESMStereo_trt", "ESMStereo_confidence", "GraphedStereo", "__models__",
+__all__ = ["ESMStereo", "ESMStereo_trt", "ESMStereo_confidence", "GraphedStereo", "StereoPipeline", "__models__",
            "build_gwc_volume", "build_norm_correlation_volume", "disparity_regression", "regression_topk"]

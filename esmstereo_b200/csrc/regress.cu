@@ -17,17 +17,28 @@ __global__ void __launch_bounds__(128) regression_top2_kernel(const float* __res
   const long long b = i / plane;
   const long long p = i - b * plane;
   const float* c = cost + b * D * plane + p;
-  // descending stable order: strict '>' keeps the lower index first on ties
+  // descending stable order: strict '>' keeps the lower index first on ties.
+  // The D loads of a pixel are independent: issue them 16 at a time (memory-level parallelism; the
+  // plain loop paid one DRAM round trip per disparity) and fold them into the running top-2 in order.
   float v1 = -INFINITY, v2 = -INFINITY;
   int i1 = 0, i2 = 0;
   bool has1 = false, has2 = false;
-  for (int d = 0; d < D; ++d) {
-    const float v = __ldg(c + (long long)d * plane);
-    if (!has1 || v > v1) {
-      v2 = v1; i2 = i1; has2 = has1;
-      v1 = v; i1 = d; has1 = true;
-    } else if (!has2 || v > v2) {
-      v2 = v; i2 = d; has2 = true;
+  constexpr int U = 16;
+  for (int d0 = 0; d0 < D; d0 += U) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = (d0 + u < D) ? __ldg(c + (long long)(d0 + u) * plane) : 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (d0 + u < D) {
+        const float x = v[u];
+        if (!has1 || x > v1) {
+          v2 = v1; i2 = i1; has2 = has1;
+          v1 = x; i1 = d0 + u; has1 = true;
+        } else if (!has2 || x > v2) {
+          v2 = x; i2 = d0 + u; has2 = true;
+        }
+      }
     }
   }
   float out;
@@ -56,7 +67,15 @@ __global__ void __launch_bounds__(128) disparity_regression_kernel(const float* 
   const long long p = i - b * plane;
   const float* c = cost + b * D * plane + p;
   float s = 0.f;
-  for (int d = 0; d < D; ++d) s = __fadd_rn(s, __fmul_rn(__ldg(c + (long long)d * plane), (float)d));
+  constexpr int U = 16;
+  for (int d0 = 0; d0 < D; d0 += U) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = (d0 + u < D) ? __ldg(c + (long long)(d0 + u) * plane) : 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (d0 + u < D) s = __fadd_rn(s, __fmul_rn(v[u], (float)(d0 + u)));
+  }
   pred[i] = s;
 }
 

@@ -239,3 +239,52 @@ class GraphedStereo:
         self.right.copy_(right, non_blocking=True)
         self.graph.replay()
         return self.out
+
+
+class StereoPipeline:
+    """Host-to-host serving loop around a `GraphedStereo`: pinned host images in, pinned host disparity
+    out, with the H2D copy of pair i+1 and the D2H copy of pair i-1 overlapping the graph replay of pair i
+    (separate copy stream, `depth` staging slots).
+
+        pipe = StereoPipeline(GraphedStereo(model, shape, train_status=False))
+        pipe.submit(left_pinned, right_pinned); ...; disp_host = pipe.result()   # results come back in order
+    """
+
+    def __init__(self, graphed: GraphedStereo, depth: int = 2, pick=lambda out: out[-1]) -> None:
+        self.g, self.depth, self.pick = graphed, depth, pick
+        dev = graphed.left.device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        example = pick(graphed.out)
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append(dict(
+                left=torch.empty_like(graphed.left), right=torch.empty_like(graphed.right),
+                out=torch.empty(example.shape, dtype=example.dtype).pin_memory(),
+                staged=torch.cuda.Event(), consumed=torch.cuda.Event(), done=torch.cuda.Event()))
+        self.submitted = self.returned = 0
+
+    def submit(self, left_host: torch.Tensor, right_host: torch.Tensor) -> None:
+        if self.submitted - self.returned >= self.depth:
+            raise RuntimeError("StereoPipeline: %d results outstanding, call result() first" % self.depth)
+        slot = self.slots[self.submitted % self.depth]
+        cur = torch.cuda.current_stream(self.g.left.device)
+        with torch.cuda.stream(self.copy_stream):
+            if self.submitted >= self.depth:
+                self.copy_stream.wait_event(slot["consumed"])  # staging buffers were read by the replay 2 steps ago
+            slot["left"].copy_(left_host, non_blocking=True)
+            slot["right"].copy_(right_host, non_blocking=True)
+            slot["staged"].record(self.copy_stream)
+        cur.wait_event(slot["staged"])
+        out = self.pick(self.g(slot["left"], slot["right"]))
+        slot["consumed"].record(cur)
+        slot["out"].copy_(out, non_blocking=True)
+        slot["done"].record(cur)
+        self.submitted += 1
+
+    def result(self) -> torch.Tensor:
+        if self.returned >= self.submitted:
+            raise RuntimeError("StereoPipeline: nothing submitted")
+        slot = self.slots[self.returned % self.depth]
+        slot["done"].synchronize()
+        self.returned += 1
+        return slot["out"]

@@ -208,3 +208,23 @@ def test_cpu_inputs_fail_loudly():
     m = build("ESMStereo", True, False, "efficientnet_b2", 4)
     with pytest.raises(RuntimeError):
         m.cpu()(torch.zeros(1, 3, 64, 128), torch.zeros(1, 3, 64, 128), False)
+
+
+def test_host_pipeline_matches_direct_call():
+    """StereoPipeline (pinned host in/out, overlapped copies) returns the same disparities, in order."""
+    from esmstereo_b200 import GraphedStereo, StereoPipeline
+    name = "cv4_gwc"
+    m = build("ESMStereo", True, False, "efficientnet_b2", 4, golden_state_dict(name))
+    pairs = [synthetic_pair(1, 64, 128, shift=5 + i, seed=40 + i) for i in range(5)]
+    want = [m(l.cuda(), r.cuda(), False)[-1].cpu() for l, r in pairs]
+    g = GraphedStereo(m, (1, 3, 64, 128), train_status=False)
+    pipe = StereoPipeline(g, depth=2)
+    got = []
+    for i, (l, r) in enumerate(pairs):
+        pipe.submit(l.pin_memory(), r.pin_memory())
+        if i >= 1:
+            got.append(pipe.result().clone())
+    got.append(pipe.result().clone())
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
