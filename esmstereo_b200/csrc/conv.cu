@@ -120,7 +120,7 @@ static PackGeom pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transpo
 // host-side tiling + dispatch
 // ------------------------------------------------------------------------------------------
 struct Tiling {
-  int TWG, TH, TD, slots, IWP, ID, IH, IWR, IWL, nstages;
+  int TWG, TH, TD, slots, IWP, ID, IH, IWR, IWL, nstages, NV;
   size_t smem;
 };
 
@@ -157,24 +157,26 @@ struct Candidate {
 };
 
 // Enumerate tile shapes for one (channel split, chunk depth) and append them with their modelled cost.
-static void enumerate_tilings(int Jw, int Jh, int Jd, int cin, int COG, int KW, int KH, int KD, int S, int CK, int COP,
+static void enumerate_tilings(int Jw, int Jh, int Jd, int cin, int COG, int NV, int KW, int KH, int KD, int S, int CK, int COP,
                               int cosplit, bool gwc, int cpg, int xo, long long work_mult, int num_sms, double extra_cost,
                               std::vector<Candidate>* out) {
   const int ncog = COP / COG;
   for (int slots = 32; slots * ncog <= 256; slots += 32) {
-    for (int TWG = 1; TWG <= 16; TWG *= 2) {
+    for (int TWG = 1; TWG <= (NV == 1 ? 32 : 16); TWG *= 2) {
       if (slots % TWG) continue;
       const int R = slots / TWG;
       for (int TD = 1; TD <= R; ++TD) {
         if (R % TD) continue;
         const int TH = R / TD;
         if (Jd == 1 && TD != 1) continue;
-        const int TW = TWG * 4;
+        const int TW = TWG * NV;
+        if ((TW * S) % 4) continue;  // tile origins must stay on 16-byte columns (TMA box alignment)
         const int ID = (TD - 1) * S + KD, IH = (TH - 1) * S + KH;
-        const int XN = 3 * S + KW, XL = (XN + 3) / 4 * 4;
-        // row window of the last thread: aligned float4s (xo=0) or scalar@3 + float4s from column 4 (xo=3)
-        int IWP = (TWG - 1) * 4 * S + (xo == 3 ? 4 + 4 * ((XN + 2) / 4) : XL);
-        if (S == 1 && TWG < 8) {
+        const int XN = (NV - 1) * S + KW, XL = (XN + 3) / 4 * 4;
+        // row window of the last thread: aligned float4s (xo=0) or scalar@3 + float4s from column 4 (xo=3);
+        // NV=1: a scalar window of KW columns starting at column xo
+        int IWP = NV == 1 ? round_up((TWG - 1) * S + xo + KW, 4) : (TWG - 1) * 4 * S + (xo == 3 ? 4 + 4 * ((XN + 2) / 4) : XL);
+        if (NV == 4 && S == 1 && TWG < 8) {
           const int want = (4 * TWG) % 32;  // rows of an 8-lane LDS.128 phase land on distinct banks
           while (IWP % 32 != want) IWP += 4;
         }
@@ -195,7 +197,7 @@ static void enumerate_tilings(int Jw, int Jh, int Jd, int cin, int COG, int KW, 
         const int warps = nthreads / 32;
         const double smsp_load = (double)((ctas * warps + 3) / 4);
         const double hide = ctas * warps >= 12 ? 1.0 : 12.0 / (ctas * warps);
-        const double ffma2 = (double)KD * KH * KW * CK * 2 * COG;  // per warp per item: 4 voxels x COG/2 channel pairs per (tap, channel)
+        const double ffma2 = (double)KD * KH * KW * CK * NV * COG / 2;  // per warp per item: NV voxels x COG/2 channel pairs per (tap, channel)
         const double t_math = ffma2 * 2.0 * smsp_load * 1.3 * hide;
         const double t_tma = nstages > 2 ? 700.0 : 1500.0;  // exposed TMA round trip per item
         const double t_item = t_math > t_tma ? t_math : t_tma;
@@ -216,6 +218,7 @@ static void enumerate_tilings(int Jw, int Jh, int Jd, int cin, int COG, int KW, 
         c.tl.IWR = IWR;
         c.tl.IWL = IWL;
         c.tl.nstages = nstages;
+        c.tl.NV = NV;
         c.tl.smem = smem;
         c.CK = CK;
         c.COP = COP;
@@ -228,14 +231,14 @@ static void enumerate_tilings(int Jw, int Jh, int Jd, int cin, int COG, int KW, 
   }
 }
 
-static conv_fn_t pick_kernel(int KW, int S, int COG, int CK, bool gwc, bool tma, int xo) {
+static conv_fn_t pick_kernel(int KW, int S, int COG, int CK, bool gwc, bool tma, int xo, int nv) {
   if (S == 1) {
-    if (KW == 1) return conv_kernels_k1(COG, CK, gwc, tma, xo);
-    if (KW == 2) return conv_kernels_k2(COG, CK, gwc, tma, xo);
-    if (KW == 3) return conv_kernels_k3(COG, CK, gwc, tma, xo);
-    if (KW == 5) return conv_kernels_k5(COG, CK, gwc, tma, xo);
+    if (KW == 1) return conv_kernels_k1(COG, CK, gwc, tma, xo, nv);
+    if (KW == 2) return conv_kernels_k2(COG, CK, gwc, tma, xo, nv);
+    if (KW == 3) return conv_kernels_k3(COG, CK, gwc, tma, xo, nv);
+    if (KW == 5) return conv_kernels_k5(COG, CK, gwc, tma, xo, nv);
   } else if (S == 2 && KW == 3) {
-    return conv_kernels_k3s2(COG, CK, gwc, tma, xo);
+    return conv_kernels_k3s2(COG, CK, gwc, tma, xo, nv);
   }
   return nullptr;
 }
@@ -318,7 +321,7 @@ static int launch_plan(const esm_conv_t* d, const PackGeom& g, ConvK k, const Pl
   k.IWL = tl.IWL;
   k.pzw_sel = -1;
   k.nstages = tl.nstages;
-  k.tilesW = ceil_div(lg.Jw, tl.TWG * 4);
+  k.tilesW = ceil_div(lg.Jw, tl.TWG * tl.NV);
   k.tilesH = ceil_div(lg.Jh, tl.TH);
   k.tilesD = ceil_div(lg.Jd, tl.TD);
   k.phases = g.phases;
@@ -574,8 +577,12 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
       const double extra = 1.0 + 0.03 * (cosplit - 1);
       for (int ck = ck0; ck >= (ck0 == 8 && COG == 8 ? 4 : ck0); ck /= 2) {
         // chunk depth 8 or 4: a shallower chunk halves the staged brick (more resident warps on the 8-channel layers)
-        enumerate_tilings(lg.Jw, lg.Jh, lg.Jd, d->Cin, COG, g.KW, g.KH, g.KD, S, ck, COP, cosplit, gwc, k.cpg, xo_plan, mult,
+        enumerate_tilings(lg.Jw, lg.Jh, lg.Jd, d->Cin, COG, 4, g.KW, g.KH, g.KD, S, ck, COP, cosplit, gwc, k.cpg, xo_plan, mult,
                           num_sms, extra, &cands);
+        // one voxel per thread: only worth trying on small layers (and only instantiated for CK=8, k != 5)
+        if (ck == 8 && !gwc && g.KW != 5 && (long long)lg.Jw * lg.Jh * lg.Jd * d->B <= 80000)
+          enumerate_tilings(lg.Jw, lg.Jh, lg.Jd, d->Cin, COG, 1, g.KW, g.KH, g.KD, S, ck, COP, cosplit, gwc, k.cpg, xo_plan, mult,
+                            num_sms, extra, &cands);
         if (ck == 1) break;
       }
     }
@@ -591,9 +598,9 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
     np->cosplit = c.cosplit;
     const int COG = c.COG;
     np->COG = COG;
-    np->fn = pick_kernel(g.KW, S, COG, c.CK, gwc, false, 0);
-    np->fn_tma[0] = pick_kernel(g.KW, S, COG, c.CK, gwc, true, 0);
-    np->fn_tma[1] = pick_kernel(g.KW, S, COG, c.CK, gwc, true, 3);
+    np->fn = pick_kernel(g.KW, S, COG, c.CK, gwc, false, 0, c.tl.NV);
+    np->fn_tma[0] = pick_kernel(g.KW, S, COG, c.CK, gwc, true, 0, c.tl.NV);
+    np->fn_tma[1] = pick_kernel(g.KW, S, COG, c.CK, gwc, true, 3, c.tl.NV);
     ESM_REQUIRE(np->fn, "conv: unsupported kernel width %d / stride %d%s", g.KW, S, gwc ? " with ESM_SRC_GWC" : "");
     np->blocks_per_sm = 1;
     if (num_sms > 0) {
@@ -626,18 +633,25 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   const char* env = getenv("ESM_AUTOTUNE");
   const bool tune = cap == cudaStreamCaptureStatusNone && !(env && env[0] == '0');
   if (tune && cands.size() > 1) {
-    // shortlist: the 6 best by model + the best of every distinct CTA size (diversity)
-    std::vector<Candidate> shortlist(cands.begin(), cands.begin() + std::min<size_t>(8, cands.size()));
-    for (int nt = 32; nt <= 256; nt += 32)
-      for (const Candidate& c : cands)
-        if (c.tl.slots * (c.COP / c.COG) == nt) {
-          bool dup = false;
-          for (const Candidate& s2 : shortlist)
-            if (s2.tl.slots == c.tl.slots && s2.tl.TWG == c.tl.TWG && s2.tl.TD == c.tl.TD && s2.CK == c.CK && s2.COP == c.COP &&
-                s2.tl.nstages == c.tl.nstages && s2.COG == c.COG)
-              dup = true;
-          if (!dup) shortlist.push_back(c);
-          break;
+    // shortlist: the 6 best by model + the best of every (voxels/thread, channel-group width, CTA size
+    // class) combination, so that structurally different plans always get a device timing
+    std::vector<Candidate> shortlist(cands.begin(), cands.begin() + std::min<size_t>(6, cands.size()));
+    auto same = [](const Candidate& a, const Candidate& b) {
+      return a.tl.slots == b.tl.slots && a.tl.TWG == b.tl.TWG && a.tl.TD == b.tl.TD && a.CK == b.CK && a.COP == b.COP &&
+             a.tl.nstages == b.tl.nstages && a.COG == b.COG && a.tl.NV == b.tl.NV;
+    };
+    for (int nv = 1; nv <= 4; nv += 3)
+      for (int cog = 4; cog <= 8; cog += 4)
+        for (int cls = 0; cls < 3; ++cls) {
+          const int lo = cls == 0 ? 0 : cls == 1 ? 64 : 128, hi = cls == 0 ? 64 : cls == 1 ? 128 : 256;
+          for (const Candidate& c : cands) {
+            const int nt = c.tl.slots * (c.COP / c.COG);
+            if (c.tl.NV != nv || c.COG != cog || nt <= lo || nt > hi) continue;
+            bool dup = false;
+            for (const Candidate& s2 : shortlist) dup = dup || same(s2, c);
+            if (!dup) shortlist.push_back(c);
+            break;
+          }
         }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
@@ -647,21 +661,24 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
       Plan cp;
       if (make_plan(c, &cp) != ESM_OK) continue;
       if (launch_plan(d, g, k, cp, lg, num_sms, st) != ESM_OK) continue;  // warm (also sets attributes)
-      cudaEventRecord(e0, st);
-      launch_plan(d, g, k, cp, lg, num_sms, st);
-      launch_plan(d, g, k, cp, lg, num_sms, st);
-      cudaEventRecord(e1, st);
-      if (cudaEventSynchronize(e1) != cudaSuccess) {
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-        return check_launch("conv(autotune)");
+      float ms = 1e30f;
+      for (int rep = 0; rep < 2; ++rep) {  // best of two timings of 3 back-to-back launches
+        cudaEventRecord(e0, st);
+        for (int l = 0; l < 3; ++l) launch_plan(d, g, k, cp, lg, num_sms, st);
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) {
+          cudaEventDestroy(e0);
+          cudaEventDestroy(e1);
+          return check_launch("conv(autotune)");
+        }
+        float m3 = 0.f;
+        cudaEventElapsedTime(&m3, e0, e1);
+        if (m3 / 3.f < ms) ms = m3 / 3.f;
       }
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, e0, e1);
       if (getenv("ESM_DEBUG_PLAN"))
-        fprintf(stderr, "[esm tune] Cin=%d Cout=%d k=%d J=(%d,%d,%d): CK=%d COP=%d tile=(%d,%d,%d) thr=%d ns=%d smem=%zuKB -> %.1f us\n",
-                d->Cin, d->Cout, d->kw, lg.Jd, lg.Jh, lg.Jw, c.CK, c.COP, c.tl.TD, c.tl.TH, c.tl.TWG * 4, c.tl.slots * (c.COP / c.COG),
-                c.tl.nstages, c.tl.smem / 1024, ms * 500.f);
+        fprintf(stderr, "[esm tune] Cin=%d Cout=%d k=%d J=(%d,%d,%d): CK=%d COP=%d COG=%d NV=%d tile=(%d,%d,%d) thr=%d ns=%d smem=%zuKB -> %.1f us\n",
+                d->Cin, d->Cout, d->kw, lg.Jd, lg.Jh, lg.Jw, c.CK, c.COP, c.COG, c.tl.NV, c.tl.TD, c.tl.TH, c.tl.TWG * c.tl.NV, c.tl.slots * (c.COP / c.COG),
+                c.tl.nstages, c.tl.smem / 1024, ms * 1000.f);
       if (ms < best_ms) {
         best_ms = ms;
         best_plan = cp;
@@ -674,7 +691,7 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
     fprintf(stderr, "[esm plan] Cin=%d Cout=%d k=(%d,%d,%d) s=%d%s%s J=(%d,%d,%d): CK=%d COP=%d cosplit=%d tile=(%d,%d,%d) threads=%d "
             "smem=%zu KB occ=%d tuned=%d\n",
             d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed ? " T" : "", gwc ? " gwc" : "", lg.Jd, lg.Jh, lg.Jw,
-            best_plan.CK, best_plan.COP, best_plan.cosplit, best_plan.tl.TD, best_plan.tl.TH, best_plan.tl.TWG * 4,
+            best_plan.CK, best_plan.COP, best_plan.cosplit, best_plan.tl.TD, best_plan.tl.TH, best_plan.tl.TWG * best_plan.tl.NV,
             best_plan.tl.slots * (best_plan.COP / best_plan.COG), best_plan.tl.smem / 1024, best_plan.blocks_per_sm, (int)tune);
   plans.emplace(key, best_plan);
   return launch_plan(d, g, k, best_plan, lg, num_sms, st);

@@ -147,12 +147,14 @@ __device__ __forceinline__ TileCtx decode_work(const ConvK& p, int w) {
 // XO: column of the first needed input inside a thread's row window.  TMA boxes must start on a
 // 16-byte boundary in W, so for pad-1 kernels the brick origin is 3 columns left of the first tap
 // (XO=3: one scalar LDS + aligned LDS.128s); XO=0 otherwise.
-template <int KW, int S, int COG, int CK, bool GWC, bool TMA, int XO>
+// NV: output voxels per thread along W.  4 for the throughput-bound layers (vector LDS, weights
+// amortised over 4 voxels); 1 for the small, latency-bound ones (4x the threads, 1/4 of the serial
+// FFMA2 chain per thread).
+template <int KW, int S, int COG, int CK, bool GWC, bool TMA, int XO, int NV = 4>
 __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ ConvK p, const __grid_constant__ ConvMaps maps) {
   // TMA destinations must be 128-byte aligned.  Declared aligned (not realigned by pointer
   // arithmetic) so that every derived pointer stays in the .shared state space: LDS, not generic LD.
   extern __shared__ __align__(1024) float smem[];
-  constexpr int NV = 4;
   constexpr int XN = (NV - 1) * S + KW;
   constexpr int XL = (XN + 3) / 4 * 4;
   constexpr int NP = 4;  // fill positions per thread per pass over a plane
@@ -524,7 +526,10 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
 #pragma unroll
           for (int c = 0; c < CK; ++c) {
             float x[XL];
-            if (XO == 0) {
+            if (NV == 1) {  // scalar window
+#pragma unroll
+              for (int q = 0; q < XN; ++q) x[q] = xr[c * chan_stride + XO + q];
+            } else if (XO == 0) {
 #pragma unroll
               for (int q = 0; q < XL / 4; ++q) {
                 const float4 t4 = *reinterpret_cast<const float4*>(xr + c * chan_stride + q * 4);
@@ -589,6 +594,65 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
       if (od < p.OD && oh < p.OH) {
         const int act = p.act, act2 = p.act2;
         const bool post = p.out_mul || p.residual || act2 != ESM_ACT_NONE || p.out_scale != 1.0f;
+        if (NV == 1) {
+          // one voxel x COG channels per thread: the activation call takes 4 channels at a time
+          const int ow = jw0 * osw + t.pz_w;
+          if (ow < p.OW) {
+#pragma unroll
+            for (int j4 = 0; j4 < COG; j4 += 4) {
+              const int co0 = t.co_base + cog * COG + j4;
+              float rv[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int co = co0 + q;
+                const float a = (q & 1) ? acc[0][(j4 + q) / 2].y : acc[0][(j4 + q) / 2].x;
+                const float sc = (p.scale && co < p.Cout) ? __ldg(p.scale + co) : 1.f;
+                const float sh = (p.shift && co < p.Cout) ? __ldg(p.shift + co) : 0.f;
+                rv[q] = fmaf(a, sc, sh);
+              }
+              float4 r = make_float4(rv[0], rv[1], rv[2], rv[3]);
+              if (act != ESM_ACT_NONE) r = apply_act4(r, act);
+              rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
+              if (p.ps == 0) {
+                if (post) {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const int co = co0 + q;
+                    if (co < p.Cout) {
+                      if (p.out_mul) rv[q] *= __ldg(p.out_mul + (long long)b * p.omB + (long long)co * p.omC + (long long)oh * p.omH + ow);
+                      if (p.residual)
+                        rv[q] += __ldg(p.residual + (long long)b * p.oB + (long long)co * p.oC + (long long)od * p.oD + (long long)oh * p.oH + ow);
+                    }
+                  }
+                  if (act2 != ESM_ACT_NONE) {
+                    r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), act2);
+                    rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
+                  }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int co = co0 + q;
+                  if (co < p.Cout)
+                    p.out[(long long)b * p.oB + (long long)co * p.oC + (long long)od * p.oD + (long long)oh * p.oH + ow] = rv[q] * p.out_scale;
+                }
+              } else {
+                if (act2 != ESM_ACT_NONE) {
+                  r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), act2);
+                  rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
+                }
+                const int rr = p.ps;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int co = co0 + q;
+                  if (co < p.Cout) {
+                    const int c = co / (rr * rr), a = (co / rr) % rr, bb = co % rr;
+                    p.out[(long long)b * p.oB + (long long)c * p.oC + (long long)(oh * rr + a) * p.oH + ow * rr + bb] = rv[q] * p.out_scale;
+                  }
+                }
+              }
+            }
+          }
+        } else {
 #pragma unroll
         for (int j = 0; j < COG; ++j) {
           const int co = t.co_base + cog * COG + j;
@@ -596,10 +660,11 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
             const float sc = p.scale ? __ldg(p.scale + co) : 1.f;
             const float sh = p.shift ? __ldg(p.shift + co) : 0.f;
             float4 r;
+            constexpr int V1 = NV > 1 ? 1 : 0, V2 = NV > 2 ? 2 : 0, V3 = NV > 3 ? 3 : 0;  // (NV == 1 never gets here)
             r.x = fmaf((j & 1) ? acc[0][j / 2].y : acc[0][j / 2].x, sc, sh);
-            r.y = fmaf((j & 1) ? acc[1][j / 2].y : acc[1][j / 2].x, sc, sh);
-            r.z = fmaf((j & 1) ? acc[2][j / 2].y : acc[2][j / 2].x, sc, sh);
-            r.w = fmaf((j & 1) ? acc[3][j / 2].y : acc[3][j / 2].x, sc, sh);
+            r.y = fmaf((j & 1) ? acc[V1][j / 2].y : acc[V1][j / 2].x, sc, sh);
+            r.z = fmaf((j & 1) ? acc[V2][j / 2].y : acc[V2][j / 2].x, sc, sh);
+            r.w = fmaf((j & 1) ? acc[V3][j / 2].y : acc[V3][j / 2].x, sc, sh);
             if (act != ESM_ACT_NONE) r = apply_act4(r, act);
             if (p.ps == 0) {
               const long long obase = (long long)b * p.oB + (long long)co * p.oC + (long long)od * p.oD + (long long)oh * p.oH;
@@ -649,6 +714,7 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
             }
           }
         }
+        }
       }
 #pragma unroll
       for (int v = 0; v < NV; ++v)
@@ -666,7 +732,11 @@ typedef void (*conv_fn_t)(const ConvK, const ConvMaps);
 
 // One translation unit per (KW, S) keeps the build parallel; each exports its instantiations.
 template <int KW, int S, bool TMA, int XO>
-static conv_fn_t pick_cog_ck(int COG, int CK) {
+static conv_fn_t pick_cog_ck(int COG, int CK, int nv) {
+  if (nv == 1) {  // small-layer variant: instantiated for 8-channel chunks only
+    if (CK != 8) return nullptr;
+    return COG == 8 ? (conv_fn_t)conv_kernel<KW, S, 8, 8, false, TMA, XO, 1> : (conv_fn_t)conv_kernel<KW, S, 4, 8, false, TMA, XO, 1>;
+  }
   if (COG == 8 && CK == 8) return conv_kernel<KW, S, 8, 8, false, TMA, XO>;
   if (COG == 8 && CK == 4) return conv_kernel<KW, S, 8, 4, false, TMA, XO>;
   if (COG == 8 && CK == 1) return conv_kernel<KW, S, 8, 1, false, TMA, XO>;
@@ -682,10 +752,10 @@ static conv_fn_t pick_gwc(int COG, int CK) {
 }
 
 // xo: 0 or 3 (only meaningful with tma)
-conv_fn_t conv_kernels_k1(int COG, int CK, bool gwc, bool tma, int xo);
-conv_fn_t conv_kernels_k2(int COG, int CK, bool gwc, bool tma, int xo);
-conv_fn_t conv_kernels_k3(int COG, int CK, bool gwc, bool tma, int xo);
-conv_fn_t conv_kernels_k3s2(int COG, int CK, bool gwc, bool tma, int xo);
-conv_fn_t conv_kernels_k5(int COG, int CK, bool gwc, bool tma, int xo);
+conv_fn_t conv_kernels_k1(int COG, int CK, bool gwc, bool tma, int xo, int nv);
+conv_fn_t conv_kernels_k2(int COG, int CK, bool gwc, bool tma, int xo, int nv);
+conv_fn_t conv_kernels_k3(int COG, int CK, bool gwc, bool tma, int xo, int nv);
+conv_fn_t conv_kernels_k3s2(int COG, int CK, bool gwc, bool tma, int xo, int nv);
+conv_fn_t conv_kernels_k5(int COG, int CK, bool gwc, bool tma, int xo, int nv);
 
 }  // namespace esm
