@@ -17,6 +17,7 @@
 // pairs for FFMA2); a CTA owns a TD x TH x 4*TWG brick of voxels and ALL output channels, stages
 // CK input channels of the brick + halo in shared memory together with the matching weights.
 #include "conv_kernel.cuh"
+#include "conv_tc.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -293,6 +294,8 @@ struct Plan {
   conv_fn_t fn;         // cp.async pipeline (any strides)
   conv_fn_t fn_tma[2];  // TMA pipeline for window offset XO = 0 / 3 (nullptr if not instantiated)
   int cosplit, COP, COG, CK, blocks_per_sm;
+  bool use_tc;  // run on the tcgen05 path (conv_tc.cu) instead
+  TcPlan tc;
 };
 
 struct LayerGeom {
@@ -543,8 +546,13 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   static std::map<PlanKey, Plan> plans;
   static std::mutex plans_mu;
   static int num_sms = 0;
+  // tensor-core policy: ESM_TC=0 off, 3 (default) split-TF32 (fp32-grade), 1 single-pass TF32 (fast mode);
+  // ESM_TC_FORCE=1 takes the tensor-core path whenever the layer is eligible (tests), else it must win the timing
+  const char* tc_env = getenv("ESM_TC");
+  const int tc_pass = tc_env ? atoi(tc_env) : 3;
+  const bool tc_force = getenv("ESM_TC_FORCE") != nullptr && tc_pass != 0;
   PlanKey key = {{d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed, lg.Jw, lg.Jh, lg.Jd, gwc ? k.cpg : 0, d->B, d->pd,
-                  d->ph, d->pw, 0}};
+                  d->ph, d->pw, tc_pass * 2 + (tc_force ? 1 : 0) + (d->in_mul ? 64 : 0) + (d->pixel_shuffle ? 128 : 0)}};
   std::lock_guard<std::mutex> lock(plans_mu);
   if (num_sms == 0) {
     int dev = 0;
@@ -558,7 +566,8 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
     }
   }
   auto it = plans.find(key);
-  if (it != plans.end()) return launch_plan(d, g, k, it->second, lg, num_sms, st);
+  if (it != plans.end())
+    return it->second.use_tc ? tc_conv_launch(d, it->second.tc, st) : launch_plan(d, g, k, it->second, lg, num_sms, st);
 
   // ---- plan: enumerate (channel split x chunk depth x tile shape), rank by the analytic model ----
   const int ck0 = g.CinPad == 1 ? 1 : 8;
@@ -620,6 +629,7 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   };
 
   Plan best_plan;
+  best_plan.use_tc = false;
   if (int e = make_plan(cands[0], &best_plan)) return e;
   if (num_sms <= 0) {
     set_error("conv: no CUDA device");
@@ -632,6 +642,7 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   cudaStreamIsCapturing(st, &cap);
   const char* env = getenv("ESM_AUTOTUNE");
   const bool tune = cap == cudaStreamCaptureStatusNone && !(env && env[0] == '0');
+  float best_ms = 1e30f;
   if (tune && cands.size() > 1) {
     // shortlist: the 6 best by model + the best of every (voxels/thread, channel-group width, CTA size
     // class) combination, so that structurally different plans always get a device timing
@@ -656,9 +667,9 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    float best_ms = 1e30f;
     for (const Candidate& c : shortlist) {
       Plan cp;
+      cp.use_tc = false;
       if (make_plan(c, &cp) != ESM_OK) continue;
       if (launch_plan(d, g, k, cp, lg, num_sms, st) != ESM_OK) continue;  // warm (also sets attributes)
       float ms = 1e30f;
@@ -687,6 +698,48 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
   }
+  // ---- tensor-core candidate (conv_tc.cu): taken when forced, or when it beats the best FP32-pipe plan ----
+  TcPlan tcp;
+  if (tc_pass != 0 && tc_conv_plan(d, num_sms, tc_pass == 1 ? 1 : 3, &tcp)) {
+    bool take = tc_force;
+    if (!take && tune) {
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      auto time3 = [&](bool tc) -> float {
+        float ms = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {  // rep 0 warms
+          cudaEventRecord(e0, st);
+          for (int l = 0; l < 3; ++l) {
+            if (tc)
+              tc_conv_launch(d, tcp, st);
+            else
+              launch_plan(d, g, k, best_plan, lg, num_sms, st);
+          }
+          cudaEventRecord(e1, st);
+          if (cudaEventSynchronize(e1) != cudaSuccess) return -1.f;
+          float m3 = 0.f;
+          cudaEventElapsedTime(&m3, e0, e1);
+          if (rep > 0 && m3 / 3.f < ms) ms = m3 / 3.f;
+        }
+        return ms;
+      };
+      if (best_ms >= 1e29f) best_ms = time3(false);
+      const float tc_ms = time3(true);
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      if (best_ms < 0.f || tc_ms < 0.f) return check_launch("conv(autotune tc)");
+      take = tc_ms < best_ms;
+      if (getenv("ESM_DEBUG_PLAN"))
+        fprintf(stderr, "[esm tune] Cin=%d Cout=%d k=(%d,%d,%d) J=(%d,%d,%d)%s: tcgen05 COT=%d TZ=%d ysplit=%d ctas=%d ns=%d pass=%d -> %.1f us vs fp32 %.1f us\n",
+                d->Cin, d->Cout, d->kd, d->kh, d->kw, lg.Jd, lg.Jh, lg.Jw, gwc ? " gwc" : "", tcp.COT, tcp.TZ, tcp.ysplit,
+                tcp.ncot * tcp.ctas_per_cot, tcp.nstages, tcp.npass, tc_ms * 1000.f, best_ms * 1000.f);
+    }
+    if (take) {
+      best_plan.use_tc = true;
+      best_plan.tc = tcp;
+    }
+  }
   if (getenv("ESM_DEBUG_PLAN"))
     fprintf(stderr, "[esm plan] Cin=%d Cout=%d k=(%d,%d,%d) s=%d%s%s J=(%d,%d,%d): CK=%d COP=%d cosplit=%d tile=(%d,%d,%d) threads=%d "
             "smem=%zu KB occ=%d tuned=%d\n",
@@ -694,5 +747,5 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
             best_plan.CK, best_plan.COP, best_plan.cosplit, best_plan.tl.TD, best_plan.tl.TH, best_plan.tl.TWG * best_plan.tl.NV,
             best_plan.tl.slots * (best_plan.COP / best_plan.COG), best_plan.tl.smem / 1024, best_plan.blocks_per_sm, (int)tune);
   plans.emplace(key, best_plan);
-  return launch_plan(d, g, k, best_plan, lg, num_sms, st);
+  return best_plan.use_tc ? tc_conv_launch(d, best_plan.tc, st) : launch_plan(d, g, k, best_plan, lg, num_sms, st);
 }

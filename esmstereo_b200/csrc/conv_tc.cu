@@ -1,0 +1,585 @@
+// Tensor-core path of the convolution family: k3 s1 p1 convolutions (2D and 3D) as implicit GEMMs on
+// tcgen05.mma (kind::tf32, accumulators in TMEM), with fp32-grade accuracy from a split-TF32 scheme.
+// Replaces BasicConv (submodule.py:12-38) for group_stem / agg / the k3 layers of `aggregation`
+// (ESMStereo.py:129-182, 620-622) and the k3 s1 2D convs; with GWC also build_gwc_volume
+// (submodule.py:151-161) fused in front of group_stem.
+//
+// Shape problem and the answer to it.  Every GEMM here has a tiny Cout (8..24 per CTA) and the voxel
+// dimension must be M, so an SS-mode MMA is bound by the shared-memory read of the A operand: measured
+// 46 clk per M128 x K8 dispatch whatever N <= 64 is (scratch/umma_test.cu).  Re-reading the im2col rows
+// once per tap at N = Cout would make the tensor pipe slower than the FP32 pipe.  So the taps go into N
+// instead of K:
+//     acc[z_o][y_in][x_in, (kh,kw,co)] = sum_{kd,ci} X[z_o+kd-1, y_in, x_in, ci] * W[kd,kh,kw,ci,co]
+// i.e. one M128 x N(9*COT) x K8 MMA per (input row, kd, 8-channel group) -- N = 72..216, at or near the
+// MMA's own rate -- and the 9-way (kh,kw) gather that remains,
+//     out[z_o, y, x, co] = sum_{kh,kw} acc[z_o][y+kh-1][x+kw-1, (kh,kw,co)],
+// is done by the epilogue warps on CUDA cores: kw by two warp shuffles, kh by a rolling 3-row register
+// window while the CTA marches down y.  A CTA tile is 4 "strips" (one per epilogue warp = TMEM lane
+// quadrant): 32 consecutive input columns (30 outputs + halo) of one image row each.
+//
+// Accuracy.  kind::tf32 truncates the operands to 10 mantissa bits (measured).  Operands are split
+// x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi) and three MMAs accumulate hi*hi + lo*hi +
+// hi*lo in fp32 (relative error ~2^-22 per product, measured 5e-7 worst case against fp64 on K=8 dot
+// products).  npass = 1 keeps only hi*hi (single-pass TF32 fast mode).
+//
+// Warp roles (416 threads, 1 CTA/SM, persistent): warps 0-3 epilogue (TMEM -> registers -> global),
+// warp 4 MMA issuer (one thread), warps 5-12 operand producers: they load fp32 activations (or build
+// the correlation from left/right feature rows), split them and write the K-major, non-swizzled UMMA
+// operand tiles.  Three mbarrier pipelines: operand ring full/empty, accumulator full/empty.
+#include "conv_tc.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
+namespace esm {
+
+struct TcK {
+  esm_src_t src[3];
+  int nsrc, cpg;
+  int B, Cin, ncg, D, H, W;
+  int Cout, CinPad, CoutPad;
+  const float* weight;  // fp32 pack of esm_pack_conv_weight_f32: [tap][CinPad][CoutPad]
+  const float* scale;
+  const float* shift;
+  int act, act2;
+  const float* out_mul;
+  long long omB, omC, omH;
+  const float* residual;
+  float out_scale;
+  float* out;
+  long long oB, oC, oD, oH;
+  int nseg, segw, rows, nstrips, groups, ztiles;
+  int items_per_cot, ctas_per_cot, nstages, npass;
+};
+
+constexpr int TC_NTW = 8;                        // operand-producer warps
+constexpr int TC_THREADS = 32 * (5 + TC_NTW);    // 4 epilogue + 1 MMA + producers
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = tc_smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+// K-major, no-swizzle UMMA shared-memory descriptor: 8-row x 16-byte core matrices, rows 16 bytes
+// apart; LBO = byte distance between the two K halves, SBO = distance between 8-row groups.
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+// Three 8-column loads of this warp's TMEM lane quadrant plus the wait, in ONE asm statement so that no
+// use of the results can be scheduled ahead of tcgen05.wait::ld.
+__device__ __forceinline__ void tc_ld8x3(uint32_t ta, uint32_t tb, uint32_t tc, float (&a)[8], float (&b)[8], float (&c)[8]) {
+  uint32_t u[24];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%24];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%25];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%26];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+        "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+        "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23])
+      : "r"(ta), "r"(tb), "r"(tc)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = __uint_as_float(u[i]);
+    b[i] = __uint_as_float(u[8 + i]);
+    c[i] = __uint_as_float(u[16 + i]);
+  }
+}
+__device__ __forceinline__ float tc_rna(float x) {  // round to nearest TF32 (low 13 mantissa bits zero)
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+struct TcItem {
+  int b, z0, grp;
+};
+__device__ __forceinline__ TcItem tc_decode(const TcK& p, int item, int TZ) {
+  TcItem t;
+  t.grp = item % p.groups;
+  const int r = item / p.groups;
+  t.z0 = (r % p.ztiles) * TZ;
+  t.b = r / p.ztiles;
+  return t;
+}
+
+template <int COT, int TZ, int KD, bool GWC>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcK p) {
+  constexpr int NB = 9 * COT;                  // accumulator columns per (z_o, y_in) row tile
+  constexpr int NROW = TZ + KD - 1;            // input planes per stage
+  constexpr int CGS = (NROW == 1) ? 4 : 1;     // 8-channel groups per stage
+  constexpr int TPW = CGS * NROW;              // row tiles per stage = tasks per producer warp
+  constexpr int ROW_BYTES = 8192;              // row tile: hi [2][128][4] floats, then lo [2][128][4]
+  constexpr int STAGE_BYTES = TPW * ROW_BYTES;
+  constexpr int WSLAB = NB * 32;               // one (cg, kd, hi|lo) B operand: [2][NB][4] floats
+  constexpr int ACC_COLS = 256;                // TMEM columns per accumulator buffer (TZ*NB <= 256)
+  static_assert(TZ * NB <= ACC_COLS, "accumulator does not fit");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ncg = p.ncg;
+  const int NS = p.nstages;
+  const uint32_t wbytes = (uint32_t)ncg * KD * 2 * WSLAB;
+  uint8_t* s_w = smem;
+  uint8_t* s_stage = smem + ((wbytes + 127u) & ~127u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_stage + (size_t)NS * STAGE_BYTES);
+  uint64_t* empty = full + NS;
+  uint64_t* accf = empty + NS;
+  uint64_t* acce = accf + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + 2);
+  const int cot = blockIdx.x / p.ctas_per_cot;
+  const int cta = blockIdx.x % p.ctas_per_cot;
+  const int nsteps = p.rows + 2;
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) {
+      tc_mbar_init(&full[i], TC_NTW);
+      tc_mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc_mbar_init(&accf[i], 1);
+      tc_mbar_init(&acce[i], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // resident weights of this channel tile: split and laid out as UMMA B operands
+  // (row n = (kh*3+kw)*COT + co, K = 8 input channels of group cg)
+  for (int idx = tid; idx < ncg * KD * NB * 8; idx += TC_THREADS) {
+    const int col = idx % COT;
+    int t = idx / COT;
+    const int k = t & 7;
+    t >>= 3;
+    const int tap2 = t % 9;
+    t /= 9;
+    const int kd = t % KD;
+    const int cg = t / KD;
+    const int co = cot * COT + col, ci = cg * 8 + k;
+    float w = 0.f;
+    if (co < p.CoutPad && ci < p.CinPad) w = __ldg(p.weight + ((long long)(kd * 9 + tap2) * p.CinPad + ci) * p.CoutPad + co);
+    const float hi = tc_rna(w);
+    const float lo = tc_rna(w - hi);
+    const uint32_t off = (uint32_t)((cg * KD + kd) * 2) * WSLAB + (uint32_t)(k >> 2) * (NB * 16) + (uint32_t)(tap2 * COT + col) * 16 + (k & 3) * 4;
+    *reinterpret_cast<float*>(s_w + off) = hi;
+    *reinterpret_cast<float*>(s_w + off + WSLAB) = lo;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= 5) {
+    // ============================ operand producers ============================
+    const int tw = warp - 5;
+    const int q = (tw >> 1) & 3;   // strip (= TMEM lane quadrant) this warp feeds
+    const int khalf = tw & 1;      // which 4 of the 8 channels of a group
+    const int m = q * 32 + lane;   // A row
+    uint32_t it = 0;
+    // iteration state: (item, step, cgb)
+    int item = cta, step = 0, cgb = 0;
+    auto load_at = [&](int item_, int step_, int cgb_, float (&v)[TPW][4]) {
+      const TcItem ti = tc_decode(p, item_, TZ);
+      const int strip = ti.grp * 4 + q;
+      const int seg = strip % p.nseg, ys = strip / p.nseg;
+      const int x = seg * p.segw + lane - 1;
+      const int y = ys * p.rows - 1 + step_;
+      const bool ok = strip < p.nstrips && y >= 0 && y < p.H && x >= 0 && x < p.W && lane <= p.segw + 1;
+      if (GWC) {
+        // v = 0.5 * (L[2g]*R[2g](x-d) + L[2g+1]*R[2g+1](x-d)), un-contracted (submodule.py:147); cpg == 2
+        const int g0 = cgb_ * 8 + khalf * 4;
+        const float* lp = p.src[0].ptr + (long long)ti.b * p.src[0].sB + (long long)(g0 * 2) * p.src[0].sC + (long long)y * p.src[0].sH + x;
+        const float* rp = p.src[1].ptr + (long long)ti.b * p.src[1].sB + (long long)(g0 * 2) * p.src[1].sC + (long long)y * p.src[1].sH + x;
+        float l[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) l[c] = (ok && g0 + c / 2 < p.Cin) ? __ldg(lp + (long long)c * p.src[0].sC) : 0.f;
+#pragma unroll
+        for (int r = 0; r < NROW; ++r) {
+          const int d = ti.z0 + r - KD / 2;
+          const bool okd = ok && d >= 0 && d < p.D && x >= d;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float val = 0.f;
+            if (okd && g0 + g < p.Cin) {
+              const float r0 = __ldg(rp + (long long)(2 * g) * p.src[1].sC - d);
+              const float r1 = __ldg(rp + (long long)(2 * g + 1) * p.src[1].sC - d);
+              val = __fmul_rn(__fadd_rn(__fmul_rn(l[2 * g], r0), __fmul_rn(l[2 * g + 1], r1)), 0.5f);
+            }
+            v[r][g] = val;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < TPW; ++j) {
+          const int cgl = j / NROW, r = j % NROW;
+          const int cg = cgb_ + cgl;
+          const int z = ti.z0 + r - KD / 2;
+          int rel = cg * 8 + khalf * 4, k = 0;
+          while (k < p.nsrc - 1 && rel >= p.src[k].C) {  // host guarantees 8-channel groups never straddle sources
+            rel -= p.src[k].C;
+            ++k;
+          }
+          const esm_src_t& s = p.src[k];
+          const float* bp = s.ptr + (long long)ti.b * s.sB + (long long)rel * s.sC + (long long)z * s.sD + (long long)y * s.sH + x;
+          const bool okz = ok && cg < ncg && z >= 0 && z < p.D;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[j][c] = (okz && rel + c < s.C) ? __ldg(bp + (long long)c * s.sC) : 0.f;
+        }
+      }
+    };
+    auto advance = [&](int& item_, int& step_, int& cgb_) {
+      cgb_ += CGS;
+      if (cgb_ >= ncg) {
+        cgb_ = 0;
+        if (++step_ >= nsteps) {
+          step_ = 0;
+          item_ += p.ctas_per_cot;
+        }
+      }
+    };
+    float va[TPW][4], vb[TPW][4];
+    if (item < p.items_per_cot) load_at(item, step, cgb, va);
+    while (item < p.items_per_cot) {
+      int ni = item, nst = step, ncb = cgb;
+      advance(ni, nst, ncb);
+      if (ni < p.items_per_cot) load_at(ni, nst, ncb, vb);  // next stage's loads are in flight during this stage's stores
+      const uint32_t st = it % NS, ph = (it / NS) & 1;
+      tc_mbar_wait(&empty[st], ph ^ 1);
+      uint8_t* sb = s_stage + (size_t)st * STAGE_BYTES + khalf * 2048 + m * 16;
+#pragma unroll
+      for (int j = 0; j < TPW; ++j) {
+        float4 hi, lo;
+        hi.x = tc_rna(va[j][0]);
+        hi.y = tc_rna(va[j][1]);
+        hi.z = tc_rna(va[j][2]);
+        hi.w = tc_rna(va[j][3]);
+        *reinterpret_cast<float4*>(sb + j * ROW_BYTES) = hi;
+        if (p.npass == 3) {
+          lo.x = tc_rna(va[j][0] - hi.x);
+          lo.y = tc_rna(va[j][1] - hi.y);
+          lo.z = tc_rna(va[j][2] - hi.z);
+          lo.w = tc_rna(va[j][3] - hi.w);
+          *reinterpret_cast<float4*>(sb + j * ROW_BYTES + 4096) = lo;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(&full[st]);
+      ++it;
+#pragma unroll
+      for (int j = 0; j < TPW; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) va[j][c] = vb[j][c];
+      item = ni;
+      step = nst;
+      cgb = ncb;
+    }
+  } else if (warp == 4) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      // D = f32, A = B = tf32, both K-major, N = NB, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t w_addr = tc_smem_u32(s_w), s_addr = tc_smem_u32(s_stage);
+      uint32_t it = 0, ai = 0;
+      for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
+        for (int step = 0; step < nsteps; ++step) {
+          const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
+          tc_mbar_wait(&acce[ab], aph ^ 1);  // epilogue has drained this accumulator buffer
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int cgb = 0; cgb < ncg; cgb += CGS) {
+            const uint32_t st = it % NS, ph = (it / NS) & 1;
+            tc_mbar_wait(&full[st], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int cgl = 0; cgl < CGS; ++cgl) {
+              const int cg = cgb + cgl;
+              if (cg < ncg) {
+#pragma unroll
+                for (int zo = 0; zo < TZ; ++zo) {
+#pragma unroll
+                  for (int kd = 0; kd < KD; ++kd) {
+                    const uint32_t a = s_addr + st * STAGE_BYTES + (cgl * NROW + zo + kd) * ROW_BYTES;
+                    const uint32_t b = w_addr + (uint32_t)((cg * KD + kd) * 2) * WSLAB;
+                    const uint64_t a_hi = tc_desc(a, 2048, 128), b_hi = tc_desc(b, NB * 16, 128);
+                    const uint32_t d = tmem + ab * ACC_COLS + zo * NB;
+                    tc_mma(d, a_hi, b_hi, idesc, (cg > 0 || kd > 0) ? 1u : 0u);
+                    if (p.npass == 3) {
+                      tc_mma(d, tc_desc(a + 4096, 2048, 128), b_hi, idesc, 1u);
+                      tc_mma(d, a_hi, tc_desc(b + WSLAB, NB * 16, 128), idesc, 1u);
+                    }
+                  }
+                }
+              }
+            }
+            tc_commit(&empty[st]);  // frees the operand stage once these MMAs have read it
+            ++it;
+          }
+          tc_commit(&accf[ab]);  // accumulator rows of this y step are complete
+          ++ai;
+        }
+      }
+    }
+  } else {
+    // ============================ epilogue ============================
+    const int q = warp;
+    uint32_t ai = 0;
+    for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
+      const TcItem ti = tc_decode(p, item, TZ);
+      const int strip = ti.grp * 4 + q;
+      const int seg = strip % p.nseg, ys = strip / p.nseg;
+      const int x = seg * p.segw + lane - 1;
+      const int ya = ys * p.rows;
+      const int yb = min(ya + p.rows, p.H);
+      const bool lane_ok = strip < p.nstrips && lane >= 1 && lane <= p.segw && x < p.W;
+      float Pa[TZ][COT], Pb[TZ][COT];  // partial sums of output rows y_in-1 and y_in
+#pragma unroll
+      for (int zo = 0; zo < TZ; ++zo)
+#pragma unroll
+        for (int c = 0; c < COT; ++c) Pa[zo][c] = Pb[zo][c] = 0.f;
+      for (int step = 0; step < nsteps; ++step) {
+        const int yin = ya - 1 + step;
+        const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
+        tc_mbar_wait(&accf[ab], aph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float fin[TZ][COT];
+#pragma unroll
+        for (int zo = 0; zo < TZ; ++zo) {
+          const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + zo * NB;
+#pragma unroll
+          for (int c8 = 0; c8 < COT / 8; ++c8) {
+            float t0[8];
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              float d0[8], d1[8], d2[8];
+              tc_ld8x3(tb + (kh * 3 + 0) * COT + c8 * 8, tb + (kh * 3 + 1) * COT + c8 * 8, tb + (kh * 3 + 2) * COT + c8 * 8, d0, d1, d2);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                // out column x gathers input columns x-1 (kw=0), x (kw=1), x+1 (kw=2)
+                const float t = __shfl_up_sync(0xffffffffu, d0[j], 1) + d1[j] + __shfl_down_sync(0xffffffffu, d2[j], 1);
+                if (kh == 0)
+                  t0[j] = t;                                   // first contribution to output row y_in+1
+                else if (kh == 1)
+                  Pb[zo][c8 * 8 + j] += t;                     // output row y_in
+                else
+                  fin[zo][c8 * 8 + j] = Pa[zo][c8 * 8 + j] + t;  // output row y_in-1 is complete
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              Pa[zo][c8 * 8 + j] = Pb[zo][c8 * 8 + j];
+              Pb[zo][c8 * 8 + j] = t0[j];
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(&acce[ab]);
+        ++ai;
+        const int yo = yin - 1;
+        if (lane_ok && yo >= ya && yo < yb) {
+          const bool post = p.out_mul || p.residual || p.act2 != ESM_ACT_NONE;
+#pragma unroll
+          for (int zo = 0; zo < TZ; ++zo) {
+            const int z = ti.z0 + zo;
+            if (z < p.D) {
+              const long long obase = (long long)ti.b * p.oB + (long long)z * p.oD + (long long)yo * p.oH + x;
+#pragma unroll
+              for (int c4 = 0; c4 < COT; c4 += 4) {
+                const int co0 = cot * COT + c4;
+                float rv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int co = co0 + j;
+                  const float sc = (p.scale && co < p.Cout) ? __ldg(p.scale + co) : 1.f;
+                  const float sh = (p.shift && co < p.Cout) ? __ldg(p.shift + co) : 0.f;
+                  rv[j] = fmaf(fin[zo][c4 + j], sc, sh);
+                }
+                if (p.act != ESM_ACT_NONE) {
+                  const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), p.act);
+                  rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
+                }
+                if (post) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const int co = co0 + j;
+                    if (co < p.Cout) {
+                      if (p.out_mul) rv[j] *= __ldg(p.out_mul + (long long)ti.b * p.omB + (long long)co * p.omC + (long long)yo * p.omH + x);
+                      if (p.residual) rv[j] += __ldg(p.residual + obase + (long long)co * p.oC);
+                    }
+                  }
+                  if (p.act2 != ESM_ACT_NONE) {
+                    const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), p.act2);
+                    rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int co = co0 + j;
+                  if (co < p.Cout) p.out[obase + (long long)co * p.oC] = rv[j] * p.out_scale;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+typedef void (*tc_fn_t)(const TcK);
+static long long tc_launches = 0;
+
+static tc_fn_t tc_pick(int COT, int TZ, int KD, bool gwc) {
+  if (gwc) return (COT == 8 && TZ == 3 && KD == 3) ? (tc_fn_t)tc_conv_kernel<8, 3, 3, true> : nullptr;
+  if (KD == 3) {
+    if (COT == 8 && TZ == 3) return tc_conv_kernel<8, 3, 3, false>;
+    if (COT == 16 && TZ == 1) return tc_conv_kernel<16, 1, 3, false>;
+    if (COT == 24 && TZ == 1) return tc_conv_kernel<24, 1, 3, false>;
+  } else if (TZ == 1) {
+    if (COT == 8) return tc_conv_kernel<8, 1, 1, false>;
+    if (COT == 16) return tc_conv_kernel<16, 1, 1, false>;
+    if (COT == 24) return tc_conv_kernel<24, 1, 1, false>;
+  }
+  return nullptr;
+}
+
+bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
+  if (d->transposed || d->stride != 1 || d->kh != 3 || d->kw != 3 || d->ph != 1 || d->pw != 1) return false;
+  if (!(d->kd == 1 || d->kd == 3) || d->pd != d->kd / 2) return false;
+  if (d->pixel_shuffle || d->in_mul) return false;
+  if (d->Cin < 8 || num_sms <= 0) return false;
+  const bool gwc = d->src_mode == ESM_SRC_GWC;
+  if (gwc) {
+    if (d->nsrc != 2 || d->src[0].C != 2 * d->Cin || d->kd != 3) return false;
+  } else {
+    for (int i = 0; i + 1 < d->nsrc; ++i)
+      if (d->src[i].C % 8) return false;
+  }
+  const int CoutPad8 = round_up(d->Cout, 8);
+  int COT;
+  if (CoutPad8 <= 24) {
+    COT = CoutPad8;
+  } else {
+    const int w24 = ceil_div(CoutPad8, 24) * 24, w16 = ceil_div(CoutPad8, 16) * 16;
+    COT = (w16 < w24) ? 16 : 24;
+  }
+  if (gwc && COT != 8) return false;
+  plan->COT = COT;
+  plan->ncot = ceil_div(d->Cout, COT);
+  plan->KD = d->kd;
+  plan->TZ = (d->kd == 3 && COT == 8) ? 3 : 1;
+  plan->gwc = gwc;
+  plan->npass = npass;
+  if (!tc_pick(COT, plan->TZ, plan->KD, gwc)) return false;
+  const int NB = 9 * COT, NROW = plan->TZ + plan->KD - 1, CGS = NROW == 1 ? 4 : 1;
+  const int ncg = ceil_div(d->Cin, 8);
+  const size_t wbytes = ((size_t)ncg * plan->KD * 2 * NB * 32 + 127) & ~(size_t)127;
+  const size_t stage = (size_t)CGS * NROW * 8192;
+  const size_t limit = 227 * 1024 - 256;
+  if (wbytes + 2 * stage > limit) return false;
+  int ns = (int)((limit - wbytes) / stage);
+  plan->nstages = ns > 4 ? 4 : ns;
+  plan->smem = wbytes + plan->nstages * stage + 256;
+  plan->nseg = ceil_div(d->Wout, 30);
+  plan->segw = ceil_div(d->Wout, plan->nseg);
+  const int ztiles = ceil_div(d->Dout, plan->TZ);
+  const int sms = num_sms / plan->ncot > 0 ? num_sms / plan->ncot : 1;
+  double best = 1e30;
+  for (int ys = 1; ys <= 64 && ys <= d->Hout; ++ys) {
+    const int rows = ceil_div(d->Hout, ys);
+    if (ceil_div(d->Hout, rows) != ys) continue;
+    const long long items = (long long)d->B * ztiles * ceil_div(plan->nseg * ys, 4);
+    const long long waves = (items + sms - 1) / sms;
+    const double cost = (double)waves * (rows + 2) + 1.0;  // +1: per-item pipeline fill
+    if (cost < best) {
+      best = cost;
+      plan->ysplit = ys;
+      plan->rows = rows;
+      plan->ctas_per_cot = (int)(items < sms ? items : sms);
+    }
+  }
+  return true;
+}
+
+int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
+  TcK k;
+  memset(&k, 0, sizeof(k));
+  for (int i = 0; i < d->nsrc; ++i) k.src[i] = d->src[i];
+  k.nsrc = d->nsrc;
+  k.cpg = plan.gwc ? d->src[0].C / d->Cin : 0;
+  k.B = d->B;
+  k.Cin = d->Cin;
+  k.ncg = ceil_div(d->Cin, 8);
+  k.D = d->Dout;
+  k.H = d->Hout;
+  k.W = d->Wout;
+  k.Cout = d->Cout;
+  k.CinPad = round_up(d->Cin, 8);
+  k.CoutPad = (int)(esm_packed_weight_elems(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0) / ((long long)d->kd * 9 * k.CinPad));
+  k.weight = d->weight;
+  k.scale = d->scale;
+  k.shift = d->shift;
+  k.act = d->act;
+  k.act2 = d->act2;
+  k.out_mul = d->out_mul;
+  k.omH = d->Wout;
+  k.omC = (long long)d->Hout * d->Wout;
+  k.omB = k.omC * d->Cout;
+  k.residual = d->residual;
+  k.out_scale = d->out_scale;
+  k.out = d->out;
+  k.oB = d->oB;
+  k.oC = d->oC;
+  k.oD = d->oD;
+  k.oH = d->oH;
+  k.nseg = plan.nseg;
+  k.segw = plan.segw;
+  k.rows = plan.rows;
+  k.nstrips = plan.nseg * plan.ysplit;
+  k.groups = ceil_div(k.nstrips, 4);
+  k.ztiles = ceil_div(d->Dout, plan.TZ);
+  k.items_per_cot = d->B * k.ztiles * k.groups;
+  k.ctas_per_cot = plan.ctas_per_cot;
+  k.nstages = plan.nstages;
+  k.npass = plan.npass;
+  tc_fn_t fn = tc_pick(plan.COT, plan.TZ, plan.KD, plan.gwc != 0);
+  ESM_REQUIRE(fn, "conv(tc): no kernel for COT=%d TZ=%d KD=%d", plan.COT, plan.TZ, plan.KD);
+  if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess)
+    return check_launch("conv(tc, cudaFuncSetAttribute)");
+  fn<<<(unsigned)(plan.ncot * plan.ctas_per_cot), TC_THREADS, plan.smem, st>>>(k);
+  ++tc_launches;
+  return check_launch("conv(tc)");
+}
+
+}  // namespace esm
+
+extern "C" long long esm_tc_conv_launches(void) { return esm::tc_launches; }

@@ -1,0 +1,26 @@
+// Tensor-core (tcgen05 / TMEM) path of the convolution family: k3 s1 p1 convolutions, 2D and 3D,
+// optionally with the group-wise correlation volume generated on the fly (see conv_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace esm {
+
+struct TcPlan {
+  int COT;           // output channels per CTA (8, 16 or 24): N = 9*COT columns per accumulator row
+  int TZ;            // output planes per work item (3 for COT=8 in 3D, else 1)
+  int KD;            // 1 (2D) or 3
+  int gwc;           // input voxels are group-wise correlations
+  int ncot;          // output-channel tiles (= CTA groups; every CTA keeps one tile's weights resident)
+  int nseg, segw;    // W is cut into nseg segments of segw (<= 30) output columns
+  int ysplit, rows;  // H is cut into ysplit ranges of `rows` output rows
+  int nstages;       // operand ring depth
+  int ctas_per_cot;  // persistent CTAs per channel tile
+  int npass;         // 3: split-TF32 (fp32-grade), 1: single-pass TF32
+  size_t smem;
+};
+
+// Fills `plan` and returns true when `d` can run on the tensor-core path.
+bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan);
+int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st);
+
+}  // namespace esm

@@ -101,6 +101,10 @@ int esm_pack_conv_weight_f32(const float* w, float* packed, int Cout, int Cin, i
 int esm_fold_bn_f32(const float* gamma, const float* beta, const float* mean, const float* var,
                     const float* bias, float eps, int C, float* scale, float* shift, void* stream);
 int esm_conv_f32(const esm_conv_t* desc, void* stream);
+/* Number of esm_conv_f32 calls so far that ran on the tcgen05 tensor-core path (k3 s1 p1 layers, when
+ * it wins the on-device timing or ESM_TC_FORCE is set; ESM_TC=0 disables it, ESM_TC=1 selects the
+ * single-pass TF32 fast mode instead of the fp32-grade split).  Diagnostics / tests. */
+long long esm_tc_conv_launches(void);
 
 /* build_gwc_volume (submodule.py:151-161): L,R [B,C,H,W] -> V [B,G,D,H,W]; writes the zero
  * triangle itself (no memset). */

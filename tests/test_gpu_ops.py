@@ -285,3 +285,83 @@ def test_errors_are_loud():
     pc = gpu_pack(p, 1, 1, False)
     with pytest.raises(AssertionError):
         ops.conv(torch.zeros(1, 9, 4, 8).cuda(), pc)
+
+
+# ---- tensor-core (tcgen05) path of the k3 s1 p1 convolutions: forced on, every structural variant ----
+TC_CASES = [
+    # name, nd, cin, cout, in_shape, batch
+    ("tc3d_8_8", 3, 8, 8, (7, 37, 95), 2),        # COT=8, TZ=3: partial z tile, several strips and y ranges
+    ("tc3d_32_8", 3, 32, 8, (6, 10, 36), 1),
+    ("tc3d_24_24", 3, 24, 24, (5, 20, 61), 1),    # COT=24, TZ=1
+    ("tc3d_16_16", 3, 16, 16, (4, 9, 33), 1),     # COT=16
+    ("tc3d_24_40", 3, 24, 40, (3, 6, 20), 1),     # two channel tiles of 24 (padded)
+    ("tc3d_12_12_padded_cin", 3, 12, 12, (4, 7, 11), 1),
+    ("tc2d_32_32", 2, 32, 32, (50, 200), 1),      # two channel tiles of 16, ragged 4-group stages
+    ("tc2d_96_48", 2, 96, 48, (12, 40), 2),
+    ("tc2d_16_8", 2, 16, 8, (9, 21), 1),
+    ("tc2d_24_64", 2, 24, 64, (31, 64), 1),
+    ("tc2d_wide", 2, 32, 32, (4, 312), 1),
+]
+
+
+@pytest.fixture
+def tc_forced(monkeypatch):
+    monkeypatch.setenv("ESM_TC_FORCE", "1")
+    monkeypatch.setenv("ESM_TC", "3")
+    from esmstereo_b200 import _lib
+    return _lib.lib().esm_tc_conv_launches
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_conv_tensor_core_path(case, tc_forced, monkeypatch):
+    """Split-TF32 tcgen05 path: same gate as the FP32-pipe kernels (2e-5 of the tensor's max)."""
+    name, nd, cin, cout, sp, B = case
+    ops = _ops()
+    p = make_layer(cin, cout, 3, nd, seed=len(name))
+    x = rnd(B, cin, *sp, seed=3)
+    want = ref_conv(x, p, 1, 1, False, "gelu", nd)
+    pc = gpu_pack(p, 1, 1, False)
+    n0 = tc_forced()
+    got = ops.conv(x.cuda(), pc, "gelu")
+    assert tc_forced() == n0 + 1, "layer did not take the tensor-core path"
+    assert rel(got, want) < 2e-5, name
+    # single-pass TF32 fast mode: operands rounded to 10 mantissa bits
+    monkeypatch.setenv("ESM_TC", "1")
+    got1 = ops.conv(x.cuda(), pc, "gelu")
+    assert tc_forced() == n0 + 2
+    assert rel(got1, want) < 3e-3, name
+
+
+def test_conv_tensor_core_fusions(tc_forced):
+    ops = _ops()
+    # concat of two sources + residual + second activation + scale
+    a, b = rnd(2, 16, 11, 45, seed=1), rnd(2, 8, 11, 45, seed=2)
+    p = make_layer(24, 16, 3, 2, bias=True, seed=3)
+    res = rnd(2, 16, 11, 45, seed=4)
+    want = torch.sigmoid(ref_conv(torch.cat((a, b), 1), p, 1, 1, False, "gelu", 2) + res) * 3.0
+    n0 = tc_forced()
+    got = ops.conv([a.cuda(), b.cuda()], gpu_pack(p, 1, 1, False), "gelu", residual=res.cuda(), act2="sigmoid", out_scale=3.0)
+    assert tc_forced() == n0 + 1
+    assert rel(got, want) < 2e-5
+    # cropped 3D view as input, out_mul broadcast over D
+    full = rnd(1, 8, 6, 12, 40, seed=5)
+    v = full[:, :, :5, :11, :37]
+    att = rnd(1, 8, 11, 37, seed=6)
+    p = make_layer(8, 8, 3, 3, seed=7)
+    want = ref_conv(v, p, 1, 1, False, "gelu", 3) * att.unsqueeze(2)
+    got = ops.conv(full.cuda()[:, :, :5, :11, :37], gpu_pack(p, 1, 1, False), "gelu", out_mul=att.cuda())
+    assert tc_forced() == n0 + 2
+    assert rel(got, want) < 2e-5
+
+
+@pytest.mark.parametrize("H,W,D", [(6, 40, 12), (20, 100, 12), (5, 33, 7)])
+def test_gwc_fused_tensor_core(H, W, D, tc_forced):
+    ops = _ops()
+    L, R = rnd(1, 64, H, W, seed=1), rnd(1, 64, H, W, seed=2)
+    p = make_layer(32, 8, 3, 3, seed=3)
+    vol = EsmOracle({}, 192).gwc_volume(L, R, D, 32)
+    want = ref_conv(vol, p, 1, 1, False, "gelu", 3)
+    n0 = tc_forced()
+    got = ops.conv([L.cuda(), R.cuda()], gpu_pack(p, 1, 1, False), "gelu", gwc_disp=D)
+    assert tc_forced() == n0 + 1
+    assert rel(got, want) < 2e-5
