@@ -52,8 +52,10 @@ struct TcK {
   int items_per_cot, ctas_per_cot, nstages, npass;
 };
 
-constexpr int TC_NTW = 8;                        // operand-producer warps
-constexpr int TC_THREADS = 32 * (5 + TC_NTW);    // 4 epilogue + 1 MMA + producers
+constexpr int TC_NTW = 8;                               // operand-producer warps
+constexpr int TC_NEW = 8;                               // epilogue warps: 2 per TMEM lane quadrant
+constexpr int TC_MMA_WARP = TC_NEW;                     // warp index of the MMA issuer
+constexpr int TC_THREADS = 32 * (TC_NEW + 1 + TC_NTW);  // epilogue + MMA + producers
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
@@ -88,25 +90,24 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
-// Three 8-column loads of this warp's TMEM lane quadrant plus the wait, in ONE asm statement so that no
+// Three 4-column loads of this warp's TMEM lane quadrant plus the wait, in ONE asm statement so that no
 // use of the results can be scheduled ahead of tcgen05.wait::ld.
-__device__ __forceinline__ void tc_ld8x3(uint32_t ta, uint32_t tb, uint32_t tc, float (&a)[8], float (&b)[8], float (&c)[8]) {
-  uint32_t u[24];
+__device__ __forceinline__ void tc_ld4x3(uint32_t ta, uint32_t tb, uint32_t tc, float (&a)[4], float (&b)[4], float (&c)[4]) {
+  uint32_t u[12];
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%24];\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%25];\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%26];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%12];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4,%5,%6,%7}, [%13];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8,%9,%10,%11}, [%14];\n\t"
       "tcgen05.wait::ld.sync.aligned;"
       : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
-        "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
-        "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23])
+        "=r"(u[10]), "=r"(u[11])
       : "r"(ta), "r"(tb), "r"(tc)
       : "memory");
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
     a[i] = __uint_as_float(u[i]);
-    b[i] = __uint_as_float(u[8 + i]);
-    c[i] = __uint_as_float(u[16 + i]);
+    b[i] = __uint_as_float(u[4 + i]);
+    c[i] = __uint_as_float(u[8 + i]);
   }
 }
 __device__ __forceinline__ float tc_rna(float x) {  // round to nearest TF32 (low 13 mantissa bits zero)
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   constexpr int STAGE_BYTES = TPW * ROW_BYTES;
   constexpr int WSLAB = NB * 32;               // one (cg, kd, hi|lo) B operand: [2][NB][4] floats
   constexpr int ACC_COLS = 256;                // TMEM columns per accumulator buffer (TZ*NB <= 256)
+  constexpr int CW = COT / 2;                  // output channels per epilogue warp
   static_assert(TZ * NB <= ACC_COLS, "accumulator does not fit");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   uint64_t* accf = empty + NS;
   uint64_t* acce = accf + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + 2);
+  float* s_aff = reinterpret_cast<float*>(tmem_slot + 2);  // [2][COT] scale, shift of this channel tile
   const int cot = blockIdx.x / p.ctas_per_cot;
   const int cta = blockIdx.x % p.ctas_per_cot;
   const int nsteps = p.rows + 2;
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       tc_mbar_init(&accf[i], 1);
-      tc_mbar_init(&acce[i], 4);
+      tc_mbar_init(&acce[i], TC_NEW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -169,25 +172,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (tid < 2 * COT) {
+    const int c = tid % COT, co = cot * COT + c;
+    const float* src = tid < COT ? p.scale : p.shift;
+    s_aff[tid] = (src && co < p.Cout) ? __ldg(src + co) : (tid < COT ? 1.f : 0.f);
+  }
   // resident weights of this channel tile: split and laid out as UMMA B operands
   // (row n = (kh*3+kw)*COT + co, K = 8 input channels of group cg)
-  for (int idx = tid; idx < ncg * KD * NB * 8; idx += TC_THREADS) {
-    const int col = idx % COT;
-    int t = idx / COT;
-    const int k = t & 7;
-    t >>= 3;
-    const int tap2 = t % 9;
-    t /= 9;
-    const int kd = t % KD;
-    const int cg = t / KD;
-    const int co = cot * COT + col, ci = cg * 8 + k;
-    float w = 0.f;
-    if (co < p.CoutPad && ci < p.CinPad) w = __ldg(p.weight + ((long long)(kd * 9 + tap2) * p.CinPad + ci) * p.CoutPad + co);
-    const float hi = tc_rna(w);
-    const float lo = tc_rna(w - hi);
-    const uint32_t off = (uint32_t)((cg * KD + kd) * 2) * WSLAB + (uint32_t)(k >> 2) * (NB * 16) + (uint32_t)(tap2 * COT + col) * 16 + (k & 3) * 4;
-    *reinterpret_cast<float*>(s_w + off) = hi;
-    *reinterpret_cast<float*>(s_w + off + WSLAB) = lo;
+  {
+    const int total = ncg * KD * NB * 8;
+    constexpr int U = 4;
+    for (int base = tid; base < total; base += U * TC_THREADS) {
+      float w[U];
+      uint32_t off[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = base + u * TC_THREADS;
+        const int col = idx % COT;
+        int t = idx / COT;
+        const int k = t & 7;
+        t >>= 3;
+        const int tap2 = t % 9;
+        t /= 9;
+        const int kd = t % KD;
+        const int cg = t / KD;
+        const int co = cot * COT + col, ci = cg * 8 + k;
+        w[u] = 0.f;
+        if (idx < total && co < p.CoutPad && ci < p.CinPad)
+          w[u] = __ldg(p.weight + ((long long)(kd * 9 + tap2) * p.CinPad + ci) * p.CoutPad + co);
+        off[u] = (uint32_t)((cg * KD + kd) * 2) * WSLAB + (uint32_t)(k >> 2) * (NB * 16) + (uint32_t)(tap2 * COT + col) * 16 + (k & 3) * 4;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (base + u * TC_THREADS < total) {
+          const float hi = tc_rna(w[u]);
+          *reinterpret_cast<float*>(s_w + off[u]) = hi;
+          *reinterpret_cast<float*>(s_w + off[u] + WSLAB) = tc_rna(w[u] - hi);
+        }
+      }
+    }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -195,96 +218,107 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  if (warp >= 5) {
+  if (warp > TC_MMA_WARP) {
     // ============================ operand producers ============================
-    const int tw = warp - 5;
+    const int tw = warp - TC_MMA_WARP - 1;
     const int q = (tw >> 1) & 3;   // strip (= TMEM lane quadrant) this warp feeds
     const int khalf = tw & 1;      // which 4 of the 8 channels of a group
     const int m = q * 32 + lane;   // A row
     uint32_t it = 0;
-    // iteration state: (item, step, cgb)
+    // load cursor (item, step, cgb) and what it caches per item; offsets are 32-bit (host checks the extents)
     int item = cta, step = 0, cgb = 0;
-    auto load_at = [&](int item_, int step_, int cgb_, float (&v)[TPW][4]) {
-      const TcItem ti = tc_decode(p, item_, TZ);
+    const float* base[3] = {nullptr, nullptr, nullptr};
+    int z0 = 0, ya = 0, x = 0;
+    bool strip_ok = false;
+    auto enter_item = [&]() {
+      if (item >= p.items_per_cot) return;
+      const TcItem ti = tc_decode(p, item, TZ);
       const int strip = ti.grp * 4 + q;
       const int seg = strip % p.nseg, ys = strip / p.nseg;
-      const int x = seg * p.segw + lane - 1;
-      const int y = ys * p.rows - 1 + step_;
-      const bool ok = strip < p.nstrips && y >= 0 && y < p.H && x >= 0 && x < p.W && lane <= p.segw + 1;
-      if (GWC) {
-        // v = 0.5 * (L[2g]*R[2g](x-d) + L[2g+1]*R[2g+1](x-d)), un-contracted (submodule.py:147); cpg == 2
-        const int g0 = cgb_ * 8 + khalf * 4;
-        const float* lp = p.src[0].ptr + (long long)ti.b * p.src[0].sB + (long long)(g0 * 2) * p.src[0].sC + (long long)y * p.src[0].sH + x;
-        const float* rp = p.src[1].ptr + (long long)ti.b * p.src[1].sB + (long long)(g0 * 2) * p.src[1].sC + (long long)y * p.src[1].sH + x;
-        float l[8];
+      x = seg * p.segw + lane - 1;
+      ya = ys * p.rows;
+      z0 = ti.z0;
+      strip_ok = strip < p.nstrips && x >= 0 && x < p.W && lane <= p.segw + 1;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) l[c] = (ok && g0 + c / 2 < p.Cin) ? __ldg(lp + (long long)c * p.src[0].sC) : 0.f;
+      for (int i = 0; i < 3; ++i)
+        if (i < p.nsrc) base[i] = p.src[i].ptr + (long long)ti.b * p.src[i].sB;
+    };
+    auto load = [&](float (&v)[TPW][4]) {
+      const int y = ya - 1 + step;
+      const bool ok = strip_ok && (unsigned)y < (unsigned)p.H;
+      if (GWC) {
+        // v = 0.5 * (L[2g]*R[2g](x-d) + L[2g+1]*R[2g+1](x-d)), un-contracted (submodule.py:147); cpg == 2.
+        // All loads are issued first (predicated, never branched around) so that they overlap.
+        const int g0 = cgb * 8 + khalf * 4;
+        const int nch = 2 * min(4, p.Cin - g0);  // valid feature channels of this half group
+        const int sC = (int)p.src[0].sC;
+        const int off = (g0 * 2) * sC + y * (int)p.src[0].sH + x;
+        float l[8], rr[NROW][8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) l[c] = (ok && c < nch) ? __ldg(base[0] + (off + c * sC)) : 0.f;
 #pragma unroll
         for (int r = 0; r < NROW; ++r) {
-          const int d = ti.z0 + r - KD / 2;
-          const bool okd = ok && d >= 0 && d < p.D && x >= d;
+          const int d = z0 + r - KD / 2;
+          const bool okd = ok && (unsigned)d < (unsigned)p.D && x >= d;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float val = 0.f;
-            if (okd && g0 + g < p.Cin) {
-              const float r0 = __ldg(rp + (long long)(2 * g) * p.src[1].sC - d);
-              const float r1 = __ldg(rp + (long long)(2 * g + 1) * p.src[1].sC - d);
-              val = __fmul_rn(__fadd_rn(__fmul_rn(l[2 * g], r0), __fmul_rn(l[2 * g + 1], r1)), 0.5f);
-            }
-            v[r][g] = val;
-          }
+          for (int c = 0; c < 8; ++c) rr[r][c] = (okd && c < nch) ? __ldg(base[1] + (off + c * sC - d)) : 0.f;
         }
+#pragma unroll
+        for (int r = 0; r < NROW; ++r)
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            v[r][g] = __fmul_rn(__fadd_rn(__fmul_rn(l[2 * g], rr[r][2 * g]), __fmul_rn(l[2 * g + 1], rr[r][2 * g + 1])), 0.5f);
       } else {
 #pragma unroll
-        for (int j = 0; j < TPW; ++j) {
-          const int cgl = j / NROW, r = j % NROW;
-          const int cg = cgb_ + cgl;
-          const int z = ti.z0 + r - KD / 2;
-          int rel = cg * 8 + khalf * 4, k = 0;
-          while (k < p.nsrc - 1 && rel >= p.src[k].C) {  // host guarantees 8-channel groups never straddle sources
-            rel -= p.src[k].C;
-            ++k;
+        for (int cgl = 0; cgl < CGS; ++cgl) {
+          int rel = (cgb + cgl) * 8 + khalf * 4, k = 0;
+          if (p.nsrc > 1) {
+            while (k < p.nsrc - 1 && rel >= p.src[k].C) {  // host guarantees 8-channel groups never straddle sources
+              rel -= p.src[k].C;
+              ++k;
+            }
           }
-          const esm_src_t& s = p.src[k];
-          const float* bp = s.ptr + (long long)ti.b * s.sB + (long long)rel * s.sC + (long long)z * s.sD + (long long)y * s.sH + x;
-          const bool okz = ok && cg < ncg && z >= 0 && z < p.D;
+          const int sC = (int)p.src[k].sC, sD = (int)p.src[k].sD;
+          const int nch = p.src[k].C - rel;  // valid channels from `rel` on (<= 0 past the last group)
+          const float* bp = p.nsrc > 1 ? (k == 0 ? base[0] : k == 1 ? base[1] : base[2]) : base[0];
+          const int off = rel * sC + (z0 - KD / 2) * sD + y * (int)p.src[k].sH + x;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) v[j][c] = (okz && rel + c < s.C) ? __ldg(bp + (long long)c * s.sC) : 0.f;
+          for (int r = 0; r < NROW; ++r) {
+            const bool okz = ok && (unsigned)(z0 + r - KD / 2) < (unsigned)p.D;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[cgl * NROW + r][c] = (okz && c < nch) ? __ldg(bp + (off + r * sD + c * sC)) : 0.f;
+          }
         }
       }
     };
-    auto advance = [&](int& item_, int& step_, int& cgb_) {
-      cgb_ += CGS;
-      if (cgb_ >= ncg) {
-        cgb_ = 0;
-        if (++step_ >= nsteps) {
-          step_ = 0;
-          item_ += p.ctas_per_cot;
+    auto advance = [&]() {
+      cgb += CGS;
+      if (cgb >= ncg) {
+        cgb = 0;
+        if (++step >= nsteps) {
+          step = 0;
+          item += p.ctas_per_cot;
+          enter_item();
         }
       }
     };
-    float va[TPW][4], vb[TPW][4];
-    if (item < p.items_per_cot) load_at(item, step, cgb, va);
-    while (item < p.items_per_cot) {
-      int ni = item, nst = step, ncb = cgb;
-      advance(ni, nst, ncb);
-      if (ni < p.items_per_cot) load_at(ni, nst, ncb, vb);  // next stage's loads are in flight during this stage's stores
+    auto store_stage = [&](const float (&v)[TPW][4]) {
       const uint32_t st = it % NS, ph = (it / NS) & 1;
       tc_mbar_wait(&empty[st], ph ^ 1);
       uint8_t* sb = s_stage + (size_t)st * STAGE_BYTES + khalf * 2048 + m * 16;
 #pragma unroll
       for (int j = 0; j < TPW; ++j) {
         float4 hi, lo;
-        hi.x = tc_rna(va[j][0]);
-        hi.y = tc_rna(va[j][1]);
-        hi.z = tc_rna(va[j][2]);
-        hi.w = tc_rna(va[j][3]);
+        hi.x = tc_rna(v[j][0]);
+        hi.y = tc_rna(v[j][1]);
+        hi.z = tc_rna(v[j][2]);
+        hi.w = tc_rna(v[j][3]);
         *reinterpret_cast<float4*>(sb + j * ROW_BYTES) = hi;
         if (p.npass == 3) {
-          lo.x = tc_rna(va[j][0] - hi.x);
-          lo.y = tc_rna(va[j][1] - hi.y);
-          lo.z = tc_rna(va[j][2] - hi.z);
-          lo.w = tc_rna(va[j][3] - hi.w);
+          lo.x = tc_rna(v[j][0] - hi.x);
+          lo.y = tc_rna(v[j][1] - hi.y);
+          lo.z = tc_rna(v[j][2] - hi.z);
+          lo.w = tc_rna(v[j][3] - hi.w);
           *reinterpret_cast<float4*>(sb + j * ROW_BYTES + 4096) = lo;
         }
       }
@@ -292,15 +326,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(&full[st]);
       ++it;
-#pragma unroll
-      for (int j = 0; j < TPW; ++j)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) va[j][c] = vb[j][c];
-      item = ni;
-      step = nst;
-      cgb = ncb;
+    };
+    // two register buffers, loop unrolled by two: the loads of stage i+1 are in flight while stage i is
+    // converted and stored (no register copies, so nothing waits on a load before its own store)
+    float va[TPW][4], vb[TPW][4];
+    enter_item();
+    if (item < p.items_per_cot) load(va);
+    while (item < p.items_per_cot) {
+      advance();
+      if (item < p.items_per_cot) load(vb);
+      store_stage(va);
+      if (item >= p.items_per_cot) break;
+      advance();
+      if (item < p.items_per_cot) load(va);
+      store_stage(vb);
     }
-  } else if (warp == 4) {
+  } else if (warp == TC_MMA_WARP) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       // D = f32, A = B = tf32, both K-major, N = NB, M = 128
@@ -347,7 +388,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     }
   } else {
     // ============================ epilogue ============================
-    const int q = warp;
+    // warp w and w+4 share TMEM lane quadrant q = w % 4 (one strip) and own CW = COT/2 channels each
+    const int q = warp & 3;
+    const int ch0 = (warp >> 2) * CW;  // first channel (within the tile) of this warp
+    const int nvalid = p.Cout - (cot * COT + ch0);  // channels of this warp that exist
+    const int oC = (int)p.oC, oD = (int)p.oD, oH = (int)p.oH;
+    const bool post = p.out_mul || p.residual || p.act2 != ESM_ACT_NONE;
     uint32_t ai = 0;
     for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
       const TcItem ti = tc_decode(p, item, TZ);
@@ -357,43 +403,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       const int ya = ys * p.rows;
       const int yb = min(ya + p.rows, p.H);
       const bool lane_ok = strip < p.nstrips && lane >= 1 && lane <= p.segw && x < p.W;
-      float Pa[TZ][COT], Pb[TZ][COT];  // partial sums of output rows y_in-1 and y_in
+      float* op = p.out + (long long)ti.b * p.oB + x;  // 32-bit offsets from here (host checks the extents)
+      const float* rp = p.residual ? p.residual + (long long)ti.b * p.oB + x : nullptr;
+      const float* mp = p.out_mul ? p.out_mul + (long long)ti.b * p.omB + x : nullptr;
+      float Pa[TZ][CW], Pb[TZ][CW];  // partial sums of output rows y_in-1 and y_in
 #pragma unroll
       for (int zo = 0; zo < TZ; ++zo)
 #pragma unroll
-        for (int c = 0; c < COT; ++c) Pa[zo][c] = Pb[zo][c] = 0.f;
+        for (int c = 0; c < CW; ++c) Pa[zo][c] = Pb[zo][c] = 0.f;
       for (int step = 0; step < nsteps; ++step) {
         const int yin = ya - 1 + step;
         const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
         tc_mbar_wait(&accf[ab], aph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float fin[TZ][COT];
+        float fin[TZ][CW];
 #pragma unroll
         for (int zo = 0; zo < TZ; ++zo) {
-          const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + zo * NB;
+          const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + zo * NB + ch0;
 #pragma unroll
-          for (int c8 = 0; c8 < COT / 8; ++c8) {
-            float t0[8];
+          for (int c4 = 0; c4 < CW; c4 += 4) {
+            float t0[4];
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
-              float d0[8], d1[8], d2[8];
-              tc_ld8x3(tb + (kh * 3 + 0) * COT + c8 * 8, tb + (kh * 3 + 1) * COT + c8 * 8, tb + (kh * 3 + 2) * COT + c8 * 8, d0, d1, d2);
+              float d0[4], d1[4], d2[4];
+              tc_ld4x3(tb + (kh * 3 + 0) * COT + c4, tb + (kh * 3 + 1) * COT + c4, tb + (kh * 3 + 2) * COT + c4, d0, d1, d2);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < 4; ++j) {
                 // out column x gathers input columns x-1 (kw=0), x (kw=1), x+1 (kw=2)
                 const float t = __shfl_up_sync(0xffffffffu, d0[j], 1) + d1[j] + __shfl_down_sync(0xffffffffu, d2[j], 1);
                 if (kh == 0)
-                  t0[j] = t;                                   // first contribution to output row y_in+1
+                  t0[j] = t;                               // first contribution to output row y_in+1
                 else if (kh == 1)
-                  Pb[zo][c8 * 8 + j] += t;                     // output row y_in
+                  Pb[zo][c4 + j] += t;                     // output row y_in
                 else
-                  fin[zo][c8 * 8 + j] = Pa[zo][c8 * 8 + j] + t;  // output row y_in-1 is complete
+                  fin[zo][c4 + j] = Pa[zo][c4 + j] + t;    // output row y_in-1 is complete
               }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              Pa[zo][c8 * 8 + j] = Pb[zo][c8 * 8 + j];
-              Pb[zo][c8 * 8 + j] = t0[j];
+            for (int j = 0; j < 4; ++j) {
+              Pa[zo][c4 + j] = Pb[zo][c4 + j];
+              Pb[zo][c4 + j] = t0[j];
             }
           }
         }
@@ -403,23 +452,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         ++ai;
         const int yo = yin - 1;
         if (lane_ok && yo >= ya && yo < yb) {
-          const bool post = p.out_mul || p.residual || p.act2 != ESM_ACT_NONE;
 #pragma unroll
           for (int zo = 0; zo < TZ; ++zo) {
-            const int z = ti.z0 + zo;
-            if (z < p.D) {
-              const long long obase = (long long)ti.b * p.oB + (long long)z * p.oD + (long long)yo * p.oH + x;
+            if (ti.z0 + zo < p.D) {
+              const int o_off = (ti.z0 + zo) * oD + yo * oH;
 #pragma unroll
-              for (int c4 = 0; c4 < COT; c4 += 4) {
-                const int co0 = cot * COT + c4;
+              for (int c4 = 0; c4 < CW; c4 += 4) {
+                const int cl = ch0 + c4;  // channel within the tile
                 float rv[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int co = co0 + j;
-                  const float sc = (p.scale && co < p.Cout) ? __ldg(p.scale + co) : 1.f;
-                  const float sh = (p.shift && co < p.Cout) ? __ldg(p.shift + co) : 0.f;
-                  rv[j] = fmaf(fin[zo][c4 + j], sc, sh);
-                }
+                for (int j = 0; j < 4; ++j) rv[j] = fmaf(fin[zo][c4 + j], s_aff[cl + j], s_aff[COT + cl + j]);
                 if (p.act != ESM_ACT_NONE) {
                   const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), p.act);
                   rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
@@ -427,10 +469,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 if (post) {
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
-                    const int co = co0 + j;
-                    if (co < p.Cout) {
-                      if (p.out_mul) rv[j] *= __ldg(p.out_mul + (long long)ti.b * p.omB + (long long)co * p.omC + (long long)yo * p.omH + x);
-                      if (p.residual) rv[j] += __ldg(p.residual + obase + (long long)co * p.oC);
+                    if (c4 + j < nvalid) {
+                      const int co = cot * COT + cl + j;
+                      if (p.out_mul) rv[j] *= __ldg(mp + (co * (int)p.omC + yo * (int)p.omH));
+                      if (p.residual) rv[j] += __ldg(rp + (o_off + co * oC));
                     }
                   }
                   if (p.act2 != ESM_ACT_NONE) {
@@ -439,10 +481,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                   }
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int co = co0 + j;
-                  if (co < p.Cout) p.out[obase + (long long)co * p.oC] = rv[j] * p.out_scale;
-                }
+                for (int j = 0; j < 4; ++j)
+                  if (c4 + j < nvalid) op[o_off + (cot * COT + cl + j) * oC] = rv[j] * p.out_scale;
               }
             }
           }
@@ -477,6 +517,10 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
   if (!(d->kd == 1 || d->kd == 3) || d->pd != d->kd / 2) return false;
   if (d->pixel_shuffle || d->in_mul) return false;
   if (d->Cin < 8 || num_sms <= 0) return false;
+  // the kernel addresses one batch item with 32-bit element offsets
+  for (int i = 0; i < d->nsrc; ++i)
+    if (d->src[i].sB >= (1ll << 31) || (long long)d->src[i].C * d->src[i].sC >= (1ll << 31)) return false;
+  if ((long long)d->Cout * d->oC >= (1ll << 31)) return false;
   const bool gwc = d->src_mode == ESM_SRC_GWC;
   if (gwc) {
     if (d->nsrc != 2 || d->src[0].C != 2 * d->Cin || d->kd != 3) return false;
@@ -504,11 +548,11 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
   const int ncg = ceil_div(d->Cin, 8);
   const size_t wbytes = ((size_t)ncg * plan->KD * 2 * NB * 32 + 127) & ~(size_t)127;
   const size_t stage = (size_t)CGS * NROW * 8192;
-  const size_t limit = 227 * 1024 - 256;
+  const size_t limit = 227 * 1024 - 512;
   if (wbytes + 2 * stage > limit) return false;
   int ns = (int)((limit - wbytes) / stage);
   plan->nstages = ns > 4 ? 4 : ns;
-  plan->smem = wbytes + plan->nstages * stage + 256;
+  plan->smem = wbytes + plan->nstages * stage + 512;
   plan->nseg = ceil_div(d->Wout, 30);
   plan->segw = ceil_div(d->Wout, plan->nseg);
   const int ztiles = ceil_div(d->Dout, plan->TZ);
