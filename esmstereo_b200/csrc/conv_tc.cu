@@ -617,7 +617,9 @@ int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
   k.npass = plan.npass;
   tc_fn_t fn = tc_pick(plan.COT, plan.TZ, plan.KD, plan.gwc != 0);
   ESM_REQUIRE(fn, "conv(tc): no kernel for COT=%d TZ=%d KD=%d", plan.COT, plan.TZ, plan.KD);
-  if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess)
+  // one limit for every launch of a function: the attribute is per function, not per launch, and graph
+  // replays (and profilers re-launching graph nodes) must find it at least as large as any node's request
+  if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return check_launch("conv(tc, cudaFuncSetAttribute)");
   fn<<<(unsigned)(plan.ncot * plan.ctas_per_cot), TC_THREADS, plan.smem, st>>>(k);
   ++tc_launches;
