@@ -128,9 +128,12 @@ __device__ __forceinline__ TcItem tc_decode(const TcK& p, int item, int TZ) {
   return t;
 }
 
-template <int COT, int TZ, int KD, bool GWC>
+// TAPS = 9: k3 s1 p1 in (h, w) as described above.  TAPS = 1: pointwise (k1) convolution -- the same
+// pipeline without halos, shuffles or the rolling window (N = COT, 32 output columns per strip).
+template <int COT, int TZ, int KD, bool GWC, int TAPS = 9>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcK p) {
-  constexpr int NB = 9 * COT;                  // accumulator columns per (z_o, y_in) row tile
+  constexpr int NB = TAPS * COT;               // accumulator columns per (z_o, y_in) row tile
+  constexpr int HALO = TAPS == 9 ? 1 : 0;
   constexpr int NROW = TZ + KD - 1;            // input planes per stage
   constexpr int CGS = (NROW == 1) ? 4 : 1;     // 8-channel groups per stage
   constexpr int TPW = CGS * NROW;              // row tiles per stage = tasks per producer warp
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   float* s_aff = reinterpret_cast<float*>(tmem_slot + 2);  // [2][COT] scale, shift of this channel tile
   const int cot = blockIdx.x / p.ctas_per_cot;
   const int cta = blockIdx.x % p.ctas_per_cot;
-  const int nsteps = p.rows + 2;
+  const int nsteps = p.rows + 2 * HALO;
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
@@ -192,14 +195,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         int t = idx / COT;
         const int k = t & 7;
         t >>= 3;
-        const int tap2 = t % 9;
-        t /= 9;
+        const int tap2 = t % TAPS;
+        t /= TAPS;
         const int kd = t % KD;
         const int cg = t / KD;
         const int co = cot * COT + col, ci = cg * 8 + k;
         w[u] = 0.f;
         if (idx < total && co < p.CoutPad && ci < p.CinPad)
-          w[u] = __ldg(p.weight + ((long long)(kd * 9 + tap2) * p.CinPad + ci) * p.CoutPad + co);
+          w[u] = __ldg(p.weight + ((long long)(kd * TAPS + tap2) * p.CinPad + ci) * p.CoutPad + co);
         off[u] = (uint32_t)((cg * KD + kd) * 2) * WSLAB + (uint32_t)(k >> 2) * (NB * 16) + (uint32_t)(tap2 * COT + col) * 16 + (k & 3) * 4;
       }
 #pragma unroll
@@ -235,16 +238,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       const TcItem ti = tc_decode(p, item, TZ);
       const int strip = ti.grp * 4 + q;
       const int seg = strip % p.nseg, ys = strip / p.nseg;
-      x = seg * p.segw + lane - 1;
+      x = seg * p.segw + lane - HALO;
       ya = ys * p.rows;
       z0 = ti.z0;
-      strip_ok = strip < p.nstrips && x >= 0 && x < p.W && lane <= p.segw + 1;
+      strip_ok = strip < p.nstrips && x >= 0 && x < p.W && lane < p.segw + 2 * HALO;
 #pragma unroll
       for (int i = 0; i < 3; ++i)
         if (i < p.nsrc) base[i] = p.src[i].ptr + (long long)ti.b * p.src[i].sB;
     };
     auto load = [&](float (&v)[TPW][4]) {
-      const int y = ya - 1 + step;
+      const int y = ya - HALO + step;
       const bool ok = strip_ok && (unsigned)y < (unsigned)p.H;
       if (GWC) {
         // v = 0.5 * (L[2g]*R[2g](x-d) + L[2g+1]*R[2g+1](x-d)), un-contracted (submodule.py:147); cpg == 2.
@@ -399,20 +402,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       const TcItem ti = tc_decode(p, item, TZ);
       const int strip = ti.grp * 4 + q;
       const int seg = strip % p.nseg, ys = strip / p.nseg;
-      const int x = seg * p.segw + lane - 1;
+      const int x = seg * p.segw + lane - HALO;
       const int ya = ys * p.rows;
       const int yb = min(ya + p.rows, p.H);
-      const bool lane_ok = strip < p.nstrips && lane >= 1 && lane <= p.segw && x < p.W;
+      const bool lane_ok = strip < p.nstrips && lane >= HALO && lane < p.segw + HALO && x < p.W;
       float* op = p.out + (long long)ti.b * p.oB + x;  // 32-bit offsets from here (host checks the extents)
       const float* rp = p.residual ? p.residual + (long long)ti.b * p.oB + x : nullptr;
       const float* mp = p.out_mul ? p.out_mul + (long long)ti.b * p.omB + x : nullptr;
-      float Pa[TZ][CW], Pb[TZ][CW];  // partial sums of output rows y_in-1 and y_in
+      constexpr int PW = TAPS == 9 ? CW : 1;
+      float Pa[TZ][PW], Pb[TZ][PW];  // partial sums of output rows y_in-1 and y_in (k3 only)
 #pragma unroll
       for (int zo = 0; zo < TZ; ++zo)
 #pragma unroll
-        for (int c = 0; c < CW; ++c) Pa[zo][c] = Pb[zo][c] = 0.f;
+        for (int c = 0; c < PW; ++c) Pa[zo][c] = Pb[zo][c] = 0.f;
       for (int step = 0; step < nsteps; ++step) {
-        const int yin = ya - 1 + step;
+        const int yin = ya - HALO + step;
         const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
         tc_mbar_wait(&accf[ab], aph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -420,6 +424,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 #pragma unroll
         for (int zo = 0; zo < TZ; ++zo) {
           const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + zo * NB + ch0;
+          if (TAPS == 1) {
+#pragma unroll
+            for (int c4 = 0; c4 < CW; c4 += 12) {
+              float d0[4], d1[4], d2[4];
+              tc_ld4x3(tb + c4, tb + (c4 + 4 < CW ? c4 + 4 : c4), tb + (c4 + 8 < CW ? c4 + 8 : c4), d0, d1, d2);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                fin[zo][c4 + j] = d0[j];
+                if (c4 + 4 < CW) fin[zo][(c4 + 4 < CW ? c4 + 4 : 0) + j] = d1[j];
+                if (c4 + 8 < CW) fin[zo][(c4 + 8 < CW ? c4 + 8 : 0) + j] = d2[j];
+              }
+            }
+          } else {
 #pragma unroll
           for (int c4 = 0; c4 < CW; c4 += 4) {
             float t0[4];
@@ -445,12 +462,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
               Pb[zo][c4 + j] = t0[j];
             }
           }
+          }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) tc_mbar_arrive(&acce[ab]);
         ++ai;
-        const int yo = yin - 1;
+        const int yo = yin - HALO;
         if (lane_ok && yo >= ya && yo < yb) {
 #pragma unroll
           for (int zo = 0; zo < TZ; ++zo) {
@@ -498,7 +516,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 typedef void (*tc_fn_t)(const TcK);
 static long long tc_launches = 0;
 
-static tc_fn_t tc_pick(int COT, int TZ, int KD, bool gwc) {
+static tc_fn_t tc_pick(int COT, int TZ, int KD, bool gwc, int taps) {
+  if (taps == 1) {  // pointwise: one channel tile holds the whole Cout (<= 64)
+    if (gwc || TZ != 1 || KD != 1) return nullptr;
+    switch (COT) {
+      case 8: return tc_conv_kernel<8, 1, 1, false, 1>;
+      case 16: return tc_conv_kernel<16, 1, 1, false, 1>;
+      case 24: return tc_conv_kernel<24, 1, 1, false, 1>;
+      case 32: return tc_conv_kernel<32, 1, 1, false, 1>;
+      case 40: return tc_conv_kernel<40, 1, 1, false, 1>;
+      case 48: return tc_conv_kernel<48, 1, 1, false, 1>;
+      case 64: return tc_conv_kernel<64, 1, 1, false, 1>;
+      default: return nullptr;
+    }
+  }
   if (gwc) return (COT == 8 && TZ == 3 && KD == 3) ? (tc_fn_t)tc_conv_kernel<8, 3, 3, true> : nullptr;
   if (KD == 3) {
     if (COT == 8 && TZ == 3) return tc_conv_kernel<8, 3, 3, false>;
@@ -513,8 +544,10 @@ static tc_fn_t tc_pick(int COT, int TZ, int KD, bool gwc) {
 }
 
 bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
-  if (d->transposed || d->stride != 1 || d->kh != 3 || d->kw != 3 || d->ph != 1 || d->pw != 1) return false;
-  if (!(d->kd == 1 || d->kd == 3) || d->pd != d->kd / 2) return false;
+  if (d->transposed || d->stride != 1) return false;
+  const bool k3 = d->kh == 3 && d->kw == 3 && d->ph == 1 && d->pw == 1 && (d->kd == 1 || d->kd == 3) && d->pd == d->kd / 2;
+  const bool k1 = d->kh == 1 && d->kw == 1 && d->kd == 1 && d->ph == 0 && d->pw == 0 && d->pd == 0;
+  if (!k3 && !k1) return false;
   if (d->pixel_shuffle || d->in_mul) return false;
   if (d->Cin < 8 || num_sms <= 0) return false;
   // the kernel addresses one batch item with 32-bit element offsets
@@ -529,8 +562,12 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
       if (d->src[i].C % 8) return false;
   }
   const int CoutPad8 = round_up(d->Cout, 8);
+  const int taps = k1 ? 1 : 9;
   int COT;
-  if (CoutPad8 <= 24) {
+  if (k1) {
+    COT = CoutPad8 > 48 ? 64 : CoutPad8;  // 8..48 in steps of 8, or 64
+    if (CoutPad8 > 64) return false;
+  } else if (CoutPad8 <= 24) {
     COT = CoutPad8;
   } else {
     const int w24 = ceil_div(CoutPad8, 24) * 24, w16 = ceil_div(CoutPad8, 16) * 16;
@@ -538,22 +575,24 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
   }
   if (gwc && COT != 8) return false;
   plan->COT = COT;
+  plan->taps = taps;
   plan->ncot = ceil_div(d->Cout, COT);
   plan->KD = d->kd;
   plan->TZ = (d->kd == 3 && COT == 8) ? 3 : 1;
   plan->gwc = gwc;
   plan->npass = npass;
-  if (!tc_pick(COT, plan->TZ, plan->KD, gwc)) return false;
-  const int NB = 9 * COT, NROW = plan->TZ + plan->KD - 1, CGS = NROW == 1 ? 4 : 1;
+  if (!tc_pick(COT, plan->TZ, plan->KD, gwc, taps)) return false;
+  const int NB = taps * COT, NROW = plan->TZ + plan->KD - 1, CGS = NROW == 1 ? 4 : 1;
   const int ncg = ceil_div(d->Cin, 8);
   const size_t wbytes = ((size_t)ncg * plan->KD * 2 * NB * 32 + 127) & ~(size_t)127;
   const size_t stage = (size_t)CGS * NROW * 8192;
-  const size_t limit = 227 * 1024 - 512;
+  const size_t limit = 227 * 1024 - 1024;
   if (wbytes + 2 * stage > limit) return false;
   int ns = (int)((limit - wbytes) / stage);
   plan->nstages = ns > 4 ? 4 : ns;
-  plan->smem = wbytes + plan->nstages * stage + 512;
-  plan->nseg = ceil_div(d->Wout, 30);
+  plan->smem = wbytes + plan->nstages * stage + 1024;
+  const int segmax = k1 ? 32 : 30;
+  plan->nseg = ceil_div(d->Wout, segmax);
   plan->segw = ceil_div(d->Wout, plan->nseg);
   const int ztiles = ceil_div(d->Dout, plan->TZ);
   const int sms = num_sms / plan->ncot > 0 ? num_sms / plan->ncot : 1;
@@ -563,7 +602,7 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
     if (ceil_div(d->Hout, rows) != ys) continue;
     const long long items = (long long)d->B * ztiles * ceil_div(plan->nseg * ys, 4);
     const long long waves = (items + sms - 1) / sms;
-    const double cost = (double)waves * (rows + 2) + 1.0;  // +1: per-item pipeline fill
+    const double cost = (double)waves * (rows + (k1 ? 0 : 2)) + 1.0;  // +1: per-item pipeline fill
     if (cost < best) {
       best = cost;
       plan->ysplit = ys;
@@ -588,7 +627,7 @@ int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
   k.W = d->Wout;
   k.Cout = d->Cout;
   k.CinPad = round_up(d->Cin, 8);
-  k.CoutPad = (int)(esm_packed_weight_elems(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0) / ((long long)d->kd * 9 * k.CinPad));
+  k.CoutPad = (int)(esm_packed_weight_elems(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0) / ((long long)d->kd * d->kh * d->kw * k.CinPad));
   k.weight = d->weight;
   k.scale = d->scale;
   k.shift = d->shift;
@@ -615,7 +654,7 @@ int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
   k.ctas_per_cot = plan.ctas_per_cot;
   k.nstages = plan.nstages;
   k.npass = plan.npass;
-  tc_fn_t fn = tc_pick(plan.COT, plan.TZ, plan.KD, plan.gwc != 0);
+  tc_fn_t fn = tc_pick(plan.COT, plan.TZ, plan.KD, plan.gwc != 0, plan.taps);
   ESM_REQUIRE(fn, "conv(tc): no kernel for COT=%d TZ=%d KD=%d", plan.COT, plan.TZ, plan.KD);
   // one limit for every launch of a function: the attribute is per function, not per launch, and graph
   // replays (and profilers re-launching graph nodes) must find it at least as large as any node's request

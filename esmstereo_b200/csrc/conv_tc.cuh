@@ -6,7 +6,8 @@
 namespace esm {
 
 struct TcPlan {
-  int COT;           // output channels per CTA (8, 16 or 24): N = 9*COT columns per accumulator row
+  int COT;           // output channels per CTA (k3: 8, 16 or 24; k1: up to 64): N = taps*COT accumulator columns
+  int taps;          // 9 (k3 s1 p1 in h,w) or 1 (pointwise)
   int TZ;            // output planes per work item (3 for COT=8 in 3D, else 1)
   int KD;            // 1 (2D) or 3
   int gwc;           // input voxels are group-wise correlations

@@ -365,3 +365,47 @@ def test_gwc_fused_tensor_core(H, W, D, tc_forced):
     got = ops.conv([L.cuda(), R.cuda()], gpu_pack(p, 1, 1, False), "gelu", gwc_disp=D)
     assert tc_forced() == n0 + 1
     assert rel(got, want) < 2e-5
+
+
+TC_K1_CASES = [
+    # name, nd, cin, cout, in_shape, batch
+    ("tck1_16_64", 2, 16, 64, (37, 100), 1),
+    ("tck1_96_32", 2, 96, 32, (20, 70), 2),
+    ("tck1_112_32", 2, 112, 32, (9, 33), 1),
+    ("tck1_32_16", 2, 32, 16, (12, 312), 1),
+    ("tck1_64_40", 2, 64, 40, (7, 19), 1),
+    ("tck1_3d_48_24", 3, 48, 24, (4, 6, 18), 1),
+]
+
+
+@pytest.mark.parametrize("case", TC_K1_CASES, ids=[c[0] for c in TC_K1_CASES])
+def test_conv_tensor_core_pointwise(case, tc_forced):
+    name, nd, cin, cout, sp, B = case
+    ops = _ops()
+    p = make_layer(cin, cout, 1, nd, seed=len(name))
+    x = rnd(B, cin, *sp, seed=3)
+    want = ref_conv(x, p, 1, 0, False, "gelu", nd)
+    n0 = tc_forced()
+    got = ops.conv(x.cuda(), gpu_pack(p, 1, 0, False), "gelu")
+    assert tc_forced() == n0 + 1, "layer did not take the tensor-core path"
+    assert rel(got, want) < 2e-5, name
+
+
+def test_conv_tensor_core_pointwise_concat(tc_forced):
+    """aggregation.agg_0.0: cat(cropped deconv output, skip) -> k1 conv, on the tensor-core path."""
+    ops = _ops()
+    a_full = rnd(1, 40, 4, 6, 10, seed=1)
+    a = a_full[:, :, :3, :5, :9]
+    b = rnd(1, 40, 3, 5, 9, seed=2)
+    p = make_layer(80, 40, 1, 3, seed=5)
+    want = ref_conv(torch.cat((a, b), 1), p, 1, 0, False, "gelu", 3)
+    n0 = tc_forced()
+    got = ops.conv([a_full.cuda()[:, :, :3, :5, :9], b.cuda()], gpu_pack(p, 1, 0, False), "gelu")
+    assert tc_forced() == n0 + 1
+    assert rel(got, want) < 2e-5
+    srcs = [rnd(2, 32, 6, 20, seed=7), rnd(2, 32, 6, 20, seed=8), rnd(2, 96, 6, 20, seed=9)]
+    p = make_layer(160, 32, 1, 2, seed=6)
+    want = ref_conv(torch.cat(srcs, 1), p, 1, 0, False, "gelu", 2)
+    got = ops.conv([s.cuda() for s in srcs], gpu_pack(p, 1, 0, False), "gelu")
+    assert tc_forced() == n0 + 2
+    assert rel(got, want) < 2e-5
