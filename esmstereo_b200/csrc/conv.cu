@@ -265,8 +265,8 @@ static encode_tiled_fn get_encoder() {
 }
 
 // fp32 tensor map of rank `rank` (innermost first); strides in elements for dims 1..rank-1
-static bool encode_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const long long* strides_elems,
-                       const int* box) {
+bool encode_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const long long* strides_elems,
+                const int* box) {
   encode_tiled_fn enc = get_encoder();
   if (!enc) return false;
   cuuint64_t gd[5], gs[4];

@@ -28,6 +28,7 @@
 // operand tiles.  Three mbarrier pipelines: operand ring full/empty, accumulator full/empty.
 #include "conv_tc.cuh"
 
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -50,12 +51,20 @@ struct TcK {
   long long oB, oC, oD, oH;
   int nseg, segw, rows, nstrips, groups, ztiles;
   int items_per_cot, ctas_per_cot, nstages, npass;
+  int use_tma, rstages;  // inputs staged by TMA into a raw fp32 ring of `rstages` slots (else per-thread loads)
+};
+
+// 5D (W, H, D, C, B) fp32 maps of the sources; box (36 | 40, 1, NROW, 8 | 16, 1)
+struct __align__(64) TcMaps {
+  CUtensorMap src[3];
 };
 
 constexpr int TC_NTW = 8;                               // operand-producer warps
 constexpr int TC_NEW = 8;                               // epilogue warps: 2 per TMEM lane quadrant
 constexpr int TC_MMA_WARP = TC_NEW;                     // warp index of the MMA issuer
-constexpr int TC_THREADS = 32 * (TC_NEW + 1 + TC_NTW);  // epilogue + MMA + producers
+constexpr int TC_TMA_WARP = TC_NEW + 1 + TC_NTW;        // warp index of the TMA issuer
+constexpr int TC_THREADS = 32 * (TC_NEW + 2 + TC_NTW);  // epilogue + MMA + producers + TMA (ptxas rounds to 640: 96 regs)
+constexpr int TC_RAWW = 36, TC_RAWR = 40;               // staged row widths: 32 columns + alignment slack (+ disparity window)
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
@@ -64,14 +73,36 @@ __device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_tma_5d(uint32_t dst, const CUtensorMap* map, int x0, int x1, int x2, int x3, int x4, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(tc_smem_u32(bar)), "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(x4)
+      : "memory");
+}
+// Spin on an mbarrier phase.  A watchdog turns a pipeline deadlock (a bug) into a trapped launch with a
+// message instead of a hung GPU: ~2^26 failed polls is seconds, far beyond any legitimate wait here.
+__device__ __noinline__ void tc_deadlock(int tag, uint32_t parity, bool fatal) {
+  if ((threadIdx.x & 31) == 0 || fatal)
+    printf("esm tc_conv: deadlock in block %d warp %d lane %d waiting on barrier tag %d parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
+           (int)(threadIdx.x & 31), tag, parity);
+  if (fatal) __trap();
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   const uint32_t addr = tc_smem_u32(bar);
-  uint32_t done;
+  uint32_t done, polls = 0;
   do {
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(done)
                  : "r"(addr), "r"(parity)
                  : "memory");
+    if (!done) {
+      ++polls;
+      if (polls == (1u << 22) && blockIdx.x == 0) tc_deadlock(tag, parity, false);  // every stuck waiter of block 0 reports
+      if (polls > (1u << 26)) tc_deadlock(tag, parity, true);
+    }
   } while (!done);
 }
 // K-major, no-swizzle UMMA shared-memory descriptor: 8-row x 16-byte core matrices, rows 16 bytes
@@ -131,7 +162,7 @@ __device__ __forceinline__ TcItem tc_decode(const TcK& p, int item, int TZ) {
 // TAPS = 9: k3 s1 p1 in (h, w) as described above.  TAPS = 1: pointwise (k1) convolution -- the same
 // pipeline without halos, shuffles or the rolling window (N = COT, 32 output columns per strip).
 template <int COT, int TZ, int KD, bool GWC, int TAPS = 9>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcK p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcK p, const __grid_constant__ TcMaps maps) {
   constexpr int NB = TAPS * COT;               // accumulator columns per (z_o, y_in) row tile
   constexpr int HALO = TAPS == 9 ? 1 : 0;
   constexpr int NROW = TZ + KD - 1;            // input planes per stage
@@ -142,6 +173,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   constexpr int WSLAB = NB * 32;               // one (cg, kd, hi|lo) B operand: [2][NB][4] floats
   constexpr int ACC_COLS = 256;                // TMEM columns per accumulator buffer (TZ*NB <= 256)
   constexpr int CW = COT / 2;                  // output channels per epilogue warp
+  // raw ring slot: plain [strip][cgl][8 ch][NROW][36]; GWC [strip]{L [16 ch][36], R [16 ch][40]}
+  constexpr int RAW_Q = GWC ? 16 * (TC_RAWW + TC_RAWR) : CGS * 8 * NROW * TC_RAWW;  // floats per strip
+  constexpr int RAW_BYTES = 4 * RAW_Q * 4;
   static_assert(TZ * NB <= ACC_COLS, "accumulator does not fit");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -150,11 +184,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   const uint32_t wbytes = (uint32_t)ncg * KD * 2 * WSLAB;
   uint8_t* s_w = smem;
   uint8_t* s_stage = smem + ((wbytes + 127u) & ~127u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_stage + (size_t)NS * STAGE_BYTES);
+  const int RS = p.use_tma ? p.rstages : 0;
+  float* s_raw = reinterpret_cast<float*>(s_stage + (size_t)NS * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_stage + (size_t)NS * STAGE_BYTES + (size_t)RS * RAW_BYTES);
   uint64_t* empty = full + NS;
   uint64_t* accf = empty + NS;
   uint64_t* acce = accf + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + 2);
+  uint64_t* rfull = acce + 2;
+  uint64_t* rempty = rfull + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + 4);
   float* s_aff = reinterpret_cast<float*>(tmem_slot + 2);  // [2][COT] scale, shift of this channel tile
   const int cot = blockIdx.x / p.ctas_per_cot;
   const int cta = blockIdx.x % p.ctas_per_cot;
@@ -168,6 +206,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     for (int i = 0; i < 2; ++i) {
       tc_mbar_init(&accf[i], 1);
       tc_mbar_init(&acce[i], TC_NEW);
+    }
+    for (int i = 0; i < RS; ++i) {
+      tc_mbar_init(&rfull[i], 1);
+      tc_mbar_init(&rempty[i], TC_NTW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -221,7 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  if (warp > TC_MMA_WARP) {
+  if (warp > TC_MMA_WARP && warp < TC_TMA_WARP) {
     // ============================ operand producers ============================
     const int tw = warp - TC_MMA_WARP - 1;
     const int q = (tw >> 1) & 3;   // strip (= TMEM lane quadrant) this warp feeds
@@ -307,7 +349,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     };
     auto store_stage = [&](const float (&v)[TPW][4]) {
       const uint32_t st = it % NS, ph = (it / NS) & 1;
-      tc_mbar_wait(&empty[st], ph ^ 1);
+      tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
       uint8_t* sb = s_stage + (size_t)st * STAGE_BYTES + khalf * 2048 + m * 16;
 #pragma unroll
       for (int j = 0; j < TPW; ++j) {
@@ -330,19 +372,140 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       if (lane == 0) tc_mbar_arrive(&full[st]);
       ++it;
     };
-    // two register buffers, loop unrolled by two: the loads of stage i+1 are in flight while stage i is
-    // converted and stored (no register copies, so nothing waits on a load before its own store)
-    float va[TPW][4], vb[TPW][4];
-    enter_item();
-    if (item < p.items_per_cot) load(va);
-    while (item < p.items_per_cot) {
-      advance();
-      if (item < p.items_per_cot) load(vb);
-      store_stage(va);
-      if (item >= p.items_per_cot) break;
-      advance();
+    if (p.use_tma) {
+      // ---- inputs arrive through the raw ring (TMA, zero-filled out of bounds): LDS -> split -> UMMA tiles ----
+      enter_item();
+      int sh = 0, cR = 0;
+      auto item_consts = [&]() {
+        const int xs = x - lane;  // first column of this warp's strip (x was set by enter_item)
+        sh = xs - (xs & ~3);
+        if (GWC) {
+          const int xr = xs - (z0 - KD / 2 + NROW - 1);
+          cR = xr - (xr & ~3) + NROW - 1;
+        }
+      };
+      item_consts();
+      while (item < p.items_per_cot) {
+        const uint32_t rs = it % RS, rph = (it / RS) & 1;
+        const uint32_t st = it % NS, ph = (it / NS) & 1;
+        tc_mbar_wait(&rfull[rs], rph, 100 + (int)rs);
+        tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
+        const float* raw = s_raw + (size_t)rs * (RAW_BYTES / 4) + q * RAW_Q;
+        float v[TPW][4];
+        if (GWC) {
+          const float* rl = raw + (khalf * 8) * TC_RAWW + lane + sh;
+          const float* rr = raw + 16 * TC_RAWW + (khalf * 8) * TC_RAWR + lane + cR;
+          float l[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) l[c] = rl[c * TC_RAWW];
+#pragma unroll
+          for (int r = 0; r < NROW; ++r) {
+            const bool okd = (unsigned)(z0 + r - KD / 2) < (unsigned)p.D;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float r0 = rr[(2 * g) * TC_RAWR - r], r1 = rr[(2 * g + 1) * TC_RAWR - r];
+              const float c2 = __fmul_rn(__fadd_rn(__fmul_rn(l[2 * g], r0), __fmul_rn(l[2 * g + 1], r1)), 0.5f);
+              v[r][g] = okd ? c2 : 0.f;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < TPW; ++j) {
+            const int cgl = j / NROW, r = j % NROW;
+            const float* rp = raw + ((cgl * 8 + khalf * 4) * NROW + r) * TC_RAWW + lane + sh;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[j][c] = rp[c * NROW * TC_RAWW];
+          }
+        }
+        uint8_t* sb = s_stage + (size_t)st * STAGE_BYTES + khalf * 2048 + m * 16;
+#pragma unroll
+        for (int j = 0; j < TPW; ++j) {
+          float4 hi, lo;
+          hi.x = tc_rna(v[j][0]);
+          hi.y = tc_rna(v[j][1]);
+          hi.z = tc_rna(v[j][2]);
+          hi.w = tc_rna(v[j][3]);
+          *reinterpret_cast<float4*>(sb + j * ROW_BYTES) = hi;
+          if (p.npass == 3) {
+            lo.x = tc_rna(v[j][0] - hi.x);
+            lo.y = tc_rna(v[j][1] - hi.y);
+            lo.z = tc_rna(v[j][2] - hi.z);
+            lo.w = tc_rna(v[j][3] - hi.w);
+            *reinterpret_cast<float4*>(sb + j * ROW_BYTES + 4096) = lo;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) {
+          tc_mbar_arrive(&full[st]);
+          tc_mbar_arrive(&rempty[rs]);
+        }
+        ++it;
+        const int prev = item;
+        advance();
+        if (item != prev) item_consts();
+      }
+    } else {
+      // two register buffers, loop unrolled by two: the loads of stage i+1 are in flight while stage i is
+      // converted and stored (no register copies, so nothing waits on a load before its own store)
+      float va[TPW][4], vb[TPW][4];
+      enter_item();
       if (item < p.items_per_cot) load(va);
-      store_stage(vb);
+      while (item < p.items_per_cot) {
+        advance();
+        if (item < p.items_per_cot) load(vb);
+        store_stage(va);
+        if (item >= p.items_per_cot) break;
+        advance();
+        if (item < p.items_per_cot) load(va);
+        store_stage(vb);
+      }
+    }
+  } else if (warp == TC_TMA_WARP) {
+    // ============================ TMA issuer ============================
+    if (p.use_tma && lane == 0) {
+      const uint32_t raw_addr = tc_smem_u32(s_raw);
+      uint32_t it = 0;
+      for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
+        const TcItem ti = tc_decode(p, item, TZ);
+        int xs[4], y0[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int strip = ti.grp * 4 + q;
+          xs[q] = (strip % p.nseg) * p.segw - HALO;
+          y0[q] = strip < p.nstrips ? (strip / p.nseg) * p.rows - HALO : -(1 << 20);  // dummy strips: all rows out of range
+        }
+        for (int step = 0; step < nsteps; ++step) {
+          for (int cgb = 0; cgb < ncg; cgb += CGS) {
+            const uint32_t rs = it % RS, rph = (it / RS) & 1;
+            tc_mbar_wait(&rempty[rs], rph ^ 1, 300 + (int)rs);
+            tc_mbar_expect_tx(&rfull[rs], RAW_BYTES);
+            const uint32_t slot = raw_addr + rs * RAW_BYTES;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int y = y0[q] + step;
+              if (GWC) {
+                const int xr = xs[q] - (ti.z0 - KD / 2 + NROW - 1);
+                tc_tma_5d(slot + q * RAW_Q * 4, &maps.src[0], xs[q] & ~3, y, 0, cgb * 16, ti.b, &rfull[rs]);
+                tc_tma_5d(slot + (q * RAW_Q + 16 * TC_RAWW) * 4, &maps.src[1], xr & ~3, y, 0, cgb * 16, ti.b, &rfull[rs]);
+              } else {
+#pragma unroll
+                for (int cgl = 0; cgl < CGS; ++cgl) {
+                  int rel = (cgb + cgl) * 8, k = 0;
+                  while (k < p.nsrc - 1 && rel >= p.src[k].C) {
+                    rel -= p.src[k].C;
+                    ++k;
+                  }
+                  // past the last group: a channel coordinate beyond the source -> the box is zero-filled
+                  tc_tma_5d(slot + (q * RAW_Q + cgl * 8 * NROW * TC_RAWW) * 4, &maps.src[k], xs[q] & ~3, y, ti.z0 - KD / 2, rel, ti.b,
+                            &rfull[rs]);
+                }
+              }
+            }
+            ++it;
+          }
+        }
+      }
     }
   } else if (warp == TC_MMA_WARP) {
     // ============================ MMA issuer ============================
@@ -354,11 +517,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
         for (int step = 0; step < nsteps; ++step) {
           const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
-          tc_mbar_wait(&acce[ab], aph ^ 1);  // epilogue has drained this accumulator buffer
+          tc_mbar_wait(&acce[ab], aph ^ 1, 400 + (int)ab);  // epilogue has drained this accumulator buffer
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           for (int cgb = 0; cgb < ncg; cgb += CGS) {
             const uint32_t st = it % NS, ph = (it / NS) & 1;
-            tc_mbar_wait(&full[st], ph);
+            tc_mbar_wait(&full[st], ph, 500 + (int)st);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int cgl = 0; cgl < CGS; ++cgl) {
@@ -418,7 +581,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       for (int step = 0; step < nsteps; ++step) {
         const int yin = ya - HALO + step;
         const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
-        tc_mbar_wait(&accf[ab], aph);
+        tc_mbar_wait(&accf[ab], aph, 600 + (int)ab);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float fin[TZ][CW];
 #pragma unroll
@@ -513,7 +676,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
-typedef void (*tc_fn_t)(const TcK);
+typedef void (*tc_fn_t)(const TcK, const TcMaps);
 static long long tc_launches = 0;
 
 static tc_fn_t tc_pick(int COT, int TZ, int KD, bool gwc, int taps) {
@@ -591,6 +754,17 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
   int ns = (int)((limit - wbytes) / stage);
   plan->nstages = ns > 4 ? 4 : ns;
   plan->smem = wbytes + plan->nstages * stage + 1024;
+  // TMA-staged variant: raw fp32 ring (2..4 slots) + a shallower operand ring (2..3 slots)
+  const size_t raw = gwc ? 4 * 16 * (TC_RAWW + TC_RAWR) * 4 : (size_t)CGS * NROW * 8 * TC_RAWW * 4 * 4;
+  plan->rstages = 0;
+  if (wbytes + 2 * stage + 2 * raw <= limit) {
+    int nst = 2, rst = (int)((limit - wbytes - 2 * stage) / raw);
+    if (rst > 4) rst = 4;
+    if (wbytes + 3 * stage + rst * raw <= limit) nst = 3;
+    plan->nstages_tma = nst;
+    plan->rstages = rst;
+    plan->smem_tma = wbytes + nst * stage + rst * raw + 1024;
+  }
   const int segmax = k1 ? 32 : 30;
   plan->nseg = ceil_div(d->Wout, segmax);
   plan->segw = ceil_div(d->Wout, plan->nseg);
@@ -656,11 +830,35 @@ int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
   k.npass = plan.npass;
   tc_fn_t fn = tc_pick(plan.COT, plan.TZ, plan.KD, plan.gwc != 0, plan.taps);
   ESM_REQUIRE(fn, "conv(tc): no kernel for COT=%d TZ=%d KD=%d", plan.COT, plan.TZ, plan.KD);
+  // TMA staging needs 16-byte aligned bases and pitches (tensors made by this library have them; odd crops do not)
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const bool no_tma = getenv("ESM_TC_NO_TMA") != nullptr;  // tests: force the per-thread load path
+  bool use_tma = plan.rstages >= 2 && !no_tma;
+  const int NROW = plan.TZ + plan.KD - 1;
+  for (int i = 0; i < d->nsrc && use_tma; ++i) {
+    const esm_src_t& sv = d->src[i];
+    const bool has_d = d->Din > 1 && !plan.gwc;
+    const long long sD = has_d ? sv.sD : sv.sH * d->Hin;
+    const long long sB = (d->B > 1 || sv.sB % 4 == 0) ? sv.sB : sv.sC * sv.C;
+    if ((reinterpret_cast<uintptr_t>(sv.ptr) & 15) || sv.sH % 4 || sv.sC % 4 || sD % 4 || sB % 4) {
+      use_tma = false;
+      break;
+    }
+    const long long dims[5] = {d->Win, d->Hin, has_d ? d->Din : 1, sv.C, d->B};
+    const long long str[4] = {sv.sH, sD, sv.sC, sB};
+    const int box[5] = {plan.gwc && i == 1 ? TC_RAWR : TC_RAWW, 1, plan.gwc ? 1 : NROW, plan.gwc ? 16 : 8, 1};
+    use_tma = encode_map(&maps.src[i], sv.ptr, 5, dims, str, box);
+  }
+  k.use_tma = use_tma;
+  k.rstages = use_tma ? plan.rstages : 0;
+  k.nstages = use_tma ? plan.nstages_tma : plan.nstages;
+  const size_t smem = use_tma ? plan.smem_tma : plan.smem;
   // one limit for every launch of a function: the attribute is per function, not per launch, and graph
   // replays (and profilers re-launching graph nodes) must find it at least as large as any node's request
   if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return check_launch("conv(tc, cudaFuncSetAttribute)");
-  fn<<<(unsigned)(plan.ncot * plan.ctas_per_cot), TC_THREADS, plan.smem, st>>>(k);
+  fn<<<(unsigned)(plan.ncot * plan.ctas_per_cot), TC_THREADS, smem, st>>>(k, maps);
   ++tc_launches;
   return check_launch("conv(tc)");
 }
