@@ -28,7 +28,6 @@
 // operand tiles.  Three mbarrier pipelines: operand ring full/empty, accumulator full/empty.
 #include "conv_tc.cuh"
 
-#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -51,21 +50,12 @@ struct TcK {
   long long oB, oC, oD, oH;
   int nseg, segw, rows, nstrips, groups, ztiles;
   int items_per_cot, ctas_per_cot, nstages, npass;
-  int fast_gelu;         // GELU through tc_gelu() (erf to 1.5e-7) instead of erff(): ESM_TC_GELU=1
-  int use_tma, rstages;  // inputs staged by TMA into a raw fp32 ring of `rstages` slots (else per-thread loads)
 };
 
-// 5D (W, H, D, C, B) fp32 maps of the sources; box (36 | 40, 1, NROW, 8 | 16, 1)
-struct __align__(64) TcMaps {
-  CUtensorMap src[3];
-};
-
-constexpr int TC_NEW = 12;                              // epilogue warps: 3 per TMEM lane quadrant
+constexpr int TC_NTW = 8;                               // operand-producer warps
+constexpr int TC_NEW = 8;                               // epilogue warps: 2 per TMEM lane quadrant
 constexpr int TC_MMA_WARP = TC_NEW;                     // warp index of the MMA issuer
-constexpr int TC_NTW = 4;                               // operand-producer warps: one per strip
-constexpr int TC_TMA_WARP = TC_NEW + 1 + TC_NTW;        // warp index of the TMA issuer
-constexpr int TC_THREADS = 32 * (TC_NEW + 2 + TC_NTW);  // 576 (ptxas sizes registers for 640: 96 per thread)
-constexpr int TC_RAWW = 36, TC_RAWR = 40;               // staged row widths: 32 columns + alignment slack (+ disparity window)
+constexpr int TC_THREADS = 32 * (TC_NEW + 1 + TC_NTW);  // epilogue + MMA + producers
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
@@ -74,30 +64,14 @@ __device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tc_tma_5d(uint32_t dst, const CUtensorMap* map, int x0, int x1, int x2, int x3, int x4, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(tc_smem_u32(bar)), "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(x4)
-      : "memory");
-}
 // Spin on an mbarrier phase.  A watchdog turns a pipeline deadlock (a bug) into a trapped launch with a
-// message instead of a hung GPU: ~2^26 failed polls is seconds, far beyond any legitimate wait here.
-__device__ __noinline__ void tc_deadlock(int tag, uint32_t parity, bool fatal) {
-  if ((threadIdx.x & 31) == 0 || fatal)
-    printf("esm tc_conv: deadlock in block %d warp %d lane %d waiting on barrier tag %d parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
-           (int)(threadIdx.x & 31), tag, parity);
-  if (fatal) __trap();
+// message instead of a hung GPU: 2^26 failed polls is seconds, far beyond any legitimate wait here.
+__device__ __noinline__ void tc_deadlock(int tag, uint32_t parity) {
+  printf("esm tc_conv: deadlock in block %d warp %d lane %d waiting on barrier %d parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
+         (int)(threadIdx.x & 31), tag, parity);
+  __trap();
 }
-#ifdef TC_PROFILE
-__device__ long long tc_prof_wait[8];  // cycles spent waiting, by barrier class (tag / 100)
-#endif
 __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
-#ifdef TC_PROFILE
-  const long long t_begin = clock64();
-#endif
   const uint32_t addr = tc_smem_u32(bar);
   uint32_t done, polls = 0;
   do {
@@ -105,15 +79,8 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity, int
                  : "=r"(done)
                  : "r"(addr), "r"(parity)
                  : "memory");
-    if (!done) {
-      ++polls;
-      if (polls == (1u << 22) && blockIdx.x == 0) tc_deadlock(tag, parity, false);  // every stuck waiter of block 0 reports
-      if (polls > (1u << 26)) tc_deadlock(tag, parity, true);
-    }
+    if (!done && ++polls > (1u << 26)) tc_deadlock(tag, parity);
   } while (!done);
-#ifdef TC_PROFILE
-  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long*)&tc_prof_wait[tag / 100], (unsigned long long)(clock64() - t_begin));
-#endif
 }
 // K-major, no-swizzle UMMA shared-memory descriptor: 8-row x 16-byte core matrices, rows 16 bytes
 // apart; LBO = byte distance between the two K halves, SBO = distance between 8-row groups.
@@ -131,46 +98,30 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
-// TMEM -> registers: this warp's lane quadrant, 16 / 4 consecutive columns.  Asynchronous: tc_ld_wait()
-// before the first use (all three are volatile with a memory clobber, so they keep their order).
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* r) {
-  uint32_t u[16];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
-                 "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-               : "r"(taddr)
-               : "memory");
+// Three 4-column loads of this warp's TMEM lane quadrant plus the wait, in ONE asm statement so that no
+// use of the results can be scheduled ahead of tcgen05.wait::ld.
+__device__ __forceinline__ void tc_ld4x3(uint32_t ta, uint32_t tb, uint32_t tc, float (&a)[4], float (&b)[4], float (&c)[4]) {
+  uint32_t u[12];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%12];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4,%5,%6,%7}, [%13];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8,%9,%10,%11}, [%14];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+        "=r"(u[10]), "=r"(u[11])
+      : "r"(ta), "r"(tb), "r"(tc)
+      : "memory");
 #pragma unroll
-  for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+  for (int i = 0; i < 4; ++i) {
+    a[i] = __uint_as_float(u[i]);
+    b[i] = __uint_as_float(u[4 + i]);
+    c[i] = __uint_as_float(u[8 + i]);
+  }
 }
-__device__ __forceinline__ void tc_ld4(uint32_t taddr, float* r) {
-  uint32_t u[4];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]) : "r"(taddr) : "memory");
-#pragma unroll
-  for (int i = 0; i < 4; ++i) r[i] = __uint_as_float(u[i]);
-}
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tc_rna(float x) {  // round to nearest TF32 (low 13 mantissa bits zero)
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
-}
-
-// GELU for the tensor-core epilogue (instruction issue is what bounds these kernels; erff() costs ~27
-// instructions per value).  0.5*x*(1+erf(x/sqrt2)) with erf from Abramowitz & Stegun 7.1.26 evaluated in its
-// erfc form, 1+erf(u) = u<0 ? P(t)e^{-u^2} : 2 - P(t)e^{-u^2}, t = 1/(1+p|u|): no cancellation in the negative
-// tail, absolute error of erf <= 1.5e-7 (about one fp32 ulp of the 1+erf term).
-__device__ __forceinline__ float tc_gelu(float x) {
-  const float u = x * 0.70710678118654752440f;
-  const float au = fabsf(u);
-  const float t = __frcp_rn(fmaf(0.3275911f, au, 1.0f));
-  float pl = fmaf(1.061405429f, t, -1.453152027f);
-  pl = fmaf(pl, t, 1.421413741f);
-  pl = fmaf(pl, t, -0.284496736f);
-  pl = fmaf(pl, t, 0.254829592f);
-  const float e = pl * t * __expf(-au * au);   // erfc(|u|)
-  const float one_plus_erf = u < 0.f ? e : 2.0f - e;
-  return 0.5f * x * one_plus_erf;
 }
 
 struct TcItem {
@@ -188,7 +139,7 @@ __device__ __forceinline__ TcItem tc_decode(const TcK& p, int item, int TZ) {
 // TAPS = 9: k3 s1 p1 in (h, w) as described above.  TAPS = 1: pointwise (k1) convolution -- the same
 // pipeline without halos, shuffles or the rolling window (N = COT, 32 output columns per strip).
 template <int COT, int TZ, int KD, bool GWC, int TAPS = 9>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcK p, const __grid_constant__ TcMaps maps) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcK p) {
   constexpr int NB = TAPS * COT;               // accumulator columns per (z_o, y_in) row tile
   constexpr int HALO = TAPS == 9 ? 1 : 0;
   constexpr int NROW = TZ + KD - 1;            // input planes per stage
@@ -198,31 +149,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   constexpr int STAGE_BYTES = TPW * ROW_BYTES;
   constexpr int WSLAB = NB * 32;               // one (cg, kd, hi|lo) B operand: [2][NB][4] floats
   constexpr int ACC_COLS = 256;                // TMEM columns per accumulator buffer (TZ*NB <= 256)
-  constexpr int NU = TZ * (COT / 4);           // epilogue units (z_o, 4 channels) per strip, dealt to 3 warps
-  constexpr int UPW = (NU + 2) / 3;
-  // raw ring slot: plain [strip][cgl][8 ch][NROW][36]; GWC [strip]{L [16 ch][36], R [16 ch][40]}
-  constexpr int RAW_Q = GWC ? 16 * (TC_RAWW + TC_RAWR) : CGS * 8 * NROW * TC_RAWW;  // floats per strip
-  constexpr int RAW_BYTES = 4 * RAW_Q * 4;
+  constexpr int CW = COT / 2;                  // output channels per epilogue warp
   static_assert(TZ * NB <= ACC_COLS, "accumulator does not fit");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-#ifdef TC_PROFILE
-  const long long tc_t0 = clock64();
-#endif
   const int ncg = p.ncg;
   const int NS = p.nstages;
   const uint32_t wbytes = (uint32_t)ncg * KD * 2 * WSLAB;
   uint8_t* s_w = smem;
   uint8_t* s_stage = smem + ((wbytes + 127u) & ~127u);
-  const int RS = p.use_tma ? p.rstages : 0;
-  float* s_raw = reinterpret_cast<float*>(s_stage + (size_t)NS * STAGE_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_stage + (size_t)NS * STAGE_BYTES + (size_t)RS * RAW_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_stage + (size_t)NS * STAGE_BYTES);
   uint64_t* empty = full + NS;
   uint64_t* accf = empty + NS;
   uint64_t* acce = accf + 2;
-  uint64_t* rfull = acce + 2;
-  uint64_t* rempty = rfull + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + 2);
   float* s_aff = reinterpret_cast<float*>(tmem_slot + 2);  // [2][COT] scale, shift of this channel tile
   const int cot = blockIdx.x / p.ctas_per_cot;
   const int cta = blockIdx.x % p.ctas_per_cot;
@@ -237,10 +177,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       tc_mbar_init(&accf[i], 1);
       tc_mbar_init(&acce[i], TC_NEW);
     }
-    for (int i = 0; i < RS; ++i) {
-      tc_mbar_init(&rfull[i], 1);
-      tc_mbar_init(&rempty[i], TC_NTW);
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -253,7 +189,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     s_aff[tid] = (src && co < p.Cout) ? __ldg(src + co) : (tid < COT ? 1.f : 0.f);
   }
   // resident weights of this channel tile: split and laid out as UMMA B operands
-  // (row n = co*TAPS + kh*3+kw, K = 8 input channels of group cg)
+  // (row n = (kh*3+kw)*COT + co, K = 8 input channels of group cg)
   {
     const int total = ncg * KD * NB * 8;
     constexpr int U = 4;
@@ -275,7 +211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         w[u] = 0.f;
         if (idx < total && co < p.CoutPad && ci < p.CinPad)
           w[u] = __ldg(p.weight + ((long long)(kd * TAPS + tap2) * p.CinPad + ci) * p.CoutPad + co);
-        off[u] = (uint32_t)((cg * KD + kd) * 2) * WSLAB + (uint32_t)(k >> 2) * (NB * 16) + (uint32_t)(col * TAPS + tap2) * 16 + (k & 3) * 4;
+        off[u] = (uint32_t)((cg * KD + kd) * 2) * WSLAB + (uint32_t)(k >> 2) * (NB * 16) + (uint32_t)(tap2 * COT + col) * 16 + (k & 3) * 4;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -293,34 +229,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  if (warp > TC_MMA_WARP && warp < TC_TMA_WARP) {
+  if (warp > TC_MMA_WARP) {
     // ============================ operand producers ============================
-    // warp q feeds strip q (= TMEM lane quadrant q): 32 A rows x 8 channels of every row tile of a stage
-    const int q = warp - TC_MMA_WARP - 1;
-    const int m = q * 32 + lane;  // A row
+    const int tw = warp - TC_MMA_WARP - 1;
+    const int q = (tw >> 1) & 3;   // strip (= TMEM lane quadrant) this warp feeds
+    const int khalf = tw & 1;      // which 4 of the 8 channels of a group
+    const int m = q * 32 + lane;   // A row
     uint32_t it = 0;
-    int item = cta, step = 0, cgb = 0;  // cursor
+    // load cursor (item, step, cgb) and what it caches per item; offsets are 32-bit (host checks the extents)
+    int item = cta, step = 0, cgb = 0;
     const float* base[3] = {nullptr, nullptr, nullptr};
-    int z0 = 0, ya = 0, x = 0, sh = 0, cR = 0;
+    int z0 = 0, ya = 0, x = 0;
     bool strip_ok = false;
     auto enter_item = [&]() {
       if (item >= p.items_per_cot) return;
       const TcItem ti = tc_decode(p, item, TZ);
       const int strip = ti.grp * 4 + q;
       const int seg = strip % p.nseg, ys = strip / p.nseg;
-      const int xs = seg * p.segw - HALO;  // first input column of the strip
-      x = xs + lane;
+      x = seg * p.segw + lane - HALO;
       ya = ys * p.rows;
       z0 = ti.z0;
       strip_ok = strip < p.nstrips && x >= 0 && x < p.W && lane < p.segw + 2 * HALO;
-      sh = xs - (xs & ~3);  // column of the strip inside its 16-byte aligned TMA box
-      if (GWC) {
-        const int xr = xs - (z0 - KD / 2 + NROW - 1);
-        cR = xr - (xr & ~3) + NROW - 1;
-      }
 #pragma unroll
       for (int i = 0; i < 3; ++i)
         if (i < p.nsrc) base[i] = p.src[i].ptr + (long long)ti.b * p.src[i].sB;
+    };
+    auto load = [&](float (&v)[TPW][4]) {
+      const int y = ya - HALO + step;
+      const bool ok = strip_ok && (unsigned)y < (unsigned)p.H;
+      if (GWC) {
+        // v = 0.5 * (L[2g]*R[2g](x-d) + L[2g+1]*R[2g+1](x-d)), un-contracted (submodule.py:147); cpg == 2.
+        // All loads are issued first (predicated, never branched around) so that they overlap.
+        const int g0 = cgb * 8 + khalf * 4;
+        const int nch = 2 * min(4, p.Cin - g0);  // valid feature channels of this half group
+        const int sC = (int)p.src[0].sC;
+        const int off = (g0 * 2) * sC + y * (int)p.src[0].sH + x;
+        float l[8], rr[NROW][8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) l[c] = (ok && c < nch) ? __ldg(base[0] + (off + c * sC)) : 0.f;
+#pragma unroll
+        for (int r = 0; r < NROW; ++r) {
+          const int d = z0 + r - KD / 2;
+          const bool okd = ok && (unsigned)d < (unsigned)p.D && x >= d;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) rr[r][c] = (okd && c < nch) ? __ldg(base[1] + (off + c * sC - d)) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < NROW; ++r)
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            v[r][g] = __fmul_rn(__fadd_rn(__fmul_rn(l[2 * g], rr[r][2 * g]), __fmul_rn(l[2 * g + 1], rr[r][2 * g + 1])), 0.5f);
+      } else {
+#pragma unroll
+        for (int cgl = 0; cgl < CGS; ++cgl) {
+          int rel = (cgb + cgl) * 8 + khalf * 4, k = 0;
+          if (p.nsrc > 1) {
+            while (k < p.nsrc - 1 && rel >= p.src[k].C) {  // host guarantees 8-channel groups never straddle sources
+              rel -= p.src[k].C;
+              ++k;
+            }
+          }
+          const int sC = (int)p.src[k].sC, sD = (int)p.src[k].sD;
+          const int nch = p.src[k].C - rel;  // valid channels from `rel` on (<= 0 past the last group)
+          const float* bp = p.nsrc > 1 ? (k == 0 ? base[0] : k == 1 ? base[1] : base[2]) : base[0];
+          const int off = rel * sC + (z0 - KD / 2) * sD + y * (int)p.src[k].sH + x;
+#pragma unroll
+          for (int r = 0; r < NROW; ++r) {
+            const bool okz = ok && (unsigned)(z0 + r - KD / 2) < (unsigned)p.D;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[cgl * NROW + r][c] = (okz && c < nch) ? __ldg(bp + (off + r * sD + c * sC)) : 0.f;
+          }
+        }
+      }
     };
     auto advance = [&]() {
       cgb += CGS;
@@ -333,253 +313,96 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         }
       }
     };
-    // split 4 channels of row tile j, half `khalf`, and store them as hi / lo operand rows
-    auto put = [&](uint8_t* stage_base, int j, int khalf, const float (&v)[4]) {
-      uint8_t* sb = stage_base + j * ROW_BYTES + khalf * 2048 + m * 16;
-      float4 hi, lo;
-      hi.x = tc_rna(v[0]);
-      hi.y = tc_rna(v[1]);
-      hi.z = tc_rna(v[2]);
-      hi.w = tc_rna(v[3]);
-      *reinterpret_cast<float4*>(sb) = hi;
-      if (p.npass == 3) {
-        lo.x = tc_rna(v[0] - hi.x);
-        lo.y = tc_rna(v[1] - hi.y);
-        lo.z = tc_rna(v[2] - hi.z);
-        lo.w = tc_rna(v[3] - hi.w);
-        *reinterpret_cast<float4*>(sb + 4096) = lo;
-      }
-    };
-    // un-contracted (fea1*fea2).mean(2) for 2 channels per group (submodule.py:147)
-    auto corr = [](float l0, float r0, float l1, float r1) { return __fmul_rn(__fadd_rn(__fmul_rn(l0, r0), __fmul_rn(l1, r1)), 0.5f); };
-    enter_item();
-    while (item < p.items_per_cot) {
+    auto store_stage = [&](const float (&v)[TPW][4]) {
       const uint32_t st = it % NS, ph = (it / NS) & 1;
-      uint8_t* stage_base = s_stage + (size_t)st * STAGE_BYTES;
-      if (p.use_tma) {
-        // ---- inputs arrive through the raw ring (TMA, zero-filled out of bounds): LDS -> split -> UMMA tiles ----
-        const uint32_t rs = it % RS, rph = (it / RS) & 1;
-        tc_mbar_wait(&rfull[rs], rph, 100 + (int)rs);
-        tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
-        const float* raw = s_raw + (size_t)rs * (RAW_BYTES / 4) + q * RAW_Q;
-        if (GWC) {
+      tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
+      uint8_t* sb = s_stage + (size_t)st * STAGE_BYTES + khalf * 2048 + m * 16;
 #pragma unroll
-          for (int khalf = 0; khalf < 2; ++khalf) {
-            const float* rl = raw + (khalf * 8) * TC_RAWW + lane + sh;
-            const float* rr = raw + 16 * TC_RAWW + (khalf * 8) * TC_RAWR + lane + cR;
-            float l[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) l[c] = rl[c * TC_RAWW];
-#pragma unroll
-            for (int r = 0; r < NROW; ++r) {
-              const bool okd = (unsigned)(z0 + r - KD / 2) < (unsigned)p.D;
-              float v[4];
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const float c2 = corr(l[2 * g], rr[(2 * g) * TC_RAWR - r], l[2 * g + 1], rr[(2 * g + 1) * TC_RAWR - r]);
-                v[g] = okd ? c2 : 0.f;
-              }
-              put(stage_base, r, khalf, v);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < TPW; ++j) {
-            const int cgl = j / NROW, r = j % NROW;
-#pragma unroll
-            for (int khalf = 0; khalf < 2; ++khalf) {
-              const float* rp = raw + ((cgl * 8 + khalf * 4) * NROW + r) * TC_RAWW + lane + sh;
-              float v[4];
-#pragma unroll
-              for (int c = 0; c < 4; ++c) v[c] = rp[c * NROW * TC_RAWW];
-              put(stage_base, j, khalf, v);
-            }
-          }
+      for (int j = 0; j < TPW; ++j) {
+        float4 hi, lo;
+        hi.x = tc_rna(v[j][0]);
+        hi.y = tc_rna(v[j][1]);
+        hi.z = tc_rna(v[j][2]);
+        hi.w = tc_rna(v[j][3]);
+        *reinterpret_cast<float4*>(sb + j * ROW_BYTES) = hi;
+        if (p.npass == 3) {
+          lo.x = tc_rna(v[j][0] - hi.x);
+          lo.y = tc_rna(v[j][1] - hi.y);
+          lo.z = tc_rna(v[j][2] - hi.z);
+          lo.w = tc_rna(v[j][3] - hi.w);
+          *reinterpret_cast<float4*>(sb + j * ROW_BYTES + 4096) = lo;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
-        __syncwarp();
-        if (lane == 0) {
-          tc_mbar_arrive(&full[st]);
-          tc_mbar_arrive(&rempty[rs]);
-        }
-      } else {
-        // ---- fallback for operands TMA cannot address (unaligned bases / pitches): per-thread predicated loads ----
-        const int y = ya - HALO + step;
-        const bool ok = strip_ok && (unsigned)y < (unsigned)p.H;
-        if (GWC) {
-          bool waited = false;
-#pragma unroll
-          for (int khalf = 0; khalf < 2; ++khalf) {
-            const int g0 = cgb * 8 + khalf * 4;
-            const int nch = 2 * min(4, p.Cin - g0);  // valid feature channels of this half group
-            const int sC = (int)p.src[0].sC;
-            const int off = (g0 * 2) * sC + y * (int)p.src[0].sH + x;
-            float l[8], rr[NROW][8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) l[c] = (ok && c < nch) ? __ldg(base[0] + (off + c * sC)) : 0.f;
-#pragma unroll
-            for (int r = 0; r < NROW; ++r) {
-              const int d = z0 + r - KD / 2;
-              const bool okd = ok && (unsigned)d < (unsigned)p.D && x >= d;
-#pragma unroll
-              for (int c = 0; c < 8; ++c) rr[r][c] = (okd && c < nch) ? __ldg(base[1] + (off + c * sC - d)) : 0.f;
-            }
-            if (!waited) tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
-            waited = true;
-#pragma unroll
-            for (int r = 0; r < NROW; ++r) {
-              float v[4];
-#pragma unroll
-              for (int g = 0; g < 4; ++g) v[g] = corr(l[2 * g], rr[r][2 * g], l[2 * g + 1], rr[r][2 * g + 1]);
-              put(stage_base, r, khalf, v);
-            }
-          }
-        } else {
-          float v[TPW][2][4];
-#pragma unroll
-          for (int cgl = 0; cgl < CGS; ++cgl) {
-            int rel = (cgb + cgl) * 8, k = 0;
-            if (p.nsrc > 1) {
-              while (k < p.nsrc - 1 && rel >= p.src[k].C) {  // host guarantees 8-channel groups never straddle sources
-                rel -= p.src[k].C;
-                ++k;
-              }
-            }
-            const int sC = (int)p.src[k].sC, sD = (int)p.src[k].sD;
-            const int nch = p.src[k].C - rel;  // valid channels from `rel` on (<= 0 past the last group)
-            const float* bp = p.nsrc > 1 ? (k == 0 ? base[0] : k == 1 ? base[1] : base[2]) : base[0];
-            const int off = rel * sC + (z0 - KD / 2) * sD + y * (int)p.src[k].sH + x;
-#pragma unroll
-            for (int r = 0; r < NROW; ++r) {
-              const bool okz = ok && (unsigned)(z0 + r - KD / 2) < (unsigned)p.D;
-#pragma unroll
-              for (int c = 0; c < 8; ++c) v[cgl * NROW + r][c >> 2][c & 3] = (okz && c < nch) ? __ldg(bp + (off + r * sD + c * sC)) : 0.f;
-            }
-          }
-          tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
-#pragma unroll
-          for (int j = 0; j < TPW; ++j) {
-            put(stage_base, j, 0, v[j][0]);
-            put(stage_base, j, 1, v[j][1]);
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) tc_mbar_arrive(&full[st]);
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(&full[st]);
       ++it;
+    };
+    // two register buffers, loop unrolled by two: the loads of stage i+1 are in flight while stage i is
+    // converted and stored (no register copies, so nothing waits on a load before its own store)
+    float va[TPW][4], vb[TPW][4];
+    enter_item();
+    if (item < p.items_per_cot) load(va);
+    while (item < p.items_per_cot) {
       advance();
-    }
-  } else if (warp == TC_TMA_WARP) {
-    // ============================ TMA issuer ============================
-    if (p.use_tma && lane == 0) {
-      const uint32_t raw_addr = tc_smem_u32(s_raw);
-      uint32_t it = 0;
-      for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
-        const TcItem ti = tc_decode(p, item, TZ);
-        int xs[4], y0[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int strip = ti.grp * 4 + q;
-          xs[q] = (strip % p.nseg) * p.segw - HALO;
-          y0[q] = strip < p.nstrips ? (strip / p.nseg) * p.rows - HALO : -(1 << 20);  // dummy strips: all rows out of range
-        }
-        for (int step = 0; step < nsteps; ++step) {
-          for (int cgb = 0; cgb < ncg; cgb += CGS) {
-            const uint32_t rs = it % RS, rph = (it / RS) & 1;
-            tc_mbar_wait(&rempty[rs], rph ^ 1, 300 + (int)rs);
-            tc_mbar_expect_tx(&rfull[rs], RAW_BYTES);
-            const uint32_t slot = raw_addr + rs * RAW_BYTES;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int y = y0[q] + step;
-              if (GWC) {
-                const int xr = xs[q] - (ti.z0 - KD / 2 + NROW - 1);
-                tc_tma_5d(slot + q * RAW_Q * 4, &maps.src[0], xs[q] & ~3, y, 0, cgb * 16, ti.b, &rfull[rs]);
-                tc_tma_5d(slot + (q * RAW_Q + 16 * TC_RAWW) * 4, &maps.src[1], xr & ~3, y, 0, cgb * 16, ti.b, &rfull[rs]);
-              } else {
-#pragma unroll
-                for (int cgl = 0; cgl < CGS; ++cgl) {
-                  int rel = (cgb + cgl) * 8, k = 0;
-                  while (k < p.nsrc - 1 && rel >= p.src[k].C) {
-                    rel -= p.src[k].C;
-                    ++k;
-                  }
-                  // past the last group: a channel coordinate beyond the source -> the box is zero-filled
-                  tc_tma_5d(slot + (q * RAW_Q + cgl * 8 * NROW * TC_RAWW) * 4, &maps.src[k], xs[q] & ~3, y, ti.z0 - KD / 2, rel, ti.b,
-                            &rfull[rs]);
-                }
-              }
-            }
-            ++it;
-          }
-        }
-      }
+      if (item < p.items_per_cot) load(vb);
+      store_stage(va);
+      if (item >= p.items_per_cot) break;
+      advance();
+      if (item < p.items_per_cot) load(va);
+      store_stage(vb);
     }
   } else if (warp == TC_MMA_WARP) {
     // ============================ MMA issuer ============================
-    // One thread issues every MMA, so this instruction stream is a serial bottleneck of the CTA.  The WHOLE
-    // warp runs the (warp-uniform) control flow and descriptor arithmetic -- that keeps the descriptors in
-    // uniform registers instead of paying vector->uniform moves per MMA -- and only lane 0 executes the
-    // tcgen05 instructions.  The descriptors are built once; only their 14-bit address fields advance
-    // (the operand ring and the weights sit below 256 KB, so the field never carries).
-    {
-      const bool leader = lane == 0;
+    if (lane == 0) {
       // D = f32, A = B = tf32, both K-major, N = NB, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
-      const uint64_t a0 = tc_desc(tc_smem_u32(s_stage), 2048, 128), b0 = tc_desc(tc_smem_u32(s_w), NB * 16, 128);
-      const bool three = p.npass == 3;
+      const uint32_t w_addr = tc_smem_u32(s_w), s_addr = tc_smem_u32(s_stage);
       uint32_t it = 0, ai = 0;
       for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
         for (int step = 0; step < nsteps; ++step) {
           const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
           tc_mbar_wait(&acce[ab], aph ^ 1, 400 + (int)ab);  // epilogue has drained this accumulator buffer
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t d0 = tmem + ab * ACC_COLS;
           for (int cgb = 0; cgb < ncg; cgb += CGS) {
             const uint32_t st = it % NS, ph = (it / NS) & 1;
             tc_mbar_wait(&full[st], ph, 500 + (int)st);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t a_st = a0 + (uint64_t)((st * STAGE_BYTES) >> 4);
 #pragma unroll
             for (int cgl = 0; cgl < CGS; ++cgl) {
               const int cg = cgb + cgl;
               if (cg < ncg) {
-                const uint64_t b_cg = b0 + (uint64_t)(((uint32_t)cg * KD * 2 * WSLAB) >> 4);
-                const uint32_t acc0 = cg > 0 ? 1u : 0u;
 #pragma unroll
                 for (int zo = 0; zo < TZ; ++zo) {
 #pragma unroll
                   for (int kd = 0; kd < KD; ++kd) {
-                    const uint64_t a_hi = a_st + (uint64_t)(((cgl * NROW + zo + kd) * ROW_BYTES) >> 4);
-                    const uint64_t b_hi = b_cg + (uint64_t)((kd * 2 * WSLAB) >> 4);
-                    const uint32_t d = d0 + zo * NB;
-                    if (leader) {
-                      tc_mma(d, a_hi, b_hi, idesc, kd > 0 ? 1u : acc0);
-                      if (three) {
-                        tc_mma(d, a_hi + (4096 >> 4), b_hi, idesc, 1u);
-                        tc_mma(d, a_hi, b_hi + (WSLAB >> 4), idesc, 1u);
-                      }
+                    const uint32_t a = s_addr + st * STAGE_BYTES + (cgl * NROW + zo + kd) * ROW_BYTES;
+                    const uint32_t b = w_addr + (uint32_t)((cg * KD + kd) * 2) * WSLAB;
+                    const uint64_t a_hi = tc_desc(a, 2048, 128), b_hi = tc_desc(b, NB * 16, 128);
+                    const uint32_t d = tmem + ab * ACC_COLS + zo * NB;
+                    tc_mma(d, a_hi, b_hi, idesc, (cg > 0 || kd > 0) ? 1u : 0u);
+                    if (p.npass == 3) {
+                      tc_mma(d, tc_desc(a + 4096, 2048, 128), b_hi, idesc, 1u);
+                      tc_mma(d, a_hi, tc_desc(b + WSLAB, NB * 16, 128), idesc, 1u);
                     }
                   }
                 }
               }
             }
-            if (leader) tc_commit(&empty[st]);  // frees the operand stage once these MMAs have read it
-            __syncwarp();
+            tc_commit(&empty[st]);  // frees the operand stage once these MMAs have read it
             ++it;
           }
-          if (leader) tc_commit(&accf[ab]);  // accumulator rows of this y step are complete
-          __syncwarp();
+          tc_commit(&accf[ab]);  // accumulator rows of this y step are complete
           ++ai;
         }
       }
     }
   } else {
     // ============================ epilogue ============================
-    // Warps w, w+4, w+8 share TMEM lane quadrant q = w % 4 (one strip); its NU units (z_o, 4 channels) are
-    // dealt round-robin to the three.  A unit's 4 x TAPS accumulator columns are contiguous (n = co*TAPS + tap).
-    const int q = warp & 3, sl = warp >> 2;
+    // warp w and w+4 share TMEM lane quadrant q = w % 4 (one strip) and own CW = COT/2 channels each
+    const int q = warp & 3;
+    const int ch0 = (warp >> 2) * CW;  // first channel (within the tile) of this warp
+    const int nvalid = p.Cout - (cot * COT + ch0);  // channels of this warp that exist
     const int oC = (int)p.oC, oD = (int)p.oD, oH = (int)p.oH;
     const bool post = p.out_mul || p.residual || p.act2 != ESM_ACT_NONE;
     uint32_t ai = 0;
@@ -594,49 +417,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       float* op = p.out + (long long)ti.b * p.oB + x;  // 32-bit offsets from here (host checks the extents)
       const float* rp = p.residual ? p.residual + (long long)ti.b * p.oB + x : nullptr;
       const float* mp = p.out_mul ? p.out_mul + (long long)ti.b * p.omB + x : nullptr;
-      constexpr int PW = TAPS == 9 ? 4 : 1;
-      float Pa[UPW][PW], Pb[UPW][PW];  // partial sums of output rows y_in-1 and y_in (k3 only)
+      constexpr int PW = TAPS == 9 ? CW : 1;
+      float Pa[TZ][PW], Pb[TZ][PW];  // partial sums of output rows y_in-1 and y_in (k3 only)
 #pragma unroll
-      for (int ui = 0; ui < UPW; ++ui)
+      for (int zo = 0; zo < TZ; ++zo)
 #pragma unroll
-        for (int c = 0; c < PW; ++c) Pa[ui][c] = Pb[ui][c] = 0.f;
+        for (int c = 0; c < PW; ++c) Pa[zo][c] = Pb[zo][c] = 0.f;
       for (int step = 0; step < nsteps; ++step) {
         const int yin = ya - HALO + step;
         const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
         tc_mbar_wait(&accf[ab], aph, 600 + (int)ab);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS;
-        float fin[UPW][4];
-        if (TAPS == 1) {
+        float fin[TZ][CW];
 #pragma unroll
-          for (int ui = 0; ui < UPW; ++ui) {
-            const int u = sl + 3 * ui;
-            if (u < NU) tc_ld4(tq + (u / (COT / 4)) * NB + (u % (COT / 4)) * 4, fin[ui]);
-          }
-          tc_ld_wait();
-        } else {
+        for (int zo = 0; zo < TZ; ++zo) {
+          const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + zo * NB + ch0;
+          if (TAPS == 1) {
 #pragma unroll
-          for (int ui = 0; ui < UPW; ++ui) {
-            const int u = sl + 3 * ui;
-            if (u < NU) {
-              float d[36];  // [channel j][kh][kw]
-              const uint32_t tb = tq + (u / (COT / 4)) * NB + (u % (COT / 4)) * 36;
-              tc_ld16(tb, d);
-              tc_ld16(tb + 16, d + 16);
-              tc_ld4(tb + 32, d + 32);
-              tc_ld_wait();
+            for (int c4 = 0; c4 < CW; c4 += 12) {
+              float d0[4], d1[4], d2[4];
+              tc_ld4x3(tb + c4, tb + (c4 + 4 < CW ? c4 + 4 : c4), tb + (c4 + 8 < CW ? c4 + 8 : c4), d0, d1, d2);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                // out column x gathers input columns x-1 (kw=0), x (kw=1), x+1 (kw=2); kh = 0/1/2 feeds output
-                // rows y_in+1 / y_in / y_in-1 (the last one is then complete)
-                const float t0 = __shfl_up_sync(0xffffffffu, d[j * 9 + 0], 1) + d[j * 9 + 1] + __shfl_down_sync(0xffffffffu, d[j * 9 + 2], 1);
-                const float t1 = __shfl_up_sync(0xffffffffu, d[j * 9 + 3], 1) + d[j * 9 + 4] + __shfl_down_sync(0xffffffffu, d[j * 9 + 5], 1);
-                const float t2 = __shfl_up_sync(0xffffffffu, d[j * 9 + 6], 1) + d[j * 9 + 7] + __shfl_down_sync(0xffffffffu, d[j * 9 + 8], 1);
-                fin[ui][j] = Pa[ui][j] + t2;
-                Pa[ui][j] = Pb[ui][j] + t1;
-                Pb[ui][j] = t0;
+                fin[zo][c4 + j] = d0[j];
+                if (c4 + 4 < CW) fin[zo][(c4 + 4 < CW ? c4 + 4 : 0) + j] = d1[j];
+                if (c4 + 8 < CW) fin[zo][(c4 + 8 < CW ? c4 + 8 : 0) + j] = d2[j];
               }
             }
+          } else {
+#pragma unroll
+          for (int c4 = 0; c4 < CW; c4 += 4) {
+            float t0[4];
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              float d0[4], d1[4], d2[4];
+              tc_ld4x3(tb + (kh * 3 + 0) * COT + c4, tb + (kh * 3 + 1) * COT + c4, tb + (kh * 3 + 2) * COT + c4, d0, d1, d2);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                // out column x gathers input columns x-1 (kw=0), x (kw=1), x+1 (kw=2)
+                const float t = __shfl_up_sync(0xffffffffu, d0[j], 1) + d1[j] + __shfl_down_sync(0xffffffffu, d2[j], 1);
+                if (kh == 0)
+                  t0[j] = t;                               // first contribution to output row y_in+1
+                else if (kh == 1)
+                  Pb[zo][c4 + j] += t;                     // output row y_in
+                else
+                  fin[zo][c4 + j] = Pa[zo][c4 + j] + t;    // output row y_in-1 is complete
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              Pa[zo][c4 + j] = Pb[zo][c4 + j];
+              Pb[zo][c4 + j] = t0[j];
+            }
+          }
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -646,63 +479,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         const int yo = yin - HALO;
         if (lane_ok && yo >= ya && yo < yb) {
 #pragma unroll
-          for (int ui = 0; ui < UPW; ++ui) {
-            const int u = sl + 3 * ui;
-            const int zo = u / (COT / 4), cl = (u % (COT / 4)) * 4;  // plane and first channel (within the tile)
-            if (u < NU && ti.z0 + zo < p.D) {
+          for (int zo = 0; zo < TZ; ++zo) {
+            if (ti.z0 + zo < p.D) {
               const int o_off = (ti.z0 + zo) * oD + yo * oH;
-              const int co0 = cot * COT + cl;
-              float rv[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) rv[j] = fmaf(fin[ui][j], s_aff[cl + j], s_aff[COT + cl + j]);
-              if (p.act == ESM_ACT_GELU && p.fast_gelu) {
+              for (int c4 = 0; c4 < CW; c4 += 4) {
+                const int cl = ch0 + c4;  // channel within the tile
+                float rv[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) rv[j] = tc_gelu(rv[j]);
-              } else if (p.act != ESM_ACT_NONE) {
-                const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), p.act);
-                rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
-              }
-              if (post) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  if (co0 + j < p.Cout) {
-                    if (p.out_mul) rv[j] *= __ldg(mp + ((co0 + j) * (int)p.omC + yo * (int)p.omH));
-                    if (p.residual) rv[j] += __ldg(rp + (o_off + (co0 + j) * oC));
-                  }
-                }
-                if (p.act2 != ESM_ACT_NONE) {
-                  const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), p.act2);
+                for (int j = 0; j < 4; ++j) rv[j] = fmaf(fin[zo][c4 + j], s_aff[cl + j], s_aff[COT + cl + j]);
+                if (p.act != ESM_ACT_NONE) {
+                  const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), p.act);
                   rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
                 }
-              }
+                if (post) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (co0 + j < p.Cout) op[o_off + (co0 + j) * oC] = rv[j] * p.out_scale;
+                  for (int j = 0; j < 4; ++j) {
+                    if (c4 + j < nvalid) {
+                      const int co = cot * COT + cl + j;
+                      if (p.out_mul) rv[j] *= __ldg(mp + (co * (int)p.omC + yo * (int)p.omH));
+                      if (p.residual) rv[j] += __ldg(rp + (o_off + co * oC));
+                    }
+                  }
+                  if (p.act2 != ESM_ACT_NONE) {
+                    const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), p.act2);
+                    rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (c4 + j < nvalid) op[o_off + (cot * COT + cl + j) * oC] = rv[j] * p.out_scale;
+              }
             }
           }
         }
       }
     }
   }
-#ifdef TC_PROFILE
-  if (blockIdx.x == 0 && lane == 0) {
-    const long long t_end = clock64();
-    printf("tc_prof warp %2d: busy-until %lld cycles since kernel start\n", warp, t_end - tc_t0);
-  }
-#endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-#ifdef TC_PROFILE
-  if (blockIdx.x == 0 && tid == 0) {
-    printf("tc_prof total %lld cycles; waits: rfull(producers) %lld  empty(producers) %lld  rempty(tma) %lld  acce(mma) %lld  full(mma) %lld  accf(epilogue, 12 warps) %lld\n",
-           clock64() - tc_t0, tc_prof_wait[1], tc_prof_wait[2], tc_prof_wait[3], tc_prof_wait[4], tc_prof_wait[5], tc_prof_wait[6]);
-    for (int i = 0; i < 8; ++i) tc_prof_wait[i] = 0;
-  }
-#endif
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
-typedef void (*tc_fn_t)(const TcK, const TcMaps);
+typedef void (*tc_fn_t)(const TcK);
 static long long tc_launches = 0;
 
 static tc_fn_t tc_pick(int COT, int TZ, int KD, bool gwc, int taps) {
@@ -780,17 +599,6 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
   int ns = (int)((limit - wbytes) / stage);
   plan->nstages = ns > 4 ? 4 : ns;
   plan->smem = wbytes + plan->nstages * stage + 1024;
-  // TMA-staged variant: raw fp32 ring (2..4 slots) + a shallower operand ring (2..3 slots)
-  const size_t raw = gwc ? 4 * 16 * (TC_RAWW + TC_RAWR) * 4 : (size_t)CGS * NROW * 8 * TC_RAWW * 4 * 4;
-  plan->rstages = 0;
-  if (wbytes + 2 * stage + 2 * raw <= limit) {
-    int nst = 2, rst = (int)((limit - wbytes - 2 * stage) / raw);
-    if (rst > 4) rst = 4;
-    if (wbytes + 3 * stage + rst * raw <= limit) nst = 3;
-    plan->nstages_tma = nst;
-    plan->rstages = rst;
-    plan->smem_tma = wbytes + nst * stage + rst * raw + 1024;
-  }
   const int segmax = k1 ? 32 : 30;
   plan->nseg = ceil_div(d->Wout, segmax);
   plan->segw = ceil_div(d->Wout, plan->nseg);
@@ -856,36 +664,11 @@ int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
   k.npass = plan.npass;
   tc_fn_t fn = tc_pick(plan.COT, plan.TZ, plan.KD, plan.gwc != 0, plan.taps);
   ESM_REQUIRE(fn, "conv(tc): no kernel for COT=%d TZ=%d KD=%d", plan.COT, plan.TZ, plan.KD);
-  // TMA staging needs 16-byte aligned bases and pitches (tensors made by this library have them; odd crops do not)
-  TcMaps maps;
-  memset(&maps, 0, sizeof(maps));
-  const bool no_tma = getenv("ESM_TC_NO_TMA") != nullptr;  // tests: force the per-thread load path
-  bool use_tma = plan.rstages >= 2 && !no_tma;
-  const int NROW = plan.TZ + plan.KD - 1;
-  for (int i = 0; i < d->nsrc && use_tma; ++i) {
-    const esm_src_t& sv = d->src[i];
-    const bool has_d = d->Din > 1 && !plan.gwc;
-    const long long sD = has_d ? sv.sD : sv.sH * d->Hin;
-    const long long sB = (d->B > 1 || sv.sB % 4 == 0) ? sv.sB : sv.sC * sv.C;
-    if ((reinterpret_cast<uintptr_t>(sv.ptr) & 15) || sv.sH % 4 || sv.sC % 4 || sD % 4 || sB % 4) {
-      use_tma = false;
-      break;
-    }
-    const long long dims[5] = {d->Win, d->Hin, has_d ? d->Din : 1, sv.C, d->B};
-    const long long str[4] = {sv.sH, sD, sv.sC, sB};
-    const int box[5] = {plan.gwc && i == 1 ? TC_RAWR : TC_RAWW, 1, plan.gwc ? 1 : NROW, plan.gwc ? 16 : 8, 1};
-    use_tma = encode_map(&maps.src[i], sv.ptr, 5, dims, str, box);
-  }
-  k.fast_gelu = getenv("ESM_TC_GELU") != nullptr;
-  k.use_tma = use_tma;
-  k.rstages = use_tma ? plan.rstages : 0;
-  k.nstages = use_tma ? plan.nstages_tma : plan.nstages;
-  const size_t smem = use_tma ? plan.smem_tma : plan.smem;
   // one limit for every launch of a function: the attribute is per function, not per launch, and graph
   // replays (and profilers re-launching graph nodes) must find it at least as large as any node's request
   if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return check_launch("conv(tc, cudaFuncSetAttribute)");
-  fn<<<(unsigned)(plan.ncot * plan.ctas_per_cot), TC_THREADS, smem, st>>>(k, maps);
+  fn<<<(unsigned)(plan.ncot * plan.ctas_per_cot), TC_THREADS, plan.smem, st>>>(k);
   ++tc_launches;
   return check_launch("conv(tc)");
 }

@@ -3,8 +3,6 @@
 #pragma once
 #include "common.cuh"
 
-#include <cuda.h>  // CUtensorMap (types only)
-
 namespace esm {
 
 struct TcPlan {
@@ -17,16 +15,10 @@ struct TcPlan {
   int nseg, segw;    // W is cut into nseg segments of segw (<= 30) output columns
   int ysplit, rows;  // H is cut into ysplit ranges of `rows` output rows
   int nstages;       // operand ring depth
-  int rstages;       // raw (TMA-staged fp32) ring depth
   int ctas_per_cot;  // persistent CTAs per channel tile
   int npass;         // 3: split-TF32 (fp32-grade), 1: single-pass TF32
   size_t smem;
-  int nstages_tma;   // operand ring depth when the inputs are TMA-staged
-  size_t smem_tma;
 };
-
-// fp32 tensor map of rank `rank` (innermost first); strides in elements for dims 1..rank-1 (conv.cu)
-bool encode_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const long long* strides_elems, const int* box);
 
 // Fills `plan` and returns true when `d` can run on the tensor-core path.
 bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan);
