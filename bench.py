@@ -192,13 +192,40 @@ def kernel_rooflines(model, peaks):
     by = 4.0 * (2 * C * h * w + G * D * h * w)
     out["gwc_volume"] = {"bound": "hbm", "achieved": by / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / t / 1e9 / hbm,
                          "traffic": None, "us": t * 1e6, "algorithmic_bytes": by}
+    # The conv family runs on tcgen05 (split-TF32, conv_tc.cu) where that wins the on-device timing, else on
+    # the FP32 pipe.  Whichever path a layer took decides the roofline it is held against: "tensor" = dense
+    # TF32 peak = half of the measured bf16 burst peak (kind::tf32 runs at half the bf16 rate; MEASURED_PEAKS
+    # has no separate TF32 figure), "fp32" = the FFMA rate measured on this pool.  `achieved` counts the
+    # ALGORITHMIC FLOPs (2*Cout*Cin*taps*voxels); the split executes 3 MMAs per product, reported separately.
+    from esmstereo_b200 import _lib
+    tc_count = _lib.lib().esm_tc_conv_launches
+    tf32_peak = peaks["bf16_tflops"] / 2.0
+
+    def conv_entry(fn, fl, by):
+        n0 = tc_count()
+        fn()
+        on_tc = tc_count() > n0
+        t = time_kernel(fn, flush)
+        peak = tf32_peak if on_tc else fp32_peak
+        e = {"bound": "tensor" if on_tc else "fp32", "path": "tcgen05 split-TF32" if on_tc else "fp32 pipe",
+             "achieved": fl / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / peak, "traffic": None,
+             "us": t * 1e6, "algorithmic_flops": fl, "algorithmic_bytes": by}
+        if on_tc:
+            e["executed_mma_tflops"] = 3 * fl / t / 1e12  # hi*hi + lo*hi + hi*lo
+        return e
+
     # fused volume + group_stem (K1 fused into K2): 2*8*32*27*voxels FLOPs, 4*(2*C + 8*D)*h*w bytes
     pc = model.group_stem.packed()
-    t = time_kernel(lambda: ops.conv([L, R], pc, "gelu", gwc_disp=D), flush)
-    fl = 2.0 * 8 * 32 * 27 * D * h * w
-    out["gwc_group_stem_fused"] = {"bound": "fp32", "achieved": fl / t / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                                   "frac": fl / t / 1e12 / fp32_peak, "traffic": None, "us": t * 1e6,
-                                   "algorithmic_flops": fl, "algorithmic_bytes": 4.0 * (2 * C + 8 * D) * h * w}
+    out["gwc_group_stem_fused"] = conv_entry(lambda: ops.conv([L, R], pc, "gelu", gwc_disp=D), 2.0 * 8 * 32 * 27 * D * h * w,
+                                             4.0 * (2 * C + 8 * D) * h * w)
+    # agg (a4): 8 -> 8 k3 at full cost-volume resolution; aggregation.conv1.1 (a5): 24 -> 24 k3 at half resolution
+    x8 = torch.randn(1, 8, D, h, w, generator=g).to(dev)
+    pa = model.agg.packed()
+    out["agg_conv3d_8_8"] = conv_entry(lambda: ops.conv(x8, pa, "gelu"), 2.0 * 8 * 8 * 27 * D * h * w, 4.0 * 16 * D * h * w)
+    x24 = torch.randn(1, 24, D // 2, h // 2, w // 2, generator=g).to(dev)
+    p24 = model.aggregation_out.conv1[1].packed()
+    out["hourglass_conv3d_24_24"] = conv_entry(lambda: ops.conv(x24, p24, "gelu"), 2.0 * 24 * 24 * 27 * (D // 2) * (h // 2) * (w // 2),
+                                               4.0 * 48 * (D // 2) * (h // 2) * (w // 2))
     # regression (K4): 4*(D+1)*h*w bytes
     cost = torch.randn(1, D, h, w, generator=g).to(dev)
     t = time_kernel(lambda: ops.regression_top2(cost), flush)
@@ -345,9 +372,11 @@ def run_ours(args):
             "gpu_launches": launches_per_step * K,
             "gpu_launches_per_step": launches_per_step,
             "roofline": {k: dominant[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")},
-            "roofline_note": "dominant kernel = fused gwc-volume + group_stem conv3d (19.9 GFLOP/launch), bound by the FP32 "
-                             "FMA pipe (parity needs fp32-exact convs; see DESIGN.md); peak = FFMA rate measured on this pool "
-                             "(scratch/fma_bench.cu); HBM/tensor peaks from " + peaks["source"],
+            "roofline_note": "dominant kernel = fused gwc-volume + group_stem conv3d (19.9 GFLOP/launch, the largest single "
+                             "launch of the step) on the path the autotuner chose (%s); tensor peak = dense TF32 = measured bf16 "
+                             "burst / 2, fp32 peak = FFMA rate measured on this pool (scratch/fma_bench.cu); peaks from %s; "
+                             "`achieved` counts algorithmic FLOPs, the fp32-grade split issues 3 MMAs per product (DESIGN.md)"
+                             % (dominant.get("path", "?"), peaks["source"]),
             "kernels": kr,
             "cost_volume_hbm_gbs": kr["gwc_volume"]["achieved"],
             "cpu_baseline": cpu,

@@ -50,6 +50,8 @@ METRICS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", 
            "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tensor.sum",
+           "sm__inst_executed_pipe_uniform.sum",
            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
@@ -84,8 +86,12 @@ def full():
             for k, v in label.items():
                 if k in name:
                     key = v
-            if "conv_kernel" in name and ", 1, 1, 0>" in name:
+            if "tc_conv_kernel<8, 3, 3, 1" in name or ("conv_kernel" in name and "tc_" not in name and ", 1, 1, 0" in name):
                 key = "gwc_group_stem_fused"
+            if "tc_conv_kernel<8, 3, 3, 0" in name:
+                key = "agg_conv3d_8_8"
+            if "tc_conv_kernel<24, 1, 3, 0" in name:
+                key = "hourglass_conv3d_24_24"
             if key:
                 traffic[key] = byts
     with open(os.path.join(OUT, "traffic.json"), "w") as f:
