@@ -1,11 +1,10 @@
 // Direct (implicit-GEMM on the FP32 pipe) convolution family for the ESMStereo hot path.
 //
-// Why CUDA cores and not tcgen05 here (see DESIGN.md "conv engine"): the parity gate is fp32-exact
-// top-2 indices, which single-pass TF32 cannot meet (hard part 2), and every
-// GEMM on this path has N = Cout in {8..72}; with voxels on M the A operand (im2col rows) must be
-// re-read from shared memory once per tap, so an SS-mode UMMA is bound by the 128 B/clk/SM shared
-// memory port at ~N*32 MAC/clk/SM, i.e. below the FP32 pipe once the 3xTF32 split triples the
-// traffic.  The FP32 pipe with packed FFMA2 was measured at 67 TFLOP/s in this exact inner loop.
+// Two engines behind esm_conv_f32.  The k3 s1 p1 and k1 layers can run on tcgen05 (conv_tc.cu: taps-in-N
+// implicit GEMM, split-TF32 for fp32-grade accuracy); on the first call of a shape that plan is timed on the
+// device against the best plan of the FP32-pipe engine below and the faster one is cached.  The FP32-pipe
+// engine (packed FFMA2, measured 67 TFLOP/s in this inner loop) runs everything else: stride-2, transposed,
+// single-channel and coarse-level layers, and any layer where it wins.
 //
 // One kernel template covers conv k1/k3/k5 stride 1, k3 stride 2, and ConvTranspose k4 s2 p1
 // (as 4 / 8 sub-pixel phase convolutions with a 2-tap kernel per dimension), in 2D and 3D, with:
