@@ -23,7 +23,7 @@
 // products).  npass = 1 keeps only hi*hi (single-pass TF32 fast mode).
 //
 // Warp roles (416 threads, 1 CTA/SM, persistent): warps 0-3 epilogue (TMEM -> registers -> global),
-// warp 4 MMA issuer (one thread), warps 5-12 operand producers: they load fp32 activations (or build
+// warps 8-10 MMA issuers (one thread each, one per output plane), warps 11-18 operand producers: they load fp32 activations (or build
 // the correlation from left/right feature rows), split them and write the K-major, non-swizzled UMMA
 // operand tiles.  Three mbarrier pipelines: operand ring full/empty, accumulator full/empty.
 #include "conv_tc.cuh"
@@ -54,8 +54,10 @@ struct TcK {
 
 constexpr int TC_NTW = 8;                               // operand-producer warps
 constexpr int TC_NEW = 8;                               // epilogue warps: 2 per TMEM lane quadrant
-constexpr int TC_MMA_WARP = TC_NEW;                     // warp index of the MMA issuer
-constexpr int TC_THREADS = 32 * (TC_NEW + 1 + TC_NTW);  // epilogue + MMA + producers
+constexpr int TC_MMA_WARP = TC_NEW;                     // first MMA-issuing warp
+constexpr int TC_NMW = 3;                               // MMA warps reserved: one per output plane z_o (TZ of them are active)
+constexpr int TC_PROD_WARP = TC_NEW + TC_NMW;           // first producer warp
+constexpr int TC_THREADS = 32 * (TC_NEW + TC_NMW + TC_NTW);  // 608: epilogue + MMA + producers (ptxas sizes for 640: 96 regs)
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
@@ -98,26 +100,25 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
-// Three 4-column loads of this warp's TMEM lane quadrant plus the wait, in ONE asm statement so that no
-// use of the results can be scheduled ahead of tcgen05.wait::ld.
-__device__ __forceinline__ void tc_ld4x3(uint32_t ta, uint32_t tb, uint32_t tc, float (&a)[4], float (&b)[4], float (&c)[4]) {
-  uint32_t u[12];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%12];\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4,%5,%6,%7}, [%13];\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8,%9,%10,%11}, [%14];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
-        "=r"(u[10]), "=r"(u[11])
-      : "r"(ta), "r"(tb), "r"(tc)
-      : "memory");
+// TMEM -> registers: this warp's lane quadrant, 16 / 4 consecutive columns.  Asynchronous: tc_ld_wait()
+// before the first use (all three are volatile with a memory clobber, so they keep their order).
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* r) {
+  uint32_t u[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+                 "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+               : "r"(taddr)
+               : "memory");
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    a[i] = __uint_as_float(u[i]);
-    b[i] = __uint_as_float(u[4 + i]);
-    c[i] = __uint_as_float(u[8 + i]);
-  }
+  for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
 }
+__device__ __forceinline__ void tc_ld4(uint32_t taddr, float* r) {
+  uint32_t u[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]) : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tc_rna(float x) {  // round to nearest TF32 (low 13 mantissa bits zero)
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -171,10 +172,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
       tc_mbar_init(&full[i], TC_NTW);
-      tc_mbar_init(&empty[i], 1);
+      tc_mbar_init(&empty[i], TZ);  // one tcgen05.commit per MMA warp
     }
     for (int i = 0; i < 2; ++i) {
-      tc_mbar_init(&accf[i], 1);
+      tc_mbar_init(&accf[i], TZ);
       tc_mbar_init(&acce[i], TC_NEW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     s_aff[tid] = (src && co < p.Cout) ? __ldg(src + co) : (tid < COT ? 1.f : 0.f);
   }
   // resident weights of this channel tile: split and laid out as UMMA B operands
-  // (row n = (kh*3+kw)*COT + co, K = 8 input channels of group cg)
+  // (row n = co*TAPS + kh*3+kw: the 9 taps of a channel are adjacent accumulator columns; K = 8 channels of group cg)
   {
     const int total = ncg * KD * NB * 8;
     constexpr int U = 4;
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         w[u] = 0.f;
         if (idx < total && co < p.CoutPad && ci < p.CinPad)
           w[u] = __ldg(p.weight + ((long long)(kd * TAPS + tap2) * p.CinPad + ci) * p.CoutPad + co);
-        off[u] = (uint32_t)((cg * KD + kd) * 2) * WSLAB + (uint32_t)(k >> 2) * (NB * 16) + (uint32_t)(tap2 * COT + col) * 16 + (k & 3) * 4;
+        off[u] = (uint32_t)((cg * KD + kd) * 2) * WSLAB + (uint32_t)(k >> 2) * (NB * 16) + (uint32_t)(col * TAPS + tap2) * 16 + (k & 3) * 4;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -229,9 +230,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  if (warp > TC_MMA_WARP) {
+  if (warp >= TC_PROD_WARP) {
     // ============================ operand producers ============================
-    const int tw = warp - TC_MMA_WARP - 1;
+    const int tw = warp - TC_PROD_WARP;
     const int q = (tw >> 1) & 3;   // strip (= TMEM lane quadrant) this warp feeds
     const int khalf = tw & 1;      // which 4 of the 8 channels of a group
     const int m = q * 32 + lane;   // A row
@@ -352,47 +353,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       if (item < p.items_per_cot) load(va);
       store_stage(vb);
     }
-  } else if (warp == TC_MMA_WARP) {
-    // ============================ MMA issuer ============================
-    if (lane == 0) {
+  } else if (warp >= TC_MMA_WARP) {
+    // ============================ MMA issuers ============================
+    // One thread per output plane z_o: the MMAs of different planes accumulate into different TMEM columns, so
+    // their issue streams are independent -- and the issue stream of a single thread, not the tensor pipe, is
+    // what bounded the kernel (measured: ~140 clk per MMA issued against 50 clk per MMA executed).  Every
+    // issuer commits to the stage's `empty` barrier and to the step's `accf` barrier (count TZ).
+    const int zo = warp - TC_MMA_WARP;
+    if (zo < TZ && lane == 0) {
       // D = f32, A = B = tf32, both K-major, N = NB, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t w_addr = tc_smem_u32(s_w), s_addr = tc_smem_u32(s_stage);
+      // descriptors are built once; only their 14-bit address fields advance (everything sits below 256 KB)
+      const uint64_t a0 = tc_desc(tc_smem_u32(s_stage) + zo * ROW_BYTES, 2048, 128), b0 = tc_desc(tc_smem_u32(s_w), NB * 16, 128);
+      const bool three = p.npass == 3;
       uint32_t it = 0, ai = 0;
       for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
         for (int step = 0; step < nsteps; ++step) {
           const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
           tc_mbar_wait(&acce[ab], aph ^ 1, 400 + (int)ab);  // epilogue has drained this accumulator buffer
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d = tmem + ab * ACC_COLS + zo * NB;
           for (int cgb = 0; cgb < ncg; cgb += CGS) {
             const uint32_t st = it % NS, ph = (it / NS) & 1;
             tc_mbar_wait(&full[st], ph, 500 + (int)st);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t a_st = a0 + (uint64_t)((st * STAGE_BYTES) >> 4);
 #pragma unroll
             for (int cgl = 0; cgl < CGS; ++cgl) {
               const int cg = cgb + cgl;
               if (cg < ncg) {
+                const uint64_t b_cg = b0 + (uint64_t)(((uint32_t)cg * KD * 2 * WSLAB) >> 4);
+                const uint32_t acc0 = cg > 0 ? 1u : 0u;
 #pragma unroll
-                for (int zo = 0; zo < TZ; ++zo) {
-#pragma unroll
-                  for (int kd = 0; kd < KD; ++kd) {
-                    const uint32_t a = s_addr + st * STAGE_BYTES + (cgl * NROW + zo + kd) * ROW_BYTES;
-                    const uint32_t b = w_addr + (uint32_t)((cg * KD + kd) * 2) * WSLAB;
-                    const uint64_t a_hi = tc_desc(a, 2048, 128), b_hi = tc_desc(b, NB * 16, 128);
-                    const uint32_t d = tmem + ab * ACC_COLS + zo * NB;
-                    tc_mma(d, a_hi, b_hi, idesc, (cg > 0 || kd > 0) ? 1u : 0u);
-                    if (p.npass == 3) {
-                      tc_mma(d, tc_desc(a + 4096, 2048, 128), b_hi, idesc, 1u);
-                      tc_mma(d, a_hi, tc_desc(b + WSLAB, NB * 16, 128), idesc, 1u);
-                    }
+                for (int kd = 0; kd < KD; ++kd) {
+                  const uint64_t a_hi = a_st + (uint64_t)(((cgl * NROW + kd) * ROW_BYTES) >> 4);
+                  const uint64_t b_hi = b_cg + (uint64_t)((kd * 2 * WSLAB) >> 4);
+                  tc_mma(d, a_hi, b_hi, idesc, kd > 0 ? 1u : acc0);
+                  if (three) {
+                    tc_mma(d, a_hi + (4096 >> 4), b_hi, idesc, 1u);
+                    tc_mma(d, a_hi, b_hi + (WSLAB >> 4), idesc, 1u);
                   }
                 }
               }
             }
-            tc_commit(&empty[st]);  // frees the operand stage once these MMAs have read it
+            tc_commit(&empty[st]);  // the stage is free once the MMAs of every issuer have read it
             ++it;
           }
-          tc_commit(&accf[ab]);  // accumulator rows of this y step are complete
+          tc_commit(&accf[ab]);  // this plane's accumulator row of the y step is complete
           ++ai;
         }
       }
@@ -431,45 +438,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         float fin[TZ][CW];
 #pragma unroll
         for (int zo = 0; zo < TZ; ++zo) {
-          const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + zo * NB + ch0;
+          const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + zo * NB + ch0 * TAPS;
           if (TAPS == 1) {
 #pragma unroll
-            for (int c4 = 0; c4 < CW; c4 += 12) {
-              float d0[4], d1[4], d2[4];
-              tc_ld4x3(tb + c4, tb + (c4 + 4 < CW ? c4 + 4 : c4), tb + (c4 + 8 < CW ? c4 + 8 : c4), d0, d1, d2);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                fin[zo][c4 + j] = d0[j];
-                if (c4 + 4 < CW) fin[zo][(c4 + 4 < CW ? c4 + 4 : 0) + j] = d1[j];
-                if (c4 + 8 < CW) fin[zo][(c4 + 8 < CW ? c4 + 8 : 0) + j] = d2[j];
-              }
-            }
+            for (int c4 = 0; c4 < CW; c4 += 4) tc_ld4(tb + c4, fin[zo] + c4);
+            tc_ld_wait();
           } else {
 #pragma unroll
-          for (int c4 = 0; c4 < CW; c4 += 4) {
-            float t0[4];
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-              float d0[4], d1[4], d2[4];
-              tc_ld4x3(tb + (kh * 3 + 0) * COT + c4, tb + (kh * 3 + 1) * COT + c4, tb + (kh * 3 + 2) * COT + c4, d0, d1, d2);
+            for (int c4 = 0; c4 < CW; c4 += 4) {
+              float d[36];  // [channel j][kh][kw]: 4 channels x 9 taps are 36 adjacent columns
+              tc_ld16(tb + c4 * 9, d);
+              tc_ld16(tb + c4 * 9 + 16, d + 16);
+              tc_ld4(tb + c4 * 9 + 32, d + 32);
+              tc_ld_wait();
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                // out column x gathers input columns x-1 (kw=0), x (kw=1), x+1 (kw=2)
-                const float t = __shfl_up_sync(0xffffffffu, d0[j], 1) + d1[j] + __shfl_down_sync(0xffffffffu, d2[j], 1);
-                if (kh == 0)
-                  t0[j] = t;                               // first contribution to output row y_in+1
-                else if (kh == 1)
-                  Pb[zo][c4 + j] += t;                     // output row y_in
-                else
-                  fin[zo][c4 + j] = Pa[zo][c4 + j] + t;    // output row y_in-1 is complete
+                // out column x gathers input columns x-1 (kw=0), x (kw=1), x+1 (kw=2); kh = 0/1/2 feeds output rows
+                // y_in+1 / y_in / y_in-1 (the last one is then complete)
+                const float t0 = __shfl_up_sync(0xffffffffu, d[j * 9 + 0], 1) + d[j * 9 + 1] + __shfl_down_sync(0xffffffffu, d[j * 9 + 2], 1);
+                const float t1 = __shfl_up_sync(0xffffffffu, d[j * 9 + 3], 1) + d[j * 9 + 4] + __shfl_down_sync(0xffffffffu, d[j * 9 + 5], 1);
+                const float t2 = __shfl_up_sync(0xffffffffu, d[j * 9 + 6], 1) + d[j * 9 + 7] + __shfl_down_sync(0xffffffffu, d[j * 9 + 8], 1);
+                fin[zo][c4 + j] = Pa[zo][c4 + j] + t2;
+                Pa[zo][c4 + j] = Pb[zo][c4 + j] + t1;
+                Pb[zo][c4 + j] = t0;
               }
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              Pa[zo][c4 + j] = Pb[zo][c4 + j];
-              Pb[zo][c4 + j] = t0[j];
-            }
-          }
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
