@@ -39,6 +39,8 @@ def build(force: bool = False, verbose: bool = True) -> str:
     headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "conv_kernel.cuh"), os.path.join(CSRC, "conv_tc.cuh"),
                os.path.join(os.path.dirname(os.path.dirname(CSRC)), "include", "esm_b200.h")]
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    if os.environ.get("ESM_TC_PROFILE") == "1":  # role timers of the tcgen05 conv kernel (conv_tc.cu), diagnostics only
+        flags = flags + ["-DTC_PROFILE"]
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))

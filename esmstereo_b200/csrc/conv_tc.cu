@@ -73,7 +73,14 @@ __device__ __noinline__ void tc_deadlock(int tag, uint32_t parity) {
          (int)(threadIdx.x & 31), tag, parity);
   __trap();
 }
+#ifdef TC_PROFILE
+// role profiler (build with ESM_TC_PROFILE=1): cycles block 0's warps spend in each class of mbarrier wait
+__device__ unsigned long long tc_prof_wait[32][8];
+#endif
 __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+#ifdef TC_PROFILE
+  const long long t_begin = clock64();
+#endif
   const uint32_t addr = tc_smem_u32(bar);
   uint32_t done, polls = 0;
   do {
@@ -83,6 +90,9 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity, int
                  : "memory");
     if (!done && ++polls > (1u << 26)) tc_deadlock(tag, parity);
   } while (!done);
+#ifdef TC_PROFILE
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) tc_prof_wait[threadIdx.x >> 5][tag / 100] += (unsigned long long)(clock64() - t_begin);
+#endif
 }
 // K-major, no-swizzle UMMA shared-memory descriptor: 8-row x 16-byte core matrices, rows 16 bytes
 // apart; LBO = byte distance between the two K halves, SBO = distance between 8-row groups.
@@ -119,10 +129,36 @@ __device__ __forceinline__ void tc_ld4(uint32_t taddr, float* r) {
   for (int i = 0; i < 4; ++i) r[i] = __uint_as_float(u[i]);
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float tc_rna(float x) {  // round to nearest TF32 (low 13 mantissa bits zero)
+// Round to the nearest TF32 (low 13 mantissa bits zero).  `.rn` (ties to even) is one native instruction on
+// sm_100a (F2FP.TF32.F32); `.rna` is emulated with four (FSETP/IADD/SEL/LOP3) -- and the producers convert
+// 40 values per stage.  The split x = hi + lo is exact for either rounding.
+__device__ __forceinline__ float tc_rna(float x) {
   uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
+}
+
+// GELU for the epilogue warps, which bound most of these kernels: erff() costs ~35 instructions per value on a
+// divergent warp (two branches), this one 16, branch-free.  erfc(t) = 2^p(t) with p a degree-8 fit of
+// log2(erfcx(t)) - t^2 log2(e) on [0, 4] weighted by the GELU's sensitivity, so that
+//   gelu(x) = x - h (x >= 0),  h (x < 0),   h = 0.5 x erfc(|x| / sqrt 2).
+// Absolute error <= 6e-8 (an ulp of an O(1) activation), relative error <= 3e-7 for x >= 0; the fit and its
+// error table are in tests/test_host_cpu.py::test_tc_gelu_polynomial.
+__device__ __forceinline__ float tc_gelu(float x) {
+  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
+  float q = -2.906944503e-05f;
+  q = fmaf(q, t, 3.042682386e-04f);
+  q = fmaf(q, t, -1.000199492e-03f);
+  q = fmaf(q, t, -1.645459926e-03f);
+  q = fmaf(q, t, 2.910655108e-02f);
+  q = fmaf(q, t, -1.489377188e-01f);
+  q = fmaf(q, t, -9.182927772e-01f);
+  q = fmaf(q, t, -1.627922676e+00f);
+  q = fmaf(q, t, 3.958853834e-07f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  const float h = (0.5f * x) * e;
+  return x >= 0.f ? x - h : h;
 }
 
 struct TcItem {
@@ -154,6 +190,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   static_assert(TZ * NB <= ACC_COLS, "accumulator does not fit");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef TC_PROFILE
+  const long long tc_t0 = clock64();
+#endif
   const int ncg = p.ncg;
   const int NS = p.nstages;
   const uint32_t wbytes = (uint32_t)ncg * KD * 2 * WSLAB;
@@ -211,7 +250,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         const int co = cot * COT + col, ci = cg * 8 + k;
         w[u] = 0.f;
         if (idx < total && co < p.CoutPad && ci < p.CinPad)
-          w[u] = __ldg(p.weight + ((long long)(kd * TAPS + tap2) * p.CinPad + ci) * p.CoutPad + co);
+          w[u] = (GWC ? 0.5f : 1.0f) * __ldg(p.weight + ((long long)(kd * TAPS + tap2) * p.CinPad + ci) * p.CoutPad + co);
         off[u] = (uint32_t)((cg * KD + kd) * 2) * WSLAB + (uint32_t)(k >> 2) * (NB * 16) + (uint32_t)(col * TAPS + tap2) * 16 + (k & 3) * 4;
       }
 #pragma unroll
@@ -236,7 +275,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     const int q = (tw >> 1) & 3;   // strip (= TMEM lane quadrant) this warp feeds
     const int khalf = tw & 1;      // which 4 of the 8 channels of a group
     const int m = q * 32 + lane;   // A row
-    uint32_t it = 0;
+    uint32_t st = 0, ph = 0;       // ring cursor: stage and its phase bit (no runtime division in the loop)
     // load cursor (item, step, cgb) and what it caches per item; offsets are 32-bit (host checks the extents)
     int item = cta, step = 0, cgb = 0;
     const float* base[3] = {nullptr, nullptr, nullptr};
@@ -259,8 +298,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       const int y = ya - HALO + step;
       const bool ok = strip_ok && (unsigned)y < (unsigned)p.H;
       if (GWC) {
-        // v = 0.5 * (L[2g]*R[2g](x-d) + L[2g+1]*R[2g+1](x-d)), un-contracted (submodule.py:147); cpg == 2.
-        // All loads are issued first (predicated, never branched around) so that they overlap.
+        // v = L[2g]*R[2g](x-d) + L[2g+1]*R[2g+1](x-d); the 0.5 of the group mean (submodule.py:147, cpg == 2) is
+        // folded into the resident weights, exactly (a power of two).  All loads are issued first (predicated,
+        // never branched around) so that they overlap.
         const int g0 = cgb * 8 + khalf * 4;
         const int nch = 2 * min(4, p.Cin - g0);  // valid feature channels of this half group
         const int sC = (int)p.src[0].sC;
@@ -279,7 +319,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         for (int r = 0; r < NROW; ++r)
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            v[r][g] = __fmul_rn(__fadd_rn(__fmul_rn(l[2 * g], rr[r][2 * g]), __fmul_rn(l[2 * g + 1], rr[r][2 * g + 1])), 0.5f);
+            v[r][g] = fmaf(l[2 * g], rr[r][2 * g], __fmul_rn(l[2 * g + 1], rr[r][2 * g + 1]));
       } else {
 #pragma unroll
         for (int cgl = 0; cgl < CGS; ++cgl) {
@@ -315,7 +355,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       }
     };
     auto store_stage = [&](const float (&v)[TPW][4]) {
-      const uint32_t st = it % NS, ph = (it / NS) & 1;
       tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
       uint8_t* sb = s_stage + (size_t)st * STAGE_BYTES + khalf * 2048 + m * 16;
 #pragma unroll
@@ -337,7 +376,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(&full[st]);
-      ++it;
+      if (++st == (uint32_t)NS) {
+        st = 0;
+        ph ^= 1;
+      }
     };
     // two register buffers, loop unrolled by two: the loads of stage i+1 are in flight while stage i is
     // converted and stored (no register copies, so nothing waits on a load before its own store)
@@ -366,7 +408,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       // descriptors are built once; only their 14-bit address fields advance (everything sits below 256 KB)
       const uint64_t a0 = tc_desc(tc_smem_u32(s_stage) + zo * ROW_BYTES, 2048, 128), b0 = tc_desc(tc_smem_u32(s_w), NB * 16, 128);
       const bool three = p.npass == 3;
-      uint32_t it = 0, ai = 0;
+      uint32_t st = 0, ph = 0, ai = 0;
       for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
         for (int step = 0; step < nsteps; ++step) {
           const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
@@ -374,7 +416,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t d = tmem + ab * ACC_COLS + zo * NB;
           for (int cgb = 0; cgb < ncg; cgb += CGS) {
-            const uint32_t st = it % NS, ph = (it / NS) & 1;
             tc_mbar_wait(&full[st], ph, 500 + (int)st);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t a_st = a0 + (uint64_t)((st * STAGE_BYTES) >> 4);
@@ -397,7 +438,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
               }
             }
             tc_commit(&empty[st]);  // the stage is free once the MMAs of every issuer have read it
-            ++it;
+            if (++st == (uint32_t)NS) {
+              st = 0;
+              ph ^= 1;
+            }
           }
           tc_commit(&accf[ab]);  // this plane's accumulator row of the y step is complete
           ++ai;
@@ -481,7 +525,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 float rv[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) rv[j] = fmaf(fin[zo][c4 + j], s_aff[cl + j], s_aff[COT + cl + j]);
-                if (p.act != ESM_ACT_NONE) {
+                if (p.act == ESM_ACT_GELU) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) rv[j] = tc_gelu(rv[j]);
+                } else if (p.act != ESM_ACT_NONE) {
                   const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), p.act);
                   rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
                 }
@@ -509,6 +556,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       }
     }
   }
+#ifdef TC_PROFILE
+  if (blockIdx.x == 0 && lane == 0) {
+    printf("tc_prof warp %2d: done at %8lld clk; waits: empty %8llu  acce %8llu  full %8llu  accf %8llu\n", warp, clock64() - tc_t0,
+           tc_prof_wait[warp][2], tc_prof_wait[warp][4], tc_prof_wait[warp][5], tc_prof_wait[warp][6]);
+    for (int i = 0; i < 8; ++i) tc_prof_wait[warp][i] = 0;
+  }
+#endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
