@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       const int y = ya - HALO + step;
       const bool ok = strip_ok && (unsigned)y < (unsigned)p.H;
       if (GWC) {
-        // v = L[2g]*R[2g](x-d) + L[2g+1]*R[2g+1](x-d); the 0.5 of the group mean (submodule.py:147, cpg == 2) is
+        // v = L[2g]*R[2g](x-d) + L[2g+1]*R[2g+1](x-d), un-contracted like the reference; the 0.5 of the group mean (submodule.py:147, cpg == 2) is
         // folded into the resident weights, exactly (a power of two).  All loads are issued first (predicated,
         // never branched around) so that they overlap.
         const int g0 = cgb * 8 + khalf * 4;
@@ -318,8 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 #pragma unroll
         for (int r = 0; r < NROW; ++r)
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            v[r][g] = fmaf(l[2 * g], rr[r][2 * g], __fmul_rn(l[2 * g + 1], rr[r][2 * g + 1]));
+          for (int g = 0; g < 4; ++g) v[r][g] = __fadd_rn(__fmul_rn(l[2 * g], rr[r][2 * g]), __fmul_rn(l[2 * g + 1], rr[r][2 * g + 1]));
       } else {
 #pragma unroll
         for (int cgl = 0; cgl < CGS; ++cgl) {
@@ -450,12 +449,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     }
   } else {
     // ============================ epilogue ============================
-    // warp w and w+4 share TMEM lane quadrant q = w % 4 (one strip) and own CW = COT/2 channels each
+    // warp w and w+4 share TMEM lane quadrant q = w % 4 (one strip) and own CW = COT/2 channels each.  A
+    // (z_o, 4 channels) unit goes TMEM -> 9-tap gather -> BN/activation -> global before the next one is read, so
+    // only the rolling window stays live in registers; addresses are 32-bit offsets from one pointer per item.
     const int q = warp & 3;
     const int ch0 = (warp >> 2) * CW;  // first channel (within the tile) of this warp
     const int nvalid = p.Cout - (cot * COT + ch0);  // channels of this warp that exist
     const int oC = (int)p.oC, oD = (int)p.oD, oH = (int)p.oH;
     const bool post = p.out_mul || p.residual || p.act2 != ESM_ACT_NONE;
+    const bool gelu = p.act == ESM_ACT_GELU;
+    const float oscale = p.out_scale;
     uint32_t ai = 0;
     for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
       const TcItem ti = tc_decode(p, item, TZ);
@@ -465,9 +468,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       const int ya = ys * p.rows;
       const int yb = min(ya + p.rows, p.H);
       const bool lane_ok = strip < p.nstrips && lane >= HALO && lane < p.segw + HALO && x < p.W;
-      float* op = p.out + (long long)ti.b * p.oB + x;  // 32-bit offsets from here (host checks the extents)
-      const float* rp = p.residual ? p.residual + (long long)ti.b * p.oB + x : nullptr;
-      const float* mp = p.out_mul ? p.out_mul + (long long)ti.b * p.omB + x : nullptr;
+      // first channel of this warp, plane z0, row 0, column x (host checks that the offsets below fit 32 bits)
+      float* op = p.out + ((long long)ti.b * p.oB + (long long)(cot * COT + ch0) * p.oC + (long long)ti.z0 * p.oD + x);
+      const float* rp = p.residual ? p.residual + ((long long)ti.b * p.oB + (long long)(cot * COT + ch0) * p.oC + (long long)ti.z0 * p.oD + x) : nullptr;
+      const float* mp = p.out_mul ? p.out_mul + ((long long)ti.b * p.omB + (long long)(cot * COT + ch0) * p.omC + x) : nullptr;
+      const int nz = min(TZ, p.D - ti.z0);  // planes of this item that exist
       constexpr int PW = TAPS == 9 ? CW : 1;
       float Pa[TZ][PW], Pb[TZ][PW];  // partial sums of output rows y_in-1 and y_in (k3 only)
 #pragma unroll
@@ -475,21 +480,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 #pragma unroll
         for (int c = 0; c < PW; ++c) Pa[zo][c] = Pb[zo][c] = 0.f;
       for (int step = 0; step < nsteps; ++step) {
-        const int yin = ya - HALO + step;
+        const int yo = ya - 2 * HALO + step;  // the output row this step completes
+        const bool row_ok = lane_ok && yo >= ya && yo < yb;
         const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
         tc_mbar_wait(&accf[ab], aph, 600 + (int)ab);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float fin[TZ][CW];
 #pragma unroll
         for (int zo = 0; zo < TZ; ++zo) {
           const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + zo * NB + ch0 * TAPS;
-          if (TAPS == 1) {
 #pragma unroll
-            for (int c4 = 0; c4 < CW; c4 += 4) tc_ld4(tb + c4, fin[zo] + c4);
-            tc_ld_wait();
-          } else {
-#pragma unroll
-            for (int c4 = 0; c4 < CW; c4 += 4) {
+          for (int c4 = 0; c4 < CW; c4 += 4) {
+            float rv[4];
+            if (TAPS == 1) {
+              tc_ld4(tb + c4, rv);
+              tc_ld_wait();
+            } else {
               float d[36];  // [channel j][kh][kw]: 4 channels x 9 taps are 36 adjacent columns
               tc_ld16(tb + c4 * 9, d);
               tc_ld16(tb + c4 * 9 + 16, d + 16);
@@ -502,57 +507,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 const float t0 = __shfl_up_sync(0xffffffffu, d[j * 9 + 0], 1) + d[j * 9 + 1] + __shfl_down_sync(0xffffffffu, d[j * 9 + 2], 1);
                 const float t1 = __shfl_up_sync(0xffffffffu, d[j * 9 + 3], 1) + d[j * 9 + 4] + __shfl_down_sync(0xffffffffu, d[j * 9 + 5], 1);
                 const float t2 = __shfl_up_sync(0xffffffffu, d[j * 9 + 6], 1) + d[j * 9 + 7] + __shfl_down_sync(0xffffffffu, d[j * 9 + 8], 1);
-                fin[zo][c4 + j] = Pa[zo][c4 + j] + t2;
+                rv[j] = Pa[zo][c4 + j] + t2;
                 Pa[zo][c4 + j] = Pb[zo][c4 + j] + t1;
                 Pb[zo][c4 + j] = t0;
               }
             }
-          }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) tc_mbar_arrive(&acce[ab]);
-        ++ai;
-        const int yo = yin - HALO;
-        if (lane_ok && yo >= ya && yo < yb) {
+            if (zo == TZ - 1 && c4 + 4 >= CW) {  // last TMEM read of this step: hand the accumulator buffer back
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) tc_mbar_arrive(&acce[ab]);
+            }
+            if (row_ok && zo < nz) {
+              const int cl = ch0 + c4;  // channel within the tile
 #pragma unroll
-          for (int zo = 0; zo < TZ; ++zo) {
-            if (ti.z0 + zo < p.D) {
-              const int o_off = (ti.z0 + zo) * oD + yo * oH;
+              for (int j = 0; j < 4; ++j) rv[j] = fmaf(rv[j], s_aff[cl + j], s_aff[COT + cl + j]);
+              if (gelu) {
 #pragma unroll
-              for (int c4 = 0; c4 < CW; c4 += 4) {
-                const int cl = ch0 + c4;  // channel within the tile
-                float rv[4];
+                for (int j = 0; j < 4; ++j) rv[j] = tc_gelu(rv[j]);
+              } else if (p.act != ESM_ACT_NONE) {
+                const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), p.act);
+                rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
+              }
+              const int o_off = zo * oD + yo * oH + c4 * oC;
+              if (post) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) rv[j] = fmaf(fin[zo][c4 + j], s_aff[cl + j], s_aff[COT + cl + j]);
-                if (p.act == ESM_ACT_GELU) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) rv[j] = tc_gelu(rv[j]);
-                } else if (p.act != ESM_ACT_NONE) {
-                  const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), p.act);
+                for (int j = 0; j < 4; ++j) {
+                  if (c4 + j < nvalid) {
+                    if (mp) rv[j] *= __ldg(mp + ((c4 + j) * (int)p.omC + yo * (int)p.omH));
+                    if (rp) rv[j] += __ldg(rp + (o_off + j * oC));
+                  }
+                }
+                if (p.act2 != ESM_ACT_NONE) {
+                  const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), p.act2);
                   rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
                 }
-                if (post) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    if (c4 + j < nvalid) {
-                      const int co = cot * COT + cl + j;
-                      if (p.out_mul) rv[j] *= __ldg(mp + (co * (int)p.omC + yo * (int)p.omH));
-                      if (p.residual) rv[j] += __ldg(rp + (o_off + co * oC));
-                    }
-                  }
-                  if (p.act2 != ESM_ACT_NONE) {
-                    const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), p.act2);
-                    rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
-                  }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (c4 + j < nvalid) op[o_off + (cot * COT + cl + j) * oC] = rv[j] * p.out_scale;
               }
+              float* o = op + o_off;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (c4 + j < nvalid) o[j * oC] = rv[j] * oscale;
             }
           }
         }
+        ++ai;
       }
     }
   }
