@@ -400,8 +400,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     // their issue streams are independent -- and the issue stream of a single thread, not the tensor pipe, is
     // what bounded the kernel (measured: ~140 clk per MMA issued against 50 clk per MMA executed).  Every
     // issuer commits to the stage's `empty` barrier and to the step's `accf` barrier (count TZ).
-    const int zo = warp - TC_MMA_WARP;
-    if (zo < TZ && lane == 0) {
+    // The whole warp runs the loop so that every descriptor lives in uniform registers and tcgen05.mma issues
+    // straight from them; with a single active lane the compiler wraps each MMA in an elect / R2UR.BROADCAST
+    // waterfall of ~17 dependent instructions (measured: ~140 clk per MMA issued).  One elected lane issues.
+    const int zo = __shfl_sync(0xffffffffu, warp - TC_MMA_WARP, 0);
+    if (zo < TZ) {
+      uint32_t leader;
+      asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}\n" : "=r"(leader));
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       // D = f32, A = B = tf32, both K-major, N = NB, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) | ((128u >> 4) << 24);
       // descriptors are built once; only their 14-bit address fields advance (everything sits below 256 KB)
@@ -413,36 +419,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
           const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
           tc_mbar_wait(&acce[ab], aph ^ 1, 400 + (int)ab);  // epilogue has drained this accumulator buffer
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t d = tmem + ab * ACC_COLS + zo * NB;
+          const uint32_t d = tmem_u + ab * ACC_COLS + zo * NB;
           for (int cgb = 0; cgb < ncg; cgb += CGS) {
             tc_mbar_wait(&full[st], ph, 500 + (int)st);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t a_st = a0 + (uint64_t)((st * STAGE_BYTES) >> 4);
+            if (leader) {
 #pragma unroll
-            for (int cgl = 0; cgl < CGS; ++cgl) {
-              const int cg = cgb + cgl;
-              if (cg < ncg) {
-                const uint64_t b_cg = b0 + (uint64_t)(((uint32_t)cg * KD * 2 * WSLAB) >> 4);
-                const uint32_t acc0 = cg > 0 ? 1u : 0u;
+              for (int cgl = 0; cgl < CGS; ++cgl) {
+                const int cg = cgb + cgl;
+                if (cg < ncg) {
+                  const uint64_t b_cg = b0 + (uint64_t)(((uint32_t)cg * KD * 2 * WSLAB) >> 4);
+                  const uint32_t acc0 = cg > 0 ? 1u : 0u;
 #pragma unroll
-                for (int kd = 0; kd < KD; ++kd) {
-                  const uint64_t a_hi = a_st + (uint64_t)(((cgl * NROW + kd) * ROW_BYTES) >> 4);
-                  const uint64_t b_hi = b_cg + (uint64_t)((kd * 2 * WSLAB) >> 4);
-                  tc_mma(d, a_hi, b_hi, idesc, kd > 0 ? 1u : acc0);
-                  if (three) {
-                    tc_mma(d, a_hi + (4096 >> 4), b_hi, idesc, 1u);
-                    tc_mma(d, a_hi, b_hi + (WSLAB >> 4), idesc, 1u);
+                  for (int kd = 0; kd < KD; ++kd) {
+                    const uint64_t a_hi = a_st + (uint64_t)(((cgl * NROW + kd) * ROW_BYTES) >> 4);
+                    const uint64_t b_hi = b_cg + (uint64_t)((kd * 2 * WSLAB) >> 4);
+                    tc_mma(d, a_hi, b_hi, idesc, kd > 0 ? 1u : acc0);
+                    if (three) {
+                      tc_mma(d, a_hi + (4096 >> 4), b_hi, idesc, 1u);
+                      tc_mma(d, a_hi, b_hi + (WSLAB >> 4), idesc, 1u);
+                    }
                   }
                 }
               }
+              tc_commit(&empty[st]);  // the stage is free once the MMAs of every issuer have read it
             }
-            tc_commit(&empty[st]);  // the stage is free once the MMAs of every issuer have read it
+            __syncwarp();
             if (++st == (uint32_t)NS) {
               st = 0;
               ph ^= 1;
             }
           }
-          tc_commit(&accf[ab]);  // this plane's accumulator row of the y step is complete
+          if (leader) tc_commit(&accf[ab]);  // this plane's accumulator row of the y step is complete
+          __syncwarp();
           ++ai;
         }
       }
