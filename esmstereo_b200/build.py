@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libesm_b200.so")
-SOURCES = ["api.cu", "conv.cu", "conv_k1.cu", "conv_k2.cu", "conv_k3.cu", "conv_k3s2.cu", "conv_k5.cu", "conv_tc.cu", "volume.cu", "regress.cu",
+SOURCES = ["api.cu", "conv.cu", "conv_k1.cu", "conv_k2.cu", "conv_k3.cu", "conv_k3s2.cu", "conv_k5.cu", "conv_tc.cu", "conv_tcg.cu", "volume.cu", "regress.cu",
            "mixer.cu", "conf.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
@@ -36,7 +36,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
     nvcc = _nvcc()
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "conv_kernel.cuh"), os.path.join(CSRC, "conv_tc.cuh"),
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "conv_kernel.cuh"), os.path.join(CSRC, "conv_tc.cuh"), os.path.join(CSRC, "tc_common.cuh"),
                os.path.join(os.path.dirname(os.path.dirname(CSRC)), "include", "esm_b200.h")]
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     if os.environ.get("ESM_TC_PROFILE") == "1":  # role timers of the tcgen05 conv kernel (conv_tc.cu), diagnostics only

@@ -116,6 +116,65 @@ static PackGeom pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transpo
   return g;
 }
 
+// Second region of a packed weight, right after the fp32 pack: the operand slabs of the streamed-weight tcgen05
+// path (conv_tcg.cu), already split for the fp32-grade TF32 scheme.  One slab per (phase, tap, 8-channel group):
+//   [hi | lo][k / 4][CoutX][k % 4]   (K-major, no-swizzle UMMA B tile; a CTA's channel tile is a row range of it)
+TcgPack tcg_pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed) {
+  const PackGeom g = pack_geom(Cout, Cin, kd, kh, kw, transposed);
+  TcgPack t;
+  t.offset = g.per_phase * g.phases;
+  t.phases = g.phases;
+  t.taps = g.KD * g.KH * g.KW;
+  t.KD = g.KD;
+  t.KH = g.KH;
+  t.KW = g.KW;
+  t.ncg = ceil_div(Cin, 8);
+  t.CoutX = round_up(Cout, 8);
+  t.elems = Cin >= 8 ? (long long)t.phases * t.taps * t.ncg * 16 * t.CoutX : 0;
+  return t;
+}
+
+__global__ void pack_tcg_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kd, int kh, int kw,
+                                int transposed, int KD, int KH, int KW, int phases_d, int ncg, int CoutX, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long r = i;
+  const int co = r % CoutX;
+  r /= CoutX;
+  const int k = r % 8;
+  r /= 8;
+  const int cg = r % ncg;
+  r /= ncg;
+  const int tw = r % KW;
+  r /= KW;
+  const int thh = r % KH;
+  r /= KH;
+  const int tdd = r % KD;
+  r /= KD;
+  const int z = (int)r;  // phase
+  const int ci = cg * 8 + k;
+  float v = 0.f;
+  if (co < Cout && ci < Cin) {
+    if (!transposed) {
+      v = w[(((long long)(co * Cin + ci) * kd + tdd) * kh + thh) * kw + tw];
+    } else {
+      const int pzw = z & 1, pzh = (z >> 1) & 1, pzd = (phases_d == 2) ? ((z >> 2) & 1) : 0;
+      const int kkw = 3 - pzw - 2 * tw;
+      const int kkh = 3 - pzh - 2 * thh;
+      const int kkd = (phases_d == 2) ? 3 - pzd - 2 * tdd : 0;
+      v = w[(((long long)(ci * Cout + co) * kd + kkd) * kh + kkh) * kw + kkw];  // [Cin,Cout,k,k,k]
+    }
+  }
+  uint32_t hb, lb;
+  asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+  const float hi = __uint_as_float(hb);
+  asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
+  const long long slab = ((((long long)z * KD + tdd) * KH + thh) * KW + tw) * ncg + cg;  // 16 * CoutX floats each
+  float* o = out + slab * 16 * CoutX + (k >> 2) * (4 * CoutX) + co * 4 + (k & 3);
+  o[0] = hi;
+  o[8 * CoutX] = __uint_as_float(lb);
+}
+
 // ------------------------------------------------------------------------------------------
 // host-side tiling + dispatch
 // ------------------------------------------------------------------------------------------
@@ -293,8 +352,9 @@ struct Plan {
   conv_fn_t fn;         // cp.async pipeline (any strides)
   conv_fn_t fn_tma[2];  // TMA pipeline for window offset XO = 0 / 3 (nullptr if not instantiated)
   int cosplit, COP, COG, CK, blocks_per_sm;
-  bool use_tc;  // run on the tcgen05 path (conv_tc.cu) instead
+  int use_tc;  // 1: run on the resident-weight tcgen05 path (conv_tc.cu), 2: on the streamed-weight one (conv_tcg.cu)
   TcPlan tc;
+  TcgPlan tcg;
 };
 
 struct LayerGeom {
@@ -425,7 +485,7 @@ using namespace esm;
 
 extern "C" long long esm_packed_weight_elems(int Cout, int Cin, int kd, int kh, int kw, int transposed) {
   const PackGeom g = pack_geom(Cout, Cin, kd, kh, kw, transposed);
-  return g.per_phase * g.phases;
+  return g.per_phase * g.phases + tcg_pack_geom(Cout, Cin, kd, kh, kw, transposed).elems;
 }
 
 extern "C" int esm_pack_conv_weight_f32(const float* w, float* packed, int Cout, int Cin, int kd, int kh, int kw,
@@ -439,6 +499,12 @@ extern "C" int esm_pack_conv_weight_f32(const float* w, float* packed, int Cout,
   const int threads = 256;
   pack_weight_kernel<<<(unsigned)ceil_div_ll(total, threads), threads, 0, (cudaStream_t)stream>>>(
       w, packed, Cout, Cin, kd, kh, kw, transposed, g.CinPad, g.CoutPad, g.KD, g.KH, g.KW, g.phases, g.phases_d, total);
+  const TcgPack t = tcg_pack_geom(Cout, Cin, kd, kh, kw, transposed);
+  if (t.elems > 0) {
+    const long long n = t.elems / 2;  // one thread per weight writes its hi and lo parts
+    pack_tcg_kernel<<<(unsigned)ceil_div_ll(n, threads), threads, 0, (cudaStream_t)stream>>>(
+        w, packed + t.offset, Cout, Cin, kd, kh, kw, transposed, g.KD, g.KH, g.KW, g.phases_d, t.ncg, t.CoutX, n);
+  }
   return check_launch("pack_conv_weight");
 }
 
@@ -549,9 +615,10 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   // ESM_TC_FORCE=1 takes the tensor-core path whenever the layer is eligible (tests), else it must win the timing
   const char* tc_env = getenv("ESM_TC");
   const int tc_pass = tc_env ? atoi(tc_env) : 3;
-  const bool tc_force = getenv("ESM_TC_FORCE") != nullptr && tc_pass != 0;
+  // ESM_TC_FORCE=1 forces the resident-weight engine, =2 the streamed-weight engine, wherever eligible
+  const int tc_force = (getenv("ESM_TC_FORCE") != nullptr && tc_pass != 0) ? (atoi(getenv("ESM_TC_FORCE")) == 2 ? 2 : 1) : 0;
   PlanKey key = {{d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed, lg.Jw, lg.Jh, lg.Jd, gwc ? k.cpg : 0, d->B, d->pd,
-                  d->ph, d->pw, tc_pass * 2 + (tc_force ? 1 : 0) + (d->in_mul ? 64 : 0) + (d->pixel_shuffle ? 128 : 0)}};
+                  d->ph, d->pw, tc_pass * 4 + tc_force + (d->in_mul ? 64 : 0) + (d->pixel_shuffle ? 128 : 0)}};
   std::lock_guard<std::mutex> lock(plans_mu);
   if (num_sms == 0) {
     int dev = 0;
@@ -566,7 +633,9 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   }
   auto it = plans.find(key);
   if (it != plans.end())
-    return it->second.use_tc ? tc_conv_launch(d, it->second.tc, st) : launch_plan(d, g, k, it->second, lg, num_sms, st);
+    return it->second.use_tc == 2   ? tcg_conv_launch(d, it->second.tcg, st)
+           : it->second.use_tc == 1 ? tc_conv_launch(d, it->second.tc, st)
+                                    : launch_plan(d, g, k, it->second, lg, num_sms, st);
 
   // ---- plan: enumerate (channel split x chunk depth x tile shape), rank by the analytic model ----
   const int ck0 = g.CinPad == 1 ? 1 : 8;
@@ -697,48 +766,58 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
   }
-  // ---- tensor-core candidate (conv_tc.cu): taken when forced, or when it beats the best FP32-pipe plan ----
+  // ---- tensor-core candidates (conv_tc.cu: resident weights, taps in N; conv_tcg.cu: streamed weights, taps in K):
+  // taken when forced, or when they beat the best FP32-pipe plan in the on-device timing ----
   TcPlan tcp;
-  if (tc_pass != 0 && tc_conv_plan(d, num_sms, tc_pass == 1 ? 1 : 3, &tcp)) {
-    bool take = tc_force;
-    if (!take && tune) {
-      cudaEvent_t e0, e1;
-      cudaEventCreate(&e0);
-      cudaEventCreate(&e1);
-      auto time3 = [&](bool tc) -> float {
-        float ms = 1e30f;
-        for (int rep = 0; rep < 3; ++rep) {  // rep 0 warms
-          cudaEventRecord(e0, st);
-          for (int l = 0; l < 3; ++l) {
-            if (tc)
-              tc_conv_launch(d, tcp, st);
-            else
-              launch_plan(d, g, k, best_plan, lg, num_sms, st);
-          }
-          cudaEventRecord(e1, st);
-          if (cudaEventSynchronize(e1) != cudaSuccess) return -1.f;
-          float m3 = 0.f;
-          cudaEventElapsedTime(&m3, e0, e1);
-          if (rep > 0 && m3 / 3.f < ms) ms = m3 / 3.f;
+  TcgPlan tgp;
+  const bool tc_ok = tc_pass != 0 && tc_force != 2 && tc_conv_plan(d, num_sms, tc_pass == 1 ? 1 : 3, &tcp);
+  const bool tg_ok = tc_pass != 0 && tc_force != 1 && getenv("ESM_TCG_OFF") == nullptr && tcg_conv_plan(d, num_sms, tc_pass == 1 ? 1 : 3, &tgp);
+  best_plan.use_tc = 0;
+  if (tc_force == 1 && tc_ok) {
+    best_plan.use_tc = 1;
+  } else if (tc_force == 2 && tg_ok) {
+    best_plan.use_tc = 2;
+  } else if (!tc_force && tune && (tc_ok || tg_ok)) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    auto time3 = [&](int engine) -> float {
+      float ms = 1e30f;
+      for (int rep = 0; rep < 3; ++rep) {  // rep 0 warms
+        cudaEventRecord(e0, st);
+        for (int l = 0; l < 3; ++l) {
+          if (engine == 2)
+            tcg_conv_launch(d, tgp, st);
+          else if (engine == 1)
+            tc_conv_launch(d, tcp, st);
+          else
+            launch_plan(d, g, k, best_plan, lg, num_sms, st);
         }
-        return ms;
-      };
-      if (best_ms >= 1e29f) best_ms = time3(false);
-      const float tc_ms = time3(true);
-      cudaEventDestroy(e0);
-      cudaEventDestroy(e1);
-      if (best_ms < 0.f || tc_ms < 0.f) return check_launch("conv(autotune tc)");
-      take = tc_ms < best_ms;
-      if (getenv("ESM_DEBUG_PLAN"))
-        fprintf(stderr, "[esm tune] Cin=%d Cout=%d k=(%d,%d,%d) J=(%d,%d,%d)%s: tcgen05 COT=%d TZ=%d ysplit=%d ctas=%d ns=%d pass=%d -> %.1f us vs fp32 %.1f us\n",
-                d->Cin, d->Cout, d->kd, d->kh, d->kw, lg.Jd, lg.Jh, lg.Jw, gwc ? " gwc" : "", tcp.COT, tcp.TZ, tcp.ysplit,
-                tcp.ncot * tcp.ctas_per_cot, tcp.nstages, tcp.npass, tc_ms * 1000.f, best_ms * 1000.f);
-    }
-    if (take) {
-      best_plan.use_tc = true;
-      best_plan.tc = tcp;
-    }
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) return -1.f;
+        float m3 = 0.f;
+        cudaEventElapsedTime(&m3, e0, e1);
+        if (rep > 0 && m3 / 3.f < ms) ms = m3 / 3.f;
+      }
+      return ms;
+    };
+    if (best_ms >= 1e29f) best_ms = time3(0);
+    const float tc_ms = tc_ok ? time3(1) : 1e30f;
+    const float tg_ms = tg_ok ? time3(2) : 1e30f;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (best_ms < 0.f || tc_ms < 0.f || tg_ms < 0.f) return check_launch("conv(autotune tc)");
+    if (tc_ms < best_ms && tc_ms <= tg_ms) best_plan.use_tc = 1;
+    if (tg_ms < best_ms && tg_ms < tc_ms) best_plan.use_tc = 2;
+    if (getenv("ESM_DEBUG_PLAN"))
+      fprintf(stderr, "[esm tune] Cin=%d Cout=%d k=(%d,%d,%d) s=%d%s J=(%d,%d,%d)%s: fp32 %.1f us | tcgen05 resident %.1f us (COT=%d TZ=%d) | "
+              "streamed %.1f us (NT=%d x%d, %d ctas, %d stages) -> engine %d\n",
+              d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed ? " T" : "", lg.Jd, lg.Jh, lg.Jw, gwc ? " gwc" : "", best_ms * 1000.f,
+              tc_ok ? tc_ms * 1000.f : -1.f, tc_ok ? tcp.COT : 0, tc_ok ? tcp.TZ : 0, tg_ok ? tg_ms * 1000.f : -1.f, tg_ok ? tgp.NT : 0,
+              tg_ok ? tgp.ncot : 0, tg_ok ? tgp.ctas : 0, tg_ok ? tgp.nstages : 0, best_plan.use_tc);
   }
+  if (best_plan.use_tc == 1) best_plan.tc = tcp;
+  if (best_plan.use_tc == 2) best_plan.tcg = tgp;
   if (getenv("ESM_DEBUG_PLAN"))
     fprintf(stderr, "[esm plan] Cin=%d Cout=%d k=(%d,%d,%d) s=%d%s%s J=(%d,%d,%d): CK=%d COP=%d cosplit=%d tile=(%d,%d,%d) threads=%d "
             "smem=%zu KB occ=%d tuned=%d\n",
@@ -746,5 +825,7 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
             best_plan.CK, best_plan.COP, best_plan.cosplit, best_plan.tl.TD, best_plan.tl.TH, best_plan.tl.TWG * best_plan.tl.NV,
             best_plan.tl.slots * (best_plan.COP / best_plan.COG), best_plan.tl.smem / 1024, best_plan.blocks_per_sm, (int)tune);
   plans.emplace(key, best_plan);
-  return best_plan.use_tc ? tc_conv_launch(d, best_plan.tc, st) : launch_plan(d, g, k, best_plan, lg, num_sms, st);
+  return best_plan.use_tc == 2   ? tcg_conv_launch(d, best_plan.tcg, st)
+         : best_plan.use_tc == 1 ? tc_conv_launch(d, best_plan.tc, st)
+                                 : launch_plan(d, g, k, best_plan, lg, num_sms, st);
 }

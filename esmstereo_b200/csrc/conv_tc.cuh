@@ -20,6 +20,26 @@ struct TcPlan {
   size_t smem;
 };
 
+// Geometry of the split-TF32 weight slabs stored after the fp32 pack (conv.cu: esm_pack_conv_weight_f32).
+struct TcgPack {
+  long long offset, elems;  // in floats, from the start of the packed weight
+  int phases, taps, KD, KH, KW, ncg, CoutX;
+};
+TcgPack tcg_pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed);
+
+// Streamed-weight GEMM path (conv_tcg.cu): any k / stride 1-2 / transposed k4 s2 layer with Cin >= 8.
+struct TcgPlan {
+  int NT;        // output channels (accumulator columns) per CTA, multiple of 8, <= 128
+  int ncot;      // channel tiles
+  int mtiles;    // 128-voxel tiles of the output lattice (per batch item and phase)
+  int nstages;   // operand ring depth
+  int ctas;      // persistent CTAs
+  int npass;
+  size_t smem;
+};
+bool tcg_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcgPlan* plan);
+int tcg_conv_launch(const esm_conv_t* d, const TcgPlan& plan, cudaStream_t st);
+
 // Fills `plan` and returns true when `d` can run on the tensor-core path.
 bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan);
 int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st);

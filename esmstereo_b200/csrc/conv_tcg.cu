@@ -1,0 +1,509 @@
+// Streamed-weight tensor-core path of the convolution family: an implicit GEMM on tcgen05.mma (kind::tf32,
+// accumulators in TMEM, fp32-grade split-TF32) with the kernel taps in K and the weights streamed through the
+// operand ring by TMA bulk copies.  Replaces BasicConv (submodule.py:12-38) for the layers conv_tc.cu cannot
+// hold resident weights for or has no gather for: the wide hourglass levels of `aggregation` (40->40, 72->72,
+// ESMStereo.py:129-182), its stride-2 convs and its ConvTranspose3d k4 s2 p1 layers (as 8 sub-pixel phases of
+// 2x2x2-tap convolutions), and the deep small-resolution 2D convs / deconvs of FeatUp (ESMStereo.py:79-125).
+//
+//   acc[m, co] = sum_{tap, ci} X[voxel(m) * stride + tap - pad, ci] * W[tap, ci, co]
+//
+// M = 128 consecutive voxels of the (flattened) output lattice, N = NT <= 128 output channels, one
+// M128 x N x K8 MMA triple (hi*hi + lo*hi + hi*lo) per (8-channel group, tap).  With N this small an MMA is bound
+// by the shared-memory read of A (46 clk, scratch/umma_test.cu), so the kernel wins where the FP32 pipe is starved
+// instead: few voxels, many channels.
+//
+// Warp roles (448 threads, 1 CTA/SM, persistent): warps 0-3 epilogue (one per TMEM lane quadrant: TMEM -> BN /
+// activation -> global), warp 4 MMA issuer (warp-uniform, one elected lane), warp 5 weight streamer (one lane: four
+// bulk copies per slab, completing on the stage's `full` barrier), warps 6-13 A-operand producers (predicated
+// global loads, four in flight per thread, split into hi / lo, stored as K-major non-swizzled UMMA tiles).
+#include "conv_tc.cuh"
+#include "tc_common.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
+namespace esm {
+
+struct TcgK {
+  esm_src_t src[3];
+  int nsrc;
+  int B, Cin, ncg;
+  int Din, Hin, Win;            // input extent
+  int Jd, Jh, Jw;               // output lattice per phase (transposed: ceil(out / 2))
+  int Dout, Hout, Wout, Cout;
+  int KD, KH, KW, taps;         // taps per phase
+  int sz, sxy;                  // input step per lattice step (stride; 1 for transposed)
+  int od, oh, ow;               // input offset of tap 0 at lattice 0 (regular: -pad; transposed: phase - 1, added per phase)
+  int transposed, phases, phases_d;
+  const float* wtc;             // split weight slabs (TcgPack)
+  int CoutX;
+  const float* scale;
+  const float* shift;
+  int act, act2;
+  const float* out_mul;
+  long long omB, omC, omH;
+  const float* residual;
+  float out_scale;
+  float* out;
+  long long oB, oC, oD, oH;
+  int NT, ncot, mtiles, items, ctas, nstages, npass;
+};
+
+constexpr int TG_NEW = 4;                      // epilogue warps
+constexpr int TG_MMA_WARP = TG_NEW;            // MMA issuer
+constexpr int TG_W_WARP = TG_NEW + 1;          // weight streamer
+constexpr int TG_PROD_WARP = TG_NEW + 2;       // first A producer warp
+constexpr int TG_NTW = 8;                      // A producer warps
+constexpr int TG_THREADS = 32 * (TG_NEW + 2 + TG_NTW);
+constexpr int TG_PD = 4;                       // loads in flight per producer thread (slabs ahead)
+
+struct TgItem {
+  int b, phase, mt, cot;
+};
+__device__ __forceinline__ TgItem tg_decode(const TcgK& p, int item) {
+  TgItem t;
+  t.cot = item % p.ncot;  // channel tiles of one voxel tile are neighbours: they share the A rows in L2
+  int r = item / p.ncot;
+  t.mt = r % p.mtiles;
+  r /= p.mtiles;
+  t.phase = r % p.phases;
+  t.b = r / p.phases;
+  return t;
+}
+
+__global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_constant__ TcgK p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef TC_PROFILE
+  const long long tc_t0 = clock64();
+#endif
+  const int NT = p.NT, NS = p.nstages;
+  const uint32_t BHALF = (uint32_t)NT * 32;           // bytes of the hi (or lo) B tile: [2][NT][4] floats
+  const uint32_t STAGE = 8192 + 2 * BHALF;            // A hi | A lo | B hi | B lo
+  uint8_t* s_stage = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NS * STAGE);
+  uint64_t* empty = full + NS;
+  uint64_t* accf = empty + NS;
+  uint64_t* acce = accf + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + 2);
+  const int KT = p.ncg * p.taps;  // K steps (slabs) per item
+  const int voxels = p.Jd * p.Jh * p.Jw;
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) {
+      tc_mbar_init(&full[i], TG_NTW + 1);  // 8 producer warps + the weight streamer's expect_tx arrive
+      tc_mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc_mbar_init(&accf[i], 1);
+      tc_mbar_init(&acce[i], TG_NEW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= TG_PROD_WARP) {
+    // ============================ A-operand producers ============================
+    const int tw = warp - TG_PROD_WARP;
+    const int q = (tw >> 1) & 3;   // TMEM lane quadrant = rows q*32 .. q*32+31 of the tile
+    const int khalf = tw & 1;      // which 4 of the 8 channels of a group
+    const int m = q * 32 + lane;   // A row
+    // load cursor
+    int item = blockIdx.x, cg = 0, td = 0, th = 0, tww = 0;
+    int iz0 = 0, iy0 = 0, ix0 = 0;  // input coordinate of tap (0,0,0) for this thread's voxel
+    bool vox_ok = false;
+    const float* bptr = nullptr;    // source base of the current channel group (+ batch)
+    int sC = 0, sD = 0, sH = 0, nch = 0, boff = 0;
+    auto enter_group = [&](int b) {
+      int rel = cg * 8 + khalf * 4, k = 0;
+      while (k < p.nsrc - 1 && rel >= p.src[k].C) {  // host guarantees 8-channel groups never straddle sources
+        rel -= p.src[k].C;
+        ++k;
+      }
+      const esm_src_t& s = p.src[k];
+      sC = (int)s.sC;
+      sD = (int)s.sD;
+      sH = (int)s.sH;
+      nch = s.C - rel;  // valid channels from `rel` on (<= 0 past the last group)
+      bptr = s.ptr + (long long)b * s.sB;
+      boff = rel * sC;
+    };
+    int cur_b = 0;
+    auto enter_item = [&]() {
+      if (item >= p.items) return;
+      const TgItem ti = tg_decode(p, item);
+      const int v = ti.mt * 128 + m;
+      vox_ok = v < voxels;
+      const int jx = v % p.Jw, r = v / p.Jw;
+      const int jy = r % p.Jh, jz = r / p.Jh;
+      const int pzw = ti.phase & 1, pzh = (ti.phase >> 1) & 1, pzd = (p.phases_d == 2) ? ((ti.phase >> 2) & 1) : 0;
+      iz0 = jz * p.sz + p.od + (p.transposed ? pzd : 0);
+      iy0 = jy * p.sxy + p.oh + (p.transposed ? pzh : 0);
+      ix0 = jx * p.sxy + p.ow + (p.transposed ? pzw : 0);
+      cur_b = ti.b;
+      cg = 0;
+      td = th = tww = 0;
+      enter_group(cur_b);
+    };
+    auto load = [&](float (&v)[4]) {
+      const int iz = iz0 + td, iy = iy0 + th, ix = ix0 + tww;
+      const bool ok = vox_ok && (unsigned)iz < (unsigned)p.Din && (unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win;
+      const int off = boff + iz * sD + iy * sH + ix;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = (ok && c < nch) ? __ldg(bptr + (off + c * sC)) : 0.f;
+    };
+    auto advance = [&]() {
+      if (++tww < p.KW) return;
+      tww = 0;
+      if (++th < p.KH) return;
+      th = 0;
+      if (++td < p.KD) return;
+      td = 0;
+      if (++cg < p.ncg) {
+        enter_group(cur_b);
+        return;
+      }
+      item += p.ctas;
+      enter_item();
+    };
+    uint32_t st = 0, ph = 0;
+    auto store_stage = [&](const float (&v)[4]) {
+      tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
+      uint8_t* sb = s_stage + (size_t)st * STAGE + khalf * 2048 + m * 16;
+      float4 hi, lo;
+      hi.x = tc_rna(v[0]);
+      hi.y = tc_rna(v[1]);
+      hi.z = tc_rna(v[2]);
+      hi.w = tc_rna(v[3]);
+      *reinterpret_cast<float4*>(sb) = hi;
+      if (p.npass == 3) {
+        lo.x = tc_rna(v[0] - hi.x);
+        lo.y = tc_rna(v[1] - hi.y);
+        lo.z = tc_rna(v[2] - hi.z);
+        lo.w = tc_rna(v[3] - hi.w);
+        *reinterpret_cast<float4*>(sb + 4096) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(&full[st]);
+      if (++st == (uint32_t)NS) {
+        st = 0;
+        ph ^= 1;
+      }
+    };
+    // TG_PD register buffers: the loads of slab i + TG_PD are issued right after slab i is stored
+    float v[TG_PD][4];
+    long long remaining = 0;  // slabs this CTA still has to store
+    for (int it = blockIdx.x; it < p.items; it += p.ctas) remaining += KT;
+    enter_item();
+#pragma unroll
+    for (int i = 0; i < TG_PD; ++i) {
+      if (item < p.items) {
+        load(v[i]);
+        advance();
+      }
+    }
+    while (remaining > 0) {
+#pragma unroll
+      for (int i = 0; i < TG_PD; ++i) {
+        if (remaining > 0) {
+          store_stage(v[i]);
+          --remaining;
+          if (item < p.items) {
+            load(v[i]);
+            advance();
+          }
+        }
+      }
+    }
+  } else if (warp == TG_W_WARP) {
+    // ============================ weight streamer ============================
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      const long long slab_floats = 16ll * p.CoutX;
+      for (int item = blockIdx.x; item < p.items; item += p.ctas) {
+        const TgItem ti = tg_decode(p, item);
+        const int n0 = ti.cot * NT;
+        const int rows = min(NT, p.CoutX - n0);
+        const uint32_t bytes = (uint32_t)rows * 16;
+        for (int cg = 0; cg < p.ncg; ++cg) {
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const float* slab = p.wtc + ((long long)(ti.phase * p.taps + tap) * p.ncg + cg) * slab_floats + n0 * 4;
+            tc_mbar_wait(&empty[st], ph ^ 1, 300 + (int)st);
+            uint8_t* sb = s_stage + (size_t)st * STAGE + 8192;
+            tc_mbar_expect_tx(&full[st], (p.npass == 3 ? 4u : 2u) * bytes);
+            tc_bulk_g2s(sb, slab, bytes, &full[st]);                                     // hi, k 0..3
+            tc_bulk_g2s(sb + NT * 16, slab + 4 * p.CoutX, bytes, &full[st]);            // hi, k 4..7
+            if (p.npass == 3) {
+              tc_bulk_g2s(sb + BHALF, slab + 8 * p.CoutX, bytes, &full[st]);             // lo, k 0..3
+              tc_bulk_g2s(sb + BHALF + NT * 16, slab + 12 * p.CoutX, bytes, &full[st]);  // lo, k 4..7
+            }
+            if (++st == (uint32_t)NS) {
+              st = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == TG_MMA_WARP) {
+    // ============================ MMA issuer (warp-uniform, see conv_tc.cu) ============================
+    const uint32_t leader = tc_elect();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    // D = f32, A = B = tf32, both K-major, N = NT, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t a0 = tc_desc(tc_smem_u32(s_stage), 2048, 128), b0 = tc_desc(tc_smem_u32(s_stage) + 8192, (uint32_t)NT * 16, 128);
+    const bool three = p.npass == 3;
+    uint32_t st = 0, ph = 0, ai = 0;
+    for (int item = blockIdx.x; item < p.items; item += p.ctas) {
+      const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
+      tc_mbar_wait(&acce[ab], aph ^ 1, 400 + (int)ab);  // epilogue has drained this accumulator buffer
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d = tmem_u + ab * 128;
+      for (int k = 0; k < KT; ++k) {
+        tc_mbar_wait(&full[st], ph, 500 + (int)st);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (leader) {
+          const uint64_t so = (uint64_t)((st * STAGE) >> 4);
+          const uint64_t a_hi = a0 + so, b_hi = b0 + so;
+          tc_mma(d, a_hi, b_hi, idesc, k > 0 ? 1u : 0u);
+          if (three) {
+            tc_mma(d, a_hi + (4096 >> 4), b_hi, idesc, 1u);
+            tc_mma(d, a_hi, b_hi + (BHALF >> 4), idesc, 1u);
+          }
+          tc_commit(&empty[st]);
+        }
+        __syncwarp();
+        if (++st == (uint32_t)NS) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+      if (leader) tc_commit(&accf[ab]);
+      __syncwarp();
+      ++ai;
+    }
+  } else {
+    // ============================ epilogue ============================
+    const int q = warp;  // TMEM lane quadrant
+    const int m = q * 32 + lane;
+    const bool post = p.out_mul || p.residual || p.act2 != ESM_ACT_NONE;
+    const bool gelu = p.act == ESM_ACT_GELU;
+    const int so = p.transposed ? 2 : 1;
+    uint32_t ai = 0;
+    for (int item = blockIdx.x; item < p.items; item += p.ctas) {
+      const TgItem ti = tg_decode(p, item);
+      const int v = ti.mt * 128 + m;
+      const int jx = v % p.Jw, r = v / p.Jw;
+      const int jy = r % p.Jh, jz = r / p.Jh;
+      const int pzw = ti.phase & 1, pzh = (ti.phase >> 1) & 1, pzd = (p.phases_d == 2) ? ((ti.phase >> 2) & 1) : 0;
+      const int oz = p.transposed ? jz * (p.phases_d == 2 ? 2 : 1) + pzd : jz;
+      const int oy = p.transposed ? jy * so + pzh : jy, ox = p.transposed ? jx * so + pzw : jx;
+      const bool ok = v < voxels && oz < p.Dout && oy < p.Hout && ox < p.Wout;
+      const int co0 = ti.cot * NT;
+      const long long obase = (long long)ti.b * p.oB + (long long)oz * p.oD + (long long)oy * p.oH + ox;
+      float* op = p.out + obase;
+      const float* rp = p.residual ? p.residual + obase : nullptr;
+      const float* mp = p.out_mul ? p.out_mul + (long long)ti.b * p.omB + (long long)oy * p.omH + ox : nullptr;
+      const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
+      tc_mbar_wait(&accf[ab], aph, 600 + (int)ab);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * 128;
+      for (int c8 = 0; c8 < NT; c8 += 8) {
+        float rv[8];
+        tc_ld8(tb + c8, rv);
+        tc_ld_wait();
+        if (c8 + 8 >= NT) {  // last TMEM read of this item: hand the accumulator buffer back
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tc_mbar_arrive(&acce[ab]);
+        }
+        const int co = co0 + c8;
+        if (ok && co < p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int cj = min(co + j, p.Cout - 1);
+            rv[j] = fmaf(rv[j], p.scale ? __ldg(p.scale + cj) : 1.f, p.shift ? __ldg(p.shift + cj) : 0.f);
+          }
+          if (gelu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = tc_gelu(rv[j]);
+          } else if (p.act != ESM_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+              const float4 a = apply_act4(make_float4(rv[j], rv[j + 1], rv[j + 2], rv[j + 3]), p.act);
+              rv[j] = a.x; rv[j + 1] = a.y; rv[j + 2] = a.z; rv[j + 3] = a.w;
+            }
+          }
+          if (post) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (co + j < p.Cout) {
+                if (mp) rv[j] *= __ldg(mp + (long long)(co + j) * p.omC);
+                if (rp) rv[j] += __ldg(rp + (long long)(co + j) * p.oC);
+              }
+            }
+            if (p.act2 != ESM_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 8; j += 4) {
+                const float4 a = apply_act4(make_float4(rv[j], rv[j + 1], rv[j + 2], rv[j + 3]), p.act2);
+                rv[j] = a.x; rv[j + 1] = a.y; rv[j + 2] = a.z; rv[j + 3] = a.w;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (co + j < p.Cout) op[(long long)(co + j) * p.oC] = rv[j] * p.out_scale;
+        }
+      }
+      ++ai;
+    }
+  }
+#ifdef TC_PROFILE
+  if (blockIdx.x == 0 && lane == 0) {
+    printf("tcg_prof warp %2d: done at %8lld clk; waits: empty %8llu (w %8llu)  acce %8llu  full %8llu  accf %8llu\n", warp, clock64() - tc_t0,
+           tc_prof_wait[warp][2], tc_prof_wait[warp][3], tc_prof_wait[warp][4], tc_prof_wait[warp][5], tc_prof_wait[warp][6]);
+    for (int i = 0; i < 8; ++i) tc_prof_wait[warp][i] = 0;
+  }
+#endif
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+}
+
+static long long tcg_launches = 0;
+
+bool tcg_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcgPlan* plan) {
+  if (d->src_mode != ESM_SRC_TENSORS || d->pixel_shuffle || d->in_mul) return false;
+  if (d->Cin < 8 || num_sms <= 0) return false;
+  if (d->stride != 1 && d->stride != 2) return false;
+  if (d->transposed && !(d->kh == 4 && d->kw == 4 && (d->kd == 4 || d->kd == 1) && d->stride == 2)) return false;
+  for (int i = 0; i + 1 < d->nsrc; ++i)
+    if (d->src[i].C % 8) return false;
+  // the producers address one batch item of one source with 32-bit element offsets
+  for (int i = 0; i < d->nsrc; ++i)
+    if ((long long)d->src[i].C * d->src[i].sC >= (1ll << 31) || (long long)d->Din * d->src[i].sD >= (1ll << 31)) return false;
+  const TcgPack tp = tcg_pack_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, d->transposed);
+  if (tp.elems == 0) return false;
+  const int phases_d = (d->transposed && d->kd == 4) ? 2 : 1;
+  const int Jd = d->transposed ? ceil_div(d->Dout, phases_d) : d->Dout;
+  const int Jh = d->transposed ? ceil_div(d->Hout, 2) : d->Hout;
+  const int Jw = d->transposed ? ceil_div(d->Wout, 2) : d->Wout;
+  const long long voxels = (long long)Jd * Jh * Jw;
+  if (voxels >= (1ll << 30)) return false;
+  const int mtiles = (int)ceil_div_ll(voxels, 128);
+  const long long mt_all = (long long)d->B * tp.phases * mtiles;
+  const int KT = tp.ncg * tp.taps;
+  // channel tile: the MMA costs ~max(46, N/2 + 10) clk (A-read bound below N ~ 72), a CTA walks KT slabs per item;
+  // pick the tile count that finishes first
+  double best = 1e30;
+  int best_ncot = 0, best_nt = 0;
+  for (int ncot = 1; ncot <= 16; ++ncot) {
+    const int nt = round_up(ceil_div(tp.CoutX, ncot), 8);
+    if (nt > 128 || (ncot > 1 && (ncot - 1) * nt >= tp.CoutX)) continue;
+    const long long items = mt_all * ncot;
+    const long long waves = ceil_div_ll(items, num_sms);
+    const double mma = (nt / 2.0 + 10.0) > 46.0 ? (nt / 2.0 + 10.0) : 46.0;
+    const double cost = (double)waves * (KT * 3.0 * mma + 600.0 + nt * 12.0);
+    if (cost < best) {
+      best = cost;
+      best_ncot = ncot;
+      best_nt = nt;
+    }
+  }
+  if (!best_ncot) return false;
+  plan->NT = best_nt;
+  plan->ncot = best_ncot;
+  plan->mtiles = mtiles;
+  plan->npass = npass;
+  const size_t stage = 8192 + (size_t)best_nt * 64;
+  const size_t limit = 227 * 1024 - 1024;
+  int ns = (int)(limit / stage);
+  plan->nstages = ns > 12 ? 12 : ns;
+  if (plan->nstages < TG_PD + 1) return false;
+  plan->smem = plan->nstages * stage + 1024;
+  const long long items = mt_all * best_ncot;
+  if (items >= (1ll << 31)) return false;
+  plan->ctas = (int)(items < num_sms ? items : num_sms);
+  (void)KT;
+  return true;
+}
+
+int tcg_conv_launch(const esm_conv_t* d, const TcgPlan& plan, cudaStream_t st) {
+  TcgK k;
+  memset(&k, 0, sizeof(k));
+  for (int i = 0; i < d->nsrc; ++i) k.src[i] = d->src[i];
+  k.nsrc = d->nsrc;
+  const TcgPack tp = tcg_pack_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, d->transposed);
+  k.B = d->B;
+  k.Cin = d->Cin;
+  k.ncg = tp.ncg;
+  k.Din = d->Din;
+  k.Hin = d->Hin;
+  k.Win = d->Win;
+  k.phases_d = (d->transposed && d->kd == 4) ? 2 : 1;
+  k.Jd = d->transposed ? ceil_div(d->Dout, k.phases_d) : d->Dout;
+  k.Jh = d->transposed ? ceil_div(d->Hout, 2) : d->Hout;
+  k.Jw = d->transposed ? ceil_div(d->Wout, 2) : d->Wout;
+  k.Dout = d->Dout;
+  k.Hout = d->Hout;
+  k.Wout = d->Wout;
+  k.Cout = d->Cout;
+  k.KD = tp.KD;
+  k.KH = tp.KH;
+  k.KW = tp.KW;
+  k.taps = tp.taps;
+  k.transposed = d->transposed;
+  k.phases = tp.phases;
+  if (d->transposed) {
+    k.sz = k.sxy = 1;
+    k.od = (k.phases_d == 2) ? -1 : 0;  // input index of tap t at lattice j, phase pz: j + pz - 1 + t
+    k.oh = k.ow = -1;
+  } else {
+    k.sz = d->kd == 1 ? 1 : d->stride;
+    k.sxy = d->stride;
+    k.od = -d->pd;
+    k.oh = -d->ph;
+    k.ow = -d->pw;
+  }
+  k.wtc = d->weight + tp.offset;
+  k.CoutX = tp.CoutX;
+  k.scale = d->scale;
+  k.shift = d->shift;
+  k.act = d->act;
+  k.act2 = d->act2;
+  k.out_mul = d->out_mul;
+  k.omH = d->Wout;
+  k.omC = (long long)d->Hout * d->Wout;
+  k.omB = k.omC * d->Cout;
+  k.residual = d->residual;
+  k.out_scale = d->out_scale;
+  k.out = d->out;
+  k.oB = d->oB;
+  k.oC = d->oC;
+  k.oD = d->oD;
+  k.oH = d->oH;
+  k.NT = plan.NT;
+  k.ncot = plan.ncot;
+  k.mtiles = plan.mtiles;
+  k.items = d->B * tp.phases * plan.mtiles * plan.ncot;
+  k.ctas = plan.ctas;
+  k.nstages = plan.nstages;
+  k.npass = plan.npass;
+  if (cudaFuncSetAttribute((const void*)tcg_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    return check_launch("conv(tcg, cudaFuncSetAttribute)");
+  tcg_conv_kernel<<<(unsigned)plan.ctas, TG_THREADS, plan.smem, st>>>(k);
+  ++tcg_launches;
+  return check_launch("conv(tcg)");
+}
+
+}  // namespace esm
+
+extern "C" long long esm_tcg_conv_launches(void) { return esm::tcg_launches; }

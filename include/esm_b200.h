@@ -105,6 +105,9 @@ int esm_conv_f32(const esm_conv_t* desc, void* stream);
  * it wins the on-device timing or ESM_TC_FORCE is set; ESM_TC=0 disables it, ESM_TC=1 selects the
  * single-pass TF32 fast mode instead of the fp32-grade split).  Diagnostics / tests. */
 long long esm_tc_conv_launches(void);
+/* Same for the streamed-weight tcgen05 engine (taps in K, weights through the operand ring: wide / strided /
+ * transposed layers; ESM_TC_FORCE=2 forces it wherever eligible, ESM_TCG_OFF=1 disables it). */
+long long esm_tcg_conv_launches(void);
 
 /* build_gwc_volume (submodule.py:151-161): L,R [B,C,H,W] -> V [B,G,D,H,W]; writes the zero
  * triangle itself (no memset). */

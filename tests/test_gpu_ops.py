@@ -410,3 +410,75 @@ def test_conv_tensor_core_pointwise_concat(tc_forced):
     got = ops.conv([s.cuda() for s in srcs], gpu_pack(p, 1, 0, False), "gelu")
     assert tc_forced() == n0 + 2
     assert rel(got, want) < 2e-5
+
+
+# ---- streamed-weight tcgen05 engine (conv_tcg.cu: taps in K, weights through the ring): forced on ----
+TCG_CASES = [
+    # name, nd, cin, cout, k, stride, pad, transposed, act, in_shape, batch
+    ("tcg3d_40_40", 3, 40, 40, 3, 1, 1, False, "gelu", (5, 9, 31), 1),
+    ("tcg3d_72_72", 3, 72, 72, 3, 1, 1, False, "gelu", (3, 6, 20), 2),
+    ("tcg3d_8_24_s2", 3, 8, 24, 3, 2, 1, False, "gelu", (12, 18, 40), 1),
+    ("tcg3d_odd_40_72_s2", 3, 40, 72, 3, 2, 1, False, "gelu", (3, 5, 7), 1),
+    ("tcg3d_deconv_72_40", 3, 72, 40, 4, 2, 1, True, "gelu", (2, 3, 5), 1),
+    ("tcg3d_deconv_40_24", 3, 40, 24, 4, 2, 1, True, "gelu", (3, 6, 20), 2),
+    ("tcg3d_deconv_24_1", 3, 24, 1, 4, 2, 1, True, None, (4, 6, 13), 2),
+    ("tcg2d_240_240", 2, 240, 240, 3, 1, 1, False, "gelu", (6, 20), 1),   # several channel tiles
+    ("tcg2d_deconv_208_120", 2, 208, 120, 4, 2, 1, True, "gelu", (3, 10), 1),
+    ("tcg2d_120_208_s2", 2, 120, 208, 3, 2, 1, False, "gelu", (6, 20), 1),
+    ("tcg2d_12_12_padded_cin", 2, 12, 12, 3, 1, 1, False, "gelu", (9, 21), 1),
+    ("tcg2d_k1_112_32", 2, 112, 32, 1, 1, 0, False, "gelu", (9, 33), 1),
+    ("tcg2d_k1p1_32_32", 2, 32, 32, 1, 1, 1, False, "gelu", (10, 38), 1),
+    ("tcg2d_s2_32_32", 2, 32, 32, 3, 2, 1, False, "gelu", (12, 40), 2),
+    ("tcg2d_big", 2, 16, 24, 3, 1, 1, False, "silu", (70, 150), 1),       # many voxel tiles per CTA (ring wrap, 2 accumulators)
+]
+
+
+@pytest.fixture
+def tcg_forced(monkeypatch):
+    monkeypatch.setenv("ESM_TC_FORCE", "2")
+    monkeypatch.setenv("ESM_TC", "3")
+    from esmstereo_b200 import _lib
+    return _lib.lib().esm_tcg_conv_launches
+
+
+@pytest.mark.parametrize("case", TCG_CASES, ids=[c[0] for c in TCG_CASES])
+def test_conv_streamed_tensor_core_path(case, tcg_forced):
+    name, nd, cin, cout, k, stride, pad, transposed, act, sp, B = case
+    ops = _ops()
+    p = make_layer(cin, cout, k, nd, transposed=transposed, bn=act is not None, seed=len(name))
+    x = rnd(B, cin, *sp, seed=3)
+    want = ref_conv(x, p, stride, pad, transposed, act, nd)
+    n0 = tcg_forced()
+    got = ops.conv(x.cuda(), gpu_pack(p, stride, pad, transposed), act)
+    assert tcg_forced() == n0 + 1, "layer did not take the streamed-weight tensor-core path"
+    assert rel(got, want) < 2e-5, name
+
+
+def test_conv_streamed_tensor_core_fusions(tcg_forced):
+    ops = _ops()
+    # aggregation.agg_0.0: cat(cropped deconv output, skip) -> k1 conv
+    a_full = rnd(1, 40, 4, 6, 10, seed=1)
+    b = rnd(1, 40, 3, 5, 9, seed=2)
+    p = make_layer(80, 40, 1, 3, seed=5)
+    want = ref_conv(torch.cat((a_full[:, :, :3, :5, :9], b), 1), p, 1, 0, False, "gelu", 3)
+    n0 = tcg_forced()
+    got = ops.conv([a_full.cuda()[:, :, :3, :5, :9], b.cuda()], gpu_pack(p, 1, 0, False), "gelu")
+    assert tcg_forced() == n0 + 1
+    assert rel(got, want) < 2e-5
+    # concat + residual + second activation + scale, k3
+    a, b2 = rnd(2, 16, 11, 45, seed=1), rnd(2, 8, 11, 45, seed=2)
+    p = make_layer(24, 16, 3, 2, bias=True, seed=3)
+    res = rnd(2, 16, 11, 45, seed=4)
+    want = torch.sigmoid(ref_conv(torch.cat((a, b2), 1), p, 1, 1, False, "gelu", 2) + res) * 3.0
+    got = ops.conv([a.cuda(), b2.cuda()], gpu_pack(p, 1, 1, False), "gelu", residual=res.cuda(), act2="sigmoid", out_scale=3.0)
+    assert tcg_forced() == n0 + 2
+    assert rel(got, want) < 2e-5
+    # transposed conv cropped to the skip's extent (ESMStereo.py:172), out_mul broadcast over D
+    x = rnd(1, 40, 3, 6, 20, seed=7)
+    p = make_layer(40, 24, 4, 3, transposed=True, seed=8)
+    full = ref_conv(x, p, 2, 1, True, "gelu", 3)
+    att = rnd(1, 24, 11, 39, seed=9)
+    want = full[:, :, :5, :11, :39] * att.unsqueeze(2)
+    got = ops.conv(x.cuda(), gpu_pack(p, 2, 1, True), "gelu", out_size=(5, 11, 39), out_mul=att.cuda())
+    assert tcg_forced() == n0 + 3
+    assert rel(got, want) < 2e-5

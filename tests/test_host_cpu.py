@@ -31,12 +31,14 @@ def test_argument_errors_need_no_gpu():
     assert L.esm_gwc_volume_f32(None, None, None, 1, 64, 4, 8, 4, 32, None) == -1
     assert b"null" in L.esm_last_error()
     assert L.esm_conv_f32(None, None) == -1
+    # fp32 pack [phase][tap][Cin_pad][Cout_pad] + (Cin >= 8) the split-TF32 slabs of the streamed tcgen05 engine:
+    # phases * taps * ceil(Cin/8) slabs of [hi|lo][2][round_up(Cout,8)][4]
     n = L.esm_packed_weight_elems(8, 32, 3, 3, 3, 0)
-    assert n == 27 * 32 * 8
-    assert L.esm_packed_weight_elems(40, 72, 4, 4, 4, 1) == 8 * 8 * 72 * 40
-    assert L.esm_packed_weight_elems(72, 8, 1, 1, 1, 0) == 8 * 80   # Cout 72 -> 2 CTAs x 40 channels
-    assert L.esm_packed_weight_elems(1, 24, 4, 4, 4, 1) == 8 * 8 * 24 * 4   # Cout=1 padded to 4 (16-byte weight rows)
-    assert L.esm_packed_weight_elems(32, 1, 1, 5, 5, 0) == 25 * 1 * 32      # Cin=1 keeps CK=1
+    assert n == 27 * 32 * 8 + 27 * 4 * 16 * 8
+    assert L.esm_packed_weight_elems(40, 72, 4, 4, 4, 1) == 8 * 8 * 72 * 40 + 8 * 8 * 9 * 16 * 40
+    assert L.esm_packed_weight_elems(72, 8, 1, 1, 1, 0) == 8 * 80 + 1 * 1 * 16 * 72   # Cout 72 -> 2 CTAs x 40 channels
+    assert L.esm_packed_weight_elems(1, 24, 4, 4, 4, 1) == 8 * 8 * 24 * 4 + 8 * 8 * 3 * 16 * 8   # Cout=1 padded to 4 (16-byte weight rows)
+    assert L.esm_packed_weight_elems(32, 1, 1, 5, 5, 0) == 25 * 1 * 32      # Cin=1 keeps CK=1, no tensor-core slabs
 
 
 def test_no_cpu_fallback():
