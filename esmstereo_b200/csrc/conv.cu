@@ -117,8 +117,11 @@ static PackGeom pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transpo
 }
 
 // Second region of a packed weight, right after the fp32 pack: the operand slabs of the streamed-weight tcgen05
-// path (conv_tcg.cu), already split for the fp32-grade TF32 scheme.  One slab per (phase, tap, 8-channel group):
-//   [hi | lo][k / 4][CoutX][k % 4]   (K-major, no-swizzle UMMA B tile; a CTA's channel tile is a row range of it)
+// path (conv_tcg.cu), already split for the fp32-grade TF32 scheme.  One slab per (phase, 8-channel group, tap), in
+// that order, laid out as 8-row groups of four 128-byte UMMA core matrices (K-major, no swizzle):
+//   [co / 8][hi | lo][k / 4][co % 8][k % 4]
+// so that a CTA's channel tile of a slab -- and, when one tile covers every channel, the slabs of consecutive taps --
+// is one contiguous TMA bulk copy (LBO = 128 B between the K halves, SBO = 512 B between row groups).
 TcgPack tcg_pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed) {
   const PackGeom g = pack_geom(Cout, Cin, kd, kh, kw, transposed);
   TcgPack t;
@@ -169,10 +172,10 @@ __global__ void pack_tcg_kernel(const float* __restrict__ w, float* __restrict__
   asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
   const float hi = __uint_as_float(hb);
   asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
-  const long long slab = ((((long long)z * KD + tdd) * KH + thh) * KW + tw) * ncg + cg;  // 16 * CoutX floats each
-  float* o = out + slab * 16 * CoutX + (k >> 2) * (4 * CoutX) + co * 4 + (k & 3);
+  const long long slab = (((long long)z * ncg + cg) * KD + tdd) * KH * KW + thh * KW + tw;  // 16 * CoutX floats each
+  float* o = out + slab * 16 * CoutX + (co >> 3) * 128 + (k >> 2) * 32 + (co & 7) * 4 + (k & 3);
   o[0] = hi;
-  o[8 * CoutX] = __uint_as_float(lb);
+  o[64] = __uint_as_float(lb);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -15,7 +15,12 @@
 // Warp roles (448 threads, 1 CTA/SM, persistent): warps 0-3 epilogue (one per TMEM lane quadrant: TMEM -> BN /
 // activation -> global), warp 4 MMA issuer (warp-uniform, one elected lane), warp 5 weight streamer (one lane: four
 // bulk copies per slab, completing on the stage's `full` barrier), warps 6-13 A-operand producers (predicated
-// global loads, four in flight per thread, split into hi / lo, stored as K-major non-swizzled UMMA tiles).
+// global loads split into hi / lo and stored as K-major non-swizzled UMMA tiles).  A ring stage holds
+// G = GC x GD x KW^2 (channel group, tap) slabs -- 9 for k3, 8 for the transposed layers -- with every tap offset
+// a compile-time constant: the fence.proxy.async that publishes the producers' shared-memory stores compiles to
+// MEMBAR.ALL.CTA, which also waits for the loads already in flight for the next stage, so a stage pays one global
+// load latency (measured 844 clk per slab with one-slab stages), and a generic per-slab tap cursor unrolled nine
+// times was 2900 instructions per stage (instruction-cache bound).
 #include "conv_tc.cuh"
 #include "tc_common.cuh"
 
@@ -55,7 +60,6 @@ constexpr int TG_W_WARP = TG_NEW + 1;          // weight streamer
 constexpr int TG_PROD_WARP = TG_NEW + 2;       // first A producer warp
 constexpr int TG_NTW = 8;                      // A producer warps
 constexpr int TG_THREADS = 32 * (TG_NEW + 2 + TG_NTW);
-constexpr int TG_PD = 4;                       // loads in flight per producer thread (slabs ahead)
 
 struct TgItem {
   int b, phase, mt, cot;
@@ -71,22 +75,28 @@ __device__ __forceinline__ TgItem tg_decode(const TcgK& p, int item) {
   return t;
 }
 
+// KW = KH: 3 (k3) or 2 (sub-pixel phase of a transposed k4 s2).  A stage covers GC channel groups x GD depth taps x
+// KW x KW taps; slab g = ((gc * GD + gd) * KW + th) * KW + tw.
+template <int KW, int GD, int GC>
 __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_constant__ TcgK p) {
+  constexpr int G = GC * GD * KW * KW;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef TC_PROFILE
   const long long tc_t0 = clock64();
 #endif
   const int NT = p.NT, NS = p.nstages;
-  const uint32_t BHALF = (uint32_t)NT * 32;           // bytes of the hi (or lo) B tile: [2][NT][4] floats
-  const uint32_t STAGE = 8192 + 2 * BHALF;            // A hi | A lo | B hi | B lo
+  const uint32_t BSLAB = (uint32_t)NT * 64;           // bytes of one B slab: [NT / 8][hi | lo][k / 4][8][4] floats
+  const uint32_t STAGE = (uint32_t)G * (8192 + BSLAB);  // G A slabs (hi 4 KB | lo 4 KB each), then G B slabs
+  const uint32_t BOFF = (uint32_t)G * 8192;
   uint8_t* s_stage = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NS * STAGE);
   uint64_t* empty = full + NS;
   uint64_t* accf = empty + NS;
   uint64_t* acce = accf + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + 2);
-  const int KT = p.ncg * p.taps;  // K steps (slabs) per item
+  const int ZST = p.KD / GD;                             // depth-tap stages per channel-group block
+  const int SPI = ((p.ncg + GC - 1) / GC) * ZST;         // ring stages per item; the last block may hold fewer groups
   const int voxels = p.Jd * p.Jh * p.Jw;
 
   if (tid == 0) {
@@ -115,27 +125,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
     const int q = (tw >> 1) & 3;   // TMEM lane quadrant = rows q*32 .. q*32+31 of the tile
     const int khalf = tw & 1;      // which 4 of the 8 channels of a group
     const int m = q * 32 + lane;   // A row
-    // load cursor
-    int item = blockIdx.x, cg = 0, td = 0, th = 0, tww = 0;
+    // load cursor: (item, cg0, td0) names a stage
+    int item = blockIdx.x, cg0 = 0, td0 = 0, cur_b = 0;
     int iz0 = 0, iy0 = 0, ix0 = 0;  // input coordinate of tap (0,0,0) for this thread's voxel
     bool vox_ok = false;
-    const float* bptr = nullptr;    // source base of the current channel group (+ batch)
-    int sC = 0, sD = 0, sH = 0, nch = 0, boff = 0;
-    auto enter_group = [&](int b) {
-      int rel = cg * 8 + khalf * 4, k = 0;
-      while (k < p.nsrc - 1 && rel >= p.src[k].C) {  // host guarantees 8-channel groups never straddle sources
-        rel -= p.src[k].C;
-        ++k;
-      }
-      const esm_src_t& s = p.src[k];
-      sC = (int)s.sC;
-      sD = (int)s.sD;
-      sH = (int)s.sH;
-      nch = s.C - rel;  // valid channels from `rel` on (<= 0 past the last group)
-      bptr = s.ptr + (long long)b * s.sB;
-      boff = rel * sC;
-    };
-    int cur_b = 0;
     auto enter_item = [&]() {
       if (item >= p.items) return;
       const TgItem ti = tg_decode(p, item);
@@ -148,47 +141,79 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
       iy0 = jy * p.sxy + p.oh + (p.transposed ? pzh : 0);
       ix0 = jx * p.sxy + p.ow + (p.transposed ? pzw : 0);
       cur_b = ti.b;
-      cg = 0;
-      td = th = tww = 0;
-      enter_group(cur_b);
+      cg0 = td0 = 0;
     };
-    auto load = [&](float (&v)[4]) {
-      const int iz = iz0 + td, iy = iy0 + th, ix = ix0 + tww;
-      const bool ok = vox_ok && (unsigned)iz < (unsigned)p.Din && (unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win;
-      const int off = boff + iz * sD + iy * sH + ix;
+    // issues the loads of one stage (all of them before any use) and steps the cursor; returns the slabs loaded
+    auto load_stage = [&](float (&v)[G][4]) -> int {
+      if (item >= p.items) return 0;
+      const int ngc = min(GC, p.ncg - cg0);
+      bool xok[KW], yok[KW];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) v[c] = (ok && c < nch) ? __ldg(bptr + (off + c * sC)) : 0.f;
-    };
-    auto advance = [&]() {
-      if (++tww < p.KW) return;
-      tww = 0;
-      if (++th < p.KH) return;
-      th = 0;
-      if (++td < p.KD) return;
-      td = 0;
-      if (++cg < p.ncg) {
-        enter_group(cur_b);
-        return;
+      for (int t = 0; t < KW; ++t) {
+        xok[t] = (unsigned)(ix0 + t) < (unsigned)p.Win;
+        yok[t] = (unsigned)(iy0 + t) < (unsigned)p.Hin;
       }
-      item += p.ctas;
-      enter_item();
+#pragma unroll
+      for (int gc = 0; gc < GC; ++gc) {
+        if (gc < ngc) {
+          int rel = (cg0 + gc) * 8 + khalf * 4, k = 0;
+          while (k < p.nsrc - 1 && rel >= p.src[k].C) {  // host guarantees 8-channel groups never straddle sources
+            rel -= p.src[k].C;
+            ++k;
+          }
+          const esm_src_t& sr = p.src[k];
+          const int sC = (int)sr.sC, sD = (int)sr.sD, sH = (int)sr.sH;
+          const int nch = sr.C - rel;  // valid channels from `rel` on (<= 0 past the last group)
+          const float* bp = sr.ptr + (long long)cur_b * sr.sB;
+          const int off0 = rel * sC + (iz0 + td0) * sD + iy0 * sH + ix0;
+#pragma unroll
+          for (int gd = 0; gd < GD; ++gd) {
+            const bool zok = vox_ok && (unsigned)(iz0 + td0 + gd) < (unsigned)p.Din;
+#pragma unroll
+            for (int th = 0; th < KW; ++th) {
+#pragma unroll
+              for (int tw = 0; tw < KW; ++tw) {
+                const bool ok = zok && yok[th] && xok[tw];
+                const int off = off0 + gd * sD + th * sH + tw;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[((gc * GD + gd) * KW + th) * KW + tw][c] = (ok && c < nch) ? __ldg(bp + (off + c * sC)) : 0.f;
+              }
+            }
+          }
+        }
+      }
+      td0 += GD;
+      if (td0 >= p.KD) {
+        td0 = 0;
+        cg0 += GC;
+        if (cg0 >= p.ncg) {
+          item += p.ctas;
+          enter_item();
+        }
+      }
+      return ngc * (GD * KW * KW);
     };
     uint32_t st = 0, ph = 0;
-    auto store_stage = [&](const float (&v)[4]) {
+    auto store_stage = [&](const float (&v)[G][4], int nv) {
       tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
       uint8_t* sb = s_stage + (size_t)st * STAGE + khalf * 2048 + m * 16;
-      float4 hi, lo;
-      hi.x = tc_rna(v[0]);
-      hi.y = tc_rna(v[1]);
-      hi.z = tc_rna(v[2]);
-      hi.w = tc_rna(v[3]);
-      *reinterpret_cast<float4*>(sb) = hi;
-      if (p.npass == 3) {
-        lo.x = tc_rna(v[0] - hi.x);
-        lo.y = tc_rna(v[1] - hi.y);
-        lo.z = tc_rna(v[2] - hi.z);
-        lo.w = tc_rna(v[3] - hi.w);
-        *reinterpret_cast<float4*>(sb + 4096) = lo;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (g < nv) {
+          float4 hi, lo;
+          hi.x = tc_rna(v[g][0]);
+          hi.y = tc_rna(v[g][1]);
+          hi.z = tc_rna(v[g][2]);
+          hi.w = tc_rna(v[g][3]);
+          *reinterpret_cast<float4*>(sb + g * 8192) = hi;
+          if (p.npass == 3) {
+            lo.x = tc_rna(v[g][0] - hi.x);
+            lo.y = tc_rna(v[g][1] - hi.y);
+            lo.z = tc_rna(v[g][2] - hi.z);
+            lo.w = tc_rna(v[g][3] - hi.w);
+            *reinterpret_cast<float4*>(sb + g * 8192 + 4096) = lo;
+          }
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
       __syncwarp();
@@ -198,52 +223,43 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
         ph ^= 1;
       }
     };
-    // TG_PD register buffers: the loads of slab i + TG_PD are issued right after slab i is stored
-    float v[TG_PD][4];
-    long long remaining = 0;  // slabs this CTA still has to store
-    for (int it = blockIdx.x; it < p.items; it += p.ctas) remaining += KT;
+    // two register buffers, loop unrolled by two: the loads of stage i+1 are in flight while stage i is converted
+    // and stored
+    float va[G][4], vb[G][4];
     enter_item();
-#pragma unroll
-    for (int i = 0; i < TG_PD; ++i) {
-      if (item < p.items) {
-        load(v[i]);
-        advance();
-      }
-    }
-    while (remaining > 0) {
-#pragma unroll
-      for (int i = 0; i < TG_PD; ++i) {
-        if (remaining > 0) {
-          store_stage(v[i]);
-          --remaining;
-          if (item < p.items) {
-            load(v[i]);
-            advance();
-          }
-        }
-      }
+    int na = load_stage(va), nb = 0;
+    while (na > 0) {
+      nb = load_stage(vb);
+      store_stage(va, na);
+      if (nb == 0) break;
+      na = load_stage(va);
+      store_stage(vb, nb);
     }
   } else if (warp == TG_W_WARP) {
     // ============================ weight streamer ============================
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
       const long long slab_floats = 16ll * p.CoutX;
+      constexpr int TPB = GD * KW * KW;  // taps of one channel group in a stage: consecutive slabs of the pack
       for (int item = blockIdx.x; item < p.items; item += p.ctas) {
         const TgItem ti = tg_decode(p, item);
         const int n0 = ti.cot * NT;
         const int rows = min(NT, p.CoutX - n0);
-        const uint32_t bytes = (uint32_t)rows * 16;
-        for (int cg = 0; cg < p.ncg; ++cg) {
-          for (int tap = 0; tap < p.taps; ++tap) {
-            const float* slab = p.wtc + ((long long)(ti.phase * p.taps + tap) * p.ncg + cg) * slab_floats + n0 * 4;
+        const uint32_t bytes = (uint32_t)rows * 64;
+        const bool whole = p.ncot == 1;  // the tile is the whole slab: the TPB slabs of a group are one contiguous copy
+        for (int cg0 = 0; cg0 < p.ncg; cg0 += GC) {
+          const int ngc = min(GC, p.ncg - cg0);
+          for (int td0 = 0; td0 < p.KD; td0 += GD) {
             tc_mbar_wait(&empty[st], ph ^ 1, 300 + (int)st);
-            uint8_t* sb = s_stage + (size_t)st * STAGE + 8192;
-            tc_mbar_expect_tx(&full[st], (p.npass == 3 ? 4u : 2u) * bytes);
-            tc_bulk_g2s(sb, slab, bytes, &full[st]);                                     // hi, k 0..3
-            tc_bulk_g2s(sb + NT * 16, slab + 4 * p.CoutX, bytes, &full[st]);            // hi, k 4..7
-            if (p.npass == 3) {
-              tc_bulk_g2s(sb + BHALF, slab + 8 * p.CoutX, bytes, &full[st]);             // lo, k 0..3
-              tc_bulk_g2s(sb + BHALF + NT * 16, slab + 12 * p.CoutX, bytes, &full[st]);  // lo, k 4..7
+            tc_mbar_expect_tx(&full[st], (uint32_t)(ngc * TPB) * bytes);
+            uint8_t* sb = s_stage + (size_t)st * STAGE + BOFF;
+            for (int gc = 0; gc < ngc; ++gc) {
+              const float* src = p.wtc + (((long long)ti.phase * p.ncg + cg0 + gc) * p.taps + td0 * KW * KW) * slab_floats + n0 * 16;
+              if (whole) {
+                tc_bulk_g2s(sb + (size_t)(gc * TPB) * BSLAB, src, TPB * bytes, &full[st]);
+              } else {
+                for (int t = 0; t < TPB; ++t) tc_bulk_g2s(sb + (size_t)(gc * TPB + t) * BSLAB, src + t * slab_floats, bytes, &full[st]);
+              }
             }
             if (++st == (uint32_t)NS) {
               st = 0;
@@ -259,7 +275,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
     // D = f32, A = B = tf32, both K-major, N = NT, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-    const uint64_t a0 = tc_desc(tc_smem_u32(s_stage), 2048, 128), b0 = tc_desc(tc_smem_u32(s_stage) + 8192, (uint32_t)NT * 16, 128);
+    const uint64_t a0 = tc_desc(tc_smem_u32(s_stage), 2048, 128), b0 = tc_desc(tc_smem_u32(s_stage) + BOFF, 128, 512);
     const bool three = p.npass == 3;
     uint32_t st = 0, ph = 0, ai = 0;
     for (int item = blockIdx.x; item < p.items; item += p.ctas) {
@@ -267,16 +283,19 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
       tc_mbar_wait(&acce[ab], aph ^ 1, 400 + (int)ab);  // epilogue has drained this accumulator buffer
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d = tmem_u + ab * 128;
-      for (int k = 0; k < KT; ++k) {
+      for (int sg = 0; sg < SPI; ++sg) {
+        const int nv = min(GC, p.ncg - (sg / ZST) * GC) * (GD * KW * KW);
         tc_mbar_wait(&full[st], ph, 500 + (int)st);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (leader) {
           const uint64_t so = (uint64_t)((st * STAGE) >> 4);
-          const uint64_t a_hi = a0 + so, b_hi = b0 + so;
-          tc_mma(d, a_hi, b_hi, idesc, k > 0 ? 1u : 0u);
-          if (three) {
-            tc_mma(d, a_hi + (4096 >> 4), b_hi, idesc, 1u);
-            tc_mma(d, a_hi, b_hi + (BHALF >> 4), idesc, 1u);
+          for (int g = 0; g < nv; ++g) {
+            const uint64_t a_hi = a0 + so + (uint64_t)((g * 8192) >> 4), b_hi = b0 + so + (uint64_t)((g * BSLAB) >> 4);
+            tc_mma(d, a_hi, b_hi, idesc, (sg | g) ? 1u : 0u);
+            if (three) {
+              tc_mma(d, a_hi + (4096 >> 4), b_hi, idesc, 1u);
+              tc_mma(d, a_hi, b_hi + (256 >> 4), idesc, 1u);
+            }
           }
           tc_commit(&empty[st]);
         }
@@ -385,6 +404,7 @@ bool tcg_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcgPlan* plan) {
   if (d->Cin < 8 || num_sms <= 0) return false;
   if (d->stride != 1 && d->stride != 2) return false;
   if (d->transposed && !(d->kh == 4 && d->kw == 4 && (d->kd == 4 || d->kd == 1) && d->stride == 2)) return false;
+  if (!d->transposed && !(d->kh == 3 && d->kw == 3 && (d->kd == 3 || d->kd == 1))) return false;  // k1 / k5 stay on the other engines
   for (int i = 0; i + 1 < d->nsrc; ++i)
     if (d->src[i].C % 8) return false;
   // the producers address one batch item of one source with 32-bit element offsets
@@ -408,6 +428,7 @@ bool tcg_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcgPlan* plan) {
   for (int ncot = 1; ncot <= 16; ++ncot) {
     const int nt = round_up(ceil_div(tp.CoutX, ncot), 8);
     if (nt > 128 || (ncot > 1 && (ncot - 1) * nt >= tp.CoutX)) continue;
+    if (2 * (d->transposed ? 8 : 9) * (8192 + (size_t)nt * 64) > 227 * 1024 - 1024) continue;  // two ring stages must fit
     const long long items = mt_all * ncot;
     const long long waves = ceil_div_ll(items, num_sms);
     const double mma = (nt / 2.0 + 10.0) > 46.0 ? (nt / 2.0 + 10.0) : 46.0;
@@ -423,16 +444,16 @@ bool tcg_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcgPlan* plan) {
   plan->ncot = best_ncot;
   plan->mtiles = mtiles;
   plan->npass = npass;
-  const size_t stage = 8192 + (size_t)best_nt * 64;
+  const size_t slab = 8192 + (size_t)best_nt * 64;
   const size_t limit = 227 * 1024 - 1024;
-  int ns = (int)(limit / stage);
-  plan->nstages = ns > 12 ? 12 : ns;
-  if (plan->nstages < TG_PD + 1) return false;
-  plan->smem = plan->nstages * stage + 1024;
+  const int G = d->transposed ? 8 : 9;
+  int ns = (int)(limit / (G * slab));
+  if (ns < 2) return false;
+  plan->nstages = ns > 4 ? 4 : ns;
+  plan->smem = plan->nstages * G * slab + 1024;
   const long long items = mt_all * best_ncot;
   if (items >= (1ll << 31)) return false;
   plan->ctas = (int)(items < num_sms ? items : num_sms);
-  (void)KT;
   return true;
 }
 
@@ -497,9 +518,10 @@ int tcg_conv_launch(const esm_conv_t* d, const TcgPlan& plan, cudaStream_t st) {
   k.ctas = plan.ctas;
   k.nstages = plan.nstages;
   k.npass = plan.npass;
-  if (cudaFuncSetAttribute((const void*)tcg_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+  void (*fn)(const TcgK) = !d->transposed ? tcg_conv_kernel<3, 1, 1> : (d->kd == 4 ? tcg_conv_kernel<2, 2, 1> : tcg_conv_kernel<2, 1, 2>);
+  if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return check_launch("conv(tcg, cudaFuncSetAttribute)");
-  tcg_conv_kernel<<<(unsigned)plan.ctas, TG_THREADS, plan.smem, st>>>(k);
+  fn<<<(unsigned)plan.ctas, TG_THREADS, plan.smem, st>>>(k);
   ++tcg_launches;
   return check_launch("conv(tcg)");
 }

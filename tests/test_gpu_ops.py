@@ -426,8 +426,6 @@ TCG_CASES = [
     ("tcg2d_deconv_208_120", 2, 208, 120, 4, 2, 1, True, "gelu", (3, 10), 1),
     ("tcg2d_120_208_s2", 2, 120, 208, 3, 2, 1, False, "gelu", (6, 20), 1),
     ("tcg2d_12_12_padded_cin", 2, 12, 12, 3, 1, 1, False, "gelu", (9, 21), 1),
-    ("tcg2d_k1_112_32", 2, 112, 32, 1, 1, 0, False, "gelu", (9, 33), 1),
-    ("tcg2d_k1p1_32_32", 2, 32, 32, 1, 1, 1, False, "gelu", (10, 38), 1),
     ("tcg2d_s2_32_32", 2, 32, 32, 3, 2, 1, False, "gelu", (12, 40), 2),
     ("tcg2d_big", 2, 16, 24, 3, 1, 1, False, "silu", (70, 150), 1),       # many voxel tiles per CTA (ring wrap, 2 accumulators)
 ]
@@ -456,13 +454,13 @@ def test_conv_streamed_tensor_core_path(case, tcg_forced):
 
 def test_conv_streamed_tensor_core_fusions(tcg_forced):
     ops = _ops()
-    # aggregation.agg_0.0: cat(cropped deconv output, skip) -> k1 conv
+    # cat(cropped 3D view, skip) -> k3 conv (three sources' worth of channel groups, 3D crop strides)
     a_full = rnd(1, 40, 4, 6, 10, seed=1)
     b = rnd(1, 40, 3, 5, 9, seed=2)
-    p = make_layer(80, 40, 1, 3, seed=5)
-    want = ref_conv(torch.cat((a_full[:, :, :3, :5, :9], b), 1), p, 1, 0, False, "gelu", 3)
+    p = make_layer(80, 40, 3, 3, seed=5)
+    want = ref_conv(torch.cat((a_full[:, :, :3, :5, :9], b), 1), p, 1, 1, False, "gelu", 3)
     n0 = tcg_forced()
-    got = ops.conv([a_full.cuda()[:, :, :3, :5, :9], b.cuda()], gpu_pack(p, 1, 0, False), "gelu")
+    got = ops.conv([a_full.cuda()[:, :, :3, :5, :9], b.cuda()], gpu_pack(p, 1, 1, False), "gelu")
     assert tcg_forced() == n0 + 1
     assert rel(got, want) < 2e-5
     # concat + residual + second activation + scale, k3
