@@ -33,6 +33,7 @@ class EsmConv(C.Structure):
         ("out_mul", vp), ("residual", vp), ("act2", C.c_int), ("out_scale", C.c_float),
         ("pixel_shuffle", C.c_int), ("out", vp),
         ("oB", C.c_longlong), ("oC", C.c_longlong), ("oD", C.c_longlong), ("oH", C.c_longlong),
+        ("engine", C.c_int),
     ]
 
 

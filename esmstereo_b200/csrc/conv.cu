@@ -617,7 +617,7 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   // tensor-core policy: ESM_TC=0 off, 3 (default) split-TF32 (fp32-grade), 1 single-pass TF32 (fast mode);
   // ESM_TC_FORCE=1 takes the tensor-core path whenever the layer is eligible (tests), else it must win the timing
   const char* tc_env = getenv("ESM_TC");
-  const int tc_pass = tc_env ? atoi(tc_env) : 3;
+  const int tc_pass = d->engine == 1 ? 0 : (tc_env ? atoi(tc_env) : 3);
   // ESM_TC_FORCE=1 forces the resident-weight engine, =2 the streamed-weight engine, wherever eligible
   const int tc_force = (getenv("ESM_TC_FORCE") != nullptr && tc_pass != 0) ? (atoi(getenv("ESM_TC_FORCE")) == 2 ? 2 : 1) : 0;
   PlanKey key = {{d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed, lg.Jw, lg.Jh, lg.Jd, gwc ? k.cpg : 0, d->B, d->pd,

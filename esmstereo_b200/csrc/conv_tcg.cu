@@ -98,6 +98,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
   const int ZST = p.KD / GD;                             // depth-tap stages per channel-group block
   const int SPI = ((p.ncg + GC - 1) / GC) * ZST;         // ring stages per item; the last block may hold fewer groups
   const int voxels = p.Jd * p.Jh * p.Jw;
+  // Accumulator layout (256 TMEM columns per buffer, two buffers).  The tensor core truncates its fp32 accumulator on
+  // every accumulate, a bias that grows with the chain length: with all 3 * ncg * taps MMAs of an item chained into
+  // one accumulator the 240->240 layer was 7x less accurate than the fp32 pipe (feature error 1.4e-5 vs 2e-6).  So
+  // the hi*hi products -- the only ones whose magnitude matters -- go round-robin by stage into P partial accumulators
+  // (chains of ~27 MMAs, like the resident-weight engine's), the two correction products into one more, and the
+  // epilogue adds the P + 1 columns of a channel in fp32 with round-to-nearest.
+  const int P = max(1, min(8, 256 / NT - 1));
+  const int Pe = min(P, SPI);  // partials an item actually writes
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(256) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -282,7 +290,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
       const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
       tc_mbar_wait(&acce[ab], aph ^ 1, 400 + (int)ab);  // epilogue has drained this accumulator buffer
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d = tmem_u + ab * 128;
+      const uint32_t dbuf = tmem_u + ab * 256, dcorr = dbuf + P * NT;
+      int part = 0;
       for (int sg = 0; sg < SPI; ++sg) {
         const int nv = min(GC, p.ncg - (sg / ZST) * GC) * (GD * KW * KW);
         tc_mbar_wait(&full[st], ph, 500 + (int)st);
@@ -291,15 +300,16 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
           const uint64_t so = (uint64_t)((st * STAGE) >> 4);
           for (int g = 0; g < nv; ++g) {
             const uint64_t a_hi = a0 + so + (uint64_t)((g * 8192) >> 4), b_hi = b0 + so + (uint64_t)((g * BSLAB) >> 4);
-            tc_mma(d, a_hi, b_hi, idesc, (sg | g) ? 1u : 0u);
+            tc_mma(dbuf + part * NT, a_hi, b_hi, idesc, (sg >= P || g) ? 1u : 0u);
             if (three) {
-              tc_mma(d, a_hi + (4096 >> 4), b_hi, idesc, 1u);
-              tc_mma(d, a_hi, b_hi + (256 >> 4), idesc, 1u);
+              tc_mma(dcorr, a_hi + (4096 >> 4), b_hi, idesc, (sg | g) ? 1u : 0u);
+              tc_mma(dcorr, a_hi, b_hi + (256 >> 4), idesc, 1u);
             }
           }
           tc_commit(&empty[st]);
         }
         __syncwarp();
+        if (++part == P) part = 0;
         if (++st == (uint32_t)NS) {
           st = 0;
           ph ^= 1;
@@ -334,10 +344,19 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
       const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
       tc_mbar_wait(&accf[ab], aph, 600 + (int)ab);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * 128;
+      const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * 256;
+      const int nacc = Pe + (p.npass == 3 ? 1 : 0);  // columns to add per channel: partials 0..Pe-1, then the corrections at P
       for (int c8 = 0; c8 < NT; c8 += 8) {
-        float rv[8];
+        float rv[8], t0[8], t1[8];
         tc_ld8(tb + c8, rv);
+        for (int j = 1; j < nacc; j += 2) {
+          const bool two = j + 1 < nacc;
+          tc_ld8(tb + (j < Pe ? j : P) * NT + c8, t0);
+          if (two) tc_ld8(tb + (j + 1 < Pe ? j + 1 : P) * NT + c8, t1);
+          tc_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rv[i] += two ? t0[i] + t1[i] : t0[i];
+        }
         tc_ld_wait();
         if (c8 + 8 >= NT) {  // last TMEM read of this item: hand the accumulator buffer back
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -394,7 +413,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
 #endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
 static long long tcg_launches = 0;

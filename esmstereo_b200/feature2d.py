@@ -26,8 +26,8 @@ _TORCH_ACT = {"gelu": F.gelu, "relu": F.relu, "relu6": F.relu6, None: lambda x: 
 
 def fused(cache: _Packed, conv: nn.Module, bn: Optional[nn.Module], x, act: Optional[str], engine: str, **kw):
     """conv (+BN) (+act) on `x` (tensor or list of channel-concatenated tensors)."""
-    if engine == "esm":
-        return ops.conv(x, packed_conv(cache, conv, bn), act, **kw)
+    if engine in ("esm", "esm_fp32"):  # "esm_fp32": same kernels, tensor-core engines off (see esm_conv_t.engine)
+        return ops.conv(x, packed_conv(cache, conv, bn), act, fp32_only=engine == "esm_fp32", **kw)
     if isinstance(x, (list, tuple)):
         x = torch.cat(list(x), 1)
     y = conv(x)
@@ -81,12 +81,12 @@ class Feature(nn.Module):
         self._caches = {}
 
     def forward(self, x: torch.Tensor, engine: str = "torch") -> List[torch.Tensor]:
-        if engine == "esm" and self.stand_in:
-            x = fused(self._caches.setdefault("stem", _Packed()), self.conv_stem, self.bn1, x, "relu6", "esm")
+        if engine in ("esm", "esm_fp32") and self.stand_in:
+            x = fused(self._caches.setdefault("stem", _Packed()), self.conv_stem, self.bn1, x, "relu6", engine)
             outs = []
             for i in range(5):
                 for j, stage in enumerate(getattr(self, "block%d" % i)):  # stage = Sequential(conv, bn, ReLU6)
-                    x = fused(self._caches.setdefault((i, j), _Packed()), stage[0], stage[1], x, "relu6", "esm")
+                    x = fused(self._caches.setdefault((i, j), _Packed()), stage[0], stage[1], x, "relu6", engine)
                 outs.append(x)
             return outs
         x = self.act1(self.bn1(self.conv_stem(x)))

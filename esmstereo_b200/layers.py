@@ -66,13 +66,14 @@ class BasicConv(nn.Module):
             self.conv = cls(in_channels, out_channels, bias=False, **kwargs)
             self.bn = nn.BatchNorm2d(out_channels)
         self._pc = _Packed()
+        self.fp32_only = False  # True: keep this layer off the tensor-core engines (see esm_conv_t.engine)
 
     def packed(self) -> ops.PackedConv:
         return packed_conv(self._pc, self.conv, self.bn if self.use_bn else None)
 
     def forward(self, x, **fused) -> torch.Tensor:
         _inference_only(self)
-        return ops.conv(x, self.packed(), "gelu" if self.gelu else None, **fused)
+        return ops.conv(x, self.packed(), "gelu" if self.gelu else None, fp32_only=self.fp32_only, **fused)
 
 
 class ConvBNAct(nn.Sequential):

@@ -60,6 +60,8 @@ class _ESMStereoBase(nn.Module):
         self.feature = Feature(backbone)
         # 2D feature side: "esm" = the fused direct-conv kernels (stand-in backbone), "torch" = cuDNN modules
         self.feature_engine = "esm" if self.feature.stand_in else "torch"
+        if confidence and self.feature_engine == "esm":
+            self.feature_engine = "esm_fp32"  # everything upstream of the confidence head's cost tower stays on the FP32 pipe (below)
         if cv_scale in (4, 8):
             self.feature_up = FeatUp(self.feature.chans, cv_scale)
         for (cin, cout), n in zip(_STEM_CH[cv_scale], (2, 4, 8, 16)):
@@ -87,6 +89,15 @@ class _ESMStereoBase(nn.Module):
         if confidence and cv_scale == 16:
             self.confidence_net = L.LAFNet_ESM(16)
         self.aggregation_out = L.aggregation(8, _ADD_CH[cv_scale])
+        if confidence:
+            # LAFNet's cost tower is softmax(-100 * cost / |cost|) (ESMStereo_confidence.py:575): it amplifies the cost
+            # volume's rounding error a hundredfold.  The split-TF32 tensor-core engines are ~3x less accurate than the
+            # FP32 pipe (the tensor core truncates its fp32 accumulator), so this model keeps the 3D path on the FP32
+            # pipe; at cv_scale 16 that path is 1.5 GFLOP, so nothing is lost.
+            for mod in [self.agg, self.aggregation_out] + [getattr(self, n) for n in ("corr_stem", "group_stem") if hasattr(self, n)]:
+                for sub in mod.modules():
+                    if isinstance(sub, L.BasicConv):
+                        sub.fp32_only = True
 
     # ------------------------------------------------------------------ 2D side (PyTorch)
     def _features_2d(self, left: torch.Tensor, right: torch.Tensor):

@@ -212,7 +212,7 @@ def _alloc_rows(device, lead, width: int) -> torch.Tensor:
 def conv(srcs: Sequence[torch.Tensor], pc: PackedConv, act: Optional[str] = None, *, out_size: Optional[Sequence[int]] = None,
          in_mul: Optional[torch.Tensor] = None, out_mul: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, act2: Optional[str] = None, out_scale: float = 1.0,
-         pixel_shuffle: int = 0, gwc_disp: Optional[int] = None, affine: bool = True) -> torch.Tensor:
+         pixel_shuffle: int = 0, gwc_disp: Optional[int] = None, affine: bool = True, fp32_only: bool = False) -> torch.Tensor:
     """Fused conv over channel-concatenated `srcs` (views with unit W stride are used in place).
 
     gwc_disp: if given, `srcs` = (left, right) feature maps [B,C,H,W] and the conv input is their
@@ -298,6 +298,7 @@ def conv(srcs: Sequence[torch.Tensor], pc: PackedConv, act: Optional[str] = None
     d.out_mul, d.residual, d.act2 = _ptr(out_mul), _ptr(residual), ACT[act2]
     d.out_scale, d.pixel_shuffle = float(out_scale), r
     d.out, d.oB, d.oC, d.oD, d.oH = out.data_ptr(), oB, oC, oD, oH
+    d.engine = 1 if fp32_only else 0
     label = "%s%dd %d->%d k%d%s s%d in %s%s" % ("deconv" if pc.transposed else "conv", nd, pc.Cin, pc.Cout, kw,
                                                   "+gwc" if gwc_disp is not None else "", S,
                                                   "x".join(str(v) for v in (Din, Hin, Win)), " ps%d" % r if r else "")

@@ -83,6 +83,9 @@ typedef struct {
   int pixel_shuffle;         /* 0, or r: out[b, co/(r*r), h*r+(co/r)%r, w*r+co%r] (2D only) */
   float* out;
   long long oB, oC, oD, oH;  /* output strides in elements (W stride 1) */
+  int engine;                /* 0: whichever engine wins the on-device timing (FP32 pipe or tcgen05 split-TF32);
+                                1: FP32 pipe only -- for layers whose consumer amplifies rounding error (the cost
+                                path of the confidence head: softmax(-100 * cost / |cost|), ESMStereo_confidence.py:575) */
 } esm_conv_t;
 
 /* Elements needed for the packed form of a conv weight (fp32 count). */
