@@ -653,6 +653,7 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
             }
           }
         } else {
+        float4 ps_hold = make_float4(0.f, 0.f, 0.f, 0.f);  // PixelShuffle(2): the even channel of a pair waits for the odd one
 #pragma unroll
         for (int j = 0; j < COG; ++j) {
           const int co = t.co_base + cog * COG + j;
@@ -706,10 +707,23 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
               float* o = p.out + (long long)b * p.oB + (long long)c * p.oC + (long long)(oh * rr + a) * p.oH;
               if (act2 != ESM_ACT_NONE) r = apply_act4(r, act2);
               const float* rv = &r.x;
+              // r == 2: channels co (even) and co + 1 are horizontally adjacent output pixels, so the 4 voxels x 2
+              // channels of a thread are 8 consecutive floats of one output row: two 16-byte stores instead of eight
+              // 4-byte stores 8 bytes apart (the scattered form made the 16->64 layer store-bound: 66 us for 38 MB)
+              const bool pair = rr == 2 && NV == 4 && jw0 + NV <= p.OW && ((reinterpret_cast<uintptr_t>(o + jw0 * 2) & 15) == 0);
+              if (pair && (j & 1) == 0) {
+                ps_hold = r;
+              } else if (pair) {
+                const float s = p.out_scale;
+                float4* o4 = reinterpret_cast<float4*>(o + jw0 * 2);
+                o4[0] = make_float4(ps_hold.x * s, r.x * s, ps_hold.y * s, r.y * s);
+                o4[1] = make_float4(ps_hold.z * s, r.z * s, ps_hold.w * s, r.w * s);
+              } else {
 #pragma unroll
-              for (int v = 0; v < NV; ++v) {
-                const int ow = jw0 + v;
-                if (ow < p.OW) o[ow * rr + bb] = rv[v] * p.out_scale;
+                for (int v = 0; v < NV; ++v) {
+                  const int ow = jw0 + v;
+                  if (ow < p.OW) o[ow * rr + bb] = rv[v] * p.out_scale;
+                }
               }
             }
           }

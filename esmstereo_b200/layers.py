@@ -43,6 +43,18 @@ def packed_conv(cache: _Packed, conv: nn.Module, bn: Optional[nn.Module]) -> ops
                                                     _bn_tuple(bn)))
 
 
+def _all_eq(v, want: int) -> bool:
+    return all(a == want for a in v) if isinstance(v, (tuple, list)) else v == want
+
+
+def _only_full_out_size(fused: dict, x: torch.Tensor) -> bool:
+    """True when the only fused argument is an out_size equal to the full 2x output (no crop)."""
+    if set(fused) != {"out_size"}:
+        return False
+    o = fused["out_size"]
+    return o is None or tuple(int(v) for v in o) == tuple(2 * int(v) for v in x.shape[2:])
+
+
 def _inference_only(m: nn.Module) -> None:
     if m.training:
         raise RuntimeError("esmstereo_b200 implements the inference path only (BatchNorm folded from running "
@@ -66,14 +78,55 @@ class BasicConv(nn.Module):
             self.conv = cls(in_channels, out_channels, bias=False, **kwargs)
             self.bn = nn.BatchNorm2d(out_channels)
         self._pc = _Packed()
+        self._pc_sub = _Packed()
         self.fp32_only = False  # True: keep this layer off the tensor-core engines (see esm_conv_t.engine)
+        # ConvTranspose k4 s2 p1 to ONE channel (conv1_up of `aggregation` and `up_refinement`, ESMStereo.py:150,209):
+        # run as its sub-pixel form, a k3 s1 p1 convolution to 2^nd channels (one per output phase) + PixelShuffle.
+        # The generic transposed path pads Cout 1 -> 4 and spends 3/4 of its FMAs on zeros (85 us for the cost volume
+        # at KITTI shape); the k3 form has no padding waste and is eligible for the tensor-core engine.
+        ks = kwargs.get("kernel_size")
+        ks = tuple(ks) if isinstance(ks, (tuple, list)) else (ks,) * (3 if is_3d else 2)
+        self._subpixel = bool(deconv and out_channels == 1 and all(k == 4 for k in ks) and _all_eq(kwargs.get("stride"), 2)
+                              and _all_eq(kwargs.get("padding"), 1))
 
     def packed(self) -> ops.PackedConv:
         return packed_conv(self._pc, self.conv, self.bn if self.use_bn else None)
 
+    def packed_subpixel(self) -> ops.PackedConv:
+        """Phase p = (pd, ph, pw) of the transposed conv reads input offsets p - 1 + t, t in {0, 1}, with kernel taps
+        3 - p - 2t: as a k3 p1 conv, tap index p + t of output channel p (channel order = PixelShuffle's)."""
+        conv, bn = self.conv, (self.bn if self.use_bn else None)
+        tensors = [conv.weight, conv.bias] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [])
+
+        def build():
+            w = conv.weight.detach()  # [Cin, 1, 4, 4(, 4)]
+            nd = w.dim() - 2
+            P = 2 ** nd
+            weq = torch.zeros((P, w.shape[0]) + (3,) * nd, device=w.device, dtype=w.dtype)
+            for p in range(P):
+                ph = [(p >> (nd - 1 - i)) & 1 for i in range(nd)]  # most significant bit = outermost dim
+                for t in range(P):
+                    tt = [(t >> (nd - 1 - i)) & 1 for i in range(nd)]
+                    dst = tuple(ph[i] + tt[i] for i in range(nd))
+                    src = tuple(3 - ph[i] - 2 * tt[i] for i in range(nd))
+                    weq[(p, slice(None)) + dst] = w[(slice(None), 0) + src]
+            rep = lambda t: None if t is None else t.detach().expand(P).contiguous()
+            bnt = None if bn is None else (rep(bn.weight), rep(bn.bias), rep(bn.running_mean), rep(bn.running_var), bn.eps)
+            return ops.pack_conv(weq, 1, 1, False, rep(conv.bias), bnt)
+
+        return self._pc_sub.get(tensors, build)
+
     def forward(self, x, **fused) -> torch.Tensor:
         _inference_only(self)
-        return ops.conv(x, self.packed(), "gelu" if self.gelu else None, fp32_only=self.fp32_only, **fused)
+        act = "gelu" if self.gelu else None
+        if self._subpixel and isinstance(x, torch.Tensor) and (not fused or _only_full_out_size(fused, x)):
+            pc = self.packed_subpixel()
+            if x.dim() == 4:
+                return ops.conv(x, pc, act, pixel_shuffle=2, fp32_only=self.fp32_only)
+            y = ops.conv(x, pc, act, fp32_only=self.fp32_only)  # [B, 8, D, H, W], channel = pd*4 + ph*2 + pw
+            B, _, D, H, W = y.shape
+            return y.view(B, 2, 2, 2, D, H, W).permute(0, 4, 1, 5, 2, 6, 3).reshape(B, 1, 2 * D, 2 * H, 2 * W)
+        return ops.conv(x, self.packed(), act, fp32_only=self.fp32_only, **fused)
 
 
 class ConvBNAct(nn.Sequential):

@@ -480,3 +480,30 @@ def test_conv_streamed_tensor_core_fusions(tcg_forced):
     got = ops.conv(x.cuda(), gpu_pack(p, 2, 1, True), "gelu", out_size=(5, 11, 39), out_mul=att.cuda())
     assert tcg_forced() == n0 + 3
     assert rel(got, want) < 2e-5
+
+
+@pytest.mark.parametrize("nd,shape,bn", [(2, (1, 32, 13, 21), False), (3, (2, 24, 4, 6, 13), False), (2, (2, 16, 7, 9), True)])
+def test_single_channel_deconv_subpixel_form(nd, shape, bn):
+    """conv1_up (ConvTranspose k4 s2 p1 -> 1 channel) runs as a k3 conv to 2^nd phase channels + PixelShuffle."""
+    from esmstereo_b200 import layers as L
+    torch.manual_seed(5)
+    m = L.BasicConv(shape[1], 1, deconv=True, is_3d=nd == 3, bn=bn, gelu=bn, kernel_size=(4,) * nd, padding=(1,) * nd, stride=(2,) * nd)
+    with torch.no_grad():
+        m.bn.running_mean.normal_(0, 0.1)
+        m.bn.running_var.uniform_(0.5, 1.5)
+        m.bn.weight.uniform_(0.5, 1.5)
+        m.bn.bias.normal_(0, 0.1)
+    m.eval()
+    assert m._subpixel
+    x = rnd(*shape, seed=2)
+    with torch.no_grad():
+        want = m.conv(x)
+        if bn:
+            want = F.gelu(m.bn(want))
+        got = m.cuda()(x.cuda())
+        assert got.shape == want.shape
+        assert rel(got, want) < 2e-5
+        # a fused argument other than a full-size out_size takes the generic transposed path; same answer
+        crop = tuple(2 * s - 1 for s in shape[2:])
+        got2 = m(x.cuda(), out_size=crop)
+        assert rel(got2, want[(slice(None), slice(None)) + tuple(slice(0, c) for c in crop)]) < 2e-5
