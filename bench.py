@@ -198,16 +198,18 @@ def kernel_rooflines(model, peaks):
     # has no separate TF32 figure), "fp32" = the FFMA rate measured on this pool.  `achieved` counts the
     # ALGORITHMIC FLOPs (2*Cout*Cin*taps*voxels); the split executes 3 MMAs per product, reported separately.
     from esmstereo_b200 import _lib
-    tc_count = _lib.lib().esm_tc_conv_launches
+    tc_count, tcg_count = _lib.lib().esm_tc_conv_launches, _lib.lib().esm_tcg_conv_launches
     tf32_peak = peaks["bf16_tflops"] / 2.0
 
     def conv_entry(fn, fl, by):
-        n0 = tc_count()
+        n0, g0 = tc_count(), tcg_count()
         fn()
-        on_tc = tc_count() > n0
+        on_tcg = tcg_count() > g0
+        on_tc = on_tcg or tc_count() > n0
         t = time_kernel(fn, flush)
         peak = tf32_peak if on_tc else fp32_peak
-        e = {"bound": "tensor" if on_tc else "fp32", "path": "tcgen05 split-TF32" if on_tc else "fp32 pipe",
+        path = "tcgen05 split-TF32, streamed weights (conv_tcg.cu)" if on_tcg else "tcgen05 split-TF32, resident weights (conv_tc.cu)"
+        e = {"bound": "tensor" if on_tc else "fp32", "path": path if on_tc else "fp32 pipe",
              "achieved": fl / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / peak, "traffic": None,
              "us": t * 1e6, "algorithmic_flops": fl, "algorithmic_bytes": by}
         if on_tc:
@@ -226,6 +228,13 @@ def kernel_rooflines(model, peaks):
     p24 = model.aggregation_out.conv1[1].packed()
     out["hourglass_conv3d_24_24"] = conv_entry(lambda: ops.conv(x24, p24, "gelu"), 2.0 * 24 * 24 * 27 * (D // 2) * (h // 2) * (w // 2),
                                                4.0 * 48 * (D // 2) * (h // 2) * (w // 2))
+    # the wide hourglass level (a5): 40 -> 40 k3 at quarter resolution, and its ConvTranspose3d k4 s2 40 -> 24
+    x40 = torch.randn(1, 40, D // 4, h // 4, w // 4, generator=g).to(dev)
+    p40 = model.aggregation_out.conv2[1].packed()
+    v40 = (D // 4) * (h // 4) * (w // 4)
+    out["hourglass_conv3d_40_40"] = conv_entry(lambda: ops.conv(x40, p40, "gelu"), 2.0 * 40 * 40 * 27 * v40, 4.0 * 80 * v40)
+    pup = model.aggregation_out.conv2_up.packed()
+    out["hourglass_deconv3d_40_24"] = conv_entry(lambda: ops.conv(x40, pup, "gelu"), 2.0 * 40 * 24 * 64 * v40, 4.0 * (40 + 8 * 24) * v40)
     # regression (K4): 4*(D+1)*h*w bytes
     cost = torch.randn(1, D, h, w, generator=g).to(dev)
     t = time_kernel(lambda: ops.regression_top2(cost), flush)

@@ -22,11 +22,13 @@ def layer(cin, cout, k, nd, stride=1, pad=1, transposed=False):
 
 
 def main():
-    which = sys.argv[1:] or ["vol", "stem", "agg", "c24", "c2d", "reg", "bil"]
+    which = sys.argv[1:] or ["vol", "stem", "agg", "c24", "c40", "d40", "c2d", "reg", "bil"]
     h, w, D, H, W = 96, 312, 48, 384, 1248
     L, R = torch.randn(1, 64, h, w, device="cuda"), torch.randn(1, 64, h, w, device="cuda")
     ls = {"stem": layer(32, 8, 3, 3), "agg": layer(8, 8, 3, 3), "c24": layer(24, 24, 3, 3), "c2d": layer(32, 32, 3, 2),
-          "s2": layer(8, 24, 3, 3, stride=2), "dec1": layer(24, 1, 4, 3, stride=2, transposed=True)}
+          "s2": layer(8, 24, 3, 3, stride=2), "dec1": layer(24, 1, 4, 3, stride=2, transposed=True),
+          "c40": layer(40, 40, 3, 3), "d40": layer(40, 24, 4, 3, stride=2, transposed=True)}
+    x40 = torch.randn(1, 40, 12, 24, 78, device="cuda")
     x8 = torch.randn(1, 8, D, h, w, device="cuda")
     x24 = torch.randn(1, 24, 24, 48, 156, device="cuda")
     x2d = torch.randn(1, 32, 192, 624, device="cuda")
@@ -44,6 +46,10 @@ def main():
             ops.conv(x8, ls["s2"], "gelu")
         if "c24" in which:
             ops.conv(x24, ls["c24"], "gelu")
+        if "c40" in which:
+            ops.conv(x40, ls["c40"], "gelu")
+        if "d40" in which:
+            ops.conv(x40, ls["d40"], "gelu")
         if "c2d" in which:
             ops.conv(x2d, ls["c2d"], "gelu")
         if "dec1" in which:

@@ -92,6 +92,10 @@ def full():
                 key = "agg_conv3d_8_8"
             if "tc_conv_kernel<24, 1, 3, 0" in name:
                 key = "hourglass_conv3d_24_24"
+            if "tcg_conv_kernel<3, 1, 1>" in name:
+                key = "hourglass_conv3d_40_40"
+            if "tcg_conv_kernel<2, 2, 1>" in name:
+                key = "hourglass_deconv3d_40_24"
             if key:
                 traffic[key] = byts
     with open(os.path.join(OUT, "traffic.json"), "w") as f:
