@@ -1,6 +1,9 @@
 // Cost-volume builders (HBM-write-bound streaming kernels).
 //   esm_gwc_volume_f32        <- build_gwc_volume + groupwise_correlation (submodule.py:143-161)
 //   esm_norm_corr_volume_f32  <- build_norm_correlation_volume + norm_correlation (submodule.py:187-200)
+//   esm_concat_volume_f32     <- build_concat_volume (submodule.py:129-140)
+//   esm_substract_volume_f32  <- build_substract_volume + groupwise_difference (submodule.py:104-126)
+//   (the last two are not used by any model configuration)
 // The reference builds the volume with a Python loop over disparities (memset + D x {mul, mean,
 // strided copy}); here one launch writes every output element exactly once, zeros included.
 //
@@ -195,4 +198,79 @@ extern "C" int esm_norm_corr_volume_f32(const float* L, const float* R, float* V
   dim3 grid((unsigned)ceil_div(W, 128), (unsigned)H, (unsigned)(B * ceil_div(D, DT)));
   norm_corr_kernel<DT><<<grid, 128, 0, st>>>(Ln, Rn, V, C, H, W, D);
   return check_launch("norm_corr_volume");
+}
+
+namespace esm {
+
+// V[b, c, d, y, x] = L[b, c, y, x] (c < C, whole row -- the reference does not mask the left half, submodule.py:134)
+//                  = R[b, c - C, y, x - d] for x >= d, else 0 (c >= C).  One thread per 4 consecutive x of one (c, d, y) row.
+__global__ void __launch_bounds__(256) concat_volume_kernel(const float* __restrict__ L, const float* __restrict__ R, float* __restrict__ V,
+                                                            int C, int H, int W, int D, int xg, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x0 = (int)(i % xg) * 4;
+  long long t = i / xg;
+  const int y = (int)(t % H);
+  t /= H;
+  const int d = (int)(t % D);
+  t /= D;
+  const int c = (int)(t % (2 * C));
+  const long long b = t / (2 * C);
+  const bool left = c < C;
+  const float* src = (left ? L : R) + ((b * C + (left ? c : c - C)) * H + y) * (long long)W;
+  float* dst = V + (((b * 2 * C + c) * D + d) * H + y) * (long long)W;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = x0 + k;
+    if (x < W) dst[x] = left ? __ldg(src + x) : (x >= d ? __ldg(src + x - d) : 0.f);
+  }
+}
+
+// V[b, g, d, y, x] = sum_{c in group g} (L[c, y, x] - R[c, y, x - d])^2 for x >= d, else 0
+__global__ void __launch_bounds__(256) substract_volume_kernel(const float* __restrict__ L, const float* __restrict__ R, float* __restrict__ V,
+                                                               int C, int H, int W, int D, int G, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % W);
+  long long t = i / W;
+  const int y = (int)(t % H);
+  t /= H;
+  const int d = (int)(t % D);
+  t /= D;
+  const int g = (int)(t % G);
+  const long long b = t / G;
+  const int cpg = C / G;
+  float s = 0.f;
+  if (x >= d) {
+    const long long plane = (long long)H * W;
+    const float* l = L + (b * C + (long long)g * cpg) * plane + (long long)y * W + x;
+    const float* r = R + (b * C + (long long)g * cpg) * plane + (long long)y * W + x - d;
+    for (int c = 0; c < cpg; ++c) {
+      const float df = __fsub_rn(__ldg(l + c * plane), __ldg(r + c * plane));
+      s = __fadd_rn(s, __fmul_rn(df, df));
+    }
+  }
+  V[i] = s;
+}
+
+}  // namespace esm
+
+extern "C" int esm_concat_volume_f32(const float* L, const float* R, float* V, int B, int C, int H, int W, int D, void* stream) {
+  ESM_REQUIRE(L && R && V, "concat_volume: null pointer");
+  ESM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "concat_volume: empty shape");
+  const int xg = esm::ceil_div(W, 4);
+  const long long total = (long long)B * 2 * C * D * H * xg;
+  ESM_REQUIRE(esm::ceil_div_ll(total, 256) < (1ll << 31), "concat_volume: grid too large");
+  esm::concat_volume_kernel<<<(unsigned)esm::ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(L, R, V, C, H, W, D, xg, total);
+  return esm::check_launch("concat_volume");
+}
+
+extern "C" int esm_substract_volume_f32(const float* L, const float* R, float* V, int B, int C, int H, int W, int D, int G, void* stream) {
+  ESM_REQUIRE(L && R && V, "substract_volume: null pointer");
+  ESM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0 && G > 0, "substract_volume: empty shape");
+  ESM_REQUIRE(C % G == 0, "substract_volume: C (%d) not divisible by groups (%d)", C, G);  // submodule.py:107
+  const long long total = (long long)B * G * D * H * W;
+  ESM_REQUIRE(esm::ceil_div_ll(total, 256) < (1ll << 31), "substract_volume: grid too large");
+  esm::substract_volume_kernel<<<(unsigned)esm::ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(L, R, V, C, H, W, D, G, total);
+  return esm::check_launch("substract_volume");
 }

@@ -48,9 +48,9 @@ class _Prof:
         return False
 
 
-def _dev(t: torch.Tensor, name: str) -> torch.Tensor:
-    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32):
-        raise TypeError("esmstereo_b200: %s must be a CUDA float32 tensor (no CPU fallback exists)" % name)
+def _dev(t: torch.Tensor, name: str, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype):
+        raise TypeError("esmstereo_b200: %s must be a CUDA %s tensor (no CPU fallback exists)" % (name, str(dtype).replace("torch.", "")))
     return t
 
 
@@ -88,6 +88,67 @@ def build_norm_correlation_volume(refimg_fea: torch.Tensor, targetimg_fea: torch
 # ---------------------------------------------------------------------------------------------
 # regression  (submodule.py:211-225)
 # ---------------------------------------------------------------------------------------------
+def build_concat_volume(refimg_fea: torch.Tensor, targetimg_fea: torch.Tensor, maxdisp: int) -> torch.Tensor:
+    """`build_concat_volume` (submodule.py:129-140): [B,C,H,W] x2 -> [B,2C,D,H,W]."""
+    L_, R_ = _dev(refimg_fea, "refimg_fea").contiguous(), _dev(targetimg_fea, "targetimg_fea").contiguous()
+    B, Cc, H, W = L_.shape
+    assert R_.shape == L_.shape
+    V = torch.empty(B, 2 * Cc, int(maxdisp), H, W, device=L_.device, dtype=torch.float32)
+    with _Prof("concat_volume C%d D%d %dx%d" % (Cc, maxdisp, H, W)):
+        check(lib().esm_concat_volume_f32(L_.data_ptr(), R_.data_ptr(), V.data_ptr(), B, Cc, H, W, int(maxdisp), _stream()), "concat_volume")
+    return V
+
+
+def build_substract_volume(refimg_fea: torch.Tensor, targetimg_fea: torch.Tensor, maxdisp: int, num_groups: int) -> torch.Tensor:
+    """`build_substract_volume` (submodule.py:116-126): squared group-wise differences, [B,G,D,H,W]."""
+    L_, R_ = _dev(refimg_fea, "refimg_fea").contiguous(), _dev(targetimg_fea, "targetimg_fea").contiguous()
+    B, Cc, H, W = L_.shape
+    assert R_.shape == L_.shape
+    assert Cc % num_groups == 0  # submodule.py:107
+    V = torch.empty(B, int(num_groups), int(maxdisp), H, W, device=L_.device, dtype=torch.float32)
+    with _Prof("substract_volume C%d G%d D%d %dx%d" % (Cc, num_groups, maxdisp, H, W)):
+        check(lib().esm_substract_volume_f32(L_.data_ptr(), R_.data_ptr(), V.data_ptr(), B, Cc, H, W, int(maxdisp), int(num_groups),
+                                             _stream()), "substract_volume")
+    return V
+
+
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def preprocess_images(rgb_u8: torch.Tensor, size: Tuple[int, int], mode: str = "test_kitti", mean=IMAGENET_MEAN, std=IMAGENET_STD) -> torch.Tensor:
+    """uint8 RGB [B,h,w,3] (device) -> normalised float32 [B,3,Hp,Wp], padded as the reference's scripts pad:
+    mode "test_kitti" = black pixels on the top / left, normalised (test_kitti.py:93-106); "kitti_dataset" = zeros on
+    the top / right after normalisation (datasets/kitti_dataset.py:145-160)."""
+    x = _dev(rgb_u8, "rgb_u8", torch.uint8).contiguous()
+    assert x.dim() == 4 and x.shape[3] == 3
+    B, h, w, _ = x.shape
+    Hp, Wp = int(size[0]), int(size[1])
+    assert Hp >= h and Wp >= w
+    assert mode in ("test_kitti", "kitti_dataset")
+    left = Wp - w if mode == "test_kitti" else 0
+    out = torch.empty(B, 3, Hp, Wp, device=x.device, dtype=torch.float32)
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    with _Prof("preprocess %dx%d" % (Hp, Wp)):
+        check(lib().esm_preprocess_u8_f32(x.data_ptr(), out.data_ptr(), B, h, w, Hp, Wp, Hp - h, left, int(mode == "test_kitti"), m3, s3,
+                                          _stream()), "preprocess")
+    return out
+
+
+def disparity_to_uint16(disp: torch.Tensor, size: Tuple[int, int], mode: str = "test_kitti", scale: float = 256.0) -> torch.Tensor:
+    """Padded disparity [B,Hp,Wp] -> uint16 [B,h,w] = round(d * 256) of the un-padded region (test_kitti.py:114,127;
+    save_disp.py:83-88)."""
+    d = _dev(disp, "disp").contiguous()
+    assert d.dim() == 3
+    B, Hp, Wp = d.shape
+    h, w = int(size[0]), int(size[1])
+    left = Wp - w if mode == "test_kitti" else 0
+    out = torch.empty(B, h, w, device=d.device, dtype=torch.uint16)
+    with _Prof("postprocess %dx%d" % (h, w)):
+        check(lib().esm_postprocess_disp_u16(d.data_ptr(), out.data_ptr(), B, Hp, Wp, Hp - h, left, h, w, float(scale), _stream()),
+              "postprocess")
+    return out
+
+
 def regression_top2(cost: torch.Tensor, return_indices: bool = False):
     """`regression_topk(cost, arange(D), 2)`: cost [B,D,H,W] -> pred [B,1,H,W] (+ int32 idx [B,2,H,W])."""
     cost = _dev(cost, "cost").contiguous()

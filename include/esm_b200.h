@@ -121,6 +121,13 @@ int esm_gwc_volume_f32(const float* L, const float* R, float* V, int B, int C, i
 int esm_norm_corr_volume_f32(const float* L, const float* R, float* V, float* ws, int B, int C, int H, int W,
                              int D, void* stream);
 
+/* build_concat_volume (submodule.py:129-140): -> V [B,2C,D,H,W]; V[:, :C, d] = L (whole row), V[:, C:, d, :, x] =
+ * R[.., x-d] for x >= d else 0.  Not used by any model configuration (kept for the reference's operator seam). */
+int esm_concat_volume_f32(const float* L, const float* R, float* V, int B, int C, int H, int W, int D, void* stream);
+/* build_substract_volume (submodule.py:104-126): V[b,g,d,y,x] = sum_{c in g} (L - R(x-d))^2 for x >= d else 0. */
+int esm_substract_volume_f32(const float* L, const float* R, float* V, int B, int C, int H, int W, int D, int G,
+                             void* stream);
+
 /* regression_topk(cost, arange(D), k=2) (submodule.py:218-225, ESMStereo.py:719-721):
  * cost [B,D,H,W] -> pred [B,1,H,W]; idx (optional, int32 [B,2,H,W]) receives the top-2 indices
  * (ties: lower index first). */
@@ -132,6 +139,19 @@ int esm_disparity_regression_f32(const float* cost, float* pred, int B, int D, i
  * (ESMStereo.py:307,316,745).  prev [B,1,h,w], residual/out [B,1,h*f,w*f]. */
 int esm_bilinear_add_f32(const float* prev, const float* residual, float* out, int B, int h, int w, int factor,
                          float out_scale, void* stream);
+
+/* Image pre-processing (test_kitti.py:93-106, datasets/kitti_dataset.py:145-160): uint8 RGB [B,h,w,3] ->
+ * float32 [B,3,Hp,Wp]: ToTensor (/255) + Normalize((x - mean) / std, true divisions) placed at (pad_top, pad_left);
+ * the padding is black pixels normalised like any other (fill_normalised = 1: test_kitti.py's PIL crop with a
+ * negative origin, pad_top = Hp - h, pad_left = Wp - w) or zeros after normalisation (fill_normalised = 0:
+ * kitti_dataset.py's np.pad on the top / right, pad_left = 0).  mean3 / std3 are HOST pointers to 3 floats. */
+int esm_preprocess_u8_f32(const unsigned char* rgb_hwc, float* out_chw, int B, int h, int w, int Hp, int Wp,
+                          int pad_top, int pad_left, int fill_normalised, const float* mean3, const float* std3,
+                          void* stream);
+/* Disparity post-processing (test_kitti.py:114,127; save_disp.py:83-88): crop [top:top+h, left:left+w] of the padded
+ * [B,Hp,Wp] disparity, round(d * scale) half-to-even -> uint16 [B,h,w] (saturating). */
+int esm_postprocess_disp_u16(const float* disp, unsigned short* out, int B, int Hp, int Wp, int top, int left,
+                             int h, int w, float scale, void* stream);
 
 /*
  * ShuffleMixer SMLayer halves (shufflemixer.py:97-112), C in {8,16}:

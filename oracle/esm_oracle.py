@@ -174,6 +174,25 @@ class EsmOracle:
             V[:, :, d, :, d:] = (Ln[:, :, :, d:] * Rn[:, :, :, : W - d]).mean(1, keepdim=True)
         return V
 
+    def concat_volume(self, L: torch.Tensor, R: torch.Tensor, D: int) -> torch.Tensor:
+        """`build_concat_volume` (`submodule.py:129-140`): the left half is the unmasked left feature at every d."""
+        B, C, H, W = L.shape
+        V = L.new_zeros(B, 2 * C, D, H, W)
+        for d in range(D):
+            V[:, :C, d] = L
+            if d < W:
+                V[:, C:, d, :, d:] = R[:, :, :, : W - d]
+        return V
+
+    def substract_volume(self, L: torch.Tensor, R: torch.Tensor, D: int, G: int) -> torch.Tensor:
+        """`build_substract_volume` + `groupwise_difference` (`submodule.py:104-126`)."""
+        B, C, H, W = L.shape
+        V = L.new_zeros(B, G, D, H, W)
+        for d in range(min(D, W)):
+            diff = (L[:, :, :, d:] - R[:, :, :, : W - d]).view(B, G, C // G, H, W - d)
+            V[:, :, d, :, d:] = torch.pow(diff, 2).sum(2)
+        return V
+
     # ------------------------------------------------------------------ hot path: 3D hourglass
     def hourglass(self, x: torch.Tensor, p: str = "aggregation_out") -> torch.Tensor:
         """`aggregation.forward` (`ESMStereo.py:165-182`)."""
@@ -430,3 +449,39 @@ class EsmOracle:
         finally:
             self.calibrating = False
         return self.sd
+
+
+# ----------------------------------------------------------------------------------------------------
+# pre / post-processing of the reference's scripts, restated on torch-CPU tensors
+# ----------------------------------------------------------------------------------------------------
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def preprocess_images(rgb_u8: torch.Tensor, size, mode: str = "test_kitti") -> torch.Tensor:
+    """uint8 [B,h,w,3] -> float32 [B,3,Hp,Wp].  "test_kitti": `limg.crop((w - wi, h - hi, w, h))` then ToTensor +
+    Normalize (`test_kitti.py:93-106`; PIL fills the area outside the image with black, which is then normalised).
+    "kitti_dataset": ToTensor + Normalize, then `np.lib.pad(((0,0),(top_pad,0),(0,right_pad)), constant 0)`
+    (`datasets/kitti_dataset.py:145-160`)."""
+    B, h, w, _ = rgb_u8.shape
+    Hp, Wp = size
+    mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, dtype=torch.float32).view(1, 3, 1, 1)
+    if mode == "test_kitti":
+        canvas = torch.zeros(B, Hp, Wp, 3, dtype=torch.uint8)
+        canvas[:, Hp - h:, Wp - w:] = rgb_u8
+        t = canvas.permute(0, 3, 1, 2).to(torch.float32).div(255)  # ToTensor
+        return t.sub(mean).div(std)                                # Normalize
+    t = rgb_u8.permute(0, 3, 1, 2).to(torch.float32).div(255).sub(mean).div(std)
+    out = torch.zeros(B, 3, Hp, Wp, dtype=torch.float32)
+    out[:, :, Hp - h:, :w] = t
+    return out
+
+
+def disparity_to_uint16(disp: torch.Tensor, size, mode: str = "test_kitti") -> torch.Tensor:
+    """`pred_disp[:, hi - h:, wi - w:]` (`test_kitti.py:114`) or `disp_est[top_pad:, :-right_pad]` (`save_disp.py:83`),
+    then `np.round(d * 256).astype(np.uint16)` (`test_kitti.py:127`, `save_disp.py:87`)."""
+    import numpy as np
+    B, Hp, Wp = disp.shape
+    h, w = size
+    crop = disp[:, Hp - h:, Wp - w:] if mode == "test_kitti" else disp[:, Hp - h:, :w]
+    return torch.from_numpy(np.round(crop.numpy() * 256).astype(np.uint16).astype(np.int32))
