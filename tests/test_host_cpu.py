@@ -65,3 +65,32 @@ def test_constructor_contract():
     assert set(__models__) == {"ESMStereo", "ESMStereo_trt", "ESMStereo_confidence"}
     with pytest.raises(NameError):  # the reference's `pirnt` typo path, ESMStereo.py:599
         __models__["ESMStereo"](192, True, False, "efficientnet_b2", 5)
+
+
+def test_tc_gelu_polynomial():
+    """The tcgen05 epilogues evaluate GELU as x - h / h with h = 0.5 x erfc(|x|/sqrt 2), erfc(t) = 2^p(t), p a degree-8
+    fit of log2(erfcx(t)) - t^2 log2(e) on [0, 4] (csrc/tc_common.cuh: tc_gelu).  Replays the fp32 Horner evaluation
+    with the coefficients parsed from the CUDA source and bounds the error against torch's exact-erf GELU."""
+    import os
+    import re
+    import numpy as np
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "esmstereo_b200", "csrc", "tc_common.cuh")).read()
+    body = src[src.index("float tc_gelu(float x)"):]
+    body = body[:body.index("ex2.approx")]
+    coef = [np.float32(c) for c in re.findall(r"(-?\d\.\d+e[+-]\d+)f", body)]
+    assert len(coef) == 9
+    x32 = torch.linspace(-8, 8, 400001, dtype=torch.float64).to(torch.float32).numpy()
+    x = torch.from_numpy(x32.astype(np.float64))  # the same (fp32-representable) inputs for the exact reference
+    t = np.minimum(np.abs(x32) * np.float32(0.70710678118654752440), np.float32(4.0)).astype(np.float32)
+    q = np.full_like(t, coef[0])
+    for c in coef[1:]:
+        q = (q * t + c).astype(np.float32)
+    e = np.exp2(q.astype(np.float64)).astype(np.float32)
+    h = (np.float32(0.5) * x32) * e
+    got = np.where(x32 >= 0, x32 - h, h).astype(np.float64)
+    want = torch.nn.functional.gelu(x).numpy()
+    small = np.abs(x32) <= 4
+    assert np.abs(got - want)[small].max() < 1.5e-7                       # an ulp of an O(1) activation
+    assert (np.abs(got - want)[~small] / np.abs(x32[~small])).max() < 6e-8  # beyond: half an ulp of x
+    pos = x32 > 1e-3
+    assert (np.abs(got - want)[pos] / want[pos]).max() < 5e-7
