@@ -12,9 +12,9 @@
 // by the shared-memory read of A (46 clk, scratch/umma_test.cu), so the kernel wins where the FP32 pipe is starved
 // instead: few voxels, many channels.
 //
-// Warp roles (448 threads, 1 CTA/SM, persistent): warps 0-3 epilogue (one per TMEM lane quadrant: TMEM -> BN /
+// Warp roles (704 threads, 1 CTA/SM, persistent): warps 0-3 epilogue (one per TMEM lane quadrant: TMEM -> BN /
 // activation -> global), warp 4 MMA issuer (warp-uniform, one elected lane), warp 5 weight streamer (one lane: four
-// bulk copies per slab, completing on the stage's `full` barrier), warps 6-13 A-operand producers (predicated
+// bulk copies per slab, completing on the stage's `full` barrier), warps 6-21 A-operand producers in two sets that take alternate stages (predicated
 // global loads split into hi / lo and stored as K-major non-swizzled UMMA tiles).  A ring stage holds
 // G = GC x GD x KW^2 (channel group, tap) slabs -- 9 for k3, 8 for the transposed layers -- with every tap offset
 // a compile-time constant: the fence.proxy.async that publishes the producers' shared-memory stores compiles to
@@ -58,8 +58,9 @@ constexpr int TG_NEW = 4;                      // epilogue warps
 constexpr int TG_MMA_WARP = TG_NEW;            // MMA issuer
 constexpr int TG_W_WARP = TG_NEW + 1;          // weight streamer
 constexpr int TG_PROD_WARP = TG_NEW + 2;       // first A producer warp
-constexpr int TG_NTW = 8;                      // A producer warps
-constexpr int TG_THREADS = 32 * (TG_NEW + 2 + TG_NTW);
+constexpr int TG_NTW = 8;                      // A producer warps per set: (lane quadrant, K half)
+constexpr int TG_NSET = 2;                     // producer sets; set s fills the stages n with n % 2 == s
+constexpr int TG_THREADS = 32 * (TG_NEW + 2 + TG_NSET * TG_NTW);
 
 struct TgItem {
   int b, phase, mt, cot;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
-      tc_mbar_init(&full[i], TG_NTW + 1);  // 8 producer warps + the weight streamer's expect_tx arrive
+      tc_mbar_init(&full[i], TG_NTW + 1);  // the 8 producer warps of one set + the weight streamer's expect_tx arrive
       tc_mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -129,7 +130,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
 
   if (warp >= TG_PROD_WARP) {
     // ============================ A-operand producers ============================
-    const int tw = warp - TG_PROD_WARP;
+    // Two sets of 8 warps take alternate ring stages.  A stage costs its producers one exposed global-load latency
+    // (the MEMBAR inside fence.proxy.async waits for every load in flight, so a second register buffer cannot hide
+    // it: measured 2.5k clk per 9-slab stage against 1.2k clk of MMAs); with two sets, one set's latency overlaps
+    // the other set's conversion and stores.
+    const int tw = (warp - TG_PROD_WARP) & (TG_NTW - 1);
+    const int set = (warp - TG_PROD_WARP) / TG_NTW;
     const int q = (tw >> 1) & 3;   // TMEM lane quadrant = rows q*32 .. q*32+31 of the tile
     const int khalf = tw & 1;      // which 4 of the 8 channels of a group
     const int m = q * 32 + lane;   // A row
@@ -190,6 +196,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
           }
         }
       }
+      return ngc * (GD * KW * KW);
+    };
+    auto next_stage = [&]() {
+      if (item >= p.items) return;
       td0 += GD;
       if (td0 >= p.KD) {
         td0 = 0;
@@ -199,9 +209,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
           enter_item();
         }
       }
-      return ngc * (GD * KW * KW);
     };
-    uint32_t st = 0, ph = 0;
+    uint32_t st = (uint32_t)set % (uint32_t)NS, ph = (uint32_t)set / (uint32_t)NS;  // ring slot / phase of stage n = set
     auto store_stage = [&](const float (&v)[G][4], int nv) {
       tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
       uint8_t* sb = s_stage + (size_t)st * STAGE + khalf * 2048 + m * 16;
@@ -226,22 +235,21 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(&full[st]);
-      if (++st == (uint32_t)NS) {
-        st = 0;
+      st += TG_NSET;  // this set's next stage is TG_NSET further along the ring
+      while (st >= (uint32_t)NS) {
+        st -= (uint32_t)NS;
         ph ^= 1;
       }
     };
-    // two register buffers, loop unrolled by two: the loads of stage i+1 are in flight while stage i is converted
-    // and stored
-    float va[G][4], vb[G][4];
+    float v[G][4];
     enter_item();
-    int na = load_stage(va), nb = 0;
-    while (na > 0) {
-      nb = load_stage(vb);
-      store_stage(va, na);
-      if (nb == 0) break;
-      na = load_stage(va);
-      store_stage(vb, nb);
+    for (int i = 0; i < set; ++i) next_stage();
+    for (;;) {
+      const int nv = load_stage(v);
+      if (nv == 0) break;
+#pragma unroll
+      for (int i = 0; i < TG_NSET; ++i) next_stage();
+      store_stage(v, nv);
     }
   } else if (warp == TG_W_WARP) {
     // ============================ weight streamer ============================
