@@ -13,9 +13,10 @@
 // instead: few voxels, many channels.
 //
 // Warp roles (704 threads, 1 CTA/SM, persistent): warps 0-3 epilogue (one per TMEM lane quadrant: TMEM -> BN /
-// activation -> global), warp 4 MMA issuer (warp-uniform, one elected lane), warp 5 weight streamer (one lane: four
-// bulk copies per slab, completing on the stage's `full` barrier), warps 6-21 A-operand producers in two sets that take alternate stages (predicated
-// global loads split into hi / lo and stored as K-major non-swizzled UMMA tiles).  A ring stage holds
+// activation -> global), warp 4 MMA issuer (warp-uniform, one elected lane, TS form: A from tensor memory), warp 5
+// weight streamer (one lane: one bulk copy per channel group, completing on the stage's `full` barrier), warps 6-21
+// A-operand producers in two sets that take alternate stages (predicated global loads split into hi / lo and written
+// to TENSOR MEMORY with tcgen05.st: row m of the tile at TMEM lane m).  A ring stage holds
 // G = GC x GD x KW^2 (channel group, tap) slabs -- 9 for k3, 8 for the transposed layers -- with every tap offset
 // a compile-time constant: the fence.proxy.async that publishes the producers' shared-memory stores compiles to
 // MEMBAR.ALL.CTA, which also waits for the loads already in flight for the next stage, so a stage pays one global
@@ -88,8 +89,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
 #endif
   const int NT = p.NT, NS = p.nstages;
   const uint32_t BSLAB = (uint32_t)NT * 64;           // bytes of one B slab: [NT / 8][hi | lo][k / 4][8][4] floats
-  const uint32_t STAGE = (uint32_t)G * (8192 + BSLAB);  // G A slabs (hi 4 KB | lo 4 KB each), then G B slabs
-  const uint32_t BOFF = (uint32_t)G * 8192;
+  const uint32_t STAGE = (uint32_t)G * BSLAB;         // shared memory holds only the B slabs of a stage
+  // The A slabs live in TENSOR MEMORY (TS-form MMA): slab g of ring stage s = 16 columns (hi k0..7 | lo k0..7) at
+  // TG_ACOL + (s * G + g) * 16.  In shared memory they cost 8 KB of stores + 12 KB of MMA reads per slab and the
+  // kernel sat at the 128 B/clk shared-memory limit (30 KB per slab = 234 clk against 3 x 46 clk of MMA).
+  constexpr uint32_t TG_ACOL = 512 - 2 * G * 16;      // two ring stages of A: the top 288 (k3) / 256 (transposed) columns
+  constexpr int TG_ACC = (int)TG_ACOL;                // columns left for the accumulators (one buffer)
   uint8_t* s_stage = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NS * STAGE);
   uint64_t* empty = full + NS;
@@ -99,13 +104,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
   const int ZST = p.KD / GD;                             // depth-tap stages per channel-group block
   const int SPI = ((p.ncg + GC - 1) / GC) * ZST;         // ring stages per item; the last block may hold fewer groups
   const int voxels = p.Jd * p.Jh * p.Jw;
-  // Accumulator layout (256 TMEM columns per buffer, two buffers).  The tensor core truncates its fp32 accumulator on
+  // Accumulator layout (one buffer of TG_ACC = 224 / 256 TMEM columns; the rest of TMEM is the A ring).  The tensor core truncates its fp32 accumulator on
   // every accumulate, a bias that grows with the chain length: with all 3 * ncg * taps MMAs of an item chained into
   // one accumulator the 240->240 layer was 7x less accurate than the fp32 pipe (feature error 1.4e-5 vs 2e-6).  So
   // the hi*hi products -- the only ones whose magnitude matters -- go round-robin by stage into P partial accumulators
   // (chains of ~27 MMAs, like the resident-weight engine's), the two correction products into one more, and the
   // epilogue adds the P + 1 columns of a channel in fp32 with round-to-nearest.
-  const int P = max(1, min(8, 256 / NT - 1));
+  const int P = max(1, min(8, TG_ACC / NT - 1));
   const int Pe = min(P, SPI);  // partials an item actually writes
 
   if (tid == 0) {
@@ -113,10 +118,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
       tc_mbar_init(&full[i], TG_NTW + 1);  // the 8 producer warps of one set + the weight streamer's expect_tx arrive
       tc_mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      tc_mbar_init(&accf[i], 1);
-      tc_mbar_init(&acce[i], TG_NEW);
-    }
+    tc_mbar_init(&accf[0], 1);
+    tc_mbar_init(&acce[0], TG_NEW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -136,8 +139,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
     // the other set's conversion and stores.
     const int tw = (warp - TG_PROD_WARP) & (TG_NTW - 1);
     const int set = (warp - TG_PROD_WARP) / TG_NTW;
-    const int q = (tw >> 1) & 3;   // TMEM lane quadrant = rows q*32 .. q*32+31 of the tile
-    const int khalf = tw & 1;      // which 4 of the 8 channels of a group
+    const int q = warp & 3;        // TMEM lane quadrant this warp may access = rows q*32 .. q*32+31 of the tile
+    const int khalf = tw >> 2;     // which 4 of the 8 channels of a group (each quadrant occurs twice among 8 consecutive warps)
     const int m = q * 32 + lane;   // A row
     // load cursor: (item, cg0, td0) names a stage
     int item = blockIdx.x, cg0 = 0, td0 = 0, cur_b = 0;
@@ -213,26 +216,18 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
     uint32_t st = (uint32_t)set % (uint32_t)NS, ph = (uint32_t)set / (uint32_t)NS;  // ring slot / phase of stage n = set
     auto store_stage = [&](const float (&v)[G][4], int nv) {
       tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
-      uint8_t* sb = s_stage + (size_t)st * STAGE + khalf * 2048 + m * 16;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + TG_ACOL + st * (G * 16) + khalf * 4;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         if (g < nv) {
-          float4 hi, lo;
-          hi.x = tc_rna(v[g][0]);
-          hi.y = tc_rna(v[g][1]);
-          hi.z = tc_rna(v[g][2]);
-          hi.w = tc_rna(v[g][3]);
-          *reinterpret_cast<float4*>(sb + g * 8192) = hi;
-          if (p.npass == 3) {
-            lo.x = tc_rna(v[g][0] - hi.x);
-            lo.y = tc_rna(v[g][1] - hi.y);
-            lo.z = tc_rna(v[g][2] - hi.z);
-            lo.w = tc_rna(v[g][3] - hi.w);
-            *reinterpret_cast<float4*>(sb + g * 8192 + 4096) = lo;
-          }
+          const float h0 = tc_rna(v[g][0]), h1 = tc_rna(v[g][1]), h2 = tc_rna(v[g][2]), h3 = tc_rna(v[g][3]);
+          tc_st4(ta + g * 16, h0, h1, h2, h3);
+          if (p.npass == 3) tc_st4(ta + g * 16 + 8, tc_rna(v[g][0] - h0), tc_rna(v[g][1] - h1), tc_rna(v[g][2] - h2), tc_rna(v[g][3] - h3));
         }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+      tc_st_wait();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(&full[st]);
       st += TG_NSET;  // this set's next stage is TG_NSET further along the ring
@@ -268,7 +263,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
           for (int td0 = 0; td0 < p.KD; td0 += GD) {
             tc_mbar_wait(&empty[st], ph ^ 1, 300 + (int)st);
             tc_mbar_expect_tx(&full[st], (uint32_t)(ngc * TPB) * bytes);
-            uint8_t* sb = s_stage + (size_t)st * STAGE + BOFF;
+            uint8_t* sb = s_stage + (size_t)st * STAGE;
             for (int gc = 0; gc < ngc; ++gc) {
               const float* src = p.wtc + (((long long)ti.phase * p.ncg + cg0 + gc) * p.taps + td0 * KW * KW) * slab_floats + n0 * 16;
               if (whole) {
@@ -291,14 +286,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
     // D = f32, A = B = tf32, both K-major, N = NT, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-    const uint64_t a0 = tc_desc(tc_smem_u32(s_stage), 2048, 128), b0 = tc_desc(tc_smem_u32(s_stage) + BOFF, 128, 512);
+    const uint64_t b0 = tc_desc(tc_smem_u32(s_stage), 128, 512);
     const bool three = p.npass == 3;
     uint32_t st = 0, ph = 0, ai = 0;
     for (int item = blockIdx.x; item < p.items; item += p.ctas) {
-      const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
-      tc_mbar_wait(&acce[ab], aph ^ 1, 400 + (int)ab);  // epilogue has drained this accumulator buffer
+      const uint32_t ab = 0, aph = ai & 1;
+      tc_mbar_wait(&acce[ab], aph ^ 1, 400 + (int)ab);  // epilogue has drained the accumulators
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t dbuf = tmem_u + ab * 256, dcorr = dbuf + P * NT;
+      const uint32_t dbuf = tmem_u, dcorr = dbuf + P * NT;
       int part = 0;
       for (int sg = 0; sg < SPI; ++sg) {
         const int nv = min(GC, p.ncg - (sg / ZST) * GC) * (GD * KW * KW);
@@ -307,11 +302,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
         if (leader) {
           const uint64_t so = (uint64_t)((st * STAGE) >> 4);
           for (int g = 0; g < nv; ++g) {
-            const uint64_t a_hi = a0 + so + (uint64_t)((g * 8192) >> 4), b_hi = b0 + so + (uint64_t)((g * BSLAB) >> 4);
-            tc_mma(dbuf + part * NT, a_hi, b_hi, idesc, (sg >= P || g) ? 1u : 0u);
+            const uint32_t a_hi = tmem_u + TG_ACOL + (st * G + g) * 16;
+            const uint64_t b_hi = b0 + so + (uint64_t)((g * BSLAB) >> 4);
+            tc_mma_ts(dbuf + part * NT, a_hi, b_hi, idesc, (sg >= P || g) ? 1u : 0u);
             if (three) {
-              tc_mma(dcorr, a_hi + (4096 >> 4), b_hi, idesc, (sg | g) ? 1u : 0u);
-              tc_mma(dcorr, a_hi, b_hi + (256 >> 4), idesc, 1u);
+              tc_mma_ts(dcorr, a_hi + 8, b_hi, idesc, (sg | g) ? 1u : 0u);
+              tc_mma_ts(dcorr, a_hi, b_hi + (256 >> 4), idesc, 1u);
             }
           }
           tc_commit(&empty[st]);
@@ -349,10 +345,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
       float* op = p.out + obase;
       const float* rp = p.residual ? p.residual + obase : nullptr;
       const float* mp = p.out_mul ? p.out_mul + (long long)ti.b * p.omB + (long long)oy * p.omH + ox : nullptr;
-      const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
+      const uint32_t ab = 0, aph = ai & 1;
       tc_mbar_wait(&accf[ab], aph, 600 + (int)ab);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * 256;
+      const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16);
       const int nacc = Pe + (p.npass == 3 ? 1 : 0);  // columns to add per channel: partials 0..Pe-1, then the corrections at P
       for (int c8 = 0; c8 < NT; c8 += 8) {
         float rv[8], t0[8], t1[8];
@@ -454,8 +450,7 @@ bool tcg_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcgPlan* plan) {
   int best_ncot = 0, best_nt = 0;
   for (int ncot = 1; ncot <= 16; ++ncot) {
     const int nt = round_up(ceil_div(tp.CoutX, ncot), 8);
-    if (nt > 128 || (ncot > 1 && (ncot - 1) * nt >= tp.CoutX)) continue;
-    if (2 * (d->transposed ? 8 : 9) * (8192 + (size_t)nt * 64) > 227 * 1024 - 1024) continue;  // two ring stages must fit
+    if (nt > 112 || (ncot > 1 && (ncot - 1) * nt >= tp.CoutX)) continue;  // one partial + the corrections in 224 columns
     const long long items = mt_all * ncot;
     const long long waves = ceil_div_ll(items, num_sms);
     const double mma = (nt / 2.0 + 10.0) > 46.0 ? (nt / 2.0 + 10.0) : 46.0;
@@ -471,13 +466,9 @@ bool tcg_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcgPlan* plan) {
   plan->ncot = best_ncot;
   plan->mtiles = mtiles;
   plan->npass = npass;
-  const size_t slab = 8192 + (size_t)best_nt * 64;
-  const size_t limit = 227 * 1024 - 1024;
   const int G = d->transposed ? 8 : 9;
-  int ns = (int)(limit / (G * slab));
-  if (ns < 2) return false;
-  plan->nstages = ns > 4 ? 4 : ns;
-  plan->smem = plan->nstages * G * slab + 1024;
+  plan->nstages = 2;  // the A ring in tensor memory has two stages; the B ring in shared memory follows it
+  plan->smem = (size_t)plan->nstages * G * best_nt * 64 + 1024;
   const long long items = mt_all * best_ncot;
   if (items >= (1ll << 31)) return false;
   plan->ctas = (int)(items < num_sms ? items : num_sms);

@@ -54,6 +54,22 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db
       "l"(da), "l"(db), "r"(idesc), "r"(acc)
       : "memory");
 }
+// TS form: the A operand (128 rows x 8 tf32) comes from tensor memory -- row m at TMEM lane m, k at column a + k
+// (scratch/umma_ts_test.cu) -- so it costs no shared-memory bandwidth; B stays a shared-memory descriptor.
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// registers -> TMEM: this warp's lane quadrant, 4 consecutive columns (asynchronous: tc_st_wait() before signalling)
+__device__ __forceinline__ void tc_st4(uint32_t taddr, float a, float b, float c, float d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)),
+               "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
+               : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
