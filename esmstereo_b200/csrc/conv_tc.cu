@@ -51,6 +51,7 @@ struct TcK {
   long long oB, oC, oD, oH;
   int nseg, segw, rows, nstrips, groups, ztiles;
   int items_per_cot, ctas_per_cot, nstages, npass;
+  int ps;  // PixelShuffle(2) store (pointwise layers only): channel co -> out[co / 4][2y + (co / 2) % 2][2x + co % 2]
 };
 
 constexpr int TC_NTW = 8;                               // operand-producer warps
@@ -438,6 +439,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), p.act);
                 rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
               }
+              if (TAPS == 1 && p.ps == 2) {
+                // UpShuffle (ESMStereo.py:265-268): the 4 channels of a unit are the 2 x 2 output pixels of shuffled
+                // channel (co / 4) at (2y, 2x): two 8-byte stores per lane, 256 contiguous bytes per warp and row
+                if (p.act2 == ESM_ACT_SILU) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) rv[j] = tc_silu(rv[j]);
+                } else if (p.act2 != ESM_ACT_NONE) {
+                  const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), p.act2);
+                  rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
+                }
+                if (c4 < nvalid) {
+                  float* o = p.out + ((long long)ti.b * p.oB + (long long)((cot * COT + cl) >> 2) * p.oC + (long long)(2 * yo) * p.oH + 2 * x);
+                  *reinterpret_cast<float2*>(o) = make_float2(rv[0] * oscale, rv[1] * oscale);
+                  *reinterpret_cast<float2*>(o + p.oH) = make_float2(rv[2] * oscale, rv[3] * oscale);
+                }
+                continue;
+              }
               const int o_off = zo * oD + yo * oH + c4 * oC;
               if (post) {
 #pragma unroll
@@ -510,7 +528,10 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
   const bool k3 = d->kh == 3 && d->kw == 3 && d->ph == 1 && d->pw == 1 && (d->kd == 1 || d->kd == 3) && d->pd == d->kd / 2;
   const bool k1 = d->kh == 1 && d->kw == 1 && d->kd == 1 && d->ph == 0 && d->pw == 0 && d->pd == 0;
   if (!k3 && !k1) return false;
-  if (d->pixel_shuffle || d->in_mul) return false;
+  if (d->in_mul) return false;
+  if (d->pixel_shuffle && !(d->pixel_shuffle == 2 && k1 && d->Cout % 4 == 0 && !d->out_mul && !d->residual && (d->oH % 2) == 0 &&
+                            (reinterpret_cast<uintptr_t>(d->out) & 7) == 0))
+    return false;
   if (d->Cin < 8 || num_sms <= 0) return false;
   // the kernel addresses one batch item with 32-bit element offsets
   for (int i = 0; i < d->nsrc; ++i)
@@ -616,6 +637,7 @@ int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
   k.ctas_per_cot = plan.ctas_per_cot;
   k.nstages = plan.nstages;
   k.npass = plan.npass;
+  k.ps = d->pixel_shuffle;
   tc_fn_t fn = tc_pick(plan.COT, plan.TZ, plan.KD, plan.gwc != 0, plan.taps);
   ESM_REQUIRE(fn, "conv(tc): no kernel for COT=%d TZ=%d KD=%d", plan.COT, plan.TZ, plan.KD);
   // one limit for every launch of a function: the attribute is per function, not per launch, and graph

@@ -131,6 +131,14 @@ __device__ __forceinline__ float tc_rna(float x) {
 //   gelu(x) = x - h (x >= 0),  h (x < 0),   h = 0.5 x erfc(|x| / sqrt 2).
 // Absolute error <= 6e-8 (an ulp of an O(1) activation), relative error <= 3e-7 for x >= 0; the fit and its
 // error table are in tests/test_host_cpu.py::test_tc_gelu_polynomial.
+// SiLU for the same epilogues: x / (1 + 2^(-x log2 e)) with ex2.approx and rcp.approx (relative error ~3e-7); expf + an
+// IEEE division cost the FP32-pipe epilogue 21 us on the 16 -> 64 UpShuffle layer.
+__device__ __forceinline__ float tc_silu(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 __device__ __forceinline__ float tc_gelu(float x) {
   const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
   float q = -2.906944503e-05f;

@@ -507,3 +507,17 @@ def test_single_channel_deconv_subpixel_form(nd, shape, bn):
         crop = tuple(2 * s - 1 for s in shape[2:])
         got2 = m(x.cuda(), out_size=crop)
         assert rel(got2, want[(slice(None), slice(None)) + tuple(slice(0, c) for c in crop)]) < 2e-5
+
+
+@pytest.mark.parametrize("cin,cout,shape", [(16, 64, (33, 70)), (8, 32, (12, 312)), (16, 16, (5, 9))])
+def test_conv_tensor_core_pointwise_pixel_shuffle(cin, cout, shape, tc_forced):
+    """UpShuffle (ESMStereo.py:265-268): 1x1 conv -> PixelShuffle(2) -> SiLU as one tcgen05 launch."""
+    ops = _ops()
+    p = make_layer(cin, cout, 1, 2, bn=False, bias=True, seed=11)
+    x = rnd(2, cin, *shape, seed=4)
+    want = F.silu(F.pixel_shuffle(ref_conv(x, p, 1, 0, False, None, 2), 2))
+    n0 = tc_forced()
+    got = ops.conv(x.cuda(), gpu_pack(p, 1, 0, False), None, pixel_shuffle=2, act2="silu")
+    assert tc_forced() == n0 + 1, "layer did not take the tensor-core path"
+    assert got.shape == want.shape
+    assert rel(got, want) < 2e-5
