@@ -52,6 +52,7 @@ SIGNATURES = {
     "esm_conv_f32": (C.c_int, [C.POINTER(EsmConv), vp]),
     "esm_tc_conv_launches": (C.c_longlong, []),
     "esm_tcg_conv_launches": (C.c_longlong, []),
+    "esm_pw_conv_launches": (C.c_longlong, []),
     "esm_gwc_volume_f32": (C.c_int, [vp, vp, vp] + [C.c_int] * 6 + [vp]),
     "esm_norm_corr_volume_f32": (C.c_int, [vp, vp, vp, vp] + [C.c_int] * 5 + [vp]),
     "esm_concat_volume_f32": (C.c_int, [vp, vp, vp] + [C.c_int] * 5 + [vp]),

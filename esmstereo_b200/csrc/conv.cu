@@ -355,9 +355,11 @@ struct Plan {
   conv_fn_t fn;         // cp.async pipeline (any strides)
   conv_fn_t fn_tma[2];  // TMA pipeline for window offset XO = 0 / 3 (nullptr if not instantiated)
   int cosplit, COP, COG, CK, blocks_per_sm;
-  int use_tc;  // 1: run on the resident-weight tcgen05 path (conv_tc.cu), 2: on the streamed-weight one (conv_tcg.cu)
+  int use_tc;  // 1: run on the resident-weight tcgen05 path (conv_tc.cu), 2: on the streamed-weight one (conv_tcg.cu),
+               // 3: on the pointwise streaming kernel (conv_pw.cu)
   TcPlan tc;
   TcgPlan tcg;
+  PwPlan pw;
 };
 
 struct LayerGeom {
@@ -619,7 +621,9 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   const char* tc_env = getenv("ESM_TC");
   const int tc_pass = d->engine == 1 ? 0 : (tc_env ? atoi(tc_env) : 3);
   // ESM_TC_FORCE=1 forces the resident-weight engine, =2 the streamed-weight engine, wherever eligible
-  const int tc_force = (getenv("ESM_TC_FORCE") != nullptr && tc_pass != 0) ? (atoi(getenv("ESM_TC_FORCE")) == 2 ? 2 : 1) : 0;
+  // ... =3 the pointwise streaming kernel (true fp32: allowed for engine == 1 layers too)
+  const int force_env = getenv("ESM_TC_FORCE") ? atoi(getenv("ESM_TC_FORCE")) : 0;
+  const int tc_force = force_env == 3 ? 3 : (force_env != 0 && tc_pass != 0) ? (force_env == 2 ? 2 : 1) : 0;
   PlanKey key = {{d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed, lg.Jw, lg.Jh, lg.Jd, gwc ? k.cpg : 0, d->B, d->pd,
                   d->ph, d->pw, tc_pass * 4 + tc_force + (d->in_mul ? 64 : 0) + (d->pixel_shuffle ? 128 : 0)}};
   std::lock_guard<std::mutex> lock(plans_mu);
@@ -636,7 +640,8 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   }
   auto it = plans.find(key);
   if (it != plans.end())
-    return it->second.use_tc == 2   ? tcg_conv_launch(d, it->second.tcg, st)
+    return it->second.use_tc == 3   ? pw_conv_launch(d, it->second.pw, st)
+           : it->second.use_tc == 2 ? tcg_conv_launch(d, it->second.tcg, st)
            : it->second.use_tc == 1 ? tc_conv_launch(d, it->second.tc, st)
                                     : launch_plan(d, g, k, it->second, lg, num_sms, st);
 
@@ -773,14 +778,19 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   // taken when forced, or when they beat the best FP32-pipe plan in the on-device timing ----
   TcPlan tcp;
   TcgPlan tgp;
-  const bool tc_ok = tc_pass != 0 && tc_force != 2 && tc_conv_plan(d, num_sms, tc_pass == 1 ? 1 : 3, &tcp);
-  const bool tg_ok = tc_pass != 0 && tc_force != 1 && getenv("ESM_TCG_OFF") == nullptr && tcg_conv_plan(d, num_sms, tc_pass == 1 ? 1 : 3, &tgp);
+  PwPlan pwp;
+  const bool tc_ok = tc_pass != 0 && (tc_force == 0 || tc_force == 1) && tc_conv_plan(d, num_sms, tc_pass == 1 ? 1 : 3, &tcp);
+  const bool tg_ok = tc_pass != 0 && (tc_force == 0 || tc_force == 2) && getenv("ESM_TCG_OFF") == nullptr &&
+                     tcg_conv_plan(d, num_sms, tc_pass == 1 ? 1 : 3, &tgp);
+  const bool pw_ok = (tc_force == 0 || tc_force == 3) && getenv("ESM_PW_OFF") == nullptr && num_sms > 0 && pw_conv_plan(d, &pwp);
   best_plan.use_tc = 0;
   if (tc_force == 1 && tc_ok) {
     best_plan.use_tc = 1;
   } else if (tc_force == 2 && tg_ok) {
     best_plan.use_tc = 2;
-  } else if (!tc_force && tune && (tc_ok || tg_ok)) {
+  } else if (tc_force == 3 && pw_ok) {
+    best_plan.use_tc = 3;
+  } else if (!tc_force && tune && (tc_ok || tg_ok || pw_ok)) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -789,7 +799,9 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
       for (int rep = 0; rep < 3; ++rep) {  // rep 0 warms
         cudaEventRecord(e0, st);
         for (int l = 0; l < 3; ++l) {
-          if (engine == 2)
+          if (engine == 3)
+            pw_conv_launch(d, pwp, st);
+          else if (engine == 2)
             tcg_conv_launch(d, tgp, st);
           else if (engine == 1)
             tc_conv_launch(d, tcp, st);
@@ -807,20 +819,23 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
     if (best_ms >= 1e29f) best_ms = time3(0);
     const float tc_ms = tc_ok ? time3(1) : 1e30f;
     const float tg_ms = tg_ok ? time3(2) : 1e30f;
+    const float pw_ms = pw_ok ? time3(3) : 1e30f;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    if (best_ms < 0.f || tc_ms < 0.f || tg_ms < 0.f) return check_launch("conv(autotune tc)");
+    if (best_ms < 0.f || tc_ms < 0.f || tg_ms < 0.f || pw_ms < 0.f) return check_launch("conv(autotune tc)");
     if (tc_ms < best_ms && tc_ms <= tg_ms) best_plan.use_tc = 1;
     if (tg_ms < best_ms && tg_ms < tc_ms) best_plan.use_tc = 2;
+    if (pw_ms < best_ms && pw_ms < tc_ms && pw_ms < tg_ms) best_plan.use_tc = 3;
     if (getenv("ESM_DEBUG_PLAN"))
       fprintf(stderr, "[esm tune] Cin=%d Cout=%d k=(%d,%d,%d) s=%d%s J=(%d,%d,%d)%s: fp32 %.1f us | tcgen05 resident %.1f us (COT=%d TZ=%d) | "
-              "streamed %.1f us (NT=%d x%d, %d ctas, %d stages) -> engine %d\n",
+              "streamed %.1f us (NT=%d x%d, %d ctas, %d stages) | pointwise %.1f us -> engine %d\n",
               d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed ? " T" : "", lg.Jd, lg.Jh, lg.Jw, gwc ? " gwc" : "", best_ms * 1000.f,
               tc_ok ? tc_ms * 1000.f : -1.f, tc_ok ? tcp.COT : 0, tc_ok ? tcp.TZ : 0, tg_ok ? tg_ms * 1000.f : -1.f, tg_ok ? tgp.NT : 0,
-              tg_ok ? tgp.ncot : 0, tg_ok ? tgp.ctas : 0, tg_ok ? tgp.nstages : 0, best_plan.use_tc);
+              tg_ok ? tgp.ncot : 0, tg_ok ? tgp.ctas : 0, tg_ok ? tgp.nstages : 0, pw_ok ? pw_ms * 1000.f : -1.f, best_plan.use_tc);
   }
   if (best_plan.use_tc == 1) best_plan.tc = tcp;
   if (best_plan.use_tc == 2) best_plan.tcg = tgp;
+  if (best_plan.use_tc == 3) best_plan.pw = pwp;
   if (getenv("ESM_DEBUG_PLAN"))
     fprintf(stderr, "[esm plan] Cin=%d Cout=%d k=(%d,%d,%d) s=%d%s%s J=(%d,%d,%d): CK=%d COP=%d cosplit=%d tile=(%d,%d,%d) threads=%d "
             "smem=%zu KB occ=%d tuned=%d\n",
@@ -828,7 +843,8 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
             best_plan.CK, best_plan.COP, best_plan.cosplit, best_plan.tl.TD, best_plan.tl.TH, best_plan.tl.TWG * best_plan.tl.NV,
             best_plan.tl.slots * (best_plan.COP / best_plan.COG), best_plan.tl.smem / 1024, best_plan.blocks_per_sm, (int)tune);
   plans.emplace(key, best_plan);
-  return best_plan.use_tc == 2   ? tcg_conv_launch(d, best_plan.tcg, st)
+  return best_plan.use_tc == 3   ? pw_conv_launch(d, best_plan.pw, st)
+         : best_plan.use_tc == 2 ? tcg_conv_launch(d, best_plan.tcg, st)
          : best_plan.use_tc == 1 ? tc_conv_launch(d, best_plan.tc, st)
                                  : launch_plan(d, g, k, best_plan, lg, num_sms, st);
 }

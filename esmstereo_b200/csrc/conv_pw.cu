@@ -1,0 +1,223 @@
+// Pointwise (1x1 / 1x1x1) convolutions as a streaming kernel: the k1 layers of the path -- aggregation.agg_0.0 /
+// agg_1.0 after the skip concatenation (ESMStereo.py:152-157), up_refinement.agg_* (:211-216), the last layer of
+// every disparity MLP (k1 with padding 1, :248-253), FMBlock's 1x1 (shufflemixer.py:126) and UpShuffle's 1x1 +
+// PixelShuffle(2) + SiLU (ESMStereo.py:265-268) -- move 30-60 MB for a fraction of a GFLOP: they are HBM-bound, and
+// both persistent conv engines ran them at 1.5 TB/s (latency per tile, not bandwidth: the 16 -> 64 UpShuffle layer took
+// 62 us for 38 MB).  Here a thread owns ONE output pixel and CO output channels in registers, walks the input
+// channels with coalesced 4-byte loads (a warp reads 128 contiguous bytes per channel; 8 channels in flight), takes the
+// weights as broadcast 16-byte shared-memory reads (one LDS.128 per 4 FMAs), and stores each channel coalesced --
+// PixelShuffle(2) pairs as 8-byte stores.  Plain grid (one small CTA per 128 pixels x channel tile): occupancy, not a
+// software pipeline, hides the latency.
+#include "conv_tc.cuh"
+#include "tc_common.cuh"
+
+#include <string.h>
+
+namespace esm {
+
+// activations of 4 values: the branch-free GELU / SiLU of the tensor-core epilogues (ulp-level error, 16 / 5 instructions
+// instead of erff / expf + IEEE division), the generic out-of-line path for the rest
+__device__ __forceinline__ void pw_act4(float (&rv)[4], int act) {
+  if (act == ESM_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rv[j] = tc_gelu(rv[j]);
+  } else if (act == ESM_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rv[j] = tc_silu(rv[j]);
+  } else if (act != ESM_ACT_NONE) {
+    const float4 r = apply_act4(make_float4(rv[0], rv[1], rv[2], rv[3]), act);
+    rv[0] = r.x; rv[1] = r.y; rv[2] = r.z; rv[3] = r.w;
+  }
+}
+
+struct PwK {
+  esm_src_t src[3];
+  int nsrc;
+  int B, Cin, CinPad, CoutPad, Cout;
+  int Din, Hin, Win;      // input extent
+  int OD, OH, OW;         // output extent (= input + 2 * pad in h, w)
+  int ph, pw;
+  const float* weight;    // fp32 pack [CinPad][CoutPad]
+  const float* scale;
+  const float* shift;
+  int act, act2, ps;
+  const float* out_mul;
+  long long omB, omC, omH;
+  const float* residual;
+  float out_scale;
+  float* out;
+  long long oB, oC, oD, oH;
+  long long pixels;       // OD * OH * OW
+  int cotiles;
+};
+
+constexpr int PW_THREADS = 128;
+
+// CO output channels per thread (one channel tile per blockIdx.y)
+template <int CO>
+__global__ void __launch_bounds__(PW_THREADS) pw_conv_kernel(const __grid_constant__ PwK p) {
+  extern __shared__ __align__(16) float s_w[];  // [Cin][CO]: this tile's weights
+  const int co0 = blockIdx.y * CO;
+  const int b = blockIdx.z;
+  for (int i = threadIdx.x; i < p.Cin * CO; i += PW_THREADS) {
+    const int ci = i / CO, c = i - ci * CO;
+    s_w[i] = (co0 + c < p.CoutPad) ? __ldg(p.weight + (long long)ci * p.CoutPad + co0 + c) : 0.f;
+  }
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * PW_THREADS + threadIdx.x;
+  if (pix >= p.pixels) return;
+  const int ox = (int)(pix % p.OW);
+  const long long t = pix / p.OW;
+  const int oy = (int)(t % p.OH), oz = (int)(t / p.OH);
+  const int iy = oy - p.ph, ix = ox - p.pw;
+  const bool inside = (unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win;  // k1 with padding: the border sees zeros
+  float acc[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+  if (inside) {
+    int ci0 = 0;
+    for (int s = 0; s < p.nsrc; ++s) {
+      const esm_src_t& sr = p.src[s];
+      const float* ip = sr.ptr + (long long)b * sr.sB + (long long)oz * sr.sD + (long long)iy * sr.sH + ix;
+      const long long sC = sr.sC;
+      int c = 0;
+      for (; c + 8 <= sr.C; c += 8) {
+        float x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = __ldg(ip + (c + u) * sC);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4* w4 = reinterpret_cast<const float4*>(s_w + (ci0 + c + u) * CO);
+#pragma unroll
+          for (int j = 0; j < CO / 4; ++j) {
+            const float4 w = w4[j];
+            acc[4 * j + 0] = fmaf(x[u], w.x, acc[4 * j + 0]);
+            acc[4 * j + 1] = fmaf(x[u], w.y, acc[4 * j + 1]);
+            acc[4 * j + 2] = fmaf(x[u], w.z, acc[4 * j + 2]);
+            acc[4 * j + 3] = fmaf(x[u], w.w, acc[4 * j + 3]);
+          }
+        }
+      }
+      for (; c < sr.C; ++c) {
+        const float x = __ldg(ip + c * sC);
+        const float4* w4 = reinterpret_cast<const float4*>(s_w + (ci0 + c) * CO);
+#pragma unroll
+        for (int j = 0; j < CO / 4; ++j) {
+          const float4 w = w4[j];
+          acc[4 * j + 0] = fmaf(x, w.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(x, w.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(x, w.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(x, w.w, acc[4 * j + 3]);
+        }
+      }
+      ci0 += sr.C;
+    }
+  }
+  // epilogue: affine -> act -> (x out_mul) -> (+ residual) -> act2 -> scale -> store
+  const bool post = p.out_mul || p.residual;
+#pragma unroll
+  for (int c4 = 0; c4 < CO; c4 += 4) {
+    const int co = co0 + c4;
+    if (co >= p.Cout) break;
+    float rv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cj = min(co + j, p.Cout - 1);
+      rv[j] = fmaf(acc[c4 + j], p.scale ? __ldg(p.scale + cj) : 1.f, p.shift ? __ldg(p.shift + cj) : 0.f);
+    }
+    pw_act4(rv, p.act);
+    if (p.ps == 2) {
+      // channel co -> (co / 4, row 2y + (co / 2) % 2, column 2x + co % 2): the 4 channels of a unit are one 2 x 2 block
+      pw_act4(rv, p.act2);
+      float* o = p.out + ((long long)b * p.oB + (long long)(co >> 2) * p.oC + (long long)(2 * oy) * p.oH + 2 * ox);
+      *reinterpret_cast<float2*>(o) = make_float2(rv[0] * p.out_scale, rv[1] * p.out_scale);
+      *reinterpret_cast<float2*>(o + p.oH) = make_float2(rv[2] * p.out_scale, rv[3] * p.out_scale);
+      continue;
+    }
+    const long long obase = (long long)b * p.oB + (long long)oz * p.oD + (long long)oy * p.oH + ox;
+    if (post) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (co + j < p.Cout) {
+          if (p.out_mul) rv[j] *= __ldg(p.out_mul + (long long)b * p.omB + (long long)(co + j) * p.omC + (long long)oy * p.omH + ox);
+          if (p.residual) rv[j] += __ldg(p.residual + obase + (long long)(co + j) * p.oC);
+        }
+      }
+    }
+    pw_act4(rv, p.act2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (co + j < p.Cout) p.out[obase + (long long)(co + j) * p.oC] = rv[j] * p.out_scale;
+  }
+}
+
+static long long pw_launches = 0;
+
+bool pw_conv_plan(const esm_conv_t* d, PwPlan* plan) {
+  if (d->src_mode != ESM_SRC_TENSORS || d->transposed || d->in_mul) return false;
+  if (!(d->kd == 1 && d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pd == 0)) return false;
+  if (d->Cin < 4 || d->Cout < 4) return false;
+  if (d->pixel_shuffle && !(d->pixel_shuffle == 2 && d->Cout % 4 == 0 && !d->out_mul && !d->residual && (d->oH % 2) == 0 &&
+                            (reinterpret_cast<uintptr_t>(d->out) & 7) == 0 && d->Dout == 1))
+    return false;
+  if (d->B > 65535) return false;
+  const int cop8 = round_up(d->Cout, 8);
+  // channels per thread: 32 accumulators at most (two CTAs' worth of registers stay resident); wider layers re-read the
+  // input once per channel tile, from L2
+  plan->CO = cop8 <= 8 ? 8 : cop8 <= 16 ? 16 : cop8 <= 24 ? 24 : 32;
+  plan->cotiles = ceil_div(d->Cout, plan->CO);
+  if (plan->cotiles > 8) return false;
+  plan->smem = (size_t)d->Cin * plan->CO * sizeof(float);
+  return plan->smem <= 96 * 1024;
+}
+
+int pw_conv_launch(const esm_conv_t* d, const PwPlan& plan, cudaStream_t st) {
+  PwK k;
+  memset(&k, 0, sizeof(k));
+  for (int i = 0; i < d->nsrc; ++i) k.src[i] = d->src[i];
+  k.nsrc = d->nsrc;
+  k.B = d->B;
+  k.Cin = d->Cin;
+  const TcgPack tp = tcg_pack_geom(d->Cout, d->Cin, 1, 1, 1, 0);
+  k.CinPad = round_up(d->Cin, 8);
+  k.CoutPad = (int)(tp.offset / k.CinPad);  // the fp32 pack is [CinPad][CoutPad] for a pointwise layer
+  k.Cout = d->Cout;
+  k.Din = d->Din;
+  k.Hin = d->Hin;
+  k.Win = d->Win;
+  k.OD = d->Dout;
+  k.OH = d->Hout;
+  k.OW = d->Wout;
+  k.ph = d->ph;
+  k.pw = d->pw;
+  k.weight = d->weight;
+  k.scale = d->scale;
+  k.shift = d->shift;
+  k.act = d->act;
+  k.act2 = d->act2;
+  k.ps = d->pixel_shuffle;
+  k.out_mul = d->out_mul;
+  k.omH = d->Wout;
+  k.omC = (long long)d->Hout * d->Wout;
+  k.omB = k.omC * d->Cout;
+  k.residual = d->residual;
+  k.out_scale = d->out_scale;
+  k.out = d->out;
+  k.oB = d->oB;
+  k.oC = d->oC;
+  k.oD = d->oD;
+  k.oH = d->oH;
+  k.pixels = (long long)d->Dout * d->Hout * d->Wout;
+  k.cotiles = plan.cotiles;
+  const dim3 grid((unsigned)ceil_div_ll(k.pixels, PW_THREADS), (unsigned)plan.cotiles, (unsigned)d->B);
+  void (*fn)(const PwK) = plan.CO == 8 ? pw_conv_kernel<8> : plan.CO == 16 ? pw_conv_kernel<16> : plan.CO == 24 ? pw_conv_kernel<24> : pw_conv_kernel<32>;
+  if (plan.smem > 48 * 1024 && cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
+    return check_launch("conv(pw, cudaFuncSetAttribute)");
+  fn<<<grid, PW_THREADS, plan.smem, st>>>(k);
+  ++pw_launches;
+  return check_launch("conv(pw)");
+}
+
+}  // namespace esm
+
+extern "C" long long esm_pw_conv_launches(void) { return esm::pw_launches; }

@@ -370,6 +370,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     const bool post = p.out_mul || p.residual || p.act2 != ESM_ACT_NONE;
     const bool gelu = p.act == ESM_ACT_GELU;
     const float oscale = p.out_scale;
+    // expected-value correction of the accumulator truncation (tc_common.cuh): every accumulator column chained
+    // ncg * KD MMA triples
+    const float debias = 1.0f + TC_TRUNC_BIAS * (float)(ncg * KD * (p.npass == 3 ? 3 : 1));
     uint32_t ai = 0;
     for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
       const TcItem ti = tc_decode(p, item, TZ);
@@ -431,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             if (row_ok && zo < nz) {
               const int cl = ch0 + c4;  // channel within the tile
 #pragma unroll
-              for (int j = 0; j < 4; ++j) rv[j] = fmaf(rv[j], s_aff[cl + j], s_aff[COT + cl + j]);
+              for (int j = 0; j < 4; ++j) rv[j] = fmaf(rv[j] * debias, s_aff[cl + j], s_aff[COT + cl + j]);
               if (gelu) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) rv[j] = tc_gelu(rv[j]);

@@ -40,6 +40,15 @@ struct TcgPlan {
 bool tcg_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcgPlan* plan);
 int tcg_conv_launch(const esm_conv_t* d, const TcgPlan& plan, cudaStream_t st);
 
+// Streaming kernel for pointwise (k1) layers (conv_pw.cu): true fp32, HBM-bound.
+struct PwPlan {
+  int CO;       // output channels per thread (8 / 16 / 24 / 32)
+  int cotiles;  // channel tiles (gridDim.y)
+  size_t smem;
+};
+bool pw_conv_plan(const esm_conv_t* d, PwPlan* plan);
+int pw_conv_launch(const esm_conv_t* d, const PwPlan& plan, cudaStream_t st);
+
 // Fills `plan` and returns true when `d` can run on the tensor-core path.
 bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan);
 int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st);

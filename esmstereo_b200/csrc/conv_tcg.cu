@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
   // the hi*hi products -- the only ones whose magnitude matters -- go round-robin by stage into P partial accumulators
   // (chains of ~27 MMAs, like the resident-weight engine's), the two correction products into one more, and the
   // epilogue adds the P + 1 columns of a channel in fp32 with round-to-nearest.
-  const int P = max(1, min(8, TG_ACC / NT - 1));
+  const int P = max(1, min(12, TG_ACC / NT - 1));
   const int Pe = min(P, SPI);  // partials an item actually writes
 
   if (tid == 0) {
@@ -350,6 +350,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16);
       const int nacc = Pe + (p.npass == 3 ? 1 : 0);  // columns to add per channel: partials 0..Pe-1, then the corrections at P
+      // expected-value correction of the accumulator truncation: each of the ~slabs/Pe chained accumulates into a
+      // partial rounds it toward zero, -1.25e-8 relative per step on average (scripts/engine_accuracy.py: the bias
+      // column; the FP32 pipe rounds to nearest and has none)
+      const float debias = 1.0f + TC_TRUNC_BIAS * (float)(p.ncg * p.taps) / (float)Pe;
       for (int c8 = 0; c8 < NT; c8 += 8) {
         float rv[8], t0[8], t1[8];
         tc_ld8(tb + c8, rv);
@@ -362,6 +366,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
           for (int i = 0; i < 8; ++i) rv[i] += two ? t0[i] + t1[i] : t0[i];
         }
         tc_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rv[i] *= debias;
         if (c8 + 8 >= NT) {  // last TMEM read of this item: hand the accumulator buffer back
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
@@ -426,6 +432,11 @@ bool tcg_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcgPlan* plan) {
   if (d->src_mode != ESM_SRC_TENSORS || d->pixel_shuffle || d->in_mul) return false;
   if (d->Cin < 8 || num_sms <= 0) return false;
   if (d->stride != 1 && d->stride != 2) return false;
+  {  // ESM_TCG_DIMS=2 / 3: only 2D / only 3D layers (accuracy experiments, scripts/sceneflow_parity.py)
+    const char* dims = getenv("ESM_TCG_DIMS");
+    const bool is3d = d->Dout > 1 || d->Din > 1;
+    if (dims && ((dims[0] == '2' && is3d) || (dims[0] == '3' && !is3d))) return false;
+  }
   if (d->transposed && !(d->kh == 4 && d->kw == 4 && (d->kd == 4 || d->kd == 1) && d->stride == 2)) return false;
   if (!d->transposed && !(d->kh == 3 && d->kw == 3 && (d->kd == 3 || d->kd == 1))) return false;  // k1 / k5 stay on the other engines
   for (int i = 0; i + 1 < d->nsrc; ++i)
@@ -446,11 +457,20 @@ bool tcg_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcgPlan* plan) {
   const int KT = tp.ncg * tp.taps;
   // channel tile: the MMA costs ~max(46, N/2 + 10) clk (A-read bound below N ~ 72), a CTA walks KT slabs per item;
   // pick the tile count that finishes first
+  // Accuracy constraint: the tensor core truncates its accumulator at every accumulate, a systematic toward-zero bias
+  // of ~1.2e-8 (relative) per chained hi*hi MMA (scripts/engine_accuracy.py).  The chain of a partial accumulator is
+  // slabs / P stages' worth of MMAs with P = columns / NT - 1, so narrower channel tiles buy shorter chains: tiles whose
+  // chain exceeds TG_MAXCHAIN slabs are skipped (FeatUp's 240 -> 240 at NT = 64 chained 135 and, upstream of the cost
+  // volume, doubled the top-2 flips of the SceneFlow-shape test).
+  constexpr int TG_MAXCHAIN = 160;
+  const int acc_cols = 512 - 2 * (d->transposed ? 8 : 9) * 16;
   double best = 1e30;
   int best_ncot = 0, best_nt = 0;
-  for (int ncot = 1; ncot <= 16; ++ncot) {
+  for (int ncot = 1; ncot <= 32; ++ncot) {
     const int nt = round_up(ceil_div(tp.CoutX, ncot), 8);
     if (nt > 112 || (ncot > 1 && (ncot - 1) * nt >= tp.CoutX)) continue;  // one partial + the corrections in 224 columns
+    const int P = acc_cols / nt - 1 > 12 ? 12 : acc_cols / nt - 1;
+    if (ceil_div(KT, P) > TG_MAXCHAIN && nt > 8) continue;
     const long long items = mt_all * ncot;
     const long long waves = ceil_div_ll(items, num_sms);
     const double mma = (nt / 2.0 + 10.0) > 46.0 ? (nt / 2.0 + 10.0) : 46.0;

@@ -131,6 +131,11 @@ __device__ __forceinline__ float tc_rna(float x) {
 //   gelu(x) = x - h (x >= 0),  h (x < 0),   h = 0.5 x erfc(|x| / sqrt 2).
 // Absolute error <= 6e-8 (an ulp of an O(1) activation), relative error <= 3e-7 for x >= 0; the fit and its
 // error table are in tests/test_host_cpu.py::test_tc_gelu_polynomial.
+// Mean relative truncation error of one tcgen05 accumulate (the tensor core rounds its fp32 accumulator toward zero),
+// measured with scripts/engine_accuracy.py on coherent sums; the epilogues scale an accumulator that chained n
+// accumulates by 1 + n * TC_TRUNC_BIAS.
+constexpr float TC_TRUNC_BIAS = 1.25e-8f;
+
 // SiLU for the same epilogues: x / (1 + 2^(-x log2 e)) with ex2.approx and rcp.approx (relative error ~3e-7); expf + an
 // IEEE division cost the FP32-pipe epilogue 21 us on the 16 -> 64 UpShuffle layer.
 __device__ __forceinline__ float tc_silu(float x) {

@@ -111,6 +111,9 @@ long long esm_tc_conv_launches(void);
 /* Same for the streamed-weight tcgen05 engine (taps in K, weights through the operand ring: wide / strided /
  * transposed layers; ESM_TC_FORCE=2 forces it wherever eligible, ESM_TCG_OFF=1 disables it). */
 long long esm_tcg_conv_launches(void);
+/* Same for the pointwise (k1) streaming kernel (conv_pw.cu: true fp32, HBM-bound; ESM_TC_FORCE=3 forces it wherever
+ * eligible, ESM_PW_OFF=1 disables it). */
+long long esm_pw_conv_launches(void);
 
 /* build_gwc_volume (submodule.py:151-161): L,R [B,C,H,W] -> V [B,G,D,H,W]; writes the zero
  * triangle itself (no memset). */

@@ -521,3 +521,60 @@ def test_conv_tensor_core_pointwise_pixel_shuffle(cin, cout, shape, tc_forced):
     assert tc_forced() == n0 + 1, "layer did not take the tensor-core path"
     assert got.shape == want.shape
     assert rel(got, want) < 2e-5
+
+
+# ---- pointwise streaming kernel (conv_pw.cu), forced on ----
+@pytest.fixture
+def pw_forced(monkeypatch):
+    monkeypatch.setenv("ESM_TC_FORCE", "3")
+    from esmstereo_b200 import _lib
+    return _lib.lib().esm_pw_conv_launches
+
+
+@pytest.mark.parametrize("case", TC_K1_CASES + [("pw_12_20", 2, 12, 20, (9, 21), 2), ("pw_160_32", 2, 160, 32, (6, 20), 1),
+                                                  ("pw3d_80_40", 3, 80, 40, (3, 5, 9), 1)], ids=lambda c: c[0])
+def test_conv_pointwise_streaming(case, pw_forced):
+    name, nd, cin, cout, sp, B = case
+    ops = _ops()
+    p = make_layer(cin, cout, 1, nd, seed=len(name))
+    x = rnd(B, cin, *sp, seed=3)
+    want = ref_conv(x, p, 1, 0, False, "gelu", nd)
+    n0 = pw_forced()
+    got = ops.conv(x.cuda(), gpu_pack(p, 1, 0, False), "gelu")
+    assert pw_forced() == n0 + 1, "layer did not take the pointwise kernel"
+    assert rel(got, want) < 2e-5, name
+
+
+def test_conv_pointwise_streaming_fusions(pw_forced):
+    ops = _ops()
+    # three concatenated sources (up_refinement.agg_0.0), residual, second activation, scale
+    srcs = [rnd(2, 32, 6, 20, seed=7), rnd(2, 32, 6, 20, seed=8), rnd(2, 96, 6, 20, seed=9)]
+    p = make_layer(160, 32, 1, 2, seed=6)
+    res = rnd(2, 32, 6, 20, seed=10)
+    want = torch.sigmoid(ref_conv(torch.cat(srcs, 1), p, 1, 0, False, "gelu", 2) + res) * 2.0
+    n0 = pw_forced()
+    got = ops.conv([s.cuda() for s in srcs], gpu_pack(p, 1, 0, False), "gelu", residual=res.cuda(), act2="sigmoid", out_scale=2.0)
+    assert pw_forced() == n0 + 1
+    assert rel(got, want) < 2e-5
+    # cropped 3D view + skip (aggregation.agg_0.0), out_mul broadcast over D
+    a_full, b = rnd(1, 40, 4, 6, 10, seed=1), rnd(1, 40, 3, 5, 9, seed=2)
+    p = make_layer(80, 40, 1, 3, seed=5)
+    att = rnd(1, 40, 5, 9, seed=3)
+    want = ref_conv(torch.cat((a_full[:, :, :3, :5, :9], b), 1), p, 1, 0, False, "gelu", 3) * att.unsqueeze(2)
+    got = ops.conv([a_full.cuda()[:, :, :3, :5, :9], b.cuda()], gpu_pack(p, 1, 0, False), "gelu", out_mul=att.cuda())
+    assert pw_forced() == n0 + 2
+    assert rel(got, want) < 2e-5
+    # k1 with padding 1 (last layer of the disparity MLP, ESMStereo.py:253): the border is act(shift)
+    x = rnd(1, 32, 10, 38, seed=4)
+    p = make_layer(32, 32, 1, 2, seed=8)
+    want = ref_conv(x, p, 1, 1, False, "gelu", 2)
+    got = ops.conv(x.cuda(), gpu_pack(p, 1, 1, False), "gelu")
+    assert pw_forced() == n0 + 3
+    assert got.shape == want.shape and rel(got, want) < 2e-5
+    # UpShuffle: 1x1 -> PixelShuffle(2) -> SiLU
+    p = make_layer(16, 64, 1, 2, bn=False, bias=True, seed=11)
+    x = rnd(2, 16, 33, 70, seed=4)
+    want = F.silu(F.pixel_shuffle(ref_conv(x, p, 1, 0, False, None, 2), 2))
+    got = ops.conv(x.cuda(), gpu_pack(p, 1, 0, False), None, pixel_shuffle=2, act2="silu")
+    assert pw_forced() == n0 + 4
+    assert got.shape == want.shape and rel(got, want) < 2e-5
