@@ -8,6 +8,10 @@
 // weights as broadcast 16-byte shared-memory reads (one LDS.128 per 4 FMAs), and stores each channel coalesced --
 // PixelShuffle(2) pairs as 8-byte stores.  Plain grid (one small CTA per 128 pixels x channel tile): occupancy, not a
 // software pipeline, hides the latency.
+//
+// The same kernel, with a tap loop, runs the 2D layers with 1 or 3 INPUT channels -- the image stems (3 -> 32 k3 s2 at
+// full resolution, ESMStereo.py:528-533) and the first layers on the disparity map (1 -> 32 k5 / k3 s2, :191,:245) --
+// which the channel-chunked engines pad to 8 input channels: 27 / 25 / 9 loads and 32 accumulators per pixel.
 #include "conv_tc.cuh"
 #include "tc_common.cuh"
 
@@ -37,7 +41,8 @@ struct PwK {
   int Din, Hin, Win;      // input extent
   int OD, OH, OW;         // output extent (= input + 2 * pad in h, w)
   int ph, pw;
-  const float* weight;    // fp32 pack [CinPad][CoutPad]
+  int KH, KW, S;          // taps and stride (1 x 1, stride 1 for the pointwise layers)
+  const float* weight;    // fp32 pack [tap][CinPad][CoutPad]
   const float* scale;
   const float* shift;
   int act, act2, ps;
@@ -56,12 +61,14 @@ constexpr int PW_THREADS = 128;
 // CO output channels per thread (one channel tile per blockIdx.y)
 template <int CO>
 __global__ void __launch_bounds__(PW_THREADS) pw_conv_kernel(const __grid_constant__ PwK p) {
-  extern __shared__ __align__(16) float s_w[];  // [Cin][CO]: this tile's weights
+  extern __shared__ __align__(16) float s_w[];  // [tap][Cin][CO]: this tile's weights
   const int co0 = blockIdx.y * CO;
   const int b = blockIdx.z;
-  for (int i = threadIdx.x; i < p.Cin * CO; i += PW_THREADS) {
-    const int ci = i / CO, c = i - ci * CO;
-    s_w[i] = (co0 + c < p.CoutPad) ? __ldg(p.weight + (long long)ci * p.CoutPad + co0 + c) : 0.f;
+  const int taps = p.KH * p.KW;
+  for (int i = threadIdx.x; i < taps * p.Cin * CO; i += PW_THREADS) {
+    const int r = i / CO, c = i - r * CO;
+    const int tap = r / p.Cin, ci = r - tap * p.Cin;
+    s_w[i] = (co0 + c < p.CoutPad) ? __ldg(p.weight + ((long long)tap * p.CinPad + ci) * p.CoutPad + co0 + c) : 0.f;
   }
   __syncthreads();
   const long long pix = (long long)blockIdx.x * PW_THREADS + threadIdx.x;
@@ -69,11 +76,36 @@ __global__ void __launch_bounds__(PW_THREADS) pw_conv_kernel(const __grid_consta
   const int ox = (int)(pix % p.OW);
   const long long t = pix / p.OW;
   const int oy = (int)(t % p.OH), oz = (int)(t / p.OH);
-  const int iy = oy - p.ph, ix = ox - p.pw;
-  const bool inside = (unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win;  // k1 with padding: the border sees zeros
   float acc[CO];
 #pragma unroll
   for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+  if (taps > 1) {
+    // few input channels, many taps: one source, every (tap, channel) is one load and CO FMAs
+    const esm_src_t& sr = p.src[0];
+    const float* ib = sr.ptr + (long long)b * sr.sB;
+    const float* wrow = s_w;
+    for (int kh = 0; kh < p.KH; ++kh) {
+      const int iy = oy * p.S - p.ph + kh;
+      for (int kw = 0; kw < p.KW; ++kw) {
+        const int ix = ox * p.S - p.pw + kw;
+        const bool in = (unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win;
+        for (int ci = 0; ci < p.Cin; ++ci, wrow += CO) {
+          const float x = in ? __ldg(ib + (long long)ci * sr.sC + (long long)iy * sr.sH + ix) : 0.f;
+          const float4* w4 = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+          for (int j = 0; j < CO / 4; ++j) {
+            const float4 w = w4[j];
+            acc[4 * j + 0] = fmaf(x, w.x, acc[4 * j + 0]);
+            acc[4 * j + 1] = fmaf(x, w.y, acc[4 * j + 1]);
+            acc[4 * j + 2] = fmaf(x, w.z, acc[4 * j + 2]);
+            acc[4 * j + 3] = fmaf(x, w.w, acc[4 * j + 3]);
+          }
+        }
+      }
+    }
+  }
+  const int iy = oy - p.ph, ix = ox - p.pw;
+  const bool inside = taps == 1 && (unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win;  // k1 with padding: the border sees zeros
   if (inside) {
     int ci0 = 0;
     for (int s = 0; s < p.nsrc; ++s) {
@@ -155,8 +187,12 @@ static long long pw_launches = 0;
 
 bool pw_conv_plan(const esm_conv_t* d, PwPlan* plan) {
   if (d->src_mode != ESM_SRC_TENSORS || d->transposed || d->in_mul) return false;
-  if (!(d->kd == 1 && d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pd == 0)) return false;
-  if (d->Cin < 4 || d->Cout < 4) return false;
+  const bool k1 = d->kd == 1 && d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pd == 0;
+  // 2D layers on 1 or 3 input channels (image stems, first layers on the disparity map): direct tap loop
+  const bool thin = d->kd == 1 && d->pd == 0 && d->Dout == 1 && d->Din == 1 && d->Cin <= 4 && d->nsrc == 1 && d->kh == d->kw && d->kh >= 3 &&
+                    (d->stride == 1 || d->stride == 2) && !d->pixel_shuffle;
+  if (!k1 && !thin) return false;
+  if ((k1 && d->Cin < 4) || d->Cout < 4) return false;
   if (d->pixel_shuffle && !(d->pixel_shuffle == 2 && d->Cout % 4 == 0 && !d->out_mul && !d->residual && (d->oH % 2) == 0 &&
                             (reinterpret_cast<uintptr_t>(d->out) & 7) == 0 && d->Dout == 1))
     return false;
@@ -167,7 +203,7 @@ bool pw_conv_plan(const esm_conv_t* d, PwPlan* plan) {
   plan->CO = cop8 <= 8 ? 8 : cop8 <= 16 ? 16 : cop8 <= 24 ? 24 : 32;
   plan->cotiles = ceil_div(d->Cout, plan->CO);
   if (plan->cotiles > 8) return false;
-  plan->smem = (size_t)d->Cin * plan->CO * sizeof(float);
+  plan->smem = (size_t)d->kh * d->kw * d->Cin * plan->CO * sizeof(float);
   return plan->smem <= 96 * 1024;
 }
 
@@ -178,9 +214,12 @@ int pw_conv_launch(const esm_conv_t* d, const PwPlan& plan, cudaStream_t st) {
   k.nsrc = d->nsrc;
   k.B = d->B;
   k.Cin = d->Cin;
-  const TcgPack tp = tcg_pack_geom(d->Cout, d->Cin, 1, 1, 1, 0);
-  k.CinPad = round_up(d->Cin, 8);
-  k.CoutPad = (int)(tp.offset / k.CinPad);  // the fp32 pack is [CinPad][CoutPad] for a pointwise layer
+  const TcgPack tp = tcg_pack_geom(d->Cout, d->Cin, 1, d->kh, d->kw, 0);
+  k.CinPad = (d->Cin == 1 && d->Cout > 4) ? 1 : round_up(d->Cin, 8);  // pad_cin (conv.cu): single-channel inputs are not padded
+  k.CoutPad = (int)(tp.offset / ((long long)k.CinPad * d->kh * d->kw));  // the fp32 pack is [tap][CinPad][CoutPad]
+  k.KH = d->kh;
+  k.KW = d->kw;
+  k.S = d->stride;
   k.Cout = d->Cout;
   k.Din = d->Din;
   k.Hin = d->Hin;

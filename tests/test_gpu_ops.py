@@ -578,3 +578,23 @@ def test_conv_pointwise_streaming_fusions(pw_forced):
     got = ops.conv(x.cuda(), gpu_pack(p, 1, 0, False), None, pixel_shuffle=2, act2="silu")
     assert pw_forced() == n0 + 4
     assert got.shape == want.shape and rel(got, want) < 2e-5
+
+
+@pytest.mark.parametrize("case", [
+    # name, cin, cout, k, stride, pad, in_shape, batch
+    ("thin_stem_3_32_s2", 3, 32, 3, 2, 1, (25, 63), 2),
+    ("thin_dm0_1_32_k5p1", 1, 32, 5, 1, 1, (12, 40), 1),
+    ("thin_ref_1_32_s2", 1, 32, 3, 2, 1, (24, 81), 1),
+    ("thin_1_16_k3", 1, 16, 3, 1, 1, (9, 21), 2),
+], ids=lambda c: c[0])
+def test_conv_thin_input_streaming(case, pw_forced):
+    """2D layers on 1 / 3 input channels (image stems, first layers on the disparity map) on the streaming kernel."""
+    name, cin, cout, k, stride, pad, sp, B = case
+    ops = _ops()
+    p = make_layer(cin, cout, k, 2, seed=len(name))
+    x = rnd(B, cin, *sp, seed=3)
+    want = ref_conv(x, p, stride, pad, False, "gelu", 2)
+    n0 = pw_forced()
+    got = ops.conv(x.cuda(), gpu_pack(p, stride, pad, False), "gelu")
+    assert pw_forced() == n0 + 1, "layer did not take the streaming kernel"
+    assert got.shape == want.shape and rel(got, want) < 2e-5, name
