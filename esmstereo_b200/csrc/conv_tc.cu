@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         if (base + u * TC_THREADS < total) {
           const float hi = tc_rna(w[u]);
           *reinterpret_cast<float*>(s_w + off[u]) = hi;
-          *reinterpret_cast<float*>(s_w + off[u] + WSLAB) = tc_rna(w[u] - hi);
+          *reinterpret_cast<float*>(s_w + off[u] + WSLAB) = tc_lo(w[u], hi);
         }
       }
     }
@@ -266,10 +266,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         hi.w = tc_rna(v[j][3]);
         *reinterpret_cast<float4*>(sb + j * ROW_BYTES) = hi;
         if (p.npass == 3) {
-          lo.x = tc_rna(v[j][0] - hi.x);
-          lo.y = tc_rna(v[j][1] - hi.y);
-          lo.z = tc_rna(v[j][2] - hi.z);
-          lo.w = tc_rna(v[j][3] - hi.w);
+          lo.x = tc_lo(v[j][0], hi.x);
+          lo.y = tc_lo(v[j][1], hi.y);
+          lo.z = tc_lo(v[j][2], hi.z);
+          lo.w = tc_lo(v[j][3], hi.w);
           *reinterpret_cast<float4*>(sb + j * ROW_BYTES + 4096) = lo;
         }
       }

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
         if (g < nv) {
           const float h0 = tc_rna(v[g][0]), h1 = tc_rna(v[g][1]), h2 = tc_rna(v[g][2]), h3 = tc_rna(v[g][3]);
           tc_st4(ta + g * 16, h0, h1, h2, h3);
-          if (p.npass == 3) tc_st4(ta + g * 16 + 8, tc_rna(v[g][0] - h0), tc_rna(v[g][1] - h1), tc_rna(v[g][2] - h2), tc_rna(v[g][3] - h3));
+          if (p.npass == 3) tc_st4(ta + g * 16 + 8, tc_lo(v[g][0], h0), tc_lo(v[g][1], h1), tc_lo(v[g][2], h2), tc_lo(v[g][3], h3));
         }
       }
       tc_st_wait();

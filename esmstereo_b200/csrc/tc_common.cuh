@@ -116,14 +116,13 @@ __device__ __forceinline__ uint32_t tc_elect() {
   return leader;
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// Round to the nearest TF32 (low 13 mantissa bits zero).  `.rn` (ties to even) is one native instruction on
-// sm_100a (F2FP.TF32.F32); `.rna` is emulated with four (FSETP/IADD/SEL/LOP3) -- and the producers convert
-// 40 values per stage.  The split x = hi + lo is exact for either rounding.
-__device__ __forceinline__ float tc_rna(float x) {
-  uint32_t u;
-  asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
+// Split helpers.  hi = x rounded to the nearest TF32 (ties away, low 13 mantissa bits zero) with two full-rate integer
+// instructions: `cvt.rna.tf32.f32` is emulated with four on sm_100a, and the native `cvt.rn.tf32.f32` (F2FP.TF32) runs on
+// a narrow conversion pipe -- ncu showed math-pipe throttling in the producers, which convert 72 values per stage.
+// lo = x - hi needs no rounding of its own: the tensor core truncates its operands to TF32 (scratch/umma_test.cu), and
+// truncating lo costs 2^-21 |x| at most, unbiased (lo has either sign).
+__device__ __forceinline__ float tc_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ float tc_lo(float x, float hi) { return x - hi; }
 
 // GELU for the epilogue warps, which bound most of these kernels: erff() costs ~35 instructions per value on a
 // divergent warp (two branches), this one 16, branch-free.  erfc(t) = 2^p(t) with p a degree-8 fit of
