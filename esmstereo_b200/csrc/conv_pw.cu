@@ -61,21 +61,33 @@ constexpr int PW_THREADS = 128;
 // CO output channels per thread (one channel tile per blockIdx.y)
 template <int CO>
 __global__ void __launch_bounds__(PW_THREADS) pw_conv_kernel(const __grid_constant__ PwK p) {
-  extern __shared__ __align__(16) float s_w[];  // [tap][Cin][CO]: this tile's weights
+  extern __shared__ __align__(16) float s_w[];  // [tap][Cin][CO]: this tile's weights, then [2][CO] scale / shift
   const int co0 = blockIdx.y * CO;
   const int b = blockIdx.z;
   const int taps = p.KH * p.KW;
-  for (int i = threadIdx.x; i < taps * p.Cin * CO; i += PW_THREADS) {
-    const int r = i / CO, c = i - r * CO;
-    const int tap = r / p.Cin, ci = r - tap * p.Cin;
+  const int nw = taps * p.Cin * CO;
+  for (int i = threadIdx.x; i < nw; i += PW_THREADS) {
+    const int r = i / CO, c = i - r * CO;  // CO is a compile-time constant
+    int tap = 0, ci = r;
+    if (taps > 1) {
+      tap = r / p.Cin;
+      ci = r - tap * p.Cin;
+    }
     s_w[i] = (co0 + c < p.CoutPad) ? __ldg(p.weight + ((long long)tap * p.CinPad + ci) * p.CoutPad + co0 + c) : 0.f;
   }
+  float* s_aff = s_w + nw;
+  if (threadIdx.x < 2 * CO) {
+    const int c = threadIdx.x % CO, co = co0 + c;
+    const float* src = threadIdx.x < CO ? p.scale : p.shift;
+    s_aff[threadIdx.x] = (src && co < p.Cout) ? __ldg(src + co) : (threadIdx.x < CO ? 1.f : 0.f);
+  }
   __syncthreads();
-  const long long pix = (long long)blockIdx.x * PW_THREADS + threadIdx.x;
-  if (pix >= p.pixels) return;
-  const int ox = (int)(pix % p.OW);
-  const long long t = pix / p.OW;
-  const int oy = (int)(t % p.OH), oz = (int)(t / p.OH);
+  // 32-bit pixel decode (the host checks OD * OH * OW < 2^31)
+  const unsigned pix = blockIdx.x * PW_THREADS + threadIdx.x;
+  if (pix >= (unsigned)p.pixels) return;
+  const int ox = (int)(pix % (unsigned)p.OW);
+  const unsigned t = pix / (unsigned)p.OW;
+  const int oy = (int)(t % (unsigned)p.OH), oz = (int)(t / (unsigned)p.OH);
   float acc[CO];
 #pragma unroll
   for (int c = 0; c < CO; ++c) acc[c] = 0.f;
@@ -147,26 +159,26 @@ __global__ void __launch_bounds__(PW_THREADS) pw_conv_kernel(const __grid_consta
   }
   // epilogue: affine -> act -> (x out_mul) -> (+ residual) -> act2 -> scale -> store
   const bool post = p.out_mul || p.residual;
+  const float oscale = p.out_scale;
+  const long long obase = (long long)b * p.oB + (long long)oz * p.oD + (long long)oy * p.oH + ox;
+  float* ops = p.out + ((long long)b * p.oB + (long long)(co0 >> 2) * p.oC + (long long)(2 * oy) * p.oH + 2 * ox);  // PixelShuffle(2) target
+  float* op = p.out + obase + (long long)co0 * p.oC;
 #pragma unroll
   for (int c4 = 0; c4 < CO; c4 += 4) {
     const int co = co0 + c4;
     if (co >= p.Cout) break;
     float rv[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int cj = min(co + j, p.Cout - 1);
-      rv[j] = fmaf(acc[c4 + j], p.scale ? __ldg(p.scale + cj) : 1.f, p.shift ? __ldg(p.shift + cj) : 0.f);
-    }
+    for (int j = 0; j < 4; ++j) rv[j] = fmaf(acc[c4 + j], s_aff[c4 + j], s_aff[CO + c4 + j]);
     pw_act4(rv, p.act);
     if (p.ps == 2) {
       // channel co -> (co / 4, row 2y + (co / 2) % 2, column 2x + co % 2): the 4 channels of a unit are one 2 x 2 block
       pw_act4(rv, p.act2);
-      float* o = p.out + ((long long)b * p.oB + (long long)(co >> 2) * p.oC + (long long)(2 * oy) * p.oH + 2 * ox);
-      *reinterpret_cast<float2*>(o) = make_float2(rv[0] * p.out_scale, rv[1] * p.out_scale);
-      *reinterpret_cast<float2*>(o + p.oH) = make_float2(rv[2] * p.out_scale, rv[3] * p.out_scale);
+      *reinterpret_cast<float2*>(ops) = make_float2(rv[0] * oscale, rv[1] * oscale);
+      *reinterpret_cast<float2*>(ops + p.oH) = make_float2(rv[2] * oscale, rv[3] * oscale);
+      ops += p.oC;
       continue;
     }
-    const long long obase = (long long)b * p.oB + (long long)oz * p.oD + (long long)oy * p.oH + ox;
     if (post) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -179,7 +191,8 @@ __global__ void __launch_bounds__(PW_THREADS) pw_conv_kernel(const __grid_consta
     pw_act4(rv, p.act2);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (co + j < p.Cout) p.out[obase + (long long)(co + j) * p.oC] = rv[j] * p.out_scale;
+      if (co + j < p.Cout) op[(long long)j * p.oC] = rv[j] * oscale;
+    op += 4 * p.oC;
   }
 }
 
@@ -203,7 +216,8 @@ bool pw_conv_plan(const esm_conv_t* d, PwPlan* plan) {
   plan->CO = cop8 <= 8 ? 8 : cop8 <= 16 ? 16 : cop8 <= 24 ? 24 : 32;
   plan->cotiles = ceil_div(d->Cout, plan->CO);
   if (plan->cotiles > 8) return false;
-  plan->smem = (size_t)d->kh * d->kw * d->Cin * plan->CO * sizeof(float);
+  plan->smem = ((size_t)d->kh * d->kw * d->Cin + 2) * plan->CO * sizeof(float);
+  if ((long long)d->Dout * d->Hout * d->Wout >= (1ll << 31)) return false;
   return plan->smem <= 96 * 1024;
 }
 
