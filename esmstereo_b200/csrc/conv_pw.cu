@@ -88,9 +88,10 @@ __global__ void __launch_bounds__(PW_THREADS) pw_conv_kernel(const __grid_consta
   const int ox = (int)(pix % (unsigned)p.OW);
   const unsigned t = pix / (unsigned)p.OW;
   const int oy = (int)(t % (unsigned)p.OH), oz = (int)(t / (unsigned)p.OH);
-  float acc[CO];
+  // accumulators as packed pairs: one FFMA2 (fma.rn.f32x2) per two channels -- the kernel is issue-bound on its FMAs
+  float2 acc2[CO / 2];
 #pragma unroll
-  for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+  for (int c = 0; c < CO / 2; ++c) acc2[c] = make_float2(0.f, 0.f);
   if (taps > 1) {
     // few input channels, many taps: one source, every (tap, channel) is one load and CO FMAs
     const esm_src_t& sr = p.src[0];
@@ -107,10 +108,8 @@ __global__ void __launch_bounds__(PW_THREADS) pw_conv_kernel(const __grid_consta
 #pragma unroll
           for (int j = 0; j < CO / 4; ++j) {
             const float4 w = w4[j];
-            acc[4 * j + 0] = fmaf(x, w.x, acc[4 * j + 0]);
-            acc[4 * j + 1] = fmaf(x, w.y, acc[4 * j + 1]);
-            acc[4 * j + 2] = fmaf(x, w.z, acc[4 * j + 2]);
-            acc[4 * j + 3] = fmaf(x, w.w, acc[4 * j + 3]);
+            ffma2(acc2[2 * j], make_float2(x, x), make_float2(w.x, w.y));
+            ffma2(acc2[2 * j + 1], make_float2(x, x), make_float2(w.z, w.w));
           }
         }
       }
@@ -135,10 +134,8 @@ __global__ void __launch_bounds__(PW_THREADS) pw_conv_kernel(const __grid_consta
 #pragma unroll
           for (int j = 0; j < CO / 4; ++j) {
             const float4 w = w4[j];
-            acc[4 * j + 0] = fmaf(x[u], w.x, acc[4 * j + 0]);
-            acc[4 * j + 1] = fmaf(x[u], w.y, acc[4 * j + 1]);
-            acc[4 * j + 2] = fmaf(x[u], w.z, acc[4 * j + 2]);
-            acc[4 * j + 3] = fmaf(x[u], w.w, acc[4 * j + 3]);
+            ffma2(acc2[2 * j], make_float2(x[u], x[u]), make_float2(w.x, w.y));
+            ffma2(acc2[2 * j + 1], make_float2(x[u], x[u]), make_float2(w.z, w.w));
           }
         }
       }
@@ -148,10 +145,8 @@ __global__ void __launch_bounds__(PW_THREADS) pw_conv_kernel(const __grid_consta
 #pragma unroll
         for (int j = 0; j < CO / 4; ++j) {
           const float4 w = w4[j];
-          acc[4 * j + 0] = fmaf(x, w.x, acc[4 * j + 0]);
-          acc[4 * j + 1] = fmaf(x, w.y, acc[4 * j + 1]);
-          acc[4 * j + 2] = fmaf(x, w.z, acc[4 * j + 2]);
-          acc[4 * j + 3] = fmaf(x, w.w, acc[4 * j + 3]);
+          ffma2(acc2[2 * j], make_float2(x, x), make_float2(w.x, w.y));
+          ffma2(acc2[2 * j + 1], make_float2(x, x), make_float2(w.z, w.w));
         }
       }
       ci0 += sr.C;
@@ -169,7 +164,10 @@ __global__ void __launch_bounds__(PW_THREADS) pw_conv_kernel(const __grid_consta
     if (co >= p.Cout) break;
     float rv[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) rv[j] = fmaf(acc[c4 + j], s_aff[c4 + j], s_aff[CO + c4 + j]);
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = acc2[(c4 + j) / 2];
+      rv[j] = fmaf((j & 1) ? a.y : a.x, s_aff[c4 + j], s_aff[CO + c4 + j]);
+    }
     pw_act4(rv, p.act);
     if (p.ps == 2) {
       // channel co -> (co / 4, row 2y + (co / 2) % 2, column 2x + co % 2): the 4 channels of a unit are one 2 x 2 block
