@@ -41,6 +41,23 @@ class EsmMixerMlp(C.Structure):
     _fields_ = [("ln_w", vp), ("fc0_w", vp), ("fc0_b", vp), ("fc2_w", vp), ("fc2_b", vp), ("hidden", C.c_int)]
 
 
+class EsmPf(C.Structure):
+    _fields_ = [("data", vp), ("B", C.c_int), ("C", C.c_int), ("Dp", C.c_int), ("Hp", C.c_int), ("P", C.c_int),
+                ("d0", C.c_int), ("d1", C.c_int), ("y0", C.c_int), ("y1", C.c_int), ("x0", C.c_int), ("x1", C.c_int)]
+
+
+class EsmConvPf(C.Structure):
+    _fields_ = [
+        ("src", EsmPf * 3), ("nsrc", C.c_int),
+        ("Cout", C.c_int), ("kd", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("stride", C.c_int), ("transposed", C.c_int),
+        ("d0", C.c_int), ("d1", C.c_int), ("y0", C.c_int), ("y1", C.c_int), ("x0", C.c_int), ("x1", C.c_int),
+        ("oD", C.c_int), ("oH", C.c_int), ("oW", C.c_int),
+        ("weight", vp), ("scale", vp), ("shift", vp), ("act", C.c_int), ("act2", C.c_int), ("out_scale", C.c_float),
+        ("pixel_shuffle", C.c_int), ("out_pf", EsmPf), ("res_pf", vp), ("out", vp),
+        ("oB", C.c_longlong), ("oC", C.c_longlong), ("oDs", C.c_longlong), ("oHs", C.c_longlong), ("residual", vp),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/esm_b200.h declares
 SIGNATURES = {
     "esm_last_error": (C.c_char_p, []),
@@ -69,6 +86,14 @@ SIGNATURES = {
     "esm_laf_sample_embed_f32": (C.c_int, [vp] * 8 + [C.c_int] * 4 + [vp]),
     "esm_conf_convex_up4_f32": (C.c_int, [vp] * 5 + [C.c_int] * 4 + [vp]),
     "esm_fill_f32": (C.c_int, [vp, C.c_longlong, C.c_float, vp]),
+    "esm_pf_elems": (C.c_longlong, [C.c_int] * 5),
+    "esm_pf_guard_elems": (C.c_longlong, [C.c_int] * 3),
+    "esm_pf_from_nchw_f32": (C.c_int, [vp] + [C.c_longlong] * 4 + [C.POINTER(EsmPf), vp]),
+    "esm_pf_to_nchw_f32": (C.c_int, [C.POINTER(EsmPf), vp] + [C.c_longlong] * 4 + [vp]),
+    "esm_packed_weight_pf_elems": (C.c_longlong, [C.c_int, C.c_int, i32p] + [C.c_int] * 4),
+    "esm_pack_conv_weight_pf_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, i32p] + [C.c_int] * 4 + [vp]),
+    "esm_conv_pf_f32": (C.c_int, [C.POINTER(EsmConvPf), vp]),
+    "esm_tcf_conv_launches": (C.c_longlong, []),
 }
 
 _lib = None

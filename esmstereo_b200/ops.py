@@ -465,3 +465,196 @@ def fill_(t: torch.Tensor, value: float) -> torch.Tensor:
     with _Prof("fill"):
         check(lib().esm_fill_f32(_dev(t, "t").data_ptr(), t.numel(), float(value), _stream()), "fill")
     return t
+
+
+# ---------------------------------------------------------------------------------------------
+# PF activations + the TMA-fed tcgen05 engine over them (conv_tcf.cu; include/esm_b200.h "PF")
+# ---------------------------------------------------------------------------------------------
+class PF:
+    """A padded-flat, pre-split activation: [B][hi|lo][C/4][Dp*Hp*P][4] fp32 with the conv's zero border stored.
+    `box` = (d0, d1, y0, y1, x0, x1) is where the logical [B, C, D, H, W] tensor sits in the padded lattice."""
+
+    __slots__ = ("buf", "guard", "B", "C", "Dp", "Hp", "P", "box", "is3d")
+
+    def __init__(self, B: int, C_: int, D: int, H: int, W: int, is3d: bool, device, zero: bool = False, geom=None, box=None):
+        self.B, self.C, self.is3d = int(B), int(C_), bool(is3d)
+        if geom is None:
+            geom = ((D + 2) if is3d else 1, H + 2, W + 2)
+            box = (1 if is3d else 0, (D + 1) if is3d else 1, 1, H + 1, 1, W + 1)
+        self.Dp, self.Hp, self.P = (int(v) for v in geom)
+        self.box = tuple(int(v) for v in box)
+        L = lib()
+        self.guard = int(L.esm_pf_guard_elems(self.Dp, self.Hp, self.P))
+        n = int(L.esm_pf_elems(self.B, self.C, self.Dp, self.Hp, self.P))
+        self.buf = (torch.zeros if zero else torch.empty)(n + 2 * self.guard, device=device, dtype=torch.float32)
+
+    @property
+    def shape(self):
+        d0, d1, y0, y1, x0, x1 = self.box
+        return (self.B, self.C, d1 - d0, y1 - y0, x1 - x0) if self.is3d else (self.B, self.C, y1 - y0, x1 - x0)
+
+    @property
+    def device(self):
+        return self.buf.device
+
+    def struct(self) -> "_lib.EsmPf":
+        s = _lib.EsmPf()
+        s.data = self.buf.data_ptr() + 4 * self.guard
+        s.B, s.C, s.Dp, s.Hp, s.P = self.B, self.C, self.Dp, self.Hp, self.P
+        s.d0, s.d1, s.y0, s.y1, s.x0, s.x1 = self.box
+        return s
+
+    def like(self, C_: int, zero: bool = False, box=None) -> "PF":
+        return PF(self.B, C_, 0, 0, 0, self.is3d, self.buf.device, zero=zero, geom=(self.Dp, self.Hp, self.P), box=box or self.box)
+
+
+def _nchw_strides(t: torch.Tensor):
+    st = t.stride()
+    return (st[0], st[1], st[2], st[3]) if t.dim() == 5 else (st[0], st[1], 0, st[2])
+
+
+def to_pf(x: torch.Tensor, like: Optional[PF] = None) -> PF:
+    """NCHW / NCDHW fp32 -> PF (one bandwidth-bound pass; zero border written too)."""
+    x = _dev(x, "x")
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    is3d = x.dim() == 5
+    if like is not None:
+        pf = like.like(x.shape[1])
+        assert tuple(pf.shape[2:]) == tuple(x.shape[2:])
+    else:
+        D = x.shape[2] if is3d else 1
+        pf = PF(x.shape[0], x.shape[1], D, x.shape[-2], x.shape[-1], is3d, x.device)
+    s = pf.struct()
+    with _Prof("pf_from_nchw C%d %s" % (x.shape[1], "x".join(str(v) for v in x.shape[2:]))):
+        check(lib().esm_pf_from_nchw_f32(x.data_ptr(), *_nchw_strides(x), C.byref(s), _stream()), "pf_from_nchw")
+    return pf
+
+
+def from_pf(pf: PF) -> torch.Tensor:
+    out = torch.empty(pf.shape, device=pf.device, dtype=torch.float32)
+    s = pf.struct()
+    with _Prof("pf_to_nchw C%d" % pf.C):
+        check(lib().esm_pf_to_nchw_f32(C.byref(s), out.data_ptr(), *_nchw_strides(out), _stream()), "pf_to_nchw")
+    return out
+
+
+class PackedConvPF:
+    __slots__ = ("weight", "scale", "shift", "Cout", "srcC", "k", "stride", "transposed", "ndim")
+
+    def __init__(self, **kw):
+        for k_, v in kw.items():
+            setattr(self, k_, v)
+
+
+def pack_conv_pf(weight: torch.Tensor, srcC: Sequence[int], stride=1, transposed: bool = False, bias: Optional[torch.Tensor] = None,
+                 bn=None) -> PackedConvPF:
+    """Weights of one layer for `conv_pf`: split TF32 hi / lo slabs in the order the engine streams them + folded affine.
+    srcC = channels of each concatenated source."""
+    w = _dev(weight.detach(), "weight").contiguous()
+    ndim = w.dim() - 2
+    Cin, Cout = (w.shape[0], w.shape[1]) if transposed else (w.shape[1], w.shape[0])
+    assert sum(srcC) == Cin, "pack_conv_pf: sources (%s) != Cin (%d)" % (srcC, Cin)
+    ks = tuple(w.shape[2:])
+    kd, kh, kw = ((1,) + ks) if ndim == 2 else ks
+    s = stride[0] if isinstance(stride, (tuple, list)) else int(stride)
+    L = lib()
+    arr = (C.c_int * len(srcC))(*[int(v) for v in srcC])
+    n = L.esm_packed_weight_pf_elems(Cout, len(srcC), arr, kd, kh, kw, int(transposed))
+    packed = torch.empty(n, device=w.device, dtype=torch.float32)
+    check(L.esm_pack_conv_weight_pf_f32(w.data_ptr(), packed.data_ptr(), Cout, len(srcC), arr, kd, kh, kw, int(transposed), _stream()),
+          "pack_conv_weight_pf")
+    scale = torch.empty(Cout, device=w.device, dtype=torch.float32)
+    shift = torch.empty(Cout, device=w.device, dtype=torch.float32)
+    if bn is not None:
+        g, b_, m, v, eps = bn
+        g, b_, m, v = [_dev(t.detach(), "bn").contiguous() for t in (g, b_, m, v)]
+        args = (g.data_ptr(), b_.data_ptr(), m.data_ptr(), v.data_ptr())
+    else:
+        eps, args = 0.0, (None, None, None, None)
+    bias_t = _dev(bias.detach(), "bias").contiguous() if bias is not None else None
+    check(L.esm_fold_bn_f32(*args, _ptr(bias_t), float(eps), Cout, scale.data_ptr(), shift.data_ptr(), _stream()), "fold_bn")
+    return PackedConvPF(weight=packed, scale=scale, shift=shift, Cout=Cout, srcC=tuple(int(v) for v in srcC), k=(kd, kh, kw), stride=s,
+                        transposed=bool(transposed), ndim=ndim)
+
+
+def conv_pf(srcs: Sequence[PF], pc: PackedConvPF, act: Optional[str] = None, *, out: str = "pf", residual=None, act2: Optional[str] = None,
+            out_scale: float = 1.0, pixel_shuffle: int = 0, out_size: Optional[Sequence[int]] = None, box=None, out_pf: Optional[PF] = None):
+    """Fused conv over PF sources on the TMA-fed tcgen05 engine.  out: "pf" | "nchw" | "both".
+    residual: a PF (layout of the PF output) or an NCHW tensor (needs an NCHW output).  box: compute box override
+    (layers whose output region differs from the sources' valid box, e.g. the k1 p1 tail of the disparity MLPs)."""
+    if isinstance(srcs, PF):
+        srcs = [srcs]
+    assert tuple(s.C for s in srcs) == pc.srcC, "conv_pf: sources %s do not match the packed layer %s" % ([s.C for s in srcs], pc.srcC)
+    s0 = srcs[0]
+    d = _lib.EsmConvPf()
+    for i, s in enumerate(srcs):
+        d.src[i] = s.struct()
+    d.nsrc = len(srcs)
+    kd, kh, kw = pc.k
+    d.Cout, d.kd, d.kh, d.kw, d.stride, d.transposed = pc.Cout, kd, kh, kw, pc.stride, int(pc.transposed)
+    cb = tuple(box) if box is not None else s0.box
+    d.d0, d.d1, d.y0, d.y1, d.x0, d.x1 = cb
+    Dc, Hc, Wc = cb[1] - cb[0], cb[3] - cb[2], cb[5] - cb[4]
+    is3d = s0.is3d
+    if pc.transposed:
+        full = ((2 * Dc) if is3d else 1, 2 * Hc, 2 * Wc)
+        if out_size is not None:
+            o = tuple(int(v) for v in out_size)
+            full = ((1,) + o) if len(o) == 2 else o
+        oD, oH, oW = full
+    elif pc.stride == 2:
+        oD, oH, oW = ((Dc - 1) // 2 + 1) if is3d else 1, (Hc - 1) // 2 + 1, (Wc - 1) // 2 + 1
+    else:
+        oD, oH, oW = Dc, Hc, Wc
+    d.oD, d.oH, d.oW = oD, oH, oW
+    d.weight, d.scale, d.shift = pc.weight.data_ptr(), pc.scale.data_ptr(), pc.shift.data_ptr()
+    d.act, d.act2, d.out_scale, d.pixel_shuffle = ACT[act], ACT[act2], float(out_scale), int(pixel_shuffle)
+    same = (not pc.transposed) and pc.stride == 1
+    res_pf = None
+    opf = None
+    if out in ("pf", "both"):
+        if out_pf is not None:
+            opf = out_pf
+        elif same:
+            opf = s0.like(pc.Cout, box=cb)
+        else:
+            opf = PF(s0.B, pc.Cout, oD, oH, oW, is3d, s0.device, zero=True)
+        d.out_pf = opf.struct()
+        if isinstance(residual, PF):
+            assert (residual.Dp, residual.Hp, residual.P, residual.C) == (opf.Dp, opf.Hp, opf.P, opf.C)
+            d.res_pf = residual.buf.data_ptr() + 4 * residual.guard
+            res_pf = residual
+    onchw = None
+    r = int(pixel_shuffle)
+    if out in ("nchw", "both"):
+        if r:
+            onchw = torch.empty(s0.B, pc.Cout // (r * r), oH * r, oW * r, device=s0.device, dtype=torch.float32)
+            st = onchw.stride()
+            d.oB, d.oC, d.oDs, d.oHs = st[0], st[1], 0, st[2]
+        elif is3d:
+            onchw = _alloc_rows(s0.device, (s0.B, pc.Cout, oD, oH), oW)
+            d.oB, d.oC, d.oDs, d.oHs = onchw.stride()[:4]
+        else:
+            onchw = _alloc_rows(s0.device, (s0.B, pc.Cout, oH), oW)
+            st = onchw.stride()
+            d.oB, d.oC, d.oDs, d.oHs = st[0], st[1], 0, st[2]
+        d.out = onchw.data_ptr()
+        if isinstance(residual, torch.Tensor):
+            residual = _dev(residual, "residual")
+            assert residual.shape == onchw.shape
+            if residual.stride() != onchw.stride():
+                tmp = torch.empty_strided(onchw.size(), onchw.stride(), device=onchw.device, dtype=onchw.dtype)
+                tmp.copy_(residual)
+                residual = tmp
+            d.residual = residual.data_ptr()
+    assert residual is None or res_pf is not None or d.residual, "conv_pf: residual format does not match the output format"
+    label = "%s%dd_pf %d->%d k%d s%d geom %dx%dx%d" % ("deconv" if pc.transposed else "conv", 3 if is3d else 2, sum(pc.srcC), pc.Cout, kw,
+                                                       pc.stride, s0.Dp, s0.Hp, s0.P)
+    with _Prof(label):
+        check(lib().esm_conv_pf_f32(C.byref(d), _stream()), "conv_pf")
+    if out == "pf":
+        return opf
+    if out == "nchw":
+        return onchw
+    return opf, onchw

@@ -200,6 +200,66 @@ int esm_conf_convex_up4_f32(const float* feat, const float* conf, const float* w
 /* Fill `n` floats with `value`. */
 int esm_fill_f32(float* p, long long n, float value, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * "PF" activations (padded-flat, pre-split) and the TMA-fed tcgen05 convolution engine over them (conv_tcf.cu).
+ *
+ * A PF tensor stores a logical [B, C, D, H, W] fp32 activation as
+ *     [B][hi | lo][Cq = 2*ceil(C/8) channel quads][Dp * Hp * P positions][4 channels]
+ * with the convolution's zero border STORED (Hp >= H + 2, P >= W + 2, Dp >= D + 2 for 3D, Dp == 1 for 2D), the
+ * data occupying the "valid box" [d0,d1) x [y0,y1) x [x0,x1) of the padded lattice and zeros everywhere else, and
+ * every value pre-split for the fp32-grade TF32 scheme: hi = x rounded to TF32, lo = x - hi.  `data` points at
+ * (b=0, hi, quad 0, position 0); the allocation must extend esm_pf_guard_elems() floats on BOTH sides of the
+ * esm_pf_elems() floats of the tensor (the engine's windows overhang; what they read there only reaches border
+ * outputs, which are stored as zeros).  Intermediate format between BasicConv layers (submodule.py:12-38): it
+ * replaces the NCHW tensors the reference passes from conv to conv inside `aggregation`, `up_refinement`, the
+ * disparity MLPs / spx blocks of `upsample4/8/16` (ESMStereo.py:129-318) and the 2D feature side (:79-125).
+ */
+typedef struct {
+  float* data;
+  int B, C;
+  int Dp, Hp, P;
+  int d0, d1, y0, y1, x0, x1;
+} esm_pf_t;
+long long esm_pf_elems(int B, int C, int Dp, int Hp, int P);
+long long esm_pf_guard_elems(int Dp, int Hp, int P);
+/* NCHW (strides in elements, W stride 1; sD ignored for 2D) -> PF, zero border included; and back (hi + lo). */
+int esm_pf_from_nchw_f32(const float* x, long long sB, long long sC, long long sD, long long sH, const esm_pf_t* out, void* stream);
+int esm_pf_to_nchw_f32(const esm_pf_t* in, float* out, long long sB, long long sC, long long sD, long long sH, void* stream);
+
+/* Weights for esm_conv_pf_f32: torch layout in ([Cout,Cin,k..]; transposed [Cin,Cout,k..]), split into TF32 hi / lo
+ * UMMA slabs out.  srcC[nsrc] = channels of each concatenated source (each is padded to a multiple of 8 in PF). */
+long long esm_packed_weight_pf_elems(int Cout, int nsrc, const int* srcC, int kd, int kh, int kw, int transposed);
+int esm_pack_conv_weight_pf_f32(const float* w, float* packed, int Cout, int nsrc, const int* srcC, int kd, int kh, int kw,
+                                int transposed, void* stream);
+/*
+ * Fused convolution over PF sources: k1 / k3 stride 1 (pad k/2), k3 stride 2 (pad 1; computed at every position,
+ * stored at the even ones), ConvTranspose k4 s2 p1 (2^nd sub-pixel phases) -- 2D or 3D, up to 3 channel-concatenated
+ * sources of one geometry -- + per-channel affine + activation + residual + second activation, written as PF
+ * (same geometry: every position, zeros outside the compute box; other geometry: the mapped valid positions only,
+ * into a buffer whose other positions are already zero) and / or as strided NCHW (optionally PixelShuffle(2)).
+ * Same seams as esm_conv_f32; operands reach the tensor core by TMA bulk copies only.
+ */
+typedef struct {
+  esm_pf_t src[3];
+  int nsrc;
+  int Cout, kd, kh, kw, stride, transposed;
+  int d0, d1, y0, y1, x0, x1;  /* compute box in the sources' padded coordinates (normally their valid box) */
+  int oD, oH, oW;              /* logical output extent (crop-to-skip for transposed layers) */
+  const float* weight;         /* esm_pack_conv_weight_pf_f32 */
+  const float* scale;
+  const float* shift;
+  int act, act2;
+  float out_scale;
+  int pixel_shuffle;           /* 0 or 2 (NCHW output only) */
+  esm_pf_t out_pf;             /* data == NULL: no PF output */
+  const float* res_pf;         /* optional residual in the layout of out_pf */
+  float* out;                  /* optional NCHW output */
+  long long oB, oC, oDs, oHs;
+  const float* residual;       /* optional NCHW residual with the output's strides */
+} esm_conv_pf_t;
+int esm_conv_pf_f32(const esm_conv_pf_t* desc, void* stream);
+long long esm_tcf_conv_launches(void);
+
 #ifdef __cplusplus
 }
 #endif
