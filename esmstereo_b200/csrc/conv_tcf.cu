@@ -63,7 +63,7 @@ struct TcfK {
   // PF output (optional)
   float* opf;
   long long o_sB, o_sHL, o_sQ;
-  int oHp, oP, od0, oy0, ox0;
+  int oHp, oP, od0, oy0, ox0, oCq;
   int same_geom;        // output PF shares the compute geometry: every position is stored (zeros outside the valid box)
   // NCHW output (optional)
   float* out;
@@ -73,10 +73,11 @@ struct TcfK {
   int Cout, ps;
 };
 
-constexpr int TF_NEW = 8;                   // epilogue warps: two per TMEM lane quadrant
+constexpr int TF_NEW = 16;                  // epilogue warps: four per TMEM lane quadrant
 constexpr int TF_MMA_WARP = TF_NEW;         // MMA issuer
-constexpr int TF_CP_WARP = TF_NEW + 1;      // bulk-copy issuer
-constexpr int TF_THREADS = 32 * (TF_NEW + 2);
+constexpr int TF_CP_WARP = TF_NEW + 1;      // first bulk-copy issuer
+constexpr int TF_NCP = 2;                   // bulk-copy issuers: warp c takes the planes hl = c (hi / lo), warp 0 also the weights
+constexpr int TF_THREADS = 32 * (TF_NEW + 1 + TF_NCP);
 constexpr int TF_ACC_COLS = 256;            // TMEM columns per accumulator buffer (two buffers)
 
 struct TfItem {
@@ -107,9 +108,20 @@ __device__ __forceinline__ TfItem tf_decode(const TcfK& p, int item) {
   return t;
 }
 
+// n / d for 0 <= n < 2^22 with inv = 1.0f / d (exact after one fix-up in each direction)
+__device__ __forceinline__ int tf_div(int n, int d, float inv) {
+  int q = (int)((float)n * inv);
+  if (q * d > n) --q;
+  if ((q + 1) * d <= n) ++q;
+  return q;
+}
+
 __global__ void __launch_bounds__(TF_THREADS, 1) tcf_conv_kernel(const __grid_constant__ TcfK p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef TC_PROFILE
+  const long long tc_t0 = clock64();
+#endif
   const int NT = p.NT, NS = p.nstages, KK = p.K * p.K;
   const uint32_t A_PLANE = (uint32_t)p.rows_total * 16;
   const uint32_t A_BYTES = 4 * A_PLANE;
@@ -127,7 +139,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tcf_conv_kernel(const __grid_co
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
-      tc_mbar_init(&full[i], 1);
+      tc_mbar_init(&full[i], TF_NCP);
       tc_mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -150,10 +162,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tcf_conv_kernel(const __grid_co
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == TF_CP_WARP) {
-    // ============================ bulk-copy issuer ============================
+  if (warp >= TF_CP_WARP) {
+    // ============================ bulk-copy issuers ============================
+    // warp hl copies the (hi | lo) planes of every window: 2 NI copies per stage, one per lane; warp 0 also the weights
+    const int hl = warp - TF_CP_WARP;
     uint32_t st = 0, ph = 0;
-    const int ncopies = 4 * p.NI;
+    const int ncopies = 2 * p.NI;
+    const uint32_t my_bytes = 2 * A_PLANE + (hl == 0 ? B_BYTES : 0u);
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const TfItem ti = tf_decode(p, item);
       const int pw = ti.phase & 1, phh = (ti.phase >> 1) & 1, pd = (ti.phase >> 2) & 1;
@@ -170,16 +185,16 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tcf_conv_kernel(const __grid_co
         }
         tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
         uint8_t* sa = smem + (size_t)st * STAGE;
-        if (lane == 0) tc_mbar_expect_tx(&full[st], A_BYTES + B_BYTES);
+        if (lane == 0) tc_mbar_expect_tx(&full[st], my_bytes);
         __syncwarp();
         const TcfSrc& sv = s_k == 0 ? p.src[0] : (s_k == 1 ? p.src[1] : p.src[2]);
-        const float* sb = sv.base + (long long)ti.b * sv.sB + (long long)(cgl * 2) * sv.sQ + (wbase + (long long)kd * p.PH) * 4;
+        const float* sb = sv.base + (long long)ti.b * sv.sB + (long long)hl * sv.sHL + (long long)(cgl * 2) * sv.sQ + (wbase + (long long)kd * p.PH) * 4;
         for (int c = lane; c < ncopies; c += 32) {
-          const int i = c >> 2, pl = c & 3;  // window, plane = hl * 2 + K-half
-          const float* g = sb + (long long)(pl >> 1) * sv.sHL + (long long)(pl & 1) * sv.sQ + (long long)i * p.P * 4;
-          tc_bulk_g2s(sa + (size_t)pl * A_PLANE + (size_t)i * p.L * 16, g, (uint32_t)p.L * 16, &full[st]);
+          const int i = c >> 1, kh_ = c & 1;  // window, K-half
+          const float* g = sb + (long long)kh_ * sv.sQ + (long long)i * p.P * 4;
+          tc_bulk_g2s(sa + (size_t)(hl * 2 + kh_) * A_PLANE + (size_t)i * p.L * 16, g, (uint32_t)p.L * 16, &full[st]);
         }
-        if (lane == 31) tc_bulk_g2s(sa + A_BYTES, wsrc + (long long)s * (KK * NT * 16), B_BYTES, &full[st]);
+        if (hl == 0 && lane == 31) tc_bulk_g2s(sa + A_BYTES, wsrc + (long long)s * (KK * NT * 16), B_BYTES, &full[st]);
         __syncwarp();
         if (++st == (uint32_t)NS) {
           st = 0;
@@ -189,78 +204,116 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tcf_conv_kernel(const __grid_co
     }
   } else if (warp == TF_MMA_WARP) {
     // ============================ MMA issuer ============================
-    // the whole warp walks the loop so that descriptors live in uniform registers (see conv_tc.cu); one elected lane issues
-    const uint32_t leader = tc_elect();
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-    const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * NT) >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-    const uint64_t a0 = tc_desc(tc_smem_u32(smem), A_PLANE, 128);
-    const uint64_t b0 = tc_desc(tc_smem_u32(smem) + A_BYTES, (uint32_t)NT * 32, 128);
-    const uint32_t lo_off = (2 * A_PLANE) >> 4;
-    uint32_t st = 0, ph = 0, ai = 0;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
-      tc_mbar_wait(&acce[ab], aph ^ 1, 400 + (int)ab);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int s = 0; s < SPI; ++s) {
-        tc_mbar_wait(&full[st], ph, 500 + (int)st);
+    // One elected thread runs the whole loop (waits, MMAs, commits): under a branch that ptxas can tie to elect.sync
+    // the descriptor arithmetic stays in the uniform datapath; `if (leader)` around each MMA group inside a
+    // warp-wide loop cost ~8 R2URs per MMA (65 clk per MMA issued against 46 executed).
+    if (tc_elect()) {
+      const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * NT) >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+      const uint64_t a0 = tc_desc(tc_smem_u32(smem), A_PLANE, 128);
+      const uint64_t b0 = tc_desc(tc_smem_u32(smem) + A_BYTES, (uint32_t)NT * 32, 128);
+      const uint32_t lo_off = (2 * A_PLANE) >> 4;
+      const uint32_t bt16 = B_TAP >> 4;
+      const int K = p.K, R = p.R, ar = p.ar, bk = p.bk, NPART = p.NPART;
+      uint32_t st = 0, ph = 0, ai = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
+        tc_mbar_wait(&acce[ab], aph ^ 1, 400 + (int)ab);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t a_st = a0 + (uint64_t)((st * STAGE) >> 4);
-        const uint64_t b_st = b0 + (uint64_t)((st * STAGE) >> 4);
-        const int part = s % p.NPART;
-        const bool first = s < p.NPART;
-        if (leader) {
-          for (int r = 0; r < p.R; ++r) {
-            const uint32_t d = tmem_u + ab * TF_ACC_COLS + (uint32_t)((r * p.NPART + part) * 2 * NT);
-            for (int kh = 0; kh < p.K; ++kh) {
-#pragma unroll 3
-              for (int kw = 0; kw < p.K; ++kw) {
-                const uint64_t a_hi = a_st + (uint64_t)(r * p.ar + kh * p.bk + kw);
-                const uint64_t b_t = b_st + (uint64_t)(((kh * p.K + kw) * B_TAP) >> 4);
-                tc_mma(d, a_hi, b_t, idesc1, (first && kh == 0 && kw == 0) ? 0u : 1u);
-                tc_mma(d + NT, a_hi + lo_off, b_t, idesc2, 1u);
+        int part = 0;
+        for (int s = 0; s < SPI; ++s) {
+          tc_mbar_wait(&full[st], ph, 500 + (int)st);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t a_st = a0 + (uint64_t)((st * STAGE) >> 4);
+          const uint64_t b_st = b0 + (uint64_t)((st * STAGE) >> 4);
+          const uint32_t first = s < NPART ? 0u : 1u;
+          const uint32_t d0 = tmem + ab * TF_ACC_COLS + (uint32_t)(part * 2 * NT);
+          for (int r = 0; r < R; ++r) {
+            const uint32_t d = d0 + (uint32_t)(r * NPART * 2 * NT);
+            uint64_t a_kh = a_st + (uint64_t)(r * ar);
+            uint64_t b_t = b_st;
+            for (int kh = 0; kh < K; ++kh) {
+              if (K == 3) {
+                tc_mma(d, a_kh, b_t, idesc1, kh == 0 ? first : 1u);
+                tc_mma(d + NT, a_kh + lo_off, b_t, idesc2, 1u);
+                tc_mma(d, a_kh + 1, b_t + bt16, idesc1, 1u);
+                tc_mma(d + NT, a_kh + 1 + lo_off, b_t + bt16, idesc2, 1u);
+                tc_mma(d, a_kh + 2, b_t + 2 * bt16, idesc1, 1u);
+                tc_mma(d + NT, a_kh + 2 + lo_off, b_t + 2 * bt16, idesc2, 1u);
+              } else if (K == 2) {
+                tc_mma(d, a_kh, b_t, idesc1, kh == 0 ? first : 1u);
+                tc_mma(d + NT, a_kh + lo_off, b_t, idesc2, 1u);
+                tc_mma(d, a_kh + 1, b_t + bt16, idesc1, 1u);
+                tc_mma(d + NT, a_kh + 1 + lo_off, b_t + bt16, idesc2, 1u);
+              } else {
+                tc_mma(d, a_kh, b_t, idesc1, first);
+                tc_mma(d + NT, a_kh + lo_off, b_t, idesc2, 1u);
               }
+              a_kh += (uint64_t)bk;
+              b_t += (uint64_t)(K * bt16);
             }
           }
           tc_commit(&empty[st]);
+          if (++part == NPART) part = 0;
+          if (++st == (uint32_t)NS) {
+            st = 0;
+            ph ^= 1;
+          }
         }
-        __syncwarp();
-        if (++st == (uint32_t)NS) {
-          st = 0;
-          ph ^= 1;
-        }
+        tc_commit(&accf[ab]);
+        ++ai;
       }
-      if (leader) tc_commit(&accf[ab]);
-      __syncwarp();
-      ++ai;
     }
   } else {
     // ============================ epilogue ============================
-    // warps w and w + 4 share TMEM lane quadrant q = w % 4 and take alternate channel quads.
-    const int q = warp & 3, half = warp >> 2;
+    // the four warps w, w + 4, w + 8, w + 12 share TMEM lane quadrant q = w % 4 and take the (tile, 8-channel chunk)
+    // units round-robin; a unit is read with two x8 loads per partial accumulator (main + correction columns).
+    const int q = warp & 3, sub = warp >> 2;
     const int m = q * 32 + lane;
-    const int nq = NT >> 2;
-    const bool gelu = p.act == ESM_ACT_GELU;
+    const int nchunk = NT >> 3;
+    const int units = p.R * nchunk;
+    const int act = p.act;
+    const float invP = 1.0f / (float)p.P, invH = 1.0f / (float)p.Hp;
     uint32_t ai = 0;
+#ifdef TC_PROFILE
+    long long prof_busy = 0;
+#endif
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const TfItem ti = tf_decode(p, item);
       const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
       const int pw = ti.phase & 1, phh = (ti.phase >> 1) & 1, pd = (ti.phase >> 2) & 1;
+      // position of row m of tile 0 (one pair of integer divisions per item; the other tiles are derived from it)
+      const long long f0 = (long long)ti.fbase + m;
+      int d_0, y_0, x_0;
+      {
+        const int fi = (int)(f0 < (long long)p.NP ? f0 : 0);
+        d_0 = fi / p.PH;
+        const int rem = fi - d_0 * p.PH;
+        y_0 = rem / p.P;
+        x_0 = rem - y_0 * p.P;
+      }
       tc_mbar_wait(&accf[ab], aph, 600 + (int)ab);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int r = 0; r < p.R; ++r) {
-        const long long f = (long long)ti.fbase + (long long)r * ti.S + m;
+#ifdef TC_PROFILE
+      const long long te0 = clock64();
+#endif
+      for (int u = sub; u < units; u += 4) {
+        const int r = u / nchunk, ck = u - r * nchunk;
+        const long long f = f0 + (long long)r * ti.S;
         const bool live = r < ti.rlive && m < ti.mlimit && f < (long long)p.NP;
-        int d = 0, y = 0, x = 0;
-        if (live) {
-          const int fi = (int)f;
-          d = fi / p.PH;
-          const int rem = fi - d * p.PH;
-          y = rem / p.P;
-          x = rem - y * p.P;
+        int d = d_0, y = y_0, x = x_0;
+        if (p.mode == 0) {
+          const int t = x_0 + 128 * r;
+          const int yq = tf_div(t, p.P, invP);
+          x = t - yq * p.P;
+          const int t2 = y_0 + yq;
+          const int dq = tf_div(t2, p.Hp, invH);
+          y = t2 - dq * p.Hp;
+          d = d_0 + dq;
+        } else {
+          y = y_0 + r;
         }
         const bool valid = live && d >= p.d0 && d < p.d1 && y >= p.y0 && y < p.y1 && x >= p.x0 && x < p.x1;
-        // mapped output coordinate (logical)
         bool ok = valid;
         int zo = d - p.d0, yo = y - p.y0, xo = x - p.x0;
         if (p.omul != 1 || p.osub != 1 || p.nphase > 1) {
@@ -275,92 +328,110 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tcf_conv_kernel(const __grid_co
           }
         }
         ok = ok && zo < p.oD && yo < p.oH && xo < p.oW;
-        const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * TF_ACC_COLS + (uint32_t)(r * p.NPART * 2 * NT);
-        for (int qd = half; qd < nq; qd += 2) {
-          float mv[4] = {0.f, 0.f, 0.f, 0.f}, cv[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int part = 0; part < p.NPART; ++part) {
-            float a[4], c[4];
-            tc_ld4(tb + part * 2 * NT + qd * 4, a);
-            tc_ld4(tb + part * 2 * NT + NT + qd * 4, c);
-            tc_ld_wait();
+        const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * TF_ACC_COLS + (uint32_t)(r * p.NPART * 2 * NT + ck * 8);
+        float mv[8], cv[8];
+        tc_ld8(tb, mv);
+        tc_ld8(tb + NT, cv);
+        tc_ld_wait();
+        for (int part = 1; part < p.NPART; ++part) {
+          float a[8], c[8];
+          tc_ld8(tb + part * 2 * NT, a);
+          tc_ld8(tb + part * 2 * NT + NT, c);
+          tc_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            mv[j] += a[j];
+            cv[j] += c[j];
+          }
+        }
+        const int c0 = ti.cot * NT + ck * 8;  // first output channel of this chunk
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(fmaf(mv[j], p.debias, cv[j]), s_aff[c0 + j], s_aff[nch + c0 + j]);
+        if (act == ESM_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = tc_gelu(v[j]);
+        } else if (act == ESM_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = tc_silu(v[j]);
+        } else if (act == ESM_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (act != ESM_ACT_NONE) {
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 t4 = apply_act4(make_float4(v[4 * h2], v[4 * h2 + 1], v[4 * h2 + 2], v[4 * h2 + 3]), act);
+            v[4 * h2] = t4.x; v[4 * h2 + 1] = t4.y; v[4 * h2 + 2] = t4.z; v[4 * h2 + 3] = t4.w;
+          }
+        }
+        if (p.ps == 2) {
+          // PixelShuffle(2) of a 2D layer: a quad's channels are the 2 x 2 pixels of channel c / 4 at (2y, 2x)
+          if (p.act2 == ESM_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = tc_silu(v[j]);
+          }
+          if (ok) {
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              if (c0 + 4 * h2 < p.Cout) {
+                float* o = p.out + (long long)ti.b * p.oB + (long long)((c0 >> 2) + h2) * p.oC + (long long)(2 * yo) * p.oHs + 2 * xo;
+                *reinterpret_cast<float2*>(o) = make_float2(v[4 * h2] * p.out_scale, v[4 * h2 + 1] * p.out_scale);
+                *reinterpret_cast<float2*>(o + p.oHs) = make_float2(v[4 * h2 + 2] * p.out_scale, v[4 * h2 + 3] * p.out_scale);
+              }
+            }
+          }
+          continue;
+        }
+        long long opos = 0;  // PF output position (floats) of the chunk's first quad
+        if (p.opf) {
+          const long long of = p.same_geom ? f : ((long long)(zo + p.od0) * p.oHp + (yo + p.oy0)) * p.oP + (xo + p.ox0);
+          opos = (long long)ti.b * p.o_sB + (long long)(c0 >> 2) * p.o_sQ + of * 4;
+        }
+        const long long npos = (long long)ti.b * p.oB + (long long)c0 * p.oC + (long long)zo * p.oDs + (long long)yo * p.oHs + xo;
+        if (ok) {
+          if (p.residual) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (c0 + j < p.Cout) v[j] += __ldg(p.residual + npos + j * p.oC);
+          }
+          if (p.res_pf) {
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              if ((c0 >> 2) + h2 >= p.oCq) break;
+              const float4 rh = __ldg(reinterpret_cast<const float4*>(p.res_pf + opos + h2 * p.o_sQ));
+              const float4 rl = __ldg(reinterpret_cast<const float4*>(p.res_pf + opos + h2 * p.o_sQ + p.o_sHL));
+              v[4 * h2] += rh.x + rl.x; v[4 * h2 + 1] += rh.y + rl.y; v[4 * h2 + 2] += rh.z + rl.z; v[4 * h2 + 3] += rh.w + rl.w;
+            }
+          }
+          if (p.act2 != ESM_ACT_NONE) {
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const float4 t4 = apply_act4(make_float4(v[4 * h2], v[4 * h2 + 1], v[4 * h2 + 2], v[4 * h2 + 3]), p.act2);
+              v[4 * h2] = t4.x; v[4 * h2 + 1] = t4.y; v[4 * h2 + 2] = t4.z; v[4 * h2 + 3] = t4.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= p.out_scale;
+        }
+        if (p.out && ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c0 + j < p.Cout) p.out[npos + j * p.oC] = v[j];
+        }
+        if (p.opf && (p.same_geom ? live : ok)) {
+          const bool keep = p.same_geom ? (valid && ok) : true;
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            if ((c0 >> 2) + h2 >= p.oCq) break;
+            float hv[4], lv[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              mv[j] += a[j];
-              cv[j] += c[j];
+              const float x_ = (keep && c0 + 4 * h2 + j < p.Cout) ? v[4 * h2 + j] : 0.f;
+              hv[j] = tc_rna(x_);
+              lv[j] = x_ - hv[j];
             }
-          }
-          const int c0 = ti.cot * NT + qd * 4;  // first output channel of this quad
-          float v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = fmaf(fmaf(mv[j], p.debias, cv[j]), s_aff[c0 + j], s_aff[nch + c0 + j]);
-          if (gelu) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = tc_gelu(v[j]);
-          } else if (p.act == ESM_ACT_SILU) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = tc_silu(v[j]);
-          } else if (p.act == ESM_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (p.act != ESM_ACT_NONE) {
-            const float4 t4 = apply_act4(make_float4(v[0], v[1], v[2], v[3]), p.act);
-            v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
-          }
-          if (p.ps == 2) {
-            // PixelShuffle(2) of a 2D layer: the quad's channels are the 2 x 2 pixels of channel c0 / 4 at (2y, 2x)
-            if (p.act2 == ESM_ACT_SILU) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) v[j] = tc_silu(v[j]);
-            }
-            if (ok && c0 < p.Cout) {
-              float* o = p.out + (long long)ti.b * p.oB + (long long)(c0 >> 2) * p.oC + (long long)(2 * yo) * p.oHs + 2 * xo;
-              *reinterpret_cast<float2*>(o) = make_float2(v[0] * p.out_scale, v[1] * p.out_scale);
-              *reinterpret_cast<float2*>(o + p.oHs) = make_float2(v[2] * p.out_scale, v[3] * p.out_scale);
-            }
-            continue;
-          }
-          long long opos = 0;  // PF output position (floats)
-          if (p.opf || p.res_pf) {
-            const long long of = p.same_geom ? f : ((long long)(zo + p.od0) * p.oHp + (yo + p.oy0)) * p.oP + (xo + p.ox0);
-            opos = (long long)ti.b * p.o_sB + (long long)(c0 >> 2) * p.o_sQ + of * 4;
-          }
-          const long long npos = (long long)ti.b * p.oB + (long long)c0 * p.oC + (long long)zo * p.oDs + (long long)yo * p.oHs + xo;
-          if (ok) {
-            if (p.residual) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (c0 + j < p.Cout) v[j] += __ldg(p.residual + npos + j * p.oC);
-            }
-            if (p.res_pf) {
-              const float4 rh = __ldg(reinterpret_cast<const float4*>(p.res_pf + opos));
-              const float4 rl = __ldg(reinterpret_cast<const float4*>(p.res_pf + opos + p.o_sHL));
-              v[0] += rh.x + rl.x; v[1] += rh.y + rl.y; v[2] += rh.z + rl.z; v[3] += rh.w + rl.w;
-            }
-            if (p.act2 != ESM_ACT_NONE) {
-              const float4 t4 = apply_act4(make_float4(v[0], v[1], v[2], v[3]), p.act2);
-              v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] *= p.out_scale;
-          }
-          if (p.out && ok) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (c0 + j < p.Cout) p.out[npos + j * p.oC] = v[j];
-          }
-          if (p.opf && (p.same_geom ? live : ok)) {
-            float4 hi, lo;
-            const bool keep = p.same_geom ? (valid && ok) : true;
-            hi.x = (keep && c0 + 0 < p.Cout) ? tc_rna(v[0]) : 0.f;
-            hi.y = (keep && c0 + 1 < p.Cout) ? tc_rna(v[1]) : 0.f;
-            hi.z = (keep && c0 + 2 < p.Cout) ? tc_rna(v[2]) : 0.f;
-            hi.w = (keep && c0 + 3 < p.Cout) ? tc_rna(v[3]) : 0.f;
-            lo.x = (keep && c0 + 0 < p.Cout) ? v[0] - hi.x : 0.f;
-            lo.y = (keep && c0 + 1 < p.Cout) ? v[1] - hi.y : 0.f;
-            lo.z = (keep && c0 + 2 < p.Cout) ? v[2] - hi.z : 0.f;
-            lo.w = (keep && c0 + 3 < p.Cout) ? v[3] - hi.w : 0.f;
-            *reinterpret_cast<float4*>(p.opf + opos) = hi;
-            *reinterpret_cast<float4*>(p.opf + opos + p.o_sHL) = lo;
+            *reinterpret_cast<float4*>(p.opf + opos + h2 * p.o_sQ) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            *reinterpret_cast<float4*>(p.opf + opos + h2 * p.o_sQ + p.o_sHL) = make_float4(lv[0], lv[1], lv[2], lv[3]);
           }
         }
       }
@@ -369,8 +440,22 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tcf_conv_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(&acce[ab]);
       ++ai;
+#ifdef TC_PROFILE
+      prof_busy += clock64() - te0;
+#endif
     }
+#ifdef TC_PROFILE
+    if (blockIdx.x == 0 && lane == 0) tc_prof_wait[warp][1] = (unsigned long long)prof_busy;
+#endif
   }
+#ifdef TC_PROFILE
+  if (blockIdx.x == 0 && lane == 0) {
+    printf("tcf_prof warp %2d: done at %8lld clk; waits: empty %8llu  acce %8llu  full %8llu  accf %8llu | issue %8llu epi busy %8llu\n", warp,
+           clock64() - tc_t0, tc_prof_wait[warp][2], tc_prof_wait[warp][4], tc_prof_wait[warp][5], tc_prof_wait[warp][6], tc_prof_wait[warp][0],
+           tc_prof_wait[warp][1]);
+    for (int i = 0; i < 8; ++i) tc_prof_wait[warp][i] = 0;
+  }
+#endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
@@ -643,7 +728,7 @@ extern "C" int esm_conv_pf_f32(const esm_conv_pf_t* d, void* stream) {
     k.o_sQ = (long long)go.NP * 4;
     k.o_sHL = k.o_sQ * go.Cq;
     k.o_sB = 2 * k.o_sHL;
-    k.oHp = go.Hp; k.oP = go.P; k.od0 = go.d0; k.oy0 = go.y0; k.ox0 = go.x0;
+    k.oHp = go.Hp; k.oP = go.P; k.od0 = go.d0; k.oy0 = go.y0; k.ox0 = go.x0; k.oCq = go.Cq;
     k.same_geom = (!tr && d->stride == 1 && go.Dp == g0.Dp && go.Hp == g0.Hp && go.P == g0.P && go.d0 == k.d0 && go.y0 == k.y0 && go.x0 == k.x0 &&
                    go.d1 == k.d1 && go.y1 == k.y1 && go.x1 == k.x1)
                       ? 1
@@ -665,16 +750,25 @@ extern "C" int esm_conv_pf_f32(const esm_conv_pf_t* d, void* stream) {
   // ---- plan ----
   int num_sms = 0;
   {
+    static int sms_cache[64] = {0};
     int dev = 0;
-    cudaDeviceProp prop;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    if (cudaGetDevice(&dev) != cudaSuccess) {
       cudaGetLastError();
       set_error("conv_pf: no CUDA device");
       return ESM_ERR_CUDA;
     }
-    static int sms_cache[64] = {0};
-    if (dev < 64 && sms_cache[dev] == 0) sms_cache[dev] = prop.multiProcessorCount;
-    num_sms = dev < 64 ? sms_cache[dev] : prop.multiProcessorCount;
+    if (dev < 0 || dev >= 64 || sms_cache[dev] == 0) {
+      int n = 0;
+      if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        set_error("conv_pf: no CUDA device");
+        return ESM_ERR_CUDA;
+      }
+      if (dev >= 0 && dev < 64) sms_cache[dev] = n;
+      num_sms = n;
+    } else {
+      num_sms = sms_cache[dev];
+    }
   }
   const int SPI = k.ncg * k.KD, KK = k.K * k.K;
   // partial accumulators: keep a chain of accumulates short (the tensor core truncates its fp32 accumulator)
