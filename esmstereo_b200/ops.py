@@ -200,12 +200,29 @@ class PackedConv:
     """Device-resident packed form of one conv layer: kernel-layout weights + folded affine.
     Built once per layer by `pack_conv` (BN fold + layout, the `esm_pack_weights` step of SURVEY 8b)."""
 
-    __slots__ = ("weight", "scale", "shift", "Cout", "Cin", "k", "stride", "pad", "transposed", "ndim")
+    __slots__ = ("weight", "scale", "shift", "Cout", "Cin", "k", "stride", "pad", "transposed", "ndim", "src", "pf")
 
-    def __init__(self, weight, scale, shift, Cout, Cin, k, stride, pad, transposed, ndim):
+    def __init__(self, weight, scale, shift, Cout, Cin, k, stride, pad, transposed, ndim, src=None):
         self.weight, self.scale, self.shift = weight, scale, shift
         self.Cout, self.Cin, self.k, self.stride, self.pad = Cout, Cin, k, stride, pad
         self.transposed, self.ndim = transposed, ndim
+        self.src = src   # the torch-layout weight: the flat tcgen05 engine packs its own form from it on first use
+        self.pf = {}     # source channel split -> PackedConvPF sharing this layer's folded affine
+
+    def pf_pack(self, srcC) -> "PackedConvPF":
+        key = tuple(int(v) for v in srcC)
+        if key not in self.pf:
+            w = self.src
+            L = lib()
+            kd, kh, kw = self.k
+            arr = (C.c_int * len(key))(*key)
+            n = L.esm_packed_weight_pf_elems(self.Cout, len(key), arr, kd, kh, kw, int(self.transposed))
+            packed = torch.empty(n, device=w.device, dtype=torch.float32)
+            check(L.esm_pack_conv_weight_pf_f32(w.data_ptr(), packed.data_ptr(), self.Cout, len(key), arr, kd, kh, kw, int(self.transposed),
+                                                _stream()), "pack_conv_weight_pf")
+            self.pf[key] = PackedConvPF(weight=packed, scale=self.scale, shift=self.shift, Cout=self.Cout, srcC=key, k=self.k,
+                                        stride=self.stride, transposed=self.transposed, ndim=self.ndim)
+        return self.pf[key]
 
 
 def _triple(v, ndim):
@@ -246,7 +263,31 @@ def pack_conv(weight: torch.Tensor, stride=1, padding=0, transposed: bool = Fals
         eps, args = 0.0, (None, None, None, None)
     bias_t = _dev(bias.detach(), "bias").contiguous() if bias is not None else None
     check(L.esm_fold_bn_f32(*args, _ptr(bias_t), float(eps), Cout, scale.data_ptr(), shift.data_ptr(), _stream()), "fold_bn")
-    return PackedConv(packed, scale, shift, Cout, Cin, (kd, kh, kw), stride_i, p, bool(transposed), ndim)
+    return PackedConv(packed, scale, shift, Cout, Cin, (kd, kh, kw), stride_i, p, bool(transposed), ndim, src=w)
+
+
+# The flat tcgen05 engine (conv_tcf.cu) takes a layer from esm_conv_f32's engines by a STATIC rule (no timing: the same
+# layer always runs on the same engine), fitted to the per-layer measurements of scratch/tcf_bench.py at KITTI shape:
+# it wins, conversion of the NCHW input included, on wide k3 stride-1 layers of modest extent (40->40, 72->72 of the
+# hourglass; 96->96, 240->240 of FeatUp) and on the large 3D transposed layer (40->24).  ESM_TCF=0 disables it.
+TCF_RULE = os.environ.get("ESM_TCF", "1") != "0"
+
+
+def _tcf_wins(pc: "PackedConv", srcs) -> bool:
+    if pc.src is None or len(srcs) != 1 or os.environ.get("ESM_TC", "3") != "3" or os.environ.get("ESM_TC_FORCE"):
+        return False  # ESM_TC=0 / =1 (no tensor cores / single-pass fast mode) and forced-engine runs keep esm_conv_f32's engines
+    x = srcs[0]
+    if x.dim() != pc.ndim + 2:
+        return False
+    pos = 1
+    for v in x.shape[2:]:
+        pos *= int(v)
+    kd, kh, kw = pc.k
+    if pc.transposed:
+        return pc.ndim == 3 and (kd, kh, kw) == (4, 4, 4) and pc.Cin >= 40 and pos >= 15000
+    if pc.stride != 1 or kh != 3 or kw != 3 or kd not in (1, 3) or tuple(pc.pad[1:]) != (1, 1) or (pc.ndim == 3 and pc.pad[0] != 1):
+        return False
+    return pc.Cin >= 40 and pc.Cout >= 40 and pc.Cin * pc.Cout >= 1600 and pos <= 60000 and (pc.Cin >= 72 or pc.ndim == 3)
 
 
 def _src_struct(t: torch.Tensor, nd: int):
@@ -284,6 +325,11 @@ def conv(srcs: Sequence[torch.Tensor], pc: PackedConv, act: Optional[str] = None
         srcs = [srcs]
     srcs = [_dev(t, "conv input") for t in srcs]
     nd = pc.ndim
+    if (TCF_RULE and gwc_disp is None and in_mul is None and out_mul is None and not pixel_shuffle and not fp32_only and affine
+            and _tcf_wins(pc, srcs)):
+        pfs = [to_pf(t) for t in srcs]
+        return conv_pf(pfs, pc.pf_pack([t.shape[1] for t in srcs]), act, out="nchw", residual=residual, act2=act2, out_scale=out_scale,
+                       out_size=out_size)
     d = EsmConv()
     keep: List[torch.Tensor] = []
     x0 = srcs[0]
