@@ -74,6 +74,7 @@ SIGNATURES = {
     "esm_norm_corr_volume_f32": (C.c_int, [vp, vp, vp, vp] + [C.c_int] * 5 + [vp]),
     "esm_concat_volume_f32": (C.c_int, [vp, vp, vp] + [C.c_int] * 5 + [vp]),
     "esm_substract_volume_f32": (C.c_int, [vp, vp, vp] + [C.c_int] * 6 + [vp]),
+    "esm_gwc_volume_norm_f32": (C.c_int, [vp, vp, vp] + [C.c_int] * 6 + [vp]),
     "esm_preprocess_u8_f32": (C.c_int, [vp, vp] + [C.c_int] * 8 + [C.POINTER(C.c_float), C.POINTER(C.c_float), vp]),
     "esm_postprocess_disp_u16": (C.c_int, [vp, vp] + [C.c_int] * 7 + [C.c_float, vp]),
     "esm_regression_top2_f32": (C.c_int, [vp, vp, vp] + [C.c_int] * 4 + [vp]),

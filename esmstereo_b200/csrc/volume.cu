@@ -3,6 +3,7 @@
 //   esm_norm_corr_volume_f32  <- build_norm_correlation_volume + norm_correlation (submodule.py:187-200)
 //   esm_concat_volume_f32     <- build_concat_volume (submodule.py:129-140)
 //   esm_substract_volume_f32  <- build_substract_volume + groupwise_difference (submodule.py:104-126)
+//   esm_gwc_volume_norm_f32   <- build_gwc_volume_norm + groupwise_correlation_norm (submodule.py:163-184)
 //   (the last two are not used by any model configuration)
 // The reference builds the volume with a Python loop over disparities (memset + D x {mul, mean,
 // strided copy}); here one launch writes every output element exactly once, zeros included.
@@ -253,7 +254,53 @@ __global__ void __launch_bounds__(256) substract_volume_kernel(const float* __re
   V[i] = s;
 }
 
+// build_gwc_volume_norm + groupwise_correlation_norm (submodule.py:163-184):
+//   V[b, g, d, y, x] = mean_{c in g} (L[c, y, x] / (|L_g(y, x)|_2 + 1e-5)) * (R[c, y, x - d] / (|R_g(y, x - d)|_2 + 1e-5))   for x >= d, else 0
+// with the norms over the channels of the group at that pixel.  Same operation order as the reference (divide, multiply, sum, divide by cpg).
+__global__ void __launch_bounds__(256) gwc_volume_norm_kernel(const float* __restrict__ L, const float* __restrict__ R, float* __restrict__ V,
+                                                              int C, int H, int W, int D, int G, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % W);
+  long long t = i / W;
+  const int y = (int)(t % H);
+  t /= H;
+  const int d = (int)(t % D);
+  t /= D;
+  const int g = (int)(t % G);
+  const long long b = t / G;
+  const int cpg = C / G;
+  float s = 0.f;
+  if (x >= d) {
+    const long long plane = (long long)H * W;
+    const float* l = L + (b * C + (long long)g * cpg) * plane + (long long)y * W + x;
+    const float* r = R + (b * C + (long long)g * cpg) * plane + (long long)y * W + x - d;
+    float nl = 0.f, nr = 0.f;
+    for (int c = 0; c < cpg; ++c) {
+      const float a = __ldg(l + c * plane), q = __ldg(r + c * plane);
+      nl = __fadd_rn(nl, __fmul_rn(a, a));
+      nr = __fadd_rn(nr, __fmul_rn(q, q));
+    }
+    nl = __fadd_rn(__fsqrt_rn(nl), 1e-5f);
+    nr = __fadd_rn(__fsqrt_rn(nr), 1e-5f);
+    for (int c = 0; c < cpg; ++c)
+      s = __fadd_rn(s, __fmul_rn(__fdiv_rn(__ldg(l + c * plane), nl), __fdiv_rn(__ldg(r + c * plane), nr)));
+    s = __fdiv_rn(s, (float)cpg);
+  }
+  V[i] = s;
+}
+
 }  // namespace esm
+
+extern "C" int esm_gwc_volume_norm_f32(const float* L, const float* R, float* V, int B, int C, int H, int W, int D, int G, void* stream) {
+  ESM_REQUIRE(L && R && V, "gwc_volume_norm: null pointer");
+  ESM_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0 && G > 0, "gwc_volume_norm: empty shape");
+  ESM_REQUIRE(C % G == 0, "gwc_volume_norm: C (%d) not divisible by groups (%d)", C, G);  // submodule.py:165
+  const long long total = (long long)B * G * D * H * W;
+  ESM_REQUIRE(esm::ceil_div_ll(total, 256) < (1ll << 31), "gwc_volume_norm: grid too large");
+  esm::gwc_volume_norm_kernel<<<(unsigned)esm::ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(L, R, V, C, H, W, D, G, total);
+  return esm::check_launch("gwc_volume_norm");
+}
 
 extern "C" int esm_concat_volume_f32(const float* L, const float* R, float* V, int B, int C, int H, int W, int D, void* stream) {
   ESM_REQUIRE(L && R && V, "concat_volume: null pointer");

@@ -112,6 +112,19 @@ def build_substract_volume(refimg_fea: torch.Tensor, targetimg_fea: torch.Tensor
     return V
 
 
+def build_gwc_volume_norm(refimg_fea: torch.Tensor, targetimg_fea: torch.Tensor, maxdisp: int, num_groups: int) -> torch.Tensor:
+    """`build_gwc_volume_norm` (submodule.py:163-184): group-wise correlation of per-group L2-normalised features."""
+    L_, R_ = _dev(refimg_fea, "refimg_fea").contiguous(), _dev(targetimg_fea, "targetimg_fea").contiguous()
+    B, Cc, H, W = L_.shape
+    assert R_.shape == L_.shape
+    assert Cc % num_groups == 0  # submodule.py:165
+    V = torch.empty(B, int(num_groups), int(maxdisp), H, W, device=L_.device, dtype=torch.float32)
+    with _Prof("gwc_volume_norm C%d G%d D%d %dx%d" % (Cc, num_groups, maxdisp, H, W)):
+        check(lib().esm_gwc_volume_norm_f32(L_.data_ptr(), R_.data_ptr(), V.data_ptr(), B, Cc, H, W, int(maxdisp), int(num_groups),
+                                            _stream()), "gwc_volume_norm")
+    return V
+
+
 IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
 
 

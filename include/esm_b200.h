@@ -131,6 +131,11 @@ int esm_concat_volume_f32(const float* L, const float* R, float* V, int B, int C
 int esm_substract_volume_f32(const float* L, const float* R, float* V, int B, int C, int H, int W, int D, int G,
                              void* stream);
 
+/* build_gwc_volume_norm (submodule.py:163-184): group-wise correlation of the features L2-normalised per group and
+ * pixel (norm + 1e-5): V[b,g,d,y,x] = mean_{c in g} L^[c,y,x] * R^[c,y,x-d] for x >= d else 0.  Unused by the models. */
+int esm_gwc_volume_norm_f32(const float* L, const float* R, float* V, int B, int C, int H, int W, int D, int G,
+                            void* stream);
+
 /* regression_topk(cost, arange(D), k=2) (submodule.py:218-225, ESMStereo.py:719-721):
  * cost [B,D,H,W] -> pred [B,1,H,W]; idx (optional, int32 [B,2,H,W]) receives the top-2 indices
  * (ties: lower index first). */

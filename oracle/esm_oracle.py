@@ -193,6 +193,18 @@ class EsmOracle:
             V[:, :, d, :, d:] = torch.pow(diff, 2).sum(2)
         return V
 
+    def gwc_volume_norm(self, L: torch.Tensor, R: torch.Tensor, D: int, G: int) -> torch.Tensor:
+        """`build_gwc_volume_norm` + `groupwise_correlation_norm` (`submodule.py:163-184`): features L2-normalised per
+        group and pixel (the norm does not depend on the disparity, so it is taken once)."""
+        B, C, H, W = L.shape
+        Lg, Rg = L.view(B, G, C // G, H, W), R.view(B, G, C // G, H, W)
+        Ln = Lg / (torch.norm(Lg, 2, 2, True) + 1e-05)
+        Rn = Rg / (torch.norm(Rg, 2, 2, True) + 1e-05)
+        V = L.new_zeros(B, G, D, H, W)
+        for d in range(min(D, W)):
+            V[:, :, d, :, d:] = (Ln[..., d:] * Rn[..., : W - d]).mean(dim=2)
+        return V
+
     # ------------------------------------------------------------------ hot path: 3D hourglass
     def hourglass(self, x: torch.Tensor, p: str = "aggregation_out") -> torch.Tensor:
         """`aggregation.forward` (`ESMStereo.py:165-182`)."""

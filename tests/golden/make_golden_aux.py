@@ -35,7 +35,8 @@ def main():
     from PIL import Image
     from torchvision import transforms
     L, R, img, disp = aux_inputs()
-    out = {"concat": sub.build_concat_volume(L, R, 6).numpy(), "substract": sub.build_substract_volume(L, R, 6, 4).numpy()}
+    out = {"concat": sub.build_concat_volume(L, R, 6).numpy(), "substract": sub.build_substract_volume(L, R, 6, 4).numpy(),
+           "gwc_norm": sub.build_gwc_volume_norm(L, R, 6, 4).numpy()}
     # test_kitti.py:93-106
     pil = Image.fromarray(img.numpy())
     w, h = pil.size

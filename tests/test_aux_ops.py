@@ -22,6 +22,7 @@ def test_oracle_matches_reference_aux_goldens():
     o = EsmOracle({}, 192)
     assert np.array_equal(o.concat_volume(L, R, 6).numpy(), GOLD["concat"])
     assert np.abs(o.substract_volume(L, R, 6, 4).numpy() - GOLD["substract"]).max() < 1e-6
+    assert np.abs(o.gwc_volume_norm(L, R, 6, 4).numpy() - GOLD["gwc_norm"]).max() < 1e-6
     size = tuple(int(v) for v in GOLD["pre_size"])
     assert np.array_equal(preprocess_images(img[None], size, "test_kitti").numpy(), GOLD["pre_test_kitti"])
     assert np.array_equal(preprocess_images(img[None], size, "kitti_dataset").numpy(), GOLD["pre_kitti_dataset"])
@@ -37,14 +38,22 @@ def test_gpu_volume_variants_match_reference():
     assert np.array_equal(got, GOLD["concat"])
     got = ops.build_substract_volume(L.cuda(), R.cuda(), 6, 4).cpu().numpy()
     assert np.abs(got - GOLD["substract"]).max() < 1e-6
+    got = ops.build_gwc_volume_norm(L.cuda(), R.cuda(), 6, 4).cpu().numpy()
+    assert np.abs(got - GOLD["gwc_norm"]).max() < 1e-6
     # odd width (scalar tail of the 4-wide rows), maxdisp > W
     o = EsmOracle({}, 192)
     g = torch.Generator().manual_seed(3)
     L2, R2 = torch.randn(1, 6, 3, 7, generator=g), torch.randn(1, 6, 3, 7, generator=g)
     assert torch.equal(ops.build_concat_volume(L2.cuda(), R2.cuda(), 9).cpu(), o.concat_volume(L2, R2, 9))
     assert (ops.build_substract_volume(L2.cuda(), R2.cuda(), 9, 3).cpu() - o.substract_volume(L2, R2, 9, 3)).abs().max() < 1e-6
+    assert (ops.build_gwc_volume_norm(L2.cuda(), R2.cuda(), 9, 3).cpu() - o.gwc_volume_norm(L2, R2, 9, 3)).abs().max() < 1e-6
+    # two channels per group (the models' gwc geometry): every operation is then the reference's, bit for bit up to the mean
+    L3, R3 = torch.randn(1, 64, 6, 40, generator=g), torch.randn(1, 64, 6, 40, generator=g)
+    assert (ops.build_gwc_volume_norm(L3.cuda(), R3.cuda(), 12, 32).cpu() - o.gwc_volume_norm(L3, R3, 12, 32)).abs().max() < 1e-6
     with pytest.raises(AssertionError):
         ops.build_substract_volume(L2.cuda(), R2.cuda(), 4, 4)  # C % G != 0, submodule.py:107
+    with pytest.raises(AssertionError):
+        ops.build_gwc_volume_norm(L2.cuda(), R2.cuda(), 4, 4)  # submodule.py:165
 
 
 @pytest.mark.gpu
