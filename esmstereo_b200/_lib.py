@@ -67,6 +67,9 @@ SIGNATURES = {
     "esm_pack_conv_weight_f32": (C.c_int, [vp, vp] + [C.c_int] * 6 + [vp]),
     "esm_fold_bn_f32": (C.c_int, [vp, vp, vp, vp, vp, C.c_float, C.c_int, vp, vp, vp]),
     "esm_conv_f32": (C.c_int, [C.POINTER(EsmConv), vp]),
+    "esm_conv_plans_export": (C.c_longlong, [C.c_char_p, C.c_longlong]),
+    "esm_conv_plans_import": (C.c_int, [C.c_char_p]),
+    "esm_conv_tuned_calls": (C.c_longlong, []),
     "esm_tc_conv_launches": (C.c_longlong, []),
     "esm_tcg_conv_launches": (C.c_longlong, []),
     "esm_pw_conv_launches": (C.c_longlong, []),
@@ -87,6 +90,7 @@ SIGNATURES = {
     "esm_laf_sample_embed_f32": (C.c_int, [vp] * 8 + [C.c_int] * 4 + [vp]),
     "esm_conf_convex_up4_f32": (C.c_int, [vp] * 5 + [C.c_int] * 4 + [vp]),
     "esm_fill_f32": (C.c_int, [vp, C.c_longlong, C.c_float, vp]),
+    "esm_umma_tf32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_float), vp]),
     "esm_pf_elems": (C.c_longlong, [C.c_int] * 5),
     "esm_pf_guard_elems": (C.c_longlong, [C.c_int] * 3),
     "esm_pf_from_nchw_f32": (C.c_int, [vp] + [C.c_longlong] * 4 + [C.POINTER(EsmPf), vp]),
@@ -113,7 +117,34 @@ def lib():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
         _lib = handle
+        _import_plans(handle)
     return _lib
+
+
+PLANS_DIR = os.path.join(_HERE, "plans")
+
+
+def _import_plans(handle) -> int:
+    """Pin the engine plans shipped in esmstereo_b200/plans/*.txt (tuned once on a B200 by scripts/tune_plans.py): the
+    conv engines then never time candidates for those shapes, so engine choice -- and rounding -- is the same in every
+    process.  ESM_PLANS=0 skips this (every shape is then timed on first use)."""
+    if os.environ.get("ESM_PLANS", "1") == "0" or not os.path.isdir(PLANS_DIR):
+        return 0
+    n = 0
+    for name in sorted(os.listdir(PLANS_DIR)):
+        if name.endswith(".txt"):
+            with open(os.path.join(PLANS_DIR, name), "rb") as f:
+                n += handle.esm_conv_plans_import(f.read())
+    return n
+
+
+def export_plans() -> str:
+    """The plans this process has tuned or imported, in the text form of esmstereo_b200/plans/*.txt."""
+    h = lib()
+    n = h.esm_conv_plans_export(None, 0)
+    buf = C.create_string_buffer(int(n))
+    h.esm_conv_plans_export(buf, n)
+    return buf.value.decode()
 
 
 def check(rc: int, what: str) -> None:

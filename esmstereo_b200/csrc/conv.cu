@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <map>
 #include <mutex>
+#include <string>
 #include <vector>
 #include <type_traits>
 
@@ -347,9 +348,18 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const long long* dim
 // Launch plans are memoised per shape: the tiling search and the occupancy query cost ~50 us on the
 // host, which matters in eager mode (under CUDA-graph replay the host never runs them).
 struct PlanKey {
-  int v[16];
+  int v[24];
   bool operator<(const PlanKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
 };
+// A plan pinned by esm_conv_plans_import (the persisted result of an earlier autotune): which engine, and for the
+// FP32-pipe engine which candidate of the tiling enumeration.
+struct PinnedPlan {
+  int use_tc;
+  int CK, COP, COG, cosplit, NV, TWG, TH, TD, slots, nstages;
+};
+static std::map<PlanKey, PinnedPlan> g_pinned;
+static std::mutex g_pinned_mu;
+static long long g_tuned_calls = 0;  // esm_conv_f32 calls that timed candidates on the device
 struct Plan {
   Tiling tl;
   conv_fn_t fn;         // cp.async pipeline (any strides)
@@ -444,6 +454,15 @@ static int launch_plan(const esm_conv_t* d, const PackGeom& g, ConvK k, const Pl
       const int box[3] = {plan.COP, plan.CK, taps};
       use_tma = encode_map(&maps.w, d->weight, 3, dims, str, box);
     }
+  }
+  // the limit is per function AND per device: set it on every launch (the plan cache may have been filled on another device)
+  {
+    conv_fn_t fn_used = !use_tma ? plan.fn : (!d->transposed ? plan.fn_tma[xo_a == 3] : nullptr);
+    conv_fn_t fns[2] = {fn_used ? fn_used : plan.fn_tma[1], fn_used ? nullptr : plan.fn_tma[0]};
+    for (int i = 0; i < 2; ++i)
+      if (fns[i] && tl.smem > 48 * 1024 &&
+          cudaFuncSetAttribute((const void*)fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
+        return check_launch("conv(cudaFuncSetAttribute)");
   }
   const long long resident = (long long)num_sms * plan.blocks_per_sm;
   // Optional programmatic stream serialization (PDL, ESM_PDL=1): the kernel's prologue (mbarrier init,
@@ -615,7 +634,7 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
 
   static std::map<PlanKey, Plan> plans;
   static std::mutex plans_mu;
-  static int num_sms = 0;
+  static int sms_by_dev[64] = {0};
   // tensor-core policy: ESM_TC=0 off, 3 (default) split-TF32 (fp32-grade), 1 single-pass TF32 (fast mode);
   // ESM_TC_FORCE=1 takes the tensor-core path whenever the layer is eligible (tests), else it must win the timing
   const char* tc_env = getenv("ESM_TC");
@@ -624,26 +643,52 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   // ... =3 the pointwise streaming kernel (true fp32: allowed for engine == 1 layers too)
   const int force_env = getenv("ESM_TC_FORCE") ? atoi(getenv("ESM_TC_FORCE")) : 0;
   const int tc_force = force_env == 3 ? 3 : (force_env != 0 && tc_pass != 0) ? (force_env == 2 ? 2 : 1) : 0;
-  PlanKey key = {{d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed, lg.Jw, lg.Jh, lg.Jd, gwc ? k.cpg : 0, d->B, d->pd,
-                  d->ph, d->pw, tc_pass * 4 + tc_force + (d->in_mul ? 64 : 0) + (d->pixel_shuffle ? 128 : 0)}};
-  std::lock_guard<std::mutex> lock(plans_mu);
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaDeviceProp prop;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
-      // no device: still run the validation / tiling below so shapes can be checked on a CPU box
-      cudaGetLastError();
-      num_sms = -1;
-    } else {
-      num_sms = prop.multiProcessorCount;
-    }
+  int dev = -1;
+  int num_sms = -1;  // no device: still run the validation / tiling below so shapes can be checked on a CPU box
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    dev = -1;
   }
+  std::lock_guard<std::mutex> lock(plans_mu);
+  if (dev >= 0 && dev < 64) {
+    if (sms_by_dev[dev] == 0) {
+      int n = 0;
+      if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = -1;
+      }
+      sms_by_dev[dev] = n;
+    }
+    num_sms = sms_by_dev[dev];
+  }
+  // Everything the engines' eligibility and tiling depend on goes into the key (a cached plan is launched without
+  // re-planning): the source split, the fused operands, the alignment classes of the output, the device.  The
+  // tensor-core plans are additionally re-validated on a hit (cheap arithmetic) and fall back to the FP32 pipe.
+  const int align_cls = (int)((reinterpret_cast<uintptr_t>(d->out) & 15) ? 1 : 0) | (d->oH % 4 ? 2 : 0) | (d->oH % 2 ? 4 : 0);
+  int src_align = 0;
+  for (int i = 0; i < d->nsrc; ++i) {
+    const esm_src_t& sv = d->src[i];
+    if ((reinterpret_cast<uintptr_t>(sv.ptr) & 15) || sv.sH % 4 || sv.sC % 4 || sv.sB % 4 || (d->Din > 1 && !gwc && sv.sD % 4)) src_align |= 1 << i;
+  }
+  PlanKey key = {{d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed, lg.Jw, lg.Jh, lg.Jd, gwc ? k.cpg : 0, d->B, d->pd,
+                  d->ph, d->pw, tc_pass * 4 + tc_force + (d->in_mul ? 64 : 0) + (d->pixel_shuffle ? 128 : 0),
+                  d->nsrc, d->nsrc > 0 ? d->src[0].C : 0, d->nsrc > 1 ? d->src[1].C : 0, d->nsrc > 2 ? d->src[2].C : 0,
+                  (d->out_mul ? 1 : 0) | (d->residual ? 2 : 0) | (d->act2 != ESM_ACT_NONE ? 4 : 0), align_cls | (src_align << 3), dev, 0}};
   auto it = plans.find(key);
-  if (it != plans.end())
-    return it->second.use_tc == 3   ? pw_conv_launch(d, it->second.pw, st)
-           : it->second.use_tc == 2 ? tcg_conv_launch(d, it->second.tcg, st)
-           : it->second.use_tc == 1 ? tc_conv_launch(d, it->second.tc, st)
-                                    : launch_plan(d, g, k, it->second, lg, num_sms, st);
+  if (it != plans.end()) {
+    const Plan& hp = it->second;
+    if (hp.use_tc == 3) {
+      PwPlan t;
+      if (pw_conv_plan(d, &t)) return pw_conv_launch(d, hp.pw, st);
+    } else if (hp.use_tc == 2) {
+      TcgPlan t;
+      if (tcg_conv_plan(d, num_sms, hp.tcg.npass, &t)) return tcg_conv_launch(d, hp.tcg, st);
+    } else if (hp.use_tc == 1) {
+      TcPlan t;
+      if (tc_conv_plan(d, num_sms, hp.tc.npass, &t)) return tc_conv_launch(d, hp.tc, st);
+    }
+    return launch_plan(d, g, k, hp, lg, num_sms, st);
+  }
 
   // ---- plan: enumerate (channel split x chunk depth x tile shape), rank by the analytic model ----
   const int ck0 = g.CinPad == 1 ? 1 : 8;
@@ -711,6 +756,40 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
     set_error("conv: no CUDA device");
     return ESM_ERR_CUDA;
   }
+  // ---- pinned plan (esm_conv_plans_import): same engine and tiling as when it was tuned, no timing, no sync ----
+  // The key is device independent (ordinal zeroed); ESM_AUTOTUNE=1 ignores pinned plans and re-times.
+  {
+    const char* env_t = getenv("ESM_AUTOTUNE");
+    PlanKey pk = key;
+    pk.v[22] = 0;
+    std::lock_guard<std::mutex> plock(g_pinned_mu);
+    auto pit = g_pinned.find(pk);
+    if (pit != g_pinned.end() && !(env_t && env_t[0] == '1') && tc_force == 0) {
+      const PinnedPlan& pp = pit->second;
+      bool found = false;
+      for (const Candidate& c : cands) {
+        if (c.CK == pp.CK && c.COP == pp.COP && c.COG == pp.COG && c.cosplit == pp.cosplit && c.tl.NV == pp.NV && c.tl.TWG == pp.TWG &&
+            c.tl.TH == pp.TH && c.tl.TD == pp.TD && c.tl.slots == pp.slots && c.tl.nstages == pp.nstages) {
+          if (make_plan(c, &best_plan) == ESM_OK) found = true;
+          break;
+        }
+      }
+      if (found || pp.use_tc != 0) {
+        const int np = tc_pass == 1 ? 1 : 3;
+        best_plan.use_tc = 0;
+        if (pp.use_tc == 1 && tc_pass != 0 && tc_conv_plan(d, num_sms, np, &best_plan.tc)) best_plan.use_tc = 1;
+        if (pp.use_tc == 2 && tc_pass != 0 && tcg_conv_plan(d, num_sms, np, &best_plan.tcg)) best_plan.use_tc = 2;
+        if (pp.use_tc == 3 && pw_conv_plan(d, &best_plan.pw)) best_plan.use_tc = 3;
+        if (best_plan.use_tc == pp.use_tc && (found || pp.use_tc != 0)) {
+          plans.emplace(key, best_plan);
+          return best_plan.use_tc == 3   ? pw_conv_launch(d, best_plan.pw, st)
+                 : best_plan.use_tc == 2 ? tcg_conv_launch(d, best_plan.tcg, st)
+                 : best_plan.use_tc == 1 ? tc_conv_launch(d, best_plan.tc, st)
+                                         : launch_plan(d, g, k, best_plan, lg, num_sms, st);
+        }
+      }
+    }
+  }
 
   // ---- autotune: time the best-ranked candidates on the device (first call per shape, never during
   // graph capture); "measure, don't guess" -- the model above mis-ranks latency-bound layers ----
@@ -718,6 +797,7 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   cudaStreamIsCapturing(st, &cap);
   const char* env = getenv("ESM_AUTOTUNE");
   const bool tune = cap == cudaStreamCaptureStatusNone && !(env && env[0] == '0');
+  if (tune) ++g_tuned_calls;
   float best_ms = 1e30f;
   if (tune && cands.size() > 1) {
     // shortlist: the 6 best by model + the best of every (voxels/thread, channel-group width, CTA size
@@ -843,8 +923,70 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
             best_plan.CK, best_plan.COP, best_plan.cosplit, best_plan.tl.TD, best_plan.tl.TH, best_plan.tl.TWG * best_plan.tl.NV,
             best_plan.tl.slots * (best_plan.COP / best_plan.COG), best_plan.tl.smem / 1024, best_plan.blocks_per_sm, (int)tune);
   plans.emplace(key, best_plan);
+  if (tune && tc_force == 0) {  // remember what the timing chose, for esm_conv_plans_export
+    PlanKey pk = key;
+    pk.v[22] = 0;
+    PinnedPlan pp = {best_plan.use_tc, best_plan.CK, best_plan.COP, best_plan.COG, best_plan.cosplit, best_plan.tl.NV, best_plan.tl.TWG,
+                     best_plan.tl.TH, best_plan.tl.TD, best_plan.tl.slots, best_plan.tl.nstages};
+    std::lock_guard<std::mutex> plock(g_pinned_mu);
+    g_pinned[pk] = pp;
+  }
   return best_plan.use_tc == 3   ? pw_conv_launch(d, best_plan.pw, st)
          : best_plan.use_tc == 2 ? tcg_conv_launch(d, best_plan.tcg, st)
          : best_plan.use_tc == 1 ? tc_conv_launch(d, best_plan.tc, st)
                                  : launch_plan(d, g, k, best_plan, lg, num_sms, st);
 }
+
+// ------------------------------------------------------------------------------------------
+// plan persistence: one text line per layer shape, "k0 k1 ... k23 : use_tc CK COP COG cosplit NV TWG TH TD slots nstages"
+// ------------------------------------------------------------------------------------------
+extern "C" long long esm_conv_plans_export(char* buf, long long cap) {
+  std::lock_guard<std::mutex> plock(g_pinned_mu);
+  std::string out;
+  char line[512];
+  for (const auto& kv : g_pinned) {
+    int n = 0;
+    for (int i = 0; i < 24; ++i) n += snprintf(line + n, sizeof(line) - n, "%d ", kv.first.v[i]);
+    const PinnedPlan& p = kv.second;
+    snprintf(line + n, sizeof(line) - n, ": %d %d %d %d %d %d %d %d %d %d %d\n", p.use_tc, p.CK, p.COP, p.COG, p.cosplit, p.NV, p.TWG, p.TH, p.TD,
+             p.slots, p.nstages);
+    out += line;
+  }
+  if (buf && cap > 0) {
+    const size_t n = out.size() < (size_t)(cap - 1) ? out.size() : (size_t)(cap - 1);
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (long long)out.size() + 1;
+}
+
+extern "C" int esm_conv_plans_import(const char* text) {
+  ESM_REQUIRE(text, "conv_plans_import: null text");
+  std::lock_guard<std::mutex> plock(g_pinned_mu);
+  int count = 0;
+  const char* p = text;
+  while (*p) {
+    const char* eol = strchr(p, '\n');
+    std::string ln(p, eol ? (size_t)(eol - p) : strlen(p));
+    p = eol ? eol + 1 : p + ln.size();
+    if (ln.empty() || ln[0] == '#') continue;
+    PlanKey k;
+    PinnedPlan pp;
+    int off = 0, n = 0;
+    bool ok = true;
+    for (int i = 0; i < 24 && ok; ++i) {
+      ok = sscanf(ln.c_str() + off, "%d%n", &k.v[i], &n) == 1;
+      off += n;
+    }
+    if (!ok) continue;
+    if (sscanf(ln.c_str() + off, " : %d %d %d %d %d %d %d %d %d %d %d", &pp.use_tc, &pp.CK, &pp.COP, &pp.COG, &pp.cosplit, &pp.NV, &pp.TWG, &pp.TH,
+               &pp.TD, &pp.slots, &pp.nstages) != 11)
+      continue;
+    k.v[22] = 0;
+    g_pinned[k] = pp;
+    ++count;
+  }
+  return count;
+}
+
+extern "C" long long esm_conv_tuned_calls(void) { return g_tuned_calls; }

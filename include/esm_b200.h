@@ -104,6 +104,19 @@ int esm_pack_conv_weight_f32(const float* w, float* packed, int Cout, int Cin, i
 int esm_fold_bn_f32(const float* gamma, const float* beta, const float* mean, const float* var,
                     const float* bias, float eps, int C, float* scale, float* shift, void* stream);
 int esm_conv_f32(const esm_conv_t* desc, void* stream);
+/*
+ * Engine plans.  esm_conv_f32 chooses, per layer shape, one of its engines (FP32 pipe tiling, resident / streamed
+ * tcgen05, pointwise) -- by timing the candidates on the device the first time a shape is seen, unless a plan for
+ * that shape has been imported: then the same engine and tiling are used with no timing and no synchronisation, so
+ * every process computes a layer with the same rounding.  esm_conv_plans_export writes the plans this process tuned
+ * (text, one line per shape; returns the bytes needed incl. the terminator), esm_conv_plans_import reads such text
+ * (returns the number of plans read).  ESM_AUTOTUNE=1 ignores imported plans and re-times; ESM_AUTOTUNE=0 never times
+ * (imported plan, else the analytic model's FP32-pipe choice).  esm_conv_tuned_calls counts the calls that timed.
+ */
+long long esm_conv_plans_export(char* buf, long long cap);
+int esm_conv_plans_import(const char* text);
+long long esm_conv_tuned_calls(void);
+
 /* Number of esm_conv_f32 calls so far that ran on the tcgen05 tensor-core path (k3 s1 p1 layers, when
  * it wins the on-device timing or ESM_TC_FORCE is set; ESM_TC=0 disables it, ESM_TC=1 selects the
  * single-pass TF32 fast mode instead of the fp32-grade split).  Diagnostics / tests. */
@@ -202,6 +215,9 @@ int esm_laf_sample_embed_f32(const float* feat, const float* scale, const float*
  * feat [B,C,h,w], conf [B,1,h,w], weight [C,9,4,4] (torch layout), bias [9] -> out [B,1,4h,4w]. */
 int esm_conf_convex_up4_f32(const float* feat, const float* conf, const float* weight, const float* bias,
                             float* out, int B, int C, int h, int w, void* stream);
+/* Measured dense TF32 tensor-core rate of the current device (TFLOP/s): every SM issues `iters` back-to-back
+ * M128 x N256 x K8 tcgen05.mma.  Synchronises; diagnostics / bench.py's tensor-roofline denominator. */
+int esm_umma_tf32_peak(int iters, float* tflops, void* stream);
 /* Fill `n` floats with `value`. */
 int esm_fill_f32(float* p, long long n, float value, void* stream);
 
