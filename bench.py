@@ -1,16 +1,20 @@
-"""Benchmark of the ESMStereo hot path (BASELINE.json: stereo pairs/sec @384x1248 maxdisp192; cost-volume
-HBM GB/s).
+"""Benchmark of the ESMStereo hot path (BASELINE.json: stereo pairs/sec @384x1248 maxdisp192; cost-volume HBM GB/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--breakdown]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config A|B|C|E] [--batch b] [--breakdown]
 
-One step = one forward of ESMStereo-L (cv4, gwc, maxdisp 192) over one synthetic KITTI-shaped stereo
-pair (BASELINE.json configs[1]) per GPU; pairs shard by rank with no data-path collective (weak
-scaling), and the per-step disparities are all-gathered over NCCL as the reference-side "gather of
-outputs".  Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port instead
-(the Python reference cannot travel to the GPU box).
+One step = one forward of the configuration's model over one synthetic batch per GPU (default config B =
+BASELINE.json configs[1]: ESMStereo-L cv4 gwc, one KITTI-shaped 384x1248 pair); pairs shard by rank with no data-path
+collective (weak scaling), and the per-rank disparities are all-gathered over NCCL on a side stream as the
+reference-side "gather of outputs".  Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port
+instead (the Python reference cannot travel to the GPU box).
+
+Configurations (BASELINE.json `configs`): A = 256x512 pair (the reference's CPU-runnable case), B = 384x1248 pair
+(latency path, the headline), C = 8 x 544x960 pairs (throughput path), E = ESMStereo_confidence 992x1472 cv16;
+D (the batch sweep across GPUs) is `--config B --batch b --gpus N`.
 """
 import argparse
 import contextlib
+import ctypes
 import io
 import json
 import os
@@ -24,9 +28,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-H, W, MAXDISP = 384, 1248, 192
-WORKLOAD = "ESMStereo-L (cv_scale 4, gwc, efficientnet_b2 stand-in backbone) 384x1248 pair, batch 1 per GPU, maxdisp 192, fp32"
-METRIC = "stereo pairs/sec @384x1248 maxdisp192"
+MAXDISP = 192
+CONFIGS = {
+    "A": dict(model="ESMStereo", backbone="efficientnet_b2", cv=4, H=256, W=512, batch=1,
+              metric="stereo pairs/sec @256x512 maxdisp192",
+              workload="ESMStereo-L (cv_scale 4, gwc, efficientnet_b2 stand-in backbone) 256x512 pair, batch 1 per GPU, maxdisp 192, fp32"),
+    "B": dict(model="ESMStereo", backbone="efficientnet_b2", cv=4, H=384, W=1248, batch=1,
+              metric="stereo pairs/sec @384x1248 maxdisp192",
+              workload="ESMStereo-L (cv_scale 4, gwc, efficientnet_b2 stand-in backbone) 384x1248 pair, batch 1 per GPU, maxdisp 192, fp32"),
+    "C": dict(model="ESMStereo", backbone="efficientnet_b2", cv=4, H=544, W=960, batch=8,
+              metric="stereo pairs/sec @544x960 maxdisp192 batch 8",
+              workload="ESMStereo-L (cv_scale 4, gwc, efficientnet_b2 stand-in backbone) 544x960 pairs, batch 8 per GPU, maxdisp 192, fp32"),
+    "E": dict(model="ESMStereo_confidence", backbone="mobilenetv2_100", cv=16, H=992, W=1472, batch=1,
+              metric="stereo pairs/sec @992x1472 maxdisp192 with confidence",
+              workload="ESMStereo_confidence (cv_scale 16, gwc, mobilenetv2_100 stand-in backbone) 992x1472 pair, batch 1 per GPU, maxdisp 192, fp32"),
+}
 
 
 def parse():
@@ -35,33 +51,46 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="B", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="pairs per step per GPU (default: the configuration's)")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-operator timing table to stderr")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true", help="skip the parity check, the GPU-eager baseline and the kernel rooflines")
+    a = ap.parse_args()
+    a.cfg = dict(CONFIGS[a.config])
+    if a.batch > 0:
+        a.cfg["batch"] = a.batch
+        a.cfg["workload"] = a.cfg["workload"].replace("batch %d per GPU" % CONFIGS[a.config]["batch"], "batch %d per GPU" % a.batch)
+    return a
 
 
-def build_weights(seed=0):
+def build_weights(cfg, seed=0):
     import torch  # noqa: F401
     from esmstereo_b200 import __models__
     from esmstereo_b200.weights import fill_deterministic
     with contextlib.redirect_stdout(io.StringIO()):
-        model = __models__["ESMStereo"](MAXDISP, True, False, "efficientnet_b2", 4)
+        model = __models__[cfg["model"]](MAXDISP, True, False, cfg["backbone"], cfg["cv"])
     sd = fill_deterministic(model.state_dict(), seed=seed)
     model.load_state_dict(sd)
     return model, sd
 
 
+def make_oracle(cfg, sd, device="cpu"):
+    from oracle.esm_oracle import EsmOracle
+    return EsmOracle(sd, MAXDISP, True, False, cfg["backbone"], cfg["cv"], confidence=cfg["model"] == "ESMStereo_confidence", device=device)
+
+
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference forward, all host threads
 # ----------------------------------------------------------------------------------------------
-def cpu_forward_rate(sd, budget_s, min_iters=2):
+def cpu_forward_rate(cfg, sd, budget_s, min_iters=2):
+    """Bounded sample of the same workload on the host cores: forwards of ONE pair of the configuration's shape."""
     import torch
     from esmstereo_b200.weights import synthetic_pair
-    from oracle.esm_oracle import EsmOracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    orc = EsmOracle(sd, MAXDISP, True, False, "efficientnet_b2", 4)
-    left, right = synthetic_pair(1, H, W, shift=23, seed=0)
+    orc = make_oracle(cfg, sd)
+    left, right = synthetic_pair(1, cfg["H"], cfg["W"], shift=23, seed=0)
     orc(left, right)  # warm-up
     times = []
     t_end = time.perf_counter() + budget_s
@@ -77,28 +106,38 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    _, sd = build_weights()
+    cfg = args.cfg
+    _, sd = build_weights(cfg)
     import torch
     from esmstereo_b200.weights import synthetic_pair
-    from oracle.esm_oracle import EsmOracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    orc = EsmOracle(sd, MAXDISP, True, False, "efficientnet_b2", 4)
-    left, right = synthetic_pair(1, H, W, shift=23, seed=0)
-    steps = max(1, min(args.steps, 20))      # bounded sample: a CPU forward is ~1 s
-    warm = max(1, min(args.warmup, 3))
-    for _ in range(warm):
+    orc = make_oracle(cfg, sd)
+    B = cfg["batch"]
+    left, right = synthetic_pair(B, cfg["H"], cfg["W"], shift=23, seed=0)
+    t0 = time.perf_counter()
+    orc(left, right)  # first warm-up, also the estimate that bounds the sample
+    est = time.perf_counter() - t0
+    # honour --warmup / --steps unless the whole run would exceed ~4 minutes of CPU work
+    budget = 240.0
+    warm = max(1, args.warmup)
+    steps = max(1, args.steps)
+    if (warm + steps) * est > budget:
+        warm = max(1, min(warm, int(0.2 * budget / est)))
+        steps = max(1, int((budget - warm * est) / est))
+    for _ in range(warm - 1):
         orc(left, right)
     t0 = time.perf_counter()
     for _ in range(steps):
         orc(left, right)
     dt = time.perf_counter() - t0
-    value = steps / dt
-    sample = "%d forwards of one 384x1248 pair (of the %d steps asked), torch-CPU fp32, %d threads" % (steps, args.steps, cores)
+    value = steps * B / dt
+    sample = "%d forwards of one batch of %d %dx%d pair(s) (%d steps asked), torch-CPU fp32, %d threads" % (
+        steps, B, cfg["H"], cfg["W"], args.steps, cores)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
+        "impl": "reference", "metric": cfg["metric"], "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "arm": "CPU oracle port of the reference forward"},
+        "dtype": "f32", "data": "synthetic", "config": {"workload": cfg["workload"]},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -175,77 +214,85 @@ def time_kernel(fn, flush, iters=20, warm=3):
     return sum(ts) / len(ts)
 
 
-def kernel_rooflines(model, peaks):
-    """Achieved algorithmic bytes / FLOPs per launch for the kernels BASELINE.json names."""
+def kernel_rooflines(model, peaks, cfg):
+    """Achieved algorithmic bytes / FLOPs per launch for the kernels BASELINE.json names, at the configuration's
+    cost-volume extent (one pair)."""
     import torch
-    from esmstereo_b200 import ops
-    h, w, D, C, G = H // 4, W // 4, MAXDISP // 4, 64, 32
+    from esmstereo_b200 import _lib, ops
+    s = cfg["cv"]
+    h, w, D, C, G = cfg["H"] // s, cfg["W"] // s, MAXDISP // s, 64, 32
+    H, W = cfg["H"], cfg["W"]
     dev = torch.device("cuda")
     g = torch.Generator(device="cpu").manual_seed(0)
     L = torch.randn(1, C, h, w, generator=g).to(dev)
     R = torch.randn(1, C, h, w, generator=g).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    hbm, fp32_peak = peaks["hbm_gbs"], peaks["fp32_tflops"]
+    hbm, fp32_peak, tf32_peak = peaks["hbm_gbs"], peaks["fp32_tflops"], peaks["tf32_tflops"]
     out = {}
-    # cost volume, standalone (K1): 4*(2*C*h*w + G*D*h*w) bytes
     t = time_kernel(lambda: ops.build_gwc_volume(L, R, D, G), flush)
     by = 4.0 * (2 * C * h * w + G * D * h * w)
     out["gwc_volume"] = {"bound": "hbm", "achieved": by / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / t / 1e9 / hbm,
                          "traffic": None, "us": t * 1e6, "algorithmic_bytes": by}
-    # The conv family runs on tcgen05 (split-TF32, conv_tc.cu) where that wins the on-device timing, else on
-    # the FP32 pipe.  Whichever path a layer took decides the roofline it is held against: "tensor" = dense
-    # TF32 peak = half of the measured bf16 burst peak (kind::tf32 runs at half the bf16 rate; MEASURED_PEAKS
-    # has no separate TF32 figure), "fp32" = the FFMA rate measured on this pool.  `achieved` counts the
-    # ALGORITHMIC FLOPs (2*Cout*Cin*taps*voxels); the split executes 3 MMAs per product, reported separately.
-    from esmstereo_b200 import _lib
-    tc_count, tcg_count = _lib.lib().esm_tc_conv_launches, _lib.lib().esm_tcg_conv_launches
-    tf32_peak = peaks["bf16_tflops"] / 2.0
+    # The conv family runs on tcgen05 (split-TF32) where that wins, else on the FP32 pipe.  Whichever path a layer
+    # took decides the roofline it is held against: "tensor" = the dense TF32 rate MEASURED in this run
+    # (esm_umma_tf32_peak: every SM issuing M128 x N256 x K8 MMAs), "fp32" = the FFMA rate measured on this pool.
+    # `achieved` counts ALGORITHMIC FLOPs (2*Cout*Cin*taps*voxels); the split executes 3 (or 2 wider) MMAs per product.
+    lib = _lib.lib()
+    counters = {"resident tcgen05 (conv_tc.cu)": lib.esm_tc_conv_launches, "streamed tcgen05 (conv_tcg.cu)": lib.esm_tcg_conv_launches,
+                "flat TMA-fed tcgen05 (conv_tcf.cu)": lib.esm_tcf_conv_launches}
 
     def conv_entry(fn, fl, by):
-        n0, g0 = tc_count(), tcg_count()
+        before = {k: c() for k, c in counters.items()}
         fn()
-        on_tcg = tcg_count() > g0
-        on_tc = on_tcg or tc_count() > n0
+        path = [k for k, c in counters.items() if c() > before[k]]
+        on_tc = bool(path)
         t = time_kernel(fn, flush)
         peak = tf32_peak if on_tc else fp32_peak
-        path = "tcgen05 split-TF32, streamed weights (conv_tcg.cu)" if on_tcg else "tcgen05 split-TF32, resident weights (conv_tc.cu)"
-        e = {"bound": "tensor" if on_tc else "fp32", "path": path if on_tc else "fp32 pipe",
+        e = {"bound": "tensor" if on_tc else "fp32", "path": (path[0] + ", split-TF32") if on_tc else "fp32 pipe",
              "achieved": fl / t / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / peak, "traffic": None,
              "us": t * 1e6, "algorithmic_flops": fl, "algorithmic_bytes": by}
         if on_tc:
             e["executed_mma_tflops"] = 3 * fl / t / 1e12  # hi*hi + lo*hi + hi*lo
         return e
 
-    # fused volume + group_stem (K1 fused into K2): 2*8*32*27*voxels FLOPs, 4*(2*C + 8*D)*h*w bytes
     pc = model.group_stem.packed()
-    out["gwc_group_stem_fused"] = conv_entry(lambda: ops.conv([L, R], pc, "gelu", gwc_disp=D), 2.0 * 8 * 32 * 27 * D * h * w,
-                                             4.0 * (2 * C + 8 * D) * h * w)
-    # agg (a4): 8 -> 8 k3 at full cost-volume resolution; aggregation.conv1.1 (a5): 24 -> 24 k3 at half resolution
+    att = torch.rand(1, G, h, w, generator=g).to(dev) if s == 16 else None
+    fp32_only = model.group_stem.fp32_only
+    out["gwc_group_stem_fused"] = conv_entry(lambda: ops.conv([L, R], pc, "gelu", gwc_disp=D, in_mul=att, fp32_only=fp32_only),
+                                             2.0 * 8 * 32 * 27 * D * h * w, 4.0 * (2 * C + 8 * D) * h * w)
     x8 = torch.randn(1, 8, D, h, w, generator=g).to(dev)
     pa = model.agg.packed()
-    out["agg_conv3d_8_8"] = conv_entry(lambda: ops.conv(x8, pa, "gelu"), 2.0 * 8 * 8 * 27 * D * h * w, 4.0 * 16 * D * h * w)
-    x24 = torch.randn(1, 24, D // 2, h // 2, w // 2, generator=g).to(dev)
-    p24 = model.aggregation_out.conv1[1].packed()
-    out["hourglass_conv3d_24_24"] = conv_entry(lambda: ops.conv(x24, p24, "gelu"), 2.0 * 24 * 24 * 27 * (D // 2) * (h // 2) * (w // 2),
-                                               4.0 * 48 * (D // 2) * (h // 2) * (w // 2))
-    # the wide hourglass level (a5): 40 -> 40 k3 at quarter resolution, and its ConvTranspose3d k4 s2 40 -> 24
-    x40 = torch.randn(1, 40, D // 4, h // 4, w // 4, generator=g).to(dev)
-    p40 = model.aggregation_out.conv2[1].packed()
-    v40 = (D // 4) * (h // 4) * (w // 4)
-    out["hourglass_conv3d_40_40"] = conv_entry(lambda: ops.conv(x40, p40, "gelu"), 2.0 * 40 * 40 * 27 * v40, 4.0 * 80 * v40)
-    pup = model.aggregation_out.conv2_up.packed()
-    out["hourglass_deconv3d_40_24"] = conv_entry(lambda: ops.conv(x40, pup, "gelu"), 2.0 * 40 * 24 * 64 * v40, 4.0 * (40 + 8 * 24) * v40)
-    # regression (K4): 4*(D+1)*h*w bytes
+    out["agg_conv3d_8_8"] = conv_entry(lambda: ops.conv(x8, pa, "gelu", fp32_only=fp32_only), 2.0 * 8 * 8 * 27 * D * h * w, 4.0 * 16 * D * h * w)
+    agg = model.aggregation_out
+    c1, c2 = agg.conv1[1].conv.weight.shape[0], agg.conv2[1].conv.weight.shape[0]
+    d2, h2, w2 = (D - 1) // 2 + 1, (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    x1 = torch.randn(1, c1, d2, h2, w2, generator=g).to(dev)
+    p1 = agg.conv1[1].packed()
+    v1 = d2 * h2 * w2
+    out["hourglass_conv3d_level1"] = conv_entry(lambda: ops.conv(x1, p1, "gelu", fp32_only=fp32_only), 2.0 * c1 * c1 * 27 * v1, 4.0 * 2 * c1 * v1)
+    d4, h4, w4 = (d2 - 1) // 2 + 1, (h2 - 1) // 2 + 1, (w2 - 1) // 2 + 1
+    x2 = torch.randn(1, c2, d4, h4, w4, generator=g).to(dev)
+    p2 = agg.conv2[1].packed()
+    v2 = d4 * h4 * w4
+    out["hourglass_conv3d_level2"] = conv_entry(lambda: ops.conv(x2, p2, "gelu", fp32_only=fp32_only), 2.0 * c2 * c2 * 27 * v2, 4.0 * 2 * c2 * v2)
+    pup = agg.conv2_up.packed()
+    out["hourglass_deconv3d_level2"] = conv_entry(lambda: ops.conv(x2, pup, "gelu", out_size=(d2, h2, w2), fp32_only=fp32_only),
+                                                  2.0 * c2 * c1 * 64 * v2, 4.0 * (c2 + 8 * c1) * v2)
     cost = torch.randn(1, D, h, w, generator=g).to(dev)
-    t = time_kernel(lambda: ops.regression_top2(cost), flush)
+    if s == 4:
+        t = time_kernel(lambda: ops.regression_top2(cost), flush)
+        name = "regression_top2"
+    else:
+        t = time_kernel(lambda: ops.disparity_regression(cost, D), flush)
+        name = "disparity_regression"
     by = 4.0 * (D + 1) * h * w
-    out["regression_top2"] = {"bound": "hbm", "achieved": by / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / t / 1e9 / hbm,
-                              "traffic": None, "us": t * 1e6, "algorithmic_bytes": by}
-    # final assembly (a11): read residual HxW + previous H/2xW/2, write HxW
-    prev = torch.randn(1, 1, H // 2, W // 2, generator=g).to(dev)
+    out[name] = {"bound": "hbm", "achieved": by / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / t / 1e9 / hbm,
+                 "traffic": None, "us": t * 1e6, "algorithmic_bytes": by}
+    r = model.upsample_module.r
+    prev = torch.randn(1, 1, H // r, W // r, generator=g).to(dev)
     res = torch.randn(1, 1, H, W, generator=g).to(dev)
-    t = time_kernel(lambda: ops.bilinear_add(prev, res, 2, 4.0), flush)
-    by = 4.0 * (H * W + H * W / 4 + H * W)
+    t = time_kernel(lambda: ops.bilinear_add(prev, res, r, 4.0), flush)
+    by = 4.0 * (H * W + H * W / (r * r) + H * W)
     out["bilinear_add_final"] = {"bound": "hbm", "achieved": by / t / 1e9, "peak": hbm, "unit": "GB/s",
                                  "frac": by / t / 1e9 / hbm, "traffic": None, "us": t * 1e6, "algorithmic_bytes": by}
     return out
@@ -260,7 +307,77 @@ def load_peaks():
         peaks.update(hbm_gbs=m["hbm_gbs"], bf16_tflops=m["bf16_tflops"], source="MEASURED_PEAKS.json")
     # FP32 FMA-pipe peak measured on this pool's B200 with scratch/fma_bench.cu (scalar FFMA, 148 SMs): 72.7 TFLOP/s
     peaks["fp32_tflops"] = 72.7
+    # dense TF32 tensor rate: measured live (every SM issuing M128 x N256 x K8 tcgen05.mma back to back)
+    from esmstereo_b200 import _lib
+    tf = ctypes.c_float(0.0)
+    _lib.check(_lib.lib().esm_umma_tf32_peak(16384, ctypes.byref(tf), None), "umma_tf32_peak")
+    peaks["tf32_tflops"] = float(tf.value)
+    peaks["tf32_source"] = "measured in this run (esm_umma_tf32_peak, csrc/peak.cu)"
     return peaks
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU-eager baseline: the oracle port (same torch ops as the reference) on the same B200 through cuDNN / ATen
+# ----------------------------------------------------------------------------------------------
+def gpu_eager_baseline(cfg, sd, dev, reps=30):
+    """"the real bar on the same box" -- the reference's PyTorch-eager path on this GPU.  The
+    oracle port issues the same ATen / cuDNN calls as the reference's modules; protocol of train_sceneflow.py:254-275
+    (10 warm-ups, CUDA events around the timed forwards), with cuDNN's TF32 off (fp32-grade, our parity mode) and on
+    (PyTorch's default for convolutions)."""
+    import torch
+    from esmstereo_b200.weights import synthetic_pair
+    orc = make_oracle(cfg, sd, device=dev)
+    B = cfg["batch"]
+    left, right = [t.to(dev) for t in synthetic_pair(B, cfg["H"], cfg["W"], shift=23, seed=0)]
+    out = {"protocol": "10 warm-ups + %d timed eager forwards, CUDA events (train_sceneflow.py:254-275)" % reps, "kind": "oracle port on cuda (ATen/cuDNN)"}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for name, tf32 in (("tf32_off", False), ("tf32_on", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            for _ in range(10):
+                orc(left, right)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                orc(left, right)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            out[name] = {"ms_per_step": ms, "pairs_per_s": B / ms * 1e3}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return out
+
+
+def parity_check(cfg, model, orc, dev):
+    """End-to-end parity of THIS run's model against the CPU oracle on one pair of the configuration's shape:
+    EPE, top-2 index flips (cv4), cost error, confidence error (config E)."""
+    import torch
+    from esmstereo_b200.weights import synthetic_pair
+    left, right = synthetic_pair(1, cfg["H"], cfg["W"], shift=23, seed=7)
+    want = orc(left, right)
+    model.capture = {}
+    with torch.no_grad():
+        if cfg["model"] == "ESMStereo_confidence":
+            disp, conf = model(left.to(dev), right.to(dev))
+        else:
+            disp, conf = model(left.to(dev), right.to(dev), train_status=False)[-1], None
+    cap = model.capture
+    model.capture = None
+    out = {"sample": "one %dx%d pair, CPU fp32 oracle vs this run's engines" % (cfg["H"], cfg["W"]),
+           "epe_px": float((disp.cpu() - want["disp"]).abs().mean()),
+           "cost_rel_err": float((cap["cost"].cpu() - want["cost"]).abs().max() / want["cost"].abs().max())}
+    if "top2_idx" in want and "top2_idx" in cap:
+        a = torch.sort(cap["top2_idx"].cpu().to(torch.int64), 1)[0]
+        b = torch.sort(want["top2_idx"].to(torch.int64), 1)[0]
+        out["top2_flips"] = int((a != b).any(1).sum())
+        out["pixels"] = int(a.shape[0] * a.shape[2] * a.shape[3])
+    if conf is not None:
+        out["conf_max_abs_err"] = float((conf.cpu() - want["conf"]).abs().max())
+        out["conf_mean_abs_err"] = float((conf.cpu() - want["conf"]).abs().mean())
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -269,9 +386,12 @@ def load_peaks():
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from esmstereo_b200 import GraphedStereo, ops  # noqa: F401
+    from esmstereo_b200 import GraphedStereo, StereoPipeline, _lib, ops, shard
     from esmstereo_b200.weights import synthetic_pair
 
+    cfg = args.cfg
+    H, W, B = cfg["H"], cfg["W"], cfg["batch"]
+    conf_model = cfg["model"] == "ESMStereo_confidence"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -279,28 +399,63 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    extras = rank == 0 and world == 1 and not args.no_extras
+    model, sd = build_weights(cfg)
+
+    # ---- CPU baseline FIRST (before any GPU work shares the host with it), then BN calibration for the parity check
+    cpu = orc = None
+    if rank == 0 and world == 1:
+        rate, cores, n, med = cpu_forward_rate(cfg, sd, args.cpu_seconds)
+        cpu = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
+               "sample": "%d forwards of ONE %dx%d pair of this workload (median %.0f ms), taken before any GPU work; oracle port of the "
+                         "reference forward, torch-CPU fp32" % (n, H, W, med * 1e3)}
+    if extras:
+        orc = make_oracle(cfg, sd)
+        cl, cr = synthetic_pair(1, H, W, shift=23, seed=0)
+        sd = orc.calibrate(cl, cr)  # random-init costs are otherwise +-3e-6 and parity is meaningless
+        model.load_state_dict(sd)
+
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    model, sd = build_weights()
     model = model.to(dev).eval()
+    fwd_kw = {} if conf_model else {"train_status": False}
 
-    # rotating pool of distinct input pairs larger than L2 (16 x 11.5 MB = 184 MB > 126 MB)
-    NPOOL = 16
-    pool = [tuple(t.to(dev) for t in synthetic_pair(1, H, W, shift=23, seed=100 + rank * NPOOL + i)) for i in range(NPOOL)]
+    # rotating pool of distinct input batches larger than L2 (126 MB)
+    per_batch = 2 * 3 * H * W * 4 * B
+    NPOOL = max(2, min(16, -(-160_000_000 // per_batch)))
+    pool = [tuple(t.to(dev) for t in synthetic_pair(B, H, W, shift=23, seed=100 + rank * NPOOL + i)) for i in range(NPOOL)]
+    tuned0 = _lib.lib().esm_conv_tuned_calls()
     ops.LAUNCHES = 0
-    model(*pool[0], train_status=False)
+    model(*pool[0], **fwd_kw)
     launches_per_step = ops.LAUNCHES
-    graphed = GraphedStereo(model, (1, 3, H, W), train_status=False)
-    gathered = torch.empty(world, H, W, device=dev) if world > 1 else None
+    graphed = GraphedStereo(model, (B, 3, H, W), **fwd_kw)
+    tuned_calls = _lib.lib().esm_conv_tuned_calls() - tuned0
+    pick = (lambda out: out[0]) if conf_model else (lambda out: out[-1])
+
+    # the only collective: gather of the per-rank disparities, issued on a side stream every GATHER_EVERY steps so that
+    # it overlaps the next replays ("once per sweep, on a side stream")
+    GATHER_EVERY = 8
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    stash = torch.empty(GATHER_EVERY * B, H, W, device=dev) if world > 1 else None
+    gather_ev = torch.cuda.Event() if world > 1 else None
 
     def step(i):
-        out = graphed(*pool[i % NPOOL])[-1]
-        if world > 1:  # the only collective: gather of the per-rank disparities (no data-path exchange)
-            dist.all_gather_into_tensor(gathered, out[0])
+        out = pick(graphed(*pool[i % NPOOL]))
+        if world > 1:
+            j = i % GATHER_EVERY
+            if j == 0 and i > 0:
+                torch.cuda.current_stream().wait_event(gather_ev)  # the side stream has read the previous sweep
+            stash[j * B:(j + 1) * B].copy_(out)
+            if j == GATHER_EVERY - 1:
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    shard.gather_disparities(stash, world * GATHER_EVERY * B, rank, world)
+                    gather_ev.record(side)
         return out
 
     def barrier():
         if world > 1:
+            torch.cuda.synchronize()
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -315,17 +470,18 @@ def run_ours(args):
         e0.record()
         for i in range(K):
             step(i)
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(side)
         e1.record()
         barrier()
         torch.cuda.profiler.stop()
         t_dev = e0.elapsed_time(e1) * 1e-3
 
         # ---- end to end through the public API with HOST buffers: every step copies both images from pinned
-        # host memory to the device and the disparity back to pinned host memory, and the host reads each
+        # host memory to the device and the result(s) back to pinned host memory, and the host reads each
         # result; `StereoPipeline` overlaps the copies of neighbouring steps with the graph replay.
-        from esmstereo_b200 import StereoPipeline
-        hl = [tuple(t.pin_memory() for t in synthetic_pair(1, H, W, shift=23, seed=200 + rank * 4 + i)) for i in range(4)]
-        pipe = StereoPipeline(graphed, depth=2)
+        hl = [tuple(t.pin_memory() for t in synthetic_pair(B, H, W, shift=23, seed=200 + rank * 4 + i)) for i in range(4)]
+        pipe = StereoPipeline(graphed, depth=2, pick=(lambda out: torch.stack(out)) if conf_model else pick)
         checksum = 0.0
 
         def e2e_run(n):
@@ -333,8 +489,8 @@ def run_ours(args):
             for i in range(n):
                 pipe.submit(*hl[i % 4])
                 if i >= 1:
-                    checksum += float(pipe.result()[0, 0, 0])  # the caller reads every result
-            checksum += float(pipe.result()[0, 0, 0])
+                    checksum += float(pipe.result().reshape(-1)[0])  # the caller reads every result
+            checksum += float(pipe.result().reshape(-1)[0])
 
         e2e_run(W_)
         barrier()
@@ -346,59 +502,66 @@ def run_ours(args):
         t_e2e = max(e0.elapsed_time(e1) * 1e-3, 0.0)
         t_e2e_wall = time.perf_counter() - t0
     times = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+    spread = None
     if world > 1:
+        allt = [torch.zeros_like(times) for _ in range(world)]
+        dist.all_gather(allt, times)
+        per_rank = [float(t[0]) for t in allt]
+        spread = {"ms_per_step_min": 1e3 * min(per_rank) / K, "ms_per_step_max": 1e3 * max(per_rank) / K}
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = float(times[0]), float(times[1])
 
     if rank == 0:
-        peaks = load_peaks()
-        kr = kernel_rooflines(model, peaks)
-        ncu_path = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(ncu_path):  # dram bytes per launch from the committed `ncu --set full` capture
-            with open(ncu_path) as f:
-                for k, v in json.load(f).items():
-                    if k in kr:
-                        kr[k]["traffic"] = v
-        breakdown = None
-        if args.breakdown:
-            breakdown = op_breakdown(model, pool[0])
-        cpu = None
-        if world == 1:
-            rate, cores, n, med = cpu_forward_rate(sd, args.cpu_seconds)
-            cpu = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
-                   "sample": "%d forwards of the same 384x1248 pair workload (median %.0f ms), oracle port of the reference "
-                             "forward, torch-CPU fp32" % (n, med * 1e3)}
-        dominant = kr["gwc_group_stem_fused"]
+        d2h = H * W * 4 * B * (2 if conf_model else 1)
         line = {
-            "metric": METRIC, "value": world * K / t_dev, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W_,
+            "metric": cfg["metric"], "value": world * K * B / t_dev, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W_,
             "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "l2": "%d rotating input pairs (%.0f MB) > 126 MB L2"
-                       % (NPOOL, NPOOL * 2 * 3 * H * W * 4 / 1e6), "cuda_graph": True, "parallelism": "pairs sharded by rank"},
+            "config": {"workload": cfg["workload"], "name": args.config, "pairs_per_step_per_gpu": B,
+                       "l2": "%d rotating input batches (%.0f MB) > 126 MB L2" % (NPOOL, NPOOL * per_batch / 1e6), "cuda_graph": True,
+                       "parallelism": "pairs sharded by rank",
+                       "gather": "NCCL all-gather of the disparities every %d steps on a side stream" % GATHER_EVERY if world > 1 else None},
             "clocks": clk.summary(),
-            "e2e": {"value": world * K / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": 2 * 3 * H * W * 4,
-                    "d2h_bytes_per_step": H * W * 4, "ms_per_step": 1e3 * t_e2e / K, "wall_ms_per_step": 1e3 * t_e2e_wall / K},
+            "e2e": {"value": world * K * B / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": per_batch,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / K, "wall_ms_per_step": 1e3 * t_e2e_wall / K},
             "gpu_launches": launches_per_step * K,
             "gpu_launches_per_step": launches_per_step,
-            "roofline": {k: dominant[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")},
-            "roofline_note": "dominant kernel = fused gwc-volume + group_stem conv3d (19.9 GFLOP/launch, the largest single "
-                             "launch of the step) on the path the autotuner chose (%s); tensor peak = dense TF32 = measured bf16 "
-                             "burst / 2, fp32 peak = FFMA rate measured on this pool (scratch/fma_bench.cu); peaks from %s; "
-                             "`achieved` counts algorithmic FLOPs, the fp32-grade split issues 3 MMAs per product (DESIGN.md)"
-                             % (dominant.get("path", "?"), peaks["source"]),
-            "kernels": kr,
-            "cost_volume_hbm_gbs": kr["gwc_volume"]["achieved"],
+            "autotune_calls": int(tuned_calls),
             "cpu_baseline": cpu,
         }
-        if breakdown is not None:
-            line["breakdown_ms"] = breakdown
+        if spread:
+            line["rank_spread"] = spread
+        if extras:
+            peaks = load_peaks()
+            kr = kernel_rooflines(model, peaks, cfg)
+            ncu_path = os.path.join(ROOT, "profiles", "traffic.json")
+            if args.config == "B" and os.path.exists(ncu_path):  # dram bytes per launch from the committed `ncu --set full` capture
+                with open(ncu_path) as f:
+                    for k, v in json.load(f).items():
+                        if k in kr:
+                            kr[k]["traffic"] = v
+            dominant = kr["gwc_group_stem_fused"]
+            line["roofline"] = {k: dominant[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+            line["roofline_note"] = ("dominant kernel = fused gwc-volume + group_stem conv3d (the largest single launch of the hot path) "
+                                     "on the path %s; tensor peak = dense TF32 rate measured in this run (%.0f TFLOP/s: every SM issuing M128 x "
+                                     "N256 x K8 tcgen05.mma), fp32 peak = FFMA rate measured on this pool (scratch/fma_bench.cu); HBM peak from "
+                                     "%s; `achieved` counts algorithmic FLOPs, the fp32-grade split issues 3 MMAs per product (DESIGN.md); "
+                                     "`traffic` = dram bytes per launch from the committed ncu --set full capture (profiles/)"
+                                     % (dominant.get("path", "?"), peaks["tf32_tflops"], peaks["source"]))
+            line["peaks"] = peaks
+            line["kernels"] = kr
+            line["cost_volume_hbm_gbs"] = kr["gwc_volume"]["achieved"]
+            line["parity"] = parity_check(cfg, model, orc, dev)
+            line["gpu_eager_baseline"] = gpu_eager_baseline(cfg, sd, dev)
+        if args.breakdown:
+            line["breakdown_ms"] = op_breakdown(model, pool[0], fwd_kw)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def op_breakdown(model, pair):
+def op_breakdown(model, pair, fwd_kw):
     """Eager-mode per-operator device times (CUDA events), for profiling only."""
     import torch
     from esmstereo_b200 import ops
@@ -407,30 +570,15 @@ def op_breakdown(model, pair):
     torch.cuda.synchronize()
     torch.cuda._sleep(60_000_000)  # keep the GPU busy (~30 ms) so the host runs ahead: event gaps are then pure device time
     e0.record()
-    model(*pair, train_status=False)
+    model(*pair, **fwd_kw)
     e1.record()
     torch.cuda.synchronize()
     rows = [(lbl, a.elapsed_time(b)) for lbl, a, b in ops.PROFILE]
     ops.PROFILE = None
     total_ops = sum(t for _, t in rows)
     sys.stderr.write("---- per-operator device time (eager forward queued behind a busy GPU: pure device time) ----\n")
-    import re
     for lbl, t in rows:
-        m = re.match(r"(de)?conv(\d)d (\d+)->(\d+) k(\d)(\+gwc)? s(\d) in (\d+)x(\d+)x(\d+)", lbl)
-        extra = ""
-        if m:
-            dec, nd, cin, cout, k, _g, st, D, Hh, Ww = m.groups()
-            nd, cin, cout, k, st, D, Hh, Ww = int(nd), int(cin), int(cout), int(k), int(st), int(D), int(Hh), int(Ww)
-            taps = k ** nd
-            vox = D * Hh * Ww  # input voxels
-            if dec:
-                fl = 2.0 * cin * cout * taps * vox
-            else:
-                out_vox = vox / (st ** nd) if st > 1 else vox
-                fl = 2.0 * cin * cout * taps * out_vox
-            fl *= pair[0].shape[0] * (2 if lbl.startswith("conv2d 3->") or False else 1)
-            extra = "  %6.2f GFLOP %5.1f TFLOP/s" % (fl / 1e9, fl / (t * 1e-3) / 1e12)
-        sys.stderr.write("%8.1f us  %s%s\n" % (t * 1e3, lbl, extra))
+        sys.stderr.write("%8.1f us  %s\n" % (t * 1e3, lbl))
     sys.stderr.write("hot-path ops total %.3f ms; forward wall (eager) %.3f ms\n" % (total_ops, e0.elapsed_time(e1)))
     agg = {}
     for lbl, t in rows:

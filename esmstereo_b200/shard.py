@@ -29,9 +29,6 @@ def gather_disparities(local: torch.Tensor, n_pairs: int, rank: int, world: int)
     padded[: local.shape[0]] = local
     out = torch.empty((world,) + shape, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out.view(world * per_rank, *shape[1:]), padded)
-    full = torch.empty((n_pairs,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    for r in range(world):
-        idx = shard_indices(n_pairs, r, world)
-        if idx:
-            full[torch.tensor(idx, device=local.device)] = out[r, : len(idx)]
-    return full
+    # pair i = j * world + r sits at out[r, j]: a transpose puts the pairs in dataset order and the padding of the
+    # shorter ranks (i >= n_pairs) at the tail -- no index tensors, no host synchronisation
+    return out.transpose(0, 1).reshape((world * per_rank,) + tuple(local.shape[1:]))[:n_pairs]

@@ -31,9 +31,11 @@ class EsmOracle:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], maxdisp: int = 192, gwc: bool = False,
                  norm_correlation: bool = True, backbone: str = "efficientnet_b2", cv_scale: int = 4,
-                 confidence: bool = False, dtype: torch.dtype = torch.float32) -> None:
-        self.dtype = dtype
-        self.sd = {k: (v.detach().to("cpu").to(dtype) if v.is_floating_point() else v.detach().cpu())
+                 confidence: bool = False, dtype: torch.dtype = torch.float32, device="cpu") -> None:
+        # device: "cpu" for the oracle proper; bench.py's `gpu_eager_baseline` runs the same torch calls on "cuda" to time
+        # the reference's eager ATen / cuDNN path on the box's GPU (a baseline, never the product)
+        self.dtype, self.device = dtype, torch.device(device)
+        self.sd = {k: (v.detach().to(self.device).to(dtype) if v.is_floating_point() else v.detach().to(self.device))
                    for k, v in state_dict.items()}
         self.maxdisp, self.gwc, self.ncorr = maxdisp, gwc, norm_correlation
         self.backbone, self.s, self.confidence = backbone, cv_scale, confidence
@@ -236,7 +238,7 @@ class EsmOracle:
     def disparity_regression(cost: torch.Tensor) -> torch.Tensor:
         """`disparity_regression` (`submodule.py:211-216`) -- NO softmax (callers `ESMStereo.py:725,730`)."""
         D = cost.shape[1]
-        dv = torch.arange(0, D, dtype=cost.dtype).view(1, D, 1, 1)
+        dv = torch.arange(0, D, dtype=cost.dtype, device=cost.device).view(1, D, 1, 1)
         return torch.sum(cost * dv, 1, keepdim=True)
 
     # ------------------------------------------------------------------ hot path: ShuffleMixer upsampler
@@ -356,19 +358,19 @@ class EsmOracle:
         # sampling grid :695-715 -- note y offsets are +-scale in normalised units, x offsets use
         # step_y = 2/(w-1); `step_x` is computed but unused in the reference.
         gw, gh = np.meshgrid(np.linspace(-1, 1, w), np.linspace(-1, 1, h))
-        gw = torch.tensor(gw, dtype=torch.float32).to(self.dtype).view(1, h, w, 1).expand(b, h, w, 1)
-        gh = torch.tensor(gh, dtype=torch.float32).to(self.dtype).view(1, h, w, 1).expand(b, h, w, 1)
+        gw = torch.tensor(gw, dtype=torch.float32).to(self.dtype).to(self.device).view(1, h, w, 1).expand(b, h, w, 1)
+        gh = torch.tensor(gh, dtype=torch.float32).to(self.dtype).to(self.device).view(1, h, w, 1).expand(b, h, w, 1)
         grid = torch.cat((gw, gh), 3)
         st = scale.permute(0, 2, 3, 1)
         step_y = 2 / (w - 1)
-        big = torch.zeros(b, 3 * h, 3 * w, 2, dtype=self.dtype)
+        big = torch.zeros(b, 3 * h, 3 * w, 2, dtype=self.dtype).to(self.device)
         for iy, oy in enumerate((-1, 0, 1)):
             for ix, ox in enumerate((-1, 0, 1)):
                 big[:, iy::3, ix::3, :] = grid + torch.cat((ox * step_y * st, oy * st), 3)
         samp = F.grid_sample(feat, big, mode="bilinear", padding_mode="zeros", align_corners=True)
         feat = self._cbr(samp, p, "embed_conv2", "embed_bn2", 0, stride=3)
         out["conf_embed"] = feat
-        o = torch.zeros(b, c, h, w, dtype=self.dtype) + 0.5
+        o = torch.zeros(b, c, h, w, dtype=self.dtype).to(self.device) + 0.5
         for it in (1, 2, 3):  # shared convs, per-iteration BN :725-739
             t = self._cbr(torch.cat((feat, o), 1), p, "fusion_conv1", "fusion_bn1_iter%d" % it, 1)
             t = self._cbr(t, p, "fusion_conv2", "fusion_bn2_iter%d" % it, 1)
