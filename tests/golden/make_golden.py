@@ -41,6 +41,13 @@ CONFIGS = {
 }
 
 
+# BASELINE.json shapes, run through the real reference too; only samples of the big tensors are stored
+CONFIGS_FULL = {
+    "kitti_cv4_gwc": ("ESMStereo", True, False, "efficientnet_b2", 4, 384, 1248),
+    "conf16_gwc_full": ("ESMStereo_confidence", True, False, "mobilenetv2_100", 16, 992, 1472),
+}
+
+
 def sample(t: torch.Tensor, limit: int = 20000) -> np.ndarray:
     """Deterministic strided subsample of a big tensor (keeps fixtures small)."""
     flat = t.detach().reshape(-1)
@@ -48,7 +55,7 @@ def sample(t: torch.Tensor, limit: int = 20000) -> np.ndarray:
     return flat[::step].to(torch.float32).numpy().copy()
 
 
-def run(name, cfg):
+def run(name, cfg, sampled=False):
     model_name, gwc, ncorr, backbone, s, H, W = cfg
     models = importlib.import_module("models")
     mod = importlib.import_module("models." + model_name)  # the module, not the re-bound class
@@ -61,7 +68,7 @@ def run(name, cfg):
     sd = fill_deterministic(net.state_dict(), seed=0)
     net.load_state_dict(sd)
 
-    left, right = synthetic_pair(1, H, W, shift=7, seed=0)
+    left, right = synthetic_pair(1, H, W, shift=23 if sampled else 7, seed=0)
     # --- BN calibration: train mode, momentum 1.0
     for m in net.modules():
         if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
@@ -149,6 +156,23 @@ def run(name, cfg):
     blob["volume_abs_sum"] = np.array(vol.abs().double().sum().item())
     blob["stem_sample"] = sample(cap["stem"])
     blob["agg_sample"] = sample(cap["agg"])
+    if sampled:
+        # full-size configuration: strided samples instead of whole tensors (fixtures stay < 1 MB)
+        blob["cost_sample"] = sample(cap["cost"])
+        blob["cost_absmax"] = np.array(cap["cost"].abs().max().item())
+        blob["init_pred"] = up_in["init_pred"].numpy().astype(np.float32)
+        if "top2_idx" in cap:
+            blob["top2_idx"] = cap["top2_idx"].numpy().astype(np.int16)
+        blob["disp_q"] = out[:, ::4, ::4].numpy().astype(np.float32)
+        blob["disp_mean"] = np.array(out.double().mean().item())
+        if conf is not None:
+            blob["conf_q"] = conf[:, ::4, ::4].numpy().astype(np.float32)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
+        keys = {k: list(v.shape) for k, v in sd.items()}
+        with open(os.path.join(HERE, name + ".keys.json"), "w") as f:
+            json.dump({"config": list(cfg), "state_dict": keys}, f, indent=0, sort_keys=True)
+        print(name, "ok (sampled): disp mean %.4f" % float(out.mean()))
+        return
     blob["cost"] = cap["cost"].squeeze(1).numpy().astype(np.float32)
     blob["init_pred"] = up_in["init_pred"].numpy().astype(np.float32)
     if "top2_idx" in cap:
@@ -180,3 +204,9 @@ if __name__ == "__main__":
         if only and n not in only:
             continue
         run(n, c)
+    for n, c in CONFIGS_FULL.items():
+        if only and n not in only:
+            continue
+        if not only:
+            continue  # the full-size ones take a minute each: only on request (python make_golden.py kitti_cv4_gwc conf16_gwc_full)
+        run(n, c, sampled=True)

@@ -228,3 +228,17 @@ def test_host_pipeline_matches_direct_call():
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("engine", ["fp32", "resident", "streamed", "pointwise", "single_pass_off_flat"])
+def test_kitti_shape_vs_oracle_per_engine(engine, monkeypatch):
+    """The parity GPUTEST certifies must not depend on which engine a layer happened to take: the KITTI-shaped forward
+    is held to the same gates with every engine forced wherever it is eligible (and with the tensor cores off)."""
+    env = {"fp32": {"ESM_TC": "0"}, "resident": {"ESM_TC_FORCE": "1"}, "streamed": {"ESM_TC_FORCE": "2"},
+           "pointwise": {"ESM_TC_FORCE": "3"}, "single_pass_off_flat": {"ESM_TCF": "0"}}[engine]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    from esmstereo_b200 import ops
+    monkeypatch.setattr(ops, "TCF_RULE", env.get("ESM_TCF", "1") != "0")
+    m, orc, want, outs, _, _ = _full_size("ESMStereo", True, "efficientnet_b2", 4, 1, 384, 1248)
+    _check_cv4(m, want, outs)

@@ -598,3 +598,78 @@ def test_conv_thin_input_streaming(case, pw_forced):
     got = ops.conv(x.cuda(), gpu_pack(p, stride, pad, False), "gelu")
     assert pw_forced() == n0 + 1, "layer did not take the streaming kernel"
     assert got.shape == want.shape and rel(got, want) < 2e-5, name
+
+
+def test_laf_sample_embed_vs_grid_sample():
+    """LAFNet's scale-adaptive 3x3 sampling + embed_conv2 (k3, stride 3) + BN + ReLU, fused on the GPU, against the
+    reference's own formulation: a 3h x 3w `grid_sample(align_corners=True, zeros)` image convolved with stride 3
+    (ESMStereo_confidence.py:693-719; note the y offsets are +-scale and the x offsets scale * 2/(w-1))."""
+    import numpy as np
+    import torch.nn.functional as F
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    for (b, c, h, w) in ((1, 16, 13, 21), (2, 16, 6, 9)):
+        feat = torch.randn(b, c, h, w, generator=g)
+        scale = 2 * torch.sigmoid(torch.randn(b, 1, h, w, generator=g))
+        wt = torch.randn(c, c, 3, 3, generator=g) * 0.1
+        sc = 0.5 + torch.rand(c, generator=g)
+        sh = torch.randn(c, generator=g) * 0.1
+        gw, gh = np.meshgrid(np.linspace(-1, 1, w), np.linspace(-1, 1, h))
+        gw = torch.tensor(gw, dtype=torch.float32).view(1, h, w, 1).expand(b, h, w, 1)
+        gh = torch.tensor(gh, dtype=torch.float32).view(1, h, w, 1).expand(b, h, w, 1)
+        grid = torch.cat((gw, gh), 3)
+        st = scale.permute(0, 2, 3, 1)
+        step_y = 2 / (w - 1)
+        big = torch.zeros(b, 3 * h, 3 * w, 2)
+        for iy, oy in enumerate((-1, 0, 1)):
+            for ix, ox in enumerate((-1, 0, 1)):
+                big[:, iy::3, ix::3, :] = grid + torch.cat((ox * step_y * st, oy * st), 3)
+        samp = F.grid_sample(feat, big, mode="bilinear", padding_mode="zeros", align_corners=True)
+        want = F.relu(F.conv2d(samp, wt, None, stride=3) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+        got = ops.laf_sample_embed(feat.cuda(), scale.cuda(), wt.cuda().contiguous(), sc.cuda(), sh.cuda())
+        assert tuple(got.shape) == (b, c, h, w)
+        assert rel(got, want) < 2e-5, (b, c, h, w)
+
+
+@pytest.mark.parametrize("engine", ["resident", "streamed", "flat"])
+@pytest.mark.parametrize("dist", ["all_positive", "cancelling", "peaked"])
+def test_tensor_core_truncation_bias_beyond_gaussian(engine, dist, monkeypatch):
+    """The tcgen05 accumulator truncates toward zero on every accumulate; the epilogues undo the EXPECTED shrink
+    (1 + n * 1.25e-8, tc_common.cuh).  That constant was fitted on Gaussian data: this holds every tensor-core engine
+    to the FP32-pipe gate, and its mean SIGNED error to a bias bound, on the distributions where a fixed factor could
+    go wrong -- all-positive sums (post-GELU activations x positive weights: every accumulate shrinks), strongly
+    cancelling sums (the accumulator is small while the addends are large) and peaked inputs."""
+    import torch.nn.functional as F
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    cin = cout = 40
+    x = torch.randn(1, cin, 6, 12, 40, generator=g)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) * 0.03
+    if dist == "all_positive":
+        x, w = x.abs() + 0.1, w.abs() + 0.01
+    elif dist == "cancelling":
+        x = 100.0 + 0.01 * x                       # large common mode ...
+        w = w - w.mean(dim=(1, 2, 3, 4), keepdim=True)   # ... against zero-sum filters: outputs are O(1e-2) sums of O(100) terms
+    else:
+        x = 0.01 * x
+        x[:, 3, 2, 5, 17] = 50.0
+    want = F.conv3d(x.double(), w.double(), None, padding=1)
+    if engine == "flat":
+        pc = ops.pack_conv_pf(w.cuda(), [cin], 1, False, None)
+        got = ops.conv_pf([ops.to_pf(x.cuda())], pc, None, out="nchw")
+    else:
+        monkeypatch.setenv("ESM_TC_FORCE", "1" if engine == "resident" else "2")
+        pc = ops.pack_conv(w.cuda(), 1, 1, False, None, None)
+        got = ops.conv(x.cuda(), pc, None)
+    ref32 = ops.conv(x.cuda(), ops.pack_conv(w.cuda(), 1, 1, False, None, None), None, fp32_only=True)
+    scale_ = want.abs().max().item()
+    err = (got.double().cpu() - want).abs().max().item() / scale_
+    err32 = (ref32.double().cpu() - want).abs().max().item() / scale_
+    if dist == "cancelling":
+        # the inputs themselves carry 100 * 2^-24 of representation noise per term; compare with the FP32 pipe instead of a fixed gate
+        assert err <= 4 * err32 + 1e-6, (err, err32)
+    else:
+        assert err < 2e-5, (err, err32)
+    interior = want.abs() > 0.05 * scale_
+    bias = ((got.double().cpu() - want)[interior] / want[interior]).mean().item()
+    assert abs(bias) < 2e-6, "mean signed relative error %g (truncation bias not compensated)" % bias
