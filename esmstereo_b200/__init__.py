@@ -10,9 +10,9 @@ The hot path has no CPU / PyTorch fallback: it needs esmstereo_b200/csrc/libesm_
 (`python -m esmstereo_b200.build`) and a CUDA device.
 """
 from .model import (ESMStereo, ESMStereo_confidence, ESMStereo_trt, GraphedStereo, StereoPipeline,  # noqa: F401
-                    __models__)
+                    __models__, load_reference_checkpoint)
 from .ops import (build_gwc_volume, build_norm_correlation_volume, disparity_regression,  # noqa: F401
                   regression_topk)
 
-__all__ = ["ESMStereo", "ESMStereo_trt", "ESMStereo_confidence", "GraphedStereo", "StereoPipeline", "__models__",
+__all__ = ["ESMStereo", "ESMStereo_trt", "ESMStereo_confidence", "GraphedStereo", "StereoPipeline", "__models__", "load_reference_checkpoint",
            "build_gwc_volume", "build_norm_correlation_volume", "disparity_regression", "regression_topk"]

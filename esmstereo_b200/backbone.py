@@ -1,13 +1,20 @@
-"""Stand-in for the timm backbones the reference pulls in (`/root/reference/models/ESMStereo.py:46,55`).
+"""Backbones behind `Feature` (`/root/reference/models/ESMStereo.py:40-77`), which the reference pulls from timm
+(`timm.create_model('efficientnet_b2' | 'mobilenetv2_100', pretrained=True, features_only=True)`, :46,55).
 
-timm is not installed in this image and there is no network, so neither the reference nor this
-package can build `timm.create_model('efficientnet_b2' | 'mobilenetv2_100', features_only=True)`.
-This module provides a structural stand-in with the attribute surface the reference touches
-(`conv_stem`, `bn1`, `blocks[0:7]`) and the stage channels / strides of the two real backbones,
-so that `Feature` (ESMStereo.py:40-77) slices it exactly like a timm model.  It is OUTSIDE the
-hot path (2D feature side stays PyTorch).  If a real `timm` is importable it
-is used instead, keeping checkpoint key compatibility.
+`make_backbone(name)` returns, in this order (ESM_BACKBONE = auto | timm | compat | standin overrides):
+  1. a real `timm` model when timm is importable ("torch" engine: its own cuDNN forward);
+  2. otherwise `timm_compat.TimmCompatBackbone`: the same two architectures restated with timm's module / parameter
+     names, so reference checkpoints load by key, running on libesm_b200 kernels;
+  3. the structural STAND-IN below only on explicit request (ESM_BACKBONE=standin).  It has the attribute surface the
+     reference touches (`conv_stem`, `bn1`, `blocks[0:7]`) and the stage widths / strides of the real backbones but
+     plain conv-bn-relu6 stages, i.e. DIFFERENT parameter names: a real checkpoint loaded through the reference's
+     key filter (test_kitti.py:57-61) would silently leave it at random weights.  It exists because the reference
+     goldens (tests/golden/timm_shim), the CPU oracle and bench.py's synthetic workload were defined on it, with
+     timm absent from the image; those callers opt in explicitly and a warning says so.
 """
+import os
+import warnings
+
 import torch.nn as nn
 
 # (out_channels, stride) of timm's 7 stages; reference slices blocks[0:1],[1:2],[2:3],[3:5],[5:6]
@@ -40,15 +47,26 @@ class StandInBackbone(nn.Module):
 
 
 def create_model(name, pretrained=False, features_only=True, **_unused):
-    """Signature-compatible with `timm.create_model` as called by the reference."""
+    """Signature-compatible with `timm.create_model` as called by the reference (the stand-in)."""
     return StandInBackbone(name)
 
 
 def make_backbone(name: str) -> nn.Module:
-    try:  # a real timm, when present, keeps checkpoint keys loadable
-        import timm  # type: ignore
-        if getattr(timm, "__esm_b200_shim__", False):
-            raise ImportError
-        return timm.create_model(name, pretrained=False, features_only=True)
-    except ImportError:
+    mode = os.environ.get("ESM_BACKBONE", "auto").lower()
+    if mode not in ("auto", "timm", "compat", "standin"):
+        raise ValueError("ESM_BACKBONE must be auto, timm, compat or standin (got %r)" % mode)
+    if mode == "standin":
+        warnings.warn("esmstereo_b200: ESM_BACKBONE=standin -- `feature.*` is a structural stand-in whose parameter names differ from "
+                      "timm's; real ESMStereo checkpoints will NOT fill it (use the default backbone for them)", stacklevel=2)
         return StandInBackbone(name)
+    if mode in ("auto", "timm"):
+        try:
+            import timm  # type: ignore
+            if getattr(timm, "__esm_b200_shim__", False):
+                raise ImportError("timm shim")
+            return timm.create_model(name, pretrained=False, features_only=True)
+        except ImportError:
+            if mode == "timm":
+                raise
+    from .timm_compat import TimmCompatBackbone
+    return TimmCompatBackbone(name)

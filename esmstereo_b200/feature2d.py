@@ -72,7 +72,11 @@ class Feature(nn.Module):
         super().__init__()
         self.backbone = backbone
         model = make_backbone(backbone)
+        from .timm_compat import TimmCompatBackbone
         self.stand_in = isinstance(model, StandInBackbone)
+        self.compat = isinstance(model, TimmCompatBackbone)
+        # kernels of libesm_b200 run the stand-in and the timm-compatible definition; a real timm model runs its own forward
+        self.esm_capable = self.stand_in or self.compat
         self.chans = FEATURE_CHANS[backbone]
         self.conv_stem, self.bn1, self.act1 = model.conv_stem, model.bn1, nn.ReLU6()
         cuts = [0, 1, 2, 3, 5, 6]
@@ -87,6 +91,16 @@ class Feature(nn.Module):
             for i in range(5):
                 for j, stage in enumerate(getattr(self, "block%d" % i)):  # stage = Sequential(conv, bn, ReLU6)
                     x = fused(self._caches.setdefault((i, j), _Packed()), stage[0], stage[1], x, "relu6", engine)
+                outs.append(x)
+            return outs
+        if engine in ("esm", "esm_fp32") and self.compat:
+            # `act1(bn1(conv_stem(x)))` (:68): timm's bn1 carries the backbone's activation, act1 = ReLU6 comes on top
+            x = fused(self._caches.setdefault("stem", _Packed()), self.conv_stem, self.bn1, x, self.bn1.act_name, engine, act2="relu6")
+            outs = []
+            for i in range(5):
+                for stage in getattr(self, "block%d" % i):
+                    for blk in stage:
+                        x = blk.forward_esm(x, fp32_only=engine == "esm_fp32")
                 outs.append(x)
             return outs
         x = self.act1(self.bn1(self.conv_stem(x)))

@@ -59,7 +59,7 @@ class _ESMStereoBase(nn.Module):
             raise NameError("Choose the cost volume resolution: 4, 8, 16")
         self.feature = Feature(backbone)
         # 2D feature side: "esm" = the fused direct-conv kernels (stand-in backbone), "torch" = cuDNN modules
-        self.feature_engine = "esm" if self.feature.stand_in else "torch"
+        self.feature_engine = "esm" if self.feature.esm_capable else "torch"
         if confidence and self.feature_engine == "esm":
             self.feature_engine = "esm_fp32"  # everything upstream of the confidence head's cost tower stays on the FP32 pipe (below)
         if cv_scale in (4, 8):
@@ -107,7 +107,7 @@ class _ESMStereoBase(nn.Module):
         both = torch.cat((left, right), 0)
         eng = self.feature_engine
         with _exact_fp32(self.exact_fp32 and eng == "torch"):
-            feats = self.feature(both, eng if self.feature.stand_in else "torch")
+            feats = self.feature(both, eng if self.feature.esm_capable else "torch")
             if self.vol_size in (4, 8):
                 feats = self.feature_up(feats, eng)
             stems = [self.stem_2(both, eng)]
@@ -212,6 +212,28 @@ class ESMStereo_confidence(_ESMStereoBase):
             raise UnboundLocalError("conf_out is only produced for cv_scale == 16 (ESMStereo_confidence.py:966-974)")
         disp, conf = self._run(left, right, False, True)
         return disp[0], conf
+
+
+def load_reference_checkpoint(model: nn.Module, state_dict: Dict[str, torch.Tensor], require_backbone: bool = True) -> List[str]:
+    """The reference's checkpoint idiom (test_kitti.py:57-61): keep the keys the model has, update, load -- with or
+    without the `module.` prefix nn.DataParallel adds -- but, unlike it, NOT silently: every model tensor the
+    checkpoint does not provide is returned, and a backbone (`feature.*`) left unfilled raises (that is what a
+    stand-in backbone, or a mismatched timm version, looks like)."""
+    model_dict = model.state_dict()
+    prefixed = any(k.startswith("module.") for k in model_dict)
+    fixed = {}
+    for k, v in state_dict.items():
+        bare = k[len("module."):] if k.startswith("module.") else k
+        fixed[("module." + bare) if prefixed else bare] = v
+    pre = {k: v for k, v in fixed.items() if k in model_dict}
+    missing = [k for k in model_dict if k not in pre and not k.endswith("num_batches_tracked")]
+    bad = [k for k in missing if ".feature." in "." + k]
+    if require_backbone and bad:
+        raise RuntimeError("checkpoint leaves %d backbone tensors unfilled (e.g. %s): the model's `feature.*` names do not match the "
+                           "checkpoint's -- stand-in backbone, or a different timm naming scheme" % (len(bad), bad[0]))
+    model_dict.update(pre)
+    model.load_state_dict(model_dict)
+    return missing
 
 
 __models__ = {

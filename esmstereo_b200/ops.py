@@ -520,6 +520,44 @@ def conf_convex_up4(feat, conf, weight, bias) -> torch.Tensor:
     return out
 
 
+# ---------------------------------------------------------------------------------------------
+# timm backbone pieces (esmstereo_b200/timm_compat.py; ESMStereo.py:40-77)
+# ---------------------------------------------------------------------------------------------
+def dwconv2d(x: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor], act: Optional[str],
+             stride: int = 1) -> torch.Tensor:
+    """Depthwise k x k conv (padding k // 2) + per-channel affine + activation, one launch."""
+    x, weight = _dev(x, "x").contiguous(), _dev(weight, "weight").contiguous()
+    B, Cc, H, W = x.shape
+    k = weight.shape[-1]
+    assert tuple(weight.shape) == (Cc, 1, k, k)
+    p = k // 2
+    Ho, Wo = (H + 2 * p - k) // stride + 1, (W + 2 * p - k) // stride + 1
+    y = torch.empty(B, Cc, Ho, Wo, device=x.device, dtype=torch.float32)
+    with _Prof("dwconv2d C%d k%d s%d %dx%d" % (Cc, k, stride, H, W)):
+        check(lib().esm_dwconv2d_f32(x.data_ptr(), weight.data_ptr(), _ptr(scale), _ptr(shift), ACT[act], y.data_ptr(), B, Cc, H, W, k, int(stride),
+                                     _stream()), "dwconv2d")
+    return y
+
+
+def global_avgpool(x: torch.Tensor) -> torch.Tensor:
+    x = _dev(x, "x").contiguous()
+    B, Cc, H, W = x.shape
+    out = torch.empty(B, Cc, 1, 1, device=x.device, dtype=torch.float32)
+    with _Prof("global_avgpool C%d %dx%d" % (Cc, H, W)):
+        check(lib().esm_global_avgpool_f32(x.data_ptr(), out.data_ptr(), B, Cc, H * W, _stream()), "global_avgpool")
+    return out
+
+
+def scale_channels_(x: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
+    """x[b, c] *= gate[b, c] in place (squeeze-and-excitation)."""
+    assert x.is_contiguous() and gate.numel() == x.shape[0] * x.shape[1]
+    B, Cc, H, W = x.shape
+    with _Prof("scale_channels C%d %dx%d" % (Cc, H, W)):
+        check(lib().esm_scale_channels_f32(_dev(x, "x").data_ptr(), _dev(gate, "gate").contiguous().data_ptr(), B, Cc, H * W, _stream()),
+              "scale_channels")
+    return x
+
+
 def fill_(t: torch.Tensor, value: float) -> torch.Tensor:
     with _Prof("fill"):
         check(lib().esm_fill_f32(_dev(t, "t").data_ptr(), t.numel(), float(value), _stream()), "fill")

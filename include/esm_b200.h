@@ -215,6 +215,17 @@ int esm_laf_sample_embed_f32(const float* feat, const float* scale, const float*
  * feat [B,C,h,w], conf [B,1,h,w], weight [C,9,4,4] (torch layout), bias [9] -> out [B,1,4h,4w]. */
 int esm_conf_convex_up4_f32(const float* feat, const float* conf, const float* weight, const float* bias,
                             float* out, int B, int C, int h, int w, void* stream);
+/*
+ * Pieces of the timm backbones behind `Feature` (ESMStereo.py:40-77: timm.create_model('efficientnet_b2' |
+ * 'mobilenetv2_100', features_only=True)) that are not plain convolutions: depthwise k x k conv (k = 3, 5, 7; stride 1
+ * or 2; padding k/2) + per-channel affine (folded BN) + activation; global average pool [B,C,H*W] -> [B,C]; in-place
+ * multiply by a per-(image, channel) gate (squeeze-and-excitation).  Their 1x1 convolutions run on esm_conv_f32.
+ */
+int esm_dwconv2d_f32(const float* x, const float* w /*[C,1,k,k]*/, const float* scale, const float* shift, int act, float* y, int B,
+                     int C, int H, int W, int k, int stride, void* stream);
+int esm_global_avgpool_f32(const float* x, float* out, int B, int C, int HW, void* stream);
+int esm_scale_channels_f32(float* x, const float* gate, int B, int C, int HW, void* stream);
+
 /* Measured dense TF32 tensor-core rate of the current device (TFLOP/s): every SM issues `iters` back-to-back
  * M128 x N256 x K8 tcgen05.mma.  Synchronises; diagnostics / bench.py's tensor-roofline denominator. */
 int esm_umma_tf32_peak(int iters, float* tflops, void* stream);

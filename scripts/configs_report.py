@@ -1,7 +1,8 @@
 """Throughput of the other BASELINE.json configurations (the bench line is configs[1]): SceneFlow-shaped 544x960 at
 batch 1 / 8 (configs[2]), KITTI-shaped batch sweep (configs[3], one GPU's share), ESMStereo_confidence 992x1472 cv16
 (configs[4]), and the cv8 / cv16 variants at KITTI shape.  CUDA-graph replay, CUDA events, 10 steps after 3 warm-ups."""
-import contextlib, io, sys
+import contextlib, io, os, sys
+os.environ.setdefault("ESM_BACKBONE", "standin")
 import torch
 sys.path.insert(0, ".")
 from esmstereo_b200 import __models__, GraphedStereo

@@ -15,6 +15,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("ESM_PLANS", "0")
+os.environ.setdefault("ESM_BACKBONE", "standin")
 os.environ.setdefault("ESM_AUTOTUNE", "1")
 from esmstereo_b200 import __models__, _lib  # noqa: E402
 from esmstereo_b200.weights import fill_deterministic, synthetic_pair  # noqa: E402
