@@ -42,6 +42,14 @@ def build(force: bool = False, verbose: bool = True) -> str:
     if os.environ.get("ESM_TC_PROFILE") == "1":  # role timers of the tcgen05 conv kernel (conv_tc.cu), diagnostics only
         flags = flags + ["-DTC_PROFILE"]
 
+    # objects built with other flags (e.g. the ESM_TC_PROFILE role timers) are stale too
+    stamp = os.path.join(objdir, "flags.txt")
+    flag_text = " ".join(flags)
+    if not os.path.exists(stamp) or open(stamp).read() != flag_text:
+        force = True
+        with open(stamp, "w") as f:
+            f.write(flag_text)
+
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         path = os.path.join(CSRC, src)

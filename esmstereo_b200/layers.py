@@ -8,6 +8,7 @@ Inference only: BatchNorm is folded from its running statistics (eval semantics)
 """
 from __future__ import annotations
 
+import threading
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -17,19 +18,42 @@ from . import ops
 
 
 class _Packed:
-    """Lazy, self-invalidating cache of a layer's packed weights (re-packed when any source tensor
-    is replaced or modified in place, e.g. by `.cuda()` or `load_state_dict`)."""
+    """Lazy, self-invalidating cache of a layer's packed weights, one entry per device (nn.DataParallel replicas share
+    the module's __dict__, hence this object: a replica must never be handed weights packed on another GPU).  An entry is
+    re-packed when any source tensor is replaced or modified in place (`.cuda()`, `load_state_dict`, optimiser steps).
+    Writes through `.data` do not bump a tensor's version: call `invalidate()` (or `esmstereo_b200.layers.invalidate_packed
+    (model)`) after editing weights that way."""
 
     def __init__(self):
-        self.key = None
-        self.value = None
+        self._entries = {}
+        self._lock = threading.Lock()
+
+    def invalidate(self) -> None:
+        with self._lock:
+            self._entries.clear()
 
     def get(self, tensors: Sequence[Optional[torch.Tensor]], build):
-        key = tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
-        if key != self.key:
-            self.value = build()
-            self.key = key
-        return self.value
+        live = [t for t in tensors if t is not None]
+        dev = live[0].device if live else None
+        key = tuple((t.data_ptr(), getattr(t, "_version", 0) if not t.is_inference() else 0) for t in live)
+        with self._lock:
+            ent = self._entries.get(dev)
+            if ent is None or ent[0] != key:
+                ent = (key, build())
+                self._entries[dev] = ent
+            return ent[1]
+
+
+def invalidate_packed(module: nn.Module) -> int:
+    """Drop every packed-weight cache under `module` (after `.data` edits, which the version check cannot see)."""
+    n = 0
+    for m in module.modules():
+        for v in list(vars(m).values()):
+            for c in (v.values() if isinstance(v, dict) else v if isinstance(v, (tuple, list)) else (v,)):
+                if isinstance(c, _Packed):
+                    c.invalidate()
+                    n += 1
+    return n
 
 
 def _bn_tuple(bn: Optional[nn.modules.batchnorm._BatchNorm]):

@@ -275,13 +275,15 @@ class GraphedStereo:
 
 
 class StereoPipeline:
-    """Host-to-host serving loop around a `GraphedStereo`: pinned host images in, pinned host disparity
-    out, with the H2D copy of pair i+1 and the D2H copy of pair i-1 overlapping the graph replay of pair i
-    (separate copy stream, `depth` staging slots).
+    """Host-to-host serving loop around a `GraphedStereo`: pinned host images in, pinned host disparity out.  The H2D
+    copy of pair i+1 and the D2H copy of pair i-1 run on a separate copy stream and overlap the graph replay of pair i:
+    the replay's output is first moved to a per-slot device buffer on the compute stream (so the next replay can start
+    at once), the D2H copy of that buffer then goes on the copy stream.
 
         pipe = StereoPipeline(GraphedStereo(model, shape, train_status=False))
         pipe.submit(left_pinned, right_pinned); ...; disp_host = pipe.result()   # results come back in order
-    """
+
+    `result()` returns the slot's pinned buffer, which is overwritten `depth` submits later: copy it if you keep it."""
 
     def __init__(self, graphed: GraphedStereo, depth: int = 2, pick=lambda out: out[-1]) -> None:
         self.g, self.depth, self.pick = graphed, depth, pick
@@ -292,8 +294,9 @@ class StereoPipeline:
         for _ in range(depth):
             self.slots.append(dict(
                 left=torch.empty_like(graphed.left), right=torch.empty_like(graphed.right),
+                dev_out=torch.empty_like(example),
                 out=torch.empty(example.shape, dtype=example.dtype).pin_memory(),
-                staged=torch.cuda.Event(), consumed=torch.cuda.Event(), done=torch.cuda.Event()))
+                staged=torch.cuda.Event(), consumed=torch.cuda.Event(), replayed=torch.cuda.Event(), done=torch.cuda.Event()))
         self.submitted = self.returned = 0
 
     def submit(self, left_host: torch.Tensor, right_host: torch.Tensor) -> None:
@@ -303,15 +306,21 @@ class StereoPipeline:
         cur = torch.cuda.current_stream(self.g.left.device)
         with torch.cuda.stream(self.copy_stream):
             if self.submitted >= self.depth:
-                self.copy_stream.wait_event(slot["consumed"])  # staging buffers were read by the replay 2 steps ago
+                self.copy_stream.wait_event(slot["consumed"])  # staging buffers were read by the replay `depth` steps ago
             slot["left"].copy_(left_host, non_blocking=True)
             slot["right"].copy_(right_host, non_blocking=True)
             slot["staged"].record(self.copy_stream)
         cur.wait_event(slot["staged"])
+        if self.submitted >= self.depth:
+            cur.wait_event(slot["done"])  # the D2H copy of this slot's previous result has left dev_out
         out = self.pick(self.g(slot["left"], slot["right"]))
         slot["consumed"].record(cur)
-        slot["out"].copy_(out, non_blocking=True)
-        slot["done"].record(cur)
+        slot["dev_out"].copy_(out, non_blocking=True)
+        slot["replayed"].record(cur)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(slot["replayed"])
+            slot["out"].copy_(slot["dev_out"], non_blocking=True)
+            slot["done"].record(self.copy_stream)
         self.submitted += 1
 
     def result(self) -> torch.Tensor:
