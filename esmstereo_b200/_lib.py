@@ -81,6 +81,10 @@ SIGNATURES = {
     "esm_preprocess_u8_f32": (C.c_int, [vp, vp] + [C.c_int] * 8 + [C.POINTER(C.c_float), C.POINTER(C.c_float), vp]),
     "esm_postprocess_disp_u16": (C.c_int, [vp, vp] + [C.c_int] * 7 + [C.c_float, vp]),
     "esm_regression_top2_f32": (C.c_int, [vp, vp, vp] + [C.c_int] * 4 + [vp]),
+    "esm_regression_top2_subpixel_f32": (C.c_int, [vp] + [C.c_longlong] * 4 + [vp, vp] + [C.c_int] * 4 + [vp]),
+    "esm_pixel_shuffle3d_f32": (C.c_int, [vp] + [C.c_longlong] * 4 + [vp] + [C.c_int] * 4 + [vp]),
+    "esm_copy_f32": (C.c_int, [vp, vp, C.c_longlong, vp]),
+    "esm_disparity_publish_u16": (C.c_int, [vp, vp] + [C.c_int] * 4 + [C.c_float, C.c_float, vp]),
     "esm_disparity_regression_f32": (C.c_int, [vp, vp] + [C.c_int] * 4 + [vp]),
     "esm_bilinear_add_f32": (C.c_int, [vp, vp, vp] + [C.c_int] * 4 + [C.c_float, vp]),
     "esm_sm_pointwise_f32": (C.c_int, [vp, vp] + [C.c_int] * 4 + [C.POINTER(EsmMixerMlp), vp, vp]),

@@ -58,9 +58,80 @@ __global__ void __launch_bounds__(256) postprocess_kernel(const float* __restric
   out[i] = (uint16_t)fminf(fmaxf(r, 0.f), 65535.f);
 }
 
+// [B, 8 = (pd, ph, pw), D2, H2, W2] (strided) -> [B, 1, 2 D2, 2 H2, 2 W2] contiguous: the PixelShuffle of the sub-pixel
+// form of a one-channel ConvTranspose3d k4 s2 p1 (ESMStereo.py:150: `conv1_up` of the hourglass)
+__global__ void __launch_bounds__(256) pixel_shuffle3d_kernel(const float* __restrict__ in, long long sB, long long sC, long long sD, long long sH,
+                                                              float* __restrict__ out, int D2, int H2, int W2, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int W = 2 * W2, H = 2 * H2, D = 2 * D2;
+  const int x = (int)(i % W);
+  long long t = i / W;
+  const int y = (int)(t % H);
+  t /= H;
+  const int d = (int)(t % D);
+  const long long b = t / D;
+  out[i] = __ldg(in + b * sB + (long long)((d & 1) * 4 + (y & 1) * 2 + (x & 1)) * sC + (long long)(d >> 1) * sD + (long long)(y >> 1) * sH + (x >> 1));
+}
+
+// Post-processing of the reference's ROS publisher (kitti_publisher/src/kitti_publisher_cuda_node.cpp:385-404): crop the
+// padded disparity to the image, cv::medianBlur(5) (float: exact median of the 5 x 5 window, replicated border), zero
+// where not 0 < d < max_disp, convertTo(CV_16UC1, scale) = saturate(round-half-even(d * scale)).
+__global__ void __launch_bounds__(256) publish_kernel(const float* __restrict__ disp, uint16_t* __restrict__ out, int Wp, int h, int w,
+                                                      float max_disp, float scale, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % w), y = (int)(i / w);
+  float v[25];
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    const int yy = min(max(y + a - 2, 0), h - 1);
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+      const int xx = min(max(x + b - 2, 0), w - 1);
+      v[a * 5 + b] = __ldg(disp + (long long)yy * Wp + xx);
+    }
+  }
+  // partial selection sort up to the 13th smallest
+#pragma unroll
+  for (int a = 0; a < 13; ++a) {
+#pragma unroll
+    for (int b = a + 1; b < 25; ++b) {
+      const float lo = fminf(v[a], v[b]), hi = fmaxf(v[a], v[b]);
+      v[a] = lo;
+      v[b] = hi;
+    }
+  }
+  float m = v[12];
+  if (!(m > 0.f && m < max_disp)) m = 0.f;
+  out[i] = (uint16_t)fminf(fmaxf(rintf(__fmul_rn(m, scale)), 0.f), 65535.f);
+}
+
 }  // namespace esm
 
 using namespace esm;
+
+extern "C" int esm_copy_f32(float* dst, const float* src, long long n, void* stream) {
+  ESM_REQUIRE(dst && src && n > 0, "copy: null pointer or empty range");
+  if (cudaMemcpyAsync(dst, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) return check_launch("copy");
+  return ESM_OK;
+}
+
+extern "C" int esm_pixel_shuffle3d_f32(const float* in, long long sB, long long sC, long long sD, long long sH, float* out, int B, int D2,
+                                       int H2, int W2, void* stream) {
+  ESM_REQUIRE(in && out && B > 0 && D2 > 0 && H2 > 0 && W2 > 0, "pixel_shuffle3d: bad arguments");
+  const long long total = 8ll * B * D2 * H2 * W2;
+  pixel_shuffle3d_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(in, sB, sC, sD, sH, out, D2, H2, W2, total);
+  return check_launch("pixel_shuffle3d");
+}
+
+extern "C" int esm_disparity_publish_u16(const float* disp, unsigned short* out, int Hp, int Wp, int h, int w, float max_disp, float scale,
+                                         void* stream) {
+  ESM_REQUIRE(disp && out && h > 0 && w > 0 && h <= Hp && w <= Wp, "disparity_publish: bad arguments");
+  const long long total = (long long)h * w;
+  publish_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(disp, out, Wp, h, w, max_disp, scale, total);
+  return check_launch("disparity_publish");
+}
 
 extern "C" int esm_preprocess_u8_f32(const unsigned char* rgb_hwc, float* out_chw, int B, int h, int w, int Hp, int Wp, int pad_top,
                                      int pad_left, int fill_normalised, const float* mean3, const float* std3, void* stream) {

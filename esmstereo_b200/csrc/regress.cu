@@ -27,9 +27,18 @@ __device__ __forceinline__ void top2_push(Top2& t, float x, int i) {
 }
 constexpr int REG_SPLIT = 4, REG_MAXR = 16;
 
+// SUB: the cost volume is read in the sub-pixel form the hourglass's last layer produces it in -- `conv1_up`
+// (ConvTranspose3d k4 s2 p1 to one channel, ESMStereo.py:150,182) runs as a k3 convolution to 8 phase channels
+// [B, 8 = (pd, ph, pw), D/2, H/2, W/2] -- so the PixelShuffle copy of the volume never happens:
+//   cost[b, d, y, x] = y8[b, (d&1)*4 + (y&1)*2 + (x&1), d>>1, y>>1, x>>1]
+struct SubSrc {
+  long long sB, sC, sD, sH;  // strides of y8 in elements (W stride 1)
+  int W;                     // full-resolution width (2 * W2)
+};
+template <bool SUB>
 __global__ void __launch_bounds__(128) regression_top2_kernel(const float* __restrict__ cost, float* __restrict__ pred,
                                                               int* __restrict__ idx, int D, long long plane,
-                                                              long long total) {
+                                                              long long total, SubSrc ss) {
   __shared__ Top2 s_part[REG_SPLIT - 1][32];
   const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
   const long long i = (long long)blockIdx.x * 32 + lane;
@@ -37,13 +46,24 @@ __global__ void __launch_bounds__(128) regression_top2_kernel(const float* __res
   const long long b = live ? i / plane : 0;
   const long long p = live ? i - b * plane : 0;
   const float* c = cost + b * D * plane + p;
+  long long sub_d = 0, sub_odd = 0;  // SUB: address of disparity d = c + (d >> 1) * sub_d + (d & 1) * sub_odd
+  if (SUB) {
+    const int y = (int)(p / ss.W), x = (int)(p - (long long)y * ss.W);
+    c = cost + b * ss.sB + (long long)((y & 1) * 2 + (x & 1)) * ss.sC + (long long)(y >> 1) * ss.sH + (x >> 1);
+    sub_d = ss.sD;
+    sub_odd = 4 * ss.sC;
+  }
   const int per = (D + REG_SPLIT - 1) / REG_SPLIT;  // disparities per warp
   Top2 t = {-INFINITY, -INFINITY, -1, -1};
   for (int d0 = part * per; d0 < min(D, (part + 1) * per); d0 += REG_MAXR) {
     const int dend = min(D, (part + 1) * per);
     float v[REG_MAXR];
 #pragma unroll
-    for (int u = 0; u < REG_MAXR; ++u) v[u] = (live && d0 + u < dend) ? __ldg(c + (long long)(d0 + u) * plane) : 0.f;
+    for (int u = 0; u < REG_MAXR; ++u) {
+      const int d = d0 + u;
+      const long long off = SUB ? (long long)(d >> 1) * sub_d + (long long)(d & 1) * sub_odd : (long long)d * plane;
+      v[u] = (live && d < dend) ? __ldg(c + off) : 0.f;
+    }
 #pragma unroll
     for (int u = 0; u < REG_MAXR; ++u)
       if (d0 + u < dend) top2_push(t, v[u], d0 + u);
@@ -132,9 +152,18 @@ extern "C" int esm_regression_top2_f32(const float* cost, float* pred, int* idx,
   ESM_REQUIRE(cost && pred, "regression_top2: null pointer");
   ESM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "regression_top2: empty shape");
   const long long plane = (long long)H * W, total = plane * B;
-  regression_top2_kernel<<<(unsigned)ceil_div_ll(total, 32), 128, 0, (cudaStream_t)stream>>>(cost, pred, idx, D, plane,
-                                                                                             total);
+  regression_top2_kernel<false><<<(unsigned)ceil_div_ll(total, 32), 128, 0, (cudaStream_t)stream>>>(cost, pred, idx, D, plane, total, SubSrc{});
   return check_launch("regression_top2");
+}
+
+extern "C" int esm_regression_top2_subpixel_f32(const float* y8, long long sB, long long sC, long long sD, long long sH, float* pred, int* idx,
+                                                int B, int D2, int H2, int W2, void* stream) {
+  ESM_REQUIRE(y8 && pred, "regression_top2_subpixel: null pointer");
+  ESM_REQUIRE(B > 0 && D2 > 0 && H2 > 0 && W2 > 0, "regression_top2_subpixel: empty shape");
+  const long long plane = 4ll * H2 * W2, total = plane * B;
+  SubSrc ss = {sB, sC, sD, sH, 2 * W2};
+  regression_top2_kernel<true><<<(unsigned)ceil_div_ll(total, 32), 128, 0, (cudaStream_t)stream>>>(y8, pred, idx, 2 * D2, plane, total, ss);
+  return check_launch("regression_top2_subpixel");
 }
 
 extern "C" int esm_disparity_regression_f32(const float* cost, float* pred, int B, int D, int H, int W, void* stream) {

@@ -143,13 +143,15 @@ class BasicConv(nn.Module):
     def forward(self, x, **fused) -> torch.Tensor:
         _inference_only(self)
         act = "gelu" if self.gelu else None
-        if self._subpixel and isinstance(x, torch.Tensor) and (not fused or _only_full_out_size(fused, x)):
+        if self._subpixel and isinstance(x, torch.Tensor) and (not fused or set(fused) == {"keep_subpixel"} or _only_full_out_size(fused, x)):
             pc = self.packed_subpixel()
             if x.dim() == 4:
                 return ops.conv(x, pc, act, pixel_shuffle=2, fp32_only=self.fp32_only)
             y = ops.conv(x, pc, act, fp32_only=self.fp32_only)  # [B, 8, D, H, W], channel = pd*4 + ph*2 + pw
-            B, _, D, H, W = y.shape
-            return y.view(B, 2, 2, 2, D, H, W).permute(0, 4, 1, 5, 2, 6, 3).reshape(B, 1, 2 * D, 2 * H, 2 * W)
+            if fused.get("keep_subpixel"):
+                return y  # the caller reads the phases directly (ops.regression_top2_subpixel)
+            return ops.pixel_shuffle3d(y)
+        fused.pop("keep_subpixel", None)
         return ops.conv(x, self.packed(), act, fp32_only=self.fp32_only, **fused)
 
 
@@ -194,7 +196,9 @@ class aggregation(nn.Module):
         self.agg_1 = nn.Sequential(BasicConv(2 * c1, c1, is_3d=True, kernel_size=1, padding=0, stride=1),
                                    BasicConv(c1, c1, stride=1, **k3))
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, keep_subpixel: bool = False) -> torch.Tensor:
+        """keep_subpixel: return `conv1_up`'s output as its 8 sub-pixel phases [B,8,D/2,H/2,W/2] instead of the shuffled
+        cost volume [B,1,D,H,W] (for ops.regression_top2_subpixel); only honoured when the layer runs in that form."""
         conv1 = self.conv1[1](self.conv1[0](x))
         conv2 = self.conv2[1](self.conv2[0](conv1))
         conv3 = self.conv3[1](self.conv3[0](conv2))
@@ -203,6 +207,8 @@ class aggregation(nn.Module):
         conv2 = self.agg_0[1](self.agg_0[0]([up3, conv2]))
         up2 = self.conv2_up(conv2, out_size=conv1.shape[2:])
         conv1 = self.agg_1[1](self.agg_1[0]([up2, conv1]))
+        if keep_subpixel and self.conv1_up._subpixel:
+            return self.conv1_up(conv1, keep_subpixel=True)
         return self.conv1_up(conv1)
 
 

@@ -104,7 +104,7 @@ class _ESMStereoBase(nn.Module):
         """Returns (features_left list, stems of the left image, match_left, match_right, att).
         Both images go through the shared layers as one batch (ESMStereo.py:640-697)."""
         B = left.shape[0]
-        both = torch.cat((left, right), 0)
+        both = ops.cat_batch(left, right)
         eng = self.feature_engine
         with _exact_fp32(self.exact_fp32 and eng == "torch"):
             feats = self.feature(both, eng if self.feature.esm_capable else "torch")
@@ -124,7 +124,7 @@ class _ESMStereoBase(nn.Module):
         return fl, [s[:B] for s in stems], match[:B].contiguous(), match[B:].contiguous(), att, extra
 
     # ------------------------------------------------------------------ hot path (libesm_b200)
-    def _aggregate_cost(self, mL, mR, att) -> torch.Tensor:
+    def _aggregate_cost(self, mL, mR, att, want_volume: bool = False) -> torch.Tensor:
         """Descriptors -> aggregated cost [B,D,h,w]: volume, stem, agg, 3D hourglass (ESMStereo.py:700-716)."""
         D = self.maxdisp // self.vol_size
         if self.norm_correlation:
@@ -138,6 +138,12 @@ class _ESMStereoBase(nn.Module):
                 vol = self.group_stem(vol, in_mul=att)
         stem = vol
         vol = self.agg(vol)
+        if self.vol_size == 4 and self.capture is None and not want_volume:
+            # cv4: the top-2 regression reads conv1_up's sub-pixel phases directly -- the shuffled volume is never written
+            y8 = self.aggregation_out(vol, keep_subpixel=True)
+            if y8.shape[1] == 8:
+                return y8
+            return y8[:, 0]
         cost = self.aggregation_out(vol)[:, 0]
         if self.capture is not None:
             self.capture.update(match_left=mL, match_right=mR, stem=stem, agg=vol, cost=cost)
@@ -149,7 +155,7 @@ class _ESMStereoBase(nn.Module):
         s, D = self.vol_size, self.maxdisp // self.vol_size
         final = 1.0 if want_scales else 4.0  # every output is *4 regardless of scale (:737-745)
         if s == 4:
-            init = ops.regression_top2(cost)
+            init = ops.regression_top2_subpixel(cost) if cost.dim() == 5 else ops.regression_top2(cost)
             scales = self.upsample_module(fl[1], fl[0], stems[0], init, out_scale=final)
         elif s == 8:
             init = ops.disparity_regression(cost, D).unsqueeze(1)
@@ -172,7 +178,7 @@ class _ESMStereoBase(nn.Module):
         with torch.no_grad():
             left, right = left.float().contiguous(), right.float().contiguous()
             fl, stems, mL, mR, att, extra = self._features_2d(left, right)
-            cost = self._aggregate_cost(mL, mR, att)
+            cost = self._aggregate_cost(mL, mR, att, want_volume=want_conf)
             init, scales = self._disparity_from_cost(cost, fl, stems, extra, want_scales)
             conf = None
             if want_conf:

@@ -175,6 +175,60 @@ def regression_top2(cost: torch.Tensor, return_indices: bool = False):
     return (pred, idx) if return_indices else pred
 
 
+def regression_top2_subpixel(y8: torch.Tensor, return_indices: bool = False):
+    """`regression_topk(k=2)` reading the cost volume in the 8-phase sub-pixel form `conv1_up` is computed in
+    (y8 [B, 8, D/2, H/2, W/2], W stride 1): the PixelShuffle copy of the volume is skipped."""
+    y8 = _dev(y8, "y8")
+    assert y8.dim() == 5 and y8.shape[1] == 8 and y8.stride(-1) == 1
+    B, _, D2, H2, W2 = y8.shape
+    pred = torch.empty(B, 1, 2 * H2, 2 * W2, device=y8.device, dtype=torch.float32)
+    idx = torch.empty(B, 2, 2 * H2, 2 * W2, device=y8.device, dtype=torch.int32) if return_indices else None
+    st = y8.stride()
+    with _Prof("regression_top2_subpixel D%d %dx%d" % (2 * D2, 2 * H2, 2 * W2)):
+        check(lib().esm_regression_top2_subpixel_f32(y8.data_ptr(), st[0], st[1], st[2], st[3], pred.data_ptr(), _ptr(idx), B, D2, H2, W2,
+                                                     _stream()), "regression_top2_subpixel")
+    return (pred, idx) if return_indices else pred
+
+
+def pixel_shuffle3d(y8: torch.Tensor) -> torch.Tensor:
+    """[B, 8 = (pd, ph, pw), D2, H2, W2] -> [B, 1, 2 D2, 2 H2, 2 W2] (the PixelShuffle of a sub-pixel ConvTranspose3d)."""
+    y8 = _dev(y8, "y8")
+    assert y8.dim() == 5 and y8.shape[1] == 8 and y8.stride(-1) == 1
+    B, _, D2, H2, W2 = y8.shape
+    out = torch.empty(B, 1, 2 * D2, 2 * H2, 2 * W2, device=y8.device, dtype=torch.float32)
+    st = y8.stride()
+    with _Prof("pixel_shuffle3d %dx%dx%d" % (2 * D2, 2 * H2, 2 * W2)):
+        check(lib().esm_pixel_shuffle3d_f32(y8.data_ptr(), st[0], st[1], st[2], st[3], out.data_ptr(), B, D2, H2, W2, _stream()),
+              "pixel_shuffle3d")
+    return out
+
+
+def cat_batch(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """torch.cat((a, b), 0) of two contiguous tensors as two device copies through the C ABI (so that a recorded
+    forward -- esmstereo_b200/engine.py -- contains every device operation)."""
+    a, b = _dev(a, "a").contiguous(), _dev(b, "b").contiguous()
+    assert a.shape[1:] == b.shape[1:]
+    out = torch.empty((a.shape[0] + b.shape[0],) + tuple(a.shape[1:]), device=a.device, dtype=torch.float32)
+    with _Prof("cat_batch", 2):
+        check(lib().esm_copy_f32(out.data_ptr(), a.data_ptr(), a.numel(), _stream()), "copy")
+        check(lib().esm_copy_f32(out.data_ptr() + 4 * a.numel(), b.data_ptr(), b.numel(), _stream()), "copy")
+    return out
+
+
+def disparity_publish_u16(disp: torch.Tensor, size: Tuple[int, int], max_disp: float = 192.0, scale: float = 256.0) -> torch.Tensor:
+    """The ROS publisher's post-processing (kitti_publisher_cuda_node.cpp:385-404): crop [h,w] at the origin of the padded
+    [Hp,Wp] disparity, 5x5 median, zero unless 0 < d < max_disp, round(d * 256) -> uint16."""
+    d = _dev(disp, "disp").contiguous()
+    assert d.dim() == 2
+    Hp, Wp = d.shape
+    h, w = int(size[0]), int(size[1])
+    out = torch.empty(h, w, device=d.device, dtype=torch.uint16)
+    with _Prof("disparity_publish %dx%d" % (h, w)):
+        check(lib().esm_disparity_publish_u16(d.data_ptr(), out.data_ptr(), Hp, Wp, h, w, float(max_disp), float(scale), _stream()),
+              "disparity_publish")
+    return out
+
+
 def regression_topk(cost: torch.Tensor, disparity_samples: Optional[torch.Tensor], k: int) -> torch.Tensor:
     """Reference signature (submodule.py:218).  The path only ever calls it with k=2 and
     `disparity_samples = arange(D)` broadcast (ESMStereo.py:719-721); anything else is rejected."""

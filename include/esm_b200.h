@@ -153,6 +153,15 @@ int esm_gwc_volume_norm_f32(const float* L, const float* R, float* V, int B, int
  * cost [B,D,H,W] -> pred [B,1,H,W]; idx (optional, int32 [B,2,H,W]) receives the top-2 indices
  * (ties: lower index first). */
 int esm_regression_top2_f32(const float* cost, float* pred, int* idx, int B, int D, int H, int W, void* stream);
+/* The same regression reading the cost volume in the sub-pixel form the hourglass's `conv1_up` (ConvTranspose3d k4 s2 p1
+ * to one channel, ESMStereo.py:150,182) is computed in: y8 [B, 8 = (pd,ph,pw), D2, H2, W2] with the given strides,
+ * cost[b,d,y,x] = y8[b, (d&1)*4 + (y&1)*2 + (x&1), d/2, y/2, x/2] -- the PixelShuffle copy of the volume is skipped.
+ * pred [B,1,2H2,2W2]; idx optional int32 [B,2,2H2,2W2]. */
+int esm_regression_top2_subpixel_f32(const float* y8, long long sB, long long sC, long long sD, long long sH, float* pred, int* idx,
+                                     int B, int D2, int H2, int W2, void* stream);
+/* ... and the PixelShuffle itself, for callers that need the volume (confidence head, tests): -> [B,1,2D2,2H2,2W2]. */
+int esm_pixel_shuffle3d_f32(const float* in, long long sB, long long sC, long long sD, long long sH, float* out, int B, int D2, int H2,
+                            int W2, void* stream);
 /* disparity_regression (submodule.py:211-216): sum_d cost[d]*d, no softmax -> [B,1,H,W]. */
 int esm_disparity_regression_f32(const float* cost, float* pred, int B, int D, int H, int W, void* stream);
 
@@ -173,6 +182,14 @@ int esm_preprocess_u8_f32(const unsigned char* rgb_hwc, float* out_chw, int B, i
  * [B,Hp,Wp] disparity, round(d * scale) half-to-even -> uint16 [B,h,w] (saturating). */
 int esm_postprocess_disp_u16(const float* disp, unsigned short* out, int B, int Hp, int Wp, int top, int left,
                              int h, int w, float scale, void* stream);
+
+/* Device-to-device copy of n floats on `stream` (torch.cat of the left / right images, ESMStereo.py:640-641 batched). */
+int esm_copy_f32(float* dst, const float* src, long long n, void* stream);
+/* Post-processing of the reference's ROS publisher (kitti_publisher/src/kitti_publisher_cuda_node.cpp:385-404): crop the
+ * padded [Hp,Wp] disparity to [h,w] at the origin, 5x5 median (cv::medianBlur semantics for CV_32F: exact median,
+ * replicated border), zero unless 0 < d < max_disp, then saturate(round-half-even(d * scale)) -> uint16 [h,w]. */
+int esm_disparity_publish_u16(const float* disp, unsigned short* out, int Hp, int Wp, int h, int w, float max_disp, float scale,
+                              void* stream);
 
 /*
  * ShuffleMixer SMLayer halves (shufflemixer.py:97-112), C in {8,16}:

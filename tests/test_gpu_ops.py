@@ -673,3 +673,36 @@ def test_tensor_core_truncation_bias_beyond_gaussian(engine, dist, monkeypatch):
     interior = want.abs() > 0.05 * scale_
     bias = ((got.double().cpu() - want)[interior] / want[interior]).mean().item()
     assert abs(bias) < 2e-6, "mean signed relative error %g (truncation bias not compensated)" % bias
+
+
+def test_regression_on_subpixel_volume_and_pixel_shuffle3d():
+    """The top-2 regression reading conv1_up's 8 sub-pixel phases == the regression on the shuffled volume, bit for bit
+    (indices and prediction); the shuffle kernel == torch's view/permute/reshape of the reference's ConvTranspose3d layout."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    for (B, D2, H2, W2) in ((1, 6, 5, 9), (2, 24, 12, 39)):
+        buf = torch.randn(B, 8, D2, H2, W2 + 3, generator=g).cuda()
+        y8 = buf[..., :W2]  # a pitched view, like the conv engines' outputs
+        vol = ops.pixel_shuffle3d(y8)
+        want = y8.contiguous().view(B, 2, 2, 2, D2, H2, W2).permute(0, 4, 1, 5, 2, 6, 3).reshape(B, 1, 2 * D2, 2 * H2, 2 * W2)
+        assert torch.equal(vol, want)
+        p0, i0 = ops.regression_top2(vol[:, 0].contiguous(), return_indices=True)
+        p1, i1 = ops.regression_top2_subpixel(y8, return_indices=True)
+        assert torch.equal(i0, i1) and torch.equal(p0, p1)
+
+
+def test_disparity_publish_matches_opencv_semantics():
+    """crop + medianBlur(5) (exact median, replicated border) + validity mask + round(d * 256) -> uint16
+    (kitti_publisher_cuda_node.cpp:385-404), against a torch restatement."""
+    import torch.nn.functional as F
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    Hp, Wp, h, w = 64, 96, 37, 61
+    d = torch.rand(Hp, Wp, generator=g) * 230.0 - 10.0  # some values outside (0, 192)
+    crop = d[:h, :w]
+    pad = F.pad(crop[None, None], (2, 2, 2, 2), mode="replicate")
+    med = pad.unfold(2, 5, 1).unfold(3, 5, 1).reshape(h, w, 25).sort(-1).values[..., 12]
+    med = torch.where((med > 0) & (med < 192.0), med, torch.zeros_like(med))
+    want = torch.clamp(torch.round(med * 256.0), 0, 65535).to(torch.int32)
+    got = ops.disparity_publish_u16(d.cuda(), (h, w), 192.0, 256.0).cpu().to(torch.int32)
+    assert torch.equal(got, want)
