@@ -94,6 +94,7 @@ SIGNATURES = {
     "esm_laf_sample_embed_f32": (C.c_int, [vp] * 8 + [C.c_int] * 4 + [vp]),
     "esm_conf_convex_up4_f32": (C.c_int, [vp] * 5 + [C.c_int] * 4 + [vp]),
     "esm_fill_f32": (C.c_int, [vp, C.c_longlong, C.c_float, vp]),
+    "esm_download": (C.c_int, [vp, vp, C.c_longlong]),
     "esm_dwconv2d_f32": (C.c_int, [vp, vp, vp, vp, C.c_int, vp] + [C.c_int] * 6 + [vp]),
     "esm_global_avgpool_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "esm_scale_channels_f32": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp]),

@@ -60,3 +60,10 @@ extern "C" int esm_fill_f32(float* p, long long n, float value, void* stream) {
   fill_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(p, n, value);
   return check_launch("fill");
 }
+
+// Synchronous device -> host copy of raw bytes (esmstereo_b200/engine.py snapshots the weights of an engine with it).
+extern "C" int esm_download(void* dst_host, const void* src_device, long long nbytes) {
+  ESM_REQUIRE(dst_host && src_device && nbytes > 0, "download: bad arguments");
+  if (cudaMemcpy(dst_host, src_device, (size_t)nbytes, cudaMemcpyDeviceToHost) != cudaSuccess) return check_launch("download");
+  return ESM_OK;
+}

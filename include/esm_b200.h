@@ -246,6 +246,8 @@ int esm_scale_channels_f32(float* x, const float* gate, int B, int C, int HW, vo
 /* Measured dense TF32 tensor-core rate of the current device (TFLOP/s): every SM issues `iters` back-to-back
  * M128 x N256 x K8 tcgen05.mma.  Synchronises; diagnostics / bench.py's tensor-roofline denominator. */
 int esm_umma_tf32_peak(int iters, float* tflops, void* stream);
+/* Synchronous device -> host copy of raw bytes (engine export: esmstereo_b200/engine.py). */
+int esm_download(void* dst_host, const void* src_device, long long nbytes);
 /* Fill `n` floats with `value`. */
 int esm_fill_f32(float* p, long long n, float value, void* stream);
 
