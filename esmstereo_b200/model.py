@@ -13,6 +13,7 @@ upsampling, confidence head -- every op is a libesm_b200 kernel (`layers`, `ops`
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -53,6 +54,8 @@ class _ESMStereoBase(nn.Module):
         self.gwc, self.norm_correlation, self.backbone = gwc, norm_correlation, backbone
         self.exact_fp32 = True      # engine "torch" only: keep cuDNN out of TF32 on the 2D feature side (parity-grade)
         self.fuse_volume = True     # gwc volume generated inside group_stem (never written to HBM)
+        self.fork_streams = os.environ.get("ESM_FORK", "1") != "0"
+        self._side_streams = {}
         self.capture: Optional[Dict[str, torch.Tensor]] = None  # set to {} to record hot-path stages (tests)
         if cv_scale not in (4, 8, 16):
             # the reference hits a misspelt `pirnt(...)` here -> NameError (ESMStereo.py:599)
@@ -107,13 +110,27 @@ class _ESMStereoBase(nn.Module):
         both = ops.cat_batch(left, right)
         eng = self.feature_engine
         with _exact_fp32(self.exact_fp32 and eng == "torch"):
+            # the image stems depend on the images only: they run on a side stream next to the backbone + FeatUp chain
+            # (fork / join by events, captured as parallel branches of the CUDA graph); ESM_FORK=0 keeps one stream
+            fork = self.fork_streams and both.is_cuda
+            cur = torch.cuda.current_stream(both.device) if fork else None
+            if fork:
+                side = self._side_streams.get(both.device)
+                if side is None:
+                    side = self._side_streams[both.device] = torch.cuda.Stream(device=both.device)
+                side.wait_stream(cur)
+            with (torch.cuda.stream(side) if fork else contextlib.nullcontext()):
+                stems = [self.stem_2(both, eng)]
+                for n in (4, 8, 16):
+                    if hasattr(self, "stem_%d" % n):
+                        stems.append(getattr(self, "stem_%d" % n)(stems[-1], eng))
             feats = self.feature(both, eng if self.feature.esm_capable else "torch")
             if self.vol_size in (4, 8):
                 feats = self.feature_up(feats, eng)
-            stems = [self.stem_2(both, eng)]
-            for n in (4, 8, 16):
-                if hasattr(self, "stem_%d" % n):
-                    stems.append(getattr(self, "stem_%d" % n)(stems[-1], eng))
+            if fork:
+                cur.wait_stream(side)
+                for t in stems:
+                    t.record_stream(cur)
             coarse = {4: feats[0], 8: feats[1], 16: feats[3]}[self.vol_size]
             match = fused(self._desc_pc, self.desc, None, self.conv([coarse, stems[-1]], eng), None, eng)
             fl = [f[:B] for f in feats]
@@ -282,7 +299,7 @@ class GraphedStereo:
 
 class StereoPipeline:
     """Host-to-host serving loop around a `GraphedStereo`: pinned host images in, pinned host disparity out.  The H2D
-    copy of pair i+1 and the D2H copy of pair i-1 run on a separate copy stream and overlap the graph replay of pair i:
+    copy of pair i+1 and the D2H copy of pair i-1 run on two copy streams and overlap the graph replay of pair i:
     the replay's output is first moved to a per-slot device buffer on the compute stream (so the next replay can start
     at once), the D2H copy of that buffer then goes on the copy stream.
 
@@ -294,8 +311,10 @@ class StereoPipeline:
     def __init__(self, graphed: GraphedStereo, depth: int = 2, pick=lambda out: out[-1]) -> None:
         self.g, self.depth, self.pick = graphed, depth, pick
         dev = graphed.left.device
-        self.copy_stream = torch.cuda.Stream(device=dev)
-        example = pick(graphed.out)
+        self.copy_stream = torch.cuda.Stream(device=dev)   # host -> device
+        self.down_stream = torch.cuda.Stream(device=dev)   # device -> host: its own stream, or the H2D of pair i+1 would queue behind
+        example = pick(graphed.out)                        # the D2H of pair i, which waits for replay i
+
         self.slots = []
         for _ in range(depth):
             self.slots.append(dict(
@@ -323,10 +342,10 @@ class StereoPipeline:
         slot["consumed"].record(cur)
         slot["dev_out"].copy_(out, non_blocking=True)
         slot["replayed"].record(cur)
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(slot["replayed"])
+        with torch.cuda.stream(self.down_stream):
+            self.down_stream.wait_event(slot["replayed"])
             slot["out"].copy_(slot["dev_out"], non_blocking=True)
-            slot["done"].record(self.copy_stream)
+            slot["done"].record(self.down_stream)
         self.submitted += 1
 
     def result(self) -> torch.Tensor:
