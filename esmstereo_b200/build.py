@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libesm_b200.so")
-SOURCES = ["api.cu", "conv.cu", "conv_k1.cu", "conv_k2.cu", "conv_k3.cu", "conv_k3s2.cu", "conv_k5.cu", "conv_tc.cu", "conv_tcg.cu", "conv_tcf.cu", "conv_pw.cu", "volume.cu", "regress.cu",
+SOURCES = ["api.cu", "conv.cu", "conv_k1.cu", "conv_k2.cu", "conv_k3.cu", "conv_k3s2.cu", "conv_k5.cu", "conv_tc.cu", "conv_tcg.cu", "conv_tcf.cu", "conv_pw.cu", "conv_stem3.cu", "volume.cu", "regress.cu",
            "mixer.cu", "conf.cu", "prepost.cu", "peak.cu", "backbone.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]

@@ -625,6 +625,10 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
 
   const bool gwc = d->src_mode == ESM_SRC_GWC;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    static const bool stem3_on = !(getenv("ESM_STEM3") && getenv("ESM_STEM3")[0] == '0');
+    if (stem3_on && !getenv("ESM_TC_FORCE") && stem3_eligible(d)) return stem3_launch(d, st);
+  }
   LayerGeom lg;
   lg.S = S;
   lg.gwc = gwc;

@@ -49,6 +49,10 @@ struct PwPlan {
 bool pw_conv_plan(const esm_conv_t* d, PwPlan* plan);
 int pw_conv_launch(const esm_conv_t* d, const PwPlan& plan, cudaStream_t st);
 
+// Dedicated kernel for the 3 -> C k3 stride-2 image-side layers (conv_stem3.cu): exact fp32, taken whenever eligible.
+bool stem3_eligible(const esm_conv_t* d);
+int stem3_launch(const esm_conv_t* d, cudaStream_t st);
+
 // Fills `plan` and returns true when `d` can run on the tensor-core path.
 bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan);
 int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st);

@@ -706,3 +706,16 @@ def test_disparity_publish_matches_opencv_semantics():
     want = torch.clamp(torch.round(med * 256.0), 0, 65535).to(torch.int32)
     got = ops.disparity_publish_u16(d.cuda(), (h, w), 192.0, 256.0).cpu().to(torch.int32)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("cout,act,shape,batch", [(32, "relu6", (96, 160), 2), (32, "gelu", (75, 131), 1), (16, "gelu", (130, 66), 1)])
+def test_image_stem_kernel(cout, act, shape, batch):
+    """conv_stem / stem_2[0] (3 -> C, k3 s2 p1 + BN + activation; ESMStereo.py:49,529-533) on the dedicated kernel
+    (conv_stem3.cu): even / odd sizes, partial tiles, both channel widths, a strided (pitched) input view."""
+    ops = _ops()
+    p = make_layer(3, cout, 3, 2, seed=cout + shape[0])
+    buf = rnd(batch, 3, shape[0], shape[1] + 5, seed=2)
+    x = buf[..., : shape[1]]
+    want = ref_conv(x.contiguous(), p, 2, 1, False, act, 2)
+    got = ops.conv(buf.cuda()[..., : shape[1]], gpu_pack(p, 2, 1, False), act)
+    assert rel(got, want) < 2e-6, (cout, shape)
