@@ -89,6 +89,7 @@ SIGNATURES = {
     "esm_bilinear_add_f32": (C.c_int, [vp, vp, vp] + [C.c_int] * 4 + [C.c_float, vp]),
     "esm_sm_pointwise_f32": (C.c_int, [vp, vp] + [C.c_int] * 4 + [C.POINTER(EsmMixerMlp), vp, vp]),
     "esm_sm_spatial_f32": (C.c_int, [vp, vp] + [C.c_int] * 4 + [vp, vp, C.c_int, C.POINTER(EsmMixerMlp), vp, vp]),
+    "esm_sm_layer_f32": (C.c_int, [vp, vp] + [C.c_int] * 4 + [C.POINTER(EsmMixerMlp), vp, vp, C.c_int, C.POINTER(EsmMixerMlp), vp, vp]),
     "esm_laf_cost_top7_f32": (C.c_int, [vp, vp] + [C.c_int] * 4 + [vp]),
     "esm_laf_attention_f32": (C.c_int, [vp] * 7 + [C.c_int] * 4 + [vp]),
     "esm_laf_sample_embed_f32": (C.c_int, [vp] * 8 + [C.c_int] * 4 + [vp]),

@@ -177,6 +177,99 @@ __global__ void __launch_bounds__(SP_TX * SP_TY) sm_spatial_kernel(const float* 
   }
 }
 
+
+// ---- whole SMLayer in one kernel (shufflemixer.py:97-112): u = shuffle(MLP1(LN1(x))) + x; t = depthwise7x7(u) + b;
+// y = shuffle(MLP2(LN2(t))) + t [+ extra].  A CTA owns a 32 x 8 output tile: phase A runs the pointwise half on the
+// tile + 3-pixel halo (the halo pixels are recomputed, 532 pixels for 256 outputs: that half is ~450 instructions per
+// pixel) and leaves it in shared memory -- zeros outside the image, which is the depthwise conv's padding -- phase B
+// gives every thread two horizontally adjacent pixels: one LDS.64 row segment and one padded weight row (2 x LDS.128)
+// feed 14 FMAs, against two loads per FMA in sm_spatial_kernel (LDS-bound: 20 us per launch at 96 x 312 x 16).
+constexpr int SL_TW = 32, SL_TH = 8, SL_K = 7, SL_R = SL_K / 2;
+constexpr int SL_PW = SL_TW + SL_K - 1, SL_PH = SL_TH + SL_K - 1;  // 38 x 14
+
+template <int C>
+__global__ void __launch_bounds__(SL_TW / 2 * SL_TH) sm_layer_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W,
+                                                                      esm_mixer_mlp_t m1, const float* __restrict__ dw_w,
+                                                                      const float* __restrict__ dw_b, esm_mixer_mlp_t m2,
+                                                                      const float* __restrict__ extra) {
+  __shared__ MlpSmem<C> s1, s2;
+  __shared__ __align__(16) float s_w[C][SL_K][8];  // depthwise rows padded to 8 floats
+  __shared__ float s_b[C];
+  __shared__ __align__(16) float tile[C][SL_PH][SL_PW];
+  const int tid = threadIdx.x, nt = SL_TW / 2 * SL_TH;
+  load_mlp<C>(s1, m1, tid, nt);
+  load_mlp<C>(s2, m2, tid, nt);
+  for (int i = tid; i < C * SL_K * 8; i += nt) {
+    const int kx = i & 7, ky = (i >> 3) % SL_K, c = i / (8 * SL_K);
+    s_w[c][ky][kx] = kx < SL_K ? dw_w[(c * SL_K + ky) * SL_K + kx] : 0.f;
+  }
+  for (int i = tid; i < C; i += nt) s_b[i] = dw_b[i];
+  __syncthreads();
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * SL_TW - SL_R, y0 = blockIdx.y * SL_TH - SL_R;
+  const long long plane = (long long)H * W;
+  const float* xb = x + (long long)b * C * plane;
+  // phase A: pointwise half on the haloed tile
+  for (int i = tid; i < SL_PH * SL_PW; i += nt) {
+    const int ty = i / SL_PW, tx = i - ty * SL_PW;
+    const int gy = y0 + ty, gx = x0 + tx;
+    float t[C];
+    if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) {
+      const float* p = xb + (long long)gy * W + gx;
+#pragma unroll
+      for (int c = 0; c < C; ++c) t[c] = __ldg(p + c * plane);
+      ln_mlp_shuffle_residual<C>(t, s1);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) t[c] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) tile[c][ty][tx] = t[c];
+  }
+  __syncthreads();
+  // phase B: depthwise 7 x 7 on two adjacent pixels, then the second pointwise half
+  const int lx = tid % (SL_TW / 2), ly = tid / (SL_TW / 2);
+  const int px = blockIdx.x * SL_TW + 2 * lx, py = blockIdx.y * SL_TH + ly;
+  float t0[C], t1[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float a0 = s_b[c], a1 = a0;
+#pragma unroll
+    for (int ky = 0; ky < SL_K; ++ky) {
+      const float2* rp = reinterpret_cast<const float2*>(&tile[c][ly + ky][2 * lx]);
+      const float2 r01 = rp[0], r23 = rp[1], r45 = rp[2], r67 = rp[3];
+      const float r[8] = {r01.x, r01.y, r23.x, r23.y, r45.x, r45.y, r67.x, r67.y};
+      const float4 wa = *reinterpret_cast<const float4*>(&s_w[c][ky][0]), wb = *reinterpret_cast<const float4*>(&s_w[c][ky][4]);
+      const float w[7] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
+#pragma unroll
+      for (int kx = 0; kx < SL_K; ++kx) {
+        a0 = fmaf(w[kx], r[kx], a0);
+        a1 = fmaf(w[kx], r[kx + 1], a1);
+      }
+    }
+    t0[c] = a0;
+    t1[c] = a1;
+  }
+  if (py >= H || px >= W) return;
+  const long long base = (long long)b * C * plane + (long long)py * W + px;
+  ln_mlp_shuffle_residual<C>(t0, s2);
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float v = t0[c];
+    if (extra) v += __ldg(extra + base + c * plane);
+    y[base + c * plane] = v;
+  }
+  if (px + 1 < W) {
+    ln_mlp_shuffle_residual<C>(t1, s2);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float v = t1[c];
+      if (extra) v += __ldg(extra + base + 1 + c * plane);
+      y[base + 1 + c * plane] = v;
+    }
+  }
+}
+
 static int check_mlp(const esm_mixer_mlp_t* m, int C) {
   ESM_REQUIRE(m && m->ln_w && m->fc0_w && m->fc0_b && m->fc2_w && m->fc2_b, "mixer: null MLP parameter");
   ESM_REQUIRE(m->hidden == C, "mixer: hidden (%d) must equal C (%d) (mlp_ratio 2 on C/2)", m->hidden, C);
@@ -222,4 +315,22 @@ extern "C" int esm_sm_spatial_f32(const float* x, float* y, int B, int C, int H,
   else
     sm_spatial_kernel<8, 0><<<grid, block, smem, st>>>(x, y, H, W, dw_w, dw_b, k, *mlp, extra_residual);
   return check_launch("sm_spatial");
+}
+
+extern "C" int esm_sm_layer_f32(const float* x, float* y, int B, int C, int H, int W, const esm_mixer_mlp_t* mlp1, const float* dw_w,
+                                const float* dw_b, int k, const esm_mixer_mlp_t* mlp2, const float* extra_residual, void* stream) {
+  ESM_REQUIRE(x && y && dw_w && dw_b && B > 0 && H > 0 && W > 0, "sm_layer: null pointer or empty shape");
+  ESM_REQUIRE(C == 8 || C == 16, "sm_layer: C must be 8 or 16 (got %d)", C);
+  ESM_REQUIRE(k == SL_K, "sm_layer: depthwise kernel must be 7 (got %d): use esm_sm_pointwise_f32 + esm_sm_spatial_f32", k);
+  ESM_REQUIRE(x != y, "sm_layer: in-place not supported (halo reads)");
+  if (int e = check_mlp(mlp1, C)) return e;
+  if (int e = check_mlp(mlp2, C)) return e;
+  ESM_REQUIRE(B <= 65535 && ceil_div(H, SL_TH) <= 65535, "sm_layer: grid too large");
+  dim3 grid((unsigned)ceil_div(W, SL_TW), (unsigned)ceil_div(H, SL_TH), (unsigned)B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 16)
+    sm_layer_kernel<16><<<grid, SL_TW / 2 * SL_TH, 0, st>>>(x, y, H, W, *mlp1, dw_w, dw_b, *mlp2, extra_residual);
+  else
+    sm_layer_kernel<8><<<grid, SL_TW / 2 * SL_TH, 0, st>>>(x, y, H, W, *mlp1, dw_w, dw_b, *mlp2, extra_residual);
+  return check_launch("sm_layer");
 }

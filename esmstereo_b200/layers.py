@@ -8,6 +8,7 @@ Inference only: BatchNorm is folded from its running statistics (eval semantics)
 """
 from __future__ import annotations
 
+import os
 import threading
 from typing import List, Optional, Sequence, Tuple
 
@@ -235,7 +236,7 @@ class LayerNorm(nn.Module):
 
 
 class SMLayer(nn.Module):
-    """LN -> split-MLP -> shuffle -> +x ; depthwise kxk ; LN -> split-MLP -> shuffle -> +x, as two kernels."""
+    """LN -> split-MLP -> shuffle -> +x ; depthwise kxk ; LN -> split-MLP -> shuffle -> +x, as one kernel (k = 7) or two."""
 
     def __init__(self, dim: int, kernel_size: int, mlp_ratio: int = 2) -> None:
         super().__init__()
@@ -243,6 +244,10 @@ class SMLayer(nn.Module):
         self.spatial = nn.Conv2d(dim, dim, kernel_size, 1, kernel_size // 2, groups=dim)
         self.mlp1, self.mlp2 = SplitPointMlp(dim, mlp_ratio), SplitPointMlp(dim, mlp_ratio)
         self._c1, self._c2 = _Packed(), _Packed()
+        # ESM_SMLAYER=1: one launch per SMLayer (esm_sm_layer_f32).  Measured SLOWER than the two half kernels at KITTI
+        # shape (+8 us per layer): 120 CTAs of 4 warps leave one warp per scheduler, nothing hides the dependent-issue
+        # latency of the halo recompute.  Kept for the C ABI and as the record of the experiment; default off.
+        self.fused = os.environ.get("ESM_SMLAYER", "0") == "1"
 
     def _mlp(self, cache: _Packed, norm: LayerNorm, mlp: SplitPointMlp) -> ops.MixerMlp:
         ts = [norm.body.weight, mlp.fc[0].weight, mlp.fc[0].bias, mlp.fc[2].weight, mlp.fc[2].bias]
@@ -250,9 +255,11 @@ class SMLayer(nn.Module):
 
     def forward(self, x: torch.Tensor, extra_residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         _inference_only(self)
-        x = ops.sm_pointwise(x, self._mlp(self._c1, self.norm1, self.mlp1))
-        return ops.sm_spatial(x, self.spatial.weight.detach(), self.spatial.bias.detach(),
-                              self._mlp(self._c2, self.norm2, self.mlp2), extra_residual)
+        m1, m2 = self._mlp(self._c1, self.norm1, self.mlp1), self._mlp(self._c2, self.norm2, self.mlp2)
+        if self.spatial.kernel_size[0] == 7 and self.fused:
+            return ops.sm_layer(x, m1, self.spatial.weight.detach(), self.spatial.bias.detach(), m2, extra_residual)
+        x = ops.sm_pointwise(x, m1)
+        return ops.sm_spatial(x, self.spatial.weight.detach(), self.spatial.bias.detach(), m2, extra_residual)
 
 
 class FMBlock(nn.Module):

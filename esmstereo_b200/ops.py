@@ -520,6 +520,21 @@ def sm_spatial(x: torch.Tensor, dw_w: torch.Tensor, dw_b: torch.Tensor, mlp: Mix
     return y
 
 
+def sm_layer(x: torch.Tensor, mlp1: MixerMlp, dw_w: torch.Tensor, dw_b: torch.Tensor, mlp2: MixerMlp,
+             extra_residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A whole SMLayer (shufflemixer.py:97-112) in one launch (depthwise kernel 7)."""
+    x = _dev(x, "x").contiguous()
+    if extra_residual is not None:
+        extra_residual = _dev(extra_residual, "extra_residual").contiguous()
+    B, Cc, H, W = x.shape
+    y = torch.empty_like(x)
+    k = dw_w.shape[-1]
+    with _Prof("sm_layer C%d k%d %dx%d" % (Cc, k, H, W)):
+        check(lib().esm_sm_layer_f32(x.data_ptr(), y.data_ptr(), B, Cc, H, W, C.byref(mlp1.s), dw_w.data_ptr(), dw_b.data_ptr(), k,
+                                     C.byref(mlp2.s), _ptr(extra_residual), _stream()), "sm_layer")
+    return y
+
+
 # ---------------------------------------------------------------------------------------------
 # confidence head pieces (ESMStereo_confidence.py:511-744)
 # ---------------------------------------------------------------------------------------------

@@ -226,6 +226,9 @@ struct Engine {
     if (n == "esm_sm_pointwise_f32") return esm_sm_pointwise_f32(CFP(0), FP(1), I(2), I(3), I(4), I(5), (const esm_mixer_mlp_t*)P(6), CFP(7), st);
     if (n == "esm_sm_spatial_f32")
       return esm_sm_spatial_f32(CFP(0), FP(1), I(2), I(3), I(4), I(5), CFP(6), CFP(7), I(8), (const esm_mixer_mlp_t*)P(9), CFP(10), st);
+    if (n == "esm_sm_layer_f32")
+      return esm_sm_layer_f32(CFP(0), FP(1), I(2), I(3), I(4), I(5), (const esm_mixer_mlp_t*)P(6), CFP(7), CFP(8), I(9),
+                              (const esm_mixer_mlp_t*)P(10), CFP(11), st);
     if (n == "esm_laf_cost_top7_f32") return esm_laf_cost_top7_f32(CFP(0), FP(1), I(2), I(3), I(4), I(5), st);
     if (n == "esm_laf_attention_f32") return esm_laf_attention_f32(CFP(0), CFP(1), CFP(2), CFP(3), CFP(4), CFP(5), FP(6), I(7), I(8), I(9), I(10), st);
     if (n == "esm_laf_sample_embed_f32")

@@ -211,6 +211,12 @@ int esm_sm_spatial_f32(const float* x, float* y, int B, int C, int H, int W, con
                        const float* dw_b /*[C]*/, int k, const esm_mixer_mlp_t* mlp, const float* extra_residual,
                        void* stream);
 
+/* A whole SMLayer (shufflemixer.py:97-112) in one launch, k = 7: pointwise half with mlp1 on the tile + halo in shared
+ * memory, depthwise 7x7 + bias, pointwise half with mlp2, optional extra residual.  Same arithmetic as
+ * esm_sm_pointwise_f32 followed by esm_sm_spatial_f32. */
+int esm_sm_layer_f32(const float* x, float* y, int B, int C, int H, int W, const esm_mixer_mlp_t* mlp1, const float* dw_w,
+                     const float* dw_b, int k, const esm_mixer_mlp_t* mlp2, const float* extra_residual, void* stream);
+
 /* LAFNet cost tower front end (ESMStereo_confidence.py:645-653): per pixel
  * softmax(-cost/||cost||_2 * 100) over D, then the 7 largest probabilities, descending.
  * cost [B,D,H,W] (D <= 64) -> out [B,7,H,W]. */

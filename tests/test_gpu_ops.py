@@ -248,6 +248,16 @@ def test_shufflemixer_block(C):
     want = EsmOracle({"b." + k: v for k, v in sd.items()}, 192).fm_block(x, "b")
     got = blk.cuda().eval()(x.cuda())
     assert rel(got, want) < 2e-5
+    # the fused SMLayer kernel (one launch) against the two half kernels: same arithmetic, bit for bit; odd sizes / partial tiles
+    for shape in ((2, C, 12, 40), (1, C, 21, 45), (1, C, 96, 312)):
+        xs = rnd(*shape, seed=shape[2]).cuda()
+        for lay in (blk.net[0], blk.net[1]):
+            lay.fused = True
+            a = lay(xs, extra_residual=xs)
+            lay.fused = False
+            b = lay(xs, extra_residual=xs)
+            lay.fused = True
+            assert torch.equal(a, b), shape
 
 
 def test_laf_pieces():
