@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(SL_TW / 2 * SL_TH) sm_layer_kernel(const float
   }
 }
 
+
 static int check_mlp(const esm_mixer_mlp_t* m, int C) {
   ESM_REQUIRE(m && m->ln_w && m->fc0_w && m->fc0_b && m->fc2_w && m->fc2_b, "mixer: null MLP parameter");
   ESM_REQUIRE(m->hidden == C, "mixer: hidden (%d) must equal C (%d) (mlp_ratio 2 on C/2)", m->hidden, C);

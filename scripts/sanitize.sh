@@ -5,6 +5,8 @@
 # The pinned engine plans keep the autotuner out of the run (no timing loops under the sanitizer).  tcgen05 / TMA
 # kernels are covered by memcheck (global + shared accesses of the generic proxy); racecheck sees their mbarrier-ordered
 # shared-memory traffic only partly (async-proxy writes are not tracked), so its verdict applies to the generic-proxy kernels.
+# (This pool refuses compute-sanitizer -- "closed on this pool and stays closed", profiles/r02_sanitize.txt -- so the
+# committed evidence is the script; the parity tests' small cases and the engines' bounds checks stand in for it.)
 set -u
 export ESM_BACKBONE=standin
 SEL="tests/test_gpu_ops.py tests/test_aux_ops.py tests/test_gpu_pf.py"
