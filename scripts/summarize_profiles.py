@@ -92,10 +92,12 @@ def full():
                 key = "agg_conv3d_8_8"
             if "tc_conv_kernel<24, 1, 3, 0" in name:
                 key = "hourglass_conv3d_24_24"
-            if "tcg_conv_kernel<3, 1, 1>" in name:
-                key = "hourglass_conv3d_40_40"
-            if "tcg_conv_kernel<2, 2, 1>" in name:
-                key = "hourglass_deconv3d_40_24"
+            if "tc_conv_kernel<24, 1, 3, 0" in name:
+                key = "hourglass_conv3d_level1"
+            if "tcf_conv_kernel" in name and "hourglass_conv3d_level2" not in traffic:
+                key = "hourglass_conv3d_level2"      # prof_conv.py runs the 40 -> 40 conv before the 40 -> 24 transposed conv
+            elif "tcf_conv_kernel" in name:
+                key = "hourglass_deconv3d_level2"
             if key:
                 traffic[key] = byts
     with open(os.path.join(OUT, "traffic.json"), "w") as f:
