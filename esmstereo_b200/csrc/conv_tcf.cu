@@ -776,6 +776,8 @@ extern "C" int esm_conv_pf_f32(const esm_conv_pf_t* d, void* stream) {
   const int maxslots = TF_ACC_COLS / (2 * k.NT);
   ESM_REQUIRE(maxslots >= 1, "conv_pf: channel tile too wide");
   if (npart > maxslots) npart = maxslots;
+  if (getenv("ESM_TCF_NPART")) npart = atoi(getenv("ESM_TCF_NPART"));
+  if (npart > maxslots) npart = maxslots;
   if (npart > SPI) npart = SPI;
   if (npart < 1) npart = 1;
   k.NPART = npart;

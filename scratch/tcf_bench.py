@@ -55,7 +55,7 @@ def layer(cin, cout, k, nd, shape, stride=1, transposed=False, out="pf"):
         "deconv" if transposed else "conv", nd, cin, cout, k, stride, "x".join(map(str, shape)), t_old, t_new, fl / t_new / 1e6, t_cvt), flush=True)
 
 
-which = sys.argv[1:] 
+which = sys.argv[1:]
 L = [
     (32, 32, 3, 2, (192, 624)), (64, 32, 3, 2, (192, 624)), (32, 16, 3, 2, (192, 624)), (96, 32, 1, 2, (192, 624)),
     (32, 32, 3, 2, (96, 312)), (80, 32, 3, 2, (96, 312)), (96, 64, 3, 2, (96, 312)), (48, 48, 3, 2, (96, 312)), (112, 32, 1, 2, (96, 312)),
@@ -63,6 +63,11 @@ L = [
     (24, 24, 3, 3, (24, 48, 156)), (48, 24, 1, 3, (24, 48, 156)), (40, 40, 3, 3, (12, 24, 78)), (80, 40, 1, 3, (12, 24, 78)), (72, 72, 3, 3, (6, 12, 39)),
     (8, 8, 3, 3, (48, 96, 312)), (24, 8, 3, 3, (24, 48, 156)),
 ]
+if which:
+    for spec in which:
+        v = spec.split(",")
+        layer(int(v[0]), int(v[1]), int(v[2]), int(v[3]), tuple(int(t) for t in v[4].split("x")), int(v[5]) if len(v) > 5 else 1, len(v) > 6 and v[6] == "T")
+    sys.exit(0)
 for a in L:
     layer(*a)
 S = [
