@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libesm_b200.so")
+LIB_PATH = os.path.join(_HERE, "csrc", "libesm_b200_prof.so" if os.environ.get("ESM_TC_PROFILE") == "1" else "libesm_b200.so")
 
 ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "silu": 3, "sigmoid": 4, "2sigmoid": 5, "relu6": 6}
 SRC_TENSORS, SRC_GWC = 0, 1
@@ -62,6 +62,7 @@ class EsmConvPf(C.Structure):
 SIGNATURES = {
     "esm_last_error": (C.c_char_p, []),
     "esm_version": (C.c_int, []),
+    "esm_set_pdl": (C.c_int, [C.c_int]),
     "esm_device_info": (C.c_int, [i32p, i32p, i32p]),
     "esm_packed_weight_elems": (C.c_longlong, [C.c_int] * 6),
     "esm_pack_conv_weight_f32": (C.c_int, [vp, vp] + [C.c_int] * 6 + [vp]),

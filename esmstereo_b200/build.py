@@ -34,7 +34,9 @@ def _stale(target, deps):
 
 def build(force: bool = False, verbose: bool = True) -> str:
     nvcc = _nvcc()
-    objdir = os.path.join(CSRC, "build")
+    prof = os.environ.get("ESM_TC_PROFILE") == "1"  # diagnostics build: its own objects and library, next to the product's
+    objdir = os.path.join(CSRC, "build_prof" if prof else "build")
+    LIB = os.path.join(CSRC, "libesm_b200_prof.so" if prof else "libesm_b200.so")
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "conv_kernel.cuh"), os.path.join(CSRC, "conv_tc.cuh"), os.path.join(CSRC, "tc_common.cuh"),
                os.path.join(os.path.dirname(os.path.dirname(CSRC)), "include", "esm_b200.h")]

@@ -2,6 +2,11 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
+
+#ifndef ESM_PDL_DEFAULT
+#define ESM_PDL_DEFAULT 0  // off: measured slower on the whole forward
+#endif
 
 namespace esm {
 
@@ -24,6 +29,16 @@ int check_launch(const char* what) {
   return ESM_OK;
 }
 
+static int g_pdl_mask = -1;
+static int pdl_mask() {
+  if (g_pdl_mask < 0) {
+    const char* e = getenv("ESM_PDL");
+    g_pdl_mask = e ? atoi(e) : ESM_PDL_DEFAULT;
+  }
+  return g_pdl_mask;
+}
+bool pdl_enabled(int family_bit) { return (pdl_mask() & family_bit) != 0; }
+
 __global__ void fill_kernel(float* p, long long n, float v) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -35,6 +50,11 @@ using namespace esm;
 
 extern "C" const char* esm_last_error(void) { return g_err; }
 extern "C" int esm_version(void) { return 100; }
+extern "C" int esm_set_pdl(int mask) {
+  const int prev = pdl_mask();
+  g_pdl_mask = mask & 63;
+  return prev;
+}
 
 extern "C" int esm_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

@@ -19,6 +19,32 @@ int check_launch(const char* what);
     }                                     \
   } while (0)
 
+// Programmatic dependent launch (PDL).  A kernel launched through launch_k(pdl = true, ...) may start while the previous
+// kernel of the stream is still draining: its CTAs are placed as soon as every CTA of that kernel has executed
+// pdl_launch_dependents() (first instruction of every kernel here) and resources are free.  EVERY kernel launched that
+// way executes pdl_wait() in every thread before its first global-memory access (weights included), which blocks until
+// the previous grid has completed and flushed; what overlaps is launch latency, CTA placement and the on-chip prologue
+// (mbarrier init, TMEM allocation).  ESM_PDL is a bit mask of the kernel families that use it: 1 FP32-pipe conv, 2
+// resident tcgen05, 4 streamed tcgen05, 8 flat tcgen05, 16 pointwise, 32 everything else on the forward path.
+bool pdl_enabled(int family_bit);
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... Params, typename... Args>
+static inline cudaError_t launch_k(bool pdl, void (*fn)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, fn, static_cast<Params>(args)...);
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

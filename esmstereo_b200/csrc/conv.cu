@@ -465,12 +465,9 @@ static int launch_plan(const esm_conv_t* d, const PackGeom& g, ConvK k, const Pl
         return check_launch("conv(cudaFuncSetAttribute)");
   }
   const long long resident = (long long)num_sms * plan.blocks_per_sm;
-  // Optional programmatic stream serialization (PDL, ESM_PDL=1): the kernel's prologue (mbarrier init,
-  // descriptor fetch) may overlap the tail of the previous kernel; it waits on griddepcontrol.wait
-  // before its first global access.  Measured on B200 it LOSES 5% end to end on this graph (206 vs 218
-  // pairs/s): early-launched dependents take SM slots from the persistent CTAs still running, so it is off
-  // by default.
-  static const bool pdl = getenv("ESM_PDL") != nullptr;
+  // Programmatic dependent launch (common.cuh), family bit 1.  Round 1 measured it as a 5% LOSS on this engine with the
+  // trigger in the last work item; it is re-measured with the trigger at kernel start.
+  const bool pdl = pdl_enabled(1);
   auto launch = [&](conv_fn_t fn, unsigned grid, const ConvK& kk) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -417,8 +417,8 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
     tma_load_5d(s_R, &maps.src[1], rx0, ih0, 0, c0 * p.cpg, t.b, bar);
     tma_load_3d(s_w0 + (item % 3) * w_elems, &maps.w, t.co_base, c0, t.z * taps, bar);
   };
-  // Programmatic dependent launch: do not touch global memory until the previous grid has completed and
-  // flushed (the trigger for our own dependents is in the work loop).
+  // Programmatic dependent launch (common.cuh): no global-memory access before pdl_wait().
+  pdl_launch_dependents();
   if (TMA) {
     if (tid == 0) {
 #pragma unroll
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
     }
     __syncthreads();
   }
-  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  pdl_wait();
 
   float2 acc[NV][COG / 2];
 #pragma unroll
@@ -471,8 +471,6 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
   }
 
   for (int item = 0; item < n_items; ++item) {
-    // this CTA is about to start its last work item: let the next kernel's CTAs take the slots that free up
-    if (item == n_items - 1) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     const int stage = (TMA && !GWC) ? item % NS : (item & 1);
     const float* s_in = s_in0 + stage * in_elems;
     const float* s_w;

@@ -62,6 +62,8 @@ constexpr int PW_THREADS = 128;
 template <int CO>
 __global__ void __launch_bounds__(PW_THREADS) pw_conv_kernel(const __grid_constant__ PwK p) {
   extern __shared__ __align__(16) float s_w[];  // [tap][Cin][CO]: this tile's weights, then [2][CO] scale / shift
+  pdl_launch_dependents();
+  pdl_wait();
   const int co0 = blockIdx.y * CO;
   const int b = blockIdx.z;
   const int taps = p.KH * p.KW;
@@ -264,7 +266,7 @@ int pw_conv_launch(const esm_conv_t* d, const PwPlan& plan, cudaStream_t st) {
   void (*fn)(const PwK) = plan.CO == 8 ? pw_conv_kernel<8> : plan.CO == 16 ? pw_conv_kernel<16> : plan.CO == 24 ? pw_conv_kernel<24> : pw_conv_kernel<32>;
   if (plan.smem > 48 * 1024 && cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
     return check_launch("conv(pw, cudaFuncSetAttribute)");
-  fn<<<grid, PW_THREADS, plan.smem, st>>>(k);
+  launch_k(pdl_enabled(16), fn, grid, dim3(PW_THREADS), plan.smem, st, k);
   ++pw_launches;
   return check_launch("conv(pw)");
 }

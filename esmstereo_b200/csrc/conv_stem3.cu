@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(2 * S3_GX * S3_GY) stem3_kernel(const Stem3K p
   __shared__ float s_in[3][S3_IH][2][S3_HALF];
   __shared__ float s_aff[2][CO];
   const int tid = threadIdx.x, nt = 2 * S3_GX * S3_GY;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = tid; i < 27 * CO; i += nt) {
     const int co = i % CO, t = i / CO;  // t = tap * 3 + ci
     const int tap = t / 3, ci = t % 3;
@@ -180,9 +182,9 @@ int stem3_launch(const esm_conv_t* d, cudaStream_t st) {
   k.out = d->out; k.oB = d->oB; k.oC = d->oC; k.oH = d->oH;
   dim3 grid((unsigned)ceil_div(d->Wout, S3_OW), (unsigned)ceil_div(d->Hout, S3_OH), (unsigned)d->B), block(2 * S3_GX * S3_GY);
   if (d->Cout <= 16)
-    stem3_kernel<16><<<grid, block, 0, st>>>(k);
+    launch_k(pdl_enabled(32), stem3_kernel<16>, grid, block, 0, st, k);
   else
-    stem3_kernel<32><<<grid, block, 0, st>>>(k);
+    launch_k(pdl_enabled(32), stem3_kernel<32>, grid, block, 0, st, k);
   return check_launch("conv(stem3)");
 }
 

@@ -103,12 +103,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   uint64_t* empty = full + NS;
   uint64_t* accf = empty + NS;
   uint64_t* acce = accf + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + 2);
+  uint64_t* wready = acce + 2;  // the resident weights are staged (one arrival per staging warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wready + 1);
   float* s_aff = reinterpret_cast<float*>(tmem_slot + 2);  // [2][COT] scale, shift of this channel tile
   const int cot = blockIdx.x / p.ctas_per_cot;
   const int cta = blockIdx.x % p.ctas_per_cot;
   const int nsteps = p.rows + 2 * HALO;
 
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
       tc_mbar_init(&full[i], TC_NTW);
@@ -118,57 +120,70 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       tc_mbar_init(&accf[i], TZ);
       tc_mbar_init(&acce[i], TC_NEW);
     }
+    tc_mbar_init(wready, TC_PROD_WARP);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();  // nothing above touches global memory
   if (tid < 2 * COT) {
     const int c = tid % COT, co = cot * COT + c;
     const float* src = tid < COT ? p.scale : p.shift;
     s_aff[tid] = (src && co < p.Cout) ? __ldg(src + co) : (tid < COT ? 1.f : 0.f);
   }
-  // resident weights of this channel tile: split and laid out as UMMA B operands
-  // (row n = co*TAPS + kh*3+kw: the 9 taps of a channel are adjacent accumulator columns; K = 8 channels of group cg)
-  {
-    const int total = ncg * KD * NB * 8;
-    constexpr int U = 4;
-    for (int base = tid; base < total; base += U * TC_THREADS) {
-      float w[U];
-      uint32_t off[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int idx = base + u * TC_THREADS;
-        const int col = idx % COT;
-        int t = idx / COT;
-        const int k = t & 7;
-        t >>= 3;
-        const int tap2 = t % TAPS;
-        t /= TAPS;
-        const int kd = t % KD;
-        const int cg = t / KD;
-        const int co = cot * COT + col, ci = cg * 8 + k;
-        w[u] = 0.f;
-        if (idx < total && co < p.CoutPad && ci < p.CinPad)
-          w[u] = (GWC ? 0.5f : 1.0f) * __ldg(p.weight + ((long long)(kd * TAPS + tap2) * p.CinPad + ci) * p.CoutPad + co);
-        off[u] = (uint32_t)((cg * KD + kd) * 2) * WSLAB + (uint32_t)(k >> 2) * (NB * 16) + (uint32_t)(col * TAPS + tap2) * 16 + (k & 3) * 4;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (base + u * TC_THREADS < total) {
-          const float hi = tc_rna(w[u]);
-          *reinterpret_cast<float*>(s_w + off[u]) = hi;
-          *reinterpret_cast<float*>(s_w + off[u] + WSLAB) = tc_lo(w[u], hi);
-        }
-      }
-    }
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
+  // The producers start on the first operand stage right away (its exposed global-load latency used to come after the
+  // weight staging: 3.5 k clk of prologue on a 14 k clk layer); the epilogue and MMA warps, idle until the first
+  // accumulator is ready, stage the weights meanwhile and the MMA issuers wait on `wready` before their first MMA.
+  if (warp < TC_PROD_WARP) {
+    constexpr int TC_STAGERS = 32 * TC_PROD_WARP;
+    // resident weights of this channel tile: split and laid out as UMMA B operands
+    // (row n = co*TAPS + kh*3+kw: the 9 taps of a channel are adjacent accumulator columns; K = 8 channels of group cg)
+    {
+      const int total = ncg * KD * NB * 8;
+      constexpr int U = 4;
+      for (int base = tid; base < total; base += U * TC_STAGERS) {
+        float w[U];
+        uint32_t off[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int idx = base + u * TC_STAGERS;
+          const int col = idx % COT;
+          int t = idx / COT;
+          const int k = t & 7;
+          t >>= 3;
+          const int tap2 = t % TAPS;
+          t /= TAPS;
+          const int kd = t % KD;
+          const int cg = t / KD;
+          const int co = cot * COT + col, ci = cg * 8 + k;
+          w[u] = 0.f;
+          if (idx < total && co < p.CoutPad && ci < p.CinPad)
+            w[u] = (GWC ? 0.5f : 1.0f) * __ldg(p.weight + ((long long)(kd * TAPS + tap2) * p.CinPad + ci) * p.CoutPad + co);
+          off[u] = (uint32_t)((cg * KD + kd) * 2) * WSLAB + (uint32_t)(k >> 2) * (NB * 16) + (uint32_t)(col * TAPS + tap2) * 16 + (k & 3) * 4;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (base + u * TC_STAGERS < total) {
+            const float hi = tc_rna(w[u]);
+            *reinterpret_cast<float*>(s_w + off[u]) = hi;
+            *reinterpret_cast<float*>(s_w + off[u] + WSLAB) = tc_lo(w[u], hi);
+          }
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+    __syncwarp();
+    if (lane == 0) tc_mbar_arrive(wready);
+  }
+#ifdef TC_PROFILE
+  const long long tc_t1 = clock64();
+#endif
 
   if (warp >= TC_PROD_WARP) {
     // ============================ operand producers ============================
@@ -315,6 +330,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
       const uint64_t a0 = tc_desc(tc_smem_u32(s_stage) + zo * ROW_BYTES, 2048, 128), b0 = tc_desc(tc_smem_u32(s_w), NB * 16, 128);
       const bool three = p.npass == 3;
       uint32_t st = 0, ph = 0, ai = 0;
+      tc_mbar_wait(wready, 0, 700);  // the staged weights (generic-proxy stores, fenced by their writers)
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
         for (int step = 0; step < nsteps; ++step) {
           const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
@@ -486,6 +503,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
   }
 #ifdef TC_PROFILE
   if (blockIdx.x == 0 && lane == 0) {
+    if (warp == 0) printf("tc_prof prologue %lld clk, grid %d\n", tc_t1 - tc_t0, gridDim.x);
     printf("tc_prof warp %2d: done at %8lld clk; waits: empty %8llu  acce %8llu  full %8llu  accf %8llu\n", warp, clock64() - tc_t0,
            tc_prof_wait[warp][2], tc_prof_wait[warp][4], tc_prof_wait[warp][5], tc_prof_wait[warp][6]);
     for (int i = 0; i < 8; ++i) tc_prof_wait[warp][i] = 0;
@@ -647,7 +665,7 @@ int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
   // replays (and profilers re-launching graph nodes) must find it at least as large as any node's request
   if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return check_launch("conv(tc, cudaFuncSetAttribute)");
-  fn<<<(unsigned)(plan.ncot * plan.ctas_per_cot), TC_THREADS, plan.smem, st>>>(k);
+  launch_k(pdl_enabled(2), fn, dim3((unsigned)(plan.ncot * plan.ctas_per_cot)), dim3(TC_THREADS), plan.smem, st, k);
   ++tc_launches;
   return check_launch("conv(tc)");
 }

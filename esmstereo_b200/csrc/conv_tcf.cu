@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tcf_conv_kernel(const __grid_co
   const int nch = p.ncot * NT;
   const int SPI = p.ncg * p.KD;  // ring stages per item
 
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
       tc_mbar_init(&full[i], TF_NCP);
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tcf_conv_kernel(const __grid_co
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();  // nothing above touches global memory
   for (int i = tid; i < 2 * nch; i += TF_THREADS) {
     const int c = i % nch;
     const float* srcp = i < nch ? p.scale : p.shift;
@@ -471,6 +473,8 @@ struct PfGeom {
 
 __global__ void pf_from_nchw_kernel(const float* __restrict__ x, long long sB, long long sC, long long sD, long long sH, float* __restrict__ o,
                                     PfGeom g, long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int f = (int)(i % g.NP);
@@ -629,7 +633,7 @@ extern "C" int esm_pf_from_nchw_f32(const float* x, long long sB, long long sC, 
   if (int e = pf_geom(out, &g, "pf_from_nchw")) return e;
   ESM_REQUIRE(x, "pf_from_nchw: null input");
   const long long total = (long long)g.B * g.Cq * g.NP;
-  pf_from_nchw_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(x, sB, sC, sD, sH, out->data, g, total);
+  launch_k(pdl_enabled(32), pf_from_nchw_kernel, dim3((unsigned)ceil_div_ll(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, sB, sC, sD, sH, out->data, g, total);
   return check_launch("pf_from_nchw");
 }
 
@@ -842,7 +846,7 @@ extern "C" int esm_conv_pf_f32(const esm_conv_pf_t* d, void* stream) {
   if (getenv("ESM_DEBUG_PLAN"))
     fprintf(stderr, "[esm tcf] Cout=%d ncg=%d KD=%d K=%d phases=%d geom=(%d,%d,%d) mode=%d R=%d NPART=%d NT=%d x%d stages=%d (%zu B) items=%d grid=%u\n",
             d->Cout, k.ncg, k.KD, k.K, k.nphase, g0.Dp, g0.Hp, g0.P, k.mode, k.R, k.NPART, k.NT, k.ncot, ns, sb, k.total_items, grid);
-  tcf_conv_kernel<<<grid, TF_THREADS, smem, (cudaStream_t)stream>>>(k);
+  launch_k(pdl_enabled(8), tcf_conv_kernel, dim3(grid), dim3(TF_THREADS), smem, (cudaStream_t)stream, k);
   ++tcf_launches;
   return check_launch("conv_pf");
 }

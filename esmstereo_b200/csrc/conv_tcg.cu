@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
   const int P = max(1, min(12, TG_ACC / NT - 1));
   const int Pe = min(P, SPI);  // partials an item actually writes
 
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
       tc_mbar_init(&full[i], TG_NTW + 1);  // the 8 producer warps of one set + the weight streamer's expect_tx arrive
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();  // nothing above touches global memory
 
   if (warp >= TG_PROD_WARP) {
     // ============================ A-operand producers ============================
@@ -559,7 +561,7 @@ int tcg_conv_launch(const esm_conv_t* d, const TcgPlan& plan, cudaStream_t st) {
   void (*fn)(const TcgK) = !d->transposed ? tcg_conv_kernel<3, 1, 1> : (d->kd == 4 ? tcg_conv_kernel<2, 2, 1> : tcg_conv_kernel<2, 1, 2>);
   if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return check_launch("conv(tcg, cudaFuncSetAttribute)");
-  fn<<<(unsigned)plan.ctas, TG_THREADS, plan.smem, st>>>(k);
+  launch_k(pdl_enabled(4), fn, dim3((unsigned)plan.ctas), dim3(TG_THREADS), plan.smem, st, k);
   ++tcg_launches;
   return check_launch("conv(tcg)");
 }

@@ -4,6 +4,7 @@
 // conv); with C in {8,16} a whole pixel fits in registers, so each half of an SMLayer is ONE kernel
 // that reads C planes and writes C planes (bandwidth bound: 8*C bytes per pixel).
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace esm {
 
@@ -44,17 +45,19 @@ __device__ __forceinline__ void ln_mlp_shuffle_residual(float (&t)[C], const Mlp
     var = fmaf(dlt, dlt, var);
   }
   var = var / (float)C;
-  const float den = sqrtf(var + 1e-5f);  // shufflemixer.py:60-62: (x - mu) / sqrt(sigma + 1e-5) * weight
+  // shufflemixer.py:60-62: (x - mu) / sqrt(sigma + 1e-5) * weight.  One IEEE division per pixel and a multiply per
+  // channel (within 1 ulp of C divisions, which were a sixth of this function's instructions).
+  const float rden = 1.0f / sqrtf(var + 1e-5f);
   float y[C];
 #pragma unroll
-  for (int c = 0; c < C; ++c) y[c] = (t[c] - mu) / den * s.ln_w[c];
+  for (int c = 0; c < C; ++c) y[c] = (t[c] - mu) * rden * s.ln_w[c];
   float hdn[C];
 #pragma unroll
   for (int j = 0; j < C; ++j) {
     float a = s.fc0_b[j];
 #pragma unroll
     for (int i = 0; i < HALF; ++i) a = fmaf(s.fc0_w[j * HALF + i], y[i], a);
-    hdn[j] = silu(a);
+    hdn[j] = tc_silu(a);  // ex2.approx + rcp.approx, relative error 3e-7 (expf + an IEEE division: ~25 instructions per value)
   }
   float u[C];
 #pragma unroll
@@ -179,38 +182,52 @@ __global__ void __launch_bounds__(SP_TX * SP_TY) sm_spatial_kernel(const float* 
 
 
 // ---- whole SMLayer in one kernel (shufflemixer.py:97-112): u = shuffle(MLP1(LN1(x))) + x; t = depthwise7x7(u) + b;
-// y = shuffle(MLP2(LN2(t))) + t [+ extra].  A CTA owns a 32 x 8 output tile: phase A runs the pointwise half on the
-// tile + 3-pixel halo (the halo pixels are recomputed, 532 pixels for 256 outputs: that half is ~450 instructions per
-// pixel) and leaves it in shared memory -- zeros outside the image, which is the depthwise conv's padding -- phase B
-// gives every thread two horizontally adjacent pixels: one LDS.64 row segment and one padded weight row (2 x LDS.128)
-// feed 14 FMAs, against two loads per FMA in sm_spatial_kernel (LDS-bound: 20 us per launch at 96 x 312 x 16).
-constexpr int SL_TW = 32, SL_TH = 8, SL_K = 7, SL_R = SL_K / 2;
-constexpr int SL_PW = SL_TW + SL_K - 1, SL_PH = SL_TH + SL_K - 1;  // 38 x 14
+// y = shuffle(MLP2(LN2(t))) + t [+ extra].  A CTA of 256 threads owns a 28 x 8 output tile, in three phases:
+//   A  the first pointwise half, one thread per pixel of the tile + 3-pixel halo (34 x 14 = 476 pixels: two nearly full
+//      rounds of 256 threads), left in shared memory -- zeros outside the image, which is the depthwise conv's padding;
+//   B  the depthwise 7 x 7 with one thread per (channel, 4-pixel strip): the channel's 49 weights stay in registers,
+//      a window row is three aligned vector loads for 28 FMAs (sm_spatial_kernel spends two scalar loads per FMA and is
+//      LDS-bound: 20 us per launch at 96 x 312 x 16), results to a second shared-memory tile;
+//   C  the second pointwise half, one thread per output pixel.
+// Every sum is taken in the order of sm_pointwise_kernel / sm_spatial_kernel: bit-identical to the two-launch form.
+constexpr int SL_TW = 28, SL_TH = 8, SL_K = 7, SL_R = SL_K / 2;
+constexpr int SL_PW = SL_TW + SL_K - 1, SL_PH = SL_TH + SL_K - 1;  // 34 x 14
+constexpr int SL_PITCH = 36;                                        // row pitch of the haloed tile (16-byte aligned strips)
+constexpr int SL_THREADS = 256;
 
 template <int C>
-__global__ void __launch_bounds__(SL_TW / 2 * SL_TH) sm_layer_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W,
-                                                                      esm_mixer_mlp_t m1, const float* __restrict__ dw_w,
-                                                                      const float* __restrict__ dw_b, esm_mixer_mlp_t m2,
-                                                                      const float* __restrict__ extra) {
-  __shared__ MlpSmem<C> s1, s2;
-  __shared__ __align__(16) float s_w[C][SL_K][8];  // depthwise rows padded to 8 floats
-  __shared__ float s_b[C];
-  __shared__ __align__(16) float tile[C][SL_PH][SL_PW];
-  const int tid = threadIdx.x, nt = SL_TW / 2 * SL_TH;
-  load_mlp<C>(s1, m1, tid, nt);
-  load_mlp<C>(s2, m2, tid, nt);
-  for (int i = tid; i < C * SL_K * 8; i += nt) {
+struct SlSmem {
+  MlpSmem<C> s1, s2;
+  float4 w[C][SL_K][2];  // depthwise rows padded to 8 floats
+  float b[C];
+  float u[C][SL_PH][SL_PITCH];
+  float t[C][SL_TH][SL_TW];
+};
+
+template <int C>
+__global__ void __launch_bounds__(SL_THREADS) sm_layer_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W,
+                                                              esm_mixer_mlp_t m1, const float* __restrict__ dw_w,
+                                                              const float* __restrict__ dw_b, esm_mixer_mlp_t m2,
+                                                              const float* __restrict__ extra) {
+  extern __shared__ __align__(16) uint8_t sl_raw[];
+  SlSmem<C>& sm = *reinterpret_cast<SlSmem<C>*>(sl_raw);
+  const int tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  load_mlp<C>(sm.s1, m1, tid, SL_THREADS);
+  load_mlp<C>(sm.s2, m2, tid, SL_THREADS);
+  for (int i = tid; i < C * SL_K * 8; i += SL_THREADS) {
     const int kx = i & 7, ky = (i >> 3) % SL_K, c = i / (8 * SL_K);
-    s_w[c][ky][kx] = kx < SL_K ? dw_w[(c * SL_K + ky) * SL_K + kx] : 0.f;
+    reinterpret_cast<float*>(&sm.w[c][ky][0])[kx] = kx < SL_K ? dw_w[(c * SL_K + ky) * SL_K + kx] : 0.f;
   }
-  for (int i = tid; i < C; i += nt) s_b[i] = dw_b[i];
+  for (int i = tid; i < C; i += SL_THREADS) sm.b[i] = dw_b[i];
   __syncthreads();
   const int b = blockIdx.z;
   const int x0 = blockIdx.x * SL_TW - SL_R, y0 = blockIdx.y * SL_TH - SL_R;
   const long long plane = (long long)H * W;
   const float* xb = x + (long long)b * C * plane;
-  // phase A: pointwise half on the haloed tile
-  for (int i = tid; i < SL_PH * SL_PW; i += nt) {
+  // phase A
+  for (int i = tid; i < SL_PH * SL_PW; i += SL_THREADS) {
     const int ty = i / SL_PW, tx = i - ty * SL_PW;
     const int gy = y0 + ty, gx = x0 + tx;
     float t[C];
@@ -218,54 +235,62 @@ __global__ void __launch_bounds__(SL_TW / 2 * SL_TH) sm_layer_kernel(const float
       const float* p = xb + (long long)gy * W + gx;
 #pragma unroll
       for (int c = 0; c < C; ++c) t[c] = __ldg(p + c * plane);
-      ln_mlp_shuffle_residual<C>(t, s1);
+      ln_mlp_shuffle_residual<C>(t, sm.s1);
     } else {
 #pragma unroll
       for (int c = 0; c < C; ++c) t[c] = 0.f;
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) tile[c][ty][tx] = t[c];
+    for (int c = 0; c < C; ++c) sm.u[c][ty][tx] = t[c];
   }
   __syncthreads();
-  // phase B: depthwise 7 x 7 on two adjacent pixels, then the second pointwise half
-  const int lx = tid % (SL_TW / 2), ly = tid / (SL_TW / 2);
-  const int px = blockIdx.x * SL_TW + 2 * lx, py = blockIdx.y * SL_TH + ly;
-  float t0[C], t1[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    float a0 = s_b[c], a1 = a0;
+  // phase B
+  {
+    constexpr int TPC = SL_THREADS / C;               // threads per channel
+    constexpr int NSTRIP = (SL_TW / 4) * SL_TH;       // 4-pixel strips per channel
+    const int c = tid / TPC, sub = tid - c * TPC;
+    float w[SL_K][8];
 #pragma unroll
     for (int ky = 0; ky < SL_K; ++ky) {
-      const float2* rp = reinterpret_cast<const float2*>(&tile[c][ly + ky][2 * lx]);
-      const float2 r01 = rp[0], r23 = rp[1], r45 = rp[2], r67 = rp[3];
-      const float r[8] = {r01.x, r01.y, r23.x, r23.y, r45.x, r45.y, r67.x, r67.y};
-      const float4 wa = *reinterpret_cast<const float4*>(&s_w[c][ky][0]), wb = *reinterpret_cast<const float4*>(&s_w[c][ky][4]);
-      const float w[7] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
-#pragma unroll
-      for (int kx = 0; kx < SL_K; ++kx) {
-        a0 = fmaf(w[kx], r[kx], a0);
-        a1 = fmaf(w[kx], r[kx + 1], a1);
-      }
+      const float4 wa = sm.w[c][ky][0], wb = sm.w[c][ky][1];
+      w[ky][0] = wa.x; w[ky][1] = wa.y; w[ky][2] = wa.z; w[ky][3] = wa.w;
+      w[ky][4] = wb.x; w[ky][5] = wb.y; w[ky][6] = wb.z; w[ky][7] = 0.f;
     }
-    t0[c] = a0;
-    t1[c] = a1;
-  }
-  if (py >= H || px >= W) return;
-  const long long base = (long long)b * C * plane + (long long)py * W + px;
-  ln_mlp_shuffle_residual<C>(t0, s2);
+    const float bias = sm.b[c];
+    for (int s = sub; s < NSTRIP; s += TPC) {
+      const int sy = s / (SL_TW / 4), sx = s - sy * (SL_TW / 4);
+      float a[4] = {bias, bias, bias, bias};
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    float v = t0[c];
-    if (extra) v += __ldg(extra + base + c * plane);
-    y[base + c * plane] = v;
-  }
-  if (px + 1 < W) {
-    ln_mlp_shuffle_residual<C>(t1, s2);
+      for (int ky = 0; ky < SL_K; ++ky) {
+        const float* rp = &sm.u[c][sy + ky][4 * sx];
+        const float4 r0 = *reinterpret_cast<const float4*>(rp), r1 = *reinterpret_cast<const float4*>(rp + 4);
+        const float2 r2 = *reinterpret_cast<const float2*>(rp + 8);
+        const float r[10] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y};
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      float v = t1[c];
-      if (extra) v += __ldg(extra + base + 1 + c * plane);
-      y[base + 1 + c * plane] = v;
+        for (int kx = 0; kx < SL_K; ++kx)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[j] = fmaf(w[ky][kx], r[kx + j], a[j]);
+      }
+      *reinterpret_cast<float4*>(&sm.t[c][sy][4 * sx]) = make_float4(a[0], a[1], a[2], a[3]);
+    }
+  }
+  __syncthreads();
+  // phase C
+  if (tid < SL_TW * SL_TH) {
+    const int ly = tid / SL_TW, lx = tid - ly * SL_TW;
+    const int px = blockIdx.x * SL_TW + lx, py = blockIdx.y * SL_TH + ly;
+    if (py < H && px < W) {
+      float t[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) t[c] = sm.t[c][ly][lx];
+      ln_mlp_shuffle_residual<C>(t, sm.s2);
+      const long long base = (long long)b * C * plane + (long long)py * W + px;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float v = t[c];
+        if (extra) v += __ldg(extra + base + c * plane);
+        y[base + c * plane] = v;
+      }
     }
   }
 }
@@ -329,9 +354,12 @@ extern "C" int esm_sm_layer_f32(const float* x, float* y, int B, int C, int H, i
   ESM_REQUIRE(B <= 65535 && ceil_div(H, SL_TH) <= 65535, "sm_layer: grid too large");
   dim3 grid((unsigned)ceil_div(W, SL_TW), (unsigned)ceil_div(H, SL_TH), (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (C == 16)
-    sm_layer_kernel<16><<<grid, SL_TW / 2 * SL_TH, 0, st>>>(x, y, H, W, *mlp1, dw_w, dw_b, *mlp2, extra_residual);
-  else
-    sm_layer_kernel<8><<<grid, SL_TW / 2 * SL_TH, 0, st>>>(x, y, H, W, *mlp1, dw_w, dw_b, *mlp2, extra_residual);
+  if (C == 16) {
+    if (cudaFuncSetAttribute((const void*)sm_layer_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SlSmem<16>)) != cudaSuccess)
+      return check_launch("sm_layer(cudaFuncSetAttribute)");
+    launch_k(pdl_enabled(32), sm_layer_kernel<16>, grid, dim3(SL_THREADS), sizeof(SlSmem<16>), st, x, y, H, W, *mlp1, dw_w, dw_b, *mlp2, extra_residual);
+  } else {
+    launch_k(pdl_enabled(32), sm_layer_kernel<8>, grid, dim3(SL_THREADS), sizeof(SlSmem<8>), st, x, y, H, W, *mlp1, dw_w, dw_b, *mlp2, extra_residual);
+  }
   return check_launch("sm_layer");
 }

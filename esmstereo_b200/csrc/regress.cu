@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(128) regression_top2_kernel(const float* __res
                                                               int* __restrict__ idx, int D, long long plane,
                                                               long long total, SubSrc ss) {
   __shared__ Top2 s_part[REG_SPLIT - 1][32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
   const long long i = (long long)blockIdx.x * 32 + lane;
   const bool live = i < total;
@@ -121,6 +123,8 @@ __global__ void __launch_bounds__(128) disparity_regression_kernel(const float* 
 __global__ void __launch_bounds__(256) bilinear_add_kernel(const float* __restrict__ prev, const float* __restrict__ res,
                                                            float* __restrict__ out, int h, int w, int f, float rscale,
                                                            float out_scale, long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int W = w * f, H = h * f;
@@ -152,7 +156,7 @@ extern "C" int esm_regression_top2_f32(const float* cost, float* pred, int* idx,
   ESM_REQUIRE(cost && pred, "regression_top2: null pointer");
   ESM_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "regression_top2: empty shape");
   const long long plane = (long long)H * W, total = plane * B;
-  regression_top2_kernel<false><<<(unsigned)ceil_div_ll(total, 32), 128, 0, (cudaStream_t)stream>>>(cost, pred, idx, D, plane, total, SubSrc{});
+  launch_k(pdl_enabled(32), regression_top2_kernel<false>, dim3((unsigned)ceil_div_ll(total, 32)), dim3(128), 0, (cudaStream_t)stream, cost, pred, idx, D, plane, total, SubSrc{});
   return check_launch("regression_top2");
 }
 
@@ -162,7 +166,7 @@ extern "C" int esm_regression_top2_subpixel_f32(const float* y8, long long sB, l
   ESM_REQUIRE(B > 0 && D2 > 0 && H2 > 0 && W2 > 0, "regression_top2_subpixel: empty shape");
   const long long plane = 4ll * H2 * W2, total = plane * B;
   SubSrc ss = {sB, sC, sD, sH, 2 * W2};
-  regression_top2_kernel<true><<<(unsigned)ceil_div_ll(total, 32), 128, 0, (cudaStream_t)stream>>>(y8, pred, idx, 2 * D2, plane, total, ss);
+  launch_k(pdl_enabled(32), regression_top2_kernel<true>, dim3((unsigned)ceil_div_ll(total, 32)), dim3(128), 0, (cudaStream_t)stream, y8, pred, idx, 2 * D2, plane, total, ss);
   return check_launch("regression_top2_subpixel");
 }
 
@@ -180,7 +184,7 @@ extern "C" int esm_bilinear_add_f32(const float* prev, const float* residual, fl
   ESM_REQUIRE(prev && residual && out, "bilinear_add: null pointer");
   ESM_REQUIRE(B > 0 && h > 0 && w > 0 && factor >= 1, "bilinear_add: empty shape");
   const long long total = (long long)B * h * factor * w * factor;
-  bilinear_add_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      prev, residual, out, h, w, factor, 1.0f / (float)factor, out_scale, total);
+  launch_k(pdl_enabled(32), bilinear_add_kernel, dim3((unsigned)ceil_div_ll(total, 256)), dim3(256), 0, (cudaStream_t)stream, prev, residual, out, h, w, factor,
+           1.0f / (float)factor, out_scale, total);
   return check_launch("bilinear_add");
 }

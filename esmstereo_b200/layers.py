@@ -244,10 +244,10 @@ class SMLayer(nn.Module):
         self.spatial = nn.Conv2d(dim, dim, kernel_size, 1, kernel_size // 2, groups=dim)
         self.mlp1, self.mlp2 = SplitPointMlp(dim, mlp_ratio), SplitPointMlp(dim, mlp_ratio)
         self._c1, self._c2 = _Packed(), _Packed()
-        # ESM_SMLAYER=1: one launch per SMLayer (esm_sm_layer_f32).  Measured SLOWER than the two half kernels at KITTI
-        # shape (+8 us per layer): 120 CTAs of 4 warps leave one warp per scheduler, nothing hides the dependent-issue
-        # latency of the halo recompute.  Kept for the C ABI and as the record of the experiment; default off.
-        self.fused = os.environ.get("ESM_SMLAYER", "0") == "1"
+        # One launch per SMLayer (esm_sm_layer_f32: pointwise half on tile + halo, depthwise with one thread per
+        # (channel, 4-pixel strip), second pointwise half; bit-identical to the two half kernels).  ESM_SMLAYER=0 runs the
+        # two half kernels (esm_sm_pointwise_f32 + esm_sm_spatial_f32), which also cover k != 7.
+        self.fused = os.environ.get("ESM_SMLAYER", "1") == "1"
 
     def _mlp(self, cache: _Packed, norm: LayerNorm, mlp: SplitPointMlp) -> ops.MixerMlp:
         ts = [norm.body.weight, mlp.fc[0].weight, mlp.fc[0].bias, mlp.fc[2].weight, mlp.fc[2].bias]

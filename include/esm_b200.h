@@ -41,6 +41,10 @@ extern "C" {
 
 const char* esm_last_error(void);
 int esm_version(void);
+/* Programmatic dependent launch (csrc/common.cuh): bit mask of the kernel families launched with it (1 FP32-pipe conv,
+ * 2 resident tcgen05, 4 streamed tcgen05, 8 flat tcgen05, 16 pointwise, 32 the rest of the forward path); the initial
+ * value comes from ESM_PDL.  Takes effect for launches (and graph captures) made afterwards; returns the previous mask. */
+int esm_set_pdl(int mask);
 /* Device properties the host side sizes grids with; returns ESM_ERR_CUDA when no device. */
 int esm_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
