@@ -17,6 +17,7 @@
 // CK input channels of the brick + halo in shared memory together with the matching weights.
 #include "conv_kernel.cuh"
 #include "conv_tc.cuh"
+#include "tc_common.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -136,6 +137,41 @@ TcgPack tcg_pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed)
   t.CoutX = round_up(Cout, 8);
   t.elems = Cin >= 8 ? (long long)t.phases * t.taps * t.ncg * 16 * t.CoutX : 0;
   return t;
+}
+
+TckPack tck_pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed) {
+  const PackGeom g = pack_geom(Cout, Cin, kd, kh, kw, transposed);
+  const TcgPack t = tcg_pack_geom(Cout, Cin, kd, kh, kw, transposed);
+  TckPack k;
+  k.offset = (g.per_phase * g.phases + t.elems + 31) / 32 * 32;
+  k.ncot = Cout / 32;
+  k.ncg = ceil_div(Cin, 8);
+  const bool ok = !transposed && kd == 1 && kh == 3 && kw == 3 && Cin >= 8 && Cout % 32 == 0;
+  k.elems = ok ? (long long)k.ncot * k.ncg * 3 * 2 * 96 * 8 : 0;
+  return k;
+}
+
+// one thread per weight of the image: out[cot][cg][kh][hi|lo][k/4][(co%32)*3 + kw][k%4]
+__global__ void pack_tck_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int ncg, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long r = i;
+  const int col = r % 32;
+  r /= 32;
+  const int k = r % 8;
+  r /= 8;
+  const int kw = r % 3;
+  r /= 3;
+  const int kh = r % 3;
+  r /= 3;
+  const int cg = r % ncg;
+  const int cot = (int)(r / ncg);
+  const int co = cot * 32 + col, ci = cg * 8 + k;
+  const float v = (co < Cout && ci < Cin) ? w[((long long)(co * Cin + ci) * 3 + kh) * 3 + kw] : 0.f;
+  const float hi = tc_rna(v);
+  float* o = out + (((long long)(cot * ncg + cg) * 3 + kh) * 2) * (96 * 8) + (k >> 2) * (96 * 4) + (col * 3 + kw) * 4 + (k & 3);
+  o[0] = hi;
+  o[96 * 8] = tc_lo(v, hi);
 }
 
 __global__ void pack_tcg_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kd, int kh, int kw,
@@ -506,7 +542,8 @@ using namespace esm;
 
 extern "C" long long esm_packed_weight_elems(int Cout, int Cin, int kd, int kh, int kw, int transposed) {
   const PackGeom g = pack_geom(Cout, Cin, kd, kh, kw, transposed);
-  return g.per_phase * g.phases + tcg_pack_geom(Cout, Cin, kd, kh, kw, transposed).elems;
+  const TckPack k = tck_pack_geom(Cout, Cin, kd, kh, kw, transposed);
+  return k.elems > 0 ? k.offset + k.elems : g.per_phase * g.phases + tcg_pack_geom(Cout, Cin, kd, kh, kw, transposed).elems;
 }
 
 extern "C" int esm_pack_conv_weight_f32(const float* w, float* packed, int Cout, int Cin, int kd, int kh, int kw,
@@ -525,6 +562,11 @@ extern "C" int esm_pack_conv_weight_f32(const float* w, float* packed, int Cout,
     const long long n = t.elems / 2;  // one thread per weight writes its hi and lo parts
     pack_tcg_kernel<<<(unsigned)ceil_div_ll(n, threads), threads, 0, (cudaStream_t)stream>>>(
         w, packed + t.offset, Cout, Cin, kd, kh, kw, transposed, g.KD, g.KH, g.KW, g.phases_d, t.ncg, t.CoutX, n);
+  }
+  const TckPack tk = tck_pack_geom(Cout, Cin, kd, kh, kw, transposed);
+  if (tk.elems > 0) {
+    const long long n = tk.elems / 2;
+    pack_tck_kernel<<<(unsigned)ceil_div_ll(n, threads), threads, 0, (cudaStream_t)stream>>>(w, packed + tk.offset, Cout, Cin, tk.ncg, n);
   }
   return check_launch("pack_conv_weight");
 }

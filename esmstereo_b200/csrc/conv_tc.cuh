@@ -17,6 +17,8 @@ struct TcPlan {
   int nstages;       // operand ring depth
   int ctas_per_cot;  // persistent CTAs per channel tile
   int npass;         // 3: split-TF32 (fp32-grade), 1: single-pass TF32
+  int NEW;           // epilogue warps: 8 (two per TMEM lane quadrant) or 16
+  int khk;           // 2D k3, Cout % 32 == 0: kh in K, kw in N, 32 channels per CTA (tck_conv_kernel)
   size_t smem;
 };
 
@@ -26,6 +28,16 @@ struct TcgPack {
   int phases, taps, KD, KH, KW, ncg, CoutX;
 };
 TcgPack tcg_pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed);
+
+// Third region of a packed weight (2D k3 layers with Cout % 32 == 0 and Cin >= 8 only): the resident-weight image of
+// tck_conv_kernel (conv_tc.cu), split into hi / lo and laid out exactly as the kernel keeps it in shared memory,
+//   [Cout / 32][cg][kh][hi | lo][k / 4][n = (co % 32) * 3 + kw][k % 4]
+// so that a CTA's weights are bulk copies instead of 10 k clk of scalar loads, index arithmetic and stores.
+struct TckPack {
+  long long offset, elems;  // in floats, from the start of the packed weight (offset is a multiple of 32)
+  int ncot, ncg;
+};
+TckPack tck_pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed);
 
 // Streamed-weight GEMM path (conv_tcg.cu): any k / stride 1-2 / transposed k4 s2 layer with Cin >= 8.
 struct TcgPlan {

@@ -14,10 +14,10 @@ __device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
 // Spin on an mbarrier phase.  A watchdog turns a pipeline deadlock (a bug) into a trapped launch with a
-// message instead of a hung GPU: 2^26 failed polls is seconds, far beyond any legitimate wait here.
+// message instead of a hung GPU: 2^23 failed polls is seconds, far beyond any legitimate wait here.
 static __device__ __noinline__ void tc_deadlock(int tag, uint32_t parity) {
-  printf("esm tc_conv: deadlock in block %d warp %d lane %d waiting on barrier %d parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
-         (int)(threadIdx.x & 31), tag, parity);
+  if ((threadIdx.x & 31) == 0)
+    printf("esm tc_conv: deadlock in block %d warp %d waiting on barrier %d parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), tag, parity);
   __trap();
 }
 #ifdef TC_PROFILE
@@ -35,7 +35,7 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity, int
                  : "=r"(done)
                  : "r"(addr), "r"(parity)
                  : "memory");
-    if (!done && ++polls > (1u << 26)) tc_deadlock(tag, parity);
+    if (!done && ++polls > (1u << 23)) tc_deadlock(tag, parity);
   } while (!done);
 #ifdef TC_PROFILE
   if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) tc_prof_wait[threadIdx.x >> 5][tag / 100] += (unsigned long long)(clock64() - t_begin);
