@@ -139,19 +139,43 @@ TcgPack tcg_pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed)
   return t;
 }
 
-TckPack tck_pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed) {
-  const PackGeom g = pack_geom(Cout, Cin, kd, kh, kw, transposed);
-  const TcgPack t = tcg_pack_geom(Cout, Cin, kd, kh, kw, transposed);
-  TckPack k;
-  k.offset = (g.per_phase * g.phases + t.elems + 31) / 32 * 32;
-  k.ncot = Cout / 32;
-  k.ncg = ceil_div(Cin, 8);
-  const bool ok = !transposed && kd == 1 && kh == 3 && kw == 3 && Cin >= 8 && Cout % 32 == 0;
-  k.elems = ok ? (long long)k.ncot * k.ncg * 3 * 2 * 96 * 8 : 0;
-  return k;
+int tc_cot(int Cout, bool k1) {
+  const int CoutPad8 = round_up(Cout, 8);
+  if (k1) return CoutPad8 > 64 ? 0 : (CoutPad8 > 48 ? 64 : CoutPad8);  // 8..48 in steps of 8, or 64
+  if (CoutPad8 <= 24) return CoutPad8;
+  const int w24 = ceil_div(CoutPad8, 24) * 24, w16 = ceil_div(CoutPad8, 16) * 16;
+  return (w16 < w24) ? 16 : 24;
 }
 
-// one thread per weight of the image: out[cot][cg][kh][hi|lo][k/4][(co%32)*3 + kw][k%4]
+TcImg tc_img_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed) {
+  const PackGeom g = pack_geom(Cout, Cin, kd, kh, kw, transposed);
+  const TcgPack t = tcg_pack_geom(Cout, Cin, kd, kh, kw, transposed);
+  TcImg m;
+  memset(&m, 0, sizeof(m));
+  m.offset = (g.per_phase * g.phases + t.elems + 31) / 32 * 32;
+  m.ncg = ceil_div(Cin, 8);
+  if (transposed || Cin < 8) return m;
+  const bool k3 = kh == 3 && kw == 3 && (kd == 1 || kd == 3), k1 = kd == 1 && kh == 1 && kw == 1;
+  if (k3 && kd == 1 && Cout % 32 == 0) {
+    m.kind = 1;
+    m.COT = 32;
+    m.taps = 9;
+    m.KD = 1;
+    m.ncot = Cout / 32;
+    m.per_cot = (long long)m.ncg * 3 * 2 * 96 * 8;
+  } else if ((k3 || k1) && tc_cot(Cout, k1) > 0) {
+    m.kind = 2;
+    m.COT = tc_cot(Cout, k1);
+    m.taps = k1 ? 1 : 9;
+    m.KD = kd;
+    m.ncot = ceil_div(Cout, m.COT);
+    m.per_cot = (long long)m.ncg * kd * 2 * (m.taps * m.COT) * 8;
+  }
+  m.elems = m.per_cot * m.ncot;
+  return m;
+}
+
+// one thread per weight of the image (kind 1): out[cot][cg][kh][hi|lo][k/4][(co%32)*3 + kw][k%4]
 __global__ void pack_tck_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int ncg, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -172,6 +196,31 @@ __global__ void pack_tck_kernel(const float* __restrict__ w, float* __restrict__
   float* o = out + (((long long)(cot * ncg + cg) * 3 + kh) * 2) * (96 * 8) + (k >> 2) * (96 * 4) + (col * 3 + kw) * 4 + (k & 3);
   o[0] = hi;
   o[96 * 8] = tc_lo(v, hi);
+}
+
+// kind 2: out[cot][cg][kd][hi|lo][k/4][(co%COT)*taps + tap][k%4], w = [Cout][Cin][KD][kh][kw] (taps = kh * kw)
+__global__ void pack_tcimg_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int ncg, int KD, int taps, int COT,
+                                  long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long r = i;
+  const int col = r % COT;
+  r /= COT;
+  const int k = r % 8;
+  r /= 8;
+  const int tap = r % taps;
+  r /= taps;
+  const int kd = r % KD;
+  r /= KD;
+  const int cg = r % ncg;
+  const int cot = (int)(r / ncg);
+  const int co = cot * COT + col, ci = cg * 8 + k;
+  const float v = (co < Cout && ci < Cin) ? w[((long long)(co * Cin + ci) * KD + kd) * taps + tap] : 0.f;
+  const float hi = tc_rna(v);
+  const int NB = taps * COT;
+  float* o = out + (((long long)(cot * ncg + cg) * KD + kd) * 2) * (NB * 8) + (k >> 2) * (NB * 4) + (col * taps + tap) * 4 + (k & 3);
+  o[0] = hi;
+  o[NB * 8] = tc_lo(v, hi);
 }
 
 __global__ void pack_tcg_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kd, int kh, int kw,
@@ -542,7 +591,7 @@ using namespace esm;
 
 extern "C" long long esm_packed_weight_elems(int Cout, int Cin, int kd, int kh, int kw, int transposed) {
   const PackGeom g = pack_geom(Cout, Cin, kd, kh, kw, transposed);
-  const TckPack k = tck_pack_geom(Cout, Cin, kd, kh, kw, transposed);
+  const TcImg k = tc_img_geom(Cout, Cin, kd, kh, kw, transposed);
   return k.elems > 0 ? k.offset + k.elems : g.per_phase * g.phases + tcg_pack_geom(Cout, Cin, kd, kh, kw, transposed).elems;
 }
 
@@ -563,10 +612,14 @@ extern "C" int esm_pack_conv_weight_f32(const float* w, float* packed, int Cout,
     pack_tcg_kernel<<<(unsigned)ceil_div_ll(n, threads), threads, 0, (cudaStream_t)stream>>>(
         w, packed + t.offset, Cout, Cin, kd, kh, kw, transposed, g.KD, g.KH, g.KW, g.phases_d, t.ncg, t.CoutX, n);
   }
-  const TckPack tk = tck_pack_geom(Cout, Cin, kd, kh, kw, transposed);
+  const TcImg tk = tc_img_geom(Cout, Cin, kd, kh, kw, transposed);
   if (tk.elems > 0) {
     const long long n = tk.elems / 2;
-    pack_tck_kernel<<<(unsigned)ceil_div_ll(n, threads), threads, 0, (cudaStream_t)stream>>>(w, packed + tk.offset, Cout, Cin, tk.ncg, n);
+    if (tk.kind == 1)
+      pack_tck_kernel<<<(unsigned)ceil_div_ll(n, threads), threads, 0, (cudaStream_t)stream>>>(w, packed + tk.offset, Cout, Cin, tk.ncg, n);
+    else
+      pack_tcimg_kernel<<<(unsigned)ceil_div_ll(n, threads), threads, 0, (cudaStream_t)stream>>>(w, packed + tk.offset, Cout, Cin, tk.ncg, tk.KD, tk.taps,
+                                                                                                  tk.COT, n);
   }
   return check_launch("pack_conv_weight");
 }

@@ -40,7 +40,7 @@ struct TcK {
   int B, Cin, ncg, D, H, W;
   int Cout, CinPad, CoutPad;
   const float* weight;  // fp32 pack of esm_pack_conv_weight_f32: [tap][CinPad][CoutPad]
-  const float* wimg;    // tck_conv_kernel: the split weight image of the pack (TckPack)
+  const float* wimg;    // tck_conv_kernel: the split weight image of the pack (TcImg)
   const float* scale;
   const float* shift;
   int act, act2;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(tc_threads(NEW), 1) tc_conv_kernel(const __gri
       tc_mbar_init(&accf[i], TZ);
       tc_mbar_init(&acce[i], TC_NEW);
     }
-    tc_mbar_init(wready, TC_PROD_WARP);
+    tc_mbar_init(wready, p.wimg ? 1 : TC_PROD_WARP);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -144,6 +144,14 @@ __global__ void __launch_bounds__(tc_threads(NEW), 1) tc_conv_kernel(const __gri
   // The producers start on the first operand stage right away (its exposed global-load latency used to come after the
   // weight staging: 3.5 k clk of prologue on a 14 k clk layer); the epilogue and MMA warps, idle until the first
   // accumulator is ready, stage the weights meanwhile and the MMA issuers wait on `wready` before their first MMA.
+  if (p.wimg) {
+    // the pack holds this channel tile's image (conv_tc.cuh TcImg): one bulk copy per (8-channel group, kd) slab pair
+    if (tid == TC_MMA_WARP * 32) {
+      tc_mbar_expect_tx(wready, wbytes);
+      const float* img = p.wimg + (long long)cot * (wbytes / 4);
+      for (int sl = 0; sl < ncg * KD; ++sl) tc_bulk_g2s(s_w + (size_t)sl * (2 * WSLAB), img + (long long)sl * (2 * WSLAB / 4), 2 * WSLAB, wready);
+    }
+  } else
   if (warp < TC_PROD_WARP) {
     constexpr int TC_STAGERS = 32 * TC_PROD_WARP;
     // resident weights of this channel tile: split and laid out as UMMA B operands
@@ -587,7 +595,7 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-  // resident weights: the pack holds this channel tile's image (split, UMMA layout: conv_tc.cuh TckPack), one bulk copy
+  // resident weights: the pack holds this channel tile's image (split, UMMA layout: conv_tc.cuh TcImg), one bulk copy
   // per 8-channel group, all completing on `wready`; the MMA issuer waits for it before its first MMA
   if (tid == TC_MMA_WARP * 32) {
     tc_mbar_expect_tx(wready, wbytes);
@@ -913,22 +921,14 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
   }
   const int CoutPad8 = round_up(d->Cout, 8);
   const int taps = k1 ? 1 : 9;
-  int COT;
-  if (k1) {
-    COT = CoutPad8 > 48 ? 64 : CoutPad8;  // 8..48 in steps of 8, or 64
-    if (CoutPad8 > 64) return false;
-  } else if (CoutPad8 <= 24) {
-    COT = CoutPad8;
-  } else {
-    const int w24 = ceil_div(CoutPad8, 24) * 24, w16 = ceil_div(CoutPad8, 16) * 16;
-    COT = (w16 < w24) ? 16 : 24;
-  }
+  int COT = tc_cot(d->Cout, k1);
+  if (COT == 0) return false;
   if (gwc && COT != 8) return false;
   // 2D k3 layers whose Cout is a multiple of 32: kh in K, kw in N, 32 channels per CTA (tck_conv_kernel), when the
   // resident weights (18 KB per 8-channel group) leave room for two ring stages.  ESM_TC_KHK=0 keeps taps-in-N.
   static const bool khk_env = !(getenv("ESM_TC_KHK") && atoi(getenv("ESM_TC_KHK")) == 0);
   plan->khk = 0;
-  if (khk_env && k3 && d->kd == 1 && !gwc && !d->pixel_shuffle && tck_pack_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0).elems > 0 &&
+  if (khk_env && k3 && d->kd == 1 && !gwc && !d->pixel_shuffle && tc_img_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0).kind == 1 &&
       (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0) {
     const size_t wb = ((size_t)ceil_div(d->Cin, 8) * 3 * 2 * (3 * 32) * 32 + 127) & ~(size_t)127;
     if (wb + 2 * 4 * 8192 <= 227 * 1024 - 1024) {
@@ -996,9 +996,16 @@ int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
   k.CoutPad = (int)(tcg_pack_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0).offset / ((long long)d->kd * d->kh * d->kw * k.CinPad));
   k.weight = d->weight;
   if (plan.khk) {
-    const TckPack tk = tck_pack_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0);
-    ESM_REQUIRE(tk.elems > 0 && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0, "conv(tc): no weight image for the kh-in-K kernel");
+    const TcImg tk = tc_img_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0);
+    ESM_REQUIRE(tk.kind == 1 && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0, "conv(tc): no weight image for the kh-in-K kernel");
     k.wimg = d->weight + tk.offset;
+  } else if (!plan.gwc) {
+    // the pack's image of this layer for tc_conv_kernel (same channel tile, taps and depth); the kernel stages the
+    // weights itself when there is none (group-wise correlation stem: its 0.5 is folded into the weights)
+    static const bool img_env = !(getenv("ESM_TC_WIMG") && atoi(getenv("ESM_TC_WIMG")) == 0);
+    const TcImg tk = tc_img_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0);
+    if (img_env && tk.kind == 2 && tk.COT == plan.COT && tk.taps == plan.taps && tk.KD == plan.KD && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0)
+      k.wimg = d->weight + tk.offset;
   }
   k.scale = d->scale;
   k.shift = d->shift;

@@ -29,15 +29,20 @@ struct TcgPack {
 };
 TcgPack tcg_pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed);
 
-// Third region of a packed weight (2D k3 layers with Cout % 32 == 0 and Cin >= 8 only): the resident-weight image of
-// tck_conv_kernel (conv_tc.cu), split into hi / lo and laid out exactly as the kernel keeps it in shared memory,
-//   [Cout / 32][cg][kh][hi | lo][k / 4][n = (co % 32) * 3 + kw][k % 4]
-// so that a CTA's weights are bulk copies instead of 10 k clk of scalar loads, index arithmetic and stores.
-struct TckPack {
+// Third region of a packed weight (stride-1 k1 / k3 layers with Cin >= 8): the resident-weight image of the tcgen05
+// kernels of conv_tc.cu, split into hi / lo and laid out exactly as the kernel keeps it in shared memory, so that a CTA's
+// weights are a few bulk copies instead of thousands of clocks of scalar loads, index arithmetic and stores:
+//   kind 1 (2D k3, Cout % 32 == 0; tck_conv_kernel):  [Cout / 32][cg][kh][hi | lo][k / 4][n = (co % 32) * 3 + kw][k % 4]
+//   kind 2 (every other k1 / k3 layer; tc_conv_kernel): [cot][cg][kd][hi | lo][k / 4][n = (co % COT) * taps + tap][k % 4]
+// with COT the channel tile tc_conv_plan uses for that Cout (tc_cot()).
+struct TcImg {
+  int kind;                 // 0: none
   long long offset, elems;  // in floats, from the start of the packed weight (offset is a multiple of 32)
-  int ncot, ncg;
+  int COT, taps, KD, ncot, ncg;
+  long long per_cot;        // floats per channel tile
 };
-TckPack tck_pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed);
+int tc_cot(int Cout, bool k1);  // output channels per CTA of tc_conv_kernel, 0 = not eligible
+TcImg tc_img_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed);
 
 // Streamed-weight GEMM path (conv_tcg.cu): any k / stride 1-2 / transposed k4 s2 layer with Cin >= 8.
 struct TcgPlan {
