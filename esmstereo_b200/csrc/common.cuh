@@ -92,6 +92,26 @@ static __device__ __noinline__ float4 apply_act4(float4 v, int act) {
   }
 }
 
+// torch upsample_bilinear2d, align_corners=False, scale 1 / rscale, of one [h, w] plane at output pixel (Y, X)
+// (src = (dst + 0.5) * rscale - 0.5, clamped at 0).  Explicit roundings: esm_bilinear_add_f32 and the PixelShuffle
+// epilogue of the conv engine (the final assembly fused into conv1_up's sub-pixel form) must agree bit for bit, whatever
+// the compiler would contract in either context.
+__device__ __forceinline__ float bilinear_up(const float* __restrict__ pb, int h, int w, int Y, int X, float rscale) {
+  float sy = __fmaf_rn((float)Y + 0.5f, rscale, -0.5f);
+  float sx = __fmaf_rn((float)X + 0.5f, rscale, -0.5f);
+  sy = sy < 0.f ? 0.f : sy;
+  sx = sx < 0.f ? 0.f : sx;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + ((y0 < h - 1) ? 1 : 0), x1 = x0 + ((x0 < w - 1) ? 1 : 0);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float v00 = __ldg(pb + (long long)y0 * w + x0), v01 = __ldg(pb + (long long)y0 * w + x1);
+  const float v10 = __ldg(pb + (long long)y1 * w + x0), v11 = __ldg(pb + (long long)y1 * w + x1);
+  const float top = __fmaf_rn(lx, v01, __fmul_rn(hx, v00));
+  const float bot = __fmaf_rn(lx, v11, __fmul_rn(hx, v10));
+  return __fmaf_rn(ly, bot, __fmul_rn(hy, top));
+}
+
 __device__ __forceinline__ int ceil_div_dev(int a, int b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }

@@ -156,7 +156,8 @@ TcImg tc_img_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed) {
   m.ncg = ceil_div(Cin, 8);
   if (transposed || Cin < 8) return m;
   const bool k3 = kh == 3 && kw == 3 && (kd == 1 || kd == 3), k1 = kd == 1 && kh == 1 && kw == 1;
-  if (k3 && kd == 1 && Cout % 32 == 0) {
+  // kind 1 only where tck_conv_kernel can keep the image resident next to two ring stages (ncg <= 8: Cin <= 64)
+  if (k3 && kd == 1 && Cout % 32 == 0 && (size_t)m.ncg * 3 * 2 * 96 * 32 + 2 * 4 * 8192 + 127 <= 227 * 1024 - 1024) {
     m.kind = 1;
     m.COT = 32;
     m.taps = 9;
@@ -652,7 +653,7 @@ extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
   }
   ESM_REQUIRE(d->pixel_shuffle == 0 || (d->Dout == 1 && !d->transposed && d->Cout % (d->pixel_shuffle * d->pixel_shuffle) == 0),
               "conv: pixel_shuffle needs a 2D conv with Cout divisible by r*r");
-  ESM_REQUIRE(d->pixel_shuffle == 0 || (!d->residual && !d->out_mul), "conv: pixel_shuffle excludes residual/out_mul");
+  ESM_REQUIRE(d->pixel_shuffle == 0 || !d->out_mul, "conv: pixel_shuffle excludes out_mul");
 
   const PackGeom g = pack_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, d->transposed);
   ConvK k;

@@ -644,6 +644,9 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
                   const int co = co0 + q;
                   if (co < p.Cout) {
                     const int c = co / (rr * rr), a = (co / rr) % rr, bb = co % rr;
+                    if (p.residual)  // low-resolution residual [B, Cout / r^2, OH, OW], bilinearly upsampled by r
+                      rv[q] = __fadd_rn(bilinear_up(p.residual + ((long long)b * (p.Cout / (rr * rr)) + c) * p.OH * p.OW, p.OH, p.OW, oh * rr + a,
+                                                    ow * rr + bb, 1.0f / (float)rr), rv[q]);
                     p.out[(long long)b * p.oB + (long long)c * p.oC + (long long)(oh * rr + a) * p.oH + ow * rr + bb] = rv[q] * p.out_scale;
                   }
                 }
@@ -704,6 +707,14 @@ __global__ void __launch_bounds__(256, 2) conv_kernel(const __grid_constant__ Co
               const int bb = co % rr;
               float* o = p.out + (long long)b * p.oB + (long long)c * p.oC + (long long)(oh * rr + a) * p.oH;
               if (act2 != ESM_ACT_NONE) r = apply_act4(r, act2);
+              if (p.residual) {  // low-resolution residual [B, Cout / r^2, OH, OW], bilinearly upsampled by r
+                const float* pb = p.residual + ((long long)b * (p.Cout / (rr * rr)) + c) * p.OH * p.OW;
+                const float rs = 1.0f / (float)rr;
+                float* rw = &r.x;
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+                  if (jw0 + v < p.OW) rw[v] = __fadd_rn(bilinear_up(pb, p.OH, p.OW, oh * rr + a, (jw0 + v) * rr + bb, rs), rw[v]);
+              }
               const float* rv = &r.x;
               // r == 2: channels co (even) and co + 1 are horizontally adjacent output pixels, so the 4 voxels x 2
               // channels of a thread are 8 consecutive floats of one output row: two 16-byte stores instead of eight

@@ -930,11 +930,8 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
   plan->khk = 0;
   if (khk_env && k3 && d->kd == 1 && !gwc && !d->pixel_shuffle && tc_img_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0).kind == 1 &&
       (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0) {
-    const size_t wb = ((size_t)ceil_div(d->Cin, 8) * 3 * 2 * (3 * 32) * 32 + 127) & ~(size_t)127;
-    if (wb + 2 * 4 * 8192 <= 227 * 1024 - 1024) {
-      plan->khk = 1;
-      COT = 32;
-    }
+    plan->khk = 1;  // (tc_img_geom gives kind 1 only when the image fits next to two ring stages)
+    COT = 32;
   }
   plan->COT = COT;
   plan->taps = taps;

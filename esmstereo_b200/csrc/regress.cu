@@ -132,19 +132,8 @@ __global__ void __launch_bounds__(256) bilinear_add_kernel(const float* __restri
   const long long t = i / W;
   const int y = (int)(t % H);
   const long long b = t / H;
-  float sy = ((float)y + 0.5f) * rscale - 0.5f;
-  float sx = ((float)x + 0.5f) * rscale - 0.5f;
-  sy = sy < 0.f ? 0.f : sy;
-  sx = sx < 0.f ? 0.f : sx;
-  const int y0 = (int)sy, x0 = (int)sx;
-  const int y1 = y0 + ((y0 < h - 1) ? 1 : 0), x1 = x0 + ((x0 < w - 1) ? 1 : 0);
-  const float ly = sy - (float)y0, lx = sx - (float)x0;
-  const float hy = 1.f - ly, hx = 1.f - lx;
-  const float* pb = prev + b * (long long)h * w;
-  const float v00 = __ldg(pb + (long long)y0 * w + x0), v01 = __ldg(pb + (long long)y0 * w + x1);
-  const float v10 = __ldg(pb + (long long)y1 * w + x0), v11 = __ldg(pb + (long long)y1 * w + x1);
-  const float up = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
-  out[i] = (up + __ldg(res + i)) * out_scale;
+  const float up = bilinear_up(prev + b * (long long)h * w, h, w, y, x, rscale);
+  out[i] = __fmul_rn(__fadd_rn(up, __ldg(res + i)), out_scale);
 }
 
 }  // namespace esm

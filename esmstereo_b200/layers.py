@@ -72,6 +72,9 @@ def _all_eq(v, want: int) -> bool:
     return all(a == want for a in v) if isinstance(v, (tuple, list)) else v == want
 
 
+FUSE_ASSEMBLY = os.environ.get("ESM_FUSE_ASSEMBLY", "1") == "1"  # 0: separate esm_bilinear_add_f32 launches
+
+
 def _only_full_out_size(fused: dict, x: torch.Tensor) -> bool:
     """True when the only fused argument is an out_size equal to the full 2x output (no crop)."""
     if set(fused) != {"out_size"}:
@@ -144,16 +147,20 @@ class BasicConv(nn.Module):
     def forward(self, x, **fused) -> torch.Tensor:
         _inference_only(self)
         act = "gelu" if self.gelu else None
+        bil = fused.pop("bilinear_prev", None)      # 2D sub-pixel form only: + bilinear x2 of this map, then * final_scale
+        final_scale = fused.pop("final_scale", 1.0)  # (the final assembly, ESMStereo.py:307,316, in this layer's epilogue)
         if self._subpixel and isinstance(x, torch.Tensor) and (not fused or set(fused) == {"keep_subpixel"} or _only_full_out_size(fused, x)):
             pc = self.packed_subpixel()
             if x.dim() == 4:
-                return ops.conv(x, pc, act, pixel_shuffle=2, fp32_only=self.fp32_only)
+                return ops.conv(x, pc, act, pixel_shuffle=2, fp32_only=self.fp32_only, residual=bil, out_scale=final_scale)
+            assert bil is None
             y = ops.conv(x, pc, act, fp32_only=self.fp32_only)  # [B, 8, D, H, W], channel = pd*4 + ph*2 + pw
             if fused.get("keep_subpixel"):
                 return y  # the caller reads the phases directly (ops.regression_top2_subpixel)
             return ops.pixel_shuffle3d(y)
         fused.pop("keep_subpixel", None)
-        return ops.conv(x, self.packed(), act, fp32_only=self.fp32_only, **fused)
+        y = ops.conv(x, self.packed(), act, fp32_only=self.fp32_only, **fused)
+        return y if bil is None else ops.bilinear_add(bil, y, 2, final_scale)
 
 
 class ConvBNAct(nn.Sequential):
@@ -357,6 +364,8 @@ class _Upsampler(nn.Module):
             x = _run_seq(self.blocks, x)
         x = getattr(self, "upsampling" + tag[0])(x)
         x = bare_conv(self._ct[tag], getattr(self, "tail" + tag), x)
+        if self.r == 2 and FUSE_ASSEMBLY:  # upsampled + refined, * final_scale, in conv1_up's epilogue
+            return getattr(self, "ref" + tag)(x, ref_f1, ref_f2, bilinear_prev=prev, final_scale=final_scale)
         x = getattr(self, "ref" + tag)(x, ref_f1, ref_f2)
         return ops.bilinear_add(prev, x, self.r, final_scale)
 

@@ -453,7 +453,12 @@ def conv(srcs: Sequence[torch.Tensor], pc: PackedConv, act: Optional[str] = None
     if out_mul is not None:
         out_mul = _dev(out_mul, "out_mul").contiguous()
         assert out_mul.numel() == B * pc.Cout * Ho * Wo
-    if residual is not None:
+    if residual is not None and r:
+        # with pixel_shuffle the residual is a dense LOW-resolution map [B, Cout / r^2, Ho, Wo]: upsampled bilinearly
+        # by r (align_corners=False) and added after the shuffle, before out_scale
+        residual = _dev(residual, "residual").contiguous()
+        assert tuple(residual.shape) == (B, pc.Cout // (r * r), Ho, Wo) and out_mul is None
+    elif residual is not None:
         residual = _dev(residual, "residual")
         assert residual.shape == out.shape
         if residual.stride() != out.stride():  # the kernel reads it with the output's strides

@@ -84,7 +84,11 @@ typedef struct {
   const float* residual;     /* optional tensor with the output's strides, added after act/out_mul */
   int act2;                  /* ESM_ACT_* applied after the residual add */
   float out_scale;           /* final multiply (1.0f = none) */
-  int pixel_shuffle;         /* 0, or r: out[b, co/(r*r), h*r+(co/r)%r, w*r+co%r] (2D only) */
+  int pixel_shuffle;         /* 0, or r: out[b, co/(r*r), h*r+(co/r)%r, w*r+co%r] (2D only).  With pixel_shuffle,
+                                `residual` is a dense LOW-resolution map [B, Cout/(r*r), Hout, Wout] that is upsampled
+                                bilinearly by r (align_corners = False) and added after the shuffle, before out_scale:
+                                `F.interpolate(prev, scale_factor=2, mode='bilinear') + conv1_up(...)` and the final
+                                `* 4` (ESMStereo.py:307,316,745) in the epilogue of conv1_up's sub-pixel form */
   float* out;
   long long oB, oC, oD, oH;  /* output strides in elements (W stride 1) */
   int engine;                /* 0: whichever engine wins the on-device timing (FP32 pipe or tcgen05 split-TF32);

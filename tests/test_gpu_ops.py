@@ -236,6 +236,26 @@ def test_bilinear_add(f):
     assert rel(got, want) < 1e-6
 
 
+@pytest.mark.parametrize("hw", [(6, 10), (24, 78), (13, 21)])
+def test_final_assembly_fused_into_conv1_up(hw):
+    """`F.interpolate(prev, x2, bilinear) + conv1_up(x)` and the final `* 4` (ESMStereo.py:307,316,745) in the epilogue of
+    conv1_up's sub-pixel form (pixel_shuffle = 2 with a low-resolution residual): bit-identical to the conv followed by
+    esm_bilinear_add_f32, and equal to the torch statement."""
+    from esmstereo_b200 import layers
+    ops = _ops()
+    h, w = hw
+    torch.manual_seed(h)
+    up = layers.BasicConv(32, 1, deconv=True, is_3d=False, bn=False, gelu=False, kernel_size=4, padding=1, stride=2)
+    x, prev = rnd(2, 32, h, w, seed=3), rnd(2, 1, h, w, seed=4) * 10
+    want = (F.interpolate(prev, scale_factor=2, mode="bilinear", align_corners=False)
+            + F.conv_transpose2d(x, up.conv.weight.detach(), None, stride=2, padding=1)) * 4
+    up = up.cuda().eval()
+    fused = up(x.cuda(), bilinear_prev=prev.cuda(), final_scale=4.0)
+    two = ops.bilinear_add(prev.cuda(), up(x.cuda()), 2, 4.0)
+    assert torch.equal(fused, two)
+    assert rel(fused, want) < 2e-5
+
+
 @pytest.mark.parametrize("C", [8, 16])
 def test_shufflemixer_block(C):
     """FMBlock (2 SMLayers + conv tail) against the oracle's restatement of shufflemixer.py."""
