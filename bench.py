@@ -284,6 +284,15 @@ def kernel_rooflines(model, peaks, cfg):
     pup = agg.conv2_up.packed()
     out["hourglass_deconv3d_level2"] = conv_entry(lambda: ops.conv(x2, pup, "gelu", out_size=(d2, h2, w2), fp32_only=fp32_only),
                                                   2.0 * c2 * c1 * 64 * v2, 4.0 * (c2 + 8 * c1) * v2)
+    # the upsampler's widest 2D layer shape: 32 -> 32 k3 at half resolution (dm4x / ref4x, ESMStereo.py:250-253,191-199);
+    # on the kh-in-K tcgen05 kernel of conv_tc.cu since round 2
+    up = getattr(model.upsample_module, "dm4x", None)
+    if up is not None:
+        pu = up[1].packed()
+        cu = up[1].conv.weight.shape[0]
+        xu = torch.randn(1, cu, H // 2, W // 2, generator=g).to(dev)
+        out["upsampler_conv2d_%d_%d_half_res" % (cu, cu)] = conv_entry(lambda: ops.conv(xu, pu, "gelu", fp32_only=up[1].fp32_only), 2.0 * cu * cu * 9 * (H // 2) * (W // 2),
+                                                                        4.0 * 2 * cu * (H // 2) * (W // 2))
     cost = torch.randn(1, D, h, w, generator=g).to(dev)
     if s == 4:
         t = time_kernel(lambda: ops.regression_top2(cost), flush)
@@ -455,7 +464,7 @@ def run_ours(args):
             if j == GATHER_EVERY - 1:
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
-                    shard.gather_disparities(stash, world * GATHER_EVERY * B, rank, world)
+                    shard.gather_disparities(stash, world * GATHER_EVERY * B, rank, world, flat=False)  # dataset-ordered view, no re-copy
                     gather_ev.record(side)
         return out
 

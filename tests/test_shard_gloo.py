@@ -27,8 +27,10 @@ def _worker(rank, world, port, n_pairs, out_dir):
     # stand-in for the per-rank forward: "disparity" of pair i is a constant image of value i
     local = torch.stack([torch.full((4, 6), float(i)) for i in mine]) if mine else torch.zeros(0, 4, 6)
     full = gather_disparities(local, n_pairs, rank, world)
+    view = gather_disparities(local, n_pairs, rank, world, flat=False)  # [per_rank, world, H, W]: pair j * world + r at [j, r]
     if rank == 0:
         torch.save(full, os.path.join(out_dir, "full.pt"))
+        torch.save(view.clone(), os.path.join(out_dir, "view.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -41,6 +43,10 @@ def test_pairs_shard_and_gather_world2(tmp_path):
     assert full.shape == (n_pairs, 4, 6)
     for i in range(n_pairs):  # every pair exactly once, in dataset order
         assert torch.all(full[i] == float(i))
+    view = torch.load(os.path.join(str(tmp_path), "view.pt"))  # the copy-free form: same order through a two-level index
+    assert view.shape == ((n_pairs + world - 1) // world, world, 4, 6)
+    for i in range(n_pairs):
+        assert torch.all(view[i // world, i % world] == float(i))
 
 
 def test_shard_indices_cover_everything_once():
