@@ -100,7 +100,10 @@ typedef struct {
 long long esm_packed_weight_elems(int Cout, int Cin, int kd, int kh, int kw, int transposed);
 /*
  * Repack a torch-layout weight ([Cout,Cin,kd,kh,kw]; transposed: [Cin,Cout,kd,kh,kw]) into the
- * kernel layout ([phase][tap][Cin_pad][Cout_pad], zero padded).  Device to device.
+ * kernel layout ([phase][tap][Cin_pad][Cout_pad], zero padded).  Device to device.  For Cin >= 8 the pack continues
+ * with the operands of the tcgen05 engines, already split into TF32 hi / lo parts: the tap slabs of the streamed-weight
+ * engine and, for stride-1 k1 / k3 layers, the resident-weight image of conv_tc.cu in its shared-memory layout (fetched
+ * by bulk copies).  `packed` must hold esm_packed_weight_elems() floats and be 16-byte aligned.
  */
 int esm_pack_conv_weight_f32(const float* w, float* packed, int Cout, int Cin, int kd, int kh, int kw,
                              int transposed, void* stream);

@@ -94,6 +94,8 @@ def full():
                 key = "hourglass_conv3d_24_24"
             if "tc_conv_kernel<24, 1, 3, 0" in name:
                 key = "hourglass_conv3d_level1"
+            if "tck_conv_kernel" in name:
+                key = "upsampler_conv2d_32_32_half_res"
             if "tcf_conv_kernel" in name and "hourglass_conv3d_level2" not in traffic:
                 key = "hourglass_conv3d_level2"      # prof_conv.py runs the 40 -> 40 conv before the 40 -> 24 transposed conv
             elif "tcf_conv_kernel" in name:
@@ -104,7 +106,7 @@ def full():
         json.dump(traffic, f, indent=1, sort_keys=True)
     print("traffic", traffic)
     # source-level hot spots of the dominant kernel
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:conv_kernel"],
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:conv_kernel|tck_conv"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
     secs, cur = [], None
