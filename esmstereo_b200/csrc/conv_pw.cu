@@ -13,6 +13,7 @@
 // full resolution, ESMStereo.py:528-533) and the first layers on the disparity map (1 -> 32 k5 / k3 s2, :191,:245) --
 // which the channel-chunked engines pad to 8 input channels: 27 / 25 / 9 loads and 32 accumulators per pixel.
 #include "conv_tc.cuh"
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 #include <string.h>
@@ -214,6 +215,27 @@ bool pw_conv_plan(const esm_conv_t* d, PwPlan* plan) {
   // channels per thread: 32 accumulators at most (two CTAs' worth of registers stay resident); wider layers re-read the
   // input once per channel tile, from L2
   plan->CO = cop8 <= 8 ? 8 : cop8 <= 16 ? 16 : cop8 <= 24 ? 24 : 32;
+  // One pixel per thread: a small image leaves a handful of warps per SM (96 x 312: 6), each walking Cin dependent
+  // load batches -- latency-bound (32 -> 32 k1 at 96 x 312: 16.5 us for 7.5 MB).  Narrower channel tiles multiply the
+  // warps (the input is re-read from L1 / L2 once per tile) until ~16 warps per SM are in flight.  ESM_PW_SPLIT=0: off.
+  {
+    static const bool split_env = !(getenv("ESM_PW_SPLIT") && atoi(getenv("ESM_PW_SPLIT")) == 0);
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const long long warps = ((long long)d->B * d->Dout * d->Hout * d->Wout + 31) / 32;
+    if (split_env && k1 && !d->pixel_shuffle && warps > 0) {
+      const long long want = (16ll * sms + warps - 1) / warps;  // channel tiles for ~16 warps per SM
+      if (want > 1) {
+        int co = (int)(cop8 / want) / 8 * 8;
+        co = co < 8 ? 8 : co;
+        if (co < plan->CO) plan->CO = co;
+      }
+    }
+  }
   plan->cotiles = ceil_div(d->Cout, plan->CO);
   if (plan->cotiles > 8) return false;
   plan->smem = ((size_t)d->kh * d->kw * d->Cin + 2) * plan->CO * sizeof(float);

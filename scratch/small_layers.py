@@ -32,7 +32,8 @@ def timeit(fn, n=50):
 
 
 CASES = [(32, 32, 3, (24, 78)), (32, 32, 3, (48, 156)), (32, 32, 3, (96, 312)), (32, 32, 3, (192, 624)), (16, 32, 3, (96, 312)),
-         (80, 32, 3, (96, 312)), (32, 16, 1, (96, 312)), (128, 32, 1, (48, 156)), (16, 16, 3, (192, 624))]
+         (80, 32, 3, (96, 312)), (32, 16, 1, (96, 312)), (128, 32, 1, (48, 156)), (16, 16, 3, (192, 624)), (48, 48, 3, (96, 312)),
+         (32, 32, 1, (96, 312)), (160, 32, 1, (48, 156)), (112, 32, 1, (96, 312)), (96, 32, 1, (192, 624))]
 
 if __name__ == "__main__":
     prof = "prof" in sys.argv
@@ -47,7 +48,7 @@ if __name__ == "__main__":
             continue
         row = []
         for name, env in (("fp32", {"ESM_TC": "0"}), ("tc", {"ESM_TC": "3", "ESM_TC_FORCE": "1"}), ("tcg", {"ESM_TC": "3", "ESM_TC_FORCE": "2"}),
-                          ("pinned", {"ESM_TC": "3"})):
+                          ("pw", {"ESM_TC": "3", "ESM_TC_FORCE": "3"}), ("pinned", {"ESM_TC": "3"})):
             os.environ.pop("ESM_TC_FORCE", None)
             os.environ.update(env)
             try:
