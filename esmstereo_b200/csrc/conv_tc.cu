@@ -41,6 +41,7 @@ struct TcK {
   int Cout, CinPad, CoutPad;
   const float* weight;  // fp32 pack of esm_pack_conv_weight_f32: [tap][CinPad][CoutPad]
   const float* wimg;    // tck_conv_kernel: the split weight image of the pack (TcImg)
+  int tail_help;        // tck_conv_kernel: the producer warps help with the epilogue of the CTA's last rows
   const float* scale;
   const float* shift;
   int act, act2;
@@ -562,11 +563,13 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid
   uint64_t* accf = empty + NS;
   uint64_t* acce = accf + NSLOT;
   uint64_t* wready = acce + NSLOT;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wready + 1);
+  uint64_t* accl = wready + 1;  // once-only "accumulator full" of the CTA's last rows (helper warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accl + NSLOT);
   float* s_aff = reinterpret_cast<float*>(tmem_slot + 2);  // [2][COT] scale, shift of this channel tile
   const int cot = blockIdx.x / p.ctas_per_cot;
   const int cta = blockIdx.x % p.ctas_per_cot;
   const int rows = p.rows, nsteps = rows + 2;
+  const bool HELP = p.tail_help != 0;  // producer warps take half of the last rows' epilogue
 
   pdl_launch_dependents();
   if (tid == 0) {
@@ -577,6 +580,7 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid
     for (int i = 0; i < NSLOT; ++i) {
       tc_mbar_init(&accf[i], 1);
       tc_mbar_init(&acce[i], TC_NEW);
+      tc_mbar_init(&accl[i], 1);
     }
     tc_mbar_init(wready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -602,6 +606,92 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid
     const float* img = p.wimg + (long long)cot * ncg * (3 * 2 * WSLAB / 4);
     for (int cg = 0; cg < ncg; ++cg) tc_bulk_g2s(s_w + (size_t)cg * (3 * 2 * WSLAB), img + (long long)cg * (3 * 2 * WSLAB / 4), 3 * 2 * WSLAB, wready);
   }
+
+  // ---- epilogue of one output row of an item for TMEM lane quadrant q: channels [ch0 + cb, ch0 + ce) of the tile, one
+  // 8-channel group (24 accumulator columns) per TMEM round trip: kw gather by two warp shuffles, BN / activation, stores.
+  // `once`: wait on the once-only barrier of one of the CTA's last four rows (the helper warps below may be several
+  // phases ahead of accf, and a parity can only name the current phase or the one before it).
+  const int oC = (int)p.oC, oH = (int)p.oH;
+  const bool post = p.out_mul || p.residual || p.act2 != ESM_ACT_NONE;
+  const bool gelu = p.act == ESM_ACT_GELU;
+  const float oscale = p.out_scale;
+  const float debias = 1.0f + TC_TRUNC_BIAS * (float)(ncg * 3 * (p.npass == 3 ? 3 : 1));
+  const int n_my = cta < p.items_per_cot ? (p.items_per_cot - cta + p.ctas_per_cot - 1) / p.ctas_per_cot : 0;  // items of this CTA
+  const int tail_rows = rows < NSLOT ? rows : NSLOT;  // rows of the last item whose slots are never reused
+  auto epi_row = [&](int item, int r, uint32_t rc, int q, int ch0, int cb, int ce, bool once, bool hand_back) {
+    const TcItem ti = tc_decode(p, item, 1);
+    const int strip = ti.grp * 4 + q;
+    const int seg = strip % p.nseg, ys = strip / p.nseg;
+    const int x = seg * p.segw + lane - 1;
+    const int ya = ys * rows;
+    const int yb = min(ya + rows, p.H);
+    const bool lane_ok = strip < p.nstrips && lane >= 1 && lane < p.segw + 1 && x < p.W;
+    const int nvalid = p.Cout - (cot * COT + ch0);
+    float* op = p.out + ((long long)ti.b * p.oB + (long long)(cot * COT + ch0) * p.oC + x);
+    const float* rp = p.residual ? p.residual + ((long long)ti.b * p.oB + (long long)(cot * COT + ch0) * p.oC + x) : nullptr;
+    const float* mp = p.out_mul ? p.out_mul + ((long long)ti.b * p.omB + (long long)(cot * COT + ch0) * p.omC + x) : nullptr;
+    {
+      {
+        const int yo = ya + r;
+        const bool row_ok = lane_ok && yo < yb;
+        tc_mbar_wait(once ? &accl[rc & 3] : &accf[rc & 3], once ? 0u : ((rc >> 2) & 1), 600 + (int)(rc & 3));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + (rc & 3) * SLOT + ch0 * 3;
+        for (int c8 = cb; c8 < ce; c8 += 8) {
+          // two 4-channel units per TMEM round trip: their gather / BN / activation chains are independent, which is
+          // what hides the dependent-issue latency of 8 epilogue warps (one unit at a time: 950 clk per unit)
+          float d[24], rv[8];  // [channel j][kw]
+          tc_ld16(tb + c8 * 3, d);
+          tc_ld8(tb + c8 * 3 + 16, d + 16);
+          tc_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)  // out column x gathers input columns x-1 (kw=0), x (kw=1), x+1 (kw=2)
+            rv[j] = __shfl_up_sync(0xffffffffu, d[j * 3 + 0], 1) + d[j * 3 + 1] + __shfl_down_sync(0xffffffffu, d[j * 3 + 2], 1);
+          if (hand_back && c8 + 8 >= ce) {  // last TMEM read of this row: hand the accumulator slot back
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&acce[rc & 3]);
+          }
+          if (row_ok) {
+            const int cl = ch0 + c8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = fmaf(rv[j] * debias, s_aff[cl + j], s_aff[COT + cl + j]);
+            if (gelu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rv[j] = tc_gelu(rv[j]);
+            } else if (p.act != ESM_ACT_NONE) {
+#pragma unroll
+              for (int h = 0; h < 8; h += 4) {
+                const float4 a = apply_act4(make_float4(rv[h], rv[h + 1], rv[h + 2], rv[h + 3]), p.act);
+                rv[h] = a.x; rv[h + 1] = a.y; rv[h + 2] = a.z; rv[h + 3] = a.w;
+              }
+            }
+            const int o_off = yo * oH + c8 * oC;
+            if (post) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (c8 + j < nvalid) {
+                  if (mp) rv[j] *= __ldg(mp + ((c8 + j) * (int)p.omC + yo * (int)p.omH));
+                  if (rp) rv[j] += __ldg(rp + (o_off + j * oC));
+                }
+              }
+              if (p.act2 != ESM_ACT_NONE) {
+#pragma unroll
+                for (int h = 0; h < 8; h += 4) {
+                  const float4 a = apply_act4(make_float4(rv[h], rv[h + 1], rv[h + 2], rv[h + 3]), p.act2);
+                  rv[h] = a.x; rv[h + 1] = a.y; rv[h + 2] = a.z; rv[h + 3] = a.w;
+                }
+              }
+            }
+            float* o = op + o_off;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (c8 + j < nvalid) o[j * oC] = rv[j] * oscale;
+          }
+        }
+      }
+    }
+  };
 
   if (warp >= TC_PROD_WARP) {
     // ============================ operand producers (as in tc_conv_kernel, 2D, one input row per step) ============================
@@ -696,6 +786,12 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid
       if (item < p.items_per_cot) load(va);
       store_stage(vb);
     }
+    // nothing left to load: take the second 8 channels of epilogue warp (warp % 4, tw / 4) on the last rows
+    if (HELP && n_my > 0) {
+      const int last_item = cta + (n_my - 1) * p.ctas_per_cot;
+      const uint32_t rowc = (uint32_t)(n_my - 1) * (uint32_t)rows;
+      for (int r = rows - tail_rows; r < rows; ++r) epi_row(last_item, r, rowc + (uint32_t)r, warp & 3, (tw >> 2) * CW, 8, CW, true, false);
+    }
   } else if (warp == TC_MMA_WARP) {
     // ============================ MMA issuer ============================
     // Step s brings input row ya - 1 + s: kh = 0 / 1 / 2 send it to output rows s / s-1 / s-2 of the item (where they
@@ -710,7 +806,8 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid
     uint32_t st = 0, ph = 0, rowc = 0;  // rowc: output rows of the items before this one
     tc_mbar_wait(wready, 0, 700);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
+    int it = 0;
+    for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot, ++it) {
       for (int step = 0; step < nsteps; ++step) {
         if (step < rows) {
           const uint32_t rc = rowc + (uint32_t)step;
@@ -751,7 +848,10 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid
           }
         }
         if (step >= 2) {
-          if (leader) tc_commit(&accf[(rowc + (uint32_t)(step - 2)) & 3]);
+          if (leader) {
+            tc_commit(&accf[(rowc + (uint32_t)(step - 2)) & 3]);
+            if (HELP && it == n_my - 1 && step - 2 >= rows - tail_rows) tc_commit(&accl[(rowc + (uint32_t)(step - 2)) & 3]);
+          }
           __syncwarp();
         }
       }
@@ -759,88 +859,17 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid
     }
   } else if (warp < TC_NEW) {
     // ============================ epilogue ============================
-    // warp w and w+4 share TMEM lane quadrant q = w % 4 (one strip) and own CW = COT/2 channels each; one 4-channel unit
-    // (12 accumulator columns) at a time: kw gather by two warp shuffles, BN / activation, stores.
+    // warp w and w+4 share TMEM lane quadrant q = w % 4 (one strip) and own CW = COT/2 channels each.  On the last
+    // tail_rows rows of the CTA's last item each of them keeps the first 8 of its 16 channels and a producer warp, idle
+    // by then, takes the other 8 (below): those rows' epilogue is exposed (nothing overlaps it).
     const int q = warp & 3;
     const int ch0 = (warp >> 2) * CW;
-    const int nvalid = p.Cout - (cot * COT + ch0);
-    const int oC = (int)p.oC, oH = (int)p.oH;
-    const bool post = p.out_mul || p.residual || p.act2 != ESM_ACT_NONE;
-    const bool gelu = p.act == ESM_ACT_GELU;
-    const float oscale = p.out_scale;
-    const float debias = 1.0f + TC_TRUNC_BIAS * (float)(ncg * 3 * (p.npass == 3 ? 3 : 1));
     uint32_t rowc = 0;
-    for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
-      const TcItem ti = tc_decode(p, item, 1);
-      const int strip = ti.grp * 4 + q;
-      const int seg = strip % p.nseg, ys = strip / p.nseg;
-      const int x = seg * p.segw + lane - 1;
-      const int ya = ys * rows;
-      const int yb = min(ya + rows, p.H);
-      const bool lane_ok = strip < p.nstrips && lane >= 1 && lane < p.segw + 1 && x < p.W;
-      float* op = p.out + ((long long)ti.b * p.oB + (long long)(cot * COT + ch0) * p.oC + x);
-      const float* rp = p.residual ? p.residual + ((long long)ti.b * p.oB + (long long)(cot * COT + ch0) * p.oC + x) : nullptr;
-      const float* mp = p.out_mul ? p.out_mul + ((long long)ti.b * p.omB + (long long)(cot * COT + ch0) * p.omC + x) : nullptr;
+    int i = 0;
+    for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot, ++i) {
       for (int r = 0; r < rows; ++r) {
-        const int yo = ya + r;
-        const bool row_ok = lane_ok && yo < yb;
-        const uint32_t rc = rowc + (uint32_t)r;
-        tc_mbar_wait(&accf[rc & 3], (rc >> 2) & 1, 600 + (int)(rc & 3));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + (rc & 3) * SLOT + ch0 * 3;
-#pragma unroll
-        for (int c8 = 0; c8 < CW; c8 += 8) {
-          // two 4-channel units per TMEM round trip: their gather / BN / activation chains are independent, which is
-          // what hides the dependent-issue latency of 8 epilogue warps (one unit at a time: 950 clk per unit)
-          float d[24], rv[8];  // [channel j][kw]
-          tc_ld16(tb + c8 * 3, d);
-          tc_ld8(tb + c8 * 3 + 16, d + 16);
-          tc_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 8; ++j)  // out column x gathers input columns x-1 (kw=0), x (kw=1), x+1 (kw=2)
-            rv[j] = __shfl_up_sync(0xffffffffu, d[j * 3 + 0], 1) + d[j * 3 + 1] + __shfl_down_sync(0xffffffffu, d[j * 3 + 2], 1);
-          if (c8 + 8 >= CW) {  // last TMEM read of this row: hand the accumulator slot back
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) tc_mbar_arrive(&acce[rc & 3]);
-          }
-          if (row_ok) {
-            const int cl = ch0 + c8;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rv[j] = fmaf(rv[j] * debias, s_aff[cl + j], s_aff[COT + cl + j]);
-            if (gelu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) rv[j] = tc_gelu(rv[j]);
-            } else if (p.act != ESM_ACT_NONE) {
-#pragma unroll
-              for (int h = 0; h < 8; h += 4) {
-                const float4 a = apply_act4(make_float4(rv[h], rv[h + 1], rv[h + 2], rv[h + 3]), p.act);
-                rv[h] = a.x; rv[h + 1] = a.y; rv[h + 2] = a.z; rv[h + 3] = a.w;
-              }
-            }
-            const int o_off = yo * oH + c8 * oC;
-            if (post) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (c8 + j < nvalid) {
-                  if (mp) rv[j] *= __ldg(mp + ((c8 + j) * (int)p.omC + yo * (int)p.omH));
-                  if (rp) rv[j] += __ldg(rp + (o_off + j * oC));
-                }
-              }
-              if (p.act2 != ESM_ACT_NONE) {
-#pragma unroll
-                for (int h = 0; h < 8; h += 4) {
-                  const float4 a = apply_act4(make_float4(rv[h], rv[h + 1], rv[h + 2], rv[h + 3]), p.act2);
-                  rv[h] = a.x; rv[h + 1] = a.y; rv[h + 2] = a.z; rv[h + 3] = a.w;
-                }
-              }
-            }
-            float* o = op + o_off;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (c8 + j < nvalid) o[j * oC] = rv[j] * oscale;
-          }
-        }
+        const bool tail = HELP && i == n_my - 1 && r >= rows - tail_rows;
+        epi_row(item, r, rowc + (uint32_t)r, q, ch0, 0, tail ? 8 : CW, false, true);
       }
       rowc += (uint32_t)rows;
     }
@@ -996,6 +1025,8 @@ int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
     const TcImg tk = tc_img_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0);
     ESM_REQUIRE(tk.kind == 1 && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0, "conv(tc): no weight image for the kh-in-K kernel");
     k.wimg = d->weight + tk.offset;
+    static const bool help_env = !(getenv("ESM_TC_TAILHELP") && atoi(getenv("ESM_TC_TAILHELP")) == 0);
+    k.tail_help = help_env ? 1 : 0;
   } else if (!plan.gwc) {
     // the pack's image of this layer for tc_conv_kernel (same channel tile, taps and depth); the kernel stages the
     // weights itself when there is none (group-wise correlation stem: its 0.5 is folded into the weights)
