@@ -159,12 +159,12 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.marks = index, [], None, []
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("ESM_CLOCK_MS", "100")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -176,6 +176,17 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.rows.append([c.strip() for c in ln.split(",")])
 
+    def wait_first(self, timeout_s):
+        """Block until nvidia-smi has attached to the GPU and delivered its first sample."""
+        t_end = time.perf_counter() + timeout_s
+        while self.proc is not None and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
+    def mark(self):
+        """Called at the start and at the end of the timed region: summary() reports the samples in between (plus one
+        on either side: a 100 ms period can leave a short region without a sample of its own)."""
+        self.marks.append(len(self.rows))
+
     def __exit__(self, *exc):
         if self.proc is not None:
             time.sleep(0.15)
@@ -186,7 +197,10 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows
+        if len(self.marks) >= 2:
+            rows = self.rows[max(0, self.marks[0] - 1):self.marks[1] + 1] or self.rows
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -475,13 +489,19 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     W_, K = max(args.warmup, 3), args.steps
-    for i in range(W_):
-        step(i)
-    barrier()
+    # The clock sampler (`nvidia-smi -lms`) is started BEFORE the warm-up and the timed region waits for its first
+    # sample: a freshly started nvidia-smi attaches to the GPU and stalls the work in flight once, for ~6 ms (measured:
+    # K = 200 and K = 2000 steps differed by a constant 5.9 ms) -- inside a short timed region that is 0.1-0.3 ms per step.
+    # It keeps sampling through the timed steps; only those samples are reported.
     with ClockSampler(local) as clk:
+        clk.wait_first(3.0)
+        for i in range(W_):
+            step(i)
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         torch.cuda.profiler.start()  # lets `ncu --profile-from-start off` capture exactly the timed steps
+        clk.mark()
         e0.record()
         for i in range(K):
             step(i)
@@ -489,6 +509,7 @@ def run_ours(args):
             torch.cuda.current_stream().wait_stream(side)
         e1.record()
         barrier()
+        clk.mark()
         torch.cuda.profiler.stop()
         t_dev = e0.elapsed_time(e1) * 1e-3
 
