@@ -34,7 +34,13 @@ def test_argument_errors_need_no_gpu():
     # fp32 pack [phase][tap][Cin_pad][Cout_pad] + (Cin >= 8) the split-TF32 slabs of the streamed tcgen05 engine:
     # phases * taps * ceil(Cin/8) slabs of [hi|lo][2][round_up(Cout,8)][4]
     n = L.esm_packed_weight_elems(8, 32, 3, 3, 3, 0)
-    assert n == 27 * 32 * 8 + 27 * 4 * 16 * 8
+    # ... + (stride-1 k1 / k3 layers) the resident-weight image of conv_tc.cu, 32-float aligned:
+    # [cot][cg][kd][hi|lo][2][taps * COT][4] with COT = 8 here
+    assert n == 27 * 32 * 8 + 27 * 4 * 16 * 8 + 1 * 4 * 3 * 2 * (9 * 8) * 8
+    # 2D k3 with Cout % 32 == 0 and Cin <= 64: the image of the kh-in-K kernel, [cot][cg][kh][hi|lo][2][96][4]
+    assert L.esm_packed_weight_elems(32, 32, 1, 3, 3, 0) == 9 * 32 * 32 + 9 * 4 * 16 * 32 + 1 * 4 * 3 * 2 * 96 * 8
+    # transposed layers carry no image
+    assert L.esm_packed_weight_elems(24, 40, 4, 4, 4, 1) == 8 * 8 * 40 * 24 + 8 * 8 * 5 * 16 * 24
     assert L.esm_packed_weight_elems(40, 72, 4, 4, 4, 1) == 8 * 8 * 72 * 40 + 8 * 8 * 9 * 16 * 40
     assert L.esm_packed_weight_elems(72, 8, 1, 1, 1, 0) == 8 * 80 + 1 * 1 * 16 * 72   # Cout 72 -> 2 CTAs x 40 channels
     assert L.esm_packed_weight_elems(1, 24, 4, 4, 4, 1) == 8 * 8 * 24 * 4 + 8 * 8 * 3 * 16 * 8   # Cout=1 padded to 4 (16-byte weight rows)
