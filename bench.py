@@ -465,8 +465,21 @@ def run_ours(args):
     # it overlaps the next replays ("once per sweep, on a side stream")
     GATHER_EVERY = 8
     side = torch.cuda.Stream(device=dev) if world > 1 else None
-    stash = torch.empty(GATHER_EVERY * B, H, W, device=dev) if world > 1 else None
     gather_ev = torch.cuda.Event() if world > 1 else None
+    stash, peer, gather_how = None, None, None
+    if world > 1:
+        # copy-engine pulls out of symmetric memory (shard.PeerGather) unless ESM_GATHER=nccl or the rendezvous fails
+        if os.environ.get("ESM_GATHER", "p2p") != "nccl":
+            try:
+                peer = shard.PeerGather(GATHER_EVERY * B, (H, W), dev)
+                stash = peer.stash
+                gather_how = "copy-engine pulls from symmetric memory over NVLink (shard.PeerGather)"
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write("[bench] symmetric-memory gather unavailable (%s): NCCL all-gather\n" % (str(e).splitlines()[0][:200],))
+                peer = None
+        if peer is None:
+            stash = torch.empty(GATHER_EVERY * B, H, W, device=dev)
+            gather_how = "NCCL all-gather (shard.gather_disparities)"
 
     def step(i):
         out = pick(graphed(*pool[i % NPOOL]))
@@ -478,7 +491,10 @@ def run_ours(args):
             if j == GATHER_EVERY - 1:
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
-                    shard.gather_disparities(stash, world * GATHER_EVERY * B, rank, world, flat=False)  # dataset-ordered view, no re-copy
+                    if peer is not None:
+                        peer.gather()
+                    else:
+                        shard.gather_disparities(stash, world * GATHER_EVERY * B, rank, world, flat=False)  # dataset-ordered view, no re-copy
                     gather_ev.record(side)
         return out
 
@@ -556,7 +572,7 @@ def run_ours(args):
             "config": {"workload": cfg["workload"], "name": args.config, "pairs_per_step_per_gpu": B,
                        "l2": "%d rotating input batches (%.0f MB) > 126 MB L2" % (NPOOL, NPOOL * per_batch / 1e6), "cuda_graph": True,
                        "parallelism": "pairs sharded by rank",
-                       "gather": "NCCL all-gather of the disparities every %d steps on a side stream" % GATHER_EVERY if world > 1 else None},
+                       "gather": ("%s of the disparities every %d steps on a side stream" % (gather_how, GATHER_EVERY)) if world > 1 else None},
             "clocks": clk.summary(),
             "e2e": {"value": world * K * B / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": per_batch,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / K, "wall_ms_per_step": 1e3 * t_e2e_wall / K},

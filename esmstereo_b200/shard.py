@@ -42,3 +42,37 @@ def gather_disparities(local: torch.Tensor, n_pairs: int, rank: int, world: int,
     if not flat:
         return ordered
     return ordered.reshape((world * per_rank,) + tuple(local.shape[1:]))[:n_pairs]
+
+
+class PeerGather:
+    """The same gather without NCCL kernels: every rank keeps its block of outputs in SYMMETRIC memory (peer-mapped over
+    NVLink: torch.distributed._symmetric_memory) and pulls the blocks of its peers with plain device copies, which the
+    copy engines execute -- no SM is taken from the forward that keeps running on the compute stream (an NCCL all-gather of
+    8 x 15 MB holds its channels' SMs for ~350 us per sweep; the persistent one-CTA-per-SM conv kernels then wait for them:
+    +30 us per step at 8 GPUs).  Two stream-ordered barriers bracket the pulls: blocks complete before anyone reads,
+    everyone done reading before a block is overwritten.
+
+        pg = PeerGather(n_local, (H, W), device);  pg.stash[j] = disparity_j ...;  view = pg.gather()   # on a side stream
+
+    gather() returns the dataset-ordered view [n_local, world, H, W] (pair j * world + r at [j, r]) of a buffer that the
+    next gather() overwrites."""
+
+    def __init__(self, n_local: int, tail, device, dtype=torch.float32) -> None:
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        group = dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:  # noqa: BLE001 -- newer torch enables every group implicitly
+            pass
+        self.stash = symm_mem.empty((n_local,) + tuple(tail), dtype=dtype, device=device)
+        self.hdl = symm_mem.rendezvous(self.stash, group.group_name)
+        self.out = torch.empty((self.world, n_local) + tuple(tail), dtype=dtype, device=device)
+
+    def gather(self) -> torch.Tensor:
+        self.hdl.barrier(channel=0)
+        for step in range(self.world):
+            r = (self.rank - step) % self.world  # staggered: every link carries one pull at a time
+            self.out[r].copy_(self.hdl.get_buffer(r, self.stash.shape, self.stash.dtype), non_blocking=True)
+        self.hdl.barrier(channel=1)
+        return self.out.transpose(0, 1)

@@ -1,4 +1,5 @@
-"""Multi-process host logic (pairs sharded by rank, gather of outputs) on CPU with the gloo backend."""
+"""Multi-process host logic (pairs sharded by rank, gather of outputs): gloo on CPU, and -- where two GPUs are present -- the
+copy-engine gather out of symmetric memory."""
 import os
 import socket
 import sys
@@ -6,6 +7,7 @@ import sys
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -56,3 +58,37 @@ def test_shard_indices_cover_everything_once():
         for world in (1, 2, 3, 8):
             seen = sorted(i for r in range(world) for i in shard_indices(n, r, world))
             assert seen == list(range(n))
+
+
+def _peer_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from esmstereo_b200.shard import PeerGather
+    pg = PeerGather(3, (4, 6), dev)
+    for sweep in range(2):  # the buffers are reused: two sweeps check the barriers, not just the copies
+        for j in range(3):
+            pg.stash[j].fill_(float(100 * sweep + j * world + rank))  # "disparity" of pair j * world + rank
+        view = pg.gather()
+        torch.cuda.synchronize()
+        got = view.clone().cpu()
+        if rank == 0:
+            torch.save(got, os.path.join(out_dir, "peer%d.pt" % sweep))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_peer_gather_symmetric_memory_world2(tmp_path):
+    """shard.PeerGather (copy-engine pulls out of symmetric memory): dataset order through the [j, r] view, two sweeps."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world = 2
+    mp.spawn(_peer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for sweep in range(2):
+        view = torch.load(os.path.join(str(tmp_path), "peer%d.pt" % sweep))
+        assert view.shape == (3, world, 4, 6)
+        for i in range(3 * world):
+            assert torch.all(view[i // world, i % world] == float(100 * sweep + i))
