@@ -24,8 +24,11 @@ int check_launch(const char* what);
 // pdl_launch_dependents() (first instruction of every kernel here) and resources are free.  EVERY kernel launched that
 // way executes pdl_wait() in every thread before its first global-memory access (weights included), which blocks until
 // the previous grid has completed and flushed; what overlaps is launch latency, CTA placement and the on-chip prologue
-// (mbarrier init, TMEM allocation).  ESM_PDL is a bit mask of the kernel families that use it: 1 FP32-pipe conv, 2
-// resident tcgen05, 4 streamed tcgen05, 8 flat tcgen05, 16 pointwise, 32 everything else on the forward path.
+// (mbarrier init, TMEM allocation).  ESM_PDL is a bit mask of the kernel families that use it: 1 FP32-pipe conv, 16
+// pointwise, 32 everything else on the forward path.  The tcgen05 kernels (bits 2 / 4 / 8 in the round-2 experiment) do
+// NOT carry the instructions any more: a `griddepcontrol.wait` in their prologue makes ptxas give up the uniform datapath
+// for the values computed around it (R2UR 20 -> 380 in the gwc stem kernel, +14 us; the MMA issue loop pays 11 R2URs per
+// stage), which cost more than the launch overlap ever returned.
 bool pdl_enabled(int family_bit);
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

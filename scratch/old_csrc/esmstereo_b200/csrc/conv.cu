@@ -1,0 +1,996 @@
+// Direct (implicit-GEMM on the FP32 pipe) convolution family for the ESMStereo hot path.
+//
+// Two engines behind esm_conv_f32.  The k3 s1 p1 and k1 layers can run on tcgen05 (conv_tc.cu: taps-in-N
+// implicit GEMM, split-TF32 for fp32-grade accuracy); on the first call of a shape that plan is timed on the
+// device against the best plan of the FP32-pipe engine below and the faster one is cached.  The FP32-pipe
+// engine (packed FFMA2, measured 67 TFLOP/s in this inner loop) runs everything else: stride-2, transposed,
+// single-channel and coarse-level layers, and any layer where it wins.
+//
+// One kernel template covers conv k1/k3/k5 stride 1, k3 stride 2, and ConvTranspose k4 s2 p1
+// (as 4 / 8 sub-pixel phase convolutions with a 2-tap kernel per dimension), in 2D and 3D, with:
+//   * up to 3 channel-concatenated strided sources (replaces torch.cat and the crop-to-skip slices),
+//   * or the group-wise correlation volume generated on the fly from left/right features,
+//   * folded BatchNorm/bias affine, activation, broadcast multiply, residual add, second activation,
+//   * PixelShuffle store.
+// Each thread owns 4 consecutive output voxels along W x COG output channels (packed as float2
+// pairs for FFMA2); a CTA owns a TD x TH x 4*TWG brick of voxels and ALL output channels, stages
+// CK input channels of the brick + halo in shared memory together with the matching weights.
+#include "conv_kernel.cuh"
+#include "conv_tc.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <type_traits>
+
+namespace esm {
+
+// ------------------------------------------------------------------------------------------
+// weight packing / BN folding
+// ------------------------------------------------------------------------------------------
+// output channels are padded to 4 (single-channel heads: one 16-byte weight row) or to a multiple
+// of 8; above 64 they are split over n CTAs of COP = round_up(ceil(Cout/n), 8) channels each
+static int pad_cout(int Cout) {
+  if (Cout <= 4) return 4;
+  if (Cout <= 64) return round_up(Cout, 8);
+  const int n = ceil_div(Cout, 64);
+  return n * round_up(ceil_div(Cout, n), 8);
+}
+// single-channel inputs (disparity / confidence maps) get their own CK=1 instantiation instead of
+// 8x zero padding (only instantiated for the 8-wide channel groups)
+static int pad_cin(int Cin, int Cout) { return (Cin == 1 && Cout > 4) ? 1 : round_up(Cin, 8); }
+
+__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kd,
+                                   int kh, int kw, int transposed, int CinPad, int CoutPad, int KD, int KH, int KW,
+                                   int phases, int phases_d, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long r = i;
+  const int co = r % CoutPad;
+  r /= CoutPad;
+  const int ci = r % CinPad;
+  r /= CinPad;
+  const int tw = r % KW;
+  r /= KW;
+  const int thh = r % KH;
+  r /= KH;
+  const int tdd = r % KD;
+  r /= KD;
+  const int z = (int)r;  // phase
+  float v = 0.f;
+  if (co < Cout && ci < Cin) {
+    if (!transposed) {
+      v = w[(((long long)(co * Cin + ci) * kd + tdd) * kh + thh) * kw + tw];
+    } else {
+      const int pzw = z & 1, pzh = (z >> 1) & 1, pzd = (phases_d == 2) ? ((z >> 2) & 1) : 0;
+      const int kkw = 3 - pzw - 2 * tw;
+      const int kkh = 3 - pzh - 2 * thh;
+      const int kkd = (phases_d == 2) ? 3 - pzd - 2 * tdd : 0;
+      v = w[(((long long)(ci * Cout + co) * kd + kkd) * kh + kkh) * kw + kkw];  // [Cin,Cout,k,k,k]
+    }
+  }
+  out[i] = v;
+}
+
+__global__ void fold_bn_kernel(const float* g, const float* bta, const float* mean, const float* var,
+                               const float* bias, float eps, int C, float* scale, float* shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  float sc = 1.f, sh = 0.f;
+  if (g) {
+    sc = g[i] / sqrtf(var[i] + eps);
+    sh = bta[i] - mean[i] * sc;
+  }
+  if (bias) sh += bias[i] * sc;
+  scale[i] = sc;
+  shift[i] = sh;
+}
+
+struct PackGeom {
+  int KD, KH, KW, phases, phases_d, CinPad, CoutPad;
+  long long per_phase;
+};
+
+static PackGeom pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed) {
+  PackGeom g;
+  g.CinPad = pad_cin(Cin, Cout);
+  g.CoutPad = pad_cout(Cout);
+  if (transposed) {
+    g.phases_d = (kd == 4) ? 2 : 1;
+    g.KD = (kd == 4) ? 2 : 1;
+    g.KH = 2;
+    g.KW = 2;
+    g.phases = 4 * g.phases_d;
+  } else {
+    g.phases_d = 1;
+    g.KD = kd;
+    g.KH = kh;
+    g.KW = kw;
+    g.phases = 1;
+  }
+  g.per_phase = (long long)g.KD * g.KH * g.KW * g.CinPad * g.CoutPad;
+  return g;
+}
+
+// Second region of a packed weight, right after the fp32 pack: the operand slabs of the streamed-weight tcgen05
+// path (conv_tcg.cu), already split for the fp32-grade TF32 scheme.  One slab per (phase, 8-channel group, tap), in
+// that order, laid out as 8-row groups of four 128-byte UMMA core matrices (K-major, no swizzle):
+//   [co / 8][hi | lo][k / 4][co % 8][k % 4]
+// so that a CTA's channel tile of a slab -- and, when one tile covers every channel, the slabs of consecutive taps --
+// is one contiguous TMA bulk copy (LBO = 128 B between the K halves, SBO = 512 B between row groups).
+TcgPack tcg_pack_geom(int Cout, int Cin, int kd, int kh, int kw, int transposed) {
+  const PackGeom g = pack_geom(Cout, Cin, kd, kh, kw, transposed);
+  TcgPack t;
+  t.offset = g.per_phase * g.phases;
+  t.phases = g.phases;
+  t.taps = g.KD * g.KH * g.KW;
+  t.KD = g.KD;
+  t.KH = g.KH;
+  t.KW = g.KW;
+  t.ncg = ceil_div(Cin, 8);
+  t.CoutX = round_up(Cout, 8);
+  t.elems = Cin >= 8 ? (long long)t.phases * t.taps * t.ncg * 16 * t.CoutX : 0;
+  return t;
+}
+
+__global__ void pack_tcg_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kd, int kh, int kw,
+                                int transposed, int KD, int KH, int KW, int phases_d, int ncg, int CoutX, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long r = i;
+  const int co = r % CoutX;
+  r /= CoutX;
+  const int k = r % 8;
+  r /= 8;
+  const int cg = r % ncg;
+  r /= ncg;
+  const int tw = r % KW;
+  r /= KW;
+  const int thh = r % KH;
+  r /= KH;
+  const int tdd = r % KD;
+  r /= KD;
+  const int z = (int)r;  // phase
+  const int ci = cg * 8 + k;
+  float v = 0.f;
+  if (co < Cout && ci < Cin) {
+    if (!transposed) {
+      v = w[(((long long)(co * Cin + ci) * kd + tdd) * kh + thh) * kw + tw];
+    } else {
+      const int pzw = z & 1, pzh = (z >> 1) & 1, pzd = (phases_d == 2) ? ((z >> 2) & 1) : 0;
+      const int kkw = 3 - pzw - 2 * tw;
+      const int kkh = 3 - pzh - 2 * thh;
+      const int kkd = (phases_d == 2) ? 3 - pzd - 2 * tdd : 0;
+      v = w[(((long long)(ci * Cout + co) * kd + kkd) * kh + kkh) * kw + kkw];  // [Cin,Cout,k,k,k]
+    }
+  }
+  uint32_t hb, lb;
+  asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+  const float hi = __uint_as_float(hb);
+  asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
+  const long long slab = (((long long)z * ncg + cg) * KD + tdd) * KH * KW + thh * KW + tw;  // 16 * CoutX floats each
+  float* o = out + slab * 16 * CoutX + (co >> 3) * 128 + (k >> 2) * 32 + (co & 7) * 4 + (k & 3);
+  o[0] = hi;
+  o[64] = __uint_as_float(lb);
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side tiling + dispatch
+// ------------------------------------------------------------------------------------------
+struct Tiling {
+  int TWG, TH, TD, slots, IWP, ID, IH, IWR, IWL, nstages, NV;
+  size_t smem;
+};
+
+static size_t conv_smem_bytes(int CK, int ID, int IH, int IWP, int taps, int COP, bool gwc, int cpg, int nstages,
+                              int* IWR_out, int* IWL_out) {
+  auto pad32 = [](size_t n) { return (n + 31) & ~(size_t)31; };  // buffers are multiples of 128 bytes (TMA destinations)
+  const size_t in_elems = pad32((size_t)CK * ID * IH * IWP);
+  const size_t w_elems = pad32((size_t)taps * CK * COP);
+  size_t total = (gwc ? 2 : nstages) * in_elems + (gwc ? 3 : nstages) * w_elems;
+  int IWR = 0, IWL = 0;
+  if (gwc) {  // staging boxes start on a multiple of 4 columns (TMA): up to 3 extra columns on the left
+    IWL = round_up(IWP + 3, 4);
+    IWR = round_up(IWP + ID - 1 + 3, 4);
+    total += pad32((size_t)CK * cpg * IH * IWL) + pad32((size_t)CK * cpg * IH * IWR);
+  }
+  if (IWR_out) *IWR_out = IWR;
+  if (IWL_out) *IWL_out = IWL;
+  return total * sizeof(float) + 128 /* slack */ + 64 /* mbarriers */;
+}
+
+// Per-SM residency estimate: the kernels compile to <=128 registers (__launch_bounds__(256, 2)), so at most 512 threads per SM;
+// shared memory: 227 KB usable per SM, 1 KB reserved per CTA.
+static int resident_ctas(int nthreads, size_t smem) {
+  const int by_regs = 512 / nthreads;
+  const int by_smem = (int)((227 * 1024) / (smem + 1024));
+  int r = by_regs < by_smem ? by_regs : by_smem;
+  return r > 8 ? 8 : r;
+}
+
+struct Candidate {
+  Tiling tl;
+  int CK, COP, COG, cosplit;
+  double cost;
+};
+
+// Enumerate tile shapes for one (channel split, chunk depth) and append them with their modelled cost.
+static void enumerate_tilings(int Jw, int Jh, int Jd, int cin, int COG, int NV, int KW, int KH, int KD, int S, int CK, int COP,
+                              int cosplit, bool gwc, int cpg, int xo, long long work_mult, int num_sms, double extra_cost,
+                              std::vector<Candidate>* out) {
+  const int ncog = COP / COG;
+  for (int slots = 32; slots * ncog <= 256; slots += 32) {
+    for (int TWG = 1; TWG <= (NV == 1 ? 32 : 16); TWG *= 2) {
+      if (slots % TWG) continue;
+      const int R = slots / TWG;
+      for (int TD = 1; TD <= R; ++TD) {
+        if (R % TD) continue;
+        const int TH = R / TD;
+        if (Jd == 1 && TD != 1) continue;
+        const int TW = TWG * NV;
+        if ((TW * S) % 4) continue;  // tile origins must stay on 16-byte columns (TMA box alignment)
+        const int ID = (TD - 1) * S + KD, IH = (TH - 1) * S + KH;
+        const int XN = (NV - 1) * S + KW, XL = (XN + 3) / 4 * 4;
+        // row window of the last thread: aligned float4s (xo=0) or scalar@3 + float4s from column 4 (xo=3);
+        // NV=1: a scalar window of KW columns starting at column xo
+        int IWP = NV == 1 ? round_up((TWG - 1) * S + xo + KW, 4) : (TWG - 1) * 4 * S + (xo == 3 ? 4 + 4 * ((XN + 2) / 4) : XL);
+        if (NV == 4 && S == 1 && TWG < 8) {
+          const int want = (4 * TWG) % 32;  // rows of an 8-lane LDS.128 phase land on distinct banks
+          while (IWP % 32 != want) IWP += 4;
+        }
+        if (IWP > 256 || IH > 256 || ID > 256) continue;  // TMA box limits
+        const int nchunks = ceil_div(cin, CK);
+        for (int nstages = 2; nstages <= (gwc ? 2 : 4); nstages += 2) {
+        if (nstages > 2 && nchunks < 3) break;  // a deeper ring only pays when a tile has more chunks than stages
+        int IWR = 0, IWL = 0;
+        const size_t smem = conv_smem_bytes(CK, ID, IH, IWP, KD * KH * KW, COP, gwc, cpg, nstages, &IWR, &IWL);
+        if (smem > 224 * 1024 || IWR > 256) continue;
+        const int nthreads = slots * ncog;
+        const int ctas = resident_ctas(nthreads, smem);
+        if (ctas < 1) continue;
+        // Analytic time model (SM clocks).  FMA pipe: a warp-level FFMA2 holds its SMSP's pipe for
+        // 2 clk; LDS / loop overhead ~30% on top; fewer than ~12 resident warps cannot hide the
+        // LDS->FFMA2 latency.  Per work item a CTA also pays one TMA round trip unless the math
+        // covers it.  The model only RANKS candidates; the best few are then timed on the device.
+        const int warps = nthreads / 32;
+        const double smsp_load = (double)((ctas * warps + 3) / 4);
+        const double hide = ctas * warps >= 12 ? 1.0 : 12.0 / (ctas * warps);
+        const double ffma2 = (double)KD * KH * KW * CK * NV * COG / 2;  // per warp per item: NV voxels x COG/2 channel pairs per (tap, channel)
+        const double t_math = ffma2 * 2.0 * smsp_load * 1.3 * hide;
+        const double t_tma = nstages > 2 ? 700.0 : 1500.0;  // exposed TMA round trip per item
+        const double t_item = t_math > t_tma ? t_math : t_tma;
+        const long long tiles = (long long)ceil_div(Jw, TW) * ceil_div(Jh, TH) * ceil_div(Jd, TD) * work_mult;
+        const long long wave = (long long)(num_sms > 0 ? num_sms : 148) * ctas;
+        const double waves = (double)ceil_div_ll(tiles, wave);
+        const double t_epi = 1200.0 * smsp_load;
+        const double halo = (double)ID * IH * IWP / ((double)TD * TH * TW * S * S * (Jd == 1 ? 1 : S));
+        Candidate c;
+        c.cost = (waves * (nchunks * t_item + t_epi) + 6000.0) * (1.0 + 0.02 * halo) * extra_cost;
+        c.tl.TWG = TWG;
+        c.tl.TH = TH;
+        c.tl.TD = TD;
+        c.tl.slots = slots;
+        c.tl.IWP = IWP;
+        c.tl.ID = ID;
+        c.tl.IH = IH;
+        c.tl.IWR = IWR;
+        c.tl.IWL = IWL;
+        c.tl.nstages = nstages;
+        c.tl.NV = NV;
+        c.tl.smem = smem;
+        c.CK = CK;
+        c.COP = COP;
+        c.COG = COG;
+        c.cosplit = cosplit;
+        out->push_back(c);
+        }
+      }
+    }
+  }
+}
+
+static conv_fn_t pick_kernel(int KW, int S, int COG, int CK, bool gwc, bool tma, int xo, int nv) {
+  if (S == 1) {
+    if (KW == 1) return conv_kernels_k1(COG, CK, gwc, tma, xo, nv);
+    if (KW == 2) return conv_kernels_k2(COG, CK, gwc, tma, xo, nv);
+    if (KW == 3) return conv_kernels_k3(COG, CK, gwc, tma, xo, nv);
+    if (KW == 5) return conv_kernels_k5(COG, CK, gwc, tma, xo, nv);
+  } else if (S == 2 && KW == 3) {
+    return conv_kernels_k3s2(COG, CK, gwc, tma, xo, nv);
+  }
+  return nullptr;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encoder() {
+  static encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (encode_tiled_fn)ptr;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// fp32 tensor map of rank `rank` (innermost first); strides in elements for dims 1..rank-1
+bool encode_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const long long* strides_elems,
+                const int* box) {
+  encode_tiled_fn enc = get_encoder();
+  if (!enc) return false;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+    es[i] = 1;
+    if (box[i] < 1 || box[i] > 256) return false;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = (cuuint64_t)strides_elems[i] * sizeof(float);
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Launch plans are memoised per shape: the tiling search and the occupancy query cost ~50 us on the
+// host, which matters in eager mode (under CUDA-graph replay the host never runs them).
+struct PlanKey {
+  int v[24];
+  bool operator<(const PlanKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
+};
+// A plan pinned by esm_conv_plans_import (the persisted result of an earlier autotune): which engine, and for the
+// FP32-pipe engine which candidate of the tiling enumeration.
+struct PinnedPlan {
+  int use_tc;
+  int CK, COP, COG, cosplit, NV, TWG, TH, TD, slots, nstages;
+};
+static std::map<PlanKey, PinnedPlan> g_pinned;
+static std::mutex g_pinned_mu;
+static long long g_tuned_calls = 0;  // esm_conv_f32 calls that timed candidates on the device
+struct Plan {
+  Tiling tl;
+  conv_fn_t fn;         // cp.async pipeline (any strides)
+  conv_fn_t fn_tma[2];  // TMA pipeline for window offset XO = 0 / 3 (nullptr if not instantiated)
+  int cosplit, COP, COG, CK, blocks_per_sm;
+  int use_tc;  // 1: run on the resident-weight tcgen05 path (conv_tc.cu), 2: on the streamed-weight one (conv_tcg.cu),
+               // 3: on the pointwise streaming kernel (conv_pw.cu)
+  TcPlan tc;
+  TcgPlan tcg;
+  PwPlan pw;
+};
+
+struct LayerGeom {
+  int S, Jw, Jh, Jd;
+  bool gwc;
+};
+
+// Fill the tile-dependent kernel arguments, encode the tensor maps when the operands are TMA-eligible
+// (16-byte aligned bases and pitches, channel chunks that never straddle two sources) and launch.
+static int launch_plan(const esm_conv_t* d, const PackGeom& g, ConvK k, const Plan& plan, const LayerGeom& lg, int num_sms,
+                       cudaStream_t st) {
+  const Tiling& tl = plan.tl;
+  const bool gwc = lg.gwc;
+  const int ncog = plan.COP / plan.COG;
+  k.cosplit = plan.cosplit;
+  k.COP = plan.COP;
+  k.TWG = tl.TWG;
+  k.TH = tl.TH;
+  k.TD = tl.TD;
+  k.slots = tl.slots;
+  k.nthreads = tl.slots * ncog;
+  k.ID = tl.ID;
+  k.IH = tl.IH;
+  k.IWP = tl.IWP;
+  k.IWR = tl.IWR;
+  k.IWL = tl.IWL;
+  k.pzw_sel = -1;
+  k.nstages = tl.nstages;
+  k.tilesW = ceil_div(lg.Jw, tl.TWG * tl.NV);
+  k.tilesH = ceil_div(lg.Jh, tl.TH);
+  k.tilesD = ceil_div(lg.Jd, tl.TD);
+  k.phases = g.phases;
+  const long long total = (long long)k.tilesW * k.tilesH * k.tilesD * d->B * g.phases * plan.cosplit;
+  ESM_REQUIRE(total < (1ll << 30), "conv: too many tiles");
+  k.total_work = (int)total;
+  if (num_sms <= 0) {
+    set_error("conv: no CUDA device");
+    return ESM_ERR_CUDA;
+  }
+  ConvMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  bool use_tma = get_encoder() != nullptr && !getenv("ESM_NO_TMA");
+  auto aligned = [](const esm_src_t& sv, bool has_d) {
+    return (reinterpret_cast<uintptr_t>(sv.ptr) & 15) == 0 && sv.sH % 4 == 0 && sv.sC % 4 == 0 && sv.sB % 4 == 0 &&
+           (!has_d || sv.sD % 4 == 0);
+  };
+  if (use_tma && (reinterpret_cast<uintptr_t>(d->weight) & 15)) use_tma = false;
+  if (use_tma && !gwc && d->in_mul) use_tma = false;
+  for (int i = 0; use_tma && i < d->nsrc; ++i) {
+    if (!aligned(d->src[i], d->Din > 1 && !gwc)) use_tma = false;
+    if (!gwc && i + 1 < d->nsrc && d->src[i].C % plan.CK) use_tma = false;
+  }
+  // window offset of the TMA brick: boxes must start on a multiple of 4 columns
+  const int xo_a = gwc ? 0 : ((4 - ((d->transposed ? 1 : d->pw) & 3)) & 3);  // transposed: W phase 0 has pad 1
+  if (use_tma && !gwc && xo_a != 0 && xo_a != 3) use_tma = false;
+  if (use_tma && !plan.fn_tma[xo_a == 3]) use_tma = false;
+  if (use_tma && d->transposed && !plan.fn_tma[0]) use_tma = false;
+  if (use_tma) {
+    const int taps = g.KD * g.KH * g.KW;
+    if (gwc) {
+      const int nch = plan.CK * k.cpg;
+      for (int i = 0; i < 2 && use_tma; ++i) {
+        const esm_src_t& sv = d->src[i];
+        const long long dims[5] = {d->Win, d->Hin, 1, sv.C, d->B};
+        const long long str[4] = {sv.sH, sv.sH * d->Hin, sv.sC, sv.sB};
+        const int box[5] = {i == 0 ? tl.IWL : tl.IWR, tl.IH, 1, nch, 1};
+        use_tma = sv.sC >= sv.sH * d->Hin && encode_map(&maps.src[i], sv.ptr, 5, dims, str, box);
+      }
+    } else {
+      for (int i = 0; i < d->nsrc && use_tma; ++i) {
+        const esm_src_t& sv = d->src[i];
+        const long long sD = d->Din > 1 ? sv.sD : sv.sH * d->Hin;
+        const long long dims[5] = {d->Win, d->Hin, d->Din, sv.C, d->B};
+        const long long str[4] = {sv.sH, sD, sv.sC, sv.sB};
+        const int box[5] = {tl.IWP, tl.IH, tl.ID, plan.CK, 1};
+        use_tma = encode_map(&maps.src[i], sv.ptr, 5, dims, str, box);
+      }
+    }
+    if (use_tma) {
+      const long long dims[3] = {g.CoutPad, g.CinPad, (long long)taps * g.phases};
+      const long long str[2] = {g.CoutPad, (long long)g.CoutPad * g.CinPad};
+      const int box[3] = {plan.COP, plan.CK, taps};
+      use_tma = encode_map(&maps.w, d->weight, 3, dims, str, box);
+    }
+  }
+  // the limit is per function AND per device: set it on every launch (the plan cache may have been filled on another device)
+  {
+    conv_fn_t fn_used = !use_tma ? plan.fn : (!d->transposed ? plan.fn_tma[xo_a == 3] : nullptr);
+    conv_fn_t fns[2] = {fn_used ? fn_used : plan.fn_tma[1], fn_used ? nullptr : plan.fn_tma[0]};
+    for (int i = 0; i < 2; ++i)
+      if (fns[i] && tl.smem > 48 * 1024 &&
+          cudaFuncSetAttribute((const void*)fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
+        return check_launch("conv(cudaFuncSetAttribute)");
+  }
+  const long long resident = (long long)num_sms * plan.blocks_per_sm;
+  // Optional programmatic stream serialization (PDL, ESM_PDL=1): the kernel's prologue (mbarrier init,
+  // descriptor fetch) may overlap the tail of the previous kernel; it waits on griddepcontrol.wait
+  // before its first global access.  Measured on B200 it LOSES 5% end to end on this graph (206 vs 218
+  // pairs/s): early-launched dependents take SM slots from the persistent CTAs still running, so it is off
+  // by default.
+  static const bool pdl = getenv("ESM_PDL") != nullptr;
+  auto launch = [&](conv_fn_t fn, unsigned grid, const ConvK& kk) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3((unsigned)kk.nthreads);
+    cfg.dynamicSmemBytes = tl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, fn, kk, maps);
+  };
+  if (!use_tma) {
+    launch(plan.fn, (unsigned)(total < resident ? total : resident), k);  // persistent CTAs stride over the tiles
+  } else if (!d->transposed) {
+    launch(plan.fn_tma[xo_a == 3], (unsigned)(total < resident ? total : resident), k);
+  } else {
+    // sub-pixel phases along W have pad 1 (phase 0, window offset 3) and pad 0 (phase 1, offset 0):
+    // one launch per W phase, each enumerating the (d,h) phases
+    k.phases = g.phases / 2;
+    k.total_work = (int)(total / 2);
+    const unsigned grid = (unsigned)(k.total_work < resident ? k.total_work : resident);
+    k.pzw_sel = 0;
+    launch(plan.fn_tma[1], grid, k);
+    k.pzw_sel = 1;
+    launch(plan.fn_tma[0], grid, k);
+  }
+  return check_launch("conv");
+}
+
+}  // namespace esm
+
+using namespace esm;
+
+extern "C" long long esm_packed_weight_elems(int Cout, int Cin, int kd, int kh, int kw, int transposed) {
+  const PackGeom g = pack_geom(Cout, Cin, kd, kh, kw, transposed);
+  return g.per_phase * g.phases + tcg_pack_geom(Cout, Cin, kd, kh, kw, transposed).elems;
+}
+
+extern "C" int esm_pack_conv_weight_f32(const float* w, float* packed, int Cout, int Cin, int kd, int kh, int kw,
+                                        int transposed, void* stream) {
+  ESM_REQUIRE(w && packed && Cout > 0 && Cin > 0, "pack_conv_weight: null pointer or empty shape");
+  if (transposed)
+    ESM_REQUIRE((kd == 4 || kd == 1) && kh == 4 && kw == 4, "pack_conv_weight: transposed conv must be k4 (got %d,%d,%d)",
+                kd, kh, kw);
+  const PackGeom g = pack_geom(Cout, Cin, kd, kh, kw, transposed);
+  const long long total = g.per_phase * g.phases;
+  const int threads = 256;
+  pack_weight_kernel<<<(unsigned)ceil_div_ll(total, threads), threads, 0, (cudaStream_t)stream>>>(
+      w, packed, Cout, Cin, kd, kh, kw, transposed, g.CinPad, g.CoutPad, g.KD, g.KH, g.KW, g.phases, g.phases_d, total);
+  const TcgPack t = tcg_pack_geom(Cout, Cin, kd, kh, kw, transposed);
+  if (t.elems > 0) {
+    const long long n = t.elems / 2;  // one thread per weight writes its hi and lo parts
+    pack_tcg_kernel<<<(unsigned)ceil_div_ll(n, threads), threads, 0, (cudaStream_t)stream>>>(
+        w, packed + t.offset, Cout, Cin, kd, kh, kw, transposed, g.KD, g.KH, g.KW, g.phases_d, t.ncg, t.CoutX, n);
+  }
+  return check_launch("pack_conv_weight");
+}
+
+extern "C" int esm_fold_bn_f32(const float* gamma, const float* beta, const float* mean, const float* var,
+                               const float* bias, float eps, int C, float* scale, float* shift, void* stream) {
+  ESM_REQUIRE(scale && shift && C > 0, "fold_bn: null output");
+  const bool any = gamma || beta || mean || var;
+  ESM_REQUIRE(!any || (gamma && beta && mean && var), "fold_bn: BN tensors must be given together");
+  fold_bn_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, bias, eps, C, scale, shift);
+  return check_launch("fold_bn");
+}
+
+extern "C" int esm_conv_f32(const esm_conv_t* d, void* stream) {
+  ESM_REQUIRE(d, "conv: null descriptor");
+  ESM_REQUIRE(d->out && d->weight, "conv: null out/weight");
+  ESM_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0 && d->Dout > 0 && d->Hout > 0 && d->Wout > 0, "conv: empty shape");
+  ESM_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2");
+  const int S = d->transposed ? 1 : d->stride;
+  if (d->transposed) {
+    ESM_REQUIRE((d->kd == 4 || d->kd == 1) && d->kh == 4 && d->kw == 4 && d->stride == 2 && d->ph == 1 && d->pw == 1 &&
+                    d->pd == (d->kd == 4 ? 1 : 0),
+                "conv: transposed conv supports k4 s2 p1 only");
+    ESM_REQUIRE(d->Dout <= (d->kd == 4 ? 2 : 1) * d->Din && d->Hout <= 2 * d->Hin && d->Wout <= 2 * d->Win,
+                "conv: transposed output larger than 2x input");
+  } else {
+    ESM_REQUIRE(d->Dout == (d->Din + 2 * d->pd - d->kd) / S + 1 && d->Hout == (d->Hin + 2 * d->ph - d->kh) / S + 1 &&
+                    d->Wout == (d->Win + 2 * d->pw - d->kw) / S + 1,
+                "conv: output extent does not match input/kernel/stride/padding");
+  }
+  ESM_REQUIRE(d->pixel_shuffle == 0 || (d->Dout == 1 && !d->transposed && d->Cout % (d->pixel_shuffle * d->pixel_shuffle) == 0),
+              "conv: pixel_shuffle needs a 2D conv with Cout divisible by r*r");
+  ESM_REQUIRE(d->pixel_shuffle == 0 || (!d->residual && !d->out_mul), "conv: pixel_shuffle excludes residual/out_mul");
+
+  const PackGeom g = pack_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, d->transposed);
+  ConvK k;
+  memset(&k, 0, sizeof(k));
+  k.src_mode = d->src_mode;
+  if (d->src_mode == ESM_SRC_GWC) {
+    ESM_REQUIRE(d->nsrc == 2 && d->gwc_groups == d->Cin && d->src[0].C == d->src[1].C && d->src[0].C % d->Cin == 0,
+                "conv: ESM_SRC_GWC needs src[0]=left, src[1]=right with C %% groups == 0");
+    k.cpg = d->src[0].C / d->Cin;
+    ESM_REQUIRE(d->src[0].sC == d->src[1].sC && d->src[0].sH == d->src[1].sH, "conv: gwc sources must share strides");
+  } else {
+    ESM_REQUIRE(d->nsrc >= 1 && d->nsrc <= 3, "conv: nsrc must be 1..3");
+    int csum = 0;
+    for (int i = 0; i < d->nsrc; ++i) csum += d->src[i].C;
+    ESM_REQUIRE(csum == d->Cin, "conv: source channels (%d) != Cin (%d)", csum, d->Cin);
+  }
+  for (int i = 0; i < d->nsrc; ++i) {
+    ESM_REQUIRE(d->src[i].ptr, "conv: null source %d", i);
+    k.src[i] = d->src[i];
+  }
+  k.nsrc = d->nsrc;
+  k.in_mul = d->in_mul;
+  k.imH = d->Win;
+  k.imC = (long long)d->Hin * d->Win;
+  k.imB = k.imC * d->Cin;
+  k.B = d->B;
+  k.Cin = d->Cin;
+  k.Din = d->Din;
+  k.Hin = d->Hin;
+  k.Win = d->Win;
+  k.OD = d->Dout;
+  k.OH = d->Hout;
+  k.OW = d->Wout;
+  k.Cout = d->Cout;
+  k.CinPad = g.CinPad;
+  k.CoutPad = g.CoutPad;
+  k.KD = g.KD;
+  k.KH = g.KH;
+  k.pd = d->pd;
+  k.ph = d->ph;
+  k.pw = d->pw;
+  k.transposed = d->transposed;
+  k.phases_d = g.phases_d;
+  k.weight = d->weight;
+  k.phase_stride = g.per_phase;
+  k.scale = d->scale;
+  k.shift = d->shift;
+  k.act = d->act;
+  k.act2 = d->act2;
+  k.out_mul = d->out_mul;
+  k.omH = d->Wout;
+  k.omC = (long long)d->Hout * d->Wout;
+  k.omB = k.omC * d->Cout;
+  k.residual = d->residual;
+  k.out_scale = d->out_scale;
+  k.ps = d->pixel_shuffle;
+  k.out = d->out;
+  k.oB = d->oB;
+  k.oC = d->oC;
+  k.oD = d->oD;
+  k.oH = d->oH;
+
+  const bool gwc = d->src_mode == ESM_SRC_GWC;
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    static const bool stem3_on = !(getenv("ESM_STEM3") && getenv("ESM_STEM3")[0] == '0');
+    if (stem3_on && !getenv("ESM_TC_FORCE") && stem3_eligible(d)) return stem3_launch(d, st);
+  }
+  LayerGeom lg;
+  lg.S = S;
+  lg.gwc = gwc;
+  lg.Jw = d->transposed ? ceil_div(d->Wout, 2) : d->Wout;
+  lg.Jh = d->transposed ? ceil_div(d->Hout, 2) : d->Hout;
+  lg.Jd = (d->transposed && g.phases_d == 2) ? ceil_div(d->Dout, 2) : d->Dout;
+
+  static std::map<PlanKey, Plan> plans;
+  static std::mutex plans_mu;
+  static int sms_by_dev[64] = {0};
+  // tensor-core policy: ESM_TC=0 off, 3 (default) split-TF32 (fp32-grade), 1 single-pass TF32 (fast mode);
+  // ESM_TC_FORCE=1 takes the tensor-core path whenever the layer is eligible (tests), else it must win the timing
+  const char* tc_env = getenv("ESM_TC");
+  const int tc_pass = d->engine == 1 ? 0 : (tc_env ? atoi(tc_env) : 3);
+  // ESM_TC_FORCE=1 forces the resident-weight engine, =2 the streamed-weight engine, wherever eligible
+  // ... =3 the pointwise streaming kernel (true fp32: allowed for engine == 1 layers too)
+  const int force_env = getenv("ESM_TC_FORCE") ? atoi(getenv("ESM_TC_FORCE")) : 0;
+  const int tc_force = force_env == 3 ? 3 : (force_env != 0 && tc_pass != 0) ? (force_env == 2 ? 2 : 1) : 0;
+  int dev = -1;
+  int num_sms = -1;  // no device: still run the validation / tiling below so shapes can be checked on a CPU box
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    dev = -1;
+  }
+  std::lock_guard<std::mutex> lock(plans_mu);
+  if (dev >= 0 && dev < 64) {
+    if (sms_by_dev[dev] == 0) {
+      int n = 0;
+      if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = -1;
+      }
+      sms_by_dev[dev] = n;
+    }
+    num_sms = sms_by_dev[dev];
+  }
+  // Everything the engines' eligibility and tiling depend on goes into the key (a cached plan is launched without
+  // re-planning): the source split, the fused operands, the alignment classes of the output, the device.  The
+  // tensor-core plans are additionally re-validated on a hit (cheap arithmetic) and fall back to the FP32 pipe.
+  const int align_cls = (int)((reinterpret_cast<uintptr_t>(d->out) & 15) ? 1 : 0) | (d->oH % 4 ? 2 : 0) | (d->oH % 2 ? 4 : 0);
+  int src_align = 0;
+  for (int i = 0; i < d->nsrc; ++i) {
+    const esm_src_t& sv = d->src[i];
+    if ((reinterpret_cast<uintptr_t>(sv.ptr) & 15) || sv.sH % 4 || sv.sC % 4 || sv.sB % 4 || (d->Din > 1 && !gwc && sv.sD % 4)) src_align |= 1 << i;
+  }
+  PlanKey key = {{d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed, lg.Jw, lg.Jh, lg.Jd, gwc ? k.cpg : 0, d->B, d->pd,
+                  d->ph, d->pw, tc_pass * 4 + tc_force + (d->in_mul ? 64 : 0) + (d->pixel_shuffle ? 128 : 0),
+                  d->nsrc, d->nsrc > 0 ? d->src[0].C : 0, d->nsrc > 1 ? d->src[1].C : 0, d->nsrc > 2 ? d->src[2].C : 0,
+                  (d->out_mul ? 1 : 0) | (d->residual ? 2 : 0) | (d->act2 != ESM_ACT_NONE ? 4 : 0), align_cls | (src_align << 3), dev, 0}};
+  auto it = plans.find(key);
+  if (it != plans.end()) {
+    const Plan& hp = it->second;
+    if (hp.use_tc == 3) {
+      PwPlan t;
+      if (pw_conv_plan(d, &t)) return pw_conv_launch(d, hp.pw, st);
+    } else if (hp.use_tc == 2) {
+      TcgPlan t;
+      if (tcg_conv_plan(d, num_sms, hp.tcg.npass, &t)) return tcg_conv_launch(d, hp.tcg, st);
+    } else if (hp.use_tc == 1) {
+      TcPlan t;
+      if (tc_conv_plan(d, num_sms, hp.tc.npass, &t)) return tc_conv_launch(d, hp.tc, st);
+    }
+    return launch_plan(d, g, k, hp, lg, num_sms, st);
+  }
+
+  // ---- plan: enumerate (channel split x chunk depth x tile shape), rank by the analytic model ----
+  const int ck0 = g.CinPad == 1 ? 1 : 8;
+  const int xo_plan = (!gwc && (d->transposed || (d->pw & 3) == 1)) ? 3 : 0;  // room for the XO=3 window
+  std::vector<Candidate> cands;
+  // channel-group width per thread: 8 (4 voxels x 8 channels = 32 accumulators) or 4 (half the serial
+  // FFMA2 chain per thread, twice the warps: wins on the latency-bound small layers)
+  for (int COG = (g.CoutPad == 4 ? 4 : 8); COG >= 4; COG -= 4) {
+    if (COG == 4 && (gwc || ck0 != 8)) break;  // instantiated for 8-channel chunks only
+    for (int cosplit = 1; cosplit <= g.CoutPad / COG; ++cosplit) {
+      // a CTA owns COP <= 64 channels (<= 256 threads); more splits re-stage the same bricks but give
+      // small layers more CTAs
+      if (g.CoutPad % cosplit || (g.CoutPad / cosplit) % COG || g.CoutPad / cosplit > 64) continue;
+      const int COP = g.CoutPad / cosplit;
+      const long long mult = (long long)d->B * g.phases * cosplit;
+      const double extra = 1.0 + 0.03 * (cosplit - 1);
+      for (int ck = ck0; ck >= (ck0 == 8 && COG == 8 ? 4 : ck0); ck /= 2) {
+        // chunk depth 8 or 4: a shallower chunk halves the staged brick (more resident warps on the 8-channel layers)
+        enumerate_tilings(lg.Jw, lg.Jh, lg.Jd, d->Cin, COG, 4, g.KW, g.KH, g.KD, S, ck, COP, cosplit, gwc, k.cpg, xo_plan, mult,
+                          num_sms, extra, &cands);
+        // one voxel per thread: only worth trying on small layers (and only instantiated for CK=8, k != 5)
+        if (ck == 8 && !gwc && g.KW != 5 && (long long)lg.Jw * lg.Jh * lg.Jd * d->B <= 80000)
+          enumerate_tilings(lg.Jw, lg.Jh, lg.Jd, d->Cin, COG, 1, g.KW, g.KH, g.KD, S, ck, COP, cosplit, gwc, k.cpg, xo_plan, mult,
+                            num_sms, extra, &cands);
+        if (ck == 1) break;
+      }
+    }
+  }
+  ESM_REQUIRE(!cands.empty(), "conv: no tiling for Cin=%d Cout=%d k=(%d,%d,%d)%s", d->Cin, d->Cout, d->kd, d->kh, d->kw,
+              gwc ? " +gwc" : "");
+  std::sort(cands.begin(), cands.end(), [](const Candidate& a, const Candidate& b) { return a.cost < b.cost; });
+
+  auto make_plan = [&](const Candidate& c, Plan* np) -> int {
+    np->tl = c.tl;
+    np->CK = c.CK;
+    np->COP = c.COP;
+    np->cosplit = c.cosplit;
+    const int COG = c.COG;
+    np->COG = COG;
+    np->fn = pick_kernel(g.KW, S, COG, c.CK, gwc, false, 0, c.tl.NV);
+    np->fn_tma[0] = pick_kernel(g.KW, S, COG, c.CK, gwc, true, 0, c.tl.NV);
+    np->fn_tma[1] = pick_kernel(g.KW, S, COG, c.CK, gwc, true, 3, c.tl.NV);
+    ESM_REQUIRE(np->fn, "conv: unsupported kernel width %d / stride %d%s", g.KW, S, gwc ? " with ESM_SRC_GWC" : "");
+    np->blocks_per_sm = 1;
+    if (num_sms > 0) {
+      conv_fn_t fns[3] = {np->fn, np->fn_tma[0], np->fn_tma[1]};
+      for (int i = 0; i < 3; ++i) {
+        if (!fns[i]) continue;
+        if (cudaFuncSetAttribute((const void*)fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess)
+          return check_launch("conv(cudaFuncSetAttribute)");
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fns[i], c.tl.slots * (c.COP / COG), c.tl.smem) !=
+            cudaSuccess)
+          return check_launch("conv(occupancy)");
+        if (i == 0 || occ < np->blocks_per_sm) np->blocks_per_sm = occ > 0 ? occ : 1;
+      }
+    }
+    return ESM_OK;
+  };
+
+  Plan best_plan;
+  best_plan.use_tc = false;
+  if (int e = make_plan(cands[0], &best_plan)) return e;
+  if (num_sms <= 0) {
+    set_error("conv: no CUDA device");
+    return ESM_ERR_CUDA;
+  }
+  // ---- pinned plan (esm_conv_plans_import): same engine and tiling as when it was tuned, no timing, no sync ----
+  // The key is device independent (ordinal zeroed); ESM_AUTOTUNE=1 ignores pinned plans and re-times.
+  {
+    const char* env_t = getenv("ESM_AUTOTUNE");
+    PlanKey pk = key;
+    pk.v[22] = 0;
+    std::lock_guard<std::mutex> plock(g_pinned_mu);
+    auto pit = g_pinned.find(pk);
+    if (pit != g_pinned.end() && !(env_t && env_t[0] == '1') && tc_force == 0) {
+      const PinnedPlan& pp = pit->second;
+      bool found = false;
+      for (const Candidate& c : cands) {
+        if (c.CK == pp.CK && c.COP == pp.COP && c.COG == pp.COG && c.cosplit == pp.cosplit && c.tl.NV == pp.NV && c.tl.TWG == pp.TWG &&
+            c.tl.TH == pp.TH && c.tl.TD == pp.TD && c.tl.slots == pp.slots && c.tl.nstages == pp.nstages) {
+          if (make_plan(c, &best_plan) == ESM_OK) found = true;
+          break;
+        }
+      }
+      if (found || pp.use_tc != 0) {
+        const int np = tc_pass == 1 ? 1 : 3;
+        best_plan.use_tc = 0;
+        if (pp.use_tc == 1 && tc_pass != 0 && tc_conv_plan(d, num_sms, np, &best_plan.tc)) best_plan.use_tc = 1;
+        if (pp.use_tc == 2 && tc_pass != 0 && tcg_conv_plan(d, num_sms, np, &best_plan.tcg)) best_plan.use_tc = 2;
+        if (pp.use_tc == 3 && pw_conv_plan(d, &best_plan.pw)) best_plan.use_tc = 3;
+        if (best_plan.use_tc == pp.use_tc && (found || pp.use_tc != 0)) {
+          plans.emplace(key, best_plan);
+          return best_plan.use_tc == 3   ? pw_conv_launch(d, best_plan.pw, st)
+                 : best_plan.use_tc == 2 ? tcg_conv_launch(d, best_plan.tcg, st)
+                 : best_plan.use_tc == 1 ? tc_conv_launch(d, best_plan.tc, st)
+                                         : launch_plan(d, g, k, best_plan, lg, num_sms, st);
+        }
+      }
+    }
+  }
+
+  // ---- autotune: time the best-ranked candidates on the device (first call per shape, never during
+  // graph capture); "measure, don't guess" -- the model above mis-ranks latency-bound layers ----
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  const char* env = getenv("ESM_AUTOTUNE");
+  const bool tune = cap == cudaStreamCaptureStatusNone && !(env && env[0] == '0');
+  if (tune) ++g_tuned_calls;
+  float best_ms = 1e30f;
+  if (tune && cands.size() > 1) {
+    // shortlist: the 6 best by model + the best of every (voxels/thread, channel-group width, CTA size
+    // class) combination, so that structurally different plans always get a device timing
+    std::vector<Candidate> shortlist(cands.begin(), cands.begin() + std::min<size_t>(6, cands.size()));
+    auto same = [](const Candidate& a, const Candidate& b) {
+      return a.tl.slots == b.tl.slots && a.tl.TWG == b.tl.TWG && a.tl.TD == b.tl.TD && a.CK == b.CK && a.COP == b.COP &&
+             a.tl.nstages == b.tl.nstages && a.COG == b.COG && a.tl.NV == b.tl.NV;
+    };
+    for (int nv = 1; nv <= 4; nv += 3)
+      for (int cog = 4; cog <= 8; cog += 4)
+        for (int cls = 0; cls < 3; ++cls) {
+          const int lo = cls == 0 ? 0 : cls == 1 ? 64 : 128, hi = cls == 0 ? 64 : cls == 1 ? 128 : 256;
+          for (const Candidate& c : cands) {
+            const int nt = c.tl.slots * (c.COP / c.COG);
+            if (c.tl.NV != nv || c.COG != cog || nt <= lo || nt > hi) continue;
+            bool dup = false;
+            for (const Candidate& s2 : shortlist) dup = dup || same(s2, c);
+            if (!dup) shortlist.push_back(c);
+            break;
+          }
+        }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (const Candidate& c : shortlist) {
+      Plan cp;
+      cp.use_tc = false;
+      if (make_plan(c, &cp) != ESM_OK) continue;
+      if (launch_plan(d, g, k, cp, lg, num_sms, st) != ESM_OK) continue;  // warm (also sets attributes)
+      float ms = 1e30f;
+      for (int rep = 0; rep < 2; ++rep) {  // best of two timings of 3 back-to-back launches
+        cudaEventRecord(e0, st);
+        for (int l = 0; l < 3; ++l) launch_plan(d, g, k, cp, lg, num_sms, st);
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) {
+          cudaEventDestroy(e0);
+          cudaEventDestroy(e1);
+          return check_launch("conv(autotune)");
+        }
+        float m3 = 0.f;
+        cudaEventElapsedTime(&m3, e0, e1);
+        if (m3 / 3.f < ms) ms = m3 / 3.f;
+      }
+      if (getenv("ESM_DEBUG_PLAN"))
+        fprintf(stderr, "[esm tune] Cin=%d Cout=%d k=%d J=(%d,%d,%d): CK=%d COP=%d COG=%d NV=%d tile=(%d,%d,%d) thr=%d ns=%d smem=%zuKB -> %.1f us\n",
+                d->Cin, d->Cout, d->kw, lg.Jd, lg.Jh, lg.Jw, c.CK, c.COP, c.COG, c.tl.NV, c.tl.TD, c.tl.TH, c.tl.TWG * c.tl.NV, c.tl.slots * (c.COP / c.COG),
+                c.tl.nstages, c.tl.smem / 1024, ms * 1000.f);
+      if (ms < best_ms) {
+        best_ms = ms;
+        best_plan = cp;
+      }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  // ---- tensor-core candidates (conv_tc.cu: resident weights, taps in N; conv_tcg.cu: streamed weights, taps in K):
+  // taken when forced, or when they beat the best FP32-pipe plan in the on-device timing ----
+  TcPlan tcp;
+  TcgPlan tgp;
+  PwPlan pwp;
+  const bool tc_ok = tc_pass != 0 && (tc_force == 0 || tc_force == 1) && tc_conv_plan(d, num_sms, tc_pass == 1 ? 1 : 3, &tcp);
+  const bool tg_ok = tc_pass != 0 && (tc_force == 0 || tc_force == 2) && getenv("ESM_TCG_OFF") == nullptr &&
+                     tcg_conv_plan(d, num_sms, tc_pass == 1 ? 1 : 3, &tgp);
+  const bool pw_ok = (tc_force == 0 || tc_force == 3) && getenv("ESM_PW_OFF") == nullptr && num_sms > 0 && pw_conv_plan(d, &pwp);
+  best_plan.use_tc = 0;
+  if (tc_force == 1 && tc_ok) {
+    best_plan.use_tc = 1;
+  } else if (tc_force == 2 && tg_ok) {
+    best_plan.use_tc = 2;
+  } else if (tc_force == 3 && pw_ok) {
+    best_plan.use_tc = 3;
+  } else if (!tc_force && tune && (tc_ok || tg_ok || pw_ok)) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    auto time3 = [&](int engine) -> float {
+      float ms = 1e30f;
+      for (int rep = 0; rep < 3; ++rep) {  // rep 0 warms
+        cudaEventRecord(e0, st);
+        for (int l = 0; l < 3; ++l) {
+          if (engine == 3)
+            pw_conv_launch(d, pwp, st);
+          else if (engine == 2)
+            tcg_conv_launch(d, tgp, st);
+          else if (engine == 1)
+            tc_conv_launch(d, tcp, st);
+          else
+            launch_plan(d, g, k, best_plan, lg, num_sms, st);
+        }
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) return -1.f;
+        float m3 = 0.f;
+        cudaEventElapsedTime(&m3, e0, e1);
+        if (rep > 0 && m3 / 3.f < ms) ms = m3 / 3.f;
+      }
+      return ms;
+    };
+    if (best_ms >= 1e29f) best_ms = time3(0);
+    const float tc_ms = tc_ok ? time3(1) : 1e30f;
+    const float tg_ms = tg_ok ? time3(2) : 1e30f;
+    const float pw_ms = pw_ok ? time3(3) : 1e30f;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (best_ms < 0.f || tc_ms < 0.f || tg_ms < 0.f || pw_ms < 0.f) return check_launch("conv(autotune tc)");
+    if (tc_ms < best_ms && tc_ms <= tg_ms) best_plan.use_tc = 1;
+    if (tg_ms < best_ms && tg_ms < tc_ms) best_plan.use_tc = 2;
+    if (pw_ms < best_ms && pw_ms < tc_ms && pw_ms < tg_ms) best_plan.use_tc = 3;
+    if (getenv("ESM_DEBUG_PLAN"))
+      fprintf(stderr, "[esm tune] Cin=%d Cout=%d k=(%d,%d,%d) s=%d%s J=(%d,%d,%d)%s: fp32 %.1f us | tcgen05 resident %.1f us (COT=%d TZ=%d) | "
+              "streamed %.1f us (NT=%d x%d, %d ctas, %d stages) | pointwise %.1f us -> engine %d\n",
+              d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed ? " T" : "", lg.Jd, lg.Jh, lg.Jw, gwc ? " gwc" : "", best_ms * 1000.f,
+              tc_ok ? tc_ms * 1000.f : -1.f, tc_ok ? tcp.COT : 0, tc_ok ? tcp.TZ : 0, tg_ok ? tg_ms * 1000.f : -1.f, tg_ok ? tgp.NT : 0,
+              tg_ok ? tgp.ncot : 0, tg_ok ? tgp.ctas : 0, tg_ok ? tgp.nstages : 0, pw_ok ? pw_ms * 1000.f : -1.f, best_plan.use_tc);
+  }
+  if (best_plan.use_tc == 1) best_plan.tc = tcp;
+  if (best_plan.use_tc == 2) best_plan.tcg = tgp;
+  if (best_plan.use_tc == 3) best_plan.pw = pwp;
+  if (getenv("ESM_DEBUG_PLAN"))
+    fprintf(stderr, "[esm plan] Cin=%d Cout=%d k=(%d,%d,%d) s=%d%s%s J=(%d,%d,%d): CK=%d COP=%d cosplit=%d tile=(%d,%d,%d) threads=%d "
+            "smem=%zu KB occ=%d tuned=%d\n",
+            d->Cin, d->Cout, d->kd, d->kh, d->kw, d->stride, d->transposed ? " T" : "", gwc ? " gwc" : "", lg.Jd, lg.Jh, lg.Jw,
+            best_plan.CK, best_plan.COP, best_plan.cosplit, best_plan.tl.TD, best_plan.tl.TH, best_plan.tl.TWG * best_plan.tl.NV,
+            best_plan.tl.slots * (best_plan.COP / best_plan.COG), best_plan.tl.smem / 1024, best_plan.blocks_per_sm, (int)tune);
+  plans.emplace(key, best_plan);
+  if (tune && tc_force == 0) {  // remember what the timing chose, for esm_conv_plans_export
+    PlanKey pk = key;
+    pk.v[22] = 0;
+    PinnedPlan pp = {best_plan.use_tc, best_plan.CK, best_plan.COP, best_plan.COG, best_plan.cosplit, best_plan.tl.NV, best_plan.tl.TWG,
+                     best_plan.tl.TH, best_plan.tl.TD, best_plan.tl.slots, best_plan.tl.nstages};
+    std::lock_guard<std::mutex> plock(g_pinned_mu);
+    g_pinned[pk] = pp;
+  }
+  return best_plan.use_tc == 3   ? pw_conv_launch(d, best_plan.pw, st)
+         : best_plan.use_tc == 2 ? tcg_conv_launch(d, best_plan.tcg, st)
+         : best_plan.use_tc == 1 ? tc_conv_launch(d, best_plan.tc, st)
+                                 : launch_plan(d, g, k, best_plan, lg, num_sms, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// plan persistence: one text line per layer shape, "k0 k1 ... k23 : use_tc CK COP COG cosplit NV TWG TH TD slots nstages"
+// ------------------------------------------------------------------------------------------
+extern "C" long long esm_conv_plans_export(char* buf, long long cap) {
+  std::lock_guard<std::mutex> plock(g_pinned_mu);
+  std::string out;
+  char line[512];
+  for (const auto& kv : g_pinned) {
+    int n = 0;
+    for (int i = 0; i < 24; ++i) n += snprintf(line + n, sizeof(line) - n, "%d ", kv.first.v[i]);
+    const PinnedPlan& p = kv.second;
+    snprintf(line + n, sizeof(line) - n, ": %d %d %d %d %d %d %d %d %d %d %d\n", p.use_tc, p.CK, p.COP, p.COG, p.cosplit, p.NV, p.TWG, p.TH, p.TD,
+             p.slots, p.nstages);
+    out += line;
+  }
+  if (buf && cap > 0) {
+    const size_t n = out.size() < (size_t)(cap - 1) ? out.size() : (size_t)(cap - 1);
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (long long)out.size() + 1;
+}
+
+extern "C" int esm_conv_plans_import(const char* text) {
+  ESM_REQUIRE(text, "conv_plans_import: null text");
+  std::lock_guard<std::mutex> plock(g_pinned_mu);
+  int count = 0;
+  const char* p = text;
+  while (*p) {
+    const char* eol = strchr(p, '\n');
+    std::string ln(p, eol ? (size_t)(eol - p) : strlen(p));
+    p = eol ? eol + 1 : p + ln.size();
+    if (ln.empty() || ln[0] == '#') continue;
+    PlanKey k;
+    PinnedPlan pp;
+    int off = 0, n = 0;
+    bool ok = true;
+    for (int i = 0; i < 24 && ok; ++i) {
+      ok = sscanf(ln.c_str() + off, "%d%n", &k.v[i], &n) == 1;
+      off += n;
+    }
+    if (!ok) continue;
+    if (sscanf(ln.c_str() + off, " : %d %d %d %d %d %d %d %d %d %d %d", &pp.use_tc, &pp.CK, &pp.COP, &pp.COG, &pp.cosplit, &pp.NV, &pp.TWG, &pp.TH,
+               &pp.TD, &pp.slots, &pp.nstages) != 11)
+      continue;
+    k.v[22] = 0;
+    g_pinned[k] = pp;
+    ++count;
+  }
+  return count;
+}
+
+extern "C" long long esm_conv_tuned_calls(void) { return g_tuned_calls; }

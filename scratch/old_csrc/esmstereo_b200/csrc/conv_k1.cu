@@ -1,0 +1,12 @@
+// Instantiations of the direct-convolution kernel for kernel width 1, stride 1 (see conv_kernel.cuh).
+#include "conv_kernel.cuh"
+
+namespace esm {
+conv_fn_t conv_kernels_k1(int COG, int CK, bool gwc, bool tma, int xo, int nv) {
+  if (gwc) return nullptr;
+  if (!tma) return pick_cog_ck<1, 1, false, 0>(COG, CK, nv);
+  if (xo == 0) return pick_cog_ck<1, 1, true, 0>(COG, CK, nv);
+  if (xo == 3) return pick_cog_ck<1, 1, true, 3>(COG, CK, nv);
+  return nullptr;
+}
+}  // namespace esm

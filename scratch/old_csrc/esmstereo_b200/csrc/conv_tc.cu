@@ -40,8 +40,6 @@ struct TcK {
   int B, Cin, ncg, D, H, W;
   int Cout, CinPad, CoutPad;
   const float* weight;  // fp32 pack of esm_pack_conv_weight_f32: [tap][CinPad][CoutPad]
-  const float* wimg;    // tck_conv_kernel: the split weight image of the pack (TcImg)
-  int tail_help;        // tck_conv_kernel: the producer warps help with the epilogue of the CTA's last rows
   const float* scale;
   const float* shift;
   int act, act2;
@@ -57,11 +55,11 @@ struct TcK {
 };
 
 constexpr int TC_NTW = 8;                               // operand-producer warps
-// Epilogue warps NEW (template): 8 = two per TMEM lane quadrant, half the channel tile each -- 608 threads with the
-// three MMA warps (one per output plane z_o, TZ of them active; ptxas sizes for 640: 96 registers); 16 = four per
-// quadrant, a quarter of the tile each, one MMA warp (TZ = 1 only): 800 threads at 80 registers.
-__host__ __device__ constexpr int tc_nmw(int NEW) { return NEW == 8 ? 3 : 1; }
-__host__ __device__ constexpr int tc_threads(int NEW) { return 32 * (NEW + tc_nmw(NEW) + TC_NTW); }
+constexpr int TC_NEW = 8;                               // epilogue warps: 2 per TMEM lane quadrant
+constexpr int TC_MMA_WARP = TC_NEW;                     // first MMA-issuing warp
+constexpr int TC_NMW = 3;                               // MMA warps reserved: one per output plane z_o (TZ of them are active)
+constexpr int TC_PROD_WARP = TC_NEW + TC_NMW;           // first producer warp
+constexpr int TC_THREADS = 32 * (TC_NEW + TC_NMW + TC_NTW);  // 608: epilogue + MMA + producers (ptxas sizes for 640: 96 regs)
 
 
 struct TcItem {
@@ -78,11 +76,8 @@ __device__ __forceinline__ TcItem tc_decode(const TcK& p, int item, int TZ) {
 
 // TAPS = 9: k3 s1 p1 in (h, w) as described above.  TAPS = 1: pointwise (k1) convolution -- the same
 // pipeline without halos, shuffles or the rolling window (N = COT, 32 output columns per strip).
-template <int COT, int TZ, int KD, bool GWC, int TAPS = 9, int NEW = 8>
-__global__ void __launch_bounds__(tc_threads(NEW), 1) tc_conv_kernel(const __grid_constant__ TcK p) {
-  constexpr int TC_NEW = NEW, TC_NMW = tc_nmw(NEW), TC_MMA_WARP = TC_NEW, TC_PROD_WARP = TC_NEW + TC_NMW;
-  static_assert(TZ <= TC_NMW, "one MMA warp per output plane");
-  static_assert(COT % (NEW / 4 * 4) == 0, "whole 4-channel units per epilogue warp");
+template <int COT, int TZ, int KD, bool GWC, int TAPS = 9>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcK p) {
   constexpr int NB = TAPS * COT;               // accumulator columns per (z_o, y_in) row tile
   constexpr int HALO = TAPS == 9 ? 1 : 0;
   constexpr int NROW = TZ + KD - 1;            // input planes per stage
@@ -92,7 +87,7 @@ __global__ void __launch_bounds__(tc_threads(NEW), 1) tc_conv_kernel(const __gri
   constexpr int STAGE_BYTES = TPW * ROW_BYTES;
   constexpr int WSLAB = NB * 32;               // one (cg, kd, hi|lo) B operand: [2][NB][4] floats
   constexpr int ACC_COLS = 256;                // TMEM columns per accumulator buffer (TZ*NB <= 256)
-  constexpr int CW = COT / (NEW / 4);          // output channels per epilogue warp
+  constexpr int CW = COT / 2;                  // output channels per epilogue warp
   static_assert(TZ * NB <= ACC_COLS, "accumulator does not fit");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -108,8 +103,7 @@ __global__ void __launch_bounds__(tc_threads(NEW), 1) tc_conv_kernel(const __gri
   uint64_t* empty = full + NS;
   uint64_t* accf = empty + NS;
   uint64_t* acce = accf + 2;
-  uint64_t* wready = acce + 2;  // the resident weights are staged (one arrival per staging warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wready + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acce + 2);
   float* s_aff = reinterpret_cast<float*>(tmem_slot + 2);  // [2][COT] scale, shift of this channel tile
   const int cot = blockIdx.x / p.ctas_per_cot;
   const int cta = blockIdx.x % p.ctas_per_cot;
@@ -124,7 +118,6 @@ __global__ void __launch_bounds__(tc_threads(NEW), 1) tc_conv_kernel(const __gri
       tc_mbar_init(&accf[i], TZ);
       tc_mbar_init(&acce[i], TC_NEW);
     }
-    tc_mbar_init(wready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -136,63 +129,46 @@ __global__ void __launch_bounds__(tc_threads(NEW), 1) tc_conv_kernel(const __gri
     const float* src = tid < COT ? p.scale : p.shift;
     s_aff[tid] = (src && co < p.Cout) ? __ldg(src + co) : (tid < COT ? 1.f : 0.f);
   }
-  // Resident weights.  With an image in the pack (conv_tc.cuh TcImg) the channel tile is one bulk copy per (8-channel
-  // group, kd) slab pair, issued below and awaited by the MMA issuers on `wready` while the producers already load.
-  // Without one (the gwc stem: the group mean's 0.5 is folded into its weights) every thread stages its share here.
-  if (!p.wimg) {
-    // resident weights of this channel tile: split and laid out as UMMA B operands
-    // (row n = co*TAPS + kh*3+kw: the 9 taps of a channel are adjacent accumulator columns; K = 8 channels of group cg)
-    {
-      const int total = ncg * KD * NB * 8;
-      constexpr int U = 4;
-      for (int base = tid; base < total; base += U * (int)blockDim.x) {
-        float w[U];
-        uint32_t off[U];
+  // resident weights of this channel tile: split and laid out as UMMA B operands
+  // (row n = co*TAPS + kh*3+kw: the 9 taps of a channel are adjacent accumulator columns; K = 8 channels of group cg)
+  {
+    const int total = ncg * KD * NB * 8;
+    constexpr int U = 4;
+    for (int base = tid; base < total; base += U * TC_THREADS) {
+      float w[U];
+      uint32_t off[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int idx = base + u * (int)blockDim.x;
-          const int col = idx % COT;
-          int t = idx / COT;
-          const int k = t & 7;
-          t >>= 3;
-          const int tap2 = t % TAPS;
-          t /= TAPS;
-          const int kd = t % KD;
-          const int cg = t / KD;
-          const int co = cot * COT + col, ci = cg * 8 + k;
-          w[u] = 0.f;
-          if (idx < total && co < p.CoutPad && ci < p.CinPad)
-            w[u] = (GWC ? 0.5f : 1.0f) * __ldg(p.weight + ((long long)(kd * TAPS + tap2) * p.CinPad + ci) * p.CoutPad + co);
-          off[u] = (uint32_t)((cg * KD + kd) * 2) * WSLAB + (uint32_t)(k >> 2) * (NB * 16) + (uint32_t)(col * TAPS + tap2) * 16 + (k & 3) * 4;
-        }
+      for (int u = 0; u < U; ++u) {
+        const int idx = base + u * TC_THREADS;
+        const int col = idx % COT;
+        int t = idx / COT;
+        const int k = t & 7;
+        t >>= 3;
+        const int tap2 = t % TAPS;
+        t /= TAPS;
+        const int kd = t % KD;
+        const int cg = t / KD;
+        const int co = cot * COT + col, ci = cg * 8 + k;
+        w[u] = 0.f;
+        if (idx < total && co < p.CoutPad && ci < p.CinPad)
+          w[u] = (GWC ? 0.5f : 1.0f) * __ldg(p.weight + ((long long)(kd * TAPS + tap2) * p.CinPad + ci) * p.CoutPad + co);
+        off[u] = (uint32_t)((cg * KD + kd) * 2) * WSLAB + (uint32_t)(k >> 2) * (NB * 16) + (uint32_t)(col * TAPS + tap2) * 16 + (k & 3) * 4;
+      }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (base + u * (int)blockDim.x < total) {
-            const float hi = tc_rna(w[u]);
-            *reinterpret_cast<float*>(s_w + off[u]) = hi;
-            *reinterpret_cast<float*>(s_w + off[u] + WSLAB) = tc_lo(w[u], hi);
-          }
+      for (int u = 0; u < U; ++u) {
+        if (base + u * TC_THREADS < total) {
+          const float hi = tc_rna(w[u]);
+          *reinterpret_cast<float*>(s_w + off[u]) = hi;
+          *reinterpret_cast<float*>(s_w + off[u] + WSLAB) = tc_lo(w[u], hi);
         }
       }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
   }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-  if (p.wimg) {
-    if (tid == TC_MMA_WARP * 32) {
-      tc_mbar_expect_tx(wready, wbytes);
-      const float* img = p.wimg + (long long)cot * (wbytes / 4);
-      for (int sl = 0; sl < ncg * KD; ++sl) tc_bulk_g2s(s_w + (size_t)sl * (2 * WSLAB), img + (long long)sl * (2 * WSLAB / 4), 2 * WSLAB, wready);
-    }
-  } else if (tid == TC_MMA_WARP * 32) {
-    tc_mbar_arrive(wready);  // staged before the barrier above
-  }
-#ifdef TC_PROFILE
-  const long long tc_t1 = clock64();
-#endif
 
   if (warp >= TC_PROD_WARP) {
     // ============================ operand producers ============================
@@ -339,8 +315,6 @@ __global__ void __launch_bounds__(tc_threads(NEW), 1) tc_conv_kernel(const __gri
       const uint64_t a0 = tc_desc(tc_smem_u32(s_stage) + zo * ROW_BYTES, 2048, 128), b0 = tc_desc(tc_smem_u32(s_w), NB * 16, 128);
       const bool three = p.npass == 3;
       uint32_t st = 0, ph = 0, ai = 0;
-      tc_mbar_wait(wready, 0, 700);  // the staged weights (generic-proxy stores, fenced by their writers)
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot) {
         for (int step = 0; step < nsteps; ++step) {
           const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
@@ -386,7 +360,7 @@ __global__ void __launch_bounds__(tc_threads(NEW), 1) tc_conv_kernel(const __gri
     }
   } else {
     // ============================ epilogue ============================
-    // warps w, w+4, ... share TMEM lane quadrant q = w % 4 (one strip) and own CW = COT / (NEW/4) channels each.  A
+    // warp w and w+4 share TMEM lane quadrant q = w % 4 (one strip) and own CW = COT/2 channels each.  A
     // (z_o, 4 channels) unit goes TMEM -> 9-tap gather -> BN/activation -> global before the next one is read, so
     // only the rolling window stays live in registers; addresses are 32-bit offsets from one pointer per item.
     const int q = warp & 3;
@@ -512,366 +486,8 @@ __global__ void __launch_bounds__(tc_threads(NEW), 1) tc_conv_kernel(const __gri
   }
 #ifdef TC_PROFILE
   if (blockIdx.x == 0 && lane == 0) {
-    if (warp == 0) printf("tc_prof prologue %lld clk, grid %d\n", tc_t1 - tc_t0, gridDim.x);
     printf("tc_prof warp %2d: done at %8lld clk; waits: empty %8llu  acce %8llu  full %8llu  accf %8llu\n", warp, clock64() - tc_t0,
            tc_prof_wait[warp][2], tc_prof_wait[warp][4], tc_prof_wait[warp][5], tc_prof_wait[warp][6]);
-    for (int i = 0; i < 8; ++i) tc_prof_wait[warp][i] = 0;
-  }
-#endif
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// kh in K, kw in N (2D k3 s1 p1, COT = 32 output channels per CTA).  The taps-in-N kernel above reads 9 accumulator
-// columns per output from tensor memory (64 B/clk/SM: 2.3 k clk per 128 x 32 outputs against 0.9 k clk of MMAs), cannot
-// hold more than 24 channels per CTA (9 * COT <= 256 columns), so a 32-channel layer runs as two channel tiles whose CTAs
-// both load and split the same activations, and its epilogue carries the kh gather in a rolling register window.  Here
-//     acc[y_out][x_in, (co, kw)] = sum_{kh, ci} X[y_out + kh - 1, x_in, ci] * W[kh, kw, ci, co]
-// an input row tile (the same ring stage as above) is multiplied by the three kh weight slabs into the accumulators
-// of the three output rows it touches (N = 3 * COT = 96), a ring of four accumulators in tensor memory; the epilogue
-// reads 3 columns per output and only the kw gather (two warp shuffles) is left.  Same producers, same split-TF32
-// arithmetic; an accumulator chains 9 * ncg MMAs (the epilogue's expected-value correction uses that count).
-template <int COT>
-__global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid_constant__ TcK p) {
-  constexpr int TC_NEW = 8, TC_MMA_WARP = TC_NEW, TC_PROD_WARP = TC_NEW + tc_nmw(8);
-  constexpr int N3 = 3 * COT;                  // accumulator columns per output row: (co, kw)
-  constexpr int SLOT = 128, NSLOT = 4;         // accumulator ring in tensor memory
-  constexpr int CGS = 4, TPW = CGS;            // 8-channel groups (= row tiles) per stage
-  constexpr int ROW_BYTES = 8192;              // row tile: hi [2][128][4] floats, then lo
-  constexpr int STAGE_BYTES = TPW * ROW_BYTES;
-  constexpr int WSLAB = N3 * 32;               // one (cg, kh, hi|lo) B operand: [2][N3][4] floats
-  constexpr int CW = COT / 2;                  // output channels per epilogue warp
-  static_assert(N3 <= SLOT && N3 % 8 == 0 && CW % 8 == 0, "accumulator slot");
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-#ifdef TC_PROFILE
-  const long long tc_t0 = clock64();
-#endif
-  const int ncg = p.ncg;
-  const int NS = p.nstages;
-  const uint32_t wbytes = (uint32_t)ncg * 3 * 2 * WSLAB;
-  uint8_t* s_w = smem;
-  uint8_t* s_stage = smem + ((wbytes + 127u) & ~127u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_stage + (size_t)NS * STAGE_BYTES);
-  uint64_t* empty = full + NS;
-  uint64_t* accf = empty + NS;
-  uint64_t* acce = accf + NSLOT;
-  uint64_t* wready = acce + NSLOT;
-  uint64_t* accl = wready + 1;  // once-only "accumulator full" of the CTA's last rows (helper warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accl + NSLOT);
-  float* s_aff = reinterpret_cast<float*>(tmem_slot + 2);  // [2][COT] scale, shift of this channel tile
-  const int cot = blockIdx.x / p.ctas_per_cot;
-  const int cta = blockIdx.x % p.ctas_per_cot;
-  const int rows = p.rows, nsteps = rows + 2;
-  const bool HELP = p.tail_help != 0;  // producer warps take half of the last rows' epilogue
-
-  if (tid == 0) {
-    for (int i = 0; i < NS; ++i) {
-      tc_mbar_init(&full[i], TC_NTW);
-      tc_mbar_init(&empty[i], 1);
-    }
-    for (int i = 0; i < NSLOT; ++i) {
-      tc_mbar_init(&accf[i], 1);
-      tc_mbar_init(&acce[i], TC_NEW);
-      tc_mbar_init(&accl[i], 1);
-    }
-    tc_mbar_init(wready, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid < 2 * COT) {
-    const int c = tid % COT, co = cot * COT + c;
-    const float* src = tid < COT ? p.scale : p.shift;
-    s_aff[tid] = (src && co < p.Cout) ? __ldg(src + co) : (tid < COT ? 1.f : 0.f);
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem = *tmem_slot;
-  // resident weights: the pack holds this channel tile's image (split, UMMA layout: conv_tc.cuh TcImg), one bulk copy
-  // per 8-channel group, all completing on `wready`; the MMA issuer waits for it before its first MMA
-  if (tid == TC_MMA_WARP * 32) {
-    tc_mbar_expect_tx(wready, wbytes);
-    const float* img = p.wimg + (long long)cot * ncg * (3 * 2 * WSLAB / 4);
-    for (int cg = 0; cg < ncg; ++cg) tc_bulk_g2s(s_w + (size_t)cg * (3 * 2 * WSLAB), img + (long long)cg * (3 * 2 * WSLAB / 4), 3 * 2 * WSLAB, wready);
-  }
-
-  // ---- epilogue of one output row of an item for TMEM lane quadrant q: channels [ch0 + cb, ch0 + ce) of the tile, one
-  // 8-channel group (24 accumulator columns) per TMEM round trip: kw gather by two warp shuffles, BN / activation, stores.
-  // `once`: wait on the once-only barrier of one of the CTA's last four rows (the helper warps below may be several
-  // phases ahead of accf, and a parity can only name the current phase or the one before it).
-  const int oC = (int)p.oC, oH = (int)p.oH;
-  const bool post = p.out_mul || p.residual || p.act2 != ESM_ACT_NONE;
-  const bool gelu = p.act == ESM_ACT_GELU;
-  const float oscale = p.out_scale;
-  const float debias = 1.0f + TC_TRUNC_BIAS * (float)(ncg * 3 * (p.npass == 3 ? 3 : 1));
-  const int n_my = cta < p.items_per_cot ? (p.items_per_cot - cta + p.ctas_per_cot - 1) / p.ctas_per_cot : 0;  // items of this CTA
-  const int tail_rows = rows < NSLOT ? rows : NSLOT;  // rows of the last item whose slots are never reused
-  auto epi_row = [&](int item, int r, uint32_t rc, int q, int ch0, int cb, int ce, bool once, bool hand_back) {
-    const TcItem ti = tc_decode(p, item, 1);
-    const int strip = ti.grp * 4 + q;
-    const int seg = strip % p.nseg, ys = strip / p.nseg;
-    const int x = seg * p.segw + lane - 1;
-    const int ya = ys * rows;
-    const int yb = min(ya + rows, p.H);
-    const bool lane_ok = strip < p.nstrips && lane >= 1 && lane < p.segw + 1 && x < p.W;
-    const int nvalid = p.Cout - (cot * COT + ch0);
-    float* op = p.out + ((long long)ti.b * p.oB + (long long)(cot * COT + ch0) * p.oC + x);
-    const float* rp = p.residual ? p.residual + ((long long)ti.b * p.oB + (long long)(cot * COT + ch0) * p.oC + x) : nullptr;
-    const float* mp = p.out_mul ? p.out_mul + ((long long)ti.b * p.omB + (long long)(cot * COT + ch0) * p.omC + x) : nullptr;
-    {
-      {
-        const int yo = ya + r;
-        const bool row_ok = lane_ok && yo < yb;
-        tc_mbar_wait(once ? &accl[rc & 3] : &accf[rc & 3], once ? 0u : ((rc >> 2) & 1), 600 + (int)(rc & 3));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + (rc & 3) * SLOT + ch0 * 3;
-        for (int c8 = cb; c8 < ce; c8 += 8) {
-          // two 4-channel units per TMEM round trip: their gather / BN / activation chains are independent, which is
-          // what hides the dependent-issue latency of 8 epilogue warps (one unit at a time: 950 clk per unit)
-          float d[24], rv[8];  // [channel j][kw]
-          tc_ld16(tb + c8 * 3, d);
-          tc_ld8(tb + c8 * 3 + 16, d + 16);
-          tc_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 8; ++j)  // out column x gathers input columns x-1 (kw=0), x (kw=1), x+1 (kw=2)
-            rv[j] = __shfl_up_sync(0xffffffffu, d[j * 3 + 0], 1) + d[j * 3 + 1] + __shfl_down_sync(0xffffffffu, d[j * 3 + 2], 1);
-          if (hand_back && c8 + 8 >= ce) {  // last TMEM read of this row: hand the accumulator slot back
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) tc_mbar_arrive(&acce[rc & 3]);
-          }
-          if (row_ok) {
-            const int cl = ch0 + c8;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rv[j] = fmaf(rv[j] * debias, s_aff[cl + j], s_aff[COT + cl + j]);
-            if (gelu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) rv[j] = tc_gelu(rv[j]);
-            } else if (p.act != ESM_ACT_NONE) {
-#pragma unroll
-              for (int h = 0; h < 8; h += 4) {
-                const float4 a = apply_act4(make_float4(rv[h], rv[h + 1], rv[h + 2], rv[h + 3]), p.act);
-                rv[h] = a.x; rv[h + 1] = a.y; rv[h + 2] = a.z; rv[h + 3] = a.w;
-              }
-            }
-            const int o_off = yo * oH + c8 * oC;
-            if (post) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (c8 + j < nvalid) {
-                  if (mp) rv[j] *= __ldg(mp + ((c8 + j) * (int)p.omC + yo * (int)p.omH));
-                  if (rp) rv[j] += __ldg(rp + (o_off + j * oC));
-                }
-              }
-              if (p.act2 != ESM_ACT_NONE) {
-#pragma unroll
-                for (int h = 0; h < 8; h += 4) {
-                  const float4 a = apply_act4(make_float4(rv[h], rv[h + 1], rv[h + 2], rv[h + 3]), p.act2);
-                  rv[h] = a.x; rv[h + 1] = a.y; rv[h + 2] = a.z; rv[h + 3] = a.w;
-                }
-              }
-            }
-            float* o = op + o_off;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (c8 + j < nvalid) o[j * oC] = rv[j] * oscale;
-          }
-        }
-      }
-    }
-  };
-
-  if (warp >= TC_PROD_WARP) {
-    // ============================ operand producers (as in tc_conv_kernel, 2D, one input row per step) ============================
-    const int tw = warp - TC_PROD_WARP;
-    const int q = (tw >> 1) & 3;
-    const int khalf = tw & 1;
-    const int m = q * 32 + lane;
-    uint32_t st = 0, ph = 0;
-    int item = cta, step = 0, cgb = 0;
-    const float* base[3] = {nullptr, nullptr, nullptr};
-    int ya = 0, x = 0;
-    bool strip_ok = false;
-    auto enter_item = [&]() {
-      if (item >= p.items_per_cot) return;
-      const TcItem ti = tc_decode(p, item, 1);
-      const int strip = ti.grp * 4 + q;
-      const int seg = strip % p.nseg, ys = strip / p.nseg;
-      x = seg * p.segw + lane - 1;
-      ya = ys * rows;
-      strip_ok = strip < p.nstrips && x >= 0 && x < p.W && lane < p.segw + 2;
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-        if (i < p.nsrc) base[i] = p.src[i].ptr + (long long)ti.b * p.src[i].sB;
-    };
-    auto load = [&](float (&v)[TPW][4]) {
-      const int y = ya - 1 + step;
-      const bool ok = strip_ok && (unsigned)y < (unsigned)p.H;
-#pragma unroll
-      for (int cgl = 0; cgl < CGS; ++cgl) {
-        int rel = (cgb + cgl) * 8 + khalf * 4, k = 0;
-        if (p.nsrc > 1) {
-          while (k < p.nsrc - 1 && rel >= p.src[k].C) {  // host guarantees 8-channel groups never straddle sources
-            rel -= p.src[k].C;
-            ++k;
-          }
-        }
-        const int sC = (int)p.src[k].sC;
-        const int nch = p.src[k].C - rel;
-        const float* bp = p.nsrc > 1 ? (k == 0 ? base[0] : k == 1 ? base[1] : base[2]) : base[0];
-        const int off = rel * sC + y * (int)p.src[k].sH + x;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) v[cgl][c] = (ok && c < nch) ? __ldg(bp + (off + c * sC)) : 0.f;
-      }
-    };
-    auto advance = [&]() {
-      cgb += CGS;
-      if (cgb >= ncg) {
-        cgb = 0;
-        if (++step >= nsteps) {
-          step = 0;
-          item += p.ctas_per_cot;
-          enter_item();
-        }
-      }
-    };
-    auto store_stage = [&](const float (&v)[TPW][4]) {
-      tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
-      uint8_t* sb = s_stage + (size_t)st * STAGE_BYTES + khalf * 2048 + m * 16;
-#pragma unroll
-      for (int j = 0; j < TPW; ++j) {
-        float4 hi, lo;
-        hi.x = tc_rna(v[j][0]);
-        hi.y = tc_rna(v[j][1]);
-        hi.z = tc_rna(v[j][2]);
-        hi.w = tc_rna(v[j][3]);
-        *reinterpret_cast<float4*>(sb + j * ROW_BYTES) = hi;
-        if (p.npass == 3) {
-          lo.x = tc_lo(v[j][0], hi.x);
-          lo.y = tc_lo(v[j][1], hi.y);
-          lo.z = tc_lo(v[j][2], hi.z);
-          lo.w = tc_lo(v[j][3], hi.w);
-          *reinterpret_cast<float4*>(sb + j * ROW_BYTES + 4096) = lo;
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) tc_mbar_arrive(&full[st]);
-      if (++st == (uint32_t)NS) {
-        st = 0;
-        ph ^= 1;
-      }
-    };
-    float va[TPW][4], vb[TPW][4];
-    enter_item();
-    if (item < p.items_per_cot) load(va);
-    while (item < p.items_per_cot) {
-      advance();
-      if (item < p.items_per_cot) load(vb);
-      store_stage(va);
-      if (item >= p.items_per_cot) break;
-      advance();
-      if (item < p.items_per_cot) load(va);
-      store_stage(vb);
-    }
-    // nothing left to load: take the second 8 channels of epilogue warp (warp % 4, tw / 4) on the last rows
-    if (HELP && n_my > 0) {
-      const int last_item = cta + (n_my - 1) * p.ctas_per_cot;
-      const uint32_t rowc = (uint32_t)(n_my - 1) * (uint32_t)rows;
-      for (int r = rows - tail_rows; r < rows; ++r) epi_row(last_item, r, rowc + (uint32_t)r, warp & 3, (tw >> 2) * CW, 8, CW, true, false);
-    }
-  } else if (warp == TC_MMA_WARP) {
-    // ============================ MMA issuer ============================
-    // Step s brings input row ya - 1 + s: kh = 0 / 1 / 2 send it to output rows s / s-1 / s-2 of the item (where they
-    // exist).  Output row r is first written at step r (kh = 0, first group: that MMA overwrites) after the epilogue
-    // has drained the slot's previous row, and is complete after step r + 2.  The whole warp walks the loop so that the
-    // descriptors stay in uniform registers; one elected lane issues.
-    const uint32_t leader = tc_elect();
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N3 >> 3) << 17) | ((128u >> 4) << 24);
-    const uint64_t a0 = tc_desc(tc_smem_u32(s_stage), 2048, 128), b0 = tc_desc(tc_smem_u32(s_w), N3 * 16, 128);
-    const bool three = p.npass == 3;
-    uint32_t st = 0, ph = 0, rowc = 0;  // rowc: output rows of the items before this one
-    tc_mbar_wait(wready, 0, 700);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    int it = 0;
-    for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot, ++it) {
-      for (int step = 0; step < nsteps; ++step) {
-        if (step < rows) {
-          const uint32_t rc = rowc + (uint32_t)step;
-          tc_mbar_wait(&acce[rc & 3], ((rc >> 2) & 1) ^ 1, 400 + (int)(rc & 3));
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        for (int cgb = 0; cgb < ncg; cgb += CGS) {
-          tc_mbar_wait(&full[st], ph, 500 + (int)st);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t a_st = a0 + (uint64_t)((st * STAGE_BYTES) >> 4);
-          if (leader) {
-#pragma unroll
-            for (int cgl = 0; cgl < CGS; ++cgl) {
-              const int cg = cgb + cgl;
-              if (cg < ncg) {
-                const uint64_t a_hi = a_st + (uint64_t)((cgl * ROW_BYTES) >> 4);
-#pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
-                  const int r = step - kh;
-                  if (r >= 0 && r < rows) {
-                    const uint32_t d = tmem_u + ((rowc + (uint32_t)r) & 3) * SLOT;
-                    const uint64_t b_hi = b0 + (uint64_t)(((uint32_t)(cg * 3 + kh) * 2 * WSLAB) >> 4);
-                    tc_mma(d, a_hi, b_hi, idesc, (kh == 0 && cg == 0) ? 0u : 1u);
-                    if (three) {
-                      tc_mma(d, a_hi + (4096 >> 4), b_hi, idesc, 1u);
-                      tc_mma(d, a_hi, b_hi + (WSLAB >> 4), idesc, 1u);
-                    }
-                  }
-                }
-              }
-            }
-            tc_commit(&empty[st]);
-          }
-          __syncwarp();
-          if (++st == (uint32_t)NS) {
-            st = 0;
-            ph ^= 1;
-          }
-        }
-        if (step >= 2) {
-          if (leader) {
-            tc_commit(&accf[(rowc + (uint32_t)(step - 2)) & 3]);
-            if (HELP && it == n_my - 1 && step - 2 >= rows - tail_rows) tc_commit(&accl[(rowc + (uint32_t)(step - 2)) & 3]);
-          }
-          __syncwarp();
-        }
-      }
-      rowc += (uint32_t)rows;
-    }
-  } else if (warp < TC_NEW) {
-    // ============================ epilogue ============================
-    // warp w and w+4 share TMEM lane quadrant q = w % 4 (one strip) and own CW = COT/2 channels each.  On the last
-    // tail_rows rows of the CTA's last item each of them keeps the first 8 of its 16 channels and a producer warp, idle
-    // by then, takes the other 8 (below): those rows' epilogue is exposed (nothing overlaps it).
-    const int q = warp & 3;
-    const int ch0 = (warp >> 2) * CW;
-    uint32_t rowc = 0;
-    int i = 0;
-    for (int item = cta; item < p.items_per_cot; item += p.ctas_per_cot, ++i) {
-      for (int r = 0; r < rows; ++r) {
-        const bool tail = HELP && i == n_my - 1 && r >= rows - tail_rows;
-        epi_row(item, r, rowc + (uint32_t)r, q, ch0, 0, tail ? 8 : CW, false, true);
-      }
-      rowc += (uint32_t)rows;
-    }
-  }
-#ifdef TC_PROFILE
-  if (blockIdx.x == 0 && lane == 0) {
-    printf("tck_prof warp %2d: done at %8lld clk (grid %d rows %d); waits: empty %8llu  acce %8llu  full %8llu  accf %8llu  wready %8llu\n", warp, clock64() - tc_t0,
-           gridDim.x, rows, tc_prof_wait[warp][2], tc_prof_wait[warp][4], tc_prof_wait[warp][5], tc_prof_wait[warp][6], tc_prof_wait[warp][7]);
     for (int i = 0; i < 8; ++i) tc_prof_wait[warp][i] = 0;
   }
 #endif
@@ -883,18 +499,7 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid
 typedef void (*tc_fn_t)(const TcK);
 static long long tc_launches = 0;
 
-static tc_fn_t tc_pick(int COT, int TZ, int KD, bool gwc, int taps, int NEW) {
-  if (NEW == 16) {  // four epilogue warps per quadrant: whole 4-channel units per warp, one output plane
-    if (gwc || TZ != 1) return nullptr;
-    if (taps == 9 && COT == 16) return KD == 1 ? (tc_fn_t)tc_conv_kernel<16, 1, 1, false, 9, 16> : KD == 3 ? (tc_fn_t)tc_conv_kernel<16, 1, 3, false, 9, 16> : nullptr;
-    if (taps == 1 && KD == 1) {
-      if (COT == 16) return tc_conv_kernel<16, 1, 1, false, 1, 16>;
-      if (COT == 32) return tc_conv_kernel<32, 1, 1, false, 1, 16>;
-      if (COT == 48) return tc_conv_kernel<48, 1, 1, false, 1, 16>;
-      if (COT == 64) return tc_conv_kernel<64, 1, 1, false, 1, 16>;
-    }
-    return nullptr;
-  }
+static tc_fn_t tc_pick(int COT, int TZ, int KD, bool gwc, int taps) {
   if (taps == 1) {  // pointwise: one channel tile holds the whole Cout (<= 64)
     if (gwc || TZ != 1 || KD != 1) return nullptr;
     switch (COT) {
@@ -944,18 +549,17 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
   }
   const int CoutPad8 = round_up(d->Cout, 8);
   const int taps = k1 ? 1 : 9;
-  int COT = tc_cot(d->Cout, k1);
-  if (COT == 0) return false;
-  if (gwc && COT != 8) return false;
-  // 2D k3 layers whose Cout is a multiple of 32: kh in K, kw in N, 32 channels per CTA (tck_conv_kernel), when the
-  // resident weights (18 KB per 8-channel group) leave room for two ring stages.  ESM_TC_KHK=0 keeps taps-in-N.
-  static const bool khk_env = !(getenv("ESM_TC_KHK") && atoi(getenv("ESM_TC_KHK")) == 0);
-  plan->khk = 0;
-  if (khk_env && k3 && d->kd == 1 && !gwc && !d->pixel_shuffle && tc_img_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0).kind == 1 &&
-      (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0) {
-    plan->khk = 1;  // (tc_img_geom gives kind 1 only when the image fits next to two ring stages)
-    COT = 32;
+  int COT;
+  if (k1) {
+    COT = CoutPad8 > 48 ? 64 : CoutPad8;  // 8..48 in steps of 8, or 64
+    if (CoutPad8 > 64) return false;
+  } else if (CoutPad8 <= 24) {
+    COT = CoutPad8;
+  } else {
+    const int w24 = ceil_div(CoutPad8, 24) * 24, w16 = ceil_div(CoutPad8, 16) * 16;
+    COT = (w16 < w24) ? 16 : 24;
   }
+  if (gwc && COT != 8) return false;
   plan->COT = COT;
   plan->taps = taps;
   plan->ncot = ceil_div(d->Cout, COT);
@@ -963,14 +567,10 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
   plan->TZ = (d->kd == 3 && COT == 8) ? 3 : 1;
   plan->gwc = gwc;
   plan->npass = npass;
-  // ESM_TC_EPI=16: four epilogue warps per quadrant wherever a kernel exists for it.  Measured SLOWER (32->32 k3 at
-  // 192x624: 29.0 against 27.2 us; 800 threads cap the kernel at 72 registers): default 8.
-  static const int epi_env = getenv("ESM_TC_EPI") ? atoi(getenv("ESM_TC_EPI")) : 8;
-  plan->NEW = (!plan->khk && epi_env == 16 && tc_pick(COT, plan->TZ, plan->KD, gwc, taps, 16)) ? 16 : 8;
-  if (!plan->khk && !tc_pick(COT, plan->TZ, plan->KD, gwc, taps, plan->NEW)) return false;
+  if (!tc_pick(COT, plan->TZ, plan->KD, gwc, taps)) return false;
   const int NB = taps * COT, NROW = plan->TZ + plan->KD - 1, CGS = NROW == 1 ? 4 : 1;
   const int ncg = ceil_div(d->Cin, 8);
-  const size_t wbytes = plan->khk ? (((size_t)ncg * 3 * 2 * (3 * COT) * 32 + 127) & ~(size_t)127) : (((size_t)ncg * plan->KD * 2 * NB * 32 + 127) & ~(size_t)127);
+  const size_t wbytes = ((size_t)ncg * plan->KD * 2 * NB * 32 + 127) & ~(size_t)127;
   const size_t stage = (size_t)CGS * NROW * 8192;
   const size_t limit = 227 * 1024 - 1024;
   if (wbytes + 2 * stage > limit) return false;
@@ -1015,20 +615,6 @@ int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
   k.CinPad = round_up(d->Cin, 8);
   k.CoutPad = (int)(tcg_pack_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0).offset / ((long long)d->kd * d->kh * d->kw * k.CinPad));
   k.weight = d->weight;
-  if (plan.khk) {
-    const TcImg tk = tc_img_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0);
-    ESM_REQUIRE(tk.kind == 1 && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0, "conv(tc): no weight image for the kh-in-K kernel");
-    k.wimg = d->weight + tk.offset;
-    static const bool help_env = !(getenv("ESM_TC_TAILHELP") && atoi(getenv("ESM_TC_TAILHELP")) == 0);
-    k.tail_help = help_env ? 1 : 0;
-  } else if (!plan.gwc) {
-    // the pack's image of this layer for tc_conv_kernel (same channel tile, taps and depth); the kernel stages the
-    // weights itself when there is none (group-wise correlation stem: its 0.5 is folded into the weights)
-    static const bool img_env = !(getenv("ESM_TC_WIMG") && atoi(getenv("ESM_TC_WIMG")) == 0);
-    const TcImg tk = tc_img_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0);
-    if (img_env && tk.kind == 2 && tk.COT == plan.COT && tk.taps == plan.taps && tk.KD == plan.KD && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0)
-      k.wimg = d->weight + tk.offset;
-  }
   k.scale = d->scale;
   k.shift = d->shift;
   k.act = d->act;
@@ -1055,13 +641,13 @@ int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
   k.nstages = plan.nstages;
   k.npass = plan.npass;
   k.ps = d->pixel_shuffle;
-  tc_fn_t fn = plan.khk ? (tc_fn_t)tck_conv_kernel<32> : tc_pick(plan.COT, plan.TZ, plan.KD, plan.gwc != 0, plan.taps, plan.NEW);
+  tc_fn_t fn = tc_pick(plan.COT, plan.TZ, plan.KD, plan.gwc != 0, plan.taps);
   ESM_REQUIRE(fn, "conv(tc): no kernel for COT=%d TZ=%d KD=%d", plan.COT, plan.TZ, plan.KD);
   // one limit for every launch of a function: the attribute is per function, not per launch, and graph
   // replays (and profilers re-launching graph nodes) must find it at least as large as any node's request
   if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return check_launch("conv(tc, cudaFuncSetAttribute)");
-  launch_k(false, fn, dim3((unsigned)(plan.ncot * plan.ctas_per_cot)), dim3(tc_threads(plan.NEW)), plan.smem, st, k);
+  fn<<<(unsigned)(plan.ncot * plan.ctas_per_cot), TC_THREADS, plan.smem, st>>>(k);
   ++tc_launches;
   return check_launch("conv(tc)");
 }

@@ -471,8 +471,6 @@ struct PfGeom {
 
 __global__ void pf_from_nchw_kernel(const float* __restrict__ x, long long sB, long long sC, long long sD, long long sH, float* __restrict__ o,
                                     PfGeom g, long long total) {
-  pdl_launch_dependents();
-  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int f = (int)(i % g.NP);
@@ -631,7 +629,7 @@ extern "C" int esm_pf_from_nchw_f32(const float* x, long long sB, long long sC, 
   if (int e = pf_geom(out, &g, "pf_from_nchw")) return e;
   ESM_REQUIRE(x, "pf_from_nchw: null input");
   const long long total = (long long)g.B * g.Cq * g.NP;
-  launch_k(pdl_enabled(32), pf_from_nchw_kernel, dim3((unsigned)ceil_div_ll(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, sB, sC, sD, sH, out->data, g, total);
+  pf_from_nchw_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(x, sB, sC, sD, sH, out->data, g, total);
   return check_launch("pf_from_nchw");
 }
 
@@ -844,7 +842,7 @@ extern "C" int esm_conv_pf_f32(const esm_conv_pf_t* d, void* stream) {
   if (getenv("ESM_DEBUG_PLAN"))
     fprintf(stderr, "[esm tcf] Cout=%d ncg=%d KD=%d K=%d phases=%d geom=(%d,%d,%d) mode=%d R=%d NPART=%d NT=%d x%d stages=%d (%zu B) items=%d grid=%u\n",
             d->Cout, k.ncg, k.KD, k.K, k.nphase, g0.Dp, g0.Hp, g0.P, k.mode, k.R, k.NPART, k.NT, k.ncot, ns, sb, k.total_items, grid);
-  launch_k(false, tcf_conv_kernel, dim3(grid), dim3(TF_THREADS), smem, (cudaStream_t)stream, k);
+  tcf_conv_kernel<<<grid, TF_THREADS, smem, (cudaStream_t)stream>>>(k);
   ++tcf_launches;
   return check_launch("conv_pf");
 }

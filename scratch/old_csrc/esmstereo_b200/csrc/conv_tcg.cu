@@ -119,7 +119,6 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
       tc_mbar_init(&empty[i], 1);
     }
     tc_mbar_init(&accf[0], 1);
-    tc_mbar_init(&accf[1], 1);  // completes once: the accumulator of this CTA's LAST item (what the helper warps wait for)
     tc_mbar_init(&acce[0], TG_NEW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -131,102 +130,6 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-
-  // Epilogue of one work item for TMEM lane quadrant q: the 8-channel groups g0, g0 + gstep, ... of the accumulator
-  // (TMEM -> sum of the partial accumulators -> BN / activation -> global).  The epilogue warps run it for every item; after
-  // the LAST item of a CTA the 16 producer warps, which have nothing left to load, take four fifths of the groups (the
-  // accumulator is single-buffered, so this epilogue is not overlapped by anything: ~5 k clk per launch with 4 warps).
-  const bool post = p.out_mul || p.residual || p.act2 != ESM_ACT_NONE;
-  const bool gelu = p.act == ESM_ACT_GELU;
-  const int so = p.transposed ? 2 : 1;
-  auto epilogue_item = [&](int item, uint32_t aph, int q, int g0, int gstep, bool hand_back) {
-    // helpers (hand_back == false) wait on the once-only barrier of the last item: they may be a whole item ahead of
-    // the MMA issuer, and a phase parity can only name the current phase of accf[0] or the one before it
-    const int m = q * 32 + lane;
-    {
-      const TgItem ti = tg_decode(p, item);
-      const int v = ti.mt * 128 + m;
-      const int jx = v % p.Jw, r = v / p.Jw;
-      const int jy = r % p.Jh, jz = r / p.Jh;
-      const int pzw = ti.phase & 1, pzh = (ti.phase >> 1) & 1, pzd = (p.phases_d == 2) ? ((ti.phase >> 2) & 1) : 0;
-      const int oz = p.transposed ? jz * (p.phases_d == 2 ? 2 : 1) + pzd : jz;
-      const int oy = p.transposed ? jy * so + pzh : jy, ox = p.transposed ? jx * so + pzw : jx;
-      const bool ok = v < voxels && oz < p.Dout && oy < p.Hout && ox < p.Wout;
-      const int co0 = ti.cot * NT;
-      const long long obase = (long long)ti.b * p.oB + (long long)oz * p.oD + (long long)oy * p.oH + ox;
-      float* op = p.out + obase;
-      const float* rp = p.residual ? p.residual + obase : nullptr;
-      const float* mp = p.out_mul ? p.out_mul + (long long)ti.b * p.omB + (long long)oy * p.omH + ox : nullptr;
-      const uint32_t ab = 0;
-      tc_mbar_wait(hand_back ? &accf[0] : &accf[1], hand_back ? aph : 0u, 600 + (hand_back ? 0 : 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16);
-      const int nacc = Pe + (p.npass == 3 ? 1 : 0);  // columns to add per channel: partials 0..Pe-1, then the corrections at P
-      // expected-value correction of the accumulator truncation: each of the ~slabs/Pe chained accumulates into a
-      // partial rounds it toward zero, -1.25e-8 relative per step on average (scripts/engine_accuracy.py: the bias
-      // column; the FP32 pipe rounds to nearest and has none)
-      const float debias = 1.0f + TC_TRUNC_BIAS * (float)(p.ncg * p.taps) / (float)Pe;
-      for (int c8 = g0 * 8; c8 < NT; c8 += gstep * 8) {
-        float rv[8], t0[8], t1[8];
-        tc_ld8(tb + c8, rv);
-        for (int j = 1; j < nacc; j += 2) {
-          const bool two = j + 1 < nacc;
-          tc_ld8(tb + (j < Pe ? j : P) * NT + c8, t0);
-          if (two) tc_ld8(tb + (j + 1 < Pe ? j + 1 : P) * NT + c8, t1);
-          tc_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) rv[i] += two ? t0[i] + t1[i] : t0[i];
-        }
-        tc_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rv[i] *= debias;
-        if (hand_back && c8 + gstep * 8 >= NT) {  // last TMEM read of this item: hand the accumulator buffer back
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) tc_mbar_arrive(&acce[ab]);
-        }
-        const int co = co0 + c8;
-        if (ok && co < p.Cout) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int cj = min(co + j, p.Cout - 1);
-            rv[j] = fmaf(rv[j], p.scale ? __ldg(p.scale + cj) : 1.f, p.shift ? __ldg(p.shift + cj) : 0.f);
-          }
-          if (gelu) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rv[j] = tc_gelu(rv[j]);
-          } else if (p.act != ESM_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 8; j += 4) {
-              const float4 a = apply_act4(make_float4(rv[j], rv[j + 1], rv[j + 2], rv[j + 3]), p.act);
-              rv[j] = a.x; rv[j + 1] = a.y; rv[j + 2] = a.z; rv[j + 3] = a.w;
-            }
-          }
-          if (post) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (co + j < p.Cout) {
-                if (mp) rv[j] *= __ldg(mp + (long long)(co + j) * p.omC);
-                if (rp) rv[j] += __ldg(rp + (long long)(co + j) * p.oC);
-              }
-            }
-            if (p.act2 != ESM_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 8; j += 4) {
-                const float4 a = apply_act4(make_float4(rv[j], rv[j + 1], rv[j + 2], rv[j + 3]), p.act2);
-                rv[j] = a.x; rv[j + 1] = a.y; rv[j + 2] = a.z; rv[j + 3] = a.w;
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (co + j < p.Cout) op[(long long)(co + j) * p.oC] = rv[j] * p.out_scale;
-        }
-      }
-    }
-  };
-  const int n_my = (int)blockIdx.x < p.items ? (p.items - (int)blockIdx.x + p.ctas - 1) / p.ctas : 0;  // items of this CTA
-  static_assert(TG_NSET * TG_NTW == 16, "four helper warps per TMEM lane quadrant");
 
   if (warp >= TG_PROD_WARP) {
     // ============================ A-operand producers ============================
@@ -343,9 +246,6 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
       for (int i = 0; i < TG_NSET; ++i) next_stage();
       store_stage(v, nv);
     }
-    // nothing left to load: help with the epilogue of this CTA's last item (helper 1..4 of quadrant warp % 4)
-    if (n_my > 0 && (1 + (warp - TG_PROD_WARP) / 4) * 8 < NT)
-      epilogue_item((int)blockIdx.x + (n_my - 1) * p.ctas, (uint32_t)(n_my - 1) & 1, warp & 3, 1 + (warp - TG_PROD_WARP) / 4, 5, false);
   } else if (warp == TG_W_WARP) {
     // ============================ weight streamer ============================
     if (lane == 0) {
@@ -419,19 +319,99 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tcg_conv_kernel(const __grid_co
           ph ^= 1;
         }
       }
-      if (leader) {
-        tc_commit(&accf[ab]);
-        if ((int)ai == n_my - 1) tc_commit(&accf[1]);
-      }
+      if (leader) tc_commit(&accf[ab]);
       __syncwarp();
       ++ai;
     }
   } else {
     // ============================ epilogue ============================
-    int i = 0;
-    for (int item = blockIdx.x; item < p.items; item += p.ctas, ++i) {
-      const bool last = i == n_my - 1;
-      epilogue_item(item, (uint32_t)i & 1, warp, 0, last ? 5 : 1, true);
+    const int q = warp;  // TMEM lane quadrant
+    const int m = q * 32 + lane;
+    const bool post = p.out_mul || p.residual || p.act2 != ESM_ACT_NONE;
+    const bool gelu = p.act == ESM_ACT_GELU;
+    const int so = p.transposed ? 2 : 1;
+    uint32_t ai = 0;
+    for (int item = blockIdx.x; item < p.items; item += p.ctas) {
+      const TgItem ti = tg_decode(p, item);
+      const int v = ti.mt * 128 + m;
+      const int jx = v % p.Jw, r = v / p.Jw;
+      const int jy = r % p.Jh, jz = r / p.Jh;
+      const int pzw = ti.phase & 1, pzh = (ti.phase >> 1) & 1, pzd = (p.phases_d == 2) ? ((ti.phase >> 2) & 1) : 0;
+      const int oz = p.transposed ? jz * (p.phases_d == 2 ? 2 : 1) + pzd : jz;
+      const int oy = p.transposed ? jy * so + pzh : jy, ox = p.transposed ? jx * so + pzw : jx;
+      const bool ok = v < voxels && oz < p.Dout && oy < p.Hout && ox < p.Wout;
+      const int co0 = ti.cot * NT;
+      const long long obase = (long long)ti.b * p.oB + (long long)oz * p.oD + (long long)oy * p.oH + ox;
+      float* op = p.out + obase;
+      const float* rp = p.residual ? p.residual + obase : nullptr;
+      const float* mp = p.out_mul ? p.out_mul + (long long)ti.b * p.omB + (long long)oy * p.omH + ox : nullptr;
+      const uint32_t ab = 0, aph = ai & 1;
+      tc_mbar_wait(&accf[ab], aph, 600 + (int)ab);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16);
+      const int nacc = Pe + (p.npass == 3 ? 1 : 0);  // columns to add per channel: partials 0..Pe-1, then the corrections at P
+      // expected-value correction of the accumulator truncation: each of the ~slabs/Pe chained accumulates into a
+      // partial rounds it toward zero, -1.25e-8 relative per step on average (scripts/engine_accuracy.py: the bias
+      // column; the FP32 pipe rounds to nearest and has none)
+      const float debias = 1.0f + TC_TRUNC_BIAS * (float)(p.ncg * p.taps) / (float)Pe;
+      for (int c8 = 0; c8 < NT; c8 += 8) {
+        float rv[8], t0[8], t1[8];
+        tc_ld8(tb + c8, rv);
+        for (int j = 1; j < nacc; j += 2) {
+          const bool two = j + 1 < nacc;
+          tc_ld8(tb + (j < Pe ? j : P) * NT + c8, t0);
+          if (two) tc_ld8(tb + (j + 1 < Pe ? j + 1 : P) * NT + c8, t1);
+          tc_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rv[i] += two ? t0[i] + t1[i] : t0[i];
+        }
+        tc_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rv[i] *= debias;
+        if (c8 + 8 >= NT) {  // last TMEM read of this item: hand the accumulator buffer back
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tc_mbar_arrive(&acce[ab]);
+        }
+        const int co = co0 + c8;
+        if (ok && co < p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int cj = min(co + j, p.Cout - 1);
+            rv[j] = fmaf(rv[j], p.scale ? __ldg(p.scale + cj) : 1.f, p.shift ? __ldg(p.shift + cj) : 0.f);
+          }
+          if (gelu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = tc_gelu(rv[j]);
+          } else if (p.act != ESM_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+              const float4 a = apply_act4(make_float4(rv[j], rv[j + 1], rv[j + 2], rv[j + 3]), p.act);
+              rv[j] = a.x; rv[j + 1] = a.y; rv[j + 2] = a.z; rv[j + 3] = a.w;
+            }
+          }
+          if (post) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (co + j < p.Cout) {
+                if (mp) rv[j] *= __ldg(mp + (long long)(co + j) * p.omC);
+                if (rp) rv[j] += __ldg(rp + (long long)(co + j) * p.oC);
+              }
+            }
+            if (p.act2 != ESM_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 8; j += 4) {
+                const float4 a = apply_act4(make_float4(rv[j], rv[j + 1], rv[j + 2], rv[j + 3]), p.act2);
+                rv[j] = a.x; rv[j + 1] = a.y; rv[j + 2] = a.z; rv[j + 3] = a.w;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (co + j < p.Cout) op[(long long)(co + j) * p.oC] = rv[j] * p.out_scale;
+        }
+      }
+      ++ai;
     }
   }
 #ifdef TC_PROFILE
@@ -579,7 +559,7 @@ int tcg_conv_launch(const esm_conv_t* d, const TcgPlan& plan, cudaStream_t st) {
   void (*fn)(const TcgK) = !d->transposed ? tcg_conv_kernel<3, 1, 1> : (d->kd == 4 ? tcg_conv_kernel<2, 2, 1> : tcg_conv_kernel<2, 1, 2>);
   if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return check_launch("conv(tcg, cudaFuncSetAttribute)");
-  launch_k(false, fn, dim3((unsigned)plan.ctas), dim3(TG_THREADS), plan.smem, st, k);
+  fn<<<(unsigned)plan.ctas, TG_THREADS, plan.smem, st>>>(k);
   ++tcg_launches;
   return check_launch("conv(tcg)");
 }
