@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libesm_b200_prof.so" if os.environ.get("ESM_TC_PROFILE") == "1" else "libesm_b200.so")
+LIB_PATH = os.environ.get("ESM_LIB") or os.path.join(_HERE, "csrc", "libesm_b200_prof.so" if os.environ.get("ESM_TC_PROFILE") == "1" else "libesm_b200.so")  # ESM_LIB: an A/B build of the same ABI (diagnostics)
 
 ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "silu": 3, "sigmoid": 4, "2sigmoid": 5, "relu6": 6}
 SRC_TENSORS, SRC_GWC = 0, 1

@@ -30,8 +30,13 @@ int check_launch(const char* what);
 // for the values computed around it (R2UR 20 -> 380 in the gwc stem kernel, +14 us; the MMA issue loop pays 11 R2URs per
 // stage), which cost more than the launch overlap ever returned.
 bool pdl_enabled(int family_bit);
+#ifdef ESM_NO_PDL
+__device__ __forceinline__ void pdl_launch_dependents() {}
+__device__ __forceinline__ void pdl_wait() {}
+#else
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 template <typename... Params, typename... Args>
 static inline cudaError_t launch_k(bool pdl, void (*fn)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
