@@ -533,17 +533,25 @@ __global__ void __launch_bounds__(tc_threads(NEW), 1) tc_conv_kernel(const __gri
 // of the three output rows it touches (N = 3 * COT = 96), a ring of four accumulators in tensor memory; the epilogue
 // reads 3 columns per output and only the kw gather (two warp shuffles) is left.  Same producers, same split-TF32
 // arithmetic; an accumulator chains 9 * ncg MMAs (the epilogue's expected-value correction uses that count).
-template <int COT>
+template <int COT, bool TS>
 __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid_constant__ TcK p) {
   constexpr int TC_NEW = 8, TC_MMA_WARP = TC_NEW, TC_PROD_WARP = TC_NEW + tc_nmw(8);
   constexpr int N3 = 3 * COT;                  // accumulator columns per output row: (co, kw)
-  constexpr int SLOT = 128, NSLOT = 4;         // accumulator ring in tensor memory
+  // TS: the A operand (activation row tiles) lives in TENSOR memory and the MMAs are TS-form (tc_mma_ts): in shared
+  // memory every M128 x N96 x K8 MMA read 4 KB of A next to 3 KB of B at 128 B/clk -- 83 clk per MMA against 56 in
+  // isolation, the kernel's bound once the weights came by bulk copy.  Tensor memory: four accumulator slots of N3 = 96
+  // columns, then a two-stage A ring of 4 groups x (hi 8 | lo 8) columns; the producers write their rows with
+  // tcgen05.st (a warp reaches only its own lane quadrant: quadrant = warp % 4), no proxy fence, no shared-memory stage.
+  constexpr int SLOT = TS ? N3 : 128, NSLOT = 4;  // accumulator ring in tensor memory
+  constexpr uint32_t ACOL = NSLOT * N3;           // TS: first column of the A ring (two stages x 4 groups x 16 columns)
+  static_assert(!TS || ACOL + 2 * 4 * 16 <= 512, "tensor memory budget");
   constexpr int CGS = 4, TPW = CGS;            // 8-channel groups (= row tiles) per stage
   constexpr int ROW_BYTES = 8192;              // row tile: hi [2][128][4] floats, then lo
   constexpr int STAGE_BYTES = TPW * ROW_BYTES;
   constexpr int WSLAB = N3 * 32;               // one (cg, kh, hi|lo) B operand: [2][N3][4] floats
   constexpr int CW = COT / 2;                  // output channels per epilogue warp
   static_assert(N3 <= SLOT && N3 % 8 == 0 && CW % 8 == 0, "accumulator slot");
+  constexpr int STAGE_SMEM = TS ? 0 : STAGE_BYTES;  // shared-memory bytes per ring stage
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef TC_PROFILE
@@ -554,7 +562,7 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid
   const uint32_t wbytes = (uint32_t)ncg * 3 * 2 * WSLAB;
   uint8_t* s_w = smem;
   uint8_t* s_stage = smem + ((wbytes + 127u) & ~127u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_stage + (size_t)NS * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_stage + (size_t)NS * STAGE_SMEM);
   uint64_t* empty = full + NS;
   uint64_t* accf = empty + NS;
   uint64_t* acce = accf + NSLOT;
@@ -690,8 +698,8 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid
   if (warp >= TC_PROD_WARP) {
     // ============================ operand producers (as in tc_conv_kernel, 2D, one input row per step) ============================
     const int tw = warp - TC_PROD_WARP;
-    const int q = (tw >> 1) & 3;
-    const int khalf = tw & 1;
+    const int q = TS ? (warp & 3) : ((tw >> 1) & 3);   // strip = TMEM lane quadrant (TS: the one this warp may write)
+    const int khalf = TS ? (tw >> 2) : (tw & 1);        // which 4 of the 8 channels of a group
     const int m = q * 32 + lane;
     uint32_t st = 0, ph = 0;
     int item = cta, step = 0, cgb = 0;
@@ -743,6 +751,25 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid
     };
     auto store_stage = [&](const float (&v)[TPW][4]) {
       tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
+      if constexpr (TS) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + ACOL + st * (TPW * 16) + khalf * 4;
+#pragma unroll
+        for (int j = 0; j < TPW; ++j) {
+          const float h0 = tc_rna(v[j][0]), h1 = tc_rna(v[j][1]), h2 = tc_rna(v[j][2]), h3 = tc_rna(v[j][3]);
+          tc_st4(ta + j * 16, h0, h1, h2, h3);
+          if (p.npass == 3) tc_st4(ta + j * 16 + 8, tc_lo(v[j][0], h0), tc_lo(v[j][1], h1), tc_lo(v[j][2], h2), tc_lo(v[j][3], h3));
+        }
+        tc_st_wait();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(&full[st]);
+        if (++st == (uint32_t)NS) {
+          st = 0;
+          ph ^= 1;
+        }
+        return;
+      }
       uint8_t* sb = s_stage + (size_t)st * STAGE_BYTES + khalf * 2048 + m * 16;
 #pragma unroll
       for (int j = 0; j < TPW; ++j) {
@@ -824,10 +851,19 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid
                   if (r >= 0 && r < rows) {
                     const uint32_t d = tmem_u + ((rowc + (uint32_t)r) & 3) * SLOT;
                     const uint64_t b_hi = b0 + (uint64_t)(((uint32_t)(cg * 3 + kh) * 2 * WSLAB) >> 4);
-                    tc_mma(d, a_hi, b_hi, idesc, (kh == 0 && cg == 0) ? 0u : 1u);
-                    if (three) {
-                      tc_mma(d, a_hi + (4096 >> 4), b_hi, idesc, 1u);
-                      tc_mma(d, a_hi, b_hi + (WSLAB >> 4), idesc, 1u);
+                    if constexpr (TS) {
+                      const uint32_t ta = tmem_u + ACOL + (st * CGS + cgl) * 16;  // hi k0..7 | lo k0..7
+                      tc_mma_ts(d, ta, b_hi, idesc, (kh == 0 && cg == 0) ? 0u : 1u);
+                      if (three) {
+                        tc_mma_ts(d, ta + 8, b_hi, idesc, 1u);
+                        tc_mma_ts(d, ta, b_hi + (WSLAB >> 4), idesc, 1u);
+                      }
+                    } else {
+                      tc_mma(d, a_hi, b_hi, idesc, (kh == 0 && cg == 0) ? 0u : 1u);
+                      if (three) {
+                        tc_mma(d, a_hi + (4096 >> 4), b_hi, idesc, 1u);
+                        tc_mma(d, a_hi, b_hi + (WSLAB >> 4), idesc, 1u);
+                      }
                     }
                   }
                 }
@@ -953,8 +989,17 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
   plan->khk = 0;
   if (khk_env && k3 && d->kd == 1 && !gwc && !d->pixel_shuffle && tc_img_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0).kind == 1 &&
       (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0) {
-    plan->khk = 1;  // (tc_img_geom gives kind 1 only when the image fits next to two ring stages)
-    COT = 32;
+    // 2: A operand in tensor memory (TS-form MMAs; no shared-memory stages, so Cin <= 96 fits); 1 (ESM_TC_KHK_TS=0):
+    // A in shared memory, which needs room for two 32 KB ring stages next to the weights (Cin <= 64)
+    static const bool ts_env = !(getenv("ESM_TC_KHK_TS") && atoi(getenv("ESM_TC_KHK_TS")) == 0);
+    const size_t wb = (size_t)ceil_div(d->Cin, 8) * 3 * 2 * 96 * 32 + 127;
+    if (ts_env) {
+      plan->khk = 2;
+      COT = 32;
+    } else if (wb + 2 * 4 * 8192 <= 227 * 1024 - 1024) {
+      plan->khk = 1;
+      COT = 32;
+    }
   }
   plan->COT = COT;
   plan->taps = taps;
@@ -973,10 +1018,16 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
   const size_t wbytes = plan->khk ? (((size_t)ncg * 3 * 2 * (3 * COT) * 32 + 127) & ~(size_t)127) : (((size_t)ncg * plan->KD * 2 * NB * 32 + 127) & ~(size_t)127);
   const size_t stage = (size_t)CGS * NROW * 8192;
   const size_t limit = 227 * 1024 - 1024;
-  if (wbytes + 2 * stage > limit) return false;
-  int ns = (int)((limit - wbytes) / stage);
-  plan->nstages = ns > 4 ? 4 : ns;
-  plan->smem = wbytes + plan->nstages * stage + 1024;
+  if (plan->khk == 2) {
+    if (wbytes > limit) return false;
+    plan->nstages = 2;  // the A ring lives in tensor memory
+    plan->smem = wbytes + 1024;
+  } else {
+    if (wbytes + 2 * stage > limit) return false;
+    int ns = (int)((limit - wbytes) / stage);
+    plan->nstages = ns > 4 ? 4 : ns;
+    plan->smem = wbytes + plan->nstages * stage + 1024;
+  }
   const int segmax = k1 ? 32 : 30;
   plan->nseg = ceil_div(d->Wout, segmax);
   plan->segw = ceil_div(d->Wout, plan->nseg);
@@ -1055,7 +1106,7 @@ int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
   k.nstages = plan.nstages;
   k.npass = plan.npass;
   k.ps = d->pixel_shuffle;
-  tc_fn_t fn = plan.khk ? (tc_fn_t)tck_conv_kernel<32> : tc_pick(plan.COT, plan.TZ, plan.KD, plan.gwc != 0, plan.taps, plan.NEW);
+  tc_fn_t fn = plan.khk ? (plan.khk == 2 ? (tc_fn_t)tck_conv_kernel<32, true> : (tc_fn_t)tck_conv_kernel<32, false>) : tc_pick(plan.COT, plan.TZ, plan.KD, plan.gwc != 0, plan.taps, plan.NEW);
   ESM_REQUIRE(fn, "conv(tc): no kernel for COT=%d TZ=%d KD=%d", plan.COT, plan.TZ, plan.KD);
   // one limit for every launch of a function: the attribute is per function, not per launch, and graph
   // replays (and profilers re-launching graph nodes) must find it at least as large as any node's request
