@@ -916,8 +916,294 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tck_conv_kernel(const __grid
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Pointwise (k1) layers, TS-form: tc1_conv_kernel.  The taps-in-N kernel runs k1 layers as TAPS = 1 over image strips
+// (32 columns of one row per TMEM lane quadrant) with its shared-memory operand ring, whose proxy fence (MEMBAR) makes a
+// producer stage cost one exposed load latency on top of its stores: these layers -- 100-160 input channels, 16-64
+// outputs, 0.2 GFLOP -- are bound by exactly that.  Here a tile is 128 CONSECUTIVE pixels of the flattened (d, h, w)
+// lattice (no strips, no idle lanes on narrow images), the producers write their rows of the activation tile straight
+// into a six-stage ring in tensor memory (tcgen05.st, no fence: the loads of the next stage stay in flight under the
+// stores of this one), the MMAs are TS-form with the resident pre-split weight image as B, and the accumulator
+// (N = COT <= 64 columns) is double-buffered.  Same split-TF32 arithmetic, same epilogue options (BN, activations,
+// broadcast multiply, residual, second activation, scale) as the taps-in-N kernel; PixelShuffle stays there.
+template <int COT>
+__global__ void __launch_bounds__(tc_threads(8), 1) tc1_conv_kernel(const __grid_constant__ TcK p) {
+  constexpr int TC_NEW = 8, TC_MMA_WARP = TC_NEW, TC_PROD_WARP = TC_NEW + tc_nmw(8);
+  constexpr int CGS = 4;                        // 8-channel groups per ring stage
+  constexpr int ACC = 64;                       // columns per accumulator buffer (COT <= 64), two buffers
+  constexpr uint32_t ACOL = 2 * ACC;            // first column of the A ring
+  constexpr int STAGE_COLS = CGS * 16;          // hi 8 | lo 8 columns per group
+  constexpr int NSA = (512 - (int)ACOL) / STAGE_COLS;  // 6 ring stages
+  constexpr int WSLAB = COT * 32;               // bytes of one (cg, hi|lo) B operand: [2][COT][4] floats
+  constexpr int CW = COT / 2;                   // output channels per epilogue warp
+  static_assert(COT % 8 == 0 && COT <= ACC && CW % 4 == 0, "channel tile");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ncg = p.ncg;
+  const uint32_t wbytes = (uint32_t)ncg * 2 * WSLAB;
+  uint8_t* s_w = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + ((wbytes + 127u) & ~127u));
+  uint64_t* empty = full + NSA;
+  uint64_t* accf = empty + NSA;
+  uint64_t* acce = accf + 2;
+  uint64_t* wready = acce + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wready + 1);
+  float* s_aff = reinterpret_cast<float*>(tmem_slot + 2);  // [2][COT] scale, shift
+  const int npix = p.D * p.H * p.W;             // pixels of one batch item
+  const int tiles = (npix + 127) >> 7;
+  const int items = p.B * tiles;
+  const int SPI = (ncg + CGS - 1) / CGS;        // ring stages per item
+
+  if (tid == 0) {
+    for (int i = 0; i < NSA; ++i) {
+      tc_mbar_init(&full[i], TC_NTW);
+      tc_mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc_mbar_init(&accf[i], 1);
+      tc_mbar_init(&acce[i], TC_NEW);
+    }
+    tc_mbar_init(wready, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid < 2 * COT) {
+    const int c = tid % COT;
+    const float* src = tid < COT ? p.scale : p.shift;
+    s_aff[tid] = (src && c < p.Cout) ? __ldg(src + c) : (tid < COT ? 1.f : 0.f);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  if (tid == TC_MMA_WARP * 32) {  // resident weights: the pack's pre-split image, one bulk copy per 8-channel group
+    tc_mbar_expect_tx(wready, wbytes);
+    for (int cg = 0; cg < ncg; ++cg) tc_bulk_g2s(s_w + (size_t)cg * (2 * WSLAB), p.wimg + (long long)cg * (2 * WSLAB / 4), 2 * WSLAB, wready);
+  }
+
+  if (warp >= TC_PROD_WARP) {
+    // ============================ A-operand producers ============================
+    const int tw = warp - TC_PROD_WARP;
+    const int q = warp & 3;        // the TMEM lane quadrant this warp may write = rows q*32 .. q*32+31 of the tile
+    const int khalf = tw >> 2;     // which 4 of the 8 channels of a group
+    uint32_t st = 0, ph = 0;
+    int item = blockIdx.x, cgb = 0;
+    const float* base[3] = {nullptr, nullptr, nullptr};  // this lane's pixel in each source
+    bool ok = false;
+    auto enter_item = [&]() {
+      if (item >= items) return;
+      const int b = item / tiles, pix = (item - b * tiles) * 128 + q * 32 + lane;
+      ok = pix < npix;
+      const int x = pix % p.W, r = pix / p.W;
+      const int y = r % p.H, z = r / p.H;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (i < p.nsrc) base[i] = p.src[i].ptr + ((long long)b * p.src[i].sB + (long long)z * p.src[i].sD + (long long)y * p.src[i].sH + x);
+    };
+    auto load = [&](float (&v)[CGS][4]) {
+#pragma unroll
+      for (int cgl = 0; cgl < CGS; ++cgl) {
+        int rel = (cgb + cgl) * 8 + khalf * 4, k = 0;
+        if (p.nsrc > 1) {
+          while (k < p.nsrc - 1 && rel >= p.src[k].C) {  // host guarantees 8-channel groups never straddle sources
+            rel -= p.src[k].C;
+            ++k;
+          }
+        }
+        const int sC = (int)p.src[k].sC;
+        const int nch = p.src[k].C - rel;  // valid channels from `rel` on (<= 0 past the last group)
+        const float* bp = p.nsrc > 1 ? (k == 0 ? base[0] : k == 1 ? base[1] : base[2]) : base[0];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[cgl][c] = (ok && c < nch) ? __ldg(bp + (rel + c) * sC) : 0.f;
+      }
+    };
+    auto advance = [&]() {
+      cgb += CGS;
+      if (cgb >= ncg) {
+        cgb = 0;
+        item += gridDim.x;
+        enter_item();
+      }
+    };
+    auto store_stage = [&](const float (&v)[CGS][4]) {
+      tc_mbar_wait(&empty[st], ph ^ 1, 200 + (int)st);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + ACOL + st * STAGE_COLS + khalf * 4;
+#pragma unroll
+      for (int j = 0; j < CGS; ++j) {
+        const float h0 = tc_rna(v[j][0]), h1 = tc_rna(v[j][1]), h2 = tc_rna(v[j][2]), h3 = tc_rna(v[j][3]);
+        tc_st4(ta + j * 16, h0, h1, h2, h3);
+        if (p.npass == 3) tc_st4(ta + j * 16 + 8, tc_lo(v[j][0], h0), tc_lo(v[j][1], h1), tc_lo(v[j][2], h2), tc_lo(v[j][3], h3));
+      }
+      tc_st_wait();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(&full[st]);
+      if (++st == (uint32_t)NSA) {
+        st = 0;
+        ph ^= 1;
+      }
+    };
+    float va[CGS][4], vb[CGS][4];
+    enter_item();
+    if (item < items) load(va);
+    while (item < items) {
+      advance();
+      if (item < items) load(vb);
+      store_stage(va);
+      if (item >= items) break;
+      advance();
+      if (item < items) load(va);
+      store_stage(vb);
+    }
+  } else if (warp == TC_MMA_WARP) {
+    // ============================ MMA issuer ============================
+    const uint32_t leader = tc_elect();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(COT >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t b0 = tc_desc(tc_smem_u32(s_w), COT * 16, 128);
+    const bool three = p.npass == 3;
+    uint32_t st = 0, ph = 0, ai = 0;
+    tc_mbar_wait(wready, 0, 700);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
+      tc_mbar_wait(&acce[ab], aph ^ 1, 400 + (int)ab);  // the epilogue has drained this accumulator buffer
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d = tmem_u + ab * ACC;
+      for (int cgb = 0; cgb < ncg; cgb += CGS) {
+        tc_mbar_wait(&full[st], ph, 500 + (int)st);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_st = tmem_u + ACOL + st * STAGE_COLS;
+        const uint64_t b_st = b0 + (uint64_t)(((uint32_t)cgb * 2 * WSLAB) >> 4);
+        if (leader) {
+#pragma unroll
+          for (int cgl = 0; cgl < CGS; ++cgl) {
+            if (cgb + cgl < ncg) {
+              const uint32_t a_hi = a_st + cgl * 16;
+              const uint64_t b_hi = b_st + (uint64_t)((cgl * 2 * WSLAB) >> 4);
+              tc_mma_ts(d, a_hi, b_hi, idesc, (cgb + cgl) > 0 ? 1u : 0u);
+              if (three) {
+                tc_mma_ts(d, a_hi + 8, b_hi, idesc, 1u);
+                tc_mma_ts(d, a_hi, b_hi + (WSLAB >> 4), idesc, 1u);
+              }
+            }
+          }
+          tc_commit(&empty[st]);
+        }
+        __syncwarp();
+        if (++st == (uint32_t)NSA) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+      if (leader) tc_commit(&accf[ab]);
+      __syncwarp();
+      ++ai;
+    }
+  } else if (warp < TC_NEW) {
+    // ============================ epilogue ============================
+    // warp w and w+4 share TMEM lane quadrant q = w % 4 and own CW = COT/2 channels each, 8 (or the last 4) at a time
+    const int q = warp & 3;
+    const int ch0 = (warp >> 2) * CW;
+    const int nvalid = p.Cout - ch0;
+    const int oC = (int)p.oC;
+    const bool post = p.out_mul || p.residual || p.act2 != ESM_ACT_NONE;
+    const bool gelu = p.act == ESM_ACT_GELU;
+    const float oscale = p.out_scale;
+    const float debias = 1.0f + TC_TRUNC_BIAS * (float)(ncg * (p.npass == 3 ? 3 : 1));
+    uint32_t ai = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int b = item / tiles, pix = (item - b * tiles) * 128 + q * 32 + lane;
+      const bool ok = pix < npix;
+      const int x = pix % p.W, r = pix / p.W;
+      const int y = r % p.H, z = r / p.H;
+      const long long obase = (long long)b * p.oB + (long long)ch0 * p.oC + (long long)z * p.oD + (long long)y * p.oH + x;
+      float* op = p.out + obase;
+      const float* rp = p.residual ? p.residual + obase : nullptr;
+      const float* mp = p.out_mul ? p.out_mul + ((long long)b * p.omB + (long long)ch0 * p.omC + (long long)y * p.omH + x) : nullptr;
+      const uint32_t ab = ai & 1, aph = (ai >> 1) & 1;
+      tc_mbar_wait(&accf[ab], aph, 600 + (int)ab);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + ab * ACC + ch0;
+#pragma unroll
+      for (int c8 = 0; c8 < CW; c8 += 8) {
+        const int nc = (CW - c8) < 8 ? (CW - c8) : 8;  // 8, or 4 for the last unit of CW = 12 / 20
+        float rv[8];
+        if (CW - c8 >= 8) {
+          tc_ld8(tb + c8, rv);
+        } else {
+          tc_ld4(tb + c8, rv);
+          rv[4] = rv[5] = rv[6] = rv[7] = 0.f;
+        }
+        tc_ld_wait();
+        if (c8 + 8 >= CW) {  // last TMEM read of this item: hand the accumulator buffer back
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tc_mbar_arrive(&acce[ab]);
+        }
+        if (ok) {
+          const int cl = ch0 + c8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < nc) rv[j] = fmaf(rv[j] * debias, s_aff[cl + j], s_aff[COT + cl + j]);
+          if (gelu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = tc_gelu(rv[j]);
+          } else if (p.act != ESM_ACT_NONE) {
+#pragma unroll
+            for (int h = 0; h < 8; h += 4) {
+              const float4 a = apply_act4(make_float4(rv[h], rv[h + 1], rv[h + 2], rv[h + 3]), p.act);
+              rv[h] = a.x; rv[h + 1] = a.y; rv[h + 2] = a.z; rv[h + 3] = a.w;
+            }
+          }
+          if (post) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j < nc && c8 + j < nvalid) {
+                if (mp) rv[j] *= __ldg(mp + (long long)(c8 + j) * p.omC);
+                if (rp) rv[j] += __ldg(rp + (long long)(c8 + j) * oC);
+              }
+            }
+            if (p.act2 != ESM_ACT_NONE) {
+#pragma unroll
+              for (int h = 0; h < 8; h += 4) {
+                const float4 a = apply_act4(make_float4(rv[h], rv[h + 1], rv[h + 2], rv[h + 3]), p.act2);
+                rv[h] = a.x; rv[h + 1] = a.y; rv[h + 2] = a.z; rv[h + 3] = a.w;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < nc && c8 + j < nvalid) op[(long long)(c8 + j) * oC] = rv[j] * oscale;
+        }
+      }
+      ++ai;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
 typedef void (*tc_fn_t)(const TcK);
 static long long tc_launches = 0;
+
+static tc_fn_t tc1_pick(int COT) {
+  switch (COT) {
+    case 8: return tc1_conv_kernel<8>;
+    case 16: return tc1_conv_kernel<16>;
+    case 24: return tc1_conv_kernel<24>;
+    case 32: return tc1_conv_kernel<32>;
+    case 40: return tc1_conv_kernel<40>;
+    case 48: return tc1_conv_kernel<48>;
+    case 64: return tc1_conv_kernel<64>;
+    default: return nullptr;
+  }
+}
 
 static tc_fn_t tc_pick(int COT, int TZ, int KD, bool gwc, int taps, int NEW) {
   if (NEW == 16) {  // four epilogue warps per quadrant: whole 4-channel units per warp, one output plane
@@ -1001,6 +1287,14 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
       COT = 32;
     }
   }
+  // pointwise layers: the TS-form kernel over flat pixel tiles (tc1_conv_kernel) wherever the pack carries the image
+  static const bool k1ts_env = !(getenv("ESM_TC_K1TS") && atoi(getenv("ESM_TC_K1TS")) == 0);
+  plan->k1ts = 0;
+  if (k1ts_env && k1 && !d->pixel_shuffle && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0) {
+    const TcImg tk = tc_img_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0);
+    const size_t wb = (size_t)ceil_div(d->Cin, 8) * 2 * COT * 32;
+    if (tk.kind == 2 && tk.COT == COT && tk.taps == 1 && tk.ncot == 1 && wb + 1024 <= 227 * 1024 && tc1_pick(COT)) plan->k1ts = 1;
+  }
   plan->COT = COT;
   plan->taps = taps;
   plan->ncot = ceil_div(d->Cout, COT);
@@ -1018,6 +1312,16 @@ bool tc_conv_plan(const esm_conv_t* d, int num_sms, int npass, TcPlan* plan) {
   const size_t wbytes = plan->khk ? (((size_t)ncg * 3 * 2 * (3 * COT) * 32 + 127) & ~(size_t)127) : (((size_t)ncg * plan->KD * 2 * NB * 32 + 127) & ~(size_t)127);
   const size_t stage = (size_t)CGS * NROW * 8192;
   const size_t limit = 227 * 1024 - 1024;
+  if (plan->k1ts) {
+    const long long items = (long long)d->B * (((long long)d->Dout * d->Hout * d->Wout + 127) / 128);
+    if (items >= (1ll << 30) || (long long)d->Dout * d->Hout * d->Wout >= (1ll << 31)) return false;
+    plan->ncot = 1;
+    plan->nstages = 6;
+    plan->smem = (size_t)ceil_div(d->Cin, 8) * 2 * COT * 32 + 1024;
+    plan->nseg = plan->segw = plan->ysplit = plan->rows = 1;
+    plan->ctas_per_cot = (int)(items < num_sms ? items : num_sms);
+    return true;
+  }
   if (plan->khk == 2) {
     if (wbytes > limit) return false;
     plan->nstages = 2;  // the A ring lives in tensor memory
@@ -1077,8 +1381,10 @@ int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
     // weights itself when there is none (group-wise correlation stem: its 0.5 is folded into the weights)
     static const bool img_env = !(getenv("ESM_TC_WIMG") && atoi(getenv("ESM_TC_WIMG")) == 0);
     const TcImg tk = tc_img_geom(d->Cout, d->Cin, d->kd, d->kh, d->kw, 0);
-    if (img_env && tk.kind == 2 && tk.COT == plan.COT && tk.taps == plan.taps && tk.KD == plan.KD && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0)
+    if ((img_env || plan.k1ts) && tk.kind == 2 && tk.COT == plan.COT && tk.taps == plan.taps && tk.KD == plan.KD &&
+        (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0)
       k.wimg = d->weight + tk.offset;
+    ESM_REQUIRE(!plan.k1ts || k.wimg, "conv(tc): no weight image for the pointwise TS-form kernel");
   }
   k.scale = d->scale;
   k.shift = d->shift;
@@ -1106,7 +1412,7 @@ int tc_conv_launch(const esm_conv_t* d, const TcPlan& plan, cudaStream_t st) {
   k.nstages = plan.nstages;
   k.npass = plan.npass;
   k.ps = d->pixel_shuffle;
-  tc_fn_t fn = plan.khk ? (plan.khk == 2 ? (tc_fn_t)tck_conv_kernel<32, true> : (tc_fn_t)tck_conv_kernel<32, false>) : tc_pick(plan.COT, plan.TZ, plan.KD, plan.gwc != 0, plan.taps, plan.NEW);
+  tc_fn_t fn = plan.k1ts ? tc1_pick(plan.COT) : plan.khk ? (plan.khk == 2 ? (tc_fn_t)tck_conv_kernel<32, true> : (tc_fn_t)tck_conv_kernel<32, false>) : tc_pick(plan.COT, plan.TZ, plan.KD, plan.gwc != 0, plan.taps, plan.NEW);
   ESM_REQUIRE(fn, "conv(tc): no kernel for COT=%d TZ=%d KD=%d", plan.COT, plan.TZ, plan.KD);
   // one limit for every launch of a function: the attribute is per function, not per launch, and graph
   // replays (and profilers re-launching graph nodes) must find it at least as large as any node's request

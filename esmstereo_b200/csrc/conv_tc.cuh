@@ -18,7 +18,8 @@ struct TcPlan {
   int ctas_per_cot;  // persistent CTAs per channel tile
   int npass;         // 3: split-TF32 (fp32-grade), 1: single-pass TF32
   int NEW;           // epilogue warps: 8 (two per TMEM lane quadrant) or 16
-  int khk;           // 2D k3, Cout % 32 == 0: kh in K, kw in N, 32 channels per CTA (tck_conv_kernel)
+  int khk;           // 2D k3, Cout % 32 == 0: kh in K, kw in N, 32 channels per CTA (tck_conv_kernel; 2 = A in tensor memory)
+  int k1ts;          // pointwise: TS-form kernel over flat pixel tiles (tc1_conv_kernel)
   size_t smem;
 };
 
