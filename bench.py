@@ -218,20 +218,27 @@ class ClockSampler:
 # per-kernel roofline measurements (CUDA events on the launching stream, L2 flushed between launches)
 # ----------------------------------------------------------------------------------------------
 def time_kernel(fn, flush, iters=20, warm=3):
+    """Median device time of one invocation of `fn` with a cold L2 (CUDA events around a graph replay: an op that is
+    several launches -- layout conversion + conv -- would otherwise include the host's launch latency between them)."""
     import torch
     for _ in range(warm):
         fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    g.replay()
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
         flush.zero_()  # 256 MiB write: evicts the 126 MB L2
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        g.replay()
         e1.record()
         e1.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e-3)
-    return sum(ts) / len(ts)
+    return statistics.median(ts)
 
 
 def kernel_rooflines(model, peaks, cfg):
