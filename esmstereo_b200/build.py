@@ -35,14 +35,17 @@ def _stale(target, deps):
 def build(force: bool = False, verbose: bool = True) -> str:
     nvcc = _nvcc()
     prof = os.environ.get("ESM_TC_PROFILE") == "1"  # diagnostics build: its own objects and library, next to the product's
-    objdir = os.path.join(CSRC, "build_prof" if prof else "build")
-    LIB = os.path.join(CSRC, "libesm_b200_prof.so" if prof else "libesm_b200.so")
+    ab = os.environ.get("ESM_AB_DEFS", "").split()  # A/B build: extra -D flags, its own objects and library (load it with ESM_LIB)
+    tag = os.environ.get("ESM_AB_TAG", "ab")
+    objdir = os.path.join(CSRC, "build_prof" if prof else "build_" + tag if ab else "build")
+    LIB = os.path.join(CSRC, "libesm_b200_prof.so" if prof else "libesm_b200_%s.so" % tag if ab else "libesm_b200.so")
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "conv_kernel.cuh"), os.path.join(CSRC, "conv_tc.cuh"), os.path.join(CSRC, "tc_common.cuh"),
                os.path.join(os.path.dirname(os.path.dirname(CSRC)), "include", "esm_b200.h")]
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     if os.environ.get("ESM_TC_PROFILE") == "1":  # role timers of the tcgen05 conv kernel (conv_tc.cu), diagnostics only
         flags = flags + ["-DTC_PROFILE"]
+    flags = flags + ab
 
     # objects built with other flags (e.g. the ESM_TC_PROFILE role timers) are stale too
     stamp = os.path.join(objdir, "flags.txt")

@@ -20,6 +20,9 @@ static __device__ __noinline__ void tc_deadlock(int tag, uint32_t parity) {
     printf("esm tc_conv: deadlock in block %d warp %d waiting on barrier %d parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), tag, parity);
   __trap();
 }
+#ifndef TC_WAIT_HINT_NS
+#define TC_WAIT_HINT_NS 0  // mbarrier.try_wait suspend-time hint in ns (0: the system default, measured ~100 clk per poll)
+#endif
 #ifdef TC_PROFILE
 // role profiler (build with ESM_TC_PROFILE=1): cycles block 0's warps spend in each class of mbarrier wait
 static __device__ unsigned long long tc_prof_wait[32][8];
@@ -31,11 +34,21 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity, int
   const uint32_t addr = tc_smem_u32(bar);
   uint32_t done, polls = 0;
   do {
+#if TC_WAIT_HINT_NS > 0
+    // suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead of
+    // re-polling every ~100 clk -- the polls of the idle roles were half of the instructions these kernels issued
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(addr), "r"(parity), "r"((uint32_t)TC_WAIT_HINT_NS)
+                 : "memory");
+    if (!done && ++polls > (2000000000u / (uint32_t)TC_WAIT_HINT_NS)) tc_deadlock(tag, parity);
+#else
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(done)
                  : "r"(addr), "r"(parity)
                  : "memory");
     if (!done && ++polls > (1u << 23)) tc_deadlock(tag, parity);
+#endif
   } while (!done);
 #ifdef TC_PROFILE
   if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) tc_prof_wait[threadIdx.x >> 5][tag / 100] += (unsigned long long)(clock64() - t_begin);
