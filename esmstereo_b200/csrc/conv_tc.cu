@@ -297,7 +297,14 @@ __global__ void __launch_bounds__(tc_threads(NEW), 1) tc_conv_kernel(const __gri
           *reinterpret_cast<float4*>(sb + j * ROW_BYTES + 4096) = lo;
         }
       }
+      // The proxy fence that makes these generic-proxy stores visible to the MMA sits on the CONSUMER side of the
+      // release (arrive below) / acquire (the issuer's wait on `full`) chain: here it compiles to MEMBAR.ALL.CTA +
+      // FENCE.VIEW.ASYNC, and the MEMBAR waited for the loads of the next stage already in flight -- one exposed
+      // load latency per stage.  -DTC_FENCE_WRITER restores the writer-side fence (A/B: 1.970 -> 1.924 ms per KITTI pair
+      // on one box, 1.965 -> 1.952 on another; tests/test_gpu_ops.py::test_tensor_core_resident_engine_is_race_free).
+#ifdef TC_FENCE_WRITER
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
+#endif
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(&full[st]);
       if (++st == (uint32_t)NS) {
@@ -349,6 +356,12 @@ __global__ void __launch_bounds__(tc_threads(NEW), 1) tc_conv_kernel(const __gri
           const uint32_t d = tmem_u + ab * ACC_COLS + zo * NB;
           for (int cgb = 0; cgb < ncg; cgb += CGS) {
             tc_mbar_wait(&full[st], ph, 500 + (int)st);
+#ifndef TC_FENCE_WRITER
+            // generic-proxy stores of the producers (ordered before this point by their release / this acquire) ->
+            // async proxy: the fence lies on the causality path between the stores and the MMAs below; this warp has
+            // no loads in flight, so its MEMBAR is free
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t a_st = a0 + (uint64_t)((st * STAGE_BYTES) >> 4);
             if (leader) {

@@ -398,6 +398,43 @@ def test_gwc_fused_tensor_core(H, W, D, tc_forced):
     assert rel(got, want) < 2e-5
 
 
+@pytest.mark.parametrize("kind", ["gwc_stem", "agg3d", "conv2d_24", "k1_96_32"])
+def test_tensor_core_resident_engine_is_race_free(kind, tc_forced):
+    """The taps-in-N tcgen05 kernel publishes its producers' shared-memory operand tiles to the tensor core with a
+    proxy fence on the CONSUMER side of the mbarrier release / acquire chain (conv_tc.cu: the writer-side fence's
+    MEMBAR waited for the producers' loads in flight).  The kernel has no atomics, so any stale operand read would
+    show as a launch whose output differs from the others: 40 launches at shapes with many ring wrap-arounds must be
+    bit-identical, and agree with the fp32 reference."""
+    ops = _ops()
+    if kind == "gwc_stem":
+        L, R = rnd(1, 64, 48, 156, seed=1), rnd(1, 64, 48, 156, seed=2)
+        p = make_layer(32, 8, 3, 3, seed=3)
+        want = ref_conv(EsmOracle({}, 192).gwc_volume(L, R, 12, 32), p, 1, 1, False, "gelu", 3)
+        args, kw = ([L.cuda(), R.cuda()], gpu_pack(p, 1, 1, False), "gelu"), dict(gwc_disp=12)
+    elif kind == "agg3d":
+        x = rnd(1, 8, 12, 48, 156, seed=4)
+        p = make_layer(8, 8, 3, 3, seed=5)
+        want = ref_conv(x, p, 1, 1, False, "gelu", 3)
+        args, kw = (x.cuda(), gpu_pack(p, 1, 1, False), "gelu"), {}
+    elif kind == "conv2d_24":
+        x = rnd(2, 24, 96, 312, seed=6)
+        p = make_layer(24, 24, 3, 2, seed=7)
+        want = ref_conv(x, p, 1, 1, False, "gelu", 2)
+        args, kw = (x.cuda(), gpu_pack(p, 1, 1, False), "gelu"), {}
+    else:
+        x = rnd(1, 96, 96, 312, seed=8)
+        p = make_layer(96, 32, 1, 2, seed=9)
+        want = ref_conv(x, p, 1, 0, False, "gelu", 2)
+        args, kw = (x.cuda(), gpu_pack(p, 1, 0, False), "gelu"), {}
+    n0 = tc_forced()
+    first = ops.conv(*args, **kw).clone()
+    assert tc_forced() == n0 + 1
+    assert rel(first, want) < 2e-5
+    for i in range(40):
+        again = ops.conv(*args, **kw)
+        assert torch.equal(again, first), "launch %d differs from the first" % i
+
+
 TC_K1_CASES = [
     # name, nd, cin, cout, in_shape, batch
     ("tck1_16_64", 2, 16, 64, (37, 100), 1),
