@@ -1,6 +1,6 @@
 """Tune the conv engine plans once on a B200 and write them to esmstereo_b200/plans/<name>.txt.
 
-    ESM_PLANS=0 ESM_AUTOTUNE=1 python scripts/tune_plans.py [out.txt]
+    ESM_PLANS=0 ESM_AUTOTUNE=1 python scripts/tune_plans.py [out.txt] [--only 0,3]     # --only: indices into RUNS
 
 Every configuration the repo ships a measurement or a test for is run once in eager mode (each new layer shape is then
 timed on the device by esm_conv_f32: FP32-pipe tilings, resident / streamed tcgen05, pointwise), and the chosen engine
@@ -40,8 +40,14 @@ RUNS = [
 
 
 def main():
-    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(_lib.PLANS_DIR, "b200.txt")
-    for name, gwc, backbone, cv, B, H, W in RUNS:
+    argv = list(sys.argv[1:])
+    runs = RUNS
+    if "--only" in argv:
+        i = argv.index("--only")
+        runs = [RUNS[int(t)] for t in argv[i + 1].split(",")]
+        del argv[i:i + 2]
+    out = argv[0] if argv else os.path.join(_lib.PLANS_DIR, "b200.txt")
+    for name, gwc, backbone, cv, B, H, W in runs:
         with contextlib.redirect_stdout(io.StringIO()):
             m = __models__[name](192, gwc, not gwc, backbone, cv)
         m.load_state_dict(fill_deterministic(m.state_dict()))
