@@ -13,13 +13,21 @@ __device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
-// Spin on an mbarrier phase.  A watchdog turns a pipeline deadlock (a bug) into a trapped launch with a
-// message instead of a hung GPU: 2^23 failed polls is seconds, far beyond any legitimate wait here.
+// Wait on an mbarrier phase.  A watchdog turns a pipeline deadlock (a bug) into a trapped launch ("unspecified launch
+// failure") instead of a hung GPU: ~2 s of failed polls, far beyond any legitimate wait here.
+#ifndef TC_DEADLOCK_PRINTF
+// The watchdog traps without a message: a printf here is an ABI call (vprintf) inside every wait loop, and a kernel that
+// contains one is register-allocated around it -- A/B of two builds: 1.952 -> 1.916 ms per KITTI pair without the call
+// (and ptxas held the regions of a setmaxnreg experiment to the smallest budget of the kernel).  -DTC_DEADLOCK_PRINTF
+// (ESM_AB_DEFS, esmstereo_b200/build.py) brings the message back for debugging a pipeline.
+static __device__ __forceinline__ void tc_deadlock(int, uint32_t) { __trap(); }
+#else
 static __device__ __noinline__ void tc_deadlock(int tag, uint32_t parity) {
   if ((threadIdx.x & 31) == 0)
     printf("esm tc_conv: deadlock in block %d warp %d waiting on barrier %d parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), tag, parity);
   __trap();
 }
+#endif
 #ifndef TC_WAIT_HINT_NS
 #define TC_WAIT_HINT_NS 20000  // mbarrier.try_wait suspend-time hint in ns (0: the system default, measured ~100 clk per poll; A/B: 1.9723 -> 1.9633 ms per KITTI pair)
 #endif
