@@ -74,11 +74,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   const unsigned addr = smem_u32(bar);
   unsigned done;
   do {
+#ifdef CONV_WAIT_HINT_NS
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"((unsigned)CONV_WAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+#endif
   } while (!done);
 }
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, int x0, int x1, int x2, int x3, int x4,

@@ -965,7 +965,6 @@ __global__ void __launch_bounds__(tc_threads(8), 1) tc1_conv_kernel(const __grid
   const int npix = p.D * p.H * p.W;             // pixels of one batch item
   const int tiles = (npix + 127) >> 7;
   const int items = p.B * tiles;
-  const int SPI = (ncg + CGS - 1) / CGS;        // ring stages per item
 
   if (tid == 0) {
     for (int i = 0; i < NSA; ++i) {
