@@ -25,6 +25,26 @@ def test_library_exports_every_declared_symbol():
     assert handle.esm_version() >= 100
 
 
+def test_shipped_library_sass_has_tcgen05_and_no_abi_printf():
+    """The product library is sm_100a code that really uses the Blackwell paths (tcgen05.mma = UTCHMMA, tensor-memory
+    loads / stores, TMA bulk copies), and no kernel carries a device printf: a vprintf ABI call inside the mbarrier wait
+    loops cost the whole forward 1.9 % (-DTC_DEADLOCK_PRINTF builds are for debugging only)."""
+    import shutil
+    import subprocess
+    from esmstereo_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    if os.environ.get("ESM_LIB"):
+        pytest.skip("an A/B build is loaded")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass
+    for op in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "NANOSLEEP.SYNCS"):
+        assert op in sass, "no %s in the shipped library" % op
+    assert "vprintf" not in sass, "a device printf (ABI call) is compiled into the shipped kernels"
+    assert "CALL.ABS" not in sass, "an ABI call is compiled into the shipped kernels"
+
+
 def test_argument_errors_need_no_gpu():
     from esmstereo_b200 import _lib
     L = _lib.lib()
